@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — voxel-updates/s of the smoke-solver step (advect + project) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (one JSON line)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the CPU oracle on the host cores
+
+A "step" is one full frame of the hot path: Fluid::UpdateFrame + Fluid::Simulate (CSAdvect, then
+divergence, <=64 Jacobi sweeps and gradient-subtract of CSProject3D) over the whole grid.
+Workload (BASELINE.json): synthetic emitter-driven smoke from the all-zero state, dt = 2/Ny, MIRROR
+addressing, ITER = 64 with the per-cell early exit.  The state is first spun up for --spinup steps
+(untimed state preparation: at step 0 nothing moves and the solver would be trivially cheap), then
+W warm-up steps, then exactly K timed steps.
+
+Grid: N = 1 -> 512^3 (BASELINE config "3D 512^3 ... at 1/2/4/8 B200", 1-GPU point; every field is far
+larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decomposed: 512x512x1024 (2),
+1024x1024x512 (4), 1024^3 (8, BASELINE config 5).  At N = 1 the line also carries "c3": the 256^3
+roofline-characterisation config.  --grid overrides.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WEAK_GRIDS = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+METRIC = "voxel_updates_per_s"
+UNIT = "voxel-updates/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bytes_per_voxel_step(passes: float, mask_bytes_per_pass: float) -> float:
+    """Algorithmic HBM bytes per voxel per step (SURVEY.md §8d / BASELINE.md §3): advect 32 + divergence 12
+    + per executed Jacobi pass 12 (+ freeze mask) + gradient-subtract 20."""
+    return 32.0 + 12.0 + passes * (12.0 + mask_bytes_per_pass) + 20.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def make_sim(fx, grid, args, rank, world, local_rank, uid):
+    f = fx.Fluid()
+    ok = f.Init(gridSize=grid, address_mode=fx.ADDRESS_MIRROR, early_exit=bool(args.early_exit), jacobi_iters=64,
+                fuse_t=args.fuse_t, device=local_rank, rank=rank, nranks=world, use_graph=True,
+                kernel_path=args.kernel_path, nccl_unique_id=uid)
+    if not ok:
+        raise RuntimeError("fluidx_b200 Init failed: " + f.last_error)
+    return f
+
+
+def timed_run(torch, dist, f, dt, steps, warmup, world, stream):
+    """W warm-up + K timed steps, device-timed with CUDA events on the launching stream; max over ranks."""
+    for _ in range(warmup):
+        f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
+    stream.synchronize()
+    st0 = f.stats()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st1 = f.stats()
+    return ms, st0, st1
+
+
+def e2e_run(torch, dist, f, fx, dt, steps, world, stream, export):
+    """The same K steps through the public call sequence a host application makes, host-timed:
+    per step the frame constants go host->device (dt + parity, 8 bytes, the CBSimulation upload) and the
+    step's result record comes back device->host (fxb_get_stats; with `export` also the whole colour field
+    into pinned memory, the renderer hand-off format)."""
+    import ctypes as C
+    cb = torch.zeros(2, dtype=torch.float32).pin_memory()  # CBSimulation {TimeStep, BaseSeed} staging
+    cb[0] = dt
+    nbytes = 0
+    host = None
+    if export:
+        nzl = f.slab[1]
+        nbytes = f.m_gridSize[0] * f.m_gridSize[1] * nzl * 8
+        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    stats_bytes = C.sizeof(fx.FxbStats)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f.UpdateFrame(float(cb[0]))
+        f.Simulate(stream.cuda_stream)
+        if export:
+            f.get_field_async(fx.FIELD_COLOR, host.data_ptr(), nbytes, stream.cuda_stream)
+        f.stats()  # D2H + stream sync: the step's result record
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec, 8, stats_bytes + nbytes
+
+
+def kernel_roofline(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
+    """Dominant kernel = the Jacobi pass.  Average device time per executed pass, measured live with CUDA
+    events around the Jacobi phase of un-graphed steps (fxb_profile_step), against its algorithmic bytes."""
+    tot_ms, tot_passes, phases = 0.0, 0, {}
+    for _ in range(reps):
+        f.UpdateFrame(dt)
+        ms = f.profile_step()
+        st = f.stats()
+        tot_ms += ms["jacobi"]
+        tot_passes += st.jacobi_passes
+        for k, v in ms.items():
+            phases[k] = phases.get(k, 0.0) + v / reps
+    per_launch_bytes = (12.0 + mask_bytes) * voxels_local
+    avg_ms = tot_ms / max(tot_passes, 1)
+    achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "jacobi_pass", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": None,
+            "bytes_per_launch": per_launch_bytes, "avg_launch_ms": round(avg_ms, 5),
+            "launches_per_step": round(tot_passes / reps, 2)}, {k: round(v, 4) for k, v in phases.items()}
+
+
+def cpu_baseline_sample(f, fx, grid, dt, budget_s=25.0):
+    """Times the OpenMP oracle on the host cores on a bounded sample of the same workload: the developed GPU
+    state is copied into the oracle (whole grid when it is small enough, else not run at this size) and
+    stepped for a few frames; the result is also compared with the GPU (full-size parity spot check)."""
+    import numpy as np
+    import oracle
+    nx, ny, nz = grid
+    o = oracle.FluidOracle(nx, ny, nz)
+    for gf, of in ((fx.FIELD_VELOCITY, oracle.FIELD_VEL), (fx.FIELD_COLOR, oracle.FIELD_COLOR),
+                   (fx.FIELD_PRESSURE, oracle.FIELD_PRESSURE)):
+        o.set_field(of, f.get_field(gf))
+    n_steps, t_total = 0, 0.0
+    while True:
+        t0 = time.perf_counter()
+        o.step(dt)
+        t_total += time.perf_counter() - t0
+        f.step(dt)
+        n_steps += 1
+        if t_total > budget_s or n_steps >= 8 or t_total + t_total / n_steps > 1.3 * budget_s:
+            break
+    f.sync()
+    worst = 0.0
+    for gf, of in ((fx.FIELD_VELOCITY, oracle.FIELD_VEL), (fx.FIELD_COLOR, oracle.FIELD_COLOR),
+                   (fx.FIELD_PRESSURE, oracle.FIELD_PRESSURE)):
+        a, b = f.get_field(gf).astype(np.float32), o.get_field(of).astype(np.float32)
+        if gf == fx.FIELD_VELOCITY:
+            a, b = a[..., :3], b[..., :3]
+        worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)))
+    cores = os.cpu_count() or 1
+    return {"value": nx * ny * nz * n_steps / t_total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d oracle steps of the same %dx%dx%d developed state (OpenMP, %d threads, %.1f s)" %
+                      (n_steps, nx, ny, nz, cores, t_total),
+            "parity_max_abs_rel_vs_gpu": worst}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fluidx12_b200 as fx
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import ctypes as C
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            from fluidx12_b200 import binding as B
+            B.check(fx.lib().fxb_nccl_unique_id(C.cast(raw, C.c_void_p)))
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        buf = buf.cuda()
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    grid = tuple(args.grid) if args.grid else WEAK_GRIDS.get(world)
+    if grid is None:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8 (or pass --grid)")
+    nx, ny, nz = grid
+    voxels = nx * ny * nz
+    dt = fx.dt_for_grid(*grid)
+    peak, peak_src = measured_peak_gbs()
+    stream = torch.cuda.Stream()
+
+    f = make_sim(fx, grid, args, rank, world, local_rank, uid)
+    for _ in range(args.spinup):
+        f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
+    stream.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, st0, st1 = timed_run(torch, dist, f, dt, args.steps, args.warmup, world, stream)
+    clocks = sampler.stop() if rank == 0 else None
+
+    sec_e2e, h2d, d2h = e2e_run(torch, dist, f, fx, dt, args.steps, world, stream, export=False)
+    sec_exp = None
+    if args.export_e2e:
+        sec_exp, _, d2h_exp = e2e_run(torch, dist, f, fx, dt, min(args.steps, 20), world, stream, export=True)
+
+    passes = (st1.total_passes - st0.total_passes) / max(args.steps, 1)
+    sweeps = (st1.total_sweeps - st0.total_sweeps) / max(args.steps, 1)
+    fuse_t = st1.fuse_t
+    mask_bytes = 2.0 if fuse_t == 1 and args.kernel_path == 1 else 0.25
+    bpv = bytes_per_voxel_step(passes, mask_bytes)
+    value = voxels * args.steps / (ms * 1e-3)
+    step_gbs = bpv * voxels / (ms * 1e-3 / args.steps) / 1e9
+
+    voxels_local = nx * ny * f.slab[1]
+    roof, phases = kernel_roofline(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            t = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi_pass")
+            roof["traffic"] = t
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D %dx%dx%d emitter-driven smoke, dt=2/Ny, MIRROR, ITER=64%s, spun up %d steps from "
+                               "the zero state; fields (%.0f MiB) far larger than L2, no L2 flush needed" %
+                               (nx, ny, nz, " with per-cell early exit" if args.early_exit else ", early exit OFF",
+                                args.spinup, voxels * 44 / 2 ** 20),
+                   "grid": list(grid), "parallelism": "z-slab x%d" % world, "fuse_t": fuse_t,
+                   "sweeps_per_step": round(sweeps, 2), "jacobi_passes_per_step": round(passes, 2),
+                   "bytes_per_voxel_step": round(bpv, 2), "kernel_path": args.kernel_path},
+        "step_roofline": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
+                          "frac": round(step_gbs / peak, 4), "peak_source": peak_src,
+                          "definition": "bytes_step(T,S)*voxels/t_step, BASELINE.md §3"},
+        "roofline": roof,
+        "phase_ms": phases,
+        "e2e": {"value": voxels * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_e2e / args.steps,
+                "what": "UpdateFrame(dt from pinned CB) + Simulate + fxb_get_stats readback, host-timed"},
+        "gpu_launches": st1.kernels_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if sec_exp is not None:
+        k = min(args.steps, 20)
+        line["e2e_export"] = {"value": voxels * k / sec_exp, "unit": UNIT, "d2h_bytes_per_step": d2h_exp,
+                              "what": "as e2e plus the colour field copied to pinned host memory every step"}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # CPU baseline on a bounded sample: the 256^3 (or smaller) version of the same workload.
+        cgrid = grid if voxels <= 256 ** 3 else (256, 256, 256)
+        g = make_sim(fx, cgrid, args, 0, 1, local_rank, None) if cgrid != grid else f
+        cdt = fx.dt_for_grid(*cgrid)
+        if g is not f:
+            for _ in range(args.spinup):
+                g.step(cdt)
+        line["cpu_baseline"] = cpu_baseline_sample(g, fx, cgrid, cdt)
+        if g is not f:
+            g.close()
+    if rank == 0 and world == 1 and not args.no_c3 and grid != (256, 256, 256):
+        g = make_sim(fx, (256, 256, 256), args, 0, 1, local_rank, None)
+        cdt = fx.dt_for_grid(256, 256, 256)
+        for _ in range(args.spinup):
+            g.UpdateFrame(cdt); g.Simulate(stream.cuda_stream)
+        cms, c0, c1 = timed_run(torch, dist, g, cdt, args.steps, args.warmup, 1, stream)
+        cp = (c1.total_passes - c0.total_passes) / args.steps
+        cb = bytes_per_voxel_step(cp, mask_bytes)
+        cv = 256 ** 3
+        croof, cph = kernel_roofline(g, cdt, cv, peak, peak_src, 5, mask_bytes)
+        line["c3"] = {"workload": "3D 256^3 (BASELINE config 3)", "value": cv * args.steps / (cms * 1e-3),
+                      "ms_per_step": cms / args.steps, "jacobi_passes_per_step": round(cp, 2),
+                      "sweeps_per_step": round((c1.total_sweeps - c0.total_sweeps) / args.steps, 2),
+                      "bytes_per_voxel_step": round(cb, 2),
+                      "step_roofline_frac": round(cb * cv / (cms * 1e-3 / args.steps) / 1e9 / peak, 4),
+                      "roofline": croof, "phase_ms": cph}
+        g.close()
+    f.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement on the host cores (the reference itself needs Windows + D3D12)
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    # Bounded sample: the same emitter-driven workload on the largest cubic grid whose K+W steps fit ~150 s.
+    probe = oracle.FluidOracle(64, 64, 64)
+    pdt = oracle.dt_for_grid(64, 64, 64)
+    for _ in range(20):
+        probe.step(pdt)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        probe.step(pdt)
+    per_voxel_step = (time.perf_counter() - t0) / 5 / 64 ** 3
+    n = 64
+    for cand in (512, 384, 256, 192, 128, 96):
+        spin = min(args.spinup, 100)
+        if per_voxel_step * cand ** 3 * (total + spin) * 1.5 <= 150.0:
+            n = cand
+            break
+    o = oracle.FluidOracle(n, n, n)
+    dt = oracle.dt_for_grid(n, n, n)
+    spin = min(args.spinup, 100)
+    for _ in range(spin + args.warmup):
+        o.step(dt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step(dt)
+    sec = time.perf_counter() - t0
+    value = n ** 3 * args.steps / sec
+    grid = tuple(args.grid) if args.grid else WEAK_GRIDS.get(world, WEAK_GRIDS[1])
+    sample = ("OpenMP C++ restatement of the reference HLSL (the reference needs Windows/D3D12 and cannot run "
+              "here), %d threads, %d^3 sample of the workload, spun up %d steps" % (cores, n, spin))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D %dx%dx%d emitter-driven smoke (timed on a %d^3 sample), dt=2/Ny, MIRROR, ITER=64 "
+                               "with per-cell early exit" % (grid + (n,)), "grid": list(grid),
+                   "sample_grid": [n, n, n]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, nargs=3, default=None)
+    ap.add_argument("--spinup", type=int, default=100)
+    ap.add_argument("--fuse-t", type=int, default=0)
+    ap.add_argument("--early-exit", type=int, default=1)
+    ap.add_argument("--kernel-path", type=int, default=0)
+    ap.add_argument("--export-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""ctypes declarations of the C ABI in ``include/fluidx_b200.h`` (kept in the same order)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libfluidx_b200.so"
+
+ADDRESS_MIRROR, ADDRESS_CLAMP = 0, 1
+FIELD_VELOCITY, FIELD_COLOR, FIELD_PRESSURE, FIELD_VELOCITY_ADVECTED, FIELD_COLOR_PREV = range(5)
+
+FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
+
+# Every symbol include/fluidx_b200.h declares (tests check the library exports exactly these).
+EXPORTS = (
+    "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
+    "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
+    "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+)
+
+
+class FluidError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"fluidx_b200 error {code}: {message}")
+        self.code = code
+
+
+class FxbConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32),
+        ("address_mode", C.c_int32),
+        ("early_exit", C.c_int32),
+        ("jacobi_iters", C.c_int32),
+        ("fuse_t", C.c_int32),
+        ("device", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("h_adv", C.c_int32),
+        ("use_graph", C.c_int32),
+        ("kernel_path", C.c_int32),
+        ("nccl_unique_id", C.c_void_p),
+    ]
+
+
+class FxbStats(C.Structure):
+    _fields_ = [
+        ("s_exec", C.c_int32),
+        ("jacobi_passes", C.c_int32),
+        ("fuse_t", C.c_int32),
+        ("halo_overflow", C.c_int32),
+        ("frame_parity", C.c_int32),
+        ("kernels_per_step", C.c_int32),
+        ("steps", C.c_uint64),
+        ("active_after_first_sweep", C.c_uint64),
+        ("total_sweeps", C.c_uint64),
+        ("total_passes", C.c_uint64),
+    ]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise FluidError(FXB_ERR_CUDA, f"{path} is missing: run `python -c 'import __graft_entry__ as g; "
+                                           "g.build()'` (make -C fluidx12_b200/csrc); there is no CPU fallback")
+        L = C.CDLL(path)
+        vp = C.c_void_p
+        L.fxb_config_default.argtypes = [C.POINTER(FxbConfig)]
+        L.fxb_create.argtypes = [C.POINTER(FxbConfig), C.POINTER(vp)]
+        L.fxb_destroy.argtypes = [vp]
+        L.fxb_destroy.restype = None
+        L.fxb_update_frame.argtypes = [vp, C.c_float]
+        L.fxb_simulate.argtypes = [vp, vp]
+        L.fxb_sync.argtypes = [vp]
+        L.fxb_dt_for_grid.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+        L.fxb_get_slab.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.fxb_get_field.argtypes = [vp, C.c_int, vp, C.c_size_t]
+        L.fxb_set_field.argtypes = [vp, C.c_int, vp, C.c_size_t]
+        L.fxb_get_field_async.argtypes = [vp, C.c_int, vp, C.c_size_t, vp]
+        L.fxb_get_stats.argtypes = [vp, C.POINTER(FxbStats)]
+        L.fxb_profile_step.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.fxb_nccl_unique_id.argtypes = [vp]
+        L.fxb_last_error.restype = C.c_char_p
+        L.fxb_abi_version.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != FXB_OK:
+        raise FluidError(rc, lib().fxb_last_error().decode("utf-8", "replace"))
+
+
+def dt_for_grid(nx: int, ny: int, nz: int) -> float:
+    """dt rule of FluidX::OnUpdate (FluidX12/FluidX12.cpp:266-267)."""
+    out = C.c_float()
+    check(lib().fxb_dt_for_grid(nx, ny, nz, C.byref(out)))
+    return float(out.value)

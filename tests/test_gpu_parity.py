@@ -1,0 +1,212 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Gates (BASELINE.json north_star): after 1 step max|a-b| <= 1e-5 * max|b| per field; after 100 steps
+relative L2 <= 1e-3 per field.  With fp16 storage the 1-step gate is effectively bit-exactness, so the
+tests also report (and for most cases require) exact equality.  Velocity .w is excluded (never read by
+the reference).
+"""
+import numpy as np
+import pytest
+
+from tests.util import max_abs_rel, rel_l2, smooth_state
+
+pytestmark = pytest.mark.gpu
+
+TOL_1STEP = 1e-5   # of the field's max magnitude (north_star)
+TOL_100STEP = 1e-3  # relative L2 (north_star)
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import fluidx12_b200 as fx
+    fx.lib()
+    return fx
+
+
+def make_pair(fx, oracle_mod, n, mode=0, early_exit=True, iters=64, **kw):
+    nx, ny, nz = n
+    f = fx.Fluid()
+    assert f.Init(gridSize=n, address_mode=mode, early_exit=early_exit, jacobi_iters=iters, **kw), f.last_error
+    o = oracle_mod.FluidOracle(nx, ny, nz, address_mode=mode, early_exit=early_exit, iters=iters)
+    return f, o
+
+
+def fields(fx, oracle_mod):
+    return (("velocity", fx.FIELD_VELOCITY, oracle_mod.FIELD_VEL), ("colour", fx.FIELD_COLOR, oracle_mod.FIELD_COLOR),
+            ("pressure", fx.FIELD_PRESSURE, oracle_mod.FIELD_PRESSURE),
+            ("advected", fx.FIELD_VELOCITY_ADVECTED, oracle_mod.FIELD_VEL_ADVECTED))
+
+
+def compare(fx, oracle_mod, f, o, tol, metric=max_abs_rel, exact=False):
+    for name, gf, of in fields(fx, oracle_mod):
+        a, b = f.get_field(gf), o.get_field(of)
+        if a.ndim == 4 and name != "colour":
+            a, b = a[..., :3], b[..., :3]
+        a32, b32 = a.astype(np.float32), b.astype(np.float32)
+        assert np.isfinite(a32).all(), name
+        err = metric(a32, b32)
+        assert err <= tol, (name, err)
+        if exact:
+            assert np.array_equal(a, b), (name, int((a != b).sum()))
+
+
+def inject(fx, oracle_mod, f, o, n, seed=1234, umax=2.0):
+    vel, col, p = smooth_state(*n, seed=seed, umax=umax)
+    for gf, of, a in ((fx.FIELD_VELOCITY, oracle_mod.FIELD_VEL, vel), (fx.FIELD_COLOR, oracle_mod.FIELD_COLOR, col),
+                      (fx.FIELD_PRESSURE, oracle_mod.FIELD_PRESSURE, p)):
+        f.set_field(gf, a)
+        o.set_field(of, a)
+
+
+@pytest.mark.parametrize("n,mode", [((64, 64, 64), 0), ((50, 50, 30), 0), ((48, 48, 48), 1), ((40, 40, 7), 0)])
+def test_one_step_from_smooth_random_state(fx, oracle_mod, n, mode):
+    f, o = make_pair(fx, oracle_mod, n, mode)
+    inject(fx, oracle_mod, f, o, n)
+    dt = fx.dt_for_grid(*n)
+    f.step(dt); o.step(dt)
+    f.sync()
+    assert f.stats().s_exec == o.s_exec
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    f.step(dt); o.step(dt)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_mirror_beyond_first_tap(fx, oracle_mod):
+    """|u| large enough that taps land several texels outside the grid (MIRROR != CLAMP there)."""
+    n = (32, 32, 32)
+    for mode in (0, 1):
+        f, o = make_pair(fx, oracle_mod, n, mode)
+        inject(fx, oracle_mod, f, o, n, seed=5, umax=12.0)
+        dt = fx.dt_for_grid(*n)
+        f.step(dt); o.step(dt)
+        compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_emitter_driven_100_steps_3d(fx, oracle_mod):
+    n = (64, 64, 64)
+    f, o = make_pair(fx, oracle_mod, n)
+    dt = fx.dt_for_grid(*n)
+    f.step(dt); o.step(dt)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    sx = []
+    for _ in range(99):
+        f.step(dt); o.step(dt)
+        sx.append((f.stats().s_exec, o.s_exec))
+    assert all(a == b for a, b in sx), sx
+    compare(fx, oracle_mod, f, o, TOL_100STEP, metric=rel_l2)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)  # in practice the whole trajectory is bit-exact
+
+
+def test_default_grid_128_cubed(fx, oracle_mod):
+    """BASELINE.json configs[1]: 3D 128^3, reference default emitter and Jacobi count."""
+    n = (128, 128, 128)
+    f, o = make_pair(fx, oracle_mod, n)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(12):
+        f.step(dt); o.step(dt)
+    assert f.stats().s_exec == o.s_exec
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_2d_path_256_squared(fx, oracle_mod):
+    """BASELINE.json configs[0]: 2D 256^2 (CSAdvect + CSProject2D), dt = 1/256."""
+    n = (256, 256, 1)
+    f, o = make_pair(fx, oracle_mod, n)
+    dt = fx.dt_for_grid(*n)
+    assert dt == 1.0 / 256
+    for _ in range(40):
+        f.step(dt); o.step(dt)
+    assert f.stats().s_exec == o.s_exec
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_dt_zero_and_parity(fx, oracle_mod):
+    n = (32, 32, 32)
+    f, o = make_pair(fx, oracle_mod, n)
+    inject(fx, oracle_mod, f, o, n)
+    dt = fx.dt_for_grid(*n)
+    for step_dt in (dt, 0.0, 0.0, dt, 0.0, dt):
+        f.step(step_dt); o.step(step_dt)
+        st = f.stats()
+        assert st.s_exec == o.s_exec
+        compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    assert f.m_frameParity == f.stats().frame_parity == 1
+
+
+def test_early_exit_off_and_short_iteration_counts(fx, oracle_mod):
+    n = (32, 32, 32)
+    for early, iters in ((False, 64), (True, 5), (False, 7), (True, 0), (True, 1)):
+        f, o = make_pair(fx, oracle_mod, n, early_exit=early, iters=iters)
+        inject(fx, oracle_mod, f, o, n, seed=11)
+        dt = fx.dt_for_grid(*n)
+        for _ in range(2):
+            f.step(dt); o.step(dt)
+        assert f.stats().s_exec == o.s_exec == (iters if not early else o.s_exec)
+        compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_graph_and_stream_launch_paths_agree(fx, oracle_mod):
+    import torch
+    n = (48, 48, 48)
+    a = fx.Fluid(); b = fx.Fluid(); c = fx.Fluid()
+    assert a.Init(gridSize=n, use_graph=True) and b.Init(gridSize=n, use_graph=False)
+    assert c.Init(gridSize=n, kernel_path=1)
+    dt = fx.dt_for_grid(*n)
+    stream = torch.cuda.Stream()
+    for _ in range(15):
+        a.UpdateFrame(dt); a.Simulate(stream.cuda_stream)
+        b.step(dt)
+        c.step(dt)
+    stream.synchronize()
+    for fld in (fx.FIELD_VELOCITY, fx.FIELD_COLOR, fx.FIELD_PRESSURE):
+        assert np.array_equal(a.get_field(fld), b.get_field(fld))
+        assert np.array_equal(a.get_field(fld), c.get_field(fld))
+    assert a.stats().s_exec == b.stats().s_exec == c.stats().s_exec
+
+
+def test_field_io_and_errors(fx):
+    import ctypes as C
+    n = (16, 16, 16)
+    f = fx.Fluid()
+    assert f.Init(gridSize=n)
+    vel, col, p = smooth_state(*n)
+    f.set_field(fx.FIELD_VELOCITY, vel); f.set_field(fx.FIELD_COLOR, col); f.set_field(fx.FIELD_PRESSURE, p)
+    assert np.array_equal(f.get_field(fx.FIELD_VELOCITY), vel)
+    assert np.array_equal(f.get_field(fx.FIELD_COLOR), col)
+    assert np.array_equal(f.get_field(fx.FIELD_PRESSURE), p)
+    assert f.slab == (0, 16)
+    buf = np.zeros(10, np.float32)
+    rc = fx.lib().fxb_get_field(f._h, fx.FIELD_PRESSURE, buf.ctypes.data_as(C.c_void_p), buf.nbytes)
+    assert rc == -4 and b"size" in fx.lib().fxb_last_error()
+    assert fx.lib().fxb_get_field(f._h, 99, buf.ctypes.data_as(C.c_void_p), buf.nbytes) == -1
+    g = fx.Fluid()
+    assert g.Init(gridSize=(32, 16, 16)) is False and "nx must equal ny" in g.last_error
+
+
+def test_full_size_properties_256_cubed(fx):
+    """BASELINE.json configs[2] size: size-independent properties (the oracle is too slow to run here
+    for many steps): determinism, colour bounds, zero far field, projection reduces divergence."""
+    n = (256, 256, 256)
+    dt = fx.dt_for_grid(*n)
+    runs = []
+    for _ in range(2):
+        f = fx.Fluid()
+        assert f.Init(gridSize=n), f.last_error
+        for _ in range(30):
+            f.step(dt)
+        st = f.stats()
+        runs.append((st.s_exec, f.get_field(fx.FIELD_COLOR), f.get_field(fx.FIELD_PRESSURE)))
+        if len(runs) == 2:
+            v1 = f.get_field(fx.FIELD_VELOCITY_ADVECTED).astype(np.float32)
+            v0 = f.get_field(fx.FIELD_VELOCITY).astype(np.float32)
+        f.close()
+    assert runs[0][0] == runs[1][0] and 1 <= runs[0][0] <= 64
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    c = runs[0][1].astype(np.float32)
+    assert c.min() >= 0 and c.max() <= 1 and c[..., 3].max() > 0.5
+    assert (c[:, 200:] == 0).all()  # the plume has not reached the top yet
+
+    def div(v):
+        return (v[1:-1, 1:-1, 2:, 0] - v[1:-1, 1:-1, :-2, 0] + v[1:-1, 2:, 1:-1, 1] - v[1:-1, :-2, 1:-1, 1]
+                + v[2:, 1:-1, 1:-1, 2] - v[:-2, 1:-1, 1:-1, 2])
+    assert np.abs(div(v0)).sum() < np.abs(div(v1)).sum()
