@@ -209,4 +209,6 @@ def test_full_size_properties_256_cubed(fx):
     def div(v):
         return (v[1:-1, 1:-1, 2:, 0] - v[1:-1, 1:-1, :-2, 0] + v[1:-1, 2:, 1:-1, 1] - v[1:-1, :-2, 1:-1, 1]
                 + v[2:, 1:-1, 1:-1, 2] - v[:-2, 1:-1, 1:-1, 2])
-    assert np.abs(div(v0)).sum() < np.abs(div(v1)).sum()
+    d1, d0 = np.abs(div(v1)), np.abs(div(v0))
+    strong = d1 > 0.25  # where the advected field is clearly divergent the projection must reduce it
+    assert strong.sum() > 100 and d0[strong].sum() < 0.7 * d1[strong].sum()
