@@ -179,6 +179,10 @@ def e2e_run(torch, dist, f, fx, dt, steps, world, stream, export):
     return sec, 8, stats_bytes + nbytes
 
 
+def voxels_local_of(f):
+    return f.m_gridSize[0] * f.m_gridSize[1] * f.slab[1]
+
+
 def kernel_roofline(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
     """Dominant kernel = the Jacobi pass.  Average device time per executed pass, measured live with CUDA
     events around the Jacobi phase of un-graphed steps (fxb_profile_step), against its algorithmic bytes."""
@@ -290,10 +294,22 @@ def run_ours(args):
     passes = (st1.total_passes - st0.total_passes) / max(args.steps, 1)
     sweeps = (st1.total_sweeps - st0.total_sweeps) / max(args.steps, 1)
     fuse_t = st1.fuse_t
-    mask_bytes = 2.0 if fuse_t == 1 and args.kernel_path == 1 else 0.25
+    mask_bytes = 0.25 if st1.jacobi_fused else 2.0
     bpv = bytes_per_voxel_step(passes, mask_bytes)
     value = voxels * args.steps / (ms * 1e-3)
     step_gbs = bpv * voxels / (ms * 1e-3 / args.steps) / 1e9
+    # bytes of the work actually needed: frozen bricks are skipped (their values are final), so only processed
+    # bricks move p/rhs/mask and copied bricks move p once
+    work = None
+    if st1.jacobi_fused:
+        proc = (st1.bricks_processed - st0.bricks_processed) / args.steps
+        cop = (st1.bricks_copied - st0.bricks_copied) / args.steps
+        jac_bytes = (proc * 12.25 + cop * 8.0) * st1.brick_cells
+        wb = (32.0 + 12.0 + 20.0) * voxels_local_of(f) + jac_bytes
+        work = {"bricks_per_pass": st1.bricks_per_pass, "bricks_processed_per_step": round(proc, 1),
+                "bricks_copied_per_step": round(cop, 1), "brick_cells": st1.brick_cells,
+                "bytes_per_step": wb, "achieved_gbs": round(wb / (ms * 1e-3 / args.steps) / 1e9, 1),
+                "frac": round(wb / (ms * 1e-3 / args.steps) / 1e9 / peak, 4)}
 
     voxels_local = nx * ny * f.slab[1]
     roof, phases = kernel_roofline(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
@@ -320,6 +336,7 @@ def run_ours(args):
                           "frac": round(step_gbs / peak, 4), "peak_source": peak_src,
                           "definition": "bytes_step(T,S)*voxels/t_step, BASELINE.md §3"},
         "roofline": roof,
+        "work_roofline": work,
         "phase_ms": phases,
         "e2e": {"value": voxels * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_e2e / args.steps,

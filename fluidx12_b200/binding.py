@@ -55,6 +55,12 @@ class FxbStats(C.Structure):
         ("active_after_first_sweep", C.c_uint64),
         ("total_sweeps", C.c_uint64),
         ("total_passes", C.c_uint64),
+        ("bricks_processed", C.c_uint64),
+        ("bricks_copied", C.c_uint64),
+        ("brick_cells", C.c_uint64),
+        ("bricks_per_pass", C.c_uint64),
+        ("jacobi_fused", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

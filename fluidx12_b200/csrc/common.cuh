@@ -37,6 +37,8 @@ struct StepState {
     int halo_overflow;                   // sticky
     unsigned long long total_sweeps;     // cumulative over all steps
     unsigned long long total_passes;
+    unsigned long long bricks_processed;  // cumulative: bricks fully relaxed by fused passes
+    unsigned long long bricks_copied;     // cumulative: frozen bricks copied once to the other buffer
     unsigned long long active_after[128];  // [k] = cells still active after sweep k (this rank)
 };
 

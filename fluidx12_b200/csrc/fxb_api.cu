@@ -57,6 +57,8 @@ struct fxb_sim {
     float* p[2] = {nullptr, nullptr};   // m_incompress (Fluid.h:93), R32F, ping-pong
     float* rhs = nullptr;               // -0.5 * (2*divergence)
     unsigned char* active = nullptr;    // per-cell freeze flags of the simple path
+    bool fused = false;                 // tuned Jacobi path in use
+    fxb::FusedJacobi jac;
     float* emitter_basis = nullptr;
     fxb::Emitter emitter{};
     fxb::FrameParams* d_frame = nullptr;
@@ -136,11 +138,20 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             launches = 2;
             break;
         case PH_JACOBI:
-            for (int k = 0; k < s->cfg.jacobi_iters; ++k)
-                fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
-                                                s->cfg.early_exit, st);
-            fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, st);
-            launches = s->cfg.jacobi_iters + 1;
+            if (s->fused) {
+                const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
+                for (int k = 0; k < npass; ++k)
+                    fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
+                                                  s->cfg.early_exit, st);
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t, st);
+                launches = npass + 1;
+            } else {
+                for (int k = 0; k < s->cfg.jacobi_iters; ++k)
+                    fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
+                                                    s->cfg.early_exit, st);
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, st);
+                launches = s->cfg.jacobi_iters + 1;
+            }
             break;
         case PH_GRADIENT:
             // Fluid.cpp:378-408: vel[1] -> vel[0]
@@ -281,11 +292,31 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
 
     int rc = build_emitter(s);
     if (rc != FXB_OK) return cleanup_fail(rc);
+    if (cfg->fuse_t < 0 || cfg->fuse_t > 4) return cleanup_fail(fail(FXB_ERR_INVALID, "fxb_create: fuse_t must be 0..4"));
+    if (s->cfg.kernel_path == 0 && fxb::fused_jacobi_supported(s->dom) && s->cfg.jacobi_iters > 0) {
+        // Tuned path: T sweeps fused per HBM pass.  Grids whose nx is not a multiple of 8 (e.g. the 150^3 of
+        // Bin/FluidGI.bat) and the 2D path use the one-sweep-per-launch kernels instead.
+        s->fuse_t = cfg->fuse_t ? cfg->fuse_t : 4;
+        const size_t mask_bytes = n / 8;
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaMalloc((void**)&s->jac.mask[i], mask_bytes);
+            if (e == cudaSuccess) e = cudaMemset(s->jac.mask[i], 0, mask_bytes);
+        }
+        if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, s->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
+            return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
+        const size_t nb = fxb::fused_jacobi_bricks(s->jac);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.brick_state, nb * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(s->jac.brick_state, 0, nb * sizeof(int));
+        if (e != cudaSuccess)
+            return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
+        s->fused = true;
+    }
     if (s->cfg.use_graph) {
         rc = capture_graph(s);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
-        s->kernels_per_step = 1 + 1 + 2 + s->cfg.jacobi_iters + 1 + 1;
+        const int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
+        s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
     }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess)
@@ -307,6 +338,9 @@ void fxb_destroy(fxb_sim* s) {
     }
     cudaFree(s->rhs);
     cudaFree(s->active);
+    cudaFree(s->jac.mask[0]);
+    cudaFree(s->jac.mask[1]);
+    cudaFree(s->jac.brick_state);
     cudaFree(s->emitter_basis);
     cudaFree(s->d_frame);
     cudaFree(s->d_state);
@@ -408,6 +442,13 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
     out->active_after_first_sweep = st.active_after[0];
     out->total_sweeps = st.total_sweeps;
     out->total_passes = st.total_passes;
+    out->bricks_processed = st.bricks_processed;
+    out->bricks_copied = st.bricks_copied;
+    out->jacobi_fused = s->fused ? 1 : 0;
+    if (s->fused) {
+        out->brick_cells = (uint64_t)120 * (32 - 2 * s->fuse_t) * s->jac.bz;
+        out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
+    }
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
 }
 

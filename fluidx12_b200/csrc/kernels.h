@@ -21,4 +21,21 @@ void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,
                      void* vel_out, const StepState* state, cudaStream_t stream);
 
+// jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
+struct FusedJacobi {
+    int T = 0;                 // sweeps fused per pass (1..4)
+    int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
+    float* p[2] = {nullptr, nullptr};
+    float* rhs = nullptr;
+    unsigned char* mask[2] = {nullptr, nullptr};  // bit-packed freeze flags, ping-pong by pass parity
+    int* brick_state = nullptr;                   // 0 active, 1 frozen (copy pending), 2 frozen in both buffers
+    alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
+    alignas(64) unsigned char map_rhs[128];
+};
+bool fused_jacobi_supported(const Domain& d);
+int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
+size_t fused_jacobi_bricks(const FusedJacobi& J);
+cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                     int pass, int iters, int early_exit, cudaStream_t stream);
+
 }  // namespace fxb

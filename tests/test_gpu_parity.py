@@ -145,6 +145,45 @@ def test_early_exit_off_and_short_iteration_counts(fx, oracle_mod):
         compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
 
 
+@pytest.mark.parametrize("fuse_t", [1, 2, 3, 4])
+@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3)])
+def test_fused_jacobi_every_T_and_ragged_tiles(fx, oracle_mod, n, fuse_t):
+    """The fused pass (TMA-staged tile, register z queue, brick skipping) against the oracle for every fusion
+    depth, on grids that are not multiples of the 120 x (32-2T) x bz brick and thinner than a brick."""
+    f, o = make_pair(fx, oracle_mod, n, fuse_t=fuse_t)
+    assert f.stats().jacobi_fused == 1 and f.stats().fuse_t == fuse_t
+    inject(fx, oracle_mod, f, o, n, seed=21)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(3):
+        f.step(dt); o.step(dt)
+        assert f.stats().s_exec == o.s_exec
+        compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+@pytest.mark.parametrize("early,iters", [(False, 64), (False, 7), (True, 5), (True, 1), (True, 64)])
+def test_fused_jacobi_partial_last_pass_and_no_early_exit(fx, oracle_mod, early, iters):
+    n = (72, 72, 40)
+    f, o = make_pair(fx, oracle_mod, n, early_exit=early, iters=iters, fuse_t=4)
+    inject(fx, oracle_mod, f, o, n, seed=4)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(2):
+        f.step(dt); o.step(dt)
+    st = f.stats()
+    assert st.s_exec == o.s_exec and st.jacobi_passes == -(-o.s_exec // 4)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
+def test_unsupported_width_falls_back_to_per_sweep_kernels(fx, oracle_mod):
+    """nx not a multiple of 8 (e.g. the 150^3 of Bin/FluidGI.bat): still CUDA, one sweep per launch."""
+    n = (30, 30, 30)
+    f, o = make_pair(fx, oracle_mod, n)
+    assert f.stats().jacobi_fused == 0
+    dt = fx.dt_for_grid(*n)
+    for _ in range(3):
+        f.step(dt); o.step(dt)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
 def test_graph_and_stream_launch_paths_agree(fx, oracle_mod):
     import torch
     n = (48, 48, 48)
