@@ -2,11 +2,16 @@
 //
 // Replaces FluidX12/Content/Shaders/CSAdvect.hlsl:41-79 (dispatch Fluid.cpp:374).  Operation order
 // follows the shipped DXBC; the two hardware SampleLevel fetches become 16
-// gathered 8-byte texel loads with fp32 weights (no texture unit, no 8-bit weights).
+// gathered 8-byte texel loads blended with fp32 weights (no texture unit, no 8-bit weights).
 //
 // Mapping: one thread per voxel, CTA = 32 x 4 x 4 voxels so that the 33 x 5 x 5 tap footprint of a
-// CTA is shared through L1 (the back-trace is spatially coherent).  Algorithmic traffic: 32 B/voxel
-// (velocity in 8 + colour in 8 + velocity out 8 + colour out 8); HBM-bound.
+// CTA is shared through L1 (the back-trace is spatially coherent).  The kernel is bounded by
+// instruction issue before HBM, so the hot path is kept lean:
+//   * (i + 0.5) / N comes from per-axis tables (three IEEE divisions per voxel otherwise);
+//   * taps that all fall inside the grid (the common case) take a fast path with 32-bit offsets and no
+//     sampler-addressing arithmetic; MIRROR/CLAMP wrapping lives in a cold out-of-line path;
+//   * the 14 lerps of the 7 used channels run as packed FADD2/FFMA2 on (x,y) and (z,w) pairs.
+// Algorithmic traffic: 32 B/voxel (velocity in 8 + colour in 8 + velocity out 8 + colour out 8).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -14,41 +19,54 @@ namespace fxb {
 
 namespace {
 
-struct Taps {
-    size_t o[8];  // texel offsets of the 8 taps, order (x0|x1) fastest, then y, then z
-    float fx, fy, fz;
+struct Pair4 {  // one RGBA16F texel widened to fp32 as two packed pairs
+    float2 lo, hi;
 };
 
-__device__ __forceinline__ float lerp3(float a000, float a100, float a010, float a110, float a001, float a101,
-                                       float a011, float a111, float fx, float fy, float fz) {
-    const float x00 = __fmaf_rn(fx, a100 - a000, a000);
-    const float x10 = __fmaf_rn(fx, a110 - a010, a010);
-    const float x01 = __fmaf_rn(fx, a101 - a001, a001);
-    const float x11 = __fmaf_rn(fx, a111 - a011, a011);
-    const float y0 = __fmaf_rn(fy, x10 - x00, x00);
-    const float y1 = __fmaf_rn(fy, x11 - x01, x01);
-    return __fmaf_rn(fz, y1 - y0, y0);
+__device__ __forceinline__ Pair4 load_pairs(const uint2* __restrict__ f, unsigned i) {
+    const uint2 r = __ldg(f + i);
+    Pair4 t;
+    t.lo = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    t.hi = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return t;
 }
 
-__device__ __forceinline__ float4 gather4(const uint2* __restrict__ f, const Taps& t) {
-    float4 a[8];
+__device__ __forceinline__ float2 lerp2(float2 f, float2 a, float2 b) { return fma2(f, sub2(b, a), a); }
+
+// x, then y, then z; each lerp is fma(f, b - a, a)
+__device__ __forceinline__ Pair4 gather(const uint2* __restrict__ f, const unsigned (&o)[8], float fx, float fy,
+                                        float fz) {
+    Pair4 t[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = load_texel4(f, t.o[k]);
-    float4 r;
-    r.x = lerp3(a[0].x, a[1].x, a[2].x, a[3].x, a[4].x, a[5].x, a[6].x, a[7].x, t.fx, t.fy, t.fz);
-    r.y = lerp3(a[0].y, a[1].y, a[2].y, a[3].y, a[4].y, a[5].y, a[6].y, a[7].y, t.fx, t.fy, t.fz);
-    r.z = lerp3(a[0].z, a[1].z, a[2].z, a[3].z, a[4].z, a[5].z, a[6].z, a[7].z, t.fx, t.fy, t.fz);
-    r.w = lerp3(a[0].w, a[1].w, a[2].w, a[3].w, a[4].w, a[5].w, a[6].w, a[7].w, t.fx, t.fy, t.fz);
+    for (int k = 0; k < 8; ++k) t[k] = load_pairs(f, o[k]);
+    const float2 wx = make_float2(fx, fx), wy = make_float2(fy, fy), wz = make_float2(fz, fz);
+    Pair4 r;
+    {
+        const float2 x00 = lerp2(wx, t[0].lo, t[1].lo), x10 = lerp2(wx, t[2].lo, t[3].lo);
+        const float2 x01 = lerp2(wx, t[4].lo, t[5].lo), x11 = lerp2(wx, t[6].lo, t[7].lo);
+        r.lo = lerp2(wz, lerp2(wy, x00, x10), lerp2(wy, x01, x11));
+    }
+    {
+        const float2 x00 = lerp2(wx, t[0].hi, t[1].hi), x10 = lerp2(wx, t[2].hi, t[3].hi);
+        const float2 x01 = lerp2(wx, t[4].hi, t[5].hi), x11 = lerp2(wx, t[6].hi, t[7].hi);
+        r.hi = lerp2(wz, lerp2(wy, x00, x10), lerp2(wy, x01, x11));
+    }
     return r;
+}
+
+// Cold path: sampler addressing of one axis when a tap may be outside the grid (or the coordinate is not
+// finite).  Out of line and returned in registers so that the hot path carries none of its cost.
+__device__ __noinline__ int2 wrapped_pair(float t, int w, int clamp_mode) {
+    const int i = floor_to_tap(t);
+    return make_int2(address_tap(i, w, clamp_mode), address_tap(i + 1, w, clamp_mode));
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(512) advect_kernel(Domain d, const FrameParams* __restrict__ frame,
-                                                     const uint2* __restrict__ vel_in,
-                                                     uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
-                                                     uint2* __restrict__ vel_out, Emitter em, int clamp_mode,
-                                                     StepState* __restrict__ state) {
+__global__ void __launch_bounds__(512, 2)
+advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in,
+              uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
+              uint2* __restrict__ vel_out, Emitter em, int clamp_mode, StepState* __restrict__ state) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int z = d.z_own0 + blockIdx.z * 4 + threadIdx.z;  // global plane
@@ -59,43 +77,43 @@ __global__ void __launch_bounds__(512) advect_kernel(Domain d, const FrameParams
     const uint2* __restrict__ col_in = parity ? col0 : col1;  // colour[!parity] (Fluid.cpp:372)
     uint2* __restrict__ col_out = parity ? col1 : col0;       // colour[parity]
 
+    const float px = __ldg(tab.pos[0] + x), py = __ldg(tab.pos[1] + y), pz = __ldg(tab.pos[2] + z);
     const float fnx = (float)d.nx, fny = (float)d.ny, fnz = (float)d.nz;
-    const float px = ((float)x + 0.5f) / fnx;
-    const float py = ((float)y + 0.5f) / fny;
-    const float pz = ((float)z + 0.5f) / fnz;
 
-    const size_t self = ((size_t)(z - d.z_first) * d.ny + y) * d.nx + x;
-    const float4 u0 = load_texel4(vel_in, self);
-    const float ax = __fmaf_rn(-u0.x, dt, px);
-    const float ay = __fmaf_rn(-u0.y, dt, py);
-    const float az = __fmaf_rn(-u0.z, dt, pz);
+    const unsigned self = ((unsigned)(z - d.z_first) * d.ny + y) * d.nx + x;
+    const Pair4 u0 = load_pairs(vel_in, self);
+    const float tx = __fmaf_rn(__fmaf_rn(-u0.lo.x, dt, px), fnx, -0.5f);
+    const float ty = __fmaf_rn(__fmaf_rn(-u0.lo.y, dt, py), fny, -0.5f);
+    const float tz = __fmaf_rn(__fmaf_rn(-u0.hi.x, dt, pz), fnz, -0.5f);
+    const float flx = floorf(tx), fly = floorf(ty), flz = floorf(tz);
+    const float fx = tx - flx, fy = ty - fly, fz = tz - flz;
 
-    Taps t;
-    {
-        const float tx = __fmaf_rn(ax, fnx, -0.5f);
-        const float ty = __fmaf_rn(ay, fny, -0.5f);
-        const float tz = __fmaf_rn(az, fnz, -0.5f);
-        const int ix = floor_to_tap(tx), iy = floor_to_tap(ty), iz = floor_to_tap(tz);
-        t.fx = tx - floorf(tx);
-        t.fy = ty - floorf(ty);
-        t.fz = tz - floorf(tz);
-        const int x0 = address_tap(ix, d.nx, clamp_mode), x1 = address_tap(ix + 1, d.nx, clamp_mode);
-        const int y0 = address_tap(iy, d.ny, clamp_mode), y1 = address_tap(iy + 1, d.ny, clamp_mode);
-        int z0 = address_tap(iz, d.nz, clamp_mode) - d.z_first;
-        int z1 = address_tap(iz + 1, d.nz, clamp_mode) - d.z_first;
-        if ((unsigned)z0 >= (unsigned)d.nz_alloc || (unsigned)z1 >= (unsigned)d.nz_alloc) {
-            // The back-trace left the exchanged halo (multi-GPU only): flag it, keep addresses legal.
-            state->halo_overflow = 1;
-            z0 = min(max(z0, 0), d.nz_alloc - 1);
-            z1 = min(max(z1, 0), d.nz_alloc - 1);
+    unsigned o[8];
+    const float zlo = (float)d.z_first, zhi = (float)(d.z_first + d.nz_alloc - 1);
+    const bool inside = tx >= 0.0f && tx < fnx - 1.0f && ty >= 0.0f && ty < fny - 1.0f && tz >= 0.0f &&
+                        tz < fnz - 1.0f && tz >= zlo && tz < zhi;
+    if (inside) {  // both taps of every axis are inside the grid (and inside the local slab)
+        const unsigned plane = (unsigned)d.nx * d.ny;
+        const unsigned base = ((unsigned)((int)flz - d.z_first) * d.ny + (unsigned)(int)fly) * d.nx + (unsigned)(int)flx;
+        o[0] = base; o[1] = base + 1; o[2] = base + d.nx; o[3] = base + d.nx + 1;
+        o[4] = base + plane; o[5] = o[4] + 1; o[6] = o[4] + d.nx; o[7] = o[6] + 1;
+    } else {
+        const int2 xs = wrapped_pair(tx, d.nx, clamp_mode), ys = wrapped_pair(ty, d.ny, clamp_mode);
+        int2 zs = wrapped_pair(tz, d.nz, clamp_mode);
+        zs.x -= d.z_first;
+        zs.y -= d.z_first;
+        if ((unsigned)zs.x >= (unsigned)d.nz_alloc || (unsigned)zs.y >= (unsigned)d.nz_alloc) {
+            state->halo_overflow = 1;  // the back-trace left the exchanged z-halo (multi-GPU only)
+            zs.x = min(max(zs.x, 0), d.nz_alloc - 1);
+            zs.y = min(max(zs.y, 0), d.nz_alloc - 1);
         }
-        const size_t r00 = ((size_t)z0 * d.ny + y0) * d.nx, r10 = ((size_t)z0 * d.ny + y1) * d.nx;
-        const size_t r01 = ((size_t)z1 * d.ny + y0) * d.nx, r11 = ((size_t)z1 * d.ny + y1) * d.nx;
-        t.o[0] = r00 + x0; t.o[1] = r00 + x1; t.o[2] = r10 + x0; t.o[3] = r10 + x1;
-        t.o[4] = r01 + x0; t.o[5] = r01 + x1; t.o[6] = r11 + x0; t.o[7] = r11 + x1;
+        const unsigned r00 = ((unsigned)zs.x * d.ny + ys.x) * d.nx, r10 = ((unsigned)zs.x * d.ny + ys.y) * d.nx;
+        const unsigned r01 = ((unsigned)zs.y * d.ny + ys.x) * d.nx, r11 = ((unsigned)zs.y * d.ny + ys.y) * d.nx;
+        o[0] = r00 + xs.x; o[1] = r00 + xs.y; o[2] = r10 + xs.x; o[3] = r10 + xs.y;
+        o[4] = r01 + xs.x; o[5] = r01 + xs.y; o[6] = r11 + xs.x; o[7] = r11 + xs.y;
     }
-    float4 u = gather4(vel_in, t);
-    float4 c = gather4(col_in, t);
+    Pair4 u = gather(vel_in, o, fx, fy, fz);
+    Pair4 c = gather(col_in, o, fx, fy, fz);
 
     // Emitter (CSAdvect.hlsl:57-68).  Outside the table's box the basis is below exp(-4) by construction.
     if (x >= em.x0 && x < em.x1 && y >= em.y0 && y < em.y1 && z >= em.z0 && z < em.z1) {
@@ -111,27 +129,32 @@ __global__ void __launch_bounds__(512) advect_kernel(Domain d, const FrameParams
             } else {
                 fx_ = 0.0f; fy_ = basis * 48.0f; fz_ = 0.0f;
             }
-            u.x = __fmaf_rn(fx_, dt, u.x);
-            u.y = __fmaf_rn(fy_, dt, u.y);
-            u.z = __fmaf_rn(fz_, dt, u.z);
+            u.lo.x = __fmaf_rn(fx_, dt, u.lo.x);
+            u.lo.y = __fmaf_rn(fy_, dt, u.lo.y);
+            u.hi.x = __fmaf_rn(fz_, dt, u.hi.x);
             const float bdt = basis * dt;
-            c.x = __saturatef(__fmaf_rn(bdt, 8.0f, c.x));
-            c.y = __saturatef(__fmaf_rn(bdt, 16.0f, c.y));
-            c.z = __saturatef(__fmaf_rn(bdt, 40.0f, c.z));
-            c.w = __saturatef(__fmaf_rn(bdt, 40.0f, c.w));
+            c.lo.x = __saturatef(__fmaf_rn(bdt, 8.0f, c.lo.x));
+            c.lo.y = __saturatef(__fmaf_rn(bdt, 16.0f, c.lo.y));
+            c.hi.x = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.x));
+            c.hi.y = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.y));
         }
     }
 
     const float atten = fmaxf(__fmaf_rn(-dt, 0.200000003f, 1.0f), 0.0f);
-    vel_out[self] = pack_texel4(u.x * atten, u.y * atten, u.z * atten, 0.0f);
-    col_out[self] = pack_texel4(c.x * atten, c.y * atten, c.z * atten, c.w * atten);
+    const float2 at2 = make_float2(atten, atten);
+    u.lo = mul2(u.lo, at2);
+    c.lo = mul2(c.lo, at2);
+    c.hi = mul2(c.hi, at2);
+    vel_out[self] = pack_texel4(u.lo.x, u.lo.y, u.hi.x * atten, 0.0f);
+    col_out[self] = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
 }
 
-void launch_advect(const Domain& d, const FrameParams* frame, const void* vel_in, void* const col[2], void* vel_out,
-                   const Emitter& em, int clamp_mode, StepState* state, cudaStream_t stream) {
+void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
+                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state,
+                   cudaStream_t stream) {
     const dim3 block(32, 4, 4);
     const dim3 grid((d.nx + 31) / 32, (d.ny + 3) / 4, (d.z_own1 - d.z_own0 + 3) / 4);
-    advect_kernel<<<grid, block, 0, stream>>>(d, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
+    advect_kernel<<<grid, block, 0, stream>>>(d, tab, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
                                               (uint2*)vel_out, em, clamp_mode, state);
 }
 

@@ -50,6 +50,22 @@ struct Emitter {
     const float* basis;          // [(z-z0)][(y-y0)][(x-x0)]
 };
 
+// Per-axis tables indexed by the global voxel coordinate, computed once on the host with the shader's own
+// arithmetic: pos = (i + 0.5) / N (a true IEEE division), bp = fma(pos, 2, -1) and
+// wall = clamp((-|bp| + 0.97) * (1/0.03), -1, 1), the soft-wall damping factor of CSProject3D.hlsl:106-108.
+struct AxisTables {
+    const float* pos[3];
+    const float* bp[3];
+    const float* wall[3];
+};
+
+// Packed fp32 (Blackwell FADD2/FMUL2/FFMA2): two IEEE round-to-nearest operations per instruction, bit-identical
+// to the scalar forms.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 __device__ __forceinline__ float4 load_texel4(const uint2* __restrict__ f, size_t i) {
     const uint2 r = __ldg(f + i);
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));

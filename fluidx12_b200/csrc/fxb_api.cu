@@ -60,6 +60,9 @@ struct fxb_sim {
     bool fused = false;                 // tuned Jacobi path in use
     fxb::FusedJacobi jac;
     float* emitter_basis = nullptr;
+    float* axis_tables = nullptr;       // pos / bp / wall per axis, one allocation
+    fxb::AxisTables tab{};
+    bool quad = false;                  // 4-cells-per-thread divergence / gradient kernels in use
     fxb::Emitter emitter{};
     fxb::FrameParams* d_frame = nullptr;
     fxb::StepState* d_state = nullptr;
@@ -119,6 +122,33 @@ int build_emitter(fxb_sim* s) {
     return FXB_OK;
 }
 
+// Per-axis tables (see fxb::AxisTables).  Same arithmetic and operation order as the shaders (App. A.1/A.2).
+int build_axis_tables(fxb_sim* s) {
+    const int n[3] = {s->dom.nx, s->dom.ny, s->dom.nz};
+    const bool is3d = s->dom.nz > 1;
+    size_t off[3], total = 0;
+    for (int a = 0; a < 3; ++a) { off[a] = total; total += ((size_t)n[a] + 3) / 4 * 4; }
+    std::vector<float> host(3 * total, 0.0f);
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < n[a]; ++i) {
+            const float pos = ((float)i + 0.5f) / (float)n[a];
+            const float bp = (a == 2 && !is3d) ? fmaf(pos, 1.0f, 0.0f) : fmaf(pos, 2.0f, -1.0f);
+            float w = (-fabsf(bp) + 0.970000029f) * 33.3333359f;
+            w = fminf(fmaxf(w, -1.0f), 1.0f);
+            host[off[a] + i] = pos;
+            host[total + off[a] + i] = bp;
+            host[2 * total + off[a] + i] = w;
+        }
+    FXB_CUDA(cudaMalloc((void**)&s->axis_tables, host.size() * sizeof(float)));
+    FXB_CUDA(cudaMemcpy(s->axis_tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int a = 0; a < 3; ++a) {
+        s->tab.pos[a] = s->axis_tables + off[a];
+        s->tab.bp[a] = s->axis_tables + total + off[a];
+        s->tab.wall[a] = s->axis_tables + 2 * total + off[a];
+    }
+    return FXB_OK;
+}
+
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 
 // Enqueues one phase of the step; returns the number of kernels launched.
@@ -128,13 +158,14 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
     switch (phase) {
         case PH_ADVECT:
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
-            fxb::launch_advect(d, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
+            fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
                                s->d_state, st);
             launches = 1;
             break;
         case PH_DIVERGENCE:
             fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);
-            fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
+            if (s->quad) fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, st);
+            else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
             launches = 2;
             break;
         case PH_JACOBI:
@@ -155,7 +186,10 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             break;
         case PH_GRADIENT:
             // Fluid.cpp:378-408: vel[1] -> vel[0]
-            fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
+            if (s->quad)
+                fxb::launch_gradient_quad(d, s->tab, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
+            else
+                fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
             launches = 1;
             break;
     }
@@ -240,6 +274,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (cfg->nx == 0 || cfg->ny == 0 || cfg->nz == 0) return fail(FXB_ERR_INVALID, "fxb_create: empty grid");
     if (cfg->nx != cfg->ny) return fail(FXB_ERR_INVALID, "fxb_create: nx must equal ny (Fluid.cpp:201)");
     if (cfg->nx > 4096 || cfg->nz > 4096) return fail(FXB_ERR_INVALID, "fxb_create: grid dimension > 4096");
+    if ((uint64_t)cfg->nx * cfg->ny * cfg->nz >= (1ull << 31))
+        return fail(FXB_ERR_INVALID, "fxb_create: more than 2^31 voxels per device (kernels use 32-bit offsets)");
     if (cfg->jacobi_iters < 0 || cfg->jacobi_iters > 128)
         return fail(FXB_ERR_INVALID, "fxb_create: jacobi_iters must be in [0, 128]");
     if (cfg->address_mode != FXB_ADDRESS_MIRROR && cfg->address_mode != FXB_ADDRESS_CLAMP)
@@ -292,6 +328,9 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
 
     int rc = build_emitter(s);
     if (rc != FXB_OK) return cleanup_fail(rc);
+    rc = build_axis_tables(s);
+    if (rc != FXB_OK) return cleanup_fail(rc);
+    s->quad = s->cfg.kernel_path == 0 && fxb::quad_kernels_supported(s->dom);
     if (cfg->fuse_t < 0 || cfg->fuse_t > 4) return cleanup_fail(fail(FXB_ERR_INVALID, "fxb_create: fuse_t must be 0..4"));
     if (s->cfg.kernel_path == 0 && fxb::fused_jacobi_supported(s->dom) && s->cfg.jacobi_iters > 0) {
         // Tuned path: T sweeps fused per HBM pass.  Grids whose nx is not a multiple of 8 (e.g. the 150^3 of
@@ -342,6 +381,7 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.mask[1]);
     cudaFree(s->jac.brick_state);
     cudaFree(s->emitter_basis);
+    cudaFree(s->axis_tables);
     cudaFree(s->d_frame);
     cudaFree(s->d_state);
     for (int i = 0; i < 8; ++i)

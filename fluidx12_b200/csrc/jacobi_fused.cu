@@ -24,6 +24,8 @@
 // Algorithmic traffic per processed cell per pass: p in 4 + rhs in 4 + p out 4 (+ 2/8 mask) bytes.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,7 +50,7 @@ struct Smem {
     static constexpr int kP0Slots = 3;
     static constexpr int kRhsSlots = T + 1;
     static constexpr int kPlanes = kP0Slots + 2 * (T - 1) + kRhsSlots;
-    static constexpr size_t kBytes = (size_t)kPlanes * kPlane * sizeof(float) + 64 + 128;  // + barriers + alignment slack
+    static constexpr size_t kBytes = (size_t)kPlanes * kPlane * sizeof(float) + 64;  // + barriers and counters
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,36 +94,38 @@ struct PassParams {
     int early_exit;
 };
 
-// One relaxation of a quad (4 x-adjacent cells).  Operation order = the DXBC's:
-// acc = p[L] + rhs; += p[R]; += p[U]; += p[D]; += p[F]; += p[B]; x = acc * (1/6); test |fma(acc, 1/6, -x0)| < 0.001.
+// One relaxation of a quad (4 x-adjacent cells) as two packed pairs.  Operation order = the DXBC's (SURVEY.md
+// App. A.3): acc = p[L] + rhs; += p[R]; += p[U]; += p[D]; += p[F]; += p[B]; x = acc * (1/6);
+// freeze when |fma(acc, 1/6, -x0)| < eps (eps < 0 disables the test: early_exit = 0).
 __device__ __forceinline__ void relax_quad(const float4 c, const float4 lo, const float4 hi, const float4 up,
                                            const float4 dn, const float left, const float right, const float4 rhs,
-                                           const unsigned act, const bool early, float4& out, unsigned& still) {
-    const float cc[4] = {c.x, c.y, c.z, c.w};
-    const float ll[4] = {left, c.x, c.y, c.z};
-    const float rr[4] = {c.y, c.z, c.w, right};
-    const float uu[4] = {up.x, up.y, up.z, up.w};
-    const float dd[4] = {dn.x, dn.y, dn.z, dn.w};
-    const float ff[4] = {lo.x, lo.y, lo.z, lo.w};
-    const float bb[4] = {hi.x, hi.y, hi.z, hi.w};
-    const float bs[4] = {rhs.x, rhs.y, rhs.z, rhs.w};
-    float o[4];
-    unsigned s = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float acc = ll[j] + bs[j];
-        acc = rr[j] + acc;
-        acc = uu[j] + acc;
-        acc = dd[j] + acc;
-        acc = ff[j] + acc;
-        acc = bb[j] + acc;
-        const float nv = acc * kInv6;
-        const bool conv = fabsf(__fmaf_rn(acc, kInv6, -cc[j])) < kEps;
-        const bool a = (act >> j) & 1u;
-        o[j] = a ? nv : cc[j];
-        if (a && !(early && conv)) s |= 1u << j;
-    }
-    out = make_float4(o[0], o[1], o[2], o[3]);
+                                           const unsigned act, const float eps, float4& out, unsigned& still) {
+    const float2 inv2 = make_float2(kInv6, kInv6);
+    const float2 cA = make_float2(c.x, c.y), cB = make_float2(c.z, c.w);
+    const float2 mid = make_float2(c.y, c.z);  // right neighbours of pair A = left neighbours of pair B
+    float2 accA = add2(make_float2(left, c.x), make_float2(rhs.x, rhs.y));
+    float2 accB = add2(mid, make_float2(rhs.z, rhs.w));
+    accA = add2(mid, accA);
+    accB = add2(make_float2(c.w, right), accB);
+    accA = add2(make_float2(up.x, up.y), accA);
+    accB = add2(make_float2(up.z, up.w), accB);
+    accA = add2(make_float2(dn.x, dn.y), accA);
+    accB = add2(make_float2(dn.z, dn.w), accB);
+    accA = add2(make_float2(lo.x, lo.y), accA);
+    accB = add2(make_float2(lo.z, lo.w), accB);
+    accA = add2(make_float2(hi.x, hi.y), accA);
+    accB = add2(make_float2(hi.z, hi.w), accB);
+    const float2 nA = mul2(accA, inv2), nB = mul2(accB, inv2);
+    const float2 dA = fma2(accA, inv2, make_float2(-cA.x, -cA.y)), dB = fma2(accB, inv2, make_float2(-cB.x, -cB.y));
+    unsigned s = act;
+    if (fabsf(dA.x) < eps) s &= ~1u;
+    if (fabsf(dA.y) < eps) s &= ~2u;
+    if (fabsf(dB.x) < eps) s &= ~4u;
+    if (fabsf(dB.y) < eps) s &= ~8u;
+    out.x = (act & 1u) ? nA.x : c.x;
+    out.y = (act & 2u) ? nA.y : c.y;
+    out.z = (act & 4u) ? nB.x : c.z;
+    out.w = (act & 8u) ? nB.y : c.w;
     still = s;
 }
 
@@ -193,13 +197,13 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         }
     }
 
-    extern __shared__ unsigned char smem_raw[];
-    float* sm = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));  // TMA dst: 128 B
+    extern __shared__ __align__(1024) float sm[];                  // TMA destinations need 128-byte alignment
     float* sm_p0 = sm;                                             // [3][kPlane]
     float* sm_lev = sm_p0 + Smem<T>::kP0Slots * kPlane;            // [T-1][2][kPlane]  (levels 1..T-1)
     float* sm_rhs = sm_lev + 2 * (T - 1) * kPlane;                 // [T+1][kPlane]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_rhs + Smem<T>::kRhsSlots * kPlane);
-    __shared__ unsigned s_cnt[T];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_rhs + Smem<T>::kRhsSlots * kPlane);  // [3]
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(bars + 4);                                // [T]
+    if ((smem_u32(sm) & 127u) != 0u) __trap();
 
     if (tid == 0) {
 #pragma unroll
@@ -268,7 +272,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
 
     if (tid == 0) issue_bundle(zl0);
     unsigned next_flags = load_flags(zl0);
-    const bool early = P.early_exit != 0;
+    const float eps = P.early_exit ? kEps : -1.0f;
     const int k_end = ze - 1 + T;
 
     for (int k = zl0; k <= k_end; ++k) {
@@ -322,7 +326,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                         if (clamp_r) right = c.w;
                         const float4 rhs = *reinterpret_cast<const float4*>(rb + off[r]);
                         unsigned st;
-                        relax_quad(c, lo, nw[r], up, dn, left, right, rhs, (act >> (4 * r)) & 0xFu, early, res[r], st);
+                        relax_quad(c, lo, nw[r], up, dn, left, right, rhs, (act >> (4 * r)) & 0xFu, eps, res[r], st);
                         rf |= st << (4 * r);
                     }
                 } else {
@@ -455,6 +459,10 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     J->nty = (d.ny + out_y - 1) / out_y;
     const int nz_out = d.z_own1 - d.z_own0;
     J->bz = nz_out >= 64 ? 32 : (nz_out >= 16 ? 16 : nz_out);
+    if (const char* e = getenv("FXB_BZ")) {  // tuning knob: planes per brick
+        const int v = atoi(e);
+        if (v >= 1 && v <= nz_out) J->bz = v;
+    }
     J->nzc = (nz_out + J->bz - 1) / J->bz;
     J->p[0] = p0; J->p[1] = p1; J->rhs = rhs;
     if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[0]), p0, d.nx, d.ny, d.nz_alloc)) return -1;

@@ -8,8 +8,9 @@
 namespace fxb {
 
 // advect.cu
-void launch_advect(const Domain& d, const FrameParams* frame, const void* vel_in, void* const col[2], void* vel_out,
-                   const Emitter& em, int clamp_mode, StepState* state, cudaStream_t stream);
+void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
+                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state,
+                   cudaStream_t stream);
 
 // project_simple.cu — one kernel per logical pass (cross-check path, kernel_path = 1)
 void launch_begin_step(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
@@ -20,6 +21,14 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
 void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int fuse_t, cudaStream_t stream);
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,
                      void* vel_out, const StepState* state, cudaStream_t stream);
+
+// project_quad.cu — 4 cells per thread (tuned path; 3D grids with nx % 8 == 0)
+bool quad_kernels_supported(const Domain& d);
+void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs,
+                            cudaStream_t stream);
+void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
+                          const float* p0, const float* p1, void* vel_out, const StepState* state,
+                          cudaStream_t stream);
 
 // jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
 struct FusedJacobi {

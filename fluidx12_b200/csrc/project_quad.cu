@@ -1,0 +1,157 @@
+// project_quad.cu — divergence and gradient-subtract of CSProject3D, one thread per 4 x-adjacent cells.
+//
+// Replaces GetDivergence (FluidX12/Content/Shaders/CSProject3D.hlsl:39-50) and Project + the soft-wall
+// damping (CSProject3D.hlsl:55-63, :106-112) for 3D grids whose width is a multiple of 8; other grids use
+// the one-thread-per-voxel kernels of project_simple.cu.  Both kernels are pure streaming stencils:
+// 128-bit loads of whole quads, clamp-to-edge neighbours by index (CSProject3D.hlsl:76-83), per-axis
+// tables instead of per-voxel divisions, 32-bit offsets.  Operation order as in SURVEY.md App. A.2.
+// Algorithmic traffic: divergence 12 B/voxel (velocity in 8 + rhs out 4); gradient-subtract 20 B/voxel
+// (pressure in 4 + velocity in 8 + velocity out 8).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fxb {
+
+namespace {
+
+struct Quad8 {  // four RGBA16F texels
+    uint4 a, b;
+};
+
+__device__ __forceinline__ Quad8 load_quad8(const uint2* __restrict__ f, unsigned i) {
+    const uint4* p = reinterpret_cast<const uint4*>(f + i);
+    Quad8 q;
+    q.a = __ldg(p);
+    q.b = __ldg(p + 1);
+    return q;
+}
+
+__device__ __forceinline__ float h_lo(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float h_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+struct Rows {
+    unsigned c, u, d, f, b;  // offsets of the quad at (x0, y, z) and of its y / z neighbours (clamped)
+    int xl, xr;              // clamped x of the left / right neighbour cell
+};
+
+__device__ __forceinline__ Rows rows_of(const Domain& d, int x0, int y, int z) {
+    Rows r;
+    const unsigned plane = (unsigned)d.nx * d.ny;
+    const unsigned zc = (unsigned)(z - d.z_first) * plane;
+    r.c = zc + (unsigned)y * d.nx + x0;
+    r.u = zc + (unsigned)(max(y, 1) - 1) * d.nx + x0;
+    r.d = zc + (unsigned)min(y + 1, d.ny - 1) * d.nx + x0;
+    r.f = (unsigned)(max(z, 1) - 1 - d.z_first) * plane + (unsigned)y * d.nx + x0;
+    r.b = (unsigned)(min(z + 1, d.nz - 1) - d.z_first) * plane + (unsigned)y * d.nx + x0;
+    r.xl = max(x0, 1) - 1;
+    r.xr = min(x0 + 4, d.nx - 1);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const FrameParams* __restrict__ frame,
+                                                              const uint2* __restrict__ vel,
+                                                              float* __restrict__ rhs) {
+    if (!(0.0f < frame->dt)) return;
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = d.z_own0 + blockIdx.z;
+    if (x0 >= d.nx || y >= d.ny) return;
+    const Rows r = rows_of(d, x0, y, z);
+    const Quad8 c = load_quad8(vel, r.c), u = load_quad8(vel, r.u), dn = load_quad8(vel, r.d);
+    const Quad8 f = load_quad8(vel, r.f), b = load_quad8(vel, r.b);
+    const unsigned row = r.c - x0;
+    const unsigned short* vs = reinterpret_cast<const unsigned short*>(vel);
+    // x component of the six texels x0-1 .. x0+4 (clamped at the faces)
+    const float vx[6] = {half_bits_to_float(__ldg(vs + 4 * (size_t)(row + r.xl))), h_lo(c.a.x), h_lo(c.a.z),
+                         h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(__ldg(vs + 4 * (size_t)(row + r.xr)))};
+    const float uy[4] = {h_hi(u.a.x), h_hi(u.a.z), h_hi(u.b.x), h_hi(u.b.z)};
+    const float dy[4] = {h_hi(dn.a.x), h_hi(dn.a.z), h_hi(dn.b.x), h_hi(dn.b.z)};
+    const float fz[4] = {h_lo(f.a.y), h_lo(f.a.w), h_lo(f.b.y), h_lo(f.b.w)};
+    const float bz[4] = {h_lo(b.a.y), h_lo(b.a.w), h_lo(b.b.y), h_lo(b.b.w)};
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = -vx[j] + vx[j + 2];
+        float s = -uy[j] + dy[j];
+        s = s + a;
+        const float cz = -fz[j] + bz[j];
+        s = cz + s;
+        out[j] = -0.5f * s;
+    }
+    *reinterpret_cast<float4*>(rhs + r.c) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+__global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables tab,
+                                                            const FrameParams* __restrict__ frame,
+                                                            const uint2* __restrict__ vel_in, const float* p0,
+                                                            const float* p1, uint2* __restrict__ vel_out,
+                                                            const StepState* __restrict__ state) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = d.z_own0 + blockIdx.z;
+    if (x0 >= d.nx || y >= d.ny) return;
+    const Rows r = rows_of(d, x0, y, z);
+    const Quad8 v = load_quad8(vel_in, r.c);
+    float ux[4] = {h_lo(v.a.x), h_lo(v.a.z), h_lo(v.b.x), h_lo(v.b.z)};
+    float uy[4] = {h_hi(v.a.x), h_hi(v.a.z), h_hi(v.b.x), h_hi(v.b.z)};
+    float uz[4] = {h_lo(v.a.y), h_lo(v.a.w), h_lo(v.b.y), h_lo(v.b.w)};
+    if (0.0f < frame->dt) {
+        const float* __restrict__ p = state->p_cur ? p1 : p0;
+        const float4 pc = __ldg(reinterpret_cast<const float4*>(p + r.c));
+        const float4 pu = __ldg(reinterpret_cast<const float4*>(p + r.u));
+        const float4 pd = __ldg(reinterpret_cast<const float4*>(p + r.d));
+        const float4 pf = __ldg(reinterpret_cast<const float4*>(p + r.f));
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(p + r.b));
+        const unsigned row = r.c - x0;
+        const float px[6] = {__ldg(p + row + r.xl), pc.x, pc.y, pc.z, pc.w, __ldg(p + row + r.xr)};
+        const float pU[4] = {pu.x, pu.y, pu.z, pu.w}, pD[4] = {pd.x, pd.y, pd.z, pd.w};
+        const float pF[4] = {pf.x, pf.y, pf.z, pf.w}, pB[4] = {pb.x, pb.y, pb.z, pb.w};
+        const float4 bpx4 = __ldg(reinterpret_cast<const float4*>(tab.bp[0] + x0));
+        const float4 wx4 = __ldg(reinterpret_cast<const float4*>(tab.wall[0] + x0));
+        const float bpx[4] = {bpx4.x, bpx4.y, bpx4.z, bpx4.w}, wx[4] = {wx4.x, wx4.y, wx4.z, wx4.w};
+        const float bpy = __ldg(tab.bp[1] + y), wy = __ldg(tab.wall[1] + y);
+        const float bpz = __ldg(tab.bp[2] + z), wz = __ldg(tab.wall[2] + z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gx = -px[j] + px[j + 2];
+            const float gy = -pU[j] + pD[j];
+            const float gz = -pF[j] + pB[j];
+            float a = __fmaf_rn(-gx, 1.04166675f, ux[j]);
+            float b = __fmaf_rn(-gy, 1.04166675f, uy[j]);
+            float c = __fmaf_rn(-gz, 1.04166675f, uz[j]);
+            a = a * ((0.0f < a * bpx[j]) ? wx[j] : 1.0f);
+            b = b * ((0.0f < b * bpy) ? wy : 1.0f);
+            c = c * ((0.0f < c * bpz) ? wz : 1.0f);
+            ux[j] = a; uy[j] = b; uz[j] = c;
+        }
+    }
+    uint4 oa, ob;
+    uint2 t;
+    t = pack_texel4(ux[0], uy[0], uz[0], 0.0f); oa.x = t.x; oa.y = t.y;
+    t = pack_texel4(ux[1], uy[1], uz[1], 0.0f); oa.z = t.x; oa.w = t.y;
+    t = pack_texel4(ux[2], uy[2], uz[2], 0.0f); ob.x = t.x; ob.y = t.y;
+    t = pack_texel4(ux[3], uy[3], uz[3], 0.0f); ob.z = t.x; ob.w = t.y;
+    uint4* o = reinterpret_cast<uint4*>(vel_out + r.c);
+    o[0] = oa;
+    o[1] = ob;
+}
+
+inline dim3 quad_grid(const Domain& d) { return dim3((d.nx / 4 + 31) / 32, (d.ny + 7) / 8, d.z_own1 - d.z_own0); }
+
+}  // namespace
+
+bool quad_kernels_supported(const Domain& d) { return d.nz > 1 && (d.nx % 8) == 0; }
+
+void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs,
+                            cudaStream_t stream) {
+    divergence_quad_kernel<<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, frame, (const uint2*)vel, rhs);
+}
+
+void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
+                          const float* p0, const float* p1, void* vel_out, const StepState* state,
+                          cudaStream_t stream) {
+    gradient_quad_kernel<<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, tab, frame, (const uint2*)vel_in, p0, p1,
+                                                                   (uint2*)vel_out, state);
+}
+
+}  // namespace fxb
