@@ -171,11 +171,12 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
         case PH_JACOBI:
             if (s->fused) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
+                cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
                 for (int k = 0; k < npass; ++k)
                     fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
                                                   s->cfg.early_exit, st);
                 fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t, st);
-                launches = npass + 1;
+                launches = 2 * npass;  // npass relax kernels + (npass - 1) copy kernels + finish
             } else {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
@@ -335,7 +336,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (s->cfg.kernel_path == 0 && fxb::fused_jacobi_supported(s->dom) && s->cfg.jacobi_iters > 0) {
         // Tuned path: T sweeps fused per HBM pass.  Grids whose nx is not a multiple of 8 (e.g. the 150^3 of
         // Bin/FluidGI.bat) and the 2D path use the one-sweep-per-launch kernels instead.
-        s->fuse_t = cfg->fuse_t ? cfg->fuse_t : 4;
+        s->fuse_t = cfg->fuse_t ? cfg->fuse_t : 2;
         const size_t mask_bytes = n / 8;
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&s->jac.mask[i], mask_bytes);
@@ -344,8 +345,11 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, s->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
             return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
         const size_t nb = fxb::fused_jacobi_bricks(s->jac);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.brick_state, nb * sizeof(int));
-        if (e == cudaSuccess) e = cudaMemset(s->jac.brick_state, 0, nb * sizeof(int));
+        const size_t nc = 3 * (fxb::FusedJacobi::kMaxPasses + 1);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+            e = cudaMalloc((void**)&s->jac.work_list[i], 2 * nb * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.work_count, nc * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(s->jac.work_count, 0, nc * sizeof(int));
         if (e != cudaSuccess)
             return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
         s->fused = true;
@@ -379,7 +383,9 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->active);
     cudaFree(s->jac.mask[0]);
     cudaFree(s->jac.mask[1]);
-    cudaFree(s->jac.brick_state);
+    cudaFree(s->jac.work_list[0]);
+    cudaFree(s->jac.work_list[1]);
+    cudaFree(s->jac.work_count);
     cudaFree(s->emitter_basis);
     cudaFree(s->axis_tables);
     cudaFree(s->d_frame);
@@ -486,7 +492,7 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
     out->bricks_copied = st.bricks_copied;
     out->jacobi_fused = s->fused ? 1 : 0;
     if (s->fused) {
-        out->brick_cells = (uint64_t)120 * (32 - 2 * s->fuse_t) * s->jac.bz;
+        out->brick_cells = fxb::fused_jacobi_brick_cells(s->jac);
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
     }
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;

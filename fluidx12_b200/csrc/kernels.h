@@ -33,17 +33,23 @@ void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FramePar
 // jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
 struct FusedJacobi {
     int T = 0;                 // sweeps fused per pass (1..4)
+    int variant = 0;           // kernel shape (rows per thread, warps, TMA depth); see jacobi_fused.cu
+    int tile_y = 32;           // rows of the xy tile
     int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
     float* p[2] = {nullptr, nullptr};
     float* rhs = nullptr;
     unsigned char* mask[2] = {nullptr, nullptr};  // bit-packed freeze flags, ping-pong by pass parity
-    int* brick_state = nullptr;                   // 0 active, 1 frozen (copy pending), 2 frozen in both buffers
+    int* work_list[2] = {nullptr, nullptr};       // [2 * bricks] per pass parity: bricks to relax, then bricks to copy
+    int* work_count = nullptr;                    // [3][kMaxPasses + 1]: relax count, copy count, relax head per pass
+    int num_sms = 0;
+    static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
 };
 bool fused_jacobi_supported(const Domain& d);
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
 size_t fused_jacobi_bricks(const FusedJacobi& J);
+size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, cudaStream_t stream);
 
