@@ -18,6 +18,7 @@
 
 #include "../../include/fluidx_b200.h"
 #include "common.cuh"
+#include "halo.h"
 #include "kernels.h"
 
 namespace {
@@ -69,8 +70,15 @@ struct fxb_sim {
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t last_stream = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
+    // One captured graph per (frame parity, pressure-buffer parity): both select pointers that the halo exchange
+    // of the multi-GPU step needs on the host side.  Single GPU uses slot [0][0] only (its kernels select on device).
+    cudaGraph_t graph[2][2] = {};
+    cudaGraphExec_t graph_exec[2][2] = {};
+    fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
+    int halo = 0;             // halo planes allocated on interior faces
+    int h_adv = 0;            // advection halo (back-trace reach in planes)
+    int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
+    bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
 
     size_t plane_voxels() const { return (size_t)dom.nx * dom.ny; }
@@ -157,12 +165,21 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
     int launches = 0;
     switch (phase) {
         case PH_ADVECT:
+            if (s->multi()) {  // back-trace reach + 1 tap of the inputs
+                const fxb::HaloField f[2] = {{s->vel[0], s->plane_voxels() * 8, s->h_adv + 1},
+                                             {s->col[!s->parity], s->plane_voxels() * 8, s->h_adv + 1}};
+                s->comm.exchange(d, f, 2, st);
+            }
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
             fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
                                s->d_state, st);
             launches = 1;
             break;
         case PH_DIVERGENCE:
+            if (s->multi() && s->dt > 0.0f) {  // z neighbours of the advected velocity
+                const fxb::HaloField f[1] = {{s->vel[1], s->plane_voxels() * 8, 1}};
+                s->comm.exchange(d, f, 1, st);
+            }
             fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);
             if (s->quad) fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, st);
             else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
@@ -172,16 +189,37 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             if (s->fused) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
-                for (int k = 0; k < npass; ++k)
+                const bool mg = s->multi() && s->dt > 0.0f;
+                if (mg) {  // the right-hand side is constant over the sweeps: one exchange of T planes
+                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, s->fuse_t}};
+                    s->comm.exchange(d, f, 1, st);
+                }
+                for (int k = 0; k < npass; ++k) {
+                    if (mg) {  // T planes of the pass's input pressure (and freeze flags) from both neighbours
+                        const fxb::HaloField f[2] = {{s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, s->fuse_t},
+                                                     {s->jac.mask[k & 1], s->plane_voxels() / 8, s->fuse_t}};
+                        s->comm.exchange(d, f, k == 0 ? 1 : 2, st);
+                    }
                     fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
-                                                  s->cfg.early_exit, st);
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t, st);
+                                                  s->cfg.early_exit, s->multi(), st);
+                }
+                if (mg) {
+                    // freeze counters are per rank: sum them so that s_exec is the global figure; every rank runs
+                    // all passes (a pass without active cells only copies), so the buffer parity stays in step
+                    s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st);
+                }
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t,
+                                         s->multi() ? npass : -1, st);
+                if (mg) {  // z neighbours of the final pressure for the gradient
+                    const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + npass) & 1], s->plane_voxels() * 4, 1}};
+                    s->comm.exchange(d, f, 1, st);
+                }
                 launches = 2 * npass;  // npass relax kernels + (npass - 1) copy kernels + finish
             } else {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
                                                     s->cfg.early_exit, st);
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, st);
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, -1, st);
                 launches = s->cfg.jacobi_iters + 1;
             }
             break;
@@ -203,12 +241,13 @@ int enqueue_step(fxb_sim* s, cudaStream_t st) {
     return launches;
 }
 
-int capture_graph(fxb_sim* s) {
+// Captures the step for the current (frame parity, pressure parity) key; single GPU always uses key [0][0].
+int capture_graph(fxb_sim* s, int a, int b) {
     FXB_CUDA(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
     const int launches = enqueue_step(s, s->own_stream);
-    cudaError_t e = cudaStreamEndCapture(s->own_stream, &s->graph);
+    cudaError_t e = cudaStreamEndCapture(s->own_stream, &s->graph[a][b]);
     if (e != cudaSuccess) return fail(FXB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-    FXB_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+    FXB_CUDA(cudaGraphInstantiate(&s->graph_exec[a][b], s->graph[a][b], 0));
     s->kernels_per_step = launches + 1;  // + set_frame_kernel
     return FXB_OK;
 }
@@ -283,7 +322,10 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         return fail(FXB_ERR_INVALID, "fxb_create: bad address_mode");
     if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks)
         return fail(FXB_ERR_INVALID, "fxb_create: bad rank/nranks");
-    if (cfg->nranks > 1) return fail(FXB_ERR_INVALID, "fxb_create: nranks > 1 not available in this build yet");
+    if (cfg->nranks > 1 && !cfg->nccl_unique_id)
+        return fail(FXB_ERR_INVALID, "fxb_create: nranks > 1 needs nccl_unique_id (fxb_nccl_unique_id on rank 0)");
+    if (cfg->nranks > 1 && (cfg->kernel_path != 0 || cfg->nz <= 1 || cfg->nx % 8 != 0 || cfg->jacobi_iters < 1))
+        return fail(FXB_ERR_INVALID, "fxb_create: the z-slab multi-GPU step needs the tuned 3D path (nx % 8 == 0)");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -302,6 +344,24 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     s->dom.z_first = 0; s->dom.nz_alloc = (int)cfg->nz;
     s->dom.z_own0 = 0; s->dom.z_own1 = (int)cfg->nz;
     s->fuse_t = 1;
+    if (cfg->nranks > 1) {
+        // z-slab decomposition (fluidx12_b200/slab.py states the same rules): rank r owns planes
+        // [r*nz/R, (r+1)*nz/R); interior faces carry `halo` extra planes, the grid's own faces none
+        const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
+        const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
+        s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;
+        s->halo = std::max(s->h_adv + 1, fuse);
+        int thinnest = nz;
+        for (int q = 0; q < R; ++q) thinnest = std::min(thinnest, (q + 1) * nz / R - q * nz / R);
+        if (R > nz || s->halo > thinnest) {
+            delete s;
+            return fail(FXB_ERR_INVALID, "fxb_create: halo deeper than the thinnest slab (fewer ranks or smaller h_adv)");
+        }
+        s->dom.z_own0 = r * nz / R;
+        s->dom.z_own1 = (r + 1) * nz / R;
+        s->dom.z_first = std::max(s->dom.z_own0 - s->halo, 0);
+        s->dom.nz_alloc = std::min(s->dom.z_own1 + s->halo, nz) - s->dom.z_first;
+    }
 
     auto cleanup_fail = [&](int rc) { fxb_destroy(s); return rc; };
     const size_t n = s->alloc_voxels();
@@ -327,6 +387,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (e != cudaSuccess)
         return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));
 
+    if (s->multi() && !s->comm.init(cfg->nccl_unique_id, cfg->rank, cfg->nranks))
+        return cleanup_fail(fail(FXB_ERR_NCCL, "fxb_create: " + fxb::halo_last_error()));
     int rc = build_emitter(s);
     if (rc != FXB_OK) return cleanup_fail(rc);
     rc = build_axis_tables(s);
@@ -354,12 +416,20 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
         s->fused = true;
     }
-    if (s->cfg.use_graph) {
-        rc = capture_graph(s);
+    if (s->cfg.use_graph && !s->multi()) {
+        rc = capture_graph(s, 0, 0);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
         const int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
         s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
+    }
+    if (s->multi()) {
+        // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
+        const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, 1}};
+        if (!s->comm.exchange(s->dom, f, 1, s->own_stream) ||
+            !s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, s->own_stream))
+            return cleanup_fail(fail(FXB_ERR_NCCL, "fxb_create: " + fxb::halo_last_error()));
+        if (cudaStreamSynchronize(s->own_stream) == cudaSuccess) cudaMemset(s->d_state, 0, sizeof(fxb::StepState));
     }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess)
@@ -372,8 +442,12 @@ void fxb_destroy(fxb_sim* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     cudaDeviceSynchronize();
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-    if (s->graph) cudaGraphDestroy(s->graph);
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            if (s->graph_exec[a][b]) cudaGraphExecDestroy(s->graph_exec[a][b]);
+            if (s->graph[a][b]) cudaGraphDestroy(s->graph[a][b]);
+        }
+    s->comm.destroy();
     for (int i = 0; i < 2; ++i) {
         cudaFree(s->vel[i]);
         cudaFree(s->col[i]);
@@ -408,8 +482,24 @@ int fxb_simulate(fxb_sim* s, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
-    if (s->graph_exec) {
-        FXB_CUDA(cudaGraphLaunch(s->graph_exec, st));
+    const int npass = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : 0;
+    if (s->multi()) {
+        // the exchanges depend on dt > 0, the frame parity and the pressure parity: one graph per key, captured on
+        // first use; a paused frame (dt <= 0) is enqueued directly
+        const int a = s->parity, b = s->p_cur_host;
+        if (s->cfg.use_graph && s->dt > 0.0f) {
+            if (!s->graph_exec[a][b]) {
+                const int rc = capture_graph(s, a, b);
+                if (rc != FXB_OK) return rc;
+            }
+            FXB_CUDA(cudaGraphLaunch(s->graph_exec[a][b], st));
+        } else {
+            enqueue_step(s, st);
+            FXB_CUDA(cudaGetLastError());
+        }
+        if (s->dt > 0.0f) s->p_cur_host = (s->p_cur_host + npass) & 1;
+    } else if (s->graph_exec[0][0]) {
+        FXB_CUDA(cudaGraphLaunch(s->graph_exec[0][0], st));
     } else {
         enqueue_step(s, st);
         FXB_CUDA(cudaGetLastError());
@@ -514,14 +604,17 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     for (int ph = 0; ph < PH_COUNT; ++ph) FXB_CUDA(cudaEventElapsedTime(&ms[ph], s->ev[ph], s->ev[ph + 1]));
     ms[4] = 0.0f;
     FXB_CUDA(cudaEventElapsedTime(&ms[5], s->ev[0], s->ev[PH_COUNT]));
+    if (s->multi() && s->fused && s->dt > 0.0f)
+        s->p_cur_host = (s->p_cur_host + (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t) & 1;
     s->last_stream = st;
     ++s->steps;
     return FXB_OK;
 }
 
 int fxb_nccl_unique_id(void* out128) {
-    (void)out128;
-    return fail(FXB_ERR_NCCL, "fxb_nccl_unique_id: multi-GPU support not built yet");
+    if (!out128) return fail(FXB_ERR_INVALID, "fxb_nccl_unique_id: null argument");
+    if (!fxb::halo_unique_id(out128)) return fail(FXB_ERR_NCCL, "fxb_nccl_unique_id: " + fxb::halo_last_error());
+    return FXB_OK;
 }
 
 }  // extern "C"

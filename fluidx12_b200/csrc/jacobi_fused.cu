@@ -105,6 +105,7 @@ struct PassParams {
     int pass;              // index of this fused pass in the frame
     int levels_total;      // ITER
     int early_exit;
+    int run_all;           // multi-GPU: never end the solve on this rank's own freeze counters
 };
 
 struct WorkLists {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) copy_frozen_bricks_kernel(const FramePara
                                                                  const WorkLists W, const PassParams P) {
     FXB_SHAPE_CONSTANTS(S);
     if (!(0.0f < frame->dt)) return;
-    if (P.pass == 0 || state->active_after[P.pass * T - 1] == 0ull) return;
+    if (P.pass == 0 || (!P.run_all && state->active_after[P.pass * T - 1] == 0ull)) return;
     const int sel = (state->p_cur + P.pass) & 1;
     const float* __restrict__ p_in = sel ? p1 : p0;
     float* __restrict__ p_out = sel ? p0 : p1;
@@ -531,7 +532,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     FXB_SHAPE_CONSTANTS(S);
     if (!(0.0f < frame->dt)) return;
     const int s0 = P.pass * T;  // sweeps completed before this pass
-    if (P.pass > 0 && state->active_after[s0 - 1] == 0ull) return;
+    if (P.pass > 0 && !P.run_all && state->active_after[s0 - 1] == 0ull) return;
     const int levels = min(T, P.levels_total - s0);
 
     const int sel = (state->p_cur + P.pass) & 1;
@@ -608,7 +609,7 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int nz_alloc,
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                         int iters, int early_exit, cudaStream_t stream) {
+                         int iters, int early_exit, bool run_all, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -622,7 +623,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     P.z_face_hi = d.nz - d.z_first;
     P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
     P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
-    P.pass = pass; P.levels_total = iters; P.early_exit = early_exit;
+    P.pass = pass; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
     const int nbricks = J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
     const int grid = nbricks < slots ? nbricks : slots;
@@ -648,14 +649,14 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
 //   2: 4 rows/thread,  8 warps (tile 128 x 32), TMA depth 2
 template <int T>
 cudaError_t launch_T(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                     int iters, int early_exit, cudaStream_t stream) {
+                     int iters, int early_exit, bool run_all, cudaStream_t stream) {
     switch (J.variant) {
         case 0:
             if constexpr (T <= 2)
-                return launch_shape<Shape<T, 2, 8, 2, 2>>(J, d, frame, state, pass, iters, early_exit, stream);
+                return launch_shape<Shape<T, 2, 8, 2, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
             break;
-        case 1: return launch_shape<Shape<T, 2, 16, 1>>(J, d, frame, state, pass, iters, early_exit, stream);
-        case 2: return launch_shape<Shape<T, 4, 8, 2>>(J, d, frame, state, pass, iters, early_exit, stream);
+        case 1: return launch_shape<Shape<T, 2, 16, 1>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 2: return launch_shape<Shape<T, 4, 8, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -700,12 +701,12 @@ size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty 
 size_t fused_jacobi_brick_cells(const FusedJacobi& J) { return (size_t)kOutX * (J.tile_y - 2 * J.T) * J.bz; }
 
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                     int pass, int iters, int early_exit, cudaStream_t stream) {
+                                     int pass, int iters, int early_exit, bool run_all, cudaStream_t stream) {
     switch (J.T) {
-        case 1: return launch_T<1>(J, d, frame, state, pass, iters, early_exit, stream);
-        case 2: return launch_T<2>(J, d, frame, state, pass, iters, early_exit, stream);
-        case 3: return launch_T<3>(J, d, frame, state, pass, iters, early_exit, stream);
-        case 4: return launch_T<4>(J, d, frame, state, pass, iters, early_exit, stream);
+        case 1: return launch_T<1>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 2: return launch_T<2>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 3: return launch_T<3>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 4: return launch_T<4>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -18,7 +18,8 @@ void launch_divergence(const Domain& d, const FrameParams* frame, const void* ve
 void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const float* rhs, float* p0, float* p1,
                                 unsigned char* active, StepState* state, int sweep, int early_exit,
                                 cudaStream_t stream);
-void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int fuse_t, cudaStream_t stream);
+void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int fuse_t, int force_passes,
+                         cudaStream_t stream);
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,
                      void* vel_out, const StepState* state, cudaStream_t stream);
 
@@ -51,6 +52,6 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                     int pass, int iters, int early_exit, cudaStream_t stream);
+                                     int pass, int iters, int early_exit, bool run_all_passes, cudaStream_t stream);
 
 }  // namespace fxb

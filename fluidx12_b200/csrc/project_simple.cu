@@ -110,15 +110,17 @@ __global__ void __launch_bounds__(256) jacobi_sweep_simple_kernel(Domain d, cons
 }
 
 // sweeps_per_flip: 1 for the simple path, T for the fused path (the pressure ping-pong flips once per pass).
+// force_passes >= 0 (multi-GPU): every rank ran exactly that many passes, whatever the freeze counters say.
 __global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters,
-                                    int sweeps_per_flip) {
+                                    int sweeps_per_flip, int force_passes) {
     if (threadIdx.x != 0) return;
     int s = 0;
     if (0.0f < frame->dt && iters > 0) {
         s = 1;
         while (s < iters && state->active_after[s - 1] != 0ull) ++s;
     }
-    const int passes = (s + sweeps_per_flip - 1) / sweeps_per_flip;
+    int passes = (s + sweeps_per_flip - 1) / sweeps_per_flip;
+    if (force_passes >= 0 && 0.0f < frame->dt) passes = force_passes;
     state->s_exec = s;
     state->passes = passes;
     state->p_cur = (state->p_cur + passes) & 1;
@@ -190,9 +192,9 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
                                                                           early_exit);
 }
 
-void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int sweeps_per_flip,
+void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int sweeps_per_flip, int force_passes,
                          cudaStream_t stream) {
-    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, sweeps_per_flip);
+    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, sweeps_per_flip, force_passes);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,

@@ -1,0 +1,35 @@
+"""Multi-GPU (z-slab + NCCL halo exchange) parity: N ranks must reproduce the single-GPU fields bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nproc, env_extra):
+    env = dict(os.environ, **env_extra)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    return out.returncode, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,t", [("64,64,96", 2), ("72,72,64", 1), ("128,128,80", 4)])
+def test_two_ranks_match_single_gpu(grid, t):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    rc, log = _run(2, {"FXB_TEST_GRID": grid, "FXB_TEST_T": str(t)})
+    assert rc == 0 and "MGPU_OK" in log, log[-3000:]
+
+
+@pytest.mark.gpu
+def test_four_ranks_and_eager_launch():
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    rc, log = _run(4, {"FXB_TEST_GRID": "64,64,128", "FXB_TEST_T": "2", "FXB_TEST_GRAPH": "0"})
+    assert rc == 0 and "MGPU_OK" in log, log[-3000:]
