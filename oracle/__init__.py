@@ -53,6 +53,10 @@ def lib() -> C.CDLL:
         L.fxo_divergence2x.argtypes = [i32, i32, i32, u16p, f32p]
         L.fxo_jacobi.argtypes = [i32, i32, i32, f32p, f32p, i32, i32, vp, vp]
         L.fxo_gradient.argtypes = [i32, i32, i32, u16p, f32p, u16p]
+        L.fxo_advect_slab.argtypes = [i32, i32, i32, i32, i32, i32, f32, u16p, u16p, u16p, u16p]
+        L.fxo_divergence2x_slab.argtypes = [i32, i32, i32, i32, i32, u16p, f32p]
+        L.fxo_jacobi_sweeps_slab.argtypes = [i32, i32, i32, i32, i32, f32p, f32p, vp, i32, i32, i32, i32, vp]
+        L.fxo_gradient_slab.argtypes = [i32, i32, i32, i32, i32, u16p, f32p, u16p]
         L.fxo_f32_to_f16.restype = C.c_uint16
         L.fxo_f32_to_f16.argtypes = [f32]
         L.fxo_f16_to_f32.restype = f32
@@ -165,6 +169,45 @@ def gradient(vel, p):
     p = np.ascontiguousarray(p, np.float32)
     out = np.empty_like(vel)
     lib().fxo_gradient(nx, ny, nz, _ptr(vel), _ptr(p), _ptr(out))
+    return out
+
+
+# ---- z-slab window wrappers (arrays are windows [z0, z0 + nzl) of a grid with nzg planes) ----------------------
+def advect_slab(vel, col, dt, nzg, z0, address_mode=ADDRESS_MIRROR):
+    nzl, ny, nx, _ = vel.shape
+    vel = np.ascontiguousarray(vel, np.float16)
+    col = np.ascontiguousarray(col, np.float16)
+    vo, co = np.empty_like(vel), np.empty_like(col)
+    lib().fxo_advect_slab(nx, ny, nzl, nzg, z0, address_mode, dt, _ptr(vel), _ptr(col), _ptr(vo), _ptr(co))
+    return vo, co
+
+
+def divergence2x_slab(vel, nzg, z0):
+    nzl, ny, nx, _ = vel.shape
+    vel = np.ascontiguousarray(vel, np.float16)
+    s = np.empty((nzl, ny, nx), np.float32)
+    lib().fxo_divergence2x_slab(nx, ny, nzl, nzg, z0, _ptr(vel), _ptr(s))
+    return s
+
+
+def jacobi_sweeps_slab(s, p, active, nsweeps, nzg, z0, c0, c1, early_exit=True):
+    """In-place on copies; returns (p, active, counts[nsweeps])."""
+    nzl, ny, nx = s.shape
+    s = np.ascontiguousarray(s, np.float32)
+    p = np.array(p, np.float32, order="C", copy=True)
+    active = np.array(active, np.uint8, order="C", copy=True)
+    counts = np.zeros(max(nsweeps, 1), np.int64)
+    lib().fxo_jacobi_sweeps_slab(nx, ny, nzl, nzg, z0, _ptr(s), _ptr(p), _ptr(active), nsweeps, int(early_exit), c0, c1,
+                                 _ptr(counts))
+    return p, active, counts[:nsweeps]
+
+
+def gradient_slab(vel, p, nzg, z0):
+    nzl, ny, nx, _ = vel.shape
+    vel = np.ascontiguousarray(vel, np.float16)
+    p = np.ascontiguousarray(p, np.float32)
+    out = np.empty_like(vel)
+    lib().fxo_gradient_slab(nx, ny, nzl, nzg, z0, _ptr(vel), _ptr(p), _ptr(out))
     return out
 
 

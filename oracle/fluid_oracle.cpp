@@ -104,10 +104,16 @@ inline int floor_to_tap(float t) {
     return (int)std::floor(t);
 }
 
+// nx, ny, nz: extent of the array the function works on.  For the z-slab tests the array is a window of a taller
+// grid: nzg = global plane count (0 = same as nz) and z0 = global index of local plane 0; positions, sampler
+// addressing, the emitter and the clamp-to-edge neighbour rule are then evaluated in GLOBAL coordinates.
 struct Grid {
     int nx, ny, nz;
+    int nzg = 0, z0 = 0;
+    int gnz() const { return nzg > 0 ? nzg : nz; }
     size_t idx(int x, int y, int z) const { return (size_t(z) * ny + y) * nx + x; }
     size_t voxels() const { return size_t(nx) * ny * nz; }
+    int local_z(int zg) const { return std::min(std::max(zg - z0, 0), nz - 1); }  // window-clamped
 };
 
 // One trilinear fetch of an RGBA16F field at normalised coordinate (cx,cy,cz) -> out[4].
@@ -116,12 +122,12 @@ inline void sample_trilinear(const uint16_t* field, const Grid& g, int mode,
                              float cx, float cy, float cz, float out[4]) {
     const float tx = std::fmaf(cx, (float)g.nx, -0.5f);
     const float ty = std::fmaf(cy, (float)g.ny, -0.5f);
-    const float tz = std::fmaf(cz, (float)g.nz, -0.5f);
+    const float tz = std::fmaf(cz, (float)g.gnz(), -0.5f);
     const int ix = floor_to_tap(tx), iy = floor_to_tap(ty), iz = floor_to_tap(tz);
     const float fx = tx - std::floor(tx), fy = ty - std::floor(ty), fz = tz - std::floor(tz);
     const int x0 = address_tap(ix, g.nx, mode), x1 = address_tap(ix + 1, g.nx, mode);
     const int y0 = address_tap(iy, g.ny, mode), y1 = address_tap(iy + 1, g.ny, mode);
-    const int z0 = address_tap(iz, g.nz, mode), z1 = address_tap(iz + 1, g.nz, mode);
+    const int z0 = g.local_z(address_tap(iz, g.gnz(), mode)), z1 = g.local_z(address_tap(iz + 1, g.gnz(), mode));
     const uint16_t* t000 = field + 4 * g.idx(x0, y0, z0);
     const uint16_t* t100 = field + 4 * g.idx(x1, y0, z0);
     const uint16_t* t010 = field + 4 * g.idx(x0, y1, z0);
@@ -149,12 +155,12 @@ inline void sample_trilinear(const uint16_t* field, const Grid& g, int mode,
 inline float emitter_basis(const Grid& g, int x, int y, int z, float disp[3]) {
     const float px = ((float)x + 0.5f) / (float)g.nx;
     const float py = ((float)y + 0.5f) / (float)g.ny;
-    const float pz = ((float)z + 0.5f) / (float)g.nz;
+    const float pz = ((float)(z + g.z0) + 0.5f) / (float)g.gnz();
     disp[0] = px + -0.5f;
     disp[1] = py + -0.100000001f;
     disp[2] = pz + -0.5f;
     const float d2 = (disp[0] * disp[0] + disp[1] * disp[1]) + disp[2] * disp[2];
-    const float r2 = (1.0f < (float)g.nz) ? 0.00390625f : 0.0009765625f;
+    const float r2 = (1.0f < (float)g.gnz()) ? 0.00390625f : 0.0009765625f;
     const float e = ((d2 * -4.0f) / r2) * 1.44269502f;
     return std::exp2f(e);
 }
@@ -164,7 +170,7 @@ inline float emitter_basis(const Grid& g, int x, int y, int z, float disp[3]) {
 // ---------------------------------------------------------------------------------------------
 void advect(const Grid& g, int mode, float dt, const uint16_t* vel_in, const uint16_t* col_in,
             uint16_t* vel_out, uint16_t* col_out) {
-    const bool is3d = 1.0f < (float)g.nz;
+    const bool is3d = 1.0f < (float)g.gnz();
     const float atten = std::max(std::fmaf(-dt, 0.200000003f, 1.0f), 0.0f);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int z = 0; z < g.nz; ++z)
@@ -173,7 +179,7 @@ void advect(const Grid& g, int mode, float dt, const uint16_t* vel_in, const uin
                 const size_t i = g.idx(x, y, z);
                 const float px = ((float)x + 0.5f) / (float)g.nx;
                 const float py = ((float)y + 0.5f) / (float)g.ny;
-                const float pz = ((float)z + 0.5f) / (float)g.nz;
+                const float pz = ((float)(z + g.z0) + 0.5f) / (float)g.gnz();
                 float disp[3];
                 const float basis = emitter_basis(g, x, y, z, disp);
                 float F[3];
@@ -217,14 +223,15 @@ inline Nbr neighbours(const Grid& g, int x, int y, int z, bool is3d) {
     n.R = g.idx(std::min(x + 1, g.nx - 1), y, z);
     n.U = g.idx(x, std::max(y, 1) - 1, z);
     n.D = g.idx(x, std::min(y + 1, g.ny - 1), z);
-    n.F = is3d ? g.idx(x, y, std::max(z, 1) - 1) : 0;
-    n.B = is3d ? g.idx(x, y, std::min(z + 1, g.nz - 1)) : 0;
+    const int zg = z + g.z0;
+    n.F = is3d ? g.idx(x, y, g.local_z(std::max(zg, 1) - 1)) : 0;
+    n.B = is3d ? g.idx(x, y, g.local_z(std::min(zg + 1, g.gnz() - 1))) : 0;
     return n;
 }
 
 // s = 2*divergence exactly as the DXBC sums it (the 0.5 is applied inside the Poisson loop).
 void divergence2x(const Grid& g, const uint16_t* vel, float* s) {
-    const bool is3d = g.nz > 1;
+    const bool is3d = g.gnz() > 1;
 #pragma omp parallel for collapse(2) schedule(static)
     for (int z = 0; z < g.nz; ++z)
         for (int y = 0; y < g.ny; ++y)
@@ -247,7 +254,7 @@ void divergence2x(const Grid& g, const uint16_t* vel, float* s) {
 // (S_exec); hist[k] = number of active cells entering sweep k.
 int jacobi(const Grid& g, const float* s, float* p, float* q, uint8_t* active, int iters,
            int early_exit, int64_t* hist) {
-    const bool is3d = g.nz > 1;
+    const bool is3d = g.gnz() > 1;
     const float inv = is3d ? 0.166666672f : 0.25f;
     const size_t n = g.voxels();
     std::memset(active, 1, n);
@@ -288,7 +295,7 @@ int jacobi(const Grid& g, const float* s, float* p, float* q, uint8_t* active, i
 
 // Gradient subtract + soft-wall damping + fp16 store (CSProject3D.hlsl:55-63,:106-112).
 void gradient(const Grid& g, const uint16_t* vel_in, const float* p, uint16_t* vel_out) {
-    const bool is3d = g.nz > 1;
+    const bool is3d = g.gnz() > 1;
 #pragma omp parallel for collapse(2) schedule(static)
     for (int z = 0; z < g.nz; ++z)
         for (int y = 0; y < g.ny; ++y)
@@ -302,7 +309,7 @@ void gradient(const Grid& g, const uint16_t* vel_in, const float* p, uint16_t* v
                 float bp[3];
                 const float px = ((float)x + 0.5f) / (float)g.nx;
                 const float py = ((float)y + 0.5f) / (float)g.ny;
-                const float pz = ((float)z + 0.5f) / (float)g.nz;
+                const float pz = ((float)(z + g.z0) + 0.5f) / (float)g.gnz();
                 if (is3d) {
                     const float gz = -p[n.F] + p[n.B];
                     u[0] = std::fmaf(-gx, 1.04166675f, u[0]);
@@ -445,6 +452,52 @@ int fxo_jacobi(int nx, int ny, int nz, const float* s, float* p, int iters, int 
 }
 void fxo_gradient(int nx, int ny, int nz, const uint16_t* vel_in, const float* p, uint16_t* vel_out) {
     gradient(Grid{nx, ny, nz}, vel_in, p, vel_out);
+}
+
+// ---- z-slab window entry points (decomposition tests: tests/test_slab_gloo.py) ----------------------------------
+void fxo_advect_slab(int nx, int ny, int nz, int nzg, int z0, int mode, float dt, const uint16_t* vel_in,
+                     const uint16_t* col_in, uint16_t* vel_out, uint16_t* col_out) {
+    Grid g{nx, ny, nz}; g.nzg = nzg; g.z0 = z0;
+    advect(g, mode, dt, vel_in, col_in, vel_out, col_out);
+}
+void fxo_divergence2x_slab(int nx, int ny, int nz, int nzg, int z0, const uint16_t* vel, float* s) {
+    Grid g{nx, ny, nz}; g.nzg = nzg; g.z0 = z0;
+    divergence2x(g, vel, s);
+}
+// Exactly `nsweeps` synchronous sweeps over the whole window starting from the given freeze flags (in/out);
+// counts[k] = cells of local planes [c0, c1) still active after sweep k.  Cells near a window end that is not a
+// grid face become invalid one plane per sweep, exactly like the halo of a fused pass.
+void fxo_jacobi_sweeps_slab(int nx, int ny, int nz, int nzg, int z0, const float* s, float* p, uint8_t* active,
+                            int nsweeps, int early_exit, int c0, int c1, int64_t* counts) {
+    Grid g{nx, ny, nz}; g.nzg = nzg; g.z0 = z0;
+    const float inv = 0.166666672f;
+    std::vector<float> q(g.voxels());
+    float* cur = p; float* nxt = q.data();
+    for (int k = 0; k < nsweeps; ++k) {
+        int64_t still = 0;
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : still)
+        for (int z = 0; z < nz; ++z)
+            for (int y = 0; y < ny; ++y)
+                for (int x = 0; x < nx; ++x) {
+                    const size_t i = g.idx(x, y, z);
+                    if (!active[i]) { nxt[i] = cur[i]; continue; }
+                    const Nbr nb = neighbours(g, x, y, z, true);
+                    float acc = std::fmaf(-s[i], 0.5f, cur[nb.L]);
+                    acc = cur[nb.R] + acc; acc = cur[nb.U] + acc; acc = cur[nb.D] + acc;
+                    acc = cur[nb.F] + acc; acc = cur[nb.B] + acc;
+                    nxt[i] = acc * inv;
+                    if (early_exit && std::fabs(std::fmaf(acc, inv, -cur[i])) < 0.00100000005f) active[i] = 0;
+                    else if (z >= c0 && z < c1) ++still;
+                }
+        counts[k] = still;
+        std::swap(cur, nxt);
+    }
+    if (cur != p) std::memcpy(p, cur, g.voxels() * sizeof(float));
+}
+void fxo_gradient_slab(int nx, int ny, int nz, int nzg, int z0, const uint16_t* vel_in, const float* p,
+                       uint16_t* vel_out) {
+    Grid g{nx, ny, nz}; g.nzg = nzg; g.z0 = z0;
+    gradient(g, vel_in, p, vel_out);
 }
 
 // ---- unit helpers -----------------------------------------------------------------------------

@@ -1,0 +1,114 @@
+"""CPU test of the multi-rank host logic (world_size 2 and 3, gloo): the z-slab rules of fluidx12_b200.slab.
+
+Each rank holds the window [z_first, z_first + nz_alloc) that ``halo_plan`` prescribes, exchanges exactly the face
+ranges the plan lists (torch.distributed send/recv over gloo) and advances its window with the oracle's slab-window
+stage functions in the same order as the CUDA multi-GPU step (csrc/fxb_api.cu: exchange velocity+colour -> advect ->
+exchange advected velocity -> divergence -> exchange rhs -> per fused pass: exchange pressure (+ freeze flags),
+T sweeps -> all-reduce the freeze counters -> exchange pressure -> gradient).  The owned planes must equal the
+single-domain oracle bit for bit, which pins the halo depths, the exchange schedule and the face handling.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tests.util import smooth_state  # noqa: E402
+
+
+def _exchange(arr, faces, z_first):
+    """Apply a list of slab.Exchange records to a window array (planes along axis 0)."""
+    reqs, recvs = [], []
+    for e in faces:
+        send = torch.from_numpy(np.ascontiguousarray(arr[e.send0 - z_first:e.send1 - z_first]).view(np.uint8).reshape(-1).copy())
+        recv = torch.empty(int(np.prod(arr[e.recv0 - z_first:e.recv1 - z_first].shape)) * arr.itemsize, dtype=torch.uint8)
+        reqs.append(dist.isend(send, e.peer))
+        reqs.append(dist.irecv(recv, e.peer))
+        recvs.append((e, recv))
+    for r in reqs:
+        r.wait()
+    for e, recv in recvs:
+        dst = arr[e.recv0 - z_first:e.recv1 - z_first]
+        dst[...] = recv.numpy().view(arr.dtype).reshape(dst.shape)
+
+
+def _worker(rank, world, port, grid, steps, fuse_t, h_adv, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from fluidx12_b200 import halo_plan
+    nx, ny, nz = grid
+    plan = halo_plan(nz, rank, world, fuse_t, h_adv)
+    zf, nza = plan.z_first, plan.nz_alloc
+    own = slice(plan.z0 - zf, plan.z1 - zf)
+    vel_g, col_g, p_g = smooth_state(nx, ny, nz, seed=9, umax=1.0)
+    vel0 = vel_g[zf:zf + nza].copy()
+    col = [np.zeros_like(vel0), col_g[zf:zf + nza].copy()]  # col[parity]; parity starts at 0, flips before step 1
+    col = [col[1], np.zeros_like(vel0)]
+    p = p_g[zf:zf + nza].copy()
+    parity, dt, iters = 0, O.dt_for_grid(nx, ny, nz), 64
+    npass = -(-iters // fuse_t)
+    s_exec = 0
+    for _ in range(steps):
+        parity ^= 1
+        _exchange(vel0, plan.advect, zf)
+        _exchange(col[1 - parity], plan.advect, zf)
+        vel1, col[parity] = O.advect_slab(vel0, col[1 - parity], dt, nz, zf)
+        _exchange(vel1, plan.stencil1, zf)
+        s = O.divergence2x_slab(vel1, nz, zf)
+        _exchange(s, plan.jacobi, zf)
+        active = np.ones(s.shape, np.uint8)
+        counts = np.zeros(npass * fuse_t, np.int64)
+        for k in range(npass):
+            _exchange(p, plan.jacobi, zf)
+            if k:
+                _exchange(active, plan.jacobi, zf)
+            p, active, c = O.jacobi_sweeps_slab(s, p, active, fuse_t, nz, zf, own.start, own.stop)
+            counts[k * fuse_t:(k + 1) * fuse_t] = c
+        t = torch.from_numpy(counts)
+        dist.all_reduce(t)
+        counts = t.numpy()
+        s_exec = 1 + int(np.argmax(np.append(counts[:iters - 1] == 0, True))) if iters else 0
+        _exchange(p, plan.stencil1, zf)
+        vel0 = O.gradient_slab(vel1, p, nz, zf)
+    res = {"z0": plan.z0, "vel": vel0[own][..., :3].copy(), "col": col[parity][own].copy(), "p": p[own].copy(),
+           "s_exec": s_exec}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, res)
+    if rank == 0:
+        o = O.FluidOracle(nx, ny, nz)
+        o.set_field(O.FIELD_VEL, vel_g); o.set_field(O.FIELD_COLOR, col_g); o.set_field(O.FIELD_PRESSURE, p_g)
+        for _ in range(steps):
+            o.step(dt)
+        gathered.sort(key=lambda r: r["z0"])
+        ok = (np.array_equal(np.concatenate([r["vel"] for r in gathered]), o.get_field(O.FIELD_VEL)[..., :3])
+              and np.array_equal(np.concatenate([r["col"] for r in gathered]), o.get_field(O.FIELD_COLOR))
+              and np.array_equal(np.concatenate([r["p"] for r in gathered]), o.get_field(O.FIELD_PRESSURE))
+              and all(r["s_exec"] == o.s_exec for r in gathered))
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid,fuse_t,h_adv", [(2, (16, 16, 24), 2, 3), (3, (16, 16, 30), 4, 5), (2, (24, 24, 20), 1, 5)])
+def test_slab_decomposition_matches_single_domain(world, grid, fuse_t, h_adv):
+    import oracle
+    oracle.build()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29700 + world * 10 + fuse_t
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, 3, fuse_t, h_adv, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=300)
+        assert pr.exitcode == 0
+    assert out.get(timeout=10) is True
