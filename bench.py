@@ -183,25 +183,45 @@ def voxels_local_of(f):
     return f.m_gridSize[0] * f.m_gridSize[1] * f.slab[1]
 
 
-def kernel_roofline(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
-    """Dominant kernel = the Jacobi pass.  Average device time per executed pass, measured live with CUDA
-    events around the Jacobi phase of un-graphed steps (fxb_profile_step), against its algorithmic bytes."""
-    tot_ms, tot_passes, phases = 0.0, 0, {}
+def jacobi_work_bytes(st0, st1, mask_bytes, voxels_local):
+    """Bytes the Jacobi passes between two stats snapshots really had to move: a relaxed brick reads p + rhs and
+    writes p (+ 2/8 B of freeze flags) per cell, a frozen brick is copied once (p in, p out), every other brick is
+    skipped because its value is already final in both pressure buffers."""
+    if st1.jacobi_fused:
+        proc = st1.bricks_processed - st0.bricks_processed
+        cop = st1.bricks_copied - st0.bricks_copied
+        return (proc * 12.25 + cop * 8.0) * st1.brick_cells, proc, cop
+    return (st1.total_passes - st0.total_passes) * (12.0 + mask_bytes) * voxels_local, 0, 0
+
+
+def phase_rooflines(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
+    """Per-phase device time measured live with CUDA events between the kernels of un-graphed steps
+    (fxb_profile_step) against each phase's algorithmic bytes.  The Jacobi passes are the dominant
+    kernel: their bytes are counted from the bricks actually relaxed / copied during these very steps."""
+    st0 = f.stats()
+    phases = {}
     for _ in range(reps):
         f.UpdateFrame(dt)
-        ms = f.profile_step()
-        st = f.stats()
-        tot_ms += ms["jacobi"]
-        tot_passes += st.jacobi_passes
-        for k, v in ms.items():
+        for k, v in f.profile_step().items():
             phases[k] = phases.get(k, 0.0) + v / reps
-    per_launch_bytes = (12.0 + mask_bytes) * voxels_local
-    avg_ms = tot_ms / max(tot_passes, 1)
-    achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "jacobi_pass", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": None,
-            "bytes_per_launch": per_launch_bytes, "avg_launch_ms": round(avg_ms, 5),
-            "launches_per_step": round(tot_passes / reps, 2)}, {k: round(v, 4) for k, v in phases.items()}
+    st1 = f.stats()
+    jb, proc, cop = jacobi_work_bytes(st0, st1, mask_bytes, voxels_local)
+    jb /= reps
+    launches = (st1.total_passes - st0.total_passes) / reps * (2 if st1.jacobi_fused else 1)
+    per = {"advect": 32.0 * voxels_local, "divergence": 12.0 * voxels_local, "jacobi": jb,
+           "gradient": 20.0 * voxels_local}
+    out = {}
+    for k, nbytes in per.items():
+        gbs = nbytes / max(phases[k] * 1e-3, 1e-12) / 1e9
+        out[k] = {"ms": round(phases[k], 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1),
+                  "frac": round(gbs / peak, 4)}
+    j = out["jacobi"]
+    roof = {"bound": "hbm", "kernel": "jacobi_pass_kernel + copy_frozen_bricks_kernel (all passes of a step)",
+            "achieved": j["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": j["frac"], "peak_source": peak_src,
+            "traffic": None, "bytes_per_step": jb, "ms_per_step": j["ms"], "launches_per_step": round(launches, 1),
+            "bricks_relaxed_per_step": round(proc / reps, 1), "bricks_copied_per_step": round(cop / reps, 1),
+            "note": "issue/latency-bound, not HBM-bound: see DESIGN.md §5 and profiles/"}
+    return roof, out, {k: round(v, 4) for k, v in phases.items()}
 
 
 def cpu_baseline_sample(f, fx, grid, dt, budget_s=25.0):
@@ -295,31 +315,29 @@ def run_ours(args):
     sweeps = (st1.total_sweeps - st0.total_sweeps) / max(args.steps, 1)
     fuse_t = st1.fuse_t
     mask_bytes = 0.25 if st1.jacobi_fused else 2.0
-    bpv = bytes_per_voxel_step(passes, mask_bytes)
-    value = voxels * args.steps / (ms * 1e-3)
-    step_gbs = bpv * voxels / (ms * 1e-3 / args.steps) / 1e9
-    # bytes of the work actually needed: frozen bricks are skipped (their values are final), so only processed
-    # bricks move p/rhs/mask and copied bricks move p once
-    work = None
-    if st1.jacobi_fused:
-        proc = (st1.bricks_processed - st0.bricks_processed) / args.steps
-        cop = (st1.bricks_copied - st0.bricks_copied) / args.steps
-        jac_bytes = (proc * 12.25 + cop * 8.0) * st1.brick_cells
-        wb = (32.0 + 12.0 + 20.0) * voxels_local_of(f) + jac_bytes
-        work = {"bricks_per_pass": st1.bricks_per_pass, "bricks_processed_per_step": round(proc, 1),
-                "bricks_copied_per_step": round(cop, 1), "brick_cells": st1.brick_cells,
-                "bytes_per_step": wb, "achieved_gbs": round(wb / (ms * 1e-3 / args.steps) / 1e9, 1),
-                "frac": round(wb / (ms * 1e-3 / args.steps) / 1e9 / peak, 4)}
-
     voxels_local = nx * ny * f.slab[1]
-    roof, phases = kernel_roofline(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
+    value = voxels * args.steps / (ms * 1e-3)
+    t_step = ms * 1e-3 / args.steps
+    # bytes the step really needs (whole job): advect 32 + divergence 12 + gradient 20 per voxel + the Jacobi work
+    jb, proc, cop = jacobi_work_bytes(st0, st1, mask_bytes, voxels_local)
+    if world > 1:
+        t = torch.tensor([jb, proc, cop], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        jb, proc, cop = (float(v) for v in t.tolist())
+    work_bytes = 64.0 * voxels + jb / args.steps
+    work_gbs = work_bytes / t_step / 1e9
+    nominal_bpv = bytes_per_voxel_step(passes, mask_bytes)
+    nominal_gbs = nominal_bpv * voxels / t_step / 1e9
+
+    roof, phase_roof, phases = phase_rooflines(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            t = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi_pass")
-            roof["traffic"] = t
+            roof["traffic"] = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi")
         except Exception:
             pass
+    if st1.halo_overflow:
+        raise SystemExit("advection back-trace left the z-halo: raise h_adv")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -331,12 +349,19 @@ def run_ours(args):
                                 args.spinup, voxels * 44 / 2 ** 20),
                    "grid": list(grid), "parallelism": "z-slab x%d" % world, "fuse_t": fuse_t,
                    "sweeps_per_step": round(sweeps, 2), "jacobi_passes_per_step": round(passes, 2),
-                   "bytes_per_voxel_step": round(bpv, 2), "kernel_path": args.kernel_path},
-        "step_roofline": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
-                          "frac": round(step_gbs / peak, 4), "peak_source": peak_src,
-                          "definition": "bytes_step(T,S)*voxels/t_step, BASELINE.md §3"},
+                   "bytes_per_voxel_step": round(work_bytes / voxels, 2), "kernel_path": args.kernel_path,
+                   "jacobi_fused": int(st1.jacobi_fused), "bricks_relaxed_per_step": round(proc / args.steps, 1),
+                   "bricks_copied_per_step": round(cop / args.steps, 1), "brick_cells": int(st1.brick_cells)},
+        "step_roofline": {"bound": "hbm", "achieved": round(work_gbs, 1), "peak": peak * world, "unit": "GB/s",
+                          "frac": round(work_gbs / (peak * world), 4), "peak_source": peak_src,
+                          "definition": "(64 B x voxels + Jacobi bytes of the bricks actually relaxed/copied) / t_step",
+                          "nominal_bytes_step_formula": {
+                              "bytes_per_voxel": round(nominal_bpv, 2), "achieved": round(nominal_gbs, 1),
+                              "frac": round(nominal_gbs / (peak * world), 4),
+                              "note": "BASELINE.md formula 32+12+ceil(S/T)*12+20: assumes every pass touches every "
+                                      "voxel; frozen bricks are skipped here, so it over-counts the bytes moved"}},
         "roofline": roof,
-        "work_roofline": work,
+        "phase_roofline": phase_roof,
         "phase_ms": phases,
         "e2e": {"value": voxels * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_e2e / args.steps,
@@ -366,16 +391,20 @@ def run_ours(args):
         for _ in range(args.spinup):
             g.UpdateFrame(cdt); g.Simulate(stream.cuda_stream)
         cms, c0, c1 = timed_run(torch, dist, g, cdt, args.steps, args.warmup, 1, stream)
-        cp = (c1.total_passes - c0.total_passes) / args.steps
-        cb = bytes_per_voxel_step(cp, mask_bytes)
         cv = 256 ** 3
-        croof, cph = kernel_roofline(g, cdt, cv, peak, peak_src, 5, mask_bytes)
-        line["c3"] = {"workload": "3D 256^3 (BASELINE config 3)", "value": cv * args.steps / (cms * 1e-3),
-                      "ms_per_step": cms / args.steps, "jacobi_passes_per_step": round(cp, 2),
+        cjb, cproc, ccop = jacobi_work_bytes(c0, c1, mask_bytes, cv)
+        cwork = 64.0 * cv + cjb / args.steps
+        cnom = bytes_per_voxel_step((c1.total_passes - c0.total_passes) / args.steps, mask_bytes)
+        croof, cphase_roof, cph = phase_rooflines(g, cdt, cv, peak, peak_src, 5, mask_bytes)
+        ct = cms * 1e-3 / args.steps
+        line["c3"] = {"workload": "3D 256^3 (BASELINE config 3: roofline characterisation)",
+                      "value": cv * args.steps / (cms * 1e-3), "ms_per_step": cms / args.steps,
+                      "jacobi_passes_per_step": round((c1.total_passes - c0.total_passes) / args.steps, 2),
                       "sweeps_per_step": round((c1.total_sweeps - c0.total_sweeps) / args.steps, 2),
-                      "bytes_per_voxel_step": round(cb, 2),
-                      "step_roofline_frac": round(cb * cv / (cms * 1e-3 / args.steps) / 1e9 / peak, 4),
-                      "roofline": croof, "phase_ms": cph}
+                      "bytes_per_voxel_step": round(cwork / cv, 2),
+                      "step_roofline_frac": round(cwork / ct / 1e9 / peak, 4),
+                      "nominal_formula_frac": round(cnom * cv / ct / 1e9 / peak, 4),
+                      "roofline": croof, "phase_roofline": cphase_roof, "phase_ms": cph}
         g.close()
     f.close()
     if rank == 0:

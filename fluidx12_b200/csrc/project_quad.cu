@@ -48,37 +48,58 @@ __device__ __forceinline__ Rows rows_of(const Domain& d, int x0, int y, int z) {
     return r;
 }
 
+// z-marching: a thread owns the quad column (x0..x0+3, y) over kDivPlanes planes and keeps the z component of the
+// plane below and the whole texels of the centre plane in registers, so every texel is fetched from L2/HBM once
+// (plus the chunk's two end planes); only the y neighbours (rows y-1, y+1 of the centre plane, loaded a moment
+// earlier by the neighbouring threads of the CTA) and the two x-edge texels come through L1 again.
+constexpr int kDivPlanes = 16;
+
 __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const FrameParams* __restrict__ frame,
                                                               const uint2* __restrict__ vel,
                                                               float* __restrict__ rhs) {
     if (!(0.0f < frame->dt)) return;
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int z = d.z_own0 + blockIdx.z;
     if (x0 >= d.nx || y >= d.ny) return;
-    const Rows r = rows_of(d, x0, y, z);
-    const Quad8 c = load_quad8(vel, r.c), u = load_quad8(vel, r.u), dn = load_quad8(vel, r.d);
-    const Quad8 f = load_quad8(vel, r.f), b = load_quad8(vel, r.b);
-    const unsigned row = r.c - x0;
+    const int z_begin = d.z_own0 + blockIdx.z * kDivPlanes;
+    const int z_end = min(z_begin + kDivPlanes, d.z_own1);
+    const unsigned plane = (unsigned)d.nx * d.ny;
+    const unsigned row_c = (unsigned)y * d.nx + x0;
+    const unsigned row_u = (unsigned)(max(y, 1) - 1) * d.nx + x0;
+    const unsigned row_d = (unsigned)min(y + 1, d.ny - 1) * d.nx + x0;
+    const unsigned row0 = (unsigned)y * d.nx;
+    const int xl = max(x0, 1) - 1, xr = min(x0 + 4, d.nx - 1);
     const unsigned short* vs = reinterpret_cast<const unsigned short*>(vel);
-    // x component of the six texels x0-1 .. x0+4 (clamped at the faces)
-    const float vx[6] = {half_bits_to_float(__ldg(vs + 4 * (size_t)(row + r.xl))), h_lo(c.a.x), h_lo(c.a.z),
-                         h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(__ldg(vs + 4 * (size_t)(row + r.xr)))};
-    const float uy[4] = {h_hi(u.a.x), h_hi(u.a.z), h_hi(u.b.x), h_hi(u.b.z)};
-    const float dy[4] = {h_hi(dn.a.x), h_hi(dn.a.z), h_hi(dn.b.x), h_hi(dn.b.z)};
-    const float fz[4] = {h_lo(f.a.y), h_lo(f.a.w), h_lo(f.b.y), h_lo(f.b.w)};
-    const float bz[4] = {h_lo(b.a.y), h_lo(b.a.w), h_lo(b.b.y), h_lo(b.b.w)};
-    float out[4];
+
+    auto zoff = [&](int z) { return (unsigned)(z - d.z_first) * plane; };
+    // plane below the first one (clamped at the grid face) and the first centre plane
+    Quad8 below = load_quad8(vel, zoff(max(z_begin, 1) - 1) + row_c);
+    float fz[4] = {h_lo(below.a.y), h_lo(below.a.w), h_lo(below.b.y), h_lo(below.b.w)};
+    Quad8 c = load_quad8(vel, zoff(z_begin) + row_c);
+    for (int z = z_begin; z < z_end; ++z) {
+        const unsigned zc = zoff(z);
+        const Quad8 b = load_quad8(vel, zoff(min(z + 1, d.nz - 1)) + row_c);  // plane above (clamped)
+        const Quad8 u = load_quad8(vel, zc + row_u), dn = load_quad8(vel, zc + row_d);
+        const float vx[6] = {half_bits_to_float(__ldg(vs + 4 * (size_t)(zc + row0 + xl))), h_lo(c.a.x), h_lo(c.a.z),
+                             h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(__ldg(vs + 4 * (size_t)(zc + row0 + xr)))};
+        const float uy[4] = {h_hi(u.a.x), h_hi(u.a.z), h_hi(u.b.x), h_hi(u.b.z)};
+        const float dy[4] = {h_hi(dn.a.x), h_hi(dn.a.z), h_hi(dn.b.x), h_hi(dn.b.z)};
+        const float bz[4] = {h_lo(b.a.y), h_lo(b.a.w), h_lo(b.b.y), h_lo(b.b.w)};
+        float out[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float a = -vx[j] + vx[j + 2];
-        float s = -uy[j] + dy[j];
-        s = s + a;
-        const float cz = -fz[j] + bz[j];
-        s = cz + s;
-        out[j] = -0.5f * s;
+        for (int j = 0; j < 4; ++j) {
+            const float a = -vx[j] + vx[j + 2];
+            float s = -uy[j] + dy[j];
+            s = s + a;
+            const float cz = -fz[j] + bz[j];
+            s = cz + s;
+            out[j] = -0.5f * s;
+        }
+        *reinterpret_cast<float4*>(rhs + zc + row_c) = make_float4(out[0], out[1], out[2], out[3]);
+        // march: the centre plane becomes the plane below, the plane above becomes the centre
+        fz[0] = h_lo(c.a.y); fz[1] = h_lo(c.a.w); fz[2] = h_lo(c.b.y); fz[3] = h_lo(c.b.w);
+        c = b;
     }
-    *reinterpret_cast<float4*>(rhs + r.c) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables tab,
@@ -144,7 +165,8 @@ bool quad_kernels_supported(const Domain& d) { return d.nz > 1 && (d.nx % 8) == 
 
 void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs,
                             cudaStream_t stream) {
-    divergence_quad_kernel<<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, frame, (const uint2*)vel, rhs);
+    const dim3 grid((d.nx / 4 + 31) / 32, (d.ny + 7) / 8, (d.z_own1 - d.z_own0 + kDivPlanes - 1) / kDivPlanes);
+    divergence_quad_kernel<<<grid, dim3(32, 8), 0, stream>>>(d, frame, (const uint2*)vel, rhs);
 }
 
 void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
