@@ -99,3 +99,32 @@ def test_slab_plan():
     assert one.nz_alloc == 128 and not one.advect
     with pytest.raises(ValueError):
         halo_plan(64, 0, 8, fuse_t=4)
+
+
+def test_cpp_mirror_header_compiles_and_fails_loudly(fx, tmp_path):
+    """include/fluid.hpp (reference member names over the C ABI) builds with plain g++ and, like the library,
+    refuses to run without a GPU instead of falling back."""
+    import torch
+    src = tmp_path / "use_fluid.cpp"
+    src.write_text('''
+#include <cstdio>
+#include "fluid.hpp"
+int main() {
+    fluidx_b200::Fluid fluid;
+    const bool ok = fluid.Init({32, 32, 32});           // FluidX12.cpp:197-201
+    if (!ok) { std::printf("INIT_FAILED %s\\n", fluid.last_error().c_str()); return 3; }
+    fluid.UpdateFrame(fluid.TimeStepForGrid(), 0);      // FluidX12.cpp:266-267, :282
+    fluid.Simulate(nullptr, 0);                          // FluidX12.cpp:536
+    std::printf("STEP_OK parity=%d rc=%d\\n", (int)fluid.frameParity(), fxb_sync(fluid.handle()));
+    return 0;
+}
+''')
+    exe = tmp_path / "use_fluid"
+    libdir = os.path.dirname(fx.lib_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lfluidx_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "STEP_OK parity=1 rc=0" in out.stdout
+    else:
+        assert out.returncode == 3 and "INIT_FAILED" in out.stdout and "CPU fallback" in out.stdout
