@@ -10,7 +10,8 @@
 //   * (i + 0.5) / N comes from per-axis tables (three IEEE divisions per voxel otherwise);
 //   * taps that all fall inside the grid (the common case) take a fast path with 32-bit offsets and no
 //     sampler-addressing arithmetic; MIRROR/CLAMP wrapping lives in a cold out-of-line path;
-//   * the 14 lerps of the 7 used channels run as packed FADD2/FFMA2 on (x,y) and (z,w) pairs.
+//   * the 14 lerps of the 7 used channels run as packed FADD2/FFMA2 on (x,y) and (z,w) pairs;
+//   * a back-trace that lands exactly on a texel centre (still-quiescent voxels) needs 2 loads, not 16.
 // Algorithmic traffic: 32 B/voxel (velocity in 8 + colour in 8 + velocity out 8 + colour out 8).
 #include "common.cuh"
 #include "kernels.h"
@@ -112,8 +113,28 @@ advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, c
         o[0] = r00 + xs.x; o[1] = r00 + xs.y; o[2] = r10 + xs.x; o[3] = r10 + xs.y;
         o[4] = r01 + xs.x; o[5] = r01 + xs.y; o[6] = r11 + xs.x; o[7] = r11 + xs.y;
     }
-    Pair4 u = gather(vel_in, o, fx, fy, fz);
-    Pair4 c = gather(col_in, o, fx, fy, fz);
+    // Exact-texel fast path.  When the back-trace lands exactly on a texel centre (all three weights are 0: in
+    // practice the voxels the flow has not reached, u = 0) every lerp is fma(0, b - a, a) = a, i.e. the fetch
+    // returns the first tap unchanged, so 2 loads replace 16.  The one case where fma(0, b - a, a) != a bitwise is
+    // a = -0 (the sum takes the sign of 0 * (b - a)); such texels take the general path.
+    Pair4 u, c;
+    bool exact = inside && fx == 0.0f && fy == 0.0f && fz == 0.0f;
+    if (exact) {
+        const uint2 rv = __ldg(vel_in + o[0]), rc = __ldg(col_in + o[0]);
+        auto neg_zero = [](unsigned w) { return (w & 0xffffu) == 0x8000u || (w >> 16) == 0x8000u; };
+        if (neg_zero(rv.x) || neg_zero(rv.y) || neg_zero(rc.x) || neg_zero(rc.y)) {
+            exact = false;
+        } else {
+            u.lo = __half22float2(*reinterpret_cast<const __half2*>(&rv.x));
+            u.hi = __half22float2(*reinterpret_cast<const __half2*>(&rv.y));
+            c.lo = __half22float2(*reinterpret_cast<const __half2*>(&rc.x));
+            c.hi = __half22float2(*reinterpret_cast<const __half2*>(&rc.y));
+        }
+    }
+    if (!exact) {
+        u = gather(vel_in, o, fx, fy, fz);
+        c = gather(col_in, o, fx, fy, fz);
+    }
 
     // Emitter (CSAdvect.hlsl:57-68).  Outside the table's box the basis is below exp(-4) by construction.
     if (x >= em.x0 && x < em.x1 && y >= em.y0 && y < em.y1 && z >= em.z0 && z < em.z1) {

@@ -123,7 +123,7 @@ template <class S>
 __global__ void __launch_bounds__(256) copy_frozen_bricks_kernel(const FrameParams* __restrict__ frame,
                                                                  StepState* __restrict__ state, float* p0, float* p1,
                                                                  unsigned char* m0, unsigned char* m1,
-                                                                 const WorkLists W, const PassParams P) {
+                                                                 const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
     FXB_SHAPE_CONSTANTS(S);
     if (!(0.0f < frame->dt)) return;
     if (P.pass == 0 || (!P.run_all && state->active_after[P.pass * T - 1] == 0ull)) return;
@@ -209,7 +209,7 @@ __device__ __forceinline__ void relax_tail(const float4 head, const float4 hi, c
 // Relaxes one brick: T fused sweeps over its 120 x (32-2T) x bz output cells (see the file header).
 // Out of line so that the persistent work loop around it does not lengthen any live range of the marching loop.
 template <class S>
-__device__ __noinline__ void relax_brick(const CUtensorMap* map_in, const CUtensorMap* map_rhs_p,
+__device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUtensorMap* map_rhs_p,
                                          float* __restrict__ p_out, const unsigned char* __restrict__ m_in,
                                          unsigned char* __restrict__ m_out, StepState* __restrict__ state,
                                          const WorkLists& W, const PassParams& P, const int brick, const int levels,
@@ -279,17 +279,17 @@ __device__ __noinline__ void relax_brick(const CUtensorMap* map_in, const CUtens
     };
     // Freeze flags of the level-0 planes (the previous pass's output mask).  The raw bytes are fetched two
     // iterations ahead and only decoded when their plane is consumed, so the load latency stays hidden.
-    auto fetch_flag_bytes = [&](int z, unsigned char (&raw)[kRows]) {
+    auto fetch_flag_bytes = [&](int z, unsigned (&raw)[kRows]) {
         if (P.pass == 0 || z >= zl1) return;
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
             if ((dom_bits >> (4 * r)) & 1u) raw[r] = __ldg(m_in + ((size_t)z * P.ny + (gyb + r)) * nxb + (gx >> 3));
     };
-    auto decode_flags = [&](const unsigned char (&raw)[kRows]) -> unsigned {
+    auto decode_flags = [&](const unsigned (&raw)[kRows]) -> unsigned {
         if (P.pass == 0) return dom_bits;
         unsigned f = 0;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) f |= (((unsigned)raw[r] >> (gx & 4)) & 0xFu) << (4 * r);
+        for (int r = 0; r < kRows; ++r) f |= ((raw[r] >> (gx & 4)) & 0xFu) << (4 * r);
         return f & dom_bits;
     };
 
@@ -313,7 +313,7 @@ __device__ __noinline__ void relax_brick(const CUtensorMap* map_in, const CUtens
 #pragma unroll
         for (int i = 0; i < kPrefetch; ++i) issue_bundle(zl0 + i);
     }
-    unsigned char raw_flags[2][kRows];  // [parity of the plane's iteration]
+    unsigned raw_flags[2][kRows];  // [parity of the plane's iteration]
 #pragma unroll
     for (int r = 0; r < kRows; ++r) raw_flags[0][r] = raw_flags[1][r] = 0;
     fetch_flag_bytes(zl0, raw_flags[0]);
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
 jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
                    const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
                    StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0, unsigned char* m1,
-                   const WorkLists W, const PassParams P) {
+                   const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
     FXB_SHAPE_CONSTANTS(S);
     if (!(0.0f < frame->dt)) return;
     const int s0 = P.pass * T;  // sweeps completed before this pass
@@ -545,20 +545,19 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     extern __shared__ __align__(1024) float sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::kFloats);  // [kPrefetch + 1]
     unsigned* s_cnt = reinterpret_cast<unsigned*>(bars + 6);               // [T]
-    int* s_work = reinterpret_cast<int*>(s_cnt + 4);
     if ((smem_u32(sm) & 127u) != 0u) __trap();
 
     // Work list of this pass: every brick in pass 0, afterwards only the bricks that still hold an active cell.
     // Bricks that froze in the previous pass are on the copy list instead (copy_frozen_bricks_kernel).
-    // CTAs are persistent (one per SM) and pull entries with an atomic counter.
+    // CTAs are persistent (kCtasPerSm per SM) and take list entries round-robin, so that the entry index — and in
+    // pass 0 the brick coordinates — stay warp-uniform values.
     const int n_work = P.pass == 0 ? P.ntx * P.nty * P.nzc : W.relax_count[P.pass];
     const int* __restrict__ list_in = W.relax[P.pass & 1];
     bool bars_live = false;
 
-    for (;;) {
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
         __syncthreads();  // the previous brick is completely finished (shared memory and barriers are idle)
         if (tid == 0) {
-            *s_work = atomicAdd(&W.relax_head[P.pass], 1);
             if (bars_live) {
 #pragma unroll
                 for (int i = 0; i <= kPrefetch; ++i)
@@ -571,8 +570,6 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         bars_live = true;
         if (tid < T) s_cnt[tid] = 0;
         __syncthreads();
-        const int work = *s_work;
-        if (work >= n_work) break;
         const int brick = P.pass == 0 ? work : list_in[work];
         relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, brick, levels, s0);
     }
