@@ -214,7 +214,7 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                     const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + npass) & 1], s->plane_voxels() * 4, 1}};
                     s->comm.exchange(d, f, 1, st);
                 }
-                launches = 2 * npass;  // npass relax kernels + (npass - 1) copy kernels + finish
+                launches = npass + 1;  // npass fused passes + finish
             } else {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,

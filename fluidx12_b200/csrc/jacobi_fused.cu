@@ -118,51 +118,39 @@ struct WorkLists {
 
 // A brick whose cells all froze during pass p-1 holds its final values in that pass's output buffer only.  Pass p
 // copies its own region once into the other buffer (and clears the other mask buffer), after which the brick is
-// final in both ping-pong buffers and is never touched again in this frame.  Pure streaming: 8 B/cell.
+// final in both ping-pong buffers and is never touched again in this frame.  Pure streaming (8 B/cell), eight
+// independent 16-byte loads in flight per thread.
 template <class S>
-__global__ void __launch_bounds__(256) copy_frozen_bricks_kernel(const FrameParams* __restrict__ frame,
-                                                                 StepState* __restrict__ state, float* p0, float* p1,
-                                                                 unsigned char* m0, unsigned char* m1,
-                                                                 const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
+__device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, float* __restrict__ p_out,
+                                               unsigned char* __restrict__ m_out, const PassParams& P,
+                                               const int brick) {
     FXB_SHAPE_CONSTANTS(S);
-    if (!(0.0f < frame->dt)) return;
-    if (P.pass == 0 || (!P.run_all && state->active_after[P.pass * T - 1] == 0ull)) return;
-    const int sel = (state->p_cur + P.pass) & 1;
-    const float* __restrict__ p_in = sel ? p1 : p0;
-    float* __restrict__ p_out = sel ? p0 : p1;
-    unsigned char* __restrict__ m_out = (P.pass & 1) ? m0 : m1;
-    const int n = W.copy_count[P.pass];
-    const int* __restrict__ list = W.copy[P.pass & 1];
     constexpr int kOutY = kTileY - 2 * T;
     const int tid = threadIdx.x, nxb = P.nx >> 3;
-    for (int w = blockIdx.x; w < n; w += gridDim.x) {
-        const int brick = list[w];
-        const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc_idx = brick / (P.ntx * P.nty);
-        const int zs = P.z_out0 + zc_idx * P.bz, ze = min(zs + P.bz, P.z_out1);
-        const int x_lo = tx * kOutX, y_lo = ty * kOutY;
-        const int rows = min(kOutY, P.ny - y_lo), planes = ze - zs;
-        const int qpr = min(kOutX, P.nx - x_lo) >> 2;  // float4 per row inside the grid
-        const int total = planes * rows * qpr;
-        for (int base = tid; base < total; base += 8 * 256) {
-            float4 v[8];
-            size_t at[8];
+    const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc_idx = brick / (P.ntx * P.nty);
+    const int zs = P.z_out0 + zc_idx * P.bz, ze = min(zs + P.bz, P.z_out1);
+    const int x_lo = tx * kOutX, y_lo = ty * kOutY;
+    const int rows = min(kOutY, P.ny - y_lo), planes = ze - zs;
+    const int qpr = min(kOutX, P.nx - x_lo) >> 2;  // float4 per row inside the grid
+    const int total = planes * rows * qpr;
+    for (int base = tid; base < total; base += 8 * kThreads) {
+        float4 v[8];
+        size_t at[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = base + u * 256;
-                const int xq = i % qpr, rz = i / qpr;
-                at[u] = ((size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows)) * P.nx + x_lo + 4 * xq;
-                if (i < total) v[u] = __ldcs(reinterpret_cast<const float4*>(p_in + at[u]));
-            }
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * kThreads;
+            const int xq = i % qpr, rz = i / qpr;
+            at[u] = ((size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows)) * P.nx + x_lo + 4 * xq;
+            if (i < total) v[u] = __ldcs(reinterpret_cast<const float4*>(p_in + at[u]));
+        }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (base + u * 256 < total) *reinterpret_cast<float4*>(p_out + at[u]) = v[u];
-        }
-        const int bpr = qpr >> 1;  // mask bytes per row
-        for (int i = tid; i < planes * rows * bpr; i += 256) {
-            const int xb = i % bpr, rz = i / bpr;
-            m_out[((size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows)) * nxb + (x_lo >> 3) + xb] = 0;
-        }
-        if (tid == 0) atomicAdd(&state->bricks_copied, 1ull);
+        for (int u = 0; u < 8; ++u)
+            if (base + u * kThreads < total) *reinterpret_cast<float4*>(p_out + at[u]) = v[u];
+    }
+    const int bpr = qpr >> 1;  // mask bytes per row
+    for (int i = tid; i < planes * rows * bpr; i += kThreads) {
+        const int xb = i % bpr, rz = i / bpr;
+        m_out[((size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows)) * nxb + (x_lo >> 3) + xb] = 0;
     }
 }
 
@@ -530,13 +518,19 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                    StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0, unsigned char* m1,
                    const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
     FXB_SHAPE_CONSTANTS(S);
-    if (!(0.0f < frame->dt)) return;
     const int s0 = P.pass * T;  // sweeps completed before this pass
-    if (P.pass > 0 && !P.run_all && state->active_after[s0 - 1] == 0ull) return;
+    // independent loads first (one round trip instead of a chain), then the decisions
+    const float dt = frame->dt;
+    const int p_cur = state->p_cur;
+    const unsigned long long still = P.pass > 0 ? state->active_after[s0 - 1] : 1ull;
+    const int n_relax = W.relax_count[P.pass], n_copy = W.copy_count[P.pass];
+    if (!(0.0f < dt)) return;
+    if (P.pass > 0 && !P.run_all && still == 0ull) return;
     const int levels = min(T, P.levels_total - s0);
 
-    const int sel = (state->p_cur + P.pass) & 1;
+    const int sel = (p_cur + P.pass) & 1;
     const CUtensorMap* map_in = sel ? &map_p1 : &map_p0;
+    const float* p_in = sel ? p1 : p0;
     float* p_out = sel ? p0 : p1;
     const unsigned char* m_in = (P.pass & 1) ? m1 : m0;
     unsigned char* m_out = (P.pass & 1) ? m0 : m1;
@@ -547,11 +541,16 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     unsigned* s_cnt = reinterpret_cast<unsigned*>(bars + 6);               // [T]
     if ((smem_u32(sm) & 127u) != 0u) __trap();
 
-    // Work list of this pass: every brick in pass 0, afterwards only the bricks that still hold an active cell.
-    // Bricks that froze in the previous pass are on the copy list instead (copy_frozen_bricks_kernel).
-    // CTAs are persistent (kCtasPerSm per SM) and take list entries round-robin, so that the entry index — and in
-    // pass 0 the brick coordinates — stay warp-uniform values.
-    const int n_work = P.pass == 0 ? P.ntx * P.nty * P.nzc : W.relax_count[P.pass];
+    // Work lists of this pass: every brick in pass 0; afterwards the bricks that froze in the previous pass (one
+    // copy each) and the bricks that still hold an active cell (relaxed again).  CTAs are persistent
+    // (kCtasPerSm per SM) and take list entries round-robin, so that the entry index — and in pass 0 the brick
+    // coordinates — stay warp-uniform values.
+    if (P.pass > 0) {
+        const int* __restrict__ copy_list = W.copy[P.pass & 1];
+        for (int w = blockIdx.x; w < n_copy; w += gridDim.x) copy_frozen_brick<S>(p_in, p_out, m_out, P, copy_list[w]);
+        if (tid == 0 && blockIdx.x == 0 && n_copy) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
+    }
+    const int n_work = P.pass == 0 ? P.ntx * P.nty * P.nzc : n_relax;
     const int* __restrict__ list_in = W.relax[P.pass & 1];
     bool bars_live = false;
 
@@ -629,10 +628,6 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
     W.copy[0] = J.work_list[0] + nbricks; W.copy[1] = J.work_list[1] + nbricks;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np; W.relax_head = J.work_count + 2 * np;
-    if (pass > 0) {
-        const int cgrid = nbricks < 8 * J.num_sms ? nbricks : 8 * J.num_sms;
-        copy_frozen_bricks_kernel<S><<<cgrid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P);
-    }
     jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
         *reinterpret_cast<const CUtensorMap*>(J.map_p[0]), *reinterpret_cast<const CUtensorMap*>(J.map_p[1]),
         *reinterpret_cast<const CUtensorMap*>(J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P);
