@@ -64,6 +64,11 @@ __device__ __noinline__ int2 wrapped_pair(float t, int w, int clamp_mode) {
 
 }  // namespace
 
+// WHAT: 3 = velocity and colour in one pass; 1 = velocity only; 2 = colour only.  The colour field is not an
+// input of the projection, so the step advects it on a side branch of the graph, under the Jacobi passes.
+enum { kAdvectVelocity = 1, kAdvectColour = 2, kAdvectBoth = 3 };
+
+template <int WHAT>
 __global__ void __launch_bounds__(512, 2)
 advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in,
               uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
@@ -117,10 +122,14 @@ advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, c
     // practice the voxels the flow has not reached, u = 0) every lerp is fma(0, b - a, a) = a, i.e. the fetch
     // returns the first tap unchanged, so 2 loads replace 16.  The one case where fma(0, b - a, a) != a bitwise is
     // a = -0 (the sum takes the sign of 0 * (b - a)); such texels take the general path.
+    constexpr bool kVel = (WHAT & kAdvectVelocity) != 0, kCol = (WHAT & kAdvectColour) != 0;
     Pair4 u, c;
+    u.lo = u.hi = c.lo = c.hi = make_float2(0.0f, 0.0f);
     bool exact = inside && fx == 0.0f && fy == 0.0f && fz == 0.0f;
     if (exact) {
-        const uint2 rv = __ldg(vel_in + o[0]), rc = __ldg(col_in + o[0]);
+        uint2 rv = make_uint2(0u, 0u), rc = make_uint2(0u, 0u);
+        if (kVel) rv = __ldg(vel_in + o[0]);
+        if (kCol) rc = __ldg(col_in + o[0]);
         auto neg_zero = [](unsigned w) { return (w & 0xffffu) == 0x8000u || (w >> 16) == 0x8000u; };
         if (neg_zero(rv.x) || neg_zero(rv.y) || neg_zero(rc.x) || neg_zero(rc.y)) {
             exact = false;
@@ -132,8 +141,8 @@ advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, c
         }
     }
     if (!exact) {
-        u = gather(vel_in, o, fx, fy, fz);
-        c = gather(col_in, o, fx, fy, fz);
+        if (kVel) u = gather(vel_in, o, fx, fy, fz);
+        if (kCol) c = gather(col_in, o, fx, fy, fz);
     }
 
     // Emitter (CSAdvect.hlsl:57-68).  Outside the table's box the basis is below exp(-4) by construction.
@@ -150,33 +159,48 @@ advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, c
             } else {
                 fx_ = 0.0f; fy_ = basis * 48.0f; fz_ = 0.0f;
             }
-            u.lo.x = __fmaf_rn(fx_, dt, u.lo.x);
-            u.lo.y = __fmaf_rn(fy_, dt, u.lo.y);
-            u.hi.x = __fmaf_rn(fz_, dt, u.hi.x);
-            const float bdt = basis * dt;
-            c.lo.x = __saturatef(__fmaf_rn(bdt, 8.0f, c.lo.x));
-            c.lo.y = __saturatef(__fmaf_rn(bdt, 16.0f, c.lo.y));
-            c.hi.x = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.x));
-            c.hi.y = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.y));
+            if (kVel) {
+                u.lo.x = __fmaf_rn(fx_, dt, u.lo.x);
+                u.lo.y = __fmaf_rn(fy_, dt, u.lo.y);
+                u.hi.x = __fmaf_rn(fz_, dt, u.hi.x);
+            }
+            if (kCol) {
+                const float bdt = basis * dt;
+                c.lo.x = __saturatef(__fmaf_rn(bdt, 8.0f, c.lo.x));
+                c.lo.y = __saturatef(__fmaf_rn(bdt, 16.0f, c.lo.y));
+                c.hi.x = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.x));
+                c.hi.y = __saturatef(__fmaf_rn(bdt, 40.0f, c.hi.y));
+            }
         }
     }
 
     const float atten = fmaxf(__fmaf_rn(-dt, 0.200000003f, 1.0f), 0.0f);
     const float2 at2 = make_float2(atten, atten);
-    u.lo = mul2(u.lo, at2);
-    c.lo = mul2(c.lo, at2);
-    c.hi = mul2(c.hi, at2);
-    vel_out[self] = pack_texel4(u.lo.x, u.lo.y, u.hi.x * atten, 0.0f);
-    col_out[self] = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
+    if (kVel) {
+        u.lo = mul2(u.lo, at2);
+        vel_out[self] = pack_texel4(u.lo.x, u.lo.y, u.hi.x * atten, 0.0f);
+    }
+    if (kCol) {
+        c.lo = mul2(c.lo, at2);
+        c.hi = mul2(c.hi, at2);
+        col_out[self] = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
+    }
 }
 
+// what: 1 = velocity only, 2 = colour only, 3 = both (see the enum above)
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
-                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state,
+                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int what,
                    cudaStream_t stream) {
     const dim3 block(32, 4, 4);
     const dim3 grid((d.nx + 31) / 32, (d.ny + 3) / 4, (d.z_own1 - d.z_own0 + 3) / 4);
-    advect_kernel<<<grid, block, 0, stream>>>(d, tab, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
-                                              (uint2*)vel_out, em, clamp_mode, state);
+    auto* v = (const uint2*)vel_in;
+    auto *c0 = (uint2*)col[0], *c1 = (uint2*)col[1], *vo = (uint2*)vel_out;
+    if (what == kAdvectVelocity)
+        advect_kernel<kAdvectVelocity><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
+    else if (what == kAdvectColour)
+        advect_kernel<kAdvectColour><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
+    else
+        advect_kernel<kAdvectBoth><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
 }
 
 }  // namespace fxb

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,6 +70,10 @@ struct fxb_sim {
     fxb::StepState* d_state = nullptr;
 
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // colour advection branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool overlap_colour = false;  // measured slower on B200 (profiles/README.md); FXB_OVERLAP_COLOUR=1 enables it
+    bool fork_colour_now = false;  // set by enqueue_step: the Jacobi phase should fork the colour branch
     cudaStream_t last_stream = nullptr;
     // One captured graph per (frame parity, pressure-buffer parity): both select pointers that the halo exchange
     // of the multi-GPU step needs on the host side.  Single GPU uses slot [0][0] only (its kernels select on device).
@@ -159,6 +164,8 @@ int build_axis_tables(fxb_sim* s) {
 
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 
+void fork_colour(fxb_sim* s, cudaStream_t st);
+
 // Enqueues one phase of the step; returns the number of kernels launched.
 int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
     const fxb::Domain& d = s->dom;
@@ -172,7 +179,7 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             }
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
             fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
-                               s->d_state, st);
+                               s->d_state, 3, st);
             launches = 1;
             break;
         case PH_DIVERGENCE:
@@ -202,6 +209,7 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                     }
                     fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
                                                   s->cfg.early_exit, s->multi(), st);
+                    if (s->fork_colour_now && (k == 1 || k == npass - 1)) fork_colour(s, st);
                 }
                 if (mg) {
                     // freeze counters are per rank: sum them so that s_exec is the global figure; every rank runs
@@ -235,9 +243,39 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
     return launches;
 }
 
+void fork_colour(fxb_sim* s, cudaStream_t st) {
+    cudaEventRecord(s->ev_fork, st);
+    cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
+    fxb::launch_advect(s->dom, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
+                       s->d_state, 2, s->side_stream);
+    cudaEventRecord(s->ev_join, s->side_stream);
+    s->fork_colour_now = false;
+}
+
+// The whole step.  The colour field is not an input of the projection (CSProject3D reads velocity and pressure
+// only), so its advection runs on a side stream — a parallel branch of the captured graph — under the divergence and
+// the latency-bound Jacobi passes, and is joined before the gradient kernel overwrites vel[0] (its back-trace input).
 int enqueue_step(fxb_sim* s, cudaStream_t st) {
-    int launches = 0;
-    for (int ph = 0; ph < PH_COUNT; ++ph) launches += enqueue_phase(s, ph, st);
+    if (!s->overlap_colour) {
+        int launches = 0;
+        for (int ph = 0; ph < PH_COUNT; ++ph) launches += enqueue_phase(s, ph, st);
+        return launches;
+    }
+    const fxb::Domain& d = s->dom;
+    if (s->multi()) {  // both halo exchanges stay on the main stream: one NCCL communicator, one order on every rank
+        const fxb::HaloField f[2] = {{s->vel[0], s->plane_voxels() * 8, s->h_adv + 1},
+                                     {s->col[!s->parity], s->plane_voxels() * 8, s->h_adv + 1}};
+        s->comm.exchange(d, f, 2, st);
+    }
+    fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode, s->d_state,
+                       1, st);
+    int launches = 2;
+    launches += enqueue_phase(s, PH_DIVERGENCE, st);
+    s->fork_colour_now = true;  // PH_JACOBI forks the colour branch after its second pass (the heavy ones are over)
+    launches += enqueue_phase(s, PH_JACOBI, st);
+    if (s->fork_colour_now) fork_colour(s, st);  // no fused passes on this grid: fork here
+    cudaStreamWaitEvent(st, s->ev_join, 0);
+    launches += enqueue_phase(s, PH_GRADIENT, st);
     return launches;
 }
 
@@ -382,7 +420,14 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (e == cudaSuccess) e = cudaMemset(s->d_frame, 0, sizeof(fxb::FrameParams));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_state, sizeof(fxb::StepState));
     if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, sizeof(fxb::StepState));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // the latency-critical chain (Jacobi passes) outranks the colour branch that fills the idle SMs
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->own_stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    if (getenv("FXB_OVERLAP_COLOUR")) s->overlap_colour = true;
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess)
         return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));
@@ -467,6 +512,9 @@ void fxb_destroy(fxb_sim* s) {
     for (int i = 0; i < 8; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
 }
 
@@ -586,6 +634,14 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
     }
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
+}
+
+int fxb_get_freeze_histogram(fxb_sim* s, uint64_t* out, int n) {
+    if (!s || !out || n < 0 || n > 128) return fail(FXB_ERR_INVALID, "fxb_get_freeze_histogram: bad argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    FXB_CUDA(cudaMemcpy(out, s->d_state->active_after, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return FXB_OK;
 }
 
 int fxb_profile_step(fxb_sim* s, float* ms, int n) {

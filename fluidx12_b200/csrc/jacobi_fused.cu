@@ -330,8 +330,15 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
         constexpr int MID = PH ^ 1;               // slot of the centre plane
         constexpr bool FACE = decltype(face)::value;
         const int it = k - zl0;
+#ifdef FXB_TIMING
+#define FXB_MARK(m) if (tid == 32 && blockIdx.x == 0 && it < 16) state->active_after[32 + 6 * it + (m)] = clock64()
+#else
+#define FXB_MARK(m)
+#endif
+        FXB_MARK(0);
         if (tid == 0) issue_bundle(k + kPrefetch);
         if (k <= zl1) mbar_wait(&bars[it % (kPrefetch + 1)], (uint32_t)(it / (kPrefetch + 1)) & 1u);
+        FXB_MARK(1);
 
         float4 head[2][kRows];  // relax_head results of the level being finished and of the next one
         bool any[T + 2];
@@ -459,14 +466,18 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
             for (int r = 0; r < kRows; ++r) q[0][PH][r] = q[0][MID][r];
             fl[0][PH] = fl[0][MID];
         }
+        FXB_MARK(2);
         if constexpr (T >= 2) do_head(std::integral_constant<int, 2>{});
         do_tail(std::integral_constant<int, 1>{});
+        FXB_MARK(3);
         if constexpr (T >= 3) do_head(std::integral_constant<int, 3>{});
         if constexpr (T >= 2) do_tail(std::integral_constant<int, 2>{});
         if constexpr (T >= 4) do_head(std::integral_constant<int, 4>{});
         if constexpr (T >= 3) do_tail(std::integral_constant<int, 3>{});
         if constexpr (T >= 4) do_tail(std::integral_constant<int, 4>{});
+        FXB_MARK(4);
         __syncthreads();
+        FXB_MARK(5);
     };
 
     {

@@ -9,7 +9,7 @@ namespace fxb {
 
 // advect.cu
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
-                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state,
+                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int what,
                    cudaStream_t stream);
 
 // project_simple.cu — one kernel per logical pass (cross-check path, kernel_path = 1)

@@ -136,6 +136,12 @@ class Fluid:
         B.check(B.lib().fxb_get_stats(self._handle(), C.byref(st)))
         return st
 
+    def freeze_histogram(self, n: int = 64) -> np.ndarray:
+        """Cells still active after sweep k+1 of the last step, k < n (the oracle's active_hist shifted by one)."""
+        h = np.zeros(n, np.uint64)
+        B.check(B.lib().fxb_get_freeze_histogram(self._handle(), h.ctypes.data_as(C.c_void_p), n))
+        return h
+
     def profile_step(self):
         """One un-graphed step timed per phase: dict of milliseconds."""
         ms = (C.c_float * 6)()

@@ -121,6 +121,10 @@ int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void*
 /* Reads back the device-side counters of the last step (synchronises the handle's stream). */
 int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 
+/* Freeze histogram of the last step: out[k] = cells still active after sweep k+1 (this rank; global after the
+ * all-reduce when nranks > 1), k < n <= 128.  The oracle reports the same numbers. */
+int fxb_get_freeze_histogram(fxb_sim* sim, uint64_t* out, int n);
+
 /* Runs one step un-graphed with CUDA events between phases.  ms[0]=advect, ms[1]=divergence,
  * ms[2]=all Jacobi passes, ms[3]=gradient-subtract, ms[4]=halo exchange (0 when nranks == 1),
  * ms[5]=whole step.  The caller must have called fxb_update_frame. */
