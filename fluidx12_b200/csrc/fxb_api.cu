@@ -82,6 +82,7 @@ struct fxb_sim {
     fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
     int halo = 0;             // halo planes allocated on interior faces
     int h_adv = 0;            // advection halo (back-trace reach in planes)
+    int jacobi_group = 4;     // multi-GPU: fused passes between two pressure-halo exchanges
     int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
@@ -197,18 +198,28 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
                 const bool mg = s->multi() && s->dt > 0.0f;
-                if (mg) {  // the right-hand side is constant over the sweeps: one exchange of T planes
-                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, s->fuse_t}};
+                // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
+                // between, pass j of a group also relaxes the (G-1-j)*T halo planes next to each interior face.
+                const int G = s->multi() ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
+                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the group
+                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * s->fuse_t}};
                     s->comm.exchange(d, f, 1, st);
                 }
                 for (int k = 0; k < npass; ++k) {
-                    if (mg) {  // T planes of the pass's input pressure (and freeze flags) from both neighbours
-                        const fxb::HaloField f[2] = {{s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, s->fuse_t},
-                                                     {s->jac.mask[k & 1], s->plane_voxels() / 8, s->fuse_t}};
-                        s->comm.exchange(d, f, k == 0 ? 1 : 2, st);
+                    int ext_lo = 0, ext_hi = 0;
+                    if (mg) {
+                        if (k % G == 0 && !getenv("FXB_DEBUG_NO_JHALO")) {
+                            const fxb::HaloField f[2] = {
+                                {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * s->fuse_t},
+                                {s->jac.mask[k & 1], s->plane_voxels() / 8, G * s->fuse_t}};
+                            s->comm.exchange(d, f, k == 0 ? 1 : 2, st);
+                        }
+                        const int ext = (G - 1 - k % G) * s->fuse_t;
+                        ext_lo = s->cfg.rank > 0 ? ext : 0;
+                        ext_hi = s->cfg.rank < s->cfg.nranks - 1 ? ext : 0;
                     }
                     fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
-                                                  s->cfg.early_exit, s->multi(), st);
+                                                  s->cfg.early_exit, s->multi(), ext_lo, ext_hi, st);
                     if (s->fork_colour_now && (k == 1 || k == npass - 1)) fork_colour(s, st);
                 }
                 if (mg) {
@@ -388,7 +399,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
         const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
         s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;
-        s->halo = std::max(s->h_adv + 1, fuse);
+        if (const char* e = getenv("FXB_JACOBI_GROUP")) s->jacobi_group = std::max(1, atoi(e));
+        s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
         int thinnest = nz;
         for (int q = 0; q < R; ++q) thinnest = std::min(thinnest, (q + 1) * nz / R - q * nz / R);
         if (R > nz || s->halo > thinnest) {

@@ -106,6 +106,7 @@ struct PassParams {
     int levels_total;      // ITER
     int early_exit;
     int run_all;           // multi-GPU: never end the solve on this rank's own freeze counters
+    int ext_lo, ext_hi;    // multi-GPU: planes below / above the owned range to relax redundantly in this pass
 };
 
 struct WorkLists {
@@ -200,8 +201,8 @@ template <class S>
 __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUtensorMap* map_rhs_p,
                                          float* __restrict__ p_out, const unsigned char* __restrict__ m_in,
                                          unsigned char* __restrict__ m_out, StepState* __restrict__ state,
-                                         const WorkLists& W, const PassParams& P, const int brick, const int levels,
-                                         const int s0) {
+                                         const WorkLists& W, const PassParams& P, const int brick, const int tx,
+                                         const int ty, const int zs, const int ze, const int levels, const int s0) {
     FXB_SHAPE_CONSTANTS(S);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kOutY = kTileY - 2 * T;
@@ -212,12 +213,10 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::kFloats);  // [kPrefetch + 1]
     unsigned* s_cnt = reinterpret_cast<unsigned*>(bars + 6);               // [T]
 
-    const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc_idx = brick / (P.ntx * P.nty);
-
+    // brick >= 0: a brick of this rank's own planes (tracked in the work lists and freeze counters);
+    // brick < 0: planes of the z-halo relaxed redundantly between two exchanges (multi-GPU): never listed or counted.
     const int gx0 = tx * kOutX - kHaloX;
     const int gy0 = ty * kOutY - T;
-    const int zs = P.z_out0 + zc_idx * P.bz;
-    const int ze = min(zs + P.bz, P.z_out1);
     const int nxb = P.nx >> 3;  // mask bytes per row
 
     const int gx = gx0 + 4 * lane;
@@ -510,6 +509,7 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
         if (lane == 0 && v) atomicAdd(&s_cnt[l - 1], v);
     }
     __syncthreads();
+    if (brick < 0) return;
     if (tid < T && tid < levels) {
         const unsigned v = s_cnt[tid];
         if (v) atomicAdd(&state->active_after[s0 + tid], (unsigned long long)v);
@@ -581,7 +581,42 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (tid < T) s_cnt[tid] = 0;
         __syncthreads();
         const int brick = P.pass == 0 ? work : list_in[work];
-        relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, brick, levels, s0);
+        const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc_idx = brick / (P.ntx * P.nty);
+        const int zs = P.z_out0 + zc_idx * P.bz;
+        relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, brick, tx, ty, zs, min(zs + P.bz, P.z_out1),
+                       levels, s0);
+    }
+
+    // Multi-GPU: the pressure halo is exchanged only every few passes, deep enough that in between the planes next
+    // to the slab faces can be relaxed here as well (redundantly with their owner, bit-identically).  These halo
+    // bricks are always processed — their cells carry the owner's freeze flags, so frozen regions cost only the copy.
+    const int tiles = P.ntx * P.nty;
+    const int lo_chunks = (P.ext_lo + P.bz - 1) / P.bz, hi_chunks = (P.ext_hi + P.bz - 1) / P.bz;
+    for (int work = blockIdx.x; work < tiles * (lo_chunks + hi_chunks); work += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            if (bars_live) {
+#pragma unroll
+                for (int i = 0; i <= kPrefetch; ++i)
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
+            }
+#pragma unroll
+            for (int i = 0; i <= kPrefetch; ++i) mbar_init(&bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        bars_live = true;
+        if (tid < T) s_cnt[tid] = 0;
+        __syncthreads();
+        const int tile = work % tiles, chunk = work / tiles;
+        int zs, ze;
+        if (chunk < lo_chunks) {
+            zs = P.z_out0 - P.ext_lo + chunk * P.bz;
+            ze = min(zs + P.bz, P.z_out0);
+        } else {
+            zs = P.z_out1 + (chunk - lo_chunks) * P.bz;
+            ze = min(zs + P.bz, P.z_out1 + P.ext_hi);
+        }
+        relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, -1, tile % P.ntx, tile / P.ntx, zs, ze, levels, s0);
     }
 }
 
@@ -616,7 +651,7 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int nz_alloc,
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                         int iters, int early_exit, bool run_all, cudaStream_t stream) {
+                         int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -631,6 +666,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
     P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
     P.pass = pass; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
+    P.ext_lo = ext_lo; P.ext_hi = ext_hi;
     const int nbricks = J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
     const int grid = nbricks < slots ? nbricks : slots;
@@ -652,14 +688,14 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
 //   2: 4 rows/thread,  8 warps (tile 128 x 32), TMA depth 2
 template <int T>
 cudaError_t launch_T(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                     int iters, int early_exit, bool run_all, cudaStream_t stream) {
+                     int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
     switch (J.variant) {
         case 0:
             if constexpr (T <= 2)
-                return launch_shape<Shape<T, 2, 8, 2, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+                return launch_shape<Shape<T, 2, 8, 2, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
             break;
-        case 1: return launch_shape<Shape<T, 2, 16, 1>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
-        case 2: return launch_shape<Shape<T, 4, 8, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 1: return launch_shape<Shape<T, 2, 16, 1>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+        case 2: return launch_shape<Shape<T, 4, 8, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -704,12 +740,13 @@ size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty 
 size_t fused_jacobi_brick_cells(const FusedJacobi& J) { return (size_t)kOutX * (J.tile_y - 2 * J.T) * J.bz; }
 
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                     int pass, int iters, int early_exit, bool run_all, cudaStream_t stream) {
+                                     int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
+                                     cudaStream_t stream) {
     switch (J.T) {
-        case 1: return launch_T<1>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
-        case 2: return launch_T<2>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
-        case 3: return launch_T<3>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
-        case 4: return launch_T<4>(J, d, frame, state, pass, iters, early_exit, run_all, stream);
+        case 1: return launch_T<1>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+        case 2: return launch_T<2>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+        case 3: return launch_T<3>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+        case 4: return launch_T<4>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -52,6 +52,7 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                     int pass, int iters, int early_exit, bool run_all_passes, cudaStream_t stream);
+                                     int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
+                                     cudaStream_t stream);
 
 }  // namespace fxb

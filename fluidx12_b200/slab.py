@@ -12,6 +12,7 @@ from dataclasses import dataclass
 from typing import List, Tuple
 
 DEFAULT_H_ADV = 8  # advection back-trace reach in planes (2*|u_z| voxels) before the +1 tap
+DEFAULT_JACOBI_GROUP = 4  # fused passes between two pressure-halo exchanges (the halo planes in between are relaxed redundantly)
 
 
 def slab_range(nz: int, rank: int, nranks: int) -> Tuple[int, int]:
@@ -40,7 +41,8 @@ class HaloPlan:
     halo: int          # halo depth allocated on interior faces
     advect: List[Exchange]   # velocity + colour before advect: h_adv + 1 planes
     stencil1: List[Exchange]  # 1 plane (advected velocity before divergence; pressure before gradient)
-    jacobi: List[Exchange]   # fuse_t planes of pressure (+ freeze mask) before each fused pass
+    jacobi: List[Exchange]   # group*fuse_t planes of rhs once, and of pressure (+ freeze mask) before every `group`-th pass
+    group: int               # fused passes per pressure-halo exchange
 
 
 def _faces(nz: int, rank: int, nranks: int, depth: int) -> List[Exchange]:
@@ -55,15 +57,18 @@ def _faces(nz: int, rank: int, nranks: int, depth: int) -> List[Exchange]:
     return out
 
 
-def halo_plan(nz: int, rank: int, nranks: int, fuse_t: int, h_adv: int = 0) -> HaloPlan:
+def halo_plan(nz: int, rank: int, nranks: int, fuse_t: int, h_adv: int = 0, group: int = 0) -> HaloPlan:
     h_adv = h_adv or DEFAULT_H_ADV
+    group = group or DEFAULT_JACOBI_GROUP
     z0, z1 = slab_range(nz, rank, nranks)
     if nranks == 1:
-        return HaloPlan(z0, z1, 0, nz, 0, [], [], [])
-    halo = max(h_adv + 1, fuse_t)
+        return HaloPlan(z0, z1, 0, nz, 0, [], [], [], 1)
+    halo = max(h_adv + 1, fuse_t)  # the group uses what the advection halo already provides
+    group = max(1, min(group, halo // fuse_t))
     if halo > min(slab_range(nz, r, nranks)[1] - slab_range(nz, r, nranks)[0] for r in range(nranks)):
         raise ValueError("halo deeper than the thinnest slab: use fewer ranks or a smaller fuse_t/h_adv")
     z_first = max(z0 - halo, 0)
     z_last = min(z1 + halo, nz)
     return HaloPlan(z0, z1, z_first, z_last - z_first, halo,
-                    _faces(nz, rank, nranks, h_adv + 1), _faces(nz, rank, nranks, 1), _faces(nz, rank, nranks, fuse_t))
+                    _faces(nz, rank, nranks, h_adv + 1), _faces(nz, rank, nranks, 1),
+                    _faces(nz, rank, nranks, group * fuse_t), group)

@@ -3,8 +3,8 @@
 Each rank holds the window [z_first, z_first + nz_alloc) that ``halo_plan`` prescribes, exchanges exactly the face
 ranges the plan lists (torch.distributed send/recv over gloo) and advances its window with the oracle's slab-window
 stage functions in the same order as the CUDA multi-GPU step (csrc/fxb_api.cu: exchange velocity+colour -> advect ->
-exchange advected velocity -> divergence -> exchange rhs -> per fused pass: exchange pressure (+ freeze flags),
-T sweeps -> all-reduce the freeze counters -> exchange pressure -> gradient).  The owned planes must equal the
+exchange advected velocity -> divergence -> exchange rhs -> every `group` fused passes: exchange pressure (+ freeze flags);
+T sweeps per pass -> all-reduce the freeze counters -> exchange pressure -> gradient).  The owned planes must equal the
 single-domain oracle bit for bit, which pins the halo depths, the exchange schedule and the face handling.
 """
 import os
@@ -68,9 +68,10 @@ def _worker(rank, world, port, grid, steps, fuse_t, h_adv, out):
         active = np.ones(s.shape, np.uint8)
         counts = np.zeros(npass * fuse_t, np.int64)
         for k in range(npass):
-            _exchange(p, plan.jacobi, zf)
-            if k:
-                _exchange(active, plan.jacobi, zf)
+            if k % plan.group == 0:  # group*T planes every `group` passes; the window is relaxed whole in between
+                _exchange(p, plan.jacobi, zf)
+                if k:
+                    _exchange(active, plan.jacobi, zf)
             p, active, c = O.jacobi_sweeps_slab(s, p, active, fuse_t, nz, zf, own.start, own.stop)
             counts[k * fuse_t:(k + 1) * fuse_t] = c
         t = torch.from_numpy(counts)
