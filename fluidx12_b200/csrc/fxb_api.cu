@@ -82,7 +82,7 @@ struct fxb_sim {
     fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
     int halo = 0;             // halo planes allocated on interior faces
     int h_adv = 0;            // advection halo (back-trace reach in planes)
-    int jacobi_group = 4;     // multi-GPU: fused passes between two pressure-halo exchanges
+    int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (FXB_JACOBI_GROUP; > 1 is experimental)
     int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
@@ -208,7 +208,7 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 for (int k = 0; k < npass; ++k) {
                     int ext_lo = 0, ext_hi = 0;
                     if (mg) {
-                        if (k % G == 0 && !getenv("FXB_DEBUG_NO_JHALO")) {
+                        if (k % G == 0) {
                             const fxb::HaloField f[2] = {
                                 {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * s->fuse_t},
                                 {s->jac.mask[k & 1], s->plane_voxels() / 8, G * s->fuse_t}};

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 from typing import List, Tuple
 
 DEFAULT_H_ADV = 8  # advection back-trace reach in planes (2*|u_z| voxels) before the +1 tap
-DEFAULT_JACOBI_GROUP = 4  # fused passes between two pressure-halo exchanges (the halo planes in between are relaxed redundantly)
+DEFAULT_JACOBI_GROUP = 1  # fused passes per pressure-halo exchange; > 1 relaxes the halo planes in between redundantly (experimental)
 
 
 def slab_range(nz: int, rank: int, nranks: int) -> Tuple[int, int]:

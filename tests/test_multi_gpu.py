@@ -27,6 +27,16 @@ def test_two_ranks_match_single_gpu(grid, t):
 
 
 @pytest.mark.gpu
+def test_two_ranks_grouped_pressure_exchange():
+    """Opt-in schedule: pressure halo exchanged every 4th pass, 4*T planes deep, halo planes relaxed redundantly."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    rc, log = _run(2, {"FXB_TEST_GRID": "64,64,96", "FXB_TEST_T": "2", "FXB_JACOBI_GROUP": "4"})
+    assert rc == 0 and "MGPU_OK" in log, log[-3000:]
+
+
+@pytest.mark.gpu
 def test_four_ranks_and_eager_launch():
     import torch
     if torch.cuda.device_count() < 4:

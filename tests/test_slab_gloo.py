@@ -39,14 +39,14 @@ def _exchange(arr, faces, z_first):
         dst[...] = recv.numpy().view(arr.dtype).reshape(dst.shape)
 
 
-def _worker(rank, world, port, grid, steps, fuse_t, h_adv, out):
+def _worker(rank, world, port, grid, steps, fuse_t, h_adv, group, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle as O
     from fluidx12_b200 import halo_plan
     nx, ny, nz = grid
-    plan = halo_plan(nz, rank, world, fuse_t, h_adv)
+    plan = halo_plan(nz, rank, world, fuse_t, h_adv, group)
     zf, nza = plan.z_first, plan.nz_alloc
     own = slice(plan.z0 - zf, plan.z1 - zf)
     vel_g, col_g, p_g = smooth_state(nx, ny, nz, seed=9, umax=1.0)
@@ -99,14 +99,15 @@ def _worker(rank, world, port, grid, steps, fuse_t, h_adv, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,grid,fuse_t,h_adv", [(2, (16, 16, 24), 2, 3), (3, (16, 16, 30), 4, 5), (2, (24, 24, 20), 1, 5)])
-def test_slab_decomposition_matches_single_domain(world, grid, fuse_t, h_adv):
+@pytest.mark.parametrize("world,grid,fuse_t,h_adv,group", [(2, (16, 16, 24), 2, 3, 1), (3, (16, 16, 30), 4, 5, 1),
+                                                           (2, (24, 24, 20), 1, 5, 1), (2, (16, 16, 24), 2, 7, 4)])
+def test_slab_decomposition_matches_single_domain(world, grid, fuse_t, h_adv, group):
     import oracle
     oracle.build()
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29700 + world * 10 + fuse_t
-    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, 3, fuse_t, h_adv, out)) for r in range(world)]
+    port = 29700 + world * 10 + fuse_t + 3 * group
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, 3, fuse_t, h_adv, group, out)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
