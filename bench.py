@@ -50,7 +50,7 @@ def bytes_per_voxel_step(passes: float, mask_bytes_per_pass: float) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -207,7 +207,7 @@ def phase_rooflines(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
     st1 = f.stats()
     jb, proc, cop = jacobi_work_bytes(st0, st1, mask_bytes, voxels_local)
     jb /= reps
-    launches = (st1.total_passes - st0.total_passes) / reps * (2 if st1.jacobi_fused else 1)
+    launches = (st1.total_passes - st0.total_passes) / reps  # one kernel per executed pass
     per = {"advect": 32.0 * voxels_local, "divergence": 12.0 * voxels_local, "jacobi": jb,
            "gradient": 20.0 * voxels_local}
     out = {}
@@ -216,9 +216,12 @@ def phase_rooflines(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
         out[k] = {"ms": round(phases[k], 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1),
                   "frac": round(gbs / peak, 4)}
     j = out["jacobi"]
-    roof = {"bound": "hbm", "kernel": "jacobi_pass_kernel + copy_frozen_bricks_kernel (all passes of a step)",
+    roof = {"bound": "hbm", "kernel": "jacobi_pass_kernel (average over the executed passes of a step; the one-time "
+                                      "copies of frozen bricks run inside it)",
             "achieved": j["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": j["frac"], "peak_source": peak_src,
-            "traffic": None, "bytes_per_step": jb, "ms_per_step": j["ms"], "launches_per_step": round(launches, 1),
+            "traffic": None, "bytes_per_launch": round(jb / max(launches, 1e-9)),
+            "avg_launch_ms": round(j["ms"] / max(launches, 1e-9), 5), "bytes_per_step": jb, "ms_per_step": j["ms"],
+            "launches_per_step": round(launches, 1),
             "bricks_relaxed_per_step": round(proc / reps, 1), "bricks_copied_per_step": round(cop / reps, 1),
             "note": "issue/latency-bound, not HBM-bound: see DESIGN.md §5 and profiles/"}
     return roof, out, {k: round(v, 4) for k, v in phases.items()}
