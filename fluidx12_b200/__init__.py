@@ -23,11 +23,11 @@ from .binding import (  # noqa: F401
     lib,
     lib_path,
 )
-from .fluid import Fluid  # noqa: F401
+from .fluid import Fluid, FluidEZ  # noqa: F401
 from .slab import slab_range, halo_plan  # noqa: F401
 
 __all__ = [
-    "Fluid", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan",
+    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
     "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV",
 ]

@@ -148,3 +148,16 @@ class Fluid:
         B.check(B.lib().fxb_profile_step(self._handle(), ms, 6))
         keys = ("advect", "divergence", "jacobi", "gradient", "halo", "step")
         return {k: float(ms[i]) for i, k in enumerate(keys)}
+
+
+class FluidEZ(Fluid):
+    """Mirror of the reference's ``FluidEZ`` (FluidX12/Content/FluidEZ.h:20-32), the app's default runtime path
+    (FluidX12.cpp:40).  Its simulation is the same two dispatches (FluidEZ.cpp:373-449); the one difference on the
+    hot path is the advection sampler, LINEAR_CLAMP instead of LINEAR_MIRROR (FluidEZ.cpp:406), and ``Init`` takes no
+    descriptor-table library."""
+
+    def Init(self, pCommandList=None, width: int = 0, height: int = 0, uploaders=None, rtFormat=None, dsFormat=None,
+             gridSize: Sequence[int] = (128, 128, 128), **kw) -> bool:
+        kw.setdefault("address_mode", B.ADDRESS_CLAMP)
+        return super().Init(pCommandList, width, height, None, uploaders, rtFormat, dsFormat, gridSize, **kw)
+

@@ -80,4 +80,15 @@ protected:
     std::string m_error;
 };
 
+// FluidEZ (Content/FluidEZ.h:20-32; the app's default runtime path, FluidX12.cpp:40): the same two dispatches
+// (FluidEZ.cpp:373-449) with the advection sampler LINEAR_CLAMP (FluidEZ.cpp:406) instead of LINEAR_MIRROR.
+class FluidEZ : public Fluid {
+public:
+    bool Init(const UInt3& gridSize, const fxb_config* cfg = nullptr) {
+        fxb_config c;
+        if (cfg) c = *cfg; else { fxb_config_default(&c); c.address_mode = FXB_ADDRESS_CLAMP; }
+        return Fluid::Init(gridSize, &c);
+    }
+};
+
 }  // namespace fluidx_b200
