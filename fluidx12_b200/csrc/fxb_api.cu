@@ -95,16 +95,15 @@ struct fxb_sim {
 
 namespace {
 
-// Conservative voxel box of the emitter sphere |pos - (0.5, 0.1, 0.5)| <= r (Impulse.hlsli:14-15,
-// CSAdvect.hlsl:58-60) and its basis values, computed exactly as the shader orders the arithmetic
-//  with libm exp2f.
-int build_emitter(fxb_sim* s) {
-    const int nx = s->dom.nx, ny = s->dom.ny, nz = s->dom.nz;
+// Emitter table (Impulse.hlsli:14-15, CSAdvect.hlsl:58-60): basis values of the voxels in the conservative box,
+// computed exactly as the shader orders the arithmetic with libm exp2f.
+// Voxel box [lo, hi) that contains every voxel whose emitter basis can reach exp(-4): the sphere
+// |pos - (0.5, 0.1, 0.5)| <= r with a 0.1 % radius margin plus one voxel per side, clipped to the grid.
+void emitter_box(int nx, int ny, int nz, int lo[3], int hi[3]) {
     const bool is3d = nz > 1;
     const float r = is3d ? 1.0f / 16.0f : 1.0f / 32.0f;
     const float centre[3] = {0.5f, 0.1f, 0.5f};
     const int n[3] = {nx, ny, nz};
-    int lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
         lo[a] = (int)std::floor((centre[a] - r * 1.001f) * n[a] - 0.5f) - 1;
         hi[a] = (int)std::ceil((centre[a] + r * 1.001f) * n[a] - 0.5f) + 2;
@@ -113,6 +112,12 @@ int build_emitter(fxb_sim* s) {
         if (hi[a] < lo[a]) hi[a] = lo[a];
     }
     if (!is3d) { lo[2] = 0; hi[2] = 1; }
+}
+
+int build_emitter(fxb_sim* s) {
+    const int nx = s->dom.nx, ny = s->dom.ny, nz = s->dom.nz;
+    int lo[3], hi[3];
+    emitter_box(nx, ny, nz, lo, hi);
     fxb::Emitter& em = s->emitter;
     em.x0 = lo[0]; em.y0 = lo[1]; em.z0 = lo[2];
     em.x1 = hi[0]; em.y1 = hi[1]; em.z1 = hi[2];
@@ -646,6 +651,14 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
     }
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
+}
+
+int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {
+    if (!out6 || nx == 0 || ny == 0 || nz == 0) return fail(FXB_ERR_INVALID, "fxb_emitter_box: bad argument");
+    int lo[3], hi[3];
+    emitter_box((int)nx, (int)ny, (int)nz, lo, hi);
+    for (int a = 0; a < 3; ++a) { out6[a] = lo[a]; out6[3 + a] = hi[a]; }
+    return FXB_OK;
 }
 
 int fxb_get_freeze_histogram(fxb_sim* s, uint64_t* out, int n) {

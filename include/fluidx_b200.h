@@ -121,6 +121,10 @@ int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void*
 /* Reads back the device-side counters of the last step (synchronises the handle's stream). */
 int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 
+/* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
+ * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
+int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);
+
 /* Freeze histogram of the last step: out[k] = cells still active after sweep k+1 (this rank; global after the
  * all-reduce when nranks > 1), k < n <= 128.  The oracle reports the same numbers. */
 int fxb_get_freeze_histogram(fxb_sim* sim, uint64_t* out, int n);

@@ -167,3 +167,26 @@ def test_sass_shows_blackwell_native_paths(fx):
     assert "FADD2" in adv and "FFMA2" in adv
     for banned in ("HMMA", "UTCHMMA", "UTCQMMA", "HGMMA"):
         assert banned not in sass
+
+
+@pytest.mark.parametrize("n", [(64, 64, 64), (150, 150, 150), (256, 256, 1), (512, 512, 1), (128, 128, 40), (30, 30, 18),
+                               (1024, 1024, 16), (8, 8, 8)])
+def test_emitter_box_contains_every_emitting_voxel(fx, n):
+    """The advection kernel only evaluates the emitter inside fxb_emitter_box; every voxel whose Gaussian basis can
+    reach exp(-4) (CSAdvect.hlsl:60) must therefore lie inside it (checked in float64 with a 0.1 % safety band)."""
+    import numpy as np
+    nx, ny, nz = n
+    box = (C.c_int32 * 6)()
+    assert fx.lib().fxb_emitter_box(nx, ny, nz, box) == 0
+    x0, y0, z0, x1, y1, z1 = list(box)
+    px = ((np.arange(nx, dtype=np.float32) + np.float32(0.5)) / np.float32(nx)).astype(np.float64)
+    py = ((np.arange(ny, dtype=np.float32) + np.float32(0.5)) / np.float32(ny)).astype(np.float64)
+    pz = ((np.arange(nz, dtype=np.float32) + np.float32(0.5)) / np.float32(nz)).astype(np.float64)
+    r = 1.0 / 16.0 if nz > 1 else 1.0 / 32.0
+    d2 = ((pz - 0.5) ** 2)[:, None, None] + ((py - float(np.float32(0.1))) ** 2)[None, :, None] + ((px - 0.5) ** 2)[None, None, :]
+    emitting = np.exp(-4.0 * d2 / (r * r)) >= np.exp(-4.0) * (1 - 1e-3)
+    zz, yy, xx = np.nonzero(emitting)
+    if zz.size:
+        assert xx.min() >= x0 and xx.max() < x1 and yy.min() >= y0 and yy.max() < y1 and zz.min() >= z0 and zz.max() < z1
+    assert 0 <= x0 <= x1 <= nx and 0 <= y0 <= y1 <= ny and 0 <= z0 <= z1 <= nz
+    assert (x1 - x0) * (y1 - y0) * (z1 - z0) <= max(64, 8 * emitting.sum() + 4096)  # and it is not wastefully large

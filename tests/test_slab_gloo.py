@@ -100,7 +100,8 @@ def _worker(rank, world, port, grid, steps, fuse_t, h_adv, group, out):
 
 
 @pytest.mark.parametrize("world,grid,fuse_t,h_adv,group", [(2, (16, 16, 24), 2, 3, 1), (3, (16, 16, 30), 4, 5, 1),
-                                                           (2, (24, 24, 20), 1, 5, 1), (2, (16, 16, 24), 2, 7, 4)])
+                                                           (2, (24, 24, 20), 1, 5, 1), (2, (16, 16, 24), 2, 7, 4),
+                                                           (3, (16, 16, 36), 2, 7, 4)])
 def test_slab_decomposition_matches_single_domain(world, grid, fuse_t, h_adv, group):
     import oracle
     oracle.build()
