@@ -333,10 +333,12 @@ def run_ours(args):
     nominal_gbs = nominal_bpv * voxels / t_step / 1e9
 
     roof, phase_roof, phases = phase_rooflines(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
+    # `traffic` stays null: the ncu capture in profiles/ is of pass 0 alone (every brick relaxed), while `achieved`
+    # averages over all passes of a step; the capture is quoted next to it instead.
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi")
+            roof["ncu_pass0_capture"] = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi")
         except Exception:
             pass
     if st1.halo_overflow:

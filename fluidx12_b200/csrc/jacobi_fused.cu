@@ -4,24 +4,26 @@
 // CSProject3D.hlsl:93 (dispatch Fluid.cpp:394-408), under the deterministic restatement of SURVEY.md
 // App. A.3: synchronous Jacobi, per-cell freeze once |x - x0| < 0.001, at most ITER sweeps.
 //
-// Scheme: z-marching 2.5-D blocking with temporal fusion.  A CTA owns a brick of 120 x (32-2T) x BZ
-// output cells.  It streams the xy tile (128 x 32 cells, halo 4 in x / T in y) plane by plane along z;
-// level l (= number of sweeps applied) of plane k-l is produced in iteration k, so T sweeps advance in
-// lock-step, each one plane behind the previous:
+// Scheme: z-marching 2.5-D blocking with temporal fusion.  A CTA owns a brick of 120 x (TILE_Y - 2T) x BZ output
+// cells (TILE_Y = rows per thread x warps; the default shape is T = 2, 2 rows x 8 warps = 16 rows, BZ = 8, two
+// CTAs per SM).  It streams the xy tile (128 x TILE_Y cells: halo 4 in x, T in y) plane by plane along z; level l
+// (= number of sweeps applied) of plane k-l is produced in iteration k, so the T sweeps advance in lock-step, each
+// one plane behind the previous:
 //   * level-0 pressure planes and the right-hand-side planes are staged into shared memory by TMA
-//     (cp.async.bulk.tensor.3d + mbarrier), one iteration ahead; out-of-grid tile parts are zero-filled;
-//   * every thread keeps its own column (4 rows x 4 cells) of the two most recent planes of every level
-//     in registers (the z queue), so the z neighbours never touch memory;
-//   * x neighbours come from warp shuffles (a warp spans the 128-cell tile row), y neighbours from the
-//     thread's own rows or from the level's plane in shared memory;
-//   * the reference's clamp-to-edge neighbour rule (CSProject3D.hlsl:76-83) is applied by index (x, y)
-//     or by reusing the centre value (z), never by TMA fill;
-//   * the per-cell freeze flags travel with the values (4 bits per quad per level); a warp whose 512
-//     cells are all frozen at a level skips that level's arithmetic; flags persist between passes in a
-//     bit-packed array (1 bit per cell, 0.25 B/voxel/pass of traffic);
-//   * a brick whose cells are all frozen is copied once to the other pressure buffer and skipped for the
-//     rest of the frame (its value is final in both ping-pong buffers).
-// Algorithmic traffic per processed cell per pass: p in 4 + rhs in 4 + p out 4 (+ 2/8 mask) bytes.
+//     (cp.async.bulk.tensor.3d + mbarrier), DEPTH iterations ahead; out-of-grid tile parts are zero-filled;
+//   * every thread keeps its own column (ROWS rows x 4 cells) of the two most recent planes of every level in
+//     registers (the z queue), so the z neighbours never touch memory; a sweep is split into a 5-addition head and
+//     a 1-addition tail so that a level's new plane overwrites the queue slot its consumer has just read;
+//   * x neighbours come from warp shuffles (a warp spans the 128-cell tile row), y neighbours from the thread's own
+//     rows or from the edge rows every warp publishes in shared memory;
+//   * the reference's clamp-to-edge neighbour rule (CSProject3D.hlsl:76-83) is applied by index (x, y) or by
+//     reusing the centre value (z), never by TMA fill;
+//   * the per-cell freeze flags travel with the values (4 bits per quad per level); a warp whose cells are all
+//     frozen at a level skips that level's arithmetic; flags persist between passes in a bit-packed array
+//     (1 bit per cell, 0.25 B/voxel/pass of traffic);
+//   * persistent CTAs take bricks from device-side work lists; a brick whose cells are all frozen is copied once to
+//     the other pressure buffer and skipped for the rest of the frame (final in both ping-pong buffers).
+// Algorithmic traffic per relaxed cell per pass: p in 4 + rhs in 4 + p out 4 (+ 2/8 mask) bytes; 8 per copied cell.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -98,7 +100,7 @@ struct PassParams {
     int nx, ny;            // grid extent in x, y
     int nz_alloc;          // local planes allocated
     int z_face_lo;         // local index of global plane 0 (or very negative when it is on another rank)
-    int z_face_hi;         // local index one past global plane nz-1 (or very large)
+    int z_face_hi;         // local index one past global plane nz-1 (informational: the array ends at that face)
     int z_out0, z_out1;    // local planes this rank must produce
     int bz;                // planes per brick
     int ntx, nty, nzc;     // brick grid
@@ -114,7 +116,6 @@ struct WorkLists {
     int* copy[2];      // bricks that froze in the previous pass: one copy into the other pressure buffer
     int* relax_count;  // [pass]
     int* copy_count;   // [pass]
-    int* relax_head;   // [pass] next entry to hand out
 };
 
 // A brick whose cells all froze during pass p-1 holds its final values in that pass's output buffer only.  Pass p
@@ -195,8 +196,7 @@ __device__ __forceinline__ void relax_tail(const float4 head, const float4 hi, c
     still = s;
 }
 
-// Relaxes one brick: T fused sweeps over its 120 x (32-2T) x bz output cells (see the file header).
-// Out of line so that the persistent work loop around it does not lengthen any live range of the marching loop.
+// Relaxes one brick: T fused sweeps over its 120 x (TILE_Y - 2T) x (ze - zs) output cells (see the file header).
 template <class S>
 __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUtensorMap* map_rhs_p,
                                          float* __restrict__ p_out, const unsigned char* __restrict__ m_in,
@@ -674,7 +674,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     const int np = FusedJacobi::kMaxPasses + 1;
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
     W.copy[0] = J.work_list[0] + nbricks; W.copy[1] = J.work_list[1] + nbricks;
-    W.relax_count = J.work_count; W.copy_count = J.work_count + np; W.relax_head = J.work_count + 2 * np;
+    W.relax_count = J.work_count; W.copy_count = J.work_count + np;
     jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
         *reinterpret_cast<const CUtensorMap*>(J.map_p[0]), *reinterpret_cast<const CUtensorMap*>(J.map_p[1]),
         *reinterpret_cast<const CUtensorMap*>(J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P);

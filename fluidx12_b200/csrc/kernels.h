@@ -41,7 +41,7 @@ struct FusedJacobi {
     float* rhs = nullptr;
     unsigned char* mask[2] = {nullptr, nullptr};  // bit-packed freeze flags, ping-pong by pass parity
     int* work_list[2] = {nullptr, nullptr};       // [2 * bricks] per pass parity: bricks to relax, then bricks to copy
-    int* work_count = nullptr;                    // [3][kMaxPasses + 1]: relax count, copy count, relax head per pass
+    int* work_count = nullptr;                    // [3][kMaxPasses + 1]: relax count and copy count per pass (+ spare)
     int num_sms = 0;
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
