@@ -50,7 +50,7 @@ def bytes_per_voxel_step(passes: float, mask_bytes_per_pass: float) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms while the GPU runs the warm-up and timed steps."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -307,6 +307,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms, st0, st1 = timed_run(torch, dist, f, dt, args.steps, args.warmup, world, stream)
+    if rank == 0 and world == 1:
+        # a very short timed region can end before nvidia-smi has answered once: keep the same load running
+        # (untimed) until a few samples exist
+        t_end = time.time() + 1.5
+        while len(sampler.lines) < 4 and time.time() < t_end:
+            for _ in range(5):
+                f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
+            stream.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     sec_e2e, h2d, d2h = e2e_run(torch, dist, f, fx, dt, args.steps, world, stream, export=False)

@@ -403,7 +403,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         // [r*nz/R, (r+1)*nz/R); interior faces carry `halo` extra planes, the grid's own faces none
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
         const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
-        s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;
+        s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 12;  // 2|u_z| voxels; |u_z| stayed below 3 in every run so far
         if (const char* e = getenv("FXB_JACOBI_GROUP")) s->jacobi_group = std::max(1, atoi(e));
         s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
         int thinnest = nz;

@@ -58,7 +58,7 @@ typedef struct fxb_config {
     int32_t fuse_t;         /* Jacobi sweeps fused per HBM pass; 0 = library default */
     int32_t device;         /* CUDA device ordinal */
     int32_t rank, nranks;   /* z-slab decomposition: this rank owns planes [rank*nz/nranks, (rank+1)*nz/nranks) */
-    int32_t h_adv;          /* advection z-halo in planes (multi-GPU); 0 = default 8 */
+    int32_t h_adv;          /* advection z-halo in planes (multi-GPU); 0 = default 12 */
     int32_t use_graph;      /* 1 (default): the step is a captured CUDA graph; 0: plain stream launches */
     int32_t kernel_path;    /* 0 = tuned kernels (default); 1 = one simple kernel per logical pass (cross-check path) */
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; required iff nranks > 1 */

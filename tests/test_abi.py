@@ -101,15 +101,15 @@ def test_slab_plan():
     from fluidx12_b200 import halo_plan, slab_range
     assert [slab_range(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
     assert slab_range(150, 1, 4) == (37, 75)
-    p = halo_plan(512, 0, 8, fuse_t=4)
-    assert (p.z_first, p.nz_alloc, p.halo, p.group) == (0, 64 + 9, 9, 1) and len(p.advect) == 1
-    q = halo_plan(512, 3, 8, fuse_t=4)
+    p = halo_plan(512, 0, 8, fuse_t=4)  # default advection halo: 12 planes (+1 for the second tap)
+    assert (p.z_first, p.nz_alloc, p.halo, p.group) == (0, 64 + 13, 13, 1) and len(p.advect) == 1
+    q = halo_plan(512, 3, 8, fuse_t=4, h_adv=8)
     assert (q.z_first, q.nz_alloc) == (192 - 9, 64 + 18)
     lo, hi = q.advect
     assert (lo.peer, lo.send0, lo.send1, lo.recv0, lo.recv1) == (2, 192, 201, 183, 192)
     assert (hi.peer, hi.send0, hi.send1, hi.recv0, hi.recv1) == (4, 247, 256, 256, 265)
     assert q.jacobi[0].recv1 - q.jacobi[0].recv0 == 4  # fuse_t planes before every pass
-    two = halo_plan(512, 3, 8, fuse_t=2, group=4)  # opt-in: exchange 8 planes every 4th pass
+    two = halo_plan(512, 3, 8, fuse_t=2, h_adv=8, group=4)  # opt-in: exchange 8 planes every 4th pass
     assert (two.halo, two.group, two.jacobi[0].recv1 - two.jacobi[0].recv0) == (9, 4, 8)
     one = halo_plan(128, 0, 1, fuse_t=8)
     assert one.nz_alloc == 128 and not one.advect
