@@ -1,0 +1,368 @@
+// jacobi_tail_body.cuh — body of the block-resident multi-sweep Jacobi kernel ("tail kernel", jacobi_tail.cu).
+//
+// Same relaxation as jacobi_fused.cu (CSPoisson.hlsli:8-26 under SURVEY.md App. A.3), for the long tail of the
+// solve in which only a few bricks still hold an active cell and the z-marching bulk kernel is bound by the latency
+// of one brick chain per launch.  Here a CTA loads one sub-block of an active brick — 40 x 12 x 8 output cells plus a
+// halo of TT cells per side — once, keeps it on chip (every thread owns the z column of one quad in registers, the
+// xy neighbours are exchanged through shared memory) and applies TT sweeps before it stores the result, so a launch
+// advances the solve by TT sweeps along a dependency chain of TT short phases instead of bz + 2T marching steps.
+// Validity shrinks by one cell per sweep from every window edge that is not a grid face (the halo of TT cells
+// absorbs exactly that); at a grid face the reference's clamp-to-edge rule applies (CSProject3D.hlsl:76-83).
+//
+// The file is written against a tiny portability layer (FXT_*) so that the SAME statements compile under nvcc
+// (threads = CUDA threads, phases separated by __syncthreads) and under g++ in tests/emu/tail_emu.cpp (threads = a
+// loop, phases = consecutive loops).  The emulation is test infrastructure: it lets the CPU suite check this file
+// bit for bit against the oracle; it is never linked into libfluidx_b200.so.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FXT_FN __device__ __forceinline__
+#define FXT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define FXT_POPC(v) __popc(v)
+#define FXT_ATOMIC_ADD_U32(p, v) atomicAdd((p), (v))
+#define FXT_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#define FXT_ATOMIC_ADD_U64(p, v) atomicAdd((p), (v))
+#define FXT_LDG_U8(p) __ldg(p)
+namespace fxb { typedef float4 Quad; }
+#else
+#include <cmath>
+#define FXT_FN inline
+#define FXT_FMA(a, b, c) std::fmaf((a), (b), (c))
+#define FXT_POPC(v) __builtin_popcount(v)
+#define FXT_ATOMIC_ADD_U32(p, v) (*(p) += (v))
+static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + v; return o; }
+#define FXT_ATOMIC_ADD_I32(p, v) fxt_fetch_add_i32((p), (v))
+#define FXT_ATOMIC_ADD_U64(p, v) (*(p) += (v))
+#define FXT_LDG_U8(p) (*(p))
+namespace fxb { struct alignas(16) Quad { float x, y, z, w; }; }
+#endif
+
+namespace fxb {
+
+constexpr float kTailInv6 = 0.166666672f;   // 0x3e2aaaab
+constexpr float kTailEps = 0.00100000005f;  // 0x3a83126f
+
+// Compile-time shape: TT sweeps per launch, output sub-block OXQ quads x OY rows x OZ planes.
+template <int TT_, int OXQ_, int OY_, int OZ_>
+struct TailShape {
+    static constexpr int TT = TT_, OXQ = OXQ_, OY = OY_, OZ = OZ_;
+    static_assert(TT_ >= 1 && TT_ <= 4, "the x halo is one quad");
+    static constexpr int OX = 4 * OXQ_;
+    static constexpr int LXQ = OXQ_ + 2, LX = 4 * LXQ;  // window: one halo quad per side in x
+    static constexpr int LY = OY_ + 2 * TT_, LZ = OZ_ + 2 * TT_;
+    static constexpr int kUsed = LXQ * LY;               // threads that own a column
+    static constexpr int kThreads = (kUsed + 31) / 32 * 32;
+    static constexpr int kPlane = LX * LY;                 // floats per window plane
+    static constexpr int kRhsPlane = LX * (LY - 2);
+    static constexpr int kFlagWords = (4 * LZ + 31) / 32;
+    static_assert(LZ <= 16, "flag words / dirty mask are sized for 16 planes");
+    // shared memory (floats): window values, right-hand side of the cells that can be relaxed, then bytes
+    static constexpr int kPFloats = LZ * kPlane;
+    static constexpr int kRhsFloats = (LZ - 2) * kRhsPlane;
+    static constexpr int kNibBytes = LZ * LY * LXQ;
+    static constexpr int kCtrlWords = 8 + TT_;  // any-own flag, per-level counters, spare
+    static constexpr size_t kBytes = (size_t)(kPFloats + kRhsFloats) * 4 + kNibBytes + kCtrlWords * 4;
+};
+
+// What one launch needs to know (uniform over the grid).
+struct TailParams {
+    int nx, ny;          // grid extent in x, y
+    int nz_alloc;        // local planes allocated
+    int z_face_lo;       // local index of global plane 0 (may be negative: on another rank)
+    int z_face_hi;       // local index one past global plane nz-1 (may exceed nz_alloc)
+    int z_out0, z_out1;  // local planes this rank owns
+    int bx, by, bz;      // brick extent (jacobi_fused.cu: 120 x (TILE_Y - 2T) x bz)
+    int ntx, nty;        // brick grid in x, y
+    int nsub;            // sub-blocks per brick in x
+    int first;           // 1: no flags exist yet (first kernel of a frame): every cell is active
+    int early_exit;
+    int levels;          // sweeps to apply (<= TT)
+};
+
+// Shared-memory view.
+template <class S>
+struct TailShared {
+    float* p;            // [LZ][LY][LX]
+    float* rhs;          // [LZ-2][LY-2][LX]  (window planes 1..LZ-2, rows 1..LY-2)
+    unsigned char* nib;  // [LZ][LY][LXQ]
+    unsigned* ctrl;      // [0] any active cell in the own region; [1 + l] active own cells after level l+1
+};
+
+// Per-thread state that lives across phases (registers under nvcc).
+template <class S>
+struct TailThread {
+    Quad v[S::LZ];
+    unsigned fl[2];     // freeze flags of the column: nibble z of the 64-bit word (1 = active)
+    unsigned own[2];    // nibbles of the cells this CTA must produce
+    unsigned dirty;     // bit z: v[z] changed in the current sweep
+    int qx, y;          // window coordinates of the column
+    int gx, gy;         // grid coordinates
+    bool used;          // owns a column at all
+    bool in_xy;         // column lies inside the grid
+    bool own_xy;        // column belongs to the output region
+};
+
+// Geometry of one work item (uniform over the CTA).
+template <class S>
+struct TailItem {
+    int ox, oy, oz;     // first output cell (grid x, grid y, local plane)
+    int ex, ey, ez;     // output extent (<= OX, OY, OZ; <= 0: nothing to do)
+    int wx, wy, wz;     // window origin
+    int zvl, zvh;       // window planes inside the array and the grid: [zvl, zvh)
+    int yvl, yvh;       // window rows inside the grid
+    bool zlo_face, zhi_face, ylo_face, yhi_face;  // the valid range ends at a grid face (clamp rule) rather than at a window edge
+};
+
+template <class S>
+FXT_FN TailItem<S> tail_item(const TailParams& P, int brick, int sub) {
+    TailItem<S> it;
+    const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc = brick / (P.ntx * P.nty);
+    it.ox = tx * P.bx + sub * S::OX;
+    it.oy = ty * P.by;
+    it.oz = P.z_out0 + zc * P.bz;
+    const int bx_end = (tx + 1) * P.bx < P.nx ? (tx + 1) * P.bx : P.nx;
+    it.ex = bx_end - it.ox < S::OX ? bx_end - it.ox : S::OX;
+    it.ey = P.ny - it.oy < P.by ? P.ny - it.oy : P.by;
+    it.ez = P.z_out1 - it.oz < P.bz ? P.z_out1 - it.oz : P.bz;
+    it.wx = it.ox - 4;
+    it.wy = it.oy - S::TT;
+    it.wz = it.oz - S::TT;
+    const int zlo = P.z_face_lo > 0 ? P.z_face_lo : 0, zhi = P.z_face_hi < P.nz_alloc ? P.z_face_hi : P.nz_alloc;
+    it.zvl = zlo - it.wz > 0 ? zlo - it.wz : 0;
+    it.zvh = zhi - it.wz < S::LZ ? zhi - it.wz : S::LZ;
+    it.yvl = -it.wy > 0 ? -it.wy : 0;
+    it.yvh = P.ny - it.wy < S::LY ? P.ny - it.wy : S::LY;
+    // A face that coincides with the first / last window plane or row is treated like a plain window edge: the cells
+    // on it have no right-hand side staged, and nothing that far out is needed (validity shrinks from there).
+    it.zlo_face = it.wz + it.zvl == P.z_face_lo && it.zvl >= 1;
+    it.zhi_face = it.wz + it.zvh == P.z_face_hi && it.zvh <= S::LZ - 1;
+    it.ylo_face = it.wy + it.yvl == 0 && it.yvl >= 1;
+    it.yhi_face = it.wy + it.yvh == P.ny && it.yvh <= S::LY - 1;
+    return it;
+}
+
+FXT_FN unsigned tail_nib(const unsigned (&fl)[2], int z) { return (fl[z >> 3] >> (4 * (z & 7))) & 0xFu; }
+FXT_FN void tail_set_nib(unsigned (&fl)[2], int z, unsigned n) {
+    fl[z >> 3] = (fl[z >> 3] & ~(0xFu << (4 * (z & 7)))) | (n << (4 * (z & 7)));
+}
+
+// ---- phase 0: thread geometry, freeze flags of the column, "is anything in the own region still active" ----------
+template <class S>
+FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
+                             const TailParams& P, const unsigned char* m_in) {
+    t.used = tid < S::kUsed;
+    t.qx = tid % S::LXQ;
+    t.y = tid / S::LXQ;
+    t.gx = it.wx + 4 * t.qx;
+    t.gy = it.wy + t.y;
+    t.in_xy = t.used && t.gx >= 0 && t.gx < P.nx && t.gy >= 0 && t.gy < P.ny;
+    t.own_xy = t.in_xy && t.qx >= 1 && 4 * (t.qx - 1) < it.ex && t.y >= S::TT && t.y - S::TT < it.ey;
+    t.fl[0] = t.fl[1] = 0u;
+    t.own[0] = t.own[1] = 0u;
+    t.dirty = 0u;
+    const int nxb = P.nx >> 3;
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        if (!t.in_xy || z < it.zvl || z >= it.zvh) continue;
+        unsigned n = 0xFu;
+        if (!P.first) {
+            const unsigned b = FXT_LDG_U8(m_in + ((size_t)(it.wz + z) * P.ny + t.gy) * nxb + (t.gx >> 3));
+            n = (b >> (t.gx & 4)) & 0xFu;
+        }
+        t.fl[z >> 3] |= n << (4 * (z & 7));
+        if (t.own_xy && z >= S::TT && z - S::TT < it.ez) t.own[z >> 3] |= 0xFu << (4 * (z & 7));
+    }
+    if (((t.fl[0] & t.own[0]) | (t.fl[1] & t.own[1])) != 0u) sh.ctrl[0] = 1u;  // benign race: everybody stores 1
+}
+
+// ---- copy path: no active cell in the own region, so the output equals the input ---------------------------------
+template <class S>
+FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailParams& P, const float* p_in,
+                            float* p_out, unsigned char* m_out) {
+    if (!t.own_xy) return;
+    const int nxb = P.nx >> 3;
+#pragma unroll
+    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+        if (z - S::TT >= it.ez) continue;
+        const size_t row = (size_t)(it.wz + z) * P.ny + t.gy;
+        *reinterpret_cast<Quad*>(p_out + row * P.nx + t.gx) = *reinterpret_cast<const Quad*>(p_in + row * P.nx + t.gx);
+        if (t.qx & 1) m_out[row * nxb + (t.gx >> 3)] = 0;
+    }
+}
+
+// ---- phase 1: window values -> registers + shared memory, right-hand side -> shared memory -----------------------
+template <class S>
+FXT_FN void tail_phase_load(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                            const float* p_in, const float* rhs) {
+    if (!t.used) return;
+    const Quad zero = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        Quad q = zero;
+        if (t.in_xy && z >= it.zvl && z < it.zvh)
+            q = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
+        t.v[z] = q;
+        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = q;
+    }
+    if (t.y >= 1 && t.y <= S::LY - 2) {
+#pragma unroll
+        for (int z = 1; z <= S::LZ - 2; ++z) {
+            Quad q = zero;
+            if (t.in_xy && z >= it.zvl && z < it.zvh)
+                q = *reinterpret_cast<const Quad*>(rhs + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
+            *reinterpret_cast<Quad*>(sh.rhs + (z - 1) * S::kRhsPlane + (t.y - 1) * S::LX + 4 * t.qx) = q;
+        }
+    }
+}
+
+// One cell: the six additions in the DXBC's order, x = acc * (1/6), freeze test on the fused
+// difference.  Returns the new value (active cells) or the old one (frozen cells); clears the cell's flag on freeze.
+FXT_FN float tail_cell(float c, float l, float r, float u, float d, float f, float b, float rhs, unsigned bit,
+                       float eps, unsigned& act) {
+    float acc = l + rhs;
+    acc = r + acc;
+    acc = u + acc;
+    acc = d + acc;
+    acc = f + acc;
+    acc = b + acc;
+    const float xn = acc * kTailInv6;
+    const float diff = FXT_FMA(acc, kTailInv6, -c);
+    if (!(act & bit)) return c;
+    if (fabsf(diff) < eps) act &= ~bit;
+    return xn;
+}
+
+// ---- phase A of sweep s (1-based): new values of the column into registers (reads shared memory only) ------------
+template <class S>
+FXT_FN void tail_phase_relax(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                             int s) {
+    t.dirty = 0u;
+    if (!t.in_xy || (t.fl[0] | t.fl[1]) == 0u) return;
+    // rows and planes that are still valid inputs of this sweep (see the file header)
+    const int yc0 = it.ylo_face ? it.yvl : it.yvl + s, yc1 = it.yhi_face ? it.yvh : it.yvh - s;
+    if (t.y < yc0 || t.y >= yc1) return;
+    const int zc0 = it.zlo_face ? it.zvl : it.zvl + s, zc1 = it.zhi_face ? it.zvh : it.zvh - s;
+    const float eps = P.early_exit ? kTailEps : -1.0f;
+    const int col = t.y * S::LX + 4 * t.qx;
+    const int up = (it.ylo_face && t.y == it.yvl) ? col : col - S::LX;          // clamp rule in y
+    const int dn = (it.yhi_face && t.y == it.yvh - 1) ? col : col + S::LX;
+    const bool clamp_l = t.qx == 0 || t.gx == 0;                                  // clamp rule / window edge in x
+    const bool clamp_r = t.qx == S::LXQ - 1 || t.gx + 4 == P.nx;
+    const int rcol = (t.y - 1) * S::LX + 4 * t.qx;
+    Quad below = t.v[0];  // previous sweep's value of plane z-1
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        const Quad c = t.v[z];
+        unsigned a = tail_nib(t.fl, z);
+        if (a != 0u && z >= zc0 && z < zc1) {
+            const float* pl = sh.p + z * S::kPlane;
+            const Quad f = (it.zlo_face && z == it.zvl) ? c : below;
+            const Quad b = (it.zhi_face && z == it.zvh - 1) ? c : t.v[z + 1 < S::LZ ? z + 1 : z];
+            const Quad u = *reinterpret_cast<const Quad*>(pl + up);
+            const Quad d = *reinterpret_cast<const Quad*>(pl + dn);
+            const float left = clamp_l ? c.x : pl[col - 1];
+            const float right = clamp_r ? c.w : pl[col + 4];
+            const Quad r = *reinterpret_cast<const Quad*>(sh.rhs + (z - 1) * S::kRhsPlane + rcol);
+            Quad n;
+            n.x = tail_cell(c.x, left, c.y, u.x, d.x, f.x, b.x, r.x, 1u, eps, a);
+            n.y = tail_cell(c.y, c.x, c.z, u.y, d.y, f.y, b.y, r.y, 2u, eps, a);
+            n.z = tail_cell(c.z, c.y, c.w, u.z, d.z, f.z, b.z, r.z, 4u, eps, a);
+            n.w = tail_cell(c.w, c.z, right, u.w, d.w, f.w, b.w, r.w, 8u, eps, a);
+            t.v[z] = n;
+            tail_set_nib(t.fl, z, a);
+            t.dirty |= 1u << z;
+        }
+        below = c;
+    }
+}
+
+// ---- phase B of sweep s: publish the changed planes, count the own cells that are still active -------------------
+template <class S>
+FXT_FN void tail_phase_publish(TailThread<S>& t, const TailShared<S>& sh, int s, bool last) {
+    if (!t.used) return;
+    if (!last && t.dirty) {
+#pragma unroll
+        for (int z = 0; z < S::LZ; ++z)
+            if ((t.dirty >> z) & 1u) *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = t.v[z];
+    }
+    const unsigned n = FXT_POPC(t.fl[0] & t.own[0]) + FXT_POPC(t.fl[1] & t.own[1]);
+    if (n) FXT_ATOMIC_ADD_U32(&sh.ctrl[s], n);
+}
+
+// ---- final phases: own cells -> the other pressure buffer; flags -> bit-packed mask (two quads per byte) ----------
+template <class S>
+FXT_FN void tail_phase_store(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                             float* p_out) {
+    if (!t.used) return;
+#pragma unroll
+    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+        sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
+        if (t.own_xy && z - S::TT < it.ez)
+            *reinterpret_cast<Quad*>(p_out + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx) = t.v[z];
+    }
+}
+
+template <class S>
+FXT_FN void tail_phase_store_mask(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                                  unsigned char* m_out) {
+    // own quads start at window quad 1 (grid x a multiple of 8) and come in pairs: the odd one writes the byte
+    if (!t.own_xy || !(t.qx & 1)) return;
+    const int nxb = P.nx >> 3;
+#pragma unroll
+    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+        if (z - S::TT >= it.ez) continue;
+        const unsigned lo = tail_nib(t.fl, z), hi = sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx + 1];
+        m_out[((size_t)(it.wz + z) * P.ny + t.gy) * nxb + (t.gx >> 3)] = (unsigned char)(lo | (hi << 4));
+    }
+}
+
+// Work lists of one launch (same lists as jacobi_fused.cu: bricks that still hold an active cell, and bricks that
+// froze in the previous kernel and need one copy into the other pressure buffer).
+struct TailWork {
+    const int* relax_in;
+    const int* copy_in;
+    int n_relax, n_copy;
+    int* relax_out;
+    int* copy_out;
+    int* relax_out_count;
+    int* copy_out_count;
+    int* brick_state;  // per brick: arrivals of its sub-blocks (low byte) and "still active" votes; zero between launches
+};
+
+// ---- after the last phase of a relax item (one thread): histogram, and the brick's entry in the next lists --------
+template <class S>
+FXT_FN void tail_finish_item(const TailShared<S>& sh, const TailParams& P, const TailWork& W, int brick,
+                             unsigned long long* active_after_s0) {
+    for (int l = 0; l < P.levels; ++l)
+        if (sh.ctrl[1 + l]) FXT_ATOMIC_ADD_U64(&active_after_s0[l], (unsigned long long)sh.ctrl[1 + l]);
+    const bool active = sh.ctrl[P.levels] != 0u;
+    const int old = FXT_ATOMIC_ADD_I32(&W.brick_state[brick], 1 + (active ? 256 : 0));
+    if ((old & 255) == P.nsub - 1) {  // last sub-block of the brick: all votes are in
+        W.brick_state[brick] = 0;
+        if (active || (old >> 8) != 0) W.relax_out[FXT_ATOMIC_ADD_I32(W.relax_out_count, 1)] = brick;
+        else W.copy_out[FXT_ATOMIC_ADD_I32(W.copy_out_count, 1)] = brick;
+    }
+}
+
+// ---- a brick of the copy list: its values are final; bring the other buffer (and mask) up to date ----------------
+// `tid` of `nthreads` threads; pure streaming, 16 bytes per access.
+FXT_FN void tail_copy_brick(int tid, int nthreads, const TailParams& P, int brick, const float* p_in, float* p_out,
+                            unsigned char* m_out) {
+    const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc = brick / (P.ntx * P.nty);
+    const int x_lo = tx * P.bx, y_lo = ty * P.by, zs = P.z_out0 + zc * P.bz;
+    const int planes = (P.z_out1 - zs < P.bz ? P.z_out1 - zs : P.bz);
+    const int rows = P.ny - y_lo < P.by ? P.ny - y_lo : P.by;
+    const int qpr = (P.nx - x_lo < P.bx ? P.nx - x_lo : P.bx) >> 2;  // quads per row inside the grid
+    const int nxb = P.nx >> 3;
+    for (int i = tid; i < planes * rows * qpr; i += nthreads) {
+        const int xq = i % qpr, rz = i / qpr;
+        const size_t row = (size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows);
+        const size_t at = row * P.nx + x_lo + 4 * xq;
+        *reinterpret_cast<Quad*>(p_out + at) = *reinterpret_cast<const Quad*>(p_in + at);
+        if (xq & 1) m_out[row * nxb + ((x_lo + 4 * xq) >> 3)] = 0;
+    }
+}
+
+}  // namespace fxb

@@ -1,0 +1,92 @@
+// tail_emu.cpp — CPU emulation of jacobi_tail_kernel (fluidx12_b200/csrc/jacobi_tail.cu).  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel's real body (jacobi_tail_body.cuh) with g++: CUDA threads become a loop over `tid`, every
+// __syncthreads() becomes the end of such a loop, shared memory becomes a heap block, atomics become plain
+// read-modify-writes (CTAs run one after the other).  tests/test_tail_emu.py drives it against the oracle
+// (oracle/fluid_oracle.cpp) bit for bit, so the indexing, clamp and freeze logic of the CUDA kernel is checked
+// on the CPU; the product library never links or loads this file.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../fluidx12_b200/csrc/jacobi_tail_body.cuh"
+
+namespace {
+
+using namespace fxb;
+
+template <class S>
+void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const float* p_in, float* p_out,
+              const float* rhs, const unsigned char* m_in, unsigned char* m_out, unsigned long long* active_after_s0) {
+    std::vector<unsigned char> smem(S::kBytes + 64, 0);
+    TailShared<S> sh;
+    sh.p = reinterpret_cast<float*>(smem.data());
+    sh.rhs = sh.p + S::kPFloats;
+    sh.ctrl = reinterpret_cast<unsigned*>(sh.rhs + S::kRhsFloats);
+    sh.nib = reinterpret_cast<unsigned char*>(sh.ctrl + S::kCtrlWords);
+    // poison the staged data so that a read of something never written shows up as a mismatch
+    for (int i = 0; i < S::kPFloats + S::kRhsFloats; ++i) sh.p[i] = 1.0e30f;
+    for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0u;
+    const TailItem<S> it = tail_item<S>(P, brick, sub);
+    std::vector<TailThread<S>> th(S::kThreads);
+    if (it.ex > 0) {
+        for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_flags<S>(tid, th[tid], sh, it, P, m_in);
+        if (sh.ctrl[0]) {
+            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_load<S>(th[tid], sh, it, P, p_in, rhs);
+            for (int s = 1; s <= P.levels; ++s) {
+                for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_relax<S>(th[tid], sh, it, P, s);
+                for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_publish<S>(th[tid], sh, s, s == P.levels);
+            }
+            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_store<S>(th[tid], sh, it, P, p_out);
+            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_store_mask<S>(th[tid], sh, it, P, m_out);
+        } else {
+            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_copy<S>(th[tid], it, P, p_in, p_out, m_out);
+        }
+    }
+    tail_finish_item<S>(sh, P, W, brick, active_after_s0);
+}
+
+}  // namespace
+
+extern "C" {
+
+// geom = {nx, ny, nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1, bx, by, bz}
+// flags = {first, early_exit, levels, tt}
+// Returns the number of work items processed, or -1 for an unsupported shape.
+int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float* p_out, const float* rhs,
+                    const unsigned char* m_in, unsigned char* m_out, const int* relax_in, int n_relax,
+                    const int* copy_in, int n_copy, int* relax_out, int* relax_out_count, int* copy_out,
+                    int* copy_out_count, int* brick_state, unsigned long long* active_after_s0) {
+    TailParams P;
+    P.nx = geom[0]; P.ny = geom[1]; P.nz_alloc = geom[2];
+    P.z_face_lo = geom[3]; P.z_face_hi = geom[4]; P.z_out0 = geom[5]; P.z_out1 = geom[6];
+    P.bx = geom[7]; P.by = geom[8]; P.bz = geom[9];
+    P.ntx = (P.nx + P.bx - 1) / P.bx;
+    P.nty = (P.ny + P.by - 1) / P.by;
+    P.first = flags[0]; P.early_exit = flags[1]; P.levels = flags[2];
+    const int tt = flags[3];
+    using S4 = TailShape<4, 10, 12, 8>;
+    using S2 = TailShape<2, 10, 12, 8>;
+    if (P.bx % S4::OX != 0 || P.by > S4::OY || P.bz > S4::OZ || P.nx % 8 != 0 || P.levels > tt) return -1;
+    P.nsub = P.bx / S4::OX;
+    TailWork W;
+    W.relax_in = relax_in; W.copy_in = copy_in; W.n_relax = n_relax; W.n_copy = n_copy;
+    W.relax_out = relax_out; W.copy_out = copy_out;
+    W.relax_out_count = relax_out_count; W.copy_out_count = copy_out_count;
+    W.brick_state = brick_state;
+    const int items = n_copy + n_relax * P.nsub;
+    for (int item = 0; item < items; ++item) {
+        if (item < n_copy) {
+            for (int tid = 0; tid < S4::kThreads; ++tid)
+                tail_copy_brick(tid, S4::kThreads, P, copy_in[item], p_in, p_out, m_out);
+            continue;
+        }
+        const int r = item - n_copy;
+        if (tt == 4) run_item<S4>(P, W, relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out, active_after_s0);
+        else if (tt == 2) run_item<S2>(P, W, relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out, active_after_s0);
+        else return -1;
+    }
+    return items;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""ctypes wrapper of tests/emu/libtail_emu.so — the CPU emulation of the tail kernel's body (test infrastructure)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libtail_emu.so"])
+        _LIB = C.CDLL(os.path.join(_HERE, "libtail_emu.so"))
+        _LIB.tail_emu_launch.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class BrickGrid:
+    """Brick decomposition of jacobi_fused.cu: bricks of bx x by x bz output cells, brick id = (zc*nty + ty)*ntx + tx."""
+
+    def __init__(self, nx, ny, nz, bx=120, by=12, bz=8):
+        self.nx, self.ny, self.nz, self.bx, self.by, self.bz = nx, ny, nz, bx, by, bz
+        self.ntx, self.nty, self.nzc = -(-nx // bx), -(-ny // by), -(-nz // bz)
+        self.n = self.ntx * self.nty * self.nzc
+
+    def region(self, brick):
+        tx, ty, zc = brick % self.ntx, (brick // self.ntx) % self.nty, brick // (self.ntx * self.nty)
+        return (slice(zc * self.bz, min((zc + 1) * self.bz, self.nz)), slice(ty * self.by, min((ty + 1) * self.by, self.ny)),
+                slice(tx * self.bx, min((tx + 1) * self.bx, self.nx)))
+
+
+def pack_mask(active):
+    """[z][y][x] 0/1 -> bit-packed [z][y][nx/8], bit j of a byte = cell 8*byte + j (the layout of jacobi_fused.cu)."""
+    return np.packbits(active.astype(np.uint8), axis=-1, bitorder="little")
+
+
+def unpack_mask(mask, nx):
+    return np.unpackbits(mask, axis=-1, bitorder="little")[..., :nx]
+
+
+def launch(g: BrickGrid, p_in, p_out, rhs, m_in, m_out, relax_in, copy_in, brick_state, hist_s0, first, early_exit=True,
+           levels=4, tt=4):
+    """One emulated launch.  Returns (relax_out, copy_out).  p_out / m_out / brick_state / hist_s0 are updated in place."""
+    geom = np.array([g.nx, g.ny, g.nz, 0, g.nz, 0, g.nz, g.bx, g.by, g.bz], np.int32)
+    flags = np.array([int(first), int(early_exit), levels, tt], np.int32)
+    relax_in = np.ascontiguousarray(relax_in, np.int32)
+    copy_in = np.ascontiguousarray(copy_in, np.int32)
+    relax_out, copy_out = np.full(g.n, -1, np.int32), np.full(g.n, -1, np.int32)
+    nr, nc = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    rc = lib().tail_emu_launch(_p(geom), _p(flags), _p(p_in), _p(p_out), _p(rhs), _p(m_in), _p(m_out), _p(relax_in),
+                               C.c_int(relax_in.size), _p(copy_in), C.c_int(copy_in.size), _p(relax_out), _p(nr),
+                               _p(copy_out), _p(nc), _p(brick_state), _p(hist_s0))
+    assert rc >= 0, "unsupported shape"
+    return relax_out[:nr[0]].copy(), copy_out[:nc[0]].copy()

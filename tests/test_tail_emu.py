@@ -1,0 +1,99 @@
+"""The tail kernel's body (fluidx12_b200/csrc/jacobi_tail_body.cuh), emulated on the CPU, against the oracle.
+
+The emulation runs the same statements the CUDA kernel runs (tests/emu/tail_emu.cpp), so these tests pin the
+indexing, the clamp-to-edge rule, the shrinking-validity argument, the freeze flags, the bit-packed masks and the
+work-list hand-over bit for bit without a GPU.  The GPU tests then only have to show that the CUDA build of the same
+body agrees (tests/test_gpu_tail.py)."""
+import numpy as np
+import pytest
+
+from tests import tail_emu as E
+from tests.util import smooth_state
+
+
+def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True):
+    """Whole pressure solve by emulated tail launches only (first launch: every brick, every cell active).
+    Returns (p, s_exec, launches).  After every launch the output buffer must equal the oracle's state everywhere."""
+    nz, ny, nx = s2.shape
+    g = E.BrickGrid(nx, ny, nz, *grid)
+    rhs = (-0.5 * s2).astype(np.float32)
+    assert np.array_equal(rhs.astype(np.float64), -0.5 * s2.astype(np.float64))  # exact
+    p = [p_start.copy(), np.full_like(p_start, np.nan)]   # NaN = never written: must not leak into a result
+    m = [np.zeros((nz, ny, nx // 8), np.uint8), np.zeros((nz, ny, nx // 8), np.uint8)]
+    brick_state = np.zeros(g.n, np.int32)
+    hist = np.zeros(iters + 8, np.uint64)
+    p_ref, act_ref = p_start.copy(), np.ones(s2.shape, np.uint8)
+    relax, copy = np.arange(g.n, dtype=np.int32), np.zeros(0, np.int32)
+    done, seq = 0, 0
+    while done < iters:
+        levels = min(tt, iters - done)
+        src, dst = seq & 1, (seq + 1) & 1
+        relax, copy_next = E.launch(g, p[src], p[dst], rhs, m[src], m[dst], relax, copy, brick_state, hist[done:],
+                                    first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt)
+        p_ref, act_ref, counts = oracle_mod.jacobi_sweeps_slab(s2, p_ref, act_ref, levels, nz, 0, 0, nz, early_exit)
+        done += levels
+        seq += 1
+        assert not brick_state.any()
+        assert np.array_equal(hist[done - levels:done].astype(np.int64), counts), (seq, hist[done - levels:done], counts)
+        if check_each:
+            assert np.array_equal(p[dst], p_ref), (seq, int((p[dst] != p_ref).sum()))
+            # flags of every brick that was relaxed or copied in this launch are current in the output mask
+            got = E.unpack_mask(m[dst], nx)
+            if seq >= 2 or True:
+                touched = np.zeros(s2.shape, bool)
+                for b in np.concatenate([relax, copy_next]):
+                    touched[g.region(int(b))] = True
+                assert np.array_equal(got[touched], act_ref[touched] if early_exit else np.ones_like(got[touched]))
+        # the next lists partition the bricks that were relaxed: still active -> relax, frozen -> copy
+        for b in relax:
+            assert act_ref[g.region(int(b))].any() or not early_exit
+        for b in copy_next:
+            assert not act_ref[g.region(int(b))].any()
+        copy = copy_next
+        if counts[-1] == 0:
+            break
+    s_exec = 1 + int(np.count_nonzero(hist[:iters - 1])) if iters else 0
+    return p[seq & 1], min(s_exec, iters), seq
+
+
+def developed_state(oracle_mod, n, steps):
+    """Divergence (x2) and warm-start pressure of a developed emitter-driven flow: realistic freeze behaviour."""
+    f = oracle_mod.FluidOracle(*n)
+    dt = oracle_mod.dt_for_grid(*n)
+    for _ in range(steps):
+        f.step(dt)
+    vel, col, p = f.get_field(oracle_mod.FIELD_VEL), f.get_field(oracle_mod.FIELD_COLOR), f.get_field(oracle_mod.FIELD_PRESSURE)
+    vo, _ = oracle_mod.advect(vel, col, dt)
+    return oracle_mod.divergence2x(vo), p
+
+
+@pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
+def test_tail_only_solve_matches_oracle(oracle_mod, n, steps):
+    s2, p0 = developed_state(oracle_mod, n, steps)
+    p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, 64, True)
+    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8))
+    assert np.array_equal(p_got, p_want)
+    assert s_got == s_want
+    assert launches == -(-s_want // 4)
+
+
+def test_tail_random_field_no_early_exit(oracle_mod):
+    """Dense activity (nothing freezes), a grid whose last brick column is 16 cells wide, 10 sweeps = 4 + 4 + 2."""
+    n = (136, 136, 20)
+    _, _, p0 = smooth_state(*n, seed=7)
+    rng = np.random.default_rng(5)
+    s2 = (rng.integers(-2 ** 20, 2 ** 20, size=p0.shape) * 2.0 ** -24).astype(np.float32)
+    p_want, _, _, _ = oracle_mod.jacobi(s2, p0, 10, False)
+    p_got, _, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), iters=10, early_exit=False)
+    assert launches == 3
+    assert np.array_equal(p_got, p_want)
+
+
+def test_tail_two_sweep_shape_and_thin_bricks(oracle_mod):
+    """TT = 2 instantiation, bricks thinner than the compiled sub-block (by = 10, bz = 5), odd plane count."""
+    n = (64, 64, 13)
+    s2, p0 = developed_state(oracle_mod, n, 8)
+    p_want, s_want, _, _ = oracle_mod.jacobi(s2, p0, 64, True)
+    p_got, s_got, _ = solve_with_tail(oracle_mod, s2, p0, (120, 10, 5), tt=2)
+    assert np.array_equal(p_got, p_want)
+    assert s_got == s_want
