@@ -40,6 +40,13 @@ struct StepState {
     unsigned long long bricks_processed;  // cumulative: bricks fully relaxed by fused passes
     unsigned long long bricks_copied;     // cumulative: frozen bricks copied once to the other buffer
     unsigned long long active_after[128];  // [k] = cells still active after sweep k (this rank)
+    // dynamic schedule (bulk passes + tail launches, jacobi_tail.cu); reset by begin_step_kernel
+    int seq;                             // relax kernels executed so far in this frame (= pressure ping-pong flips)
+    int sweeps_done;                     // sweeps completed so far in this frame
+    int done_ctas;                       // CTAs of the running relax kernel that have finished
+    int tail_launches;                   // tail launches that did work in the last step
+    unsigned long long tail_bricks;      // cumulative: bricks relaxed by tail launches (TT sweeps each)
+    unsigned long long tail_subblocks_relaxed;  // cumulative: sub-blocks that held an active cell (the rest are copies)
 };
 
 // Static emitter table (Impulse.hlsli:14-18 is time-independent): basis values of the voxels in a

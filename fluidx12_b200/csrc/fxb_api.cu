@@ -84,6 +84,10 @@ struct fxb_sim {
     int h_adv = 0;            // advection halo (back-trace reach in planes)
     int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (FXB_JACOBI_GROUP; > 1 is experimental)
     int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
+    // Dynamic schedule (FXB_TAIL=1, single GPU; experimental until measured on B200 — DESIGN.md §5): bulk passes
+    // 0..tail_mains-1 interleaved with tail launches (jacobi_tail.cu), then tail launches only.
+    bool tail = false;
+    int tail_mains = 5;
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
 
@@ -199,7 +203,33 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             launches = 2;
             break;
         case PH_JACOBI:
-            if (s->fused) {
+            if (s->fused && s->tail) {
+                // Dynamic schedule: which kernel relaxes is decided on the device (jacobi_tail.cu).  A group is one
+                // tail launch (TT sweeps) followed by the TT/T bulk passes that cover the same sweeps; the tail
+                // launch of a group runs iff few enough bricks are listed, the bulk passes run iff it did not.
+                const int T = s->fuse_t, TT = fxb::jacobi_tail_sweeps(), iters = s->cfg.jacobi_iters;
+                const int npass = (iters + T - 1) / T;
+                const int mains = std::min(std::max(s->tail_mains, 1), npass);
+                cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
+                auto bulk = [&](int k) {
+                    fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, iters, s->cfg.early_exit, false,
+                                                  0, 0, st);
+                    ++launches;
+                };
+                auto tail = [&](int threshold) {
+                    fxb::launch_jacobi_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit, threshold, st);
+                    ++launches;
+                };
+                bulk(0);
+                for (int k = 1; k < mains;) {
+                    tail(s->jac.tail_threshold);
+                    for (int j = 0; j < std::max(TT / T, 1) && k < mains; ++j, ++k) bulk(k);
+                }
+                // every group above advanced the solve by at least its bulk passes' sweeps: mains * T are done
+                for (int done = mains * T; done < iters; done += TT) tail(-1);
+                fxb::launch_finish_solve_dynamic(s->d_frame, s->d_state, iters, st);
+                ++launches;
+            } else if (s->fused) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
                 const bool mg = s->multi() && s->dt > 0.0f;
@@ -477,12 +507,33 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         if (e != cudaSuccess)
             return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
         s->fused = true;
+        const char* tail_env = getenv("FXB_TAIL");
+        if (tail_env && atoi(tail_env) != 0 && !s->multi() && s->jac.variant == 0 &&
+            fxb::jacobi_tail_supported(s->jac, s->dom)) {
+            e = cudaMalloc((void**)&s->jac.brick_state, nb * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemset(s->jac.brick_state, 0, nb * sizeof(int));
+            if (e != cudaSuccess)
+                return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
+            s->jac.dynamic = true;
+            s->jac.tail_threshold = 8192;
+            s->jac.tail_grid = s->jac.num_sms * 8;
+            if (const char* v = getenv("FXB_TAIL_THRESHOLD")) s->jac.tail_threshold = atoi(v);
+            if (const char* v = getenv("FXB_TAIL_GRID")) s->jac.tail_grid = std::max(1, atoi(v));
+            if (const char* v = getenv("FXB_TAIL_MAINS")) s->tail_mains = std::max(1, atoi(v));
+            s->tail = true;
+        }
     }
     if (s->cfg.use_graph && !s->multi()) {
         rc = capture_graph(s, 0, 0);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
-        const int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
+        int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
+        if (s->tail) {  // same count as the dynamic schedule of enqueue_phase
+            const int T = s->fuse_t, TT = fxb::jacobi_tail_sweeps(), iters = s->cfg.jacobi_iters;
+            const int mains = std::min(std::max(s->tail_mains, 1), jl);
+            const int per_group = std::max(TT / T, 1);
+            jl = mains + (mains - 1 + per_group - 1) / per_group + std::max(0, (iters - mains * T + TT - 1) / TT);
+        }
         s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
     }
     if (s->multi()) {
@@ -522,6 +573,7 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.work_list[0]);
     cudaFree(s->jac.work_list[1]);
     cudaFree(s->jac.work_count);
+    cudaFree(s->jac.brick_state);
     cudaFree(s->emitter_basis);
     cudaFree(s->axis_tables);
     cudaFree(s->d_frame);
@@ -651,6 +703,19 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
     }
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
+}
+
+int fxb_get_tail_stats(fxb_sim* s, uint64_t* out4) {
+    if (!s || !out4) return fail(FXB_ERR_INVALID, "fxb_get_tail_stats: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    fxb::StepState st;
+    FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, s->last_stream));
+    FXB_CUDA(cudaStreamSynchronize(s->last_stream));
+    out4[0] = s->tail ? 1 : 0;
+    out4[1] = (uint64_t)st.tail_launches;
+    out4[2] = st.tail_bricks;
+    out4[3] = st.tail_subblocks_relaxed;
+    return FXB_OK;
 }
 
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {

@@ -522,21 +522,23 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
     }
 }
 
+// One fused pass.  P.pass is the position in the frame's relax sequence (it selects the work lists, the freeze masks
+// and the side of the pressure ping-pong), s0 the number of sweeps completed before it.  Returns the sweeps applied
+// (0 when the pass had nothing to do).
 template <class S>
-__global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
-jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
-                   const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
-                   StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0, unsigned char* m1,
-                   const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
+__device__ __forceinline__ int jacobi_pass_body(const CUtensorMap& map_p0, const CUtensorMap& map_p1,
+                                                const CUtensorMap& map_rhs, const FrameParams* __restrict__ frame,
+                                                StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0,
+                                                unsigned char* m1, const WorkLists& W, const PassParams& P,
+                                                const int s0) {
     FXB_SHAPE_CONSTANTS(S);
-    const int s0 = P.pass * T;  // sweeps completed before this pass
     // independent loads first (one round trip instead of a chain), then the decisions
     const float dt = frame->dt;
     const int p_cur = state->p_cur;
     const unsigned long long still = P.pass > 0 ? state->active_after[s0 - 1] : 1ull;
     const int n_relax = W.relax_count[P.pass], n_copy = W.copy_count[P.pass];
-    if (!(0.0f < dt)) return;
-    if (P.pass > 0 && !P.run_all && still == 0ull) return;
+    if (!(0.0f < dt)) return 0;
+    if (P.pass > 0 && !P.run_all && still == 0ull) return 0;
     const int levels = min(T, P.levels_total - s0);
 
     const int sel = (p_cur + P.pass) & 1;
@@ -618,6 +620,39 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         }
         relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, -1, tile % P.ntx, tile / P.ntx, zs, ze, levels, s0);
     }
+    return levels;
+}
+
+// DYN = false: the static schedule (launch k is pass k of the frame).  DYN = true: the schedule is shared with the
+// tail kernel (jacobi_tail.cu): the position in the frame's relax sequence and the sweeps completed so far come from
+// StepState, and this launch only runs when the solve stands exactly at the sweep count its static index expects
+// (otherwise a tail launch has taken over, or will).
+template <class S, bool DYN>
+__global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
+jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
+                   const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
+                   StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0, unsigned char* m1,
+                   const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
+    if constexpr (!DYN) {
+        jacobi_pass_body<S>(map_p0, map_p1, map_rhs, frame, state, p0, p1, m0, m1, W, P, P.pass * S::T);
+    } else {
+        const int seq = state->seq, s0 = state->sweeps_done;
+        if (s0 != P.pass * S::T) return;
+        PassParams Q = P;
+        Q.pass = seq;
+        const int levels = jacobi_pass_body<S>(map_p0, map_p1, map_rhs, frame, state, p0, p1, m0, m1, W, Q, s0);
+        if (levels == 0) return;
+        // the last CTA to finish advances the shared schedule (every CTA has read it long before)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
+                state->done_ctas = 0;
+                state->seq = seq + 1;
+                state->sweeps_done = s0 + levels;
+            }
+        }
+    }
 }
 
 
@@ -649,12 +684,12 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int nz_alloc,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class S>
+template <class S, bool DYN = false>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
                          int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)S::kBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
@@ -675,7 +710,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
     W.copy[0] = J.work_list[0] + nbricks; W.copy[1] = J.work_list[1] + nbricks;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np;
-    jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
+    jacobi_pass_kernel<S, DYN><<<grid, S::kThreads, S::kBytes, stream>>>(
         *reinterpret_cast<const CUtensorMap*>(J.map_p[0]), *reinterpret_cast<const CUtensorMap*>(J.map_p[1]),
         *reinterpret_cast<const CUtensorMap*>(J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P);
     return cudaGetLastError();
@@ -691,8 +726,11 @@ cudaError_t launch_T(const FusedJacobi& J, const Domain& d, const FrameParams* f
                      int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
     switch (J.variant) {
         case 0:
-            if constexpr (T <= 2)
+            if constexpr (T <= 2) {
+                if (J.dynamic)  // schedule shared with the tail kernel (jacobi_tail.cu)
+                    return launch_shape<Shape<T, 2, 8, 2, 2>, true>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
                 return launch_shape<Shape<T, 2, 8, 2, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+            }
             break;
         case 1: return launch_shape<Shape<T, 2, 16, 1>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
         case 2: return launch_shape<Shape<T, 4, 8, 2>>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, stream);
@@ -738,6 +776,10 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
 size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty * J.nzc; }
 
 size_t fused_jacobi_brick_cells(const FusedJacobi& J) { return (size_t)kOutX * (J.tile_y - 2 * J.T) * J.bz; }
+
+void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
+    out[0] = kOutX; out[1] = J.tile_y - 2 * J.T; out[2] = J.bz;
+}
 
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,

@@ -1,0 +1,175 @@
+// jacobi_tail.cu — block-resident multi-sweep Jacobi kernel for the tail of the pressure solve (sm_100a).
+//
+// Replaces, like jacobi_fused.cu, the relaxation loop of FluidX12/Content/Shaders/CSPoisson.hlsli:8-26 (called from
+// CSProject3D.hlsl:93) under the deterministic restatement of SURVEY.md App. A.3.  Why a second kernel: after the first
+// couple of sweeps only a few percent of the cells are still active (tools/tail_stats.py: 256^3 after 100 steps has
+// 9.6 % active cells after sweep 2, 0.6 % after sweep 18, none after sweep 50), yet every further fused pass of the
+// bulk kernel costs a launch plus the latency of one z-marching brick chain (~25-35 us measured), ~30 times per step.
+// This kernel advances kSweeps = 4 sweeps per launch on 40 x 12 x 8 sub-blocks of the still-active bricks, each held
+// on chip by one CTA for all four sweeps (body and data layout: jacobi_tail_body.cuh), so the tail needs half the
+// launches of the T = 2 bulk kernel and the critical path of a launch is four short phases.
+//
+// Schedule ("dynamic", fxb_api.cu): bulk pass 0 always runs; afterwards tail launches and bulk passes are interleaved
+// in the captured graph and decide on the device which of them does the work: a tail launch runs when at most
+// `threshold` bricks are listed (or always, once the bulk passes of the schedule are used up), a bulk pass runs only
+// when StepState::sweeps_done equals the sweep count its static index stands for.  Both kernels use the same work
+// lists, freeze masks and ping-pong buffers, indexed by StepState::seq (relax kernels executed so far in the frame).
+// Results are bit-identical whichever kernel relaxes a brick.
+#include "common.cuh"
+#include "jacobi_tail_body.cuh"
+#include "kernels.h"
+
+namespace fxb {
+
+namespace {
+
+using TailS = TailShape<4, 10, 12, 8>;  // 4 sweeps, sub-block 40 x 12 x 8, window 48 x 20 x 16, 256 threads
+
+struct TailLaunch {
+    TailParams P;      // levels / first are filled in on the device
+    int iters;         // ITER
+    int threshold;     // run only when at most this many bricks are listed; < 0: always
+    int nbricks;
+    int* list[2];      // [2 * bricks] per parity of seq: bricks to relax, then bricks to copy (jacobi_fused.cu)
+    int* relax_count;  // [seq]
+    int* copy_count;   // [seq]
+    int* brick_state;
+};
+
+template <class S>
+__global__ void __launch_bounds__(S::kThreads, 2)
+jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
+                   const float* __restrict__ rhs, unsigned char* m0, unsigned char* m1,
+                   const __grid_constant__ TailLaunch L) {
+    const float dt = frame->dt;
+    const int seq = state->seq, s0 = state->sweeps_done, p_cur = state->p_cur;
+    if (!(0.0f < dt)) return;
+    if (seq == 0 || s0 <= 0 || s0 >= L.iters) return;         // bulk pass 0 builds the lists; nothing left to do
+    if (state->active_after[s0 - 1] == 0ull) return;           // every cell is frozen: the solve is over
+    const int n_relax = L.relax_count[seq], n_copy = L.copy_count[seq];
+    if (L.threshold >= 0 && n_relax > L.threshold) return;     // too many bricks: the bulk kernel is the better tool
+
+    TailParams P = L.P;
+    P.levels = min(S::TT, L.iters - s0);
+    P.first = 0;
+    const int sel = (p_cur + seq) & 1;
+    const float* p_in = sel ? p1 : p0;
+    float* p_out = sel ? p0 : p1;
+    const unsigned char* m_in = (seq & 1) ? m1 : m0;
+    unsigned char* m_out = (seq & 1) ? m0 : m1;
+    TailWork W;
+    W.relax_in = L.list[seq & 1];
+    W.copy_in = L.list[seq & 1] + L.nbricks;
+    W.n_relax = n_relax;
+    W.n_copy = n_copy;
+    W.relax_out = L.list[(seq + 1) & 1];
+    W.copy_out = L.list[(seq + 1) & 1] + L.nbricks;
+    W.relax_out_count = L.relax_count + seq + 1;
+    W.copy_out_count = L.copy_count + seq + 1;
+    W.brick_state = L.brick_state;
+
+    extern __shared__ __align__(16) float tail_sm[];
+    TailShared<S> sh;
+    sh.p = tail_sm;
+    sh.rhs = sh.p + S::kPFloats;
+    sh.ctrl = reinterpret_cast<unsigned*>(sh.rhs + S::kRhsFloats);
+    sh.nib = reinterpret_cast<unsigned char*>(sh.ctrl + S::kCtrlWords);
+
+    const int tid = threadIdx.x;
+    const int items = n_copy + n_relax * P.nsub;
+    unsigned relaxed = 0;  // sub-blocks of this CTA that held an active cell (thread 0)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        if (item < n_copy) {  // a brick that froze in the previous kernel: one copy into the other buffer
+            tail_copy_brick(tid, S::kThreads, P, W.copy_in[item], p_in, p_out, m_out);
+            continue;
+        }
+        const int r = item - n_copy;
+        const int brick = W.relax_in[r / P.nsub];
+        const TailItem<S> it = tail_item<S>(P, brick, r % P.nsub);
+        __syncthreads();  // the previous item is finished with shared memory
+        if (tid < S::kCtrlWords) sh.ctrl[tid] = 0u;
+        __syncthreads();
+        if (it.ex > 0) {
+            TailThread<S> t;
+            tail_phase_flags<S>(tid, t, sh, it, P, m_in);
+            __syncthreads();
+            if (sh.ctrl[0] != 0u) {
+                tail_phase_load<S>(t, sh, it, P, p_in, rhs);
+                __syncthreads();
+                for (int s = 1; s <= P.levels; ++s) {
+                    tail_phase_relax<S>(t, sh, it, P, s);
+                    __syncthreads();
+                    tail_phase_publish<S>(t, sh, s, s == P.levels);
+                    __syncthreads();
+                }
+                tail_phase_store<S>(t, sh, it, P, p_out);
+                __syncthreads();
+                tail_phase_store_mask<S>(t, sh, it, P, m_out);
+                if (tid == 0) ++relaxed;
+            } else {
+                tail_phase_copy<S>(t, it, P, p_in, p_out, m_out);
+            }
+        }
+        if (tid == 0) tail_finish_item<S>(sh, P, W, brick, state->active_after + s0);
+    }
+
+    // the last CTA to finish advances the shared schedule (every CTA has read it long before)
+    __syncthreads();
+    if (tid == 0) {
+        if (relaxed) atomicAdd(&state->tail_subblocks_relaxed, (unsigned long long)relaxed);
+        __threadfence();
+        if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
+            state->done_ctas = 0;
+            state->seq = seq + 1;
+            state->sweeps_done = s0 + P.levels;
+            state->tail_launches += 1;
+            state->tail_bricks += (unsigned long long)n_relax;
+            state->bricks_copied += (unsigned long long)n_copy;
+        }
+    }
+}
+
+}  // namespace
+
+int jacobi_tail_sweeps() { return TailS::TT; }
+
+bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d) {
+    int ext[3];
+    fused_jacobi_brick_extent(J, ext);
+    return (d.nx % 8) == 0 && ext[0] % TailS::OX == 0 && ext[0] % 8 == 0 && ext[1] <= TailS::OY && ext[2] <= TailS::OZ &&
+           ext[0] / TailS::OX <= 200;
+}
+
+cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                               int iters, int early_exit, int threshold, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(jacobi_tail_kernel<TailS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TailS::kBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int ext[3];
+    fused_jacobi_brick_extent(J, ext);
+    TailLaunch L;
+    L.P.nx = d.nx; L.P.ny = d.ny; L.P.nz_alloc = d.nz_alloc;
+    L.P.z_face_lo = 0 - d.z_first;
+    L.P.z_face_hi = d.nz - d.z_first;
+    L.P.z_out0 = d.z_own0 - d.z_first; L.P.z_out1 = d.z_own1 - d.z_first;
+    L.P.bx = ext[0]; L.P.by = ext[1]; L.P.bz = ext[2];
+    L.P.ntx = J.ntx; L.P.nty = J.nty;
+    L.P.nsub = ext[0] / TailS::OX;
+    L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = TailS::TT;
+    L.iters = iters;
+    L.threshold = threshold;
+    L.nbricks = J.ntx * J.nty * J.nzc;
+    L.list[0] = J.work_list[0]; L.list[1] = J.work_list[1];
+    const int np = FusedJacobi::kMaxPasses + 1;
+    L.relax_count = J.work_count; L.copy_count = J.work_count + np;
+    L.brick_state = J.brick_state;
+    jacobi_tail_kernel<TailS><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
+        frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+    return cudaGetLastError();
+}
+
+}  // namespace fxb

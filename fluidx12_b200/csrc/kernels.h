@@ -43,6 +43,12 @@ struct FusedJacobi {
     int* work_list[2] = {nullptr, nullptr};       // [2 * bricks] per pass parity: bricks to relax, then bricks to copy
     int* work_count = nullptr;                    // [3][kMaxPasses + 1]: relax count and copy count per pass (+ spare)
     int num_sms = 0;
+    // Dynamic schedule (FXB_TAIL=1, single GPU): bulk passes and tail launches share the relax sequence through
+    // StepState::seq / sweeps_done; see jacobi_tail.cu.
+    bool dynamic = false;
+    int* brick_state = nullptr;                   // [bricks] sub-block arrivals of the tail kernel; zero between launches
+    int tail_threshold = 0;                       // a tail launch takes over once at most this many bricks are listed
+    int tail_grid = 0;                            // CTAs of a tail launch
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
@@ -51,8 +57,17 @@ bool fused_jacobi_supported(const Domain& d);
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
+void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
                                      cudaStream_t stream);
+
+// jacobi_tail.cu — TT = 4 sweeps per launch on sub-blocks kept on chip, for the tail of the solve in which few bricks
+// are still active (dynamic schedule only).  threshold < 0: run whatever the list length.
+bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d);
+int jacobi_tail_sweeps();
+cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                               int iters, int early_exit, int threshold, cudaStream_t stream);
+void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 
 }  // namespace fxb

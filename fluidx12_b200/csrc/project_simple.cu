@@ -43,7 +43,10 @@ __device__ __forceinline__ float comp(const uint2* __restrict__ vel, size_t i, i
 __global__ void begin_step_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters) {
     const int k = threadIdx.x;
     if (k < iters && k < 128) state->active_after[k] = 0ull;
-    if (k == 0) { state->s_exec = 0; state->passes = 0; }
+    if (k == 0) {
+        state->s_exec = 0; state->passes = 0;
+        state->seq = 0; state->sweeps_done = 0; state->done_ctas = 0; state->tail_launches = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) divergence_kernel(Domain d, const FrameParams* __restrict__ frame,
@@ -128,6 +131,23 @@ __global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepS
     state->total_passes += (unsigned long long)passes;
 }
 
+// Dynamic schedule (jacobi_tail.cu): the relax kernels counted their own ping-pong flips in StepState::seq.
+__global__ void finish_solve_dynamic_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state,
+                                            int iters) {
+    if (threadIdx.x != 0) return;
+    int s = 0;
+    if (0.0f < frame->dt && iters > 0) {
+        s = 1;
+        while (s < iters && state->active_after[s - 1] != 0ull) ++s;
+    }
+    const int flips = 0.0f < frame->dt ? state->seq : 0;
+    state->s_exec = s;
+    state->passes = flips;
+    state->p_cur = (state->p_cur + flips) & 1;
+    state->total_sweeps += (unsigned long long)s;
+    state->total_passes += (unsigned long long)flips;
+}
+
 __global__ void __launch_bounds__(256) gradient_kernel(Domain d, const FrameParams* __restrict__ frame,
                                                        const uint2* __restrict__ vel_in, const float* p0,
                                                        const float* p1, uint2* __restrict__ vel_out,
@@ -195,6 +215,10 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
 void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int sweeps_per_flip, int force_passes,
                          cudaStream_t stream) {
     finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, sweeps_per_flip, force_passes);
+}
+
+void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream) {
+    finish_solve_dynamic_kernel<<<1, 32, 0, stream>>>(frame, state, iters);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,

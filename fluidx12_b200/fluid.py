@@ -142,6 +142,13 @@ class Fluid:
         B.check(B.lib().fxb_get_freeze_histogram(self._handle(), h.ctypes.data_as(C.c_void_p), n))
         return h
 
+    def tail_stats(self) -> dict:
+        """Counters of the dynamic pressure-solve schedule (FXB_TAIL=1): see fxb_get_tail_stats."""
+        out = np.zeros(4, np.uint64)
+        B.check(B.lib().fxb_get_tail_stats(self._handle(), out.ctypes.data_as(C.c_void_p)))
+        return {"enabled": bool(out[0]), "tail_launches_last_step": int(out[1]), "tail_bricks": int(out[2]),
+                "tail_subblocks_relaxed": int(out[3])}
+
     def profile_step(self):
         """One un-graphed step timed per phase: dict of milliseconds."""
         ms = (C.c_float * 6)()

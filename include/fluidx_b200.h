@@ -121,6 +121,12 @@ int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void*
 /* Reads back the device-side counters of the last step (synchronises the handle's stream). */
 int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 
+/* Counters of the dynamic pressure-solve schedule (environment FXB_TAIL=1 at fxb_create; single GPU, default brick
+ * shape): out4[0] = 1 when it is in use, out4[1] = tail-kernel launches that did work in the last step, out4[2] =
+ * cumulative bricks relaxed by tail launches (4 sweeps each), out4[3] = cumulative 40x12x8 sub-blocks among them that
+ * still held an active cell.  Synchronises the handle's stream. */
+int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out4);
+
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);
