@@ -94,7 +94,7 @@ def lib() -> C.CDLL:
         L.fxb_set_field.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.fxb_get_field_async.argtypes = [vp, C.c_int, vp, C.c_size_t, vp]
         L.fxb_get_stats.argtypes = [vp, C.POINTER(FxbStats)]
-        L.fxb_get_tail_stats.argtypes = [vp, vp]
+        L.fxb_get_tail_stats.argtypes = [vp, vp, C.c_int]
         L.fxb_emitter_box.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
         L.fxb_get_freeze_histogram.argtypes = [vp, vp, C.c_int]
         L.fxb_profile_step.argtypes = [vp, C.POINTER(C.c_float), C.c_int]

@@ -47,6 +47,7 @@ struct StepState {
     int tail_launches;                   // tail launches that did work in the last step
     unsigned long long tail_bricks;      // cumulative: bricks relaxed by tail launches (TT sweeps each)
     unsigned long long tail_subblocks_relaxed;  // cumulative: sub-blocks that held an active cell (the rest are copies)
+    unsigned long long tail_subblocks_dense;    // cumulative: ... of which took the dense (register-column) path
 };
 
 // Static emitter table (Impulse.hlsli:14-18 is time-independent): basis values of the voxels in a

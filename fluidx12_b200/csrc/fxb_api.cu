@@ -520,6 +520,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (const char* v = getenv("FXB_TAIL_THRESHOLD")) s->jac.tail_threshold = atoi(v);
             if (const char* v = getenv("FXB_TAIL_GRID")) s->jac.tail_grid = std::max(1, atoi(v));
             if (const char* v = getenv("FXB_TAIL_MAINS")) s->tail_mains = std::max(1, atoi(v));
+            if (const char* v = getenv("FXB_TAIL_SPARSE_CAP")) s->jac.tail_sparse_cap = atoi(v);
             s->tail = true;
         }
     }
@@ -705,16 +706,15 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
 }
 
-int fxb_get_tail_stats(fxb_sim* s, uint64_t* out4) {
-    if (!s || !out4) return fail(FXB_ERR_INVALID, "fxb_get_tail_stats: null argument");
+int fxb_get_tail_stats(fxb_sim* s, uint64_t* out, int n) {
+    if (!s || !out || n < 0 || n > 16) return fail(FXB_ERR_INVALID, "fxb_get_tail_stats: bad argument");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     fxb::StepState st;
     FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, s->last_stream));
     FXB_CUDA(cudaStreamSynchronize(s->last_stream));
-    out4[0] = s->tail ? 1 : 0;
-    out4[1] = (uint64_t)st.tail_launches;
-    out4[2] = st.tail_bricks;
-    out4[3] = st.tail_subblocks_relaxed;
+    const uint64_t v[5] = {s->tail ? 1ull : 0ull, (uint64_t)st.tail_launches, st.tail_bricks, st.tail_subblocks_relaxed,
+                           st.tail_subblocks_dense};
+    for (int i = 0; i < n; ++i) out[i] = i < 5 ? v[i] : 0;
     return FXB_OK;
 }
 

@@ -69,15 +69,11 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
     W.brick_state = L.brick_state;
 
     extern __shared__ __align__(16) float tail_sm[];
-    TailShared<S> sh;
-    sh.p = tail_sm;
-    sh.rhs = sh.p + S::kPFloats;
-    sh.ctrl = reinterpret_cast<unsigned*>(sh.rhs + S::kRhsFloats);
-    sh.nib = reinterpret_cast<unsigned char*>(sh.ctrl + S::kCtrlWords);
+    const TailShared<S> sh = tail_shared<S>(tail_sm);
 
     const int tid = threadIdx.x;
     const int items = n_copy + n_relax * P.nsub;
-    unsigned relaxed = 0;  // sub-blocks of this CTA that held an active cell (thread 0)
+    unsigned relaxed = 0, dense = 0;  // sub-blocks of this CTA that held an active cell / took the dense path (thread 0)
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         if (item < n_copy) {  // a brick that froze in the previous kernel: one copy into the other buffer
             tail_copy_brick(tid, S::kThreads, P, W.copy_in[item], p_in, p_out, m_out);
@@ -93,7 +89,23 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
             TailThread<S> t;
             tail_phase_flags<S>(tid, t, sh, it, P, m_in);
             __syncthreads();
-            if (sh.ctrl[0] != 0u) {
+            const int n_list = (int)sh.ctrl[S::kCtrlTotal];
+            if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
+                tail_phase_copy<S>(t, it, P, p_in, p_out, m_out);
+            } else if (n_list <= P.sparse_cap) {  // few active cells: relax a compacted list of them
+                tail_sparse_scan<S>(tid, sh);
+                __syncthreads();
+                tail_sparse_build<S>(tid, t, sh, it, P, p_in, rhs);
+                __syncthreads();
+                for (int s = 1; s <= P.levels; ++s) {
+                    tail_sparse_relax<S>(tid, sh, it, P, n_list, s);
+                    __syncthreads();
+                    tail_sparse_commit<S>(tid, sh, n_list, s);
+                    __syncthreads();
+                }
+                tail_sparse_store<S>(t, sh, it, P, p_out, m_out);
+                if (tid == 0) ++relaxed;
+            } else {  // crowded window: register columns
                 tail_phase_load<S>(t, sh, it, P, p_in, rhs);
                 __syncthreads();
                 for (int s = 1; s <= P.levels; ++s) {
@@ -105,9 +117,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
                 tail_phase_store<S>(t, sh, it, P, p_out);
                 __syncthreads();
                 tail_phase_store_mask<S>(t, sh, it, P, m_out);
-                if (tid == 0) ++relaxed;
-            } else {
-                tail_phase_copy<S>(t, it, P, p_in, p_out, m_out);
+                if (tid == 0) { ++relaxed; ++dense; }
             }
         }
         if (tid == 0) tail_finish_item<S>(sh, P, W, brick, state->active_after + s0);
@@ -117,6 +127,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
     __syncthreads();
     if (tid == 0) {
         if (relaxed) atomicAdd(&state->tail_subblocks_relaxed, (unsigned long long)relaxed);
+        if (dense) atomicAdd(&state->tail_subblocks_dense, (unsigned long long)dense);
         __threadfence();
         if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
             state->done_ctas = 0;
@@ -160,6 +171,7 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
     L.P.ntx = J.ntx; L.P.nty = J.nty;
     L.P.nsub = ext[0] / TailS::OX;
     L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = TailS::TT;
+    L.P.sparse_cap = J.tail_sparse_cap < 0 || J.tail_sparse_cap > TailS::kListCap ? TailS::kListCap : J.tail_sparse_cap;
     L.iters = iters;
     L.threshold = threshold;
     L.nbricks = J.ntx * J.nty * J.nzc;

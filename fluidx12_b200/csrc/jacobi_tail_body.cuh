@@ -9,6 +9,15 @@
 // Validity shrinks by one cell per sweep from every window edge that is not a grid face (the halo of TT cells
 // absorbs exactly that); at a grid face the reference's clamp-to-edge rule applies (CSProject3D.hlsl:76-83).
 //
+// Two ways to run the sweeps on a window, chosen per window from the number of active cells in it:
+//   * dense  (crowded windows): every thread owns the z column of one quad in registers, xy neighbours through
+//     shared memory, a warp skips a plane only when none of its 128 cells is active;
+//   * sparse (the usual case in the tail: a few percent of the cells are active, scattered): the active cells are
+//     compacted into a list in shared memory and only list entries are relaxed — new values go to a side array and
+//     are committed after a barrier (two-phase Jacobi on one window copy), a frozen cell leaves the list.
+//     Measured reason (profiles/README.md, round 1): with the dense form alone a launch cost ~85 us at 256^3 because
+//     almost all lanes of every executed warp instruction belonged to frozen cells.
+//
 // The file is written against a tiny portability layer (FXT_*) so that the SAME statements compile under nvcc
 // (threads = CUDA threads, phases separated by __syncthreads) and under g++ in tests/emu/tail_emu.cpp (threads = a
 // loop, phases = consecutive loops).  The emulation is test infrastructure: it lets the CPU suite check this file
@@ -21,21 +30,27 @@
 #define FXT_FN __device__ __forceinline__
 #define FXT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define FXT_POPC(v) __popc(v)
+#define FXT_FFS(v) __ffs(v)
 #define FXT_ATOMIC_ADD_U32(p, v) atomicAdd((p), (v))
 #define FXT_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
 #define FXT_ATOMIC_ADD_U64(p, v) atomicAdd((p), (v))
 #define FXT_LDG_U8(p) __ldg(p)
+#define FXT_LDG_F32(p) __ldg(p)
+#define FXT_ATOMIC_AND_U32(p, v) atomicAnd((p), (v))
 namespace fxb { typedef float4 Quad; }
 #else
 #include <cmath>
 #define FXT_FN inline
 #define FXT_FMA(a, b, c) std::fmaf((a), (b), (c))
 #define FXT_POPC(v) __builtin_popcount(v)
+#define FXT_FFS(v) __builtin_ffs(v)
 #define FXT_ATOMIC_ADD_U32(p, v) (*(p) += (v))
 static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + v; return o; }
 #define FXT_ATOMIC_ADD_I32(p, v) fxt_fetch_add_i32((p), (v))
 #define FXT_ATOMIC_ADD_U64(p, v) (*(p) += (v))
 #define FXT_LDG_U8(p) (*(p))
+#define FXT_LDG_F32(p) (*(p))
+#define FXT_ATOMIC_AND_U32(p, v) (*(p) &= (v))
 namespace fxb { struct alignas(16) Quad { float x, y, z, w; }; }
 #endif
 
@@ -62,9 +77,25 @@ struct TailShape {
     static constexpr int kPFloats = LZ * kPlane;
     static constexpr int kRhsFloats = (LZ - 2) * kRhsPlane;
     static constexpr int kNibBytes = LZ * LY * LXQ;
-    static constexpr int kCtrlWords = 8 + TT_;  // any-own flag, per-level counters, spare
-    static constexpr size_t kBytes = (size_t)(kPFloats + kRhsFloats) * 4 + kNibBytes + kCtrlWords * 4;
+    static constexpr int kCtrlWords = 8 + TT_;  // any-own flag, per-level counters, listable-cell count, spare
+    static constexpr int kCtrlTotal = TT_ + 1;  // ctrl index of the number of active cells that can be relaxed at all
+    // sparse path: list entries (u32) + their right-hand sides (f32) + new values (f32) live where the dense path
+    // stages the right-hand side of the whole window
+    static constexpr int kListCap = (kRhsFloats * 4 / 12) / 32 * 32;
+    static constexpr int kScanWords = kThreads + kThreads / 32;
+    static_assert(kPFloats <= (1 << 14), "list entries keep the window index in 14 bits");
+    static_assert(kNibBytes % 4 == 0, "flag bytes are cleared with 32-bit atomics");
+    static constexpr size_t kBytes =
+        (size_t)(kPFloats + kRhsFloats) * 4 + kCtrlWords * 4 + kScanWords * 4 + kNibBytes;
 };
+
+// list entry of the sparse path
+constexpr unsigned kTailIdxMask = 0x3FFFu;  // window index of the cell
+constexpr int kTailDepthShift = 14;        // 3 bits: sweeps for which the cell is a valid output (1..TT)
+constexpr unsigned kTailOwn = 1u << 17;     // the cell belongs to the CTA's output region
+constexpr unsigned kTailFresh = 1u << 18;   // a new value waits in the side array
+constexpr unsigned kTailFroze = 1u << 19;   // ... and the cell froze with it
+constexpr unsigned kTailDead = 0xFFFFFFFFu;
 
 // What one launch needs to know (uniform over the grid).
 struct TailParams {
@@ -79,6 +110,7 @@ struct TailParams {
     int first;           // 1: no flags exist yet (first kernel of a frame): every cell is active
     int early_exit;
     int levels;          // sweeps to apply (<= TT)
+    int sparse_cap;      // windows with at most this many relaxable active cells take the sparse path (<= kListCap)
 };
 
 // Shared-memory view.
@@ -86,9 +118,28 @@ template <class S>
 struct TailShared {
     float* p;            // [LZ][LY][LX]
     float* rhs;          // [LZ-2][LY-2][LX]  (window planes 1..LZ-2, rows 1..LY-2)
-    unsigned char* nib;  // [LZ][LY][LXQ]
-    unsigned* ctrl;      // [0] any active cell in the own region; [1 + l] active own cells after level l+1
+    unsigned char* nib;  // [LZ][LY][LXQ] freeze flags, one nibble per quad
+    unsigned* ctrl;      // [0] any active cell in the own region; [1 + l] active own cells after level l+1; [kCtrlTotal]
+    int* scan;           // [kThreads] list entries per thread, then [kThreads / 32] per warp
+    unsigned* list;      // [kListCap] sparse path (aliases rhs)
+    float* newv;         // [kListCap] sparse path (aliases rhs)
+    float* rhsv;         // [kListCap] sparse path (aliases rhs)
 };
+
+// Carves the views out of one block of S::kBytes bytes (16-byte aligned).
+template <class S>
+FXT_FN TailShared<S> tail_shared(void* base) {
+    TailShared<S> sh;
+    sh.p = reinterpret_cast<float*>(base);
+    sh.rhs = sh.p + S::kPFloats;
+    sh.ctrl = reinterpret_cast<unsigned*>(sh.rhs + S::kRhsFloats);
+    sh.scan = reinterpret_cast<int*>(sh.ctrl + S::kCtrlWords);
+    sh.nib = reinterpret_cast<unsigned char*>(sh.scan + S::kScanWords);
+    sh.list = reinterpret_cast<unsigned*>(sh.rhs);
+    sh.newv = reinterpret_cast<float*>(sh.list + S::kListCap);
+    sh.rhsv = sh.newv + S::kListCap;
+    return sh;
+}
 
 // Per-thread state that lives across phases (registers under nvcc).
 template <class S>
@@ -102,6 +153,8 @@ struct TailThread {
     bool used;          // owns a column at all
     bool in_xy;         // column lies inside the grid
     bool own_xy;        // column belongs to the output region
+    int nlist;          // active cells of the column that can be relaxed (sparse path: its list entries)
+    unsigned okx;       // 0x11111111 * (4-bit mask of the column's cells that can be relaxed as far as x and y go)
 };
 
 // Geometry of one work item (uniform over the CTA).
@@ -113,6 +166,8 @@ struct TailItem {
     int zvl, zvh;       // window planes inside the array and the grid: [zvl, zvh)
     int yvl, yvh;       // window rows inside the grid
     bool zlo_face, zhi_face, ylo_face, yhi_face;  // the valid range ends at a grid face (clamp rule) rather than at a window edge
+    bool xlo_face, xhi_face;
+    unsigned zok[2];    // nibble z = 0xF when cells of window plane z can be relaxed at all (tail_depth >= 1 along z)
 };
 
 template <class S>
@@ -140,7 +195,28 @@ FXT_FN TailItem<S> tail_item(const TailParams& P, int brick, int sub) {
     it.zhi_face = it.wz + it.zvh == P.z_face_hi && it.zvh <= S::LZ - 1;
     it.ylo_face = it.wy + it.yvl == 0 && it.yvl >= 1;
     it.yhi_face = it.wy + it.yvh == P.ny && it.yvh <= S::LY - 1;
+    it.xlo_face = it.wx < 0;
+    it.xhi_face = it.wx + S::LX > P.nx;
+    it.zok[0] = it.zok[1] = 0u;
+    for (int z = 0; z < S::LZ; ++z) {
+        const bool ok = z >= it.zvl && z < it.zvh && (it.zlo_face || z - it.zvl >= 1) && (it.zhi_face || it.zvh - 1 - z >= 1);
+        if (ok) it.zok[z >> 3] |= 0xFu << (4 * (z & 7));
+    }
     return it;
+}
+
+// Number of sweeps after which the window cell (x, y, z) is still a valid result: its distance to the nearest window
+// edge that is not a grid face, at most TT.  0: the cell can never be relaxed here (it sits on such an edge).
+template <class S>
+FXT_FN int tail_depth(const TailItem<S>& it, int x, int y, int z) {
+    int d = S::TT;
+    if (!it.xlo_face && x < d) d = x;
+    if (!it.xhi_face && S::LX - 1 - x < d) d = S::LX - 1 - x;
+    if (!it.ylo_face && y - it.yvl < d) d = y - it.yvl;
+    if (!it.yhi_face && it.yvh - 1 - y < d) d = it.yvh - 1 - y;
+    if (!it.zlo_face && z - it.zvl < d) d = z - it.zvl;
+    if (!it.zhi_face && it.zvh - 1 - z < d) d = it.zvh - 1 - z;
+    return d;
 }
 
 FXT_FN unsigned tail_nib(const unsigned (&fl)[2], int z) { return (fl[z >> 3] >> (4 * (z & 7))) & 0xFu; }
@@ -175,6 +251,20 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
         if (t.own_xy && z >= S::TT && z - S::TT < it.ez) t.own[z >> 3] |= 0xFu << (4 * (z & 7));
     }
     if (((t.fl[0] & t.own[0]) | (t.fl[1] & t.own[1])) != 0u) sh.ctrl[0] = 1u;  // benign race: everybody stores 1
+    // how many list entries the column would contribute (sparse path): active cells with tail_depth >= 1
+    unsigned okx = 0u;
+    if (t.in_xy && (it.ylo_face || t.y - it.yvl >= 1) && (it.yhi_face || it.yvh - 1 - t.y >= 1)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = 4 * t.qx + j;
+            if ((it.xlo_face || x >= 1) && (it.xhi_face || S::LX - 1 - x >= 1)) okx |= 1u << j;
+        }
+    }
+    t.okx = okx * 0x11111111u;
+    const int nl = FXT_POPC(t.fl[0] & it.zok[0] & t.okx) + FXT_POPC(t.fl[1] & it.zok[1] & t.okx);
+    t.nlist = nl;
+    sh.scan[tid] = nl;
+    if (nl) FXT_ATOMIC_ADD_U32(&sh.ctrl[S::kCtrlTotal], (unsigned)nl);
 }
 
 // ---- copy path: no active cell in the own region, so the output equals the input ---------------------------------
@@ -318,6 +408,120 @@ FXT_FN void tail_phase_store_mask(TailThread<S>& t, const TailShared<S>& sh, con
     }
 }
 
+// =====================================================================================================================
+// Sparse path
+// =====================================================================================================================
+
+// ---- sparse phase 1: entries per warp (exclusive scan of the per-thread counts, two levels) ------------------------
+template <class S>
+FXT_FN void tail_sparse_scan(int tid, const TailShared<S>& sh) {
+    if ((tid & 31) != 0) return;
+    int sum = 0;
+    for (int l = 0; l < 32; ++l) sum += sh.scan[tid + l];
+    sh.scan[S::kThreads + (tid >> 5)] = sum;
+}
+
+// ---- sparse phase 2: window values -> shared memory, flags -> nibble array, active cells -> list -------------------
+template <class S>
+FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
+                              const TailParams& P, const float* p_in, const float* rhs) {
+    if (!t.used) return;
+    const Quad zero = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        Quad q = zero;
+        if (t.in_xy && z >= it.zvl && z < it.zvh)
+            q = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
+        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = q;
+        sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
+    }
+    if (t.nlist == 0) return;
+    int at = 0;  // entries of the threads before this one
+    for (int w = 0; w < (tid >> 5); ++w) at += sh.scan[S::kThreads + w];
+    for (int l = tid & ~31; l < tid; ++l) at += sh.scan[l];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        unsigned m = t.fl[w] & it.zok[w] & t.okx;
+        while (m) {
+            const int bit = FXT_FFS(m) - 1;
+            m &= m - 1u;
+            const int z = 8 * w + (bit >> 2), j = bit & 3;
+            const bool own = t.own_xy && z >= S::TT && z - S::TT < it.ez;
+            const int depth = tail_depth<S>(it, 4 * t.qx + j, t.y, z);
+            sh.list[at] = (unsigned)(z * S::kPlane + t.y * S::LX + 4 * t.qx + j) | ((unsigned)depth << kTailDepthShift) |
+                          (own ? kTailOwn : 0u);
+            sh.rhsv[at] = FXT_LDG_F32(rhs + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx + j);
+            ++at;
+        }
+    }
+}
+
+// ---- sparse phase A of sweep s: new values of the listed cells into the side array ---------------------------------
+template <class S>
+FXT_FN void tail_sparse_relax(int tid, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P, int n,
+                              int s) {
+    const float eps = P.early_exit ? kTailEps : -1.0f;
+    for (int e = tid; e < n; e += S::kThreads) {
+        const unsigned ent = sh.list[e];
+        if (ent == kTailDead || (int)((ent >> kTailDepthShift) & 7u) < s) continue;
+        const int idx = (int)(ent & kTailIdxMask);
+        const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
+        const int gx = it.wx + x, gy = it.wy + y, gz = it.wz + z;
+        const float c = sh.p[idx];
+        // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); elsewhere the neighbour is inside the window
+        const float l = gx == 0 ? c : sh.p[idx - 1];
+        const float rr = gx == P.nx - 1 ? c : sh.p[idx + 1];
+        const float u = gy == 0 ? c : sh.p[idx - S::LX];
+        const float d = gy == P.ny - 1 ? c : sh.p[idx + S::LX];
+        const float f = gz == P.z_face_lo ? c : sh.p[idx - S::kPlane];
+        const float b = gz == P.z_face_hi - 1 ? c : sh.p[idx + S::kPlane];
+        unsigned act = 1u;
+        sh.newv[e] = tail_cell(c, l, rr, u, d, f, b, sh.rhsv[e], 1u, eps, act);
+        sh.list[e] = ent | kTailFresh | (act ? 0u : kTailFroze);
+    }
+}
+
+// ---- sparse phase B of sweep s: commit the new values, retire frozen cells, count the live own cells ---------------
+template <class S>
+FXT_FN void tail_sparse_commit(int tid, const TailShared<S>& sh, int n, int s) {
+    unsigned live = 0;
+    for (int e = tid; e < n; e += S::kThreads) {
+        const unsigned ent = sh.list[e];
+        if (ent == kTailDead || !(ent & kTailFresh)) continue;
+        const int idx = (int)(ent & kTailIdxMask);
+        sh.p[idx] = sh.newv[e];
+        if (ent & kTailFroze) {
+            const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
+            const int byte = (z * S::LY + y) * S::LXQ + (x >> 2);
+            FXT_ATOMIC_AND_U32(reinterpret_cast<unsigned*>(sh.nib) + (byte >> 2), ~(1u << (8 * (byte & 3) + (x & 3))));
+            sh.list[e] = kTailDead;
+        } else {
+            sh.list[e] = ent & ~kTailFresh;
+            if (ent & kTailOwn) ++live;
+        }
+    }
+    if (live) FXT_ATOMIC_ADD_U32(&sh.ctrl[s], live);
+}
+
+// ---- sparse final phase: own cells and their flags from shared memory to the other buffers --------------------------
+template <class S>
+FXT_FN void tail_sparse_store(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                              float* p_out, unsigned char* m_out) {
+    if (!t.own_xy) return;
+    const int nxb = P.nx >> 3;
+#pragma unroll
+    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+        if (z - S::TT >= it.ez) continue;
+        const size_t row = (size_t)(it.wz + z) * P.ny + t.gy;
+        *reinterpret_cast<Quad*>(p_out + row * P.nx + t.gx) =
+            *reinterpret_cast<const Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx);
+        if (t.qx & 1) {
+            const unsigned char* nb = sh.nib + (z * S::LY + t.y) * S::LXQ + t.qx;
+            m_out[row * nxb + (t.gx >> 3)] = (unsigned char)(nb[0] | (nb[1] << 4));
+        }
+    }
+}
+
 // Work lists of one launch (same lists as jacobi_fused.cu: bricks that still hold an active cell, and bricks that
 // froze in the previous kernel and need one copy into the other pressure buffer).
 struct TailWork {
@@ -356,12 +560,24 @@ FXT_FN void tail_copy_brick(int tid, int nthreads, const TailParams& P, int bric
     const int rows = P.ny - y_lo < P.by ? P.ny - y_lo : P.by;
     const int qpr = (P.nx - x_lo < P.bx ? P.nx - x_lo : P.bx) >> 2;  // quads per row inside the grid
     const int nxb = P.nx >> 3;
-    for (int i = tid; i < planes * rows * qpr; i += nthreads) {
-        const int xq = i % qpr, rz = i / qpr;
-        const size_t row = (size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows);
-        const size_t at = row * P.nx + x_lo + 4 * xq;
-        *reinterpret_cast<Quad*>(p_out + at) = *reinterpret_cast<const Quad*>(p_in + at);
-        if (xq & 1) m_out[row * nxb + ((x_lo + 4 * xq) >> 3)] = 0;
+    const int total = planes * rows * qpr;
+    for (int base = tid; base < total; base += 4 * nthreads) {
+        Quad v[4];
+        size_t at[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads;
+            const int xq = i % qpr, rz = i / qpr;
+            const size_t row = (size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows);
+            at[u] = row * P.nx + x_lo + 4 * xq;
+            if (i < total) {
+                v[u] = *reinterpret_cast<const Quad*>(p_in + at[u]);
+                if (xq & 1) m_out[row * nxb + ((x_lo + 4 * xq) >> 3)] = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (base + u * nthreads < total) *reinterpret_cast<Quad*>(p_out + at[u]) = v[u];
     }
 }
 

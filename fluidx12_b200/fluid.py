@@ -144,10 +144,10 @@ class Fluid:
 
     def tail_stats(self) -> dict:
         """Counters of the dynamic pressure-solve schedule (FXB_TAIL=1): see fxb_get_tail_stats."""
-        out = np.zeros(4, np.uint64)
-        B.check(B.lib().fxb_get_tail_stats(self._handle(), out.ctypes.data_as(C.c_void_p)))
+        out = np.zeros(5, np.uint64)
+        B.check(B.lib().fxb_get_tail_stats(self._handle(), out.ctypes.data_as(C.c_void_p), 5))
         return {"enabled": bool(out[0]), "tail_launches_last_step": int(out[1]), "tail_bricks": int(out[2]),
-                "tail_subblocks_relaxed": int(out[3])}
+                "tail_subblocks_relaxed": int(out[3]), "tail_subblocks_dense": int(out[4])}
 
     def profile_step(self):
         """One un-graphed step timed per phase: dict of milliseconds."""

@@ -122,10 +122,11 @@ int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void*
 int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 
 /* Counters of the dynamic pressure-solve schedule (environment FXB_TAIL=1 at fxb_create; single GPU, default brick
- * shape): out4[0] = 1 when it is in use, out4[1] = tail-kernel launches that did work in the last step, out4[2] =
- * cumulative bricks relaxed by tail launches (4 sweeps each), out4[3] = cumulative 40x12x8 sub-blocks among them that
- * still held an active cell.  Synchronises the handle's stream. */
-int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out4);
+ * shape).  Fills out[0..n), n <= 16: [0] = 1 when the schedule is in use, [1] = tail-kernel launches that did work in
+ * the last step, [2] = cumulative bricks relaxed by tail launches (4 sweeps each), [3] = cumulative 40x12x8 sub-blocks
+ * among them that still held an active cell, [4] = cumulative sub-blocks of [3] that took the dense path; the rest 0.
+ * Synchronises the handle's stream. */
+int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out, int n);
 
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */

@@ -15,32 +15,43 @@ namespace {
 
 using namespace fxb;
 
+long long g_paths[3] = {0, 0, 0};  // items that took the copy / sparse / dense path
+
 template <class S>
 void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const float* p_in, float* p_out,
               const float* rhs, const unsigned char* m_in, unsigned char* m_out, unsigned long long* active_after_s0) {
     std::vector<unsigned char> smem(S::kBytes + 64, 0);
-    TailShared<S> sh;
-    sh.p = reinterpret_cast<float*>(smem.data());
-    sh.rhs = sh.p + S::kPFloats;
-    sh.ctrl = reinterpret_cast<unsigned*>(sh.rhs + S::kRhsFloats);
-    sh.nib = reinterpret_cast<unsigned char*>(sh.ctrl + S::kCtrlWords);
+    const TailShared<S> sh = tail_shared<S>(smem.data());
     // poison the staged data so that a read of something never written shows up as a mismatch
     for (int i = 0; i < S::kPFloats + S::kRhsFloats; ++i) sh.p[i] = 1.0e30f;
     for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0u;
     const TailItem<S> it = tail_item<S>(P, brick, sub);
     std::vector<TailThread<S>> th(S::kThreads);
+    const int NT = S::kThreads;
     if (it.ex > 0) {
-        for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_flags<S>(tid, th[tid], sh, it, P, m_in);
-        if (sh.ctrl[0]) {
-            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_load<S>(th[tid], sh, it, P, p_in, rhs);
+        for (int tid = 0; tid < NT; ++tid) tail_phase_flags<S>(tid, th[tid], sh, it, P, m_in);
+        const int n = (int)sh.ctrl[S::kCtrlTotal];
+        if (sh.ctrl[0] == 0u) {
+            for (int tid = 0; tid < NT; ++tid) tail_phase_copy<S>(th[tid], it, P, p_in, p_out, m_out);
+            ++g_paths[0];
+        } else if (n <= P.sparse_cap) {
+            for (int tid = 0; tid < NT; ++tid) tail_sparse_scan<S>(tid, sh);
+            for (int tid = 0; tid < NT; ++tid) tail_sparse_build<S>(tid, th[tid], sh, it, P, p_in, rhs);
             for (int s = 1; s <= P.levels; ++s) {
-                for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_relax<S>(th[tid], sh, it, P, s);
-                for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_publish<S>(th[tid], sh, s, s == P.levels);
+                for (int tid = 0; tid < NT; ++tid) tail_sparse_relax<S>(tid, sh, it, P, n, s);
+                for (int tid = 0; tid < NT; ++tid) tail_sparse_commit<S>(tid, sh, n, s);
             }
-            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_store<S>(th[tid], sh, it, P, p_out);
-            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_store_mask<S>(th[tid], sh, it, P, m_out);
+            for (int tid = 0; tid < NT; ++tid) tail_sparse_store<S>(th[tid], sh, it, P, p_out, m_out);
+            ++g_paths[1];
         } else {
-            for (int tid = 0; tid < S::kThreads; ++tid) tail_phase_copy<S>(th[tid], it, P, p_in, p_out, m_out);
+            for (int tid = 0; tid < NT; ++tid) tail_phase_load<S>(th[tid], sh, it, P, p_in, rhs);
+            for (int s = 1; s <= P.levels; ++s) {
+                for (int tid = 0; tid < NT; ++tid) tail_phase_relax<S>(th[tid], sh, it, P, s);
+                for (int tid = 0; tid < NT; ++tid) tail_phase_publish<S>(th[tid], sh, s, s == P.levels);
+            }
+            for (int tid = 0; tid < NT; ++tid) tail_phase_store<S>(th[tid], sh, it, P, p_out);
+            for (int tid = 0; tid < NT; ++tid) tail_phase_store_mask<S>(th[tid], sh, it, P, m_out);
+            ++g_paths[2];
         }
     }
     tail_finish_item<S>(sh, P, W, brick, active_after_s0);
@@ -51,7 +62,7 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
 extern "C" {
 
 // geom = {nx, ny, nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1, bx, by, bz}
-// flags = {first, early_exit, levels, tt}
+// flags = {first, early_exit, levels, tt, sparse_cap (-1: the compiled capacity)}
 // Returns the number of work items processed, or -1 for an unsupported shape.
 int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float* p_out, const float* rhs,
                     const unsigned char* m_in, unsigned char* m_out, const int* relax_in, int n_relax,
@@ -67,6 +78,8 @@ int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float*
     const int tt = flags[3];
     using S4 = TailShape<4, 10, 12, 8>;
     using S2 = TailShape<2, 10, 12, 8>;
+    const int cap = tt == 4 ? S4::kListCap : S2::kListCap;
+    P.sparse_cap = flags[4] < 0 || flags[4] > cap ? cap : flags[4];
     if (P.bx % S4::OX != 0 || P.by > S4::OY || P.bz > S4::OZ || P.nx % 8 != 0 || P.levels > tt) return -1;
     P.nsub = P.bx / S4::OX;
     TailWork W;
@@ -87,6 +100,11 @@ int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float*
         else return -1;
     }
     return items;
+}
+
+// Items that took the copy / sparse / dense path since the last call (and resets the counters).
+void tail_emu_paths(long long* out3) {
+    for (int i = 0; i < 3; ++i) { out3[i] = g_paths[i]; g_paths[i] = 0; }
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ from tests import tail_emu as E
 from tests.util import smooth_state
 
 
-def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True):
+def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True, sparse_cap=-1):
     """Whole pressure solve by emulated tail launches only (first launch: every brick, every cell active).
     Returns (p, s_exec, launches).  After every launch the output buffer must equal the oracle's state everywhere."""
     nz, ny, nx = s2.shape
@@ -29,7 +29,8 @@ def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=Tr
         levels = min(tt, iters - done)
         src, dst = seq & 1, (seq + 1) & 1
         relax, copy_next = E.launch(g, p[src], p[dst], rhs, m[src], m[dst], relax, copy, brick_state, hist[done:],
-                                    first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt)
+                                    first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt,
+                                    sparse_cap=sparse_cap)
         p_ref, act_ref, counts = oracle_mod.jacobi_sweeps_slab(s2, p_ref, act_ref, levels, nz, 0, 0, nz, early_exit)
         done += levels
         seq += 1
@@ -68,13 +69,21 @@ def developed_state(oracle_mod, n, steps):
 
 
 @pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
-def test_tail_only_solve_matches_oracle(oracle_mod, n, steps):
+@pytest.mark.parametrize("sparse_cap", [-1, 0, 300])
+def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap):
+    """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve."""
     s2, p0 = developed_state(oracle_mod, n, steps)
     p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, 64, True)
-    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8))
+    E.paths()
+    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), sparse_cap=sparse_cap)
     assert np.array_equal(p_got, p_want)
     assert s_got == s_want
     assert launches == -(-s_want // 4)
+    n_copy, n_sparse, n_dense = E.paths()
+    assert n_copy > 0
+    assert (n_sparse > 0) == (sparse_cap != 0) and (n_dense > 0) == (sparse_cap != -1 or n_dense > 0)
+    if sparse_cap == 300:
+        assert n_sparse > 0 and n_dense > 0
 
 
 def test_tail_random_field_no_early_exit(oracle_mod):

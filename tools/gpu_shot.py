@@ -1,0 +1,139 @@
+"""One short GPU session for the dynamic pressure-solve schedule (FXB_TAIL=1): parity first, then timing.
+
+Written for a GPU budget of well under a minute: no torch import, results are appended to gpurun_out/shot.jsonl
+stage by stage (flushed), so whatever finished before a time limit is kept.  Timing is host-side around
+fxb_simulate ... fxb_sync over many steps (the graph launch is asynchronous; the sync is outside the loop)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out", "shot.jsonl")
+os.makedirs(os.path.dirname(OUT), exist_ok=True)
+T0 = time.time()
+
+
+def emit(**kw):
+    kw["t"] = round(time.time() - T0, 2)
+    with open(OUT, "a") as fh:
+        fh.write(json.dumps(kw) + "\n")
+        fh.flush()
+        os.fsync(fh.fileno())
+    print(kw, flush=True)
+
+
+def make(fx, n, tail, **env):
+    keys = {"FXB_TAIL": "1" if tail else "0"}
+    keys.update({k: str(v) for k, v in env.items()})
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ.update(keys)
+    try:
+        f = fx.Fluid()
+        ok = f.Init(gridSize=n)
+        if not ok:
+            raise RuntimeError(f.last_error)
+        return f
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def same_fields(fx, a, b):
+    bad = {}
+    for name, fld in (("velocity", fx.FIELD_VELOCITY), ("colour", fx.FIELD_COLOR), ("pressure", fx.FIELD_PRESSURE)):
+        x, y = a.get_field(fld), b.get_field(fld)
+        if name == "velocity":
+            x, y = x[..., :3], y[..., :3]
+        bad[name] = int((x != y).sum())
+    return bad
+
+
+def time_steps(f, dt, steps):
+    f.sync()
+    t = time.perf_counter()
+    for _ in range(steps):
+        f.step(dt)
+    f.sync()
+    return (time.perf_counter() - t) / steps * 1e3
+
+
+def oracle_check(fx, label, env, n=(64, 64, 64), steps=6):
+    try:
+        import oracle
+        dt = fx.dt_for_grid(*n)
+        f, o = make(fx, n, env is not None, **(env or {})), oracle.FluidOracle(*n)
+        for _ in range(steps):
+            f.step(dt)
+            o.step(dt)
+        f.sync()
+        bad = {}
+        for name, gf, of in (("velocity", fx.FIELD_VELOCITY, oracle.FIELD_VEL), ("colour", fx.FIELD_COLOR, oracle.FIELD_COLOR),
+                             ("pressure", fx.FIELD_PRESSURE, oracle.FIELD_PRESSURE)):
+            x, y = f.get_field(gf), o.get_field(of)
+            if name == "velocity":
+                x, y = x[..., :3], y[..., :3]
+            bad[name] = int((x != y).sum())
+        emit(stage="oracle", variant=label, grid=n, mismatches=bad, s_exec=[f.stats().s_exec, o.s_exec], tail=f.tail_stats())
+        f.close()
+    except Exception as e:
+        emit(stage="oracle", variant=label, error=repr(e))
+
+
+def timing(fx, n, spin, steps, variants, all_fields=False):
+    """Spin up on the default schedule, copy the state into each variant, time `steps` graph-launched steps."""
+    dt = fx.dt_for_grid(*n)
+    base = make(fx, n, False)
+    for _ in range(spin):
+        base.step(dt)
+    base.sync()
+    flds = (fx.FIELD_VELOCITY, fx.FIELD_COLOR, fx.FIELD_PRESSURE)
+    state = {fld: base.get_field(fld) for fld in flds}
+    res = {"default": round(time_steps(base, dt, steps), 4)}
+    base.UpdateFrame(dt)
+    res["default_phases"] = {k: round(v, 4) for k, v in base.profile_step().items()}
+    cmp_flds = flds if all_fields else (fx.FIELD_PRESSURE,)
+    ref = {fld: base.get_field(fld) for fld in cmp_flds}
+    emit(stage="timing", grid=n, **res)
+    base.close()
+    for label, env in variants:
+        try:
+            f = make(fx, n, True, **env)
+            for fld, arr in state.items():
+                f.set_field(fld, arr)
+            ms = time_steps(f, dt, steps)
+            f.UpdateFrame(dt)
+            ph = f.profile_step()
+            bad = {str(fld): int((f.get_field(fld) != ref[fld]).sum()) for fld in cmp_flds}
+            emit(stage="timing", grid=n, variant=label, ms=round(ms, 4), phases={k: round(v, 4) for k, v in ph.items()},
+                 tail=f.tail_stats(), passes=f.stats().jacobi_passes, s_exec=f.stats().s_exec, mismatch_vs_default=bad)
+            f.close()
+        except Exception as e:  # keep going: the other variants are still informative
+            emit(stage="timing", grid=n, variant=label, error=repr(e))
+
+
+def main():
+    import fluidx12_b200 as fx
+    emit(stage="import")
+    oracle_check(fx, "tail", {})
+    oracle_check(fx, "tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}, n=(64, 64, 40), steps=4)
+    timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_grid592", {"FXB_TAIL_GRID": 592}),
+                                          ("tail_mains1", {"FXB_TAIL_MAINS": 1})], all_fields=True)
+    timing(fx, (512, 512, 512), 100, 20, [("tail", {})])
+    oracle_check(fx, "default", None)
+    emit(stage="done")
+
+
+if __name__ == "__main__":
+    try:
+        main()
+    except Exception as e:
+        emit(stage="fatal", error=repr(e))
+        raise
