@@ -80,47 +80,12 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
             continue;
         }
         const int r = item - n_copy;
-        const int brick = W.relax_in[r / P.nsub];
-        const TailItem<S> it = tail_item<S>(P, brick, r % P.nsub);
-        __syncthreads();  // the previous item is finished with shared memory
-        if (tid < S::kCtrlWords) sh.ctrl[tid] = 0u;
-        __syncthreads();
-        if (it.ex > 0) {
-            TailThread<S> t;
-            tail_phase_flags<S>(tid, t, sh, it, P, m_in);
-            __syncthreads();
-            const int n_list = (int)sh.ctrl[S::kCtrlTotal];
-            if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
-                tail_phase_copy<S>(t, it, P, p_in, p_out, m_out);
-            } else if (n_list <= P.sparse_cap) {  // few active cells: relax a compacted list of them
-                tail_sparse_scan<S>(tid, sh);
-                __syncthreads();
-                tail_sparse_build<S>(tid, t, sh, it, P, p_in, rhs);
-                __syncthreads();
-                for (int s = 1; s <= P.levels; ++s) {
-                    tail_sparse_relax<S>(tid, sh, it, P, n_list, s);
-                    __syncthreads();
-                    tail_sparse_commit<S>(tid, sh, n_list, s);
-                    __syncthreads();
-                }
-                tail_sparse_store<S>(t, sh, it, P, p_out, m_out);
-                if (tid == 0) ++relaxed;
-            } else {  // crowded window: register columns
-                tail_phase_load<S>(t, sh, it, P, p_in, rhs);
-                __syncthreads();
-                for (int s = 1; s <= P.levels; ++s) {
-                    tail_phase_relax<S>(t, sh, it, P, s);
-                    __syncthreads();
-                    tail_phase_publish<S>(t, sh, s, s == P.levels);
-                    __syncthreads();
-                }
-                tail_phase_store<S>(t, sh, it, P, p_out);
-                __syncthreads();
-                tail_phase_store_mask<S>(t, sh, it, P, m_out);
-                if (tid == 0) { ++relaxed; ++dense; }
-            }
+        const int path = tail_run_item<S>(tid, sh, P, W, W.relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out,
+                                          state->active_after + s0);
+        if (tid == 0 && path != 0) {
+            ++relaxed;
+            if (path == 2) ++dense;
         }
-        if (tid == 0) tail_finish_item<S>(sh, P, W, brick, state->active_after + s0);
     }
 
     // the last CTA to finish advances the shared schedule (every CTA has read it long before)

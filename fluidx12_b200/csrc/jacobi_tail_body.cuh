@@ -28,6 +28,7 @@
 
 #if defined(__CUDACC__)
 #define FXT_FN __device__ __forceinline__
+#define FXT_COMPILER_FENCE() asm volatile("" ::: "memory")  // keeps a batch of loads ahead of the stores that follow
 #define FXT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
 #define FXT_POPC(v) __popc(v)
 #define FXT_FFS(v) __ffs(v)
@@ -37,10 +38,18 @@
 #define FXT_LDG_U8(p) __ldg(p)
 #define FXT_LDG_F32(p) __ldg(p)
 #define FXT_ATOMIC_AND_U32(p, v) atomicAnd((p), (v))
+// A work item is a sequence of phases separated by barriers (tail_run_item).  Under nvcc a phase is just the
+// statement, executed by the calling thread `tid` with its state `t`.
+#define FXT_CTX(S) const int tid
+#define FXT_THREAD_STATE(S) TailThread<S> t
+#define FXT_PHASE(...) do { __VA_ARGS__; } while (0)
+#define FXT_SYNC() __syncthreads()
+#define FXT_END() do { } while (0)
 namespace fxb { typedef float4 Quad; }
 #else
 #include <cmath>
 #define FXT_FN inline
+#define FXT_COMPILER_FENCE() asm volatile("" ::: "memory")
 #define FXT_FMA(a, b, c) std::fmaf((a), (b), (c))
 #define FXT_POPC(v) __builtin_popcount(v)
 #define FXT_FFS(v) __builtin_ffs(v)
@@ -51,6 +60,17 @@ static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + 
 #define FXT_LDG_U8(p) (*(p))
 #define FXT_LDG_F32(p) (*(p))
 #define FXT_ATOMIC_AND_U32(p, v) (*(p) &= (v))
+// Emulation: phases are queued and run at the next barrier, thread after thread — every thread runs ALL phases of
+// the barrier-free segment before the next thread starts (in ascending or descending thread order).  That is the
+// most skewed interleaving a missing __syncthreads() would permit, so a phase that needs another thread's result
+// from the same segment reads stale data and the parity tests fail.
+#include <functional>
+#include <vector>
+#define FXT_CTX(S) TailEmu<S>& emu
+#define FXT_THREAD_STATE(S) (void)0
+#define FXT_PHASE(...) emu.seg.push_back([&](int tid) { TailThread<S>& t = emu.th[tid]; (void)t; (void)tid; __VA_ARGS__; })
+#define FXT_SYNC() emu.flush()
+#define FXT_END() emu.flush()
 namespace fxb { struct alignas(16) Quad { float x, y, z, w; }; }
 #endif
 
@@ -227,7 +247,7 @@ FXT_FN void tail_set_nib(unsigned (&fl)[2], int z, unsigned n) {
 // ---- phase 0: thread geometry, freeze flags of the column, "is anything in the own region still active" ----------
 template <class S>
 FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
-                             const TailParams& P, const unsigned char* m_in) {
+                             const TailParams& P, const unsigned char* __restrict__ m_in) {
     t.used = tid < S::kUsed;
     t.qx = tid % S::LXQ;
     t.y = tid / S::LXQ;
@@ -269,15 +289,22 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
 
 // ---- copy path: no active cell in the own region, so the output equals the input ---------------------------------
 template <class S>
-FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailParams& P, const float* p_in,
-                            float* p_out, unsigned char* m_out) {
+FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailParams& P,
+                            const float* __restrict__ p_in, float* __restrict__ p_out,
+                            unsigned char* __restrict__ m_out) {
     if (!t.own_xy) return;
     const int nxb = P.nx >> 3;
+    Quad q[S::OZ];  // all loads in flight before the first store (planes past the end re-read the first one)
+#pragma unroll
+    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+        const int zz = z - S::TT < it.ez ? z : S::TT;
+        q[z - S::TT] = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + zz) * P.ny + t.gy) * P.nx + t.gx);
+    }
 #pragma unroll
     for (int z = S::TT; z < S::TT + S::OZ; ++z) {
         if (z - S::TT >= it.ez) continue;
         const size_t row = (size_t)(it.wz + z) * P.ny + t.gy;
-        *reinterpret_cast<Quad*>(p_out + row * P.nx + t.gx) = *reinterpret_cast<const Quad*>(p_in + row * P.nx + t.gx);
+        *reinterpret_cast<Quad*>(p_out + row * P.nx + t.gx) = q[z - S::TT];
         if (t.qx & 1) m_out[row * nxb + (t.gx >> 3)] = 0;
     }
 }
@@ -285,7 +312,7 @@ FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailP
 // ---- phase 1: window values -> registers + shared memory, right-hand side -> shared memory -----------------------
 template <class S>
 FXT_FN void tail_phase_load(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
-                            const float* p_in, const float* rhs) {
+                            const float* __restrict__ p_in, const float* __restrict__ rhs) {
     if (!t.used) return;
     const Quad zero = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -384,7 +411,7 @@ FXT_FN void tail_phase_publish(TailThread<S>& t, const TailShared<S>& sh, int s,
 // ---- final phases: own cells -> the other pressure buffer; flags -> bit-packed mask (two quads per byte) ----------
 template <class S>
 FXT_FN void tail_phase_store(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
-                             float* p_out) {
+                             float* __restrict__ p_out) {
     if (!t.used) return;
 #pragma unroll
     for (int z = S::TT; z < S::TT + S::OZ; ++z) {
@@ -396,7 +423,7 @@ FXT_FN void tail_phase_store(TailThread<S>& t, const TailShared<S>& sh, const Ta
 
 template <class S>
 FXT_FN void tail_phase_store_mask(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
-                                  unsigned char* m_out) {
+                                  unsigned char* __restrict__ m_out) {
     // own quads start at window quad 1 (grid x a multiple of 8) and come in pairs: the odd one writes the byte
     if (!t.own_xy || !(t.qx & 1)) return;
     const int nxb = P.nx >> 3;
@@ -424,15 +451,20 @@ FXT_FN void tail_sparse_scan(int tid, const TailShared<S>& sh) {
 // ---- sparse phase 2: window values -> shared memory, flags -> nibble array, active cells -> list -------------------
 template <class S>
 FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
-                              const TailParams& P, const float* p_in, const float* rhs) {
+                              const TailParams& P, const float* __restrict__ p_in) {
     if (!t.used) return;
     const Quad zero = {0.f, 0.f, 0.f, 0.f};
+    Quad q[S::LZ];  // every load is issued before the first store (cells outside the grid read p_in[0..3], then zero)
 #pragma unroll
     for (int z = 0; z < S::LZ; ++z) {
-        Quad q = zero;
-        if (t.in_xy && z >= it.zvl && z < it.zvh)
-            q = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
-        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = q;
+        const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+        q[z] = *reinterpret_cast<const Quad*>(in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in);
+    }
+    FXT_COMPILER_FENCE();
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = in ? q[z] : zero;
         sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
     }
     if (t.nlist == 0) return;
@@ -448,11 +480,29 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
             const int z = 8 * w + (bit >> 2), j = bit & 3;
             const bool own = t.own_xy && z >= S::TT && z - S::TT < it.ez;
             const int depth = tail_depth<S>(it, 4 * t.qx + j, t.y, z);
-            sh.list[at] = (unsigned)(z * S::kPlane + t.y * S::LX + 4 * t.qx + j) | ((unsigned)depth << kTailDepthShift) |
-                          (own ? kTailOwn : 0u);
-            sh.rhsv[at] = FXT_LDG_F32(rhs + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx + j);
-            ++at;
+            sh.list[at++] = (unsigned)(z * S::kPlane + t.y * S::LX + 4 * t.qx + j) | ((unsigned)depth << kTailDepthShift) |
+                            (own ? kTailOwn : 0u);
         }
+    }
+}
+
+// ---- sparse phase 3: right-hand sides of the listed cells -> side array (eight independent loads in flight) --------
+template <class S>
+FXT_FN void tail_sparse_gather(int tid, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
+                               const float* __restrict__ rhs, int n) {
+    for (int base = tid; base < n; base += 8 * S::kThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = base + u * S::kThreads;
+            // entries past the end re-read entry `base` (in range): no branch around the load, nothing out of bounds
+            const int idx = (int)(sh.list[e < n ? e : base] & kTailIdxMask);
+            const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
+            v[u] = FXT_LDG_F32(rhs + ((size_t)(it.wz + z) * P.ny + (it.wy + y)) * P.nx + (it.wx + x));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (base + u * S::kThreads < n) sh.rhsv[base + u * S::kThreads] = v[u];
     }
 }
 
@@ -506,7 +556,7 @@ FXT_FN void tail_sparse_commit(int tid, const TailShared<S>& sh, int n, int s) {
 // ---- sparse final phase: own cells and their flags from shared memory to the other buffers --------------------------
 template <class S>
 FXT_FN void tail_sparse_store(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
-                              float* p_out, unsigned char* m_out) {
+                              float* __restrict__ p_out, unsigned char* __restrict__ m_out) {
     if (!t.own_xy) return;
     const int nxb = P.nx >> 3;
 #pragma unroll
@@ -550,10 +600,81 @@ FXT_FN void tail_finish_item(const TailShared<S>& sh, const TailParams& P, const
     }
 }
 
+#if !defined(__CUDACC__)
+// Emulated CTA: per-thread state plus the phases queued since the last barrier (see FXT_PHASE above).
+template <class S>
+struct TailEmu {
+    std::vector<TailThread<S>> th = std::vector<TailThread<S>>(S::kThreads);
+    std::vector<std::function<void(int)>> seg;
+    bool descending = false;
+    void flush() {
+        for (int i = 0; i < S::kThreads; ++i) {
+            const int tid = descending ? S::kThreads - 1 - i : i;
+            for (auto& f : seg) f(tid);
+        }
+        seg.clear();
+    }
+};
+#endif
+
+// ---- one work item of the relax list: sub-block `sub` of `brick`, all phases and barriers ---------------------------
+// Returns the path taken: 0 = nothing active in the own region (copy) or empty sub-block, 1 = sparse, 2 = dense.
+template <class S>
+FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& P, const TailWork& W, const int brick,
+                         const int sub, const float* __restrict__ p_in, float* __restrict__ p_out,
+                         const float* __restrict__ rhs, const unsigned char* __restrict__ m_in,
+                         unsigned char* __restrict__ m_out, unsigned long long* active_after_s0) {
+    const TailItem<S> it = tail_item<S>(P, brick, sub);
+    FXT_THREAD_STATE(S);
+    int path = 0;
+    FXT_SYNC();  // the previous item is finished with shared memory
+    FXT_PHASE(if (tid < S::kCtrlWords) sh.ctrl[tid] = 0u);
+    FXT_SYNC();
+    if (it.ex > 0) {
+        FXT_PHASE(tail_phase_flags<S>(tid, t, sh, it, P, m_in));
+        FXT_SYNC();
+        const int n_list = (int)sh.ctrl[S::kCtrlTotal];
+        if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
+            FXT_PHASE(tail_phase_copy<S>(t, it, P, p_in, p_out, m_out));
+        } else if (n_list <= P.sparse_cap) {  // relax a compacted list of the active cells
+            path = 1;
+            FXT_PHASE(tail_sparse_scan<S>(tid, sh));
+            FXT_SYNC();
+            FXT_PHASE(tail_sparse_build<S>(tid, t, sh, it, P, p_in));
+            FXT_SYNC();
+            FXT_PHASE(tail_sparse_gather<S>(tid, sh, it, P, rhs, n_list));
+            FXT_SYNC();
+            for (int s = 1; s <= P.levels; ++s) {
+                FXT_PHASE(tail_sparse_relax<S>(tid, sh, it, P, n_list, s));
+                FXT_SYNC();
+                FXT_PHASE(tail_sparse_commit<S>(tid, sh, n_list, s));
+                FXT_SYNC();
+            }
+            FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
+        } else {  // crowded window: register columns
+            path = 2;
+            FXT_PHASE(tail_phase_load<S>(t, sh, it, P, p_in, rhs));
+            FXT_SYNC();
+            for (int s = 1; s <= P.levels; ++s) {
+                FXT_PHASE(tail_phase_relax<S>(t, sh, it, P, s));
+                FXT_SYNC();
+                FXT_PHASE(tail_phase_publish<S>(t, sh, s, s == P.levels));
+                FXT_SYNC();
+            }
+            FXT_PHASE(tail_phase_store<S>(t, sh, it, P, p_out));
+            FXT_SYNC();
+            FXT_PHASE(tail_phase_store_mask<S>(t, sh, it, P, m_out));
+        }
+    }
+    FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
+    FXT_END();
+    return path;
+}
+
 // ---- a brick of the copy list: its values are final; bring the other buffer (and mask) up to date ----------------
 // `tid` of `nthreads` threads; pure streaming, 16 bytes per access.
-FXT_FN void tail_copy_brick(int tid, int nthreads, const TailParams& P, int brick, const float* p_in, float* p_out,
-                            unsigned char* m_out) {
+FXT_FN void tail_copy_brick(int tid, int nthreads, const TailParams& P, int brick, const float* __restrict__ p_in,
+                            float* __restrict__ p_out, unsigned char* __restrict__ m_out) {
     const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc = brick / (P.ntx * P.nty);
     const int x_lo = tx * P.bx, y_lo = ty * P.by, zs = P.z_out0 + zc * P.bz;
     const int planes = (P.z_out1 - zs < P.bz ? P.z_out1 - zs : P.bz);
@@ -565,19 +686,17 @@ FXT_FN void tail_copy_brick(int tid, int nthreads, const TailParams& P, int bric
         Quad v[4];
         size_t at[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * nthreads;
+        for (int u = 0; u < 4; ++u) {  // four independent loads in flight; slots past the end repeat slot 0
+            const int i = base + u * nthreads < total ? base + u * nthreads : base;
             const int xq = i % qpr, rz = i / qpr;
             const size_t row = (size_t)(zs + rz / rows) * P.ny + (y_lo + rz % rows);
             at[u] = row * P.nx + x_lo + 4 * xq;
-            if (i < total) {
-                v[u] = *reinterpret_cast<const Quad*>(p_in + at[u]);
-                if (xq & 1) m_out[row * nxb + ((x_lo + 4 * xq) >> 3)] = 0;
-            }
+            v[u] = *reinterpret_cast<const Quad*>(p_in + at[u]);
+            if (xq & 1) m_out[row * nxb + ((x_lo + 4 * xq) >> 3)] = 0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (base + u * nthreads < total) *reinterpret_cast<Quad*>(p_out + at[u]) = v[u];
+            if (u == 0 || base + u * nthreads < total) *reinterpret_cast<Quad*>(p_out + at[u]) = v[u];
     }
 }
 

@@ -1,7 +1,9 @@
 // tail_emu.cpp — CPU emulation of jacobi_tail_kernel (fluidx12_b200/csrc/jacobi_tail.cu).  TEST INFRASTRUCTURE ONLY.
 //
-// Compiles the kernel's real body (jacobi_tail_body.cuh) with g++: CUDA threads become a loop over `tid`, every
-// __syncthreads() becomes the end of such a loop, shared memory becomes a heap block, atomics become plain
+// Compiles the kernel's real body (jacobi_tail_body.cuh, including the per-item sequence of phases and barriers,
+// tail_run_item) with g++: the phases between two barriers are run thread after thread (each thread runs the whole
+// barrier-free segment before the next one starts, in ascending or descending order — the most skewed interleaving
+// a missing __syncthreads() would allow), shared memory becomes a heap block, atomics become plain
 // read-modify-writes (CTAs run one after the other).  tests/test_tail_emu.py drives it against the oracle
 // (oracle/fluid_oracle.cpp) bit for bit, so the indexing, clamp and freeze logic of the CUDA kernel is checked
 // on the CPU; the product library never links or loads this file.
@@ -16,6 +18,7 @@ namespace {
 using namespace fxb;
 
 long long g_paths[3] = {0, 0, 0};  // items that took the copy / sparse / dense path
+bool g_descending = false;         // thread order inside a barrier-free segment
 
 template <class S>
 void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const float* p_in, float* p_out,
@@ -24,37 +27,11 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
     const TailShared<S> sh = tail_shared<S>(smem.data());
     // poison the staged data so that a read of something never written shows up as a mismatch
     for (int i = 0; i < S::kPFloats + S::kRhsFloats; ++i) sh.p[i] = 1.0e30f;
-    for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0u;
-    const TailItem<S> it = tail_item<S>(P, brick, sub);
-    std::vector<TailThread<S>> th(S::kThreads);
-    const int NT = S::kThreads;
-    if (it.ex > 0) {
-        for (int tid = 0; tid < NT; ++tid) tail_phase_flags<S>(tid, th[tid], sh, it, P, m_in);
-        const int n = (int)sh.ctrl[S::kCtrlTotal];
-        if (sh.ctrl[0] == 0u) {
-            for (int tid = 0; tid < NT; ++tid) tail_phase_copy<S>(th[tid], it, P, p_in, p_out, m_out);
-            ++g_paths[0];
-        } else if (n <= P.sparse_cap) {
-            for (int tid = 0; tid < NT; ++tid) tail_sparse_scan<S>(tid, sh);
-            for (int tid = 0; tid < NT; ++tid) tail_sparse_build<S>(tid, th[tid], sh, it, P, p_in, rhs);
-            for (int s = 1; s <= P.levels; ++s) {
-                for (int tid = 0; tid < NT; ++tid) tail_sparse_relax<S>(tid, sh, it, P, n, s);
-                for (int tid = 0; tid < NT; ++tid) tail_sparse_commit<S>(tid, sh, n, s);
-            }
-            for (int tid = 0; tid < NT; ++tid) tail_sparse_store<S>(th[tid], sh, it, P, p_out, m_out);
-            ++g_paths[1];
-        } else {
-            for (int tid = 0; tid < NT; ++tid) tail_phase_load<S>(th[tid], sh, it, P, p_in, rhs);
-            for (int s = 1; s <= P.levels; ++s) {
-                for (int tid = 0; tid < NT; ++tid) tail_phase_relax<S>(th[tid], sh, it, P, s);
-                for (int tid = 0; tid < NT; ++tid) tail_phase_publish<S>(th[tid], sh, s, s == P.levels);
-            }
-            for (int tid = 0; tid < NT; ++tid) tail_phase_store<S>(th[tid], sh, it, P, p_out);
-            for (int tid = 0; tid < NT; ++tid) tail_phase_store_mask<S>(th[tid], sh, it, P, m_out);
-            ++g_paths[2];
-        }
-    }
-    tail_finish_item<S>(sh, P, W, brick, active_after_s0);
+    for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0xDEADBEEFu;
+    TailEmu<S> emu;
+    emu.descending = g_descending;
+    const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0);
+    ++g_paths[path];
 }
 
 }  // namespace
@@ -101,6 +78,9 @@ int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float*
     }
     return items;
 }
+
+// Thread order inside a barrier-free segment: 0 ascending, 1 descending.
+void tail_emu_thread_order(int descending) { g_descending = descending != 0; }
 
 // Items that took the copy / sparse / dense path since the last call (and resets the counters).
 void tail_emu_paths(long long* out3) {

@@ -46,6 +46,11 @@ def unpack_mask(mask, nx):
     return np.unpackbits(mask, axis=-1, bitorder="little")[..., :nx]
 
 
+def thread_order(descending: bool):
+    """Order in which the emulated threads run a barrier-free segment (a missing barrier shows up in one of the two)."""
+    lib().tail_emu_thread_order(C.c_int(int(descending)))
+
+
 def paths():
     """Work items that took the (copy, sparse, dense) path since the last call."""
     out = np.zeros(3, np.int64)

@@ -68,9 +68,16 @@ def developed_state(oracle_mod, n, steps):
     return oracle_mod.divergence2x(vo), p
 
 
+@pytest.fixture(params=[False, True], ids=["ascending", "descending"])
+def thread_order(request):
+    E.thread_order(request.param)
+    yield request.param
+    E.thread_order(False)
+
+
 @pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
 @pytest.mark.parametrize("sparse_cap", [-1, 0, 300])
-def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap):
+def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, thread_order):
     """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve."""
     s2, p0 = developed_state(oracle_mod, n, steps)
     p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, 64, True)
@@ -86,7 +93,7 @@ def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap):
         assert n_sparse > 0 and n_dense > 0
 
 
-def test_tail_random_field_no_early_exit(oracle_mod):
+def test_tail_random_field_no_early_exit(oracle_mod, thread_order):
     """Dense activity (nothing freezes), a grid whose last brick column is 16 cells wide, 10 sweeps = 4 + 4 + 2."""
     n = (136, 136, 20)
     _, _, p0 = smooth_state(*n, seed=7)
@@ -98,7 +105,7 @@ def test_tail_random_field_no_early_exit(oracle_mod):
     assert np.array_equal(p_got, p_want)
 
 
-def test_tail_two_sweep_shape_and_thin_bricks(oracle_mod):
+def test_tail_two_sweep_shape_and_thin_bricks(oracle_mod, thread_order):
     """TT = 2 instantiation, bricks thinner than the compiled sub-block (by = 10, bz = 5), odd plane count."""
     n = (64, 64, 13)
     s2, p0 = developed_state(oracle_mod, n, 8)
