@@ -172,6 +172,28 @@ int build_axis_tables(fxb_sim* s) {
     return FXB_OK;
 }
 
+// Static launch sequence of the dynamic pressure-solve schedule.  Entry k >= 0: bulk pass with
+// static index k (runs iff exactly k*T sweeps are done); kTailIfFew: tail launch that runs iff few enough bricks are
+// listed; kTailAlways: tail launch that runs whatever the list length.  Bulk pass 0 comes first; then groups of one
+// conditional tail launch and the TT/T bulk passes that cover the same sweeps, up to bulk pass mains-1; then as many
+// unconditional tail launches as the worst case (no conditional tail launch ever ran: mains*T sweeps done) needs.
+// Every group advances the solve by at least its bulk passes' sweeps, and a tail launch that ran once keeps
+// qualifying (the brick list only shrinks), so the sequence always reaches `iters` sweeps unless the solve ends early.
+enum { kTailIfFew = -1, kTailAlways = -2 };
+std::vector<int> plan_pressure_solve(int iters, int T, int TT, int mains) {
+    std::vector<int> plan;
+    if (iters <= 0 || T <= 0 || TT <= 0) return plan;
+    const int npass = (iters + T - 1) / T;
+    mains = std::min(std::max(mains, 1), npass);
+    plan.push_back(0);
+    for (int k = 1; k < mains;) {
+        plan.push_back(kTailIfFew);
+        for (int j = 0; j < std::max(TT / T, 1) && k < mains; ++j, ++k) plan.push_back(k);
+    }
+    for (int done = mains * T; done < iters; done += TT) plan.push_back(kTailAlways);
+    return plan;
+}
+
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 
 void fork_colour(fxb_sim* s, cudaStream_t st);
@@ -207,26 +229,17 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 // Dynamic schedule: which kernel relaxes is decided on the device (jacobi_tail.cu).  A group is one
                 // tail launch (TT sweeps) followed by the TT/T bulk passes that cover the same sweeps; the tail
                 // launch of a group runs iff few enough bricks are listed, the bulk passes run iff it did not.
-                const int T = s->fuse_t, TT = fxb::jacobi_tail_sweeps(), iters = s->cfg.jacobi_iters;
-                const int npass = (iters + T - 1) / T;
-                const int mains = std::min(std::max(s->tail_mains, 1), npass);
+                const int iters = s->cfg.jacobi_iters;
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
-                auto bulk = [&](int k) {
-                    fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, iters, s->cfg.early_exit, false,
-                                                  0, 0, st);
+                for (const int kind : plan_pressure_solve(iters, s->fuse_t, fxb::jacobi_tail_sweeps(), s->tail_mains)) {
+                    if (kind >= 0)
+                        fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, kind, iters, s->cfg.early_exit,
+                                                      false, 0, 0, st);
+                    else
+                        fxb::launch_jacobi_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit,
+                                                kind == kTailIfFew ? s->jac.tail_threshold : -1, st);
                     ++launches;
-                };
-                auto tail = [&](int threshold) {
-                    fxb::launch_jacobi_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit, threshold, st);
-                    ++launches;
-                };
-                bulk(0);
-                for (int k = 1; k < mains;) {
-                    tail(s->jac.tail_threshold);
-                    for (int j = 0; j < std::max(TT / T, 1) && k < mains; ++j, ++k) bulk(k);
                 }
-                // every group above advanced the solve by at least its bulk passes' sweeps: mains * T are done
-                for (int done = mains * T; done < iters; done += TT) tail(-1);
                 fxb::launch_finish_solve_dynamic(s->d_frame, s->d_state, iters, st);
                 ++launches;
             } else if (s->fused) {
@@ -529,12 +542,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
         int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
-        if (s->tail) {  // same count as the dynamic schedule of enqueue_phase
-            const int T = s->fuse_t, TT = fxb::jacobi_tail_sweeps(), iters = s->cfg.jacobi_iters;
-            const int mains = std::min(std::max(s->tail_mains, 1), jl);
-            const int per_group = std::max(TT / T, 1);
-            jl = mains + (mains - 1 + per_group - 1) / per_group + std::max(0, (iters - mains * T + TT - 1) / TT);
-        }
+        if (s->tail)
+            jl = (int)plan_pressure_solve(s->cfg.jacobi_iters, s->fuse_t, fxb::jacobi_tail_sweeps(), s->tail_mains).size();
         s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
     }
     if (s->multi()) {
@@ -716,6 +725,14 @@ int fxb_get_tail_stats(fxb_sim* s, uint64_t* out, int n) {
                            st.tail_subblocks_dense};
     for (int i = 0; i < n; ++i) out[i] = i < 5 ? v[i] : 0;
     return FXB_OK;
+}
+
+int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_t* kinds, int32_t capacity) {
+    if (iters < 0 || iters > 128 || fuse_t < 1 || fuse_t > 4 || !kinds || capacity < 0)
+        return fail(FXB_ERR_INVALID, "fxb_plan_pressure_solve: bad argument");
+    const std::vector<int> plan = plan_pressure_solve(iters, fuse_t, fxb::jacobi_tail_sweeps(), mains);
+    for (size_t i = 0; i < plan.size() && (int)i < capacity; ++i) kinds[i] = plan[i];
+    return (int)plan.size();
 }
 
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {

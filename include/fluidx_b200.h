@@ -128,6 +128,13 @@ int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
  * Synchronises the handle's stream. */
 int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out, int n);
 
+/* Diagnostic, needs no GPU: the static launch sequence of the dynamic pressure-solve schedule for ITER = iters, T =
+ * fuse_t and `mains` bulk passes.  kinds[i] >= 0: bulk pass with that static index (runs iff exactly kinds[i] * T
+ * sweeps are done); -1: tail launch (4 sweeps) that runs iff few enough bricks are listed; -2: tail launch that
+ * always runs.  Returns the length of the sequence (which may exceed `capacity`; only `capacity` entries are
+ * written), or a negative fxb_status. */
+int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_t* kinds, int32_t capacity);
+
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);
