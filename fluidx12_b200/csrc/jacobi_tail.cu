@@ -81,7 +81,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
         }
         const int r = item - n_copy;
         const int path = tail_run_item<S>(tid, sh, P, W, W.relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out,
-                                          state->active_after + s0);
+                                          state->active_after + s0, state->active_after + 64);
         if (tid == 0 && path != 0) {
             ++relaxed;
             if (path == 2) ++dense;

@@ -45,6 +45,25 @@
 #define FXT_PHASE(...) do { __VA_ARGS__; } while (0)
 #define FXT_SYNC() __syncthreads()
 #define FXT_END() do { } while (0)
+// Phase timing (library built with EXTRA=-DFXB_TAIL_TIMING, read by tools/tail_probe.py): thread 0 of every CTA
+// accumulates the cycles between consecutive marks of an item and adds them to marks[8 * path + k] at the end,
+// plus one count in marks[24 + path].
+#ifdef FXB_TAIL_TIMING
+#define FXT_MARK_BEGIN() long long fxt_t0 = clock64(), fxt_d[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FXT_MARK(k) do { const long long c_ = clock64(); fxt_d[k] += c_ - fxt_t0; fxt_t0 = c_; } while (0)
+#define FXT_MARK_END(marks, path)                                                                      \
+    do {                                                                                               \
+        if (tid == 0 && (marks) != nullptr) {                                                          \
+            for (int k_ = 0; k_ < 8; ++k_)                                                             \
+                if (fxt_d[k_]) atomicAdd(&(marks)[8 * (path) + k_], (unsigned long long)fxt_d[k_]);    \
+            atomicAdd(&(marks)[24 + (path)], 1ull);                                                    \
+        }                                                                                              \
+    } while (0)
+#else
+#define FXT_MARK_BEGIN() do { } while (0)
+#define FXT_MARK(k) do { } while (0)
+#define FXT_MARK_END(marks, path) do { } while (0)
+#endif
 namespace fxb { typedef float4 Quad; }
 #else
 #include <cmath>
@@ -71,6 +90,9 @@ static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + 
 #define FXT_PHASE(...) emu.seg.push_back([&](int tid) { TailThread<S>& t = emu.th[tid]; (void)t; (void)tid; __VA_ARGS__; })
 #define FXT_SYNC() emu.flush()
 #define FXT_END() emu.flush()
+#define FXT_MARK_BEGIN() (void)0
+#define FXT_MARK(k) (void)0
+#define FXT_MARK_END(marks, path) (void)0
 namespace fxb { struct alignas(16) Quad { float x, y, z, w; }; }
 #endif
 
@@ -623,50 +645,65 @@ template <class S>
 FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& P, const TailWork& W, const int brick,
                          const int sub, const float* __restrict__ p_in, float* __restrict__ p_out,
                          const float* __restrict__ rhs, const unsigned char* __restrict__ m_in,
-                         unsigned char* __restrict__ m_out, unsigned long long* active_after_s0) {
+                         unsigned char* __restrict__ m_out, unsigned long long* active_after_s0,
+                         unsigned long long* marks) {
     const TailItem<S> it = tail_item<S>(P, brick, sub);
     FXT_THREAD_STATE(S);
+    FXT_MARK_BEGIN();
     int path = 0;
     FXT_SYNC();  // the previous item is finished with shared memory
     FXT_PHASE(if (tid < S::kCtrlWords) sh.ctrl[tid] = 0u);
     FXT_SYNC();
+    FXT_MARK(0);
     if (it.ex > 0) {
         FXT_PHASE(tail_phase_flags<S>(tid, t, sh, it, P, m_in));
         FXT_SYNC();
+        FXT_MARK(1);
         const int n_list = (int)sh.ctrl[S::kCtrlTotal];
         if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
             FXT_PHASE(tail_phase_copy<S>(t, it, P, p_in, p_out, m_out));
+            FXT_MARK(6);
         } else if (n_list <= P.sparse_cap) {  // relax a compacted list of the active cells
             path = 1;
             FXT_PHASE(tail_sparse_scan<S>(tid, sh));
             FXT_SYNC();
+            FXT_MARK(2);
             FXT_PHASE(tail_sparse_build<S>(tid, t, sh, it, P, p_in));
             FXT_SYNC();
+            FXT_MARK(3);
             FXT_PHASE(tail_sparse_gather<S>(tid, sh, it, P, rhs, n_list));
             FXT_SYNC();
+            FXT_MARK(4);
             for (int s = 1; s <= P.levels; ++s) {
                 FXT_PHASE(tail_sparse_relax<S>(tid, sh, it, P, n_list, s));
                 FXT_SYNC();
                 FXT_PHASE(tail_sparse_commit<S>(tid, sh, n_list, s));
                 FXT_SYNC();
             }
+            FXT_MARK(5);
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
+            FXT_MARK(6);
         } else {  // crowded window: register columns
             path = 2;
             FXT_PHASE(tail_phase_load<S>(t, sh, it, P, p_in, rhs));
             FXT_SYNC();
+            FXT_MARK(3);
             for (int s = 1; s <= P.levels; ++s) {
                 FXT_PHASE(tail_phase_relax<S>(t, sh, it, P, s));
                 FXT_SYNC();
                 FXT_PHASE(tail_phase_publish<S>(t, sh, s, s == P.levels));
                 FXT_SYNC();
             }
+            FXT_MARK(5);
             FXT_PHASE(tail_phase_store<S>(t, sh, it, P, p_out));
             FXT_SYNC();
             FXT_PHASE(tail_phase_store_mask<S>(t, sh, it, P, m_out));
+            FXT_MARK(6);
         }
     }
     FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
+    FXT_MARK(7);
+    FXT_MARK_END(marks, path);
     FXT_END();
     return path;
 }
