@@ -38,6 +38,13 @@
 #define FXT_LDG_U8(p) __ldg(p)
 #define FXT_LDG_F32(p) __ldg(p)
 #define FXT_ATOMIC_AND_U32(p, v) atomicAnd((p), (v))
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register in between, so a thread's copies are all in flight
+// at once; `valid` false zero-fills the destination (the source address must still be a mapped one).
+#define FXT_CP_ASYNC_16(dst, src, valid)                                                                       \
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), \
+                 "l"(src), "r"((valid) ? 16 : 0)                                                               \
+                 : "memory")
+#define FXT_CP_ASYNC_WAIT() asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory")
 // A work item is a sequence of phases separated by barriers (tail_run_item).  Under nvcc a phase is just the
 // statement, executed by the calling thread `tid` with its state `t`.
 #define FXT_CTX(S) const int tid
@@ -79,6 +86,12 @@ static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + 
 #define FXT_LDG_U8(p) (*(p))
 #define FXT_LDG_F32(p) (*(p))
 #define FXT_ATOMIC_AND_U32(p, v) (*(p) &= (v))
+#define FXT_CP_ASYNC_16(dst, src, valid)                                      \
+    do {                                                                      \
+        const fxb::Quad zero_ = {0.f, 0.f, 0.f, 0.f};                         \
+        *reinterpret_cast<fxb::Quad*>(dst) = (valid) ? *reinterpret_cast<const fxb::Quad*>(src) : zero_; \
+    } while (0)
+#define FXT_CP_ASYNC_WAIT() (void)0
 // Emulation: phases are queued and run at the next barrier, thread after thread — every thread runs ALL phases of
 // the barrier-free segment before the next thread starts (in ascending or descending thread order).  That is the
 // most skewed interleaving a missing __syncthreads() would permit, so a phase that needs another thread's result
@@ -153,6 +166,7 @@ struct TailParams {
     int early_exit;
     int levels;          // sweeps to apply (<= TT)
     int sparse_cap;      // windows with at most this many relaxable active cells take the sparse path (<= kListCap)
+    int cp_async;        // 1: the sparse path stages its window with cp.async; 0: through registers
 };
 
 // Shared-memory view.
@@ -281,14 +295,19 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
     t.own[0] = t.own[1] = 0u;
     t.dirty = 0u;
     const int nxb = P.nx >> 3;
+    // All flag bytes of the column are requested before the first one is decoded (an in-order core would otherwise
+    // pay one memory round trip per plane); planes outside the grid re-read byte 0 of the mask and are ignored.
+    unsigned raw[S::LZ];
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) {
+        const bool in = t.in_xy && z >= it.zvl && z < it.zvh && !P.first;
+        raw[z] = FXT_LDG_U8(in ? m_in + ((size_t)(it.wz + z) * P.ny + t.gy) * nxb + (t.gx >> 3) : m_in);
+    }
+    FXT_COMPILER_FENCE();
 #pragma unroll
     for (int z = 0; z < S::LZ; ++z) {
         if (!t.in_xy || z < it.zvl || z >= it.zvh) continue;
-        unsigned n = 0xFu;
-        if (!P.first) {
-            const unsigned b = FXT_LDG_U8(m_in + ((size_t)(it.wz + z) * P.ny + t.gy) * nxb + (t.gx >> 3));
-            n = (b >> (t.gx & 4)) & 0xFu;
-        }
+        const unsigned n = P.first ? 0xFu : (raw[z] >> (t.gx & 4)) & 0xFu;
         t.fl[z >> 3] |= n << (4 * (z & 7));
         if (t.own_xy && z >= S::TT && z - S::TT < it.ez) t.own[z >> 3] |= 0xFu << (4 * (z & 7));
     }
@@ -475,21 +494,34 @@ template <class S>
 FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
                               const TailParams& P, const float* __restrict__ p_in) {
     if (!t.used) return;
-    const Quad zero = {0.f, 0.f, 0.f, 0.f};
-    Quad q[S::LZ];  // every load is issued before the first store (cells outside the grid read p_in[0..3], then zero)
+    if (P.cp_async) {
+        // global -> shared without passing through registers: all planes of the column are in flight at once
 #pragma unroll
-    for (int z = 0; z < S::LZ; ++z) {
-        const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
-        q[z] = *reinterpret_cast<const Quad*>(in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in);
-    }
-    FXT_COMPILER_FENCE();
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            FXT_CP_ASYNC_16(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx,
+                            in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in, in);
+        }
+    } else {
+        const Quad zero = {0.f, 0.f, 0.f, 0.f};
+        Quad q[S::LZ];  // cells outside the grid read p_in[0..3] and store zero
 #pragma unroll
-    for (int z = 0; z < S::LZ; ++z) {
-        const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
-        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = in ? q[z] : zero;
-        sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            q[z] = *reinterpret_cast<const Quad*>(in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in);
+        }
+#pragma unroll
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = in ? q[z] : zero;
+        }
     }
-    if (t.nlist == 0) return;
+#pragma unroll
+    for (int z = 0; z < S::LZ; ++z) sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
+    if (t.nlist == 0) {
+        if (P.cp_async) FXT_CP_ASYNC_WAIT();
+        return;
+    }
     int at = 0;  // entries of the threads before this one
     for (int w = 0; w < (tid >> 5); ++w) at += sh.scan[S::kThreads + w];
     for (int l = tid & ~31; l < tid; ++l) at += sh.scan[l];
@@ -506,6 +538,7 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
                             (own ? kTailOwn : 0u);
         }
     }
+    if (P.cp_async) FXT_CP_ASYNC_WAIT();  // the copies land before the barrier that follows this phase
 }
 
 // ---- sparse phase 3: right-hand sides of the listed cells -> side array (eight independent loads in flight) --------
@@ -533,23 +566,43 @@ template <class S>
 FXT_FN void tail_sparse_relax(int tid, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P, int n,
                               int s) {
     const float eps = P.early_exit ? kTailEps : -1.0f;
-    for (int e = tid; e < n; e += S::kThreads) {
-        const unsigned ent = sh.list[e];
-        if (ent == kTailDead || (int)((ent >> kTailDepthShift) & 7u) < s) continue;
-        const int idx = (int)(ent & kTailIdxMask);
-        const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
-        const int gx = it.wx + x, gy = it.wy + y, gz = it.wz + z;
-        const float c = sh.p[idx];
-        // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); elsewhere the neighbour is inside the window
-        const float l = gx == 0 ? c : sh.p[idx - 1];
-        const float rr = gx == P.nx - 1 ? c : sh.p[idx + 1];
-        const float u = gy == 0 ? c : sh.p[idx - S::LX];
-        const float d = gy == P.ny - 1 ? c : sh.p[idx + S::LX];
-        const float f = gz == P.z_face_lo ? c : sh.p[idx - S::kPlane];
-        const float b = gz == P.z_face_hi - 1 ? c : sh.p[idx + S::kPlane];
-        unsigned act = 1u;
-        sh.newv[e] = tail_cell(c, l, rr, u, d, f, b, sh.rhsv[e], 1u, eps, act);
-        sh.list[e] = ent | kTailFresh | (act ? 0u : kTailFroze);
+    // Four entries per trip: their reads are independent, so the latencies overlap instead of adding up.
+    for (int base = tid; base < n; base += 4 * S::kThreads) {
+        unsigned ent[4];
+        float nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = base + u * S::kThreads;
+            ent[u] = e < n ? sh.list[e] : kTailDead;
+            if (ent[u] != kTailDead && (int)((ent[u] >> kTailDepthShift) & 7u) < s) ent[u] = kTailDead;  // skipped this sweep
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            nv[u] = 0.f;
+            if (ent[u] == kTailDead) continue;
+            const int e = base + u * S::kThreads;
+            const int idx = (int)(ent[u] & kTailIdxMask);
+            const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
+            const int gx = it.wx + x, gy = it.wy + y, gz = it.wz + z;
+            const float c = sh.p[idx];
+            // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); elsewhere the neighbour is inside the window
+            const float l = gx == 0 ? c : sh.p[idx - 1];
+            const float rr = gx == P.nx - 1 ? c : sh.p[idx + 1];
+            const float up = gy == 0 ? c : sh.p[idx - S::LX];
+            const float dn = gy == P.ny - 1 ? c : sh.p[idx + S::LX];
+            const float f = gz == P.z_face_lo ? c : sh.p[idx - S::kPlane];
+            const float b = gz == P.z_face_hi - 1 ? c : sh.p[idx + S::kPlane];
+            unsigned act = 1u;
+            nv[u] = tail_cell(c, l, rr, up, dn, f, b, sh.rhsv[e], 1u, eps, act);
+            ent[u] |= kTailFresh | (act ? 0u : kTailFroze);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ent[u] == kTailDead) continue;  // nothing computed: the list entry stays as it is
+            const int e = base + u * S::kThreads;
+            sh.newv[e] = nv[u];
+            sh.list[e] = ent[u];
+        }
     }
 }
 
@@ -557,19 +610,30 @@ FXT_FN void tail_sparse_relax(int tid, const TailShared<S>& sh, const TailItem<S
 template <class S>
 FXT_FN void tail_sparse_commit(int tid, const TailShared<S>& sh, int n, int s) {
     unsigned live = 0;
-    for (int e = tid; e < n; e += S::kThreads) {
-        const unsigned ent = sh.list[e];
-        if (ent == kTailDead || !(ent & kTailFresh)) continue;
-        const int idx = (int)(ent & kTailIdxMask);
-        sh.p[idx] = sh.newv[e];
-        if (ent & kTailFroze) {
-            const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
-            const int byte = (z * S::LY + y) * S::LXQ + (x >> 2);
-            FXT_ATOMIC_AND_U32(reinterpret_cast<unsigned*>(sh.nib) + (byte >> 2), ~(1u << (8 * (byte & 3) + (x & 3))));
-            sh.list[e] = kTailDead;
-        } else {
-            sh.list[e] = ent & ~kTailFresh;
-            if (ent & kTailOwn) ++live;
+    for (int base = tid; base < n; base += 4 * S::kThreads) {
+        unsigned ent[4];
+        float nv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = base + u * S::kThreads;
+            ent[u] = e < n ? sh.list[e] : kTailDead;
+            nv[u] = sh.newv[e < n ? e : base];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ent[u] == kTailDead || !(ent[u] & kTailFresh)) continue;
+            const int e = base + u * S::kThreads;
+            const int idx = (int)(ent[u] & kTailIdxMask);
+            sh.p[idx] = nv[u];
+            if (ent[u] & kTailFroze) {
+                const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
+                const int byte = (z * S::LY + y) * S::LXQ + (x >> 2);
+                FXT_ATOMIC_AND_U32(reinterpret_cast<unsigned*>(sh.nib) + (byte >> 2), ~(1u << (8 * (byte & 3) + (x & 3))));
+                sh.list[e] = kTailDead;
+            } else {
+                sh.list[e] = ent[u] & ~kTailFresh;
+                if (ent[u] & kTailOwn) ++live;
+            }
         }
     }
     if (live) FXT_ATOMIC_ADD_U32(&sh.ctrl[s], live);

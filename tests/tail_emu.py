@@ -59,10 +59,10 @@ def paths():
 
 
 def launch(g: BrickGrid, p_in, p_out, rhs, m_in, m_out, relax_in, copy_in, brick_state, hist_s0, first, early_exit=True,
-           levels=4, tt=4, sparse_cap=-1):
+           levels=4, tt=4, sparse_cap=-1, cp_async=1):
     """One emulated launch.  Returns (relax_out, copy_out).  p_out / m_out / brick_state / hist_s0 are updated in place."""
     geom = np.array([g.nx, g.ny, g.nz, 0, g.nz, 0, g.nz, g.bx, g.by, g.bz], np.int32)
-    flags = np.array([int(first), int(early_exit), levels, tt, sparse_cap], np.int32)
+    flags = np.array([int(first), int(early_exit), levels, tt, sparse_cap, cp_async], np.int32)
     relax_in = np.ascontiguousarray(relax_in, np.int32)
     copy_in = np.ascontiguousarray(copy_in, np.int32)
     relax_out, copy_out = np.full(g.n, -1, np.int32), np.full(g.n, -1, np.int32)

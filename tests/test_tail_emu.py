@@ -11,7 +11,8 @@ from tests import tail_emu as E
 from tests.util import smooth_state
 
 
-def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True, sparse_cap=-1):
+def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True, sparse_cap=-1,
+                    cp_async=1):
     """Whole pressure solve by emulated tail launches only (first launch: every brick, every cell active).
     Returns (p, s_exec, launches).  After every launch the output buffer must equal the oracle's state everywhere."""
     nz, ny, nx = s2.shape
@@ -30,7 +31,7 @@ def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=Tr
         src, dst = seq & 1, (seq + 1) & 1
         relax, copy_next = E.launch(g, p[src], p[dst], rhs, m[src], m[dst], relax, copy, brick_state, hist[done:],
                                     first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt,
-                                    sparse_cap=sparse_cap)
+                                    sparse_cap=sparse_cap, cp_async=cp_async)
         p_ref, act_ref, counts = oracle_mod.jacobi_sweeps_slab(s2, p_ref, act_ref, levels, nz, 0, 0, nz, early_exit)
         done += levels
         seq += 1
@@ -110,6 +111,6 @@ def test_tail_two_sweep_shape_and_thin_bricks(oracle_mod, thread_order):
     n = (64, 64, 13)
     s2, p0 = developed_state(oracle_mod, n, 8)
     p_want, s_want, _, _ = oracle_mod.jacobi(s2, p0, 64, True)
-    p_got, s_got, _ = solve_with_tail(oracle_mod, s2, p0, (120, 10, 5), tt=2)
+    p_got, s_got, _ = solve_with_tail(oracle_mod, s2, p0, (120, 10, 5), tt=2, cp_async=0)
     assert np.array_equal(p_got, p_want)
     assert s_got == s_want

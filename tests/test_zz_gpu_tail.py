@@ -74,6 +74,18 @@ def test_tail_schedule_matches_oracle(oracle_mod, n):
     assert launches > 0 and ts["tail_bricks"] > 0
 
 
+def test_tail_window_staged_through_registers(oracle_mod):
+    """FXB_TAIL_CPASYNC=0: the sparse path loads its window through registers instead of cp.async."""
+    launches, _ = run_pair(oracle_mod, (128, 128, 40), 8, {"FXB_TAIL_CPASYNC": 0}, inject_seed=15)
+    assert launches > 0
+
+
+def test_tail_dense_path_only(oracle_mod):
+    """FXB_TAIL_SPARSE_CAP=0: every window that holds an active cell takes the register-column path."""
+    _, ts = run_pair(oracle_mod, (64, 64, 40), 6, {"FXB_TAIL_SPARSE_CAP": 0})
+    assert ts["tail_subblocks_dense"] == ts["tail_subblocks_relaxed"] > 0
+
+
 def test_tail_takes_over_right_after_pass_zero(oracle_mod):
     launches, _ = run_pair(oracle_mod, (64, 64, 64), 8, {"FXB_TAIL_MAINS": 1}, inject_seed=11)
     assert launches > 0

@@ -125,8 +125,12 @@ def main():
     oracle_check(fx, "tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}, n=(64, 64, 40), steps=4)
     timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
                                           ("tail_grid592", {"FXB_TAIL_GRID": 592}),
-                                          ("tail_mains1", {"FXB_TAIL_MAINS": 1})], all_fields=True)
-    timing(fx, (512, 512, 512), 100, 20, [("tail", {})])
+                                          ("tail_mains1", {"FXB_TAIL_MAINS": 1}),
+                                          ("tail_no_cpasync", {"FXB_TAIL_CPASYNC": 0}),
+                                          ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
+                                          ("tail_thr1024", {"FXB_TAIL_THRESHOLD": 1024, "FXB_TAIL_MAINS": 12})],
+           all_fields=True)
+    timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("tail_thr2048", {"FXB_TAIL_THRESHOLD": 2048, "FXB_TAIL_MAINS": 12})])
     oracle_check(fx, "default", None)
     emit(stage="done")
 
