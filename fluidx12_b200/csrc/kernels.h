@@ -49,7 +49,8 @@ struct FusedJacobi {
     int* brick_state = nullptr;                   // [bricks] sub-block arrivals of the tail kernel; zero between launches
     int tail_threshold = 0;                       // a tail launch takes over once at most this many bricks are listed
     int tail_grid = 0;                            // CTAs of a tail launch
-    int tail_cp_async = 1;                        // sparse path stages its window with cp.async (0: through registers)
+    int tail_cp_async = 0;                        // 1 (FXB_TAIL_CPASYNC=1): the sparse path stages its window with cp.async;
+                                                  // not yet run on a GPU, hence off by default
     int tail_sparse_cap = -1;                     // active cells per window up to which the sparse path is taken (-1: capacity)
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer

@@ -126,7 +126,7 @@ def main():
     timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
                                           ("tail_grid592", {"FXB_TAIL_GRID": 592}),
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1}),
-                                          ("tail_no_cpasync", {"FXB_TAIL_CPASYNC": 0}),
+                                          ("tail_cpasync", {"FXB_TAIL_CPASYNC": 1}),
                                           ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
                                           ("tail_thr1024", {"FXB_TAIL_THRESHOLD": 1024, "FXB_TAIL_MAINS": 12})],
            all_fields=True)
