@@ -114,3 +114,68 @@ def test_tail_two_sweep_shape_and_thin_bricks(oracle_mod, thread_order):
     p_got, s_got, _ = solve_with_tail(oracle_mod, s2, p0, (120, 10, 5), tt=2, cp_async=0)
     assert np.array_equal(p_got, p_want)
     assert s_got == s_want
+
+
+@pytest.mark.parametrize("nranks,n", [(2, (64, 64, 40)), (3, (136, 136, 36))])
+def test_tail_on_z_slabs_matches_single_domain(oracle_mod, nranks, n):
+    """The multi-GPU form of the tail launches, emulated: every rank holds its slab plus `halo` planes, the pressure
+    (and, from the second launch on, the freeze mask) halo of TT planes is exchanged before each launch, the launch
+    relaxes the bricks of the owned planes only.  Owned planes must equal the single-domain oracle bit for bit, and
+    the summed histograms must match — this pins the slab-window geometry of jacobi_tail_body.cuh (z_face_lo / z_face_hi
+    / nz_alloc / z_out0 / z_out1) before the schedule is run on more than one GPU."""
+    from fluidx12_b200 import halo_plan
+    nx, ny, nz = n
+    tt, iters = 4, 64
+    s2, p0 = developed_state(oracle_mod, n, 8)
+    rhs_g = (-0.5 * s2).astype(np.float32)
+    p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, iters, True)
+
+    class Rank:
+        pass
+
+    ranks = []
+    for r in range(nranks):
+        k = Rank()
+        k.plan = halo_plan(nz, r, nranks, 2, h_adv=5)
+        zf, nza = k.plan.z_first, k.plan.nz_alloc
+        assert k.plan.halo >= tt
+        k.win = slice(zf, zf + nza)
+        k.p = [p0[k.win].copy(), np.full((nza, ny, nx), np.nan, np.float32)]
+        k.rhs = rhs_g[k.win].copy()      # the right-hand side halo is exchanged once per step (constant over the sweeps)
+        k.m = [np.zeros((nza, ny, nx // 8), np.uint8), np.zeros((nza, ny, nx // 8), np.uint8)]
+        k.g = E.BrickGrid(nx, ny, k.plan.z1 - k.plan.z0, 120, 12, 8)
+        k.slab = (nza, -zf, nz - zf, k.plan.z0 - zf, k.plan.z1 - zf)
+        k.state = np.zeros(k.g.n, np.int32)
+        k.hist = np.zeros(iters + 8, np.uint64)
+        k.relax, k.copy = np.arange(k.g.n, dtype=np.int32), np.zeros(0, np.int32)
+        ranks.append(k)
+
+    def exchange(field_of, depth):
+        """Every rank receives `depth` planes beyond each interior face from the owner of those planes."""
+        for r, k in enumerate(ranks):
+            zf = k.plan.z_first
+            for peer, lo, hi in ((r - 1, k.plan.z0 - depth, k.plan.z0), (r + 1, k.plan.z1, k.plan.z1 + depth)):
+                if 0 <= peer < nranks:
+                    o = ranks[peer]
+                    assert o.plan.z0 <= lo and hi <= o.plan.z1  # halo not deeper than the neighbour's slab
+                    field_of(k)[lo - zf:hi - zf] = field_of(o)[lo - o.plan.z_first:hi - o.plan.z_first]
+
+    done = seq = 0
+    while done < iters:
+        levels = min(tt, iters - done)
+        src, dst = seq & 1, (seq + 1) & 1
+        exchange(lambda k: k.p[src], tt)
+        if seq:
+            exchange(lambda k: k.m[src], tt)
+        for k in ranks:
+            k.relax, k.copy = E.launch(k.g, k.p[src], k.p[dst], k.rhs, k.m[src], k.m[dst], k.relax, k.copy, k.state,
+                                       k.hist[done:], first=(seq == 0), levels=levels, tt=tt, slab=k.slab)
+        done += levels
+        seq += 1
+        total = sum(k.hist[:done].astype(np.int64) for k in ranks)
+        if total[done - 1] == 0:
+            break
+    got = np.concatenate([k.p[seq & 1][k.slab[3]:k.slab[4]] for k in ranks])
+    assert np.array_equal(got, p_want)
+    total = sum(k.hist[:iters].astype(np.int64) for k in ranks)
+    assert np.array_equal(total[:s_want - 1], hist_want[1:s_want])
