@@ -194,6 +194,14 @@ std::vector<int> plan_pressure_solve(int iters, int T, int TT, int mains) {
     return plan;
 }
 
+// Pressure ping-pong flips of one (dt > 0) step as the HOST must know them (multi-GPU: they select the buffers whose
+// halos are exchanged): every launch of the plan flips once there, because every rank runs every launch.
+int flips_per_step(const fxb_sim* s) {
+    if (!s->fused) return 0;
+    if (s->tail) return (int)plan_pressure_solve(s->cfg.jacobi_iters, s->fuse_t, fxb::jacobi_tail_sweeps(), 1).size();
+    return (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
+}
+
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 
 void fork_colour(fxb_sim* s, cudaStream_t st);
@@ -229,19 +237,41 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 // Dynamic schedule: which kernel relaxes is decided on the device (jacobi_tail.cu).  A group is one
                 // tail launch (TT sweeps) followed by the TT/T bulk passes that cover the same sweeps; the tail
                 // launch of a group runs iff few enough bricks are listed, the bulk passes run iff it did not.
-                const int iters = s->cfg.jacobi_iters;
+                const int iters = s->cfg.jacobi_iters, TT = fxb::jacobi_tail_sweeps();
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
-                for (const int kind : plan_pressure_solve(iters, s->fuse_t, fxb::jacobi_tail_sweeps(), s->tail_mains)) {
+                // Multi-GPU (experimental): every rank runs every launch of the plan (tail_mains is forced to 1 and the
+                // tail launches are unconditional), so the position in the relax sequence — hence the ping-pong side and
+                // the mask buffer whose halo must be exchanged — is the launch index on every rank.
+                const bool mg = s->multi() && s->dt > 0.0f;
+                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, deep enough for a tail launch
+                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, std::max(TT, s->fuse_t)}};
+                    s->comm.exchange(d, f, 1, st);
+                }
+                int seq = 0;
+                for (const int kind : plan_pressure_solve(iters, s->fuse_t, TT, s->multi() ? 1 : s->tail_mains)) {
+                    if (mg) {
+                        const int depth = kind >= 0 ? s->fuse_t : TT;
+                        const fxb::HaloField f[2] = {{s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, depth},
+                                                     {s->jac.mask[seq & 1], s->plane_voxels() / 8, depth}};
+                        s->comm.exchange(d, f, seq == 0 ? 1 : 2, st);
+                    }
                     if (kind >= 0)
                         fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, kind, iters, s->cfg.early_exit,
-                                                      false, 0, 0, st);
+                                                      s->multi(), 0, 0, st);
                     else
                         fxb::launch_jacobi_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit,
-                                                kind == kTailIfFew ? s->jac.tail_threshold : -1, st);
+                                                kind == kTailIfFew && !s->multi() ? s->jac.tail_threshold : -1, s->multi(),
+                                                st);
                     ++launches;
+                    ++seq;
                 }
+                if (mg) s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st);  // global s_exec (as below)
                 fxb::launch_finish_solve_dynamic(s->d_frame, s->d_state, iters, st);
                 ++launches;
+                if (mg) {  // z neighbours of the final pressure for the gradient
+                    const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, 1}};
+                    s->comm.exchange(d, f, 1, st);
+                }
             } else if (s->fused) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
                 cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
@@ -521,7 +551,9 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
         s->fused = true;
         const char* tail_env = getenv("FXB_TAIL");
-        if (tail_env && atoi(tail_env) != 0 && !s->multi() && s->jac.variant == 0 &&
+        // multi-GPU: needs a pressure/mask halo as deep as a tail launch and the per-pass exchange (no grouping)
+        const bool tail_ok_multi = !s->multi() || (s->halo >= fxb::jacobi_tail_sweeps() && s->jacobi_group == 1);
+        if (tail_env && atoi(tail_env) != 0 && tail_ok_multi && s->jac.variant == 0 &&
             fxb::jacobi_tail_supported(s->jac, s->dom)) {
             e = cudaMalloc((void**)&s->jac.brick_state, nb * sizeof(int));
             if (e == cudaSuccess) e = cudaMemset(s->jac.brick_state, 0, nb * sizeof(int));
@@ -610,7 +642,7 @@ int fxb_simulate(fxb_sim* s, void* cuda_stream) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
-    const int npass = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : 0;
+    const int npass = flips_per_step(s);
     if (s->multi()) {
         // the exchanges depend on dt > 0, the frame parity and the pressure parity: one graph per key, captured on
         // first use; a paused frame (dt <= 0) is enqueued directly
@@ -768,8 +800,7 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     for (int ph = 0; ph < PH_COUNT; ++ph) FXB_CUDA(cudaEventElapsedTime(&ms[ph], s->ev[ph], s->ev[ph + 1]));
     ms[4] = 0.0f;
     FXB_CUDA(cudaEventElapsedTime(&ms[5], s->ev[0], s->ev[PH_COUNT]));
-    if (s->multi() && s->fused && s->dt > 0.0f)
-        s->p_cur_host = (s->p_cur_host + (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t) & 1;
+    if (s->multi() && s->fused && s->dt > 0.0f) s->p_cur_host = (s->p_cur_host + flips_per_step(s)) & 1;
     s->last_stream = st;
     ++s->steps;
     return FXB_OK;

@@ -29,6 +29,7 @@ struct TailLaunch {
     TailParams P;      // levels / first are filled in on the device
     int iters;         // ITER
     int threshold;     // run only when at most this many bricks are listed; < 0: always
+    int run_all;       // multi-GPU: never end the solve on this rank's own freeze counters
     int nbricks;
     int* list[2];      // [2 * bricks] per parity of seq: bricks to relax, then bricks to copy (jacobi_fused.cu)
     int* relax_count;  // [seq]
@@ -45,7 +46,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
     const int seq = state->seq, s0 = state->sweeps_done, p_cur = state->p_cur;
     if (!(0.0f < dt)) return;
     if (seq == 0 || s0 <= 0 || s0 >= L.iters) return;         // bulk pass 0 builds the lists; nothing left to do
-    if (state->active_after[s0 - 1] == 0ull) return;           // every cell is frozen: the solve is over
+    if (!L.run_all && state->active_after[s0 - 1] == 0ull) return;  // every cell is frozen: the solve is over
     const int n_relax = L.relax_count[seq], n_copy = L.copy_count[seq];
     if (L.threshold >= 0 && n_relax > L.threshold) return;     // too many bricks: the bulk kernel is the better tool
 
@@ -117,7 +118,7 @@ bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d) {
 }
 
 cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                               int iters, int early_exit, int threshold, cudaStream_t stream) {
+                               int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(jacobi_tail_kernel<TailS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -140,6 +141,7 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
     L.P.cp_async = J.tail_cp_async;
     L.iters = iters;
     L.threshold = threshold;
+    L.run_all = run_all ? 1 : 0;
     L.nbricks = J.ntx * J.nty * J.nzc;
     L.list[0] = J.work_list[0]; L.list[1] = J.work_list[1];
     const int np = FusedJacobi::kMaxPasses + 1;

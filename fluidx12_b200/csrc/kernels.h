@@ -69,8 +69,9 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
 // are still active (dynamic schedule only).  threshold < 0: run whatever the list length.
 bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d);
 int jacobi_tail_sweeps();
+// run_all (multi-GPU): the launch runs and flips the ping-pong even when this rank has nothing left to relax.
 cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                               int iters, int early_exit, int threshold, cudaStream_t stream);
+                               int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream);
 void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 
 }  // namespace fxb

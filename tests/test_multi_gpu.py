@@ -43,3 +43,18 @@ def test_four_ranks_and_eager_launch():
         pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
     rc, log = _run(4, {"FXB_TEST_GRID": "64,64,128", "FXB_TEST_T": "2", "FXB_TEST_GRAPH": "0"})
     assert rc == 0 and "MGPU_OK" in log, log[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="the dynamic schedule on z-slabs has not run on GPUs yet: FXB_TEST_EXPERIMENTAL=1 enables it")
+@pytest.mark.parametrize("nproc,grid", [(2, "64,64,96"), (4, "128,128,128")])
+def test_ranks_with_tail_schedule(nproc, grid):
+    """FXB_TAIL=1 on z-slabs: bulk pass 0, then 16 unconditional tail launches, one pressure/mask halo exchange of 4
+    planes before each (17 exchanges per step instead of 33).  Emulated on the CPU by
+    tests/test_tail_emu.py::test_tail_on_z_slabs_matches_single_domain."""
+    import torch
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (nproc, nproc))
+    rc, log = _run(nproc, {"FXB_TEST_GRID": grid, "FXB_TEST_T": "2", "FXB_TEST_TAIL": "1"})
+    assert rc == 0 and "MGPU_OK" in log, log[-3000:]
