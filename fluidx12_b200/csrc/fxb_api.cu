@@ -579,6 +579,17 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             jl = (int)plan_pressure_solve(s->cfg.jacobi_iters, s->fuse_t, fxb::jacobi_tail_sweeps(), s->tail_mains).size();
         s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
     }
+    if (s->multi() && getenv("FXB_P2P") && atoi(getenv("FXB_P2P")) != 0) {
+        // Experimental: halos through peer memory (CUDA IPC + one store/flag kernel per exchange) instead of NCCL
+        // send/recv; the all-reduce of the freeze counters stays on NCCL.
+        std::vector<void*> bufs = {s->vel[0], s->vel[1], s->col[0], s->col[1], (void*)s->p[0], (void*)s->p[1], (void*)s->rhs};
+        if (s->fused) { bufs.push_back(s->jac.mask[0]); bufs.push_back(s->jac.mask[1]); }
+        const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
+        const int zf_lo = r > 0 ? std::max((r - 1) * nz / R - s->halo, 0) : 0;
+        const int zf_hi = r < R - 1 ? std::max((r + 1) * nz / R - s->halo, 0) : 0;
+        if (!s->comm.p2p_init(bufs.data(), (int)bufs.size(), zf_lo, zf_hi, s->own_stream))
+            return cleanup_fail(fail(FXB_ERR_NCCL, "fxb_create: peer-memory halo setup failed: " + fxb::halo_last_error()));
+    }
     if (s->multi()) {
         // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
         const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, 1}};
@@ -673,6 +684,8 @@ int fxb_sync(fxb_sim* s) {
     if (!s) return fail(FXB_ERR_INVALID, "fxb_sync: null handle");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     FXB_CUDA(cudaDeviceSynchronize());
+    if (s->multi() && s->comm.p2p_timed_out())
+        return fail(FXB_ERR_NCCL, "fxb_sync: a peer-memory halo exchange timed out waiting for a neighbour (results are invalid)");
     return FXB_OK;
 }
 

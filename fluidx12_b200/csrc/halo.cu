@@ -10,7 +10,9 @@
 
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace fxb {
 
@@ -106,13 +108,204 @@ bool HaloComm::init(const void* unique_id128, int rank_, int nranks_) {
 }
 
 void HaloComm::destroy() {
+    if (p2p.enabled) {
+        for (int i = 0; i < p2p.nbuf; ++i) {
+            if (p2p.peer_lo[i]) cudaIpcCloseMemHandle(p2p.peer_lo[i]);
+            if (p2p.peer_hi[i]) cudaIpcCloseMemHandle(p2p.peer_hi[i]);
+        }
+        if (p2p.flags_lo) cudaIpcCloseMemHandle(p2p.flags_lo);
+        if (p2p.flags_hi) cudaIpcCloseMemHandle(p2p.flags_hi);
+        cudaFree(p2p.flags);
+        p2p = HaloP2P();
+    }
     if (comm && g_api.comm_destroy) g_api.comm_destroy(comm);
     comm = nullptr;
+}
+
+// ---- peer-memory backend -------------------------------------------------------------------------------------------
+namespace {
+
+struct P2PJob {
+    const char* src;
+    char* dst;
+    unsigned long long bytes;
+};
+
+struct P2PArgs {
+    P2PJob job[8];
+    int njobs;
+    int vec;                          // bytes per copy element: 16, 8 or 4 (what every job's alignment allows)
+    unsigned long long* flags;        // this rank's flag words (HaloP2P::flags)
+    unsigned long long* flags_lo;     // rank - 1's, or nullptr at the grid's lower face
+    unsigned long long* flags_hi;     // rank + 1's, or nullptr
+    long long timeout_cycles;
+};
+
+template <class V>
+__device__ __forceinline__ void p2p_copy(const P2PJob& j) {
+    const V* __restrict__ src = reinterpret_cast<const V*>(j.src);
+    V* __restrict__ dst = reinterpret_cast<V*>(j.dst);
+    const size_t n = j.bytes / sizeof(V), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void p2p_wait(volatile unsigned long long* flag, unsigned long long epoch, long long limit,
+                                         unsigned long long* timed_out) {
+    const long long t0 = clock64();
+    while (*flag < epoch) {
+        if (clock64() - t0 > limit) {  // never hang the device: record the failure and go on (results are then wrong)
+            *timed_out = 1ull;
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+// One exchange: store the face planes into the neighbours' halo planes, then (last CTA) publish this rank's epoch
+// in the neighbours' flag words and wait until both neighbours have published theirs.  Ordering: every CTA fences
+// at system scope before it reports done, the last CTA fences again before the flag stores, so a neighbour that sees
+// the epoch also sees the planes; its own consumers start after its own exchange kernel has finished.
+// A neighbour can be at most one exchange ahead (it waits for this rank's epoch at every exchange), which together
+// with the ping-pong of the pressure / mask buffers rules out overwriting planes that are still being read.
+__global__ void __launch_bounds__(256) halo_p2p_kernel(const __grid_constant__ P2PArgs a) {
+    for (int j = 0; j < a.njobs; ++j) {
+        if (a.vec == 16) p2p_copy<uint4>(a.job[j]);
+        else if (a.vec == 8) p2p_copy<uint2>(a.job[j]);
+        else p2p_copy<unsigned>(a.job[j]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (atomicAdd(&a.flags[3], 1ull) != (unsigned long long)gridDim.x - 1ull) return;
+    a.flags[3] = 0ull;
+    const unsigned long long epoch = a.flags[2] + 1ull;
+    a.flags[2] = epoch;
+    __threadfence_system();
+    if (a.flags_lo) *reinterpret_cast<volatile unsigned long long*>(a.flags_lo + 1) = epoch;  // this rank is its upper neighbour
+    if (a.flags_hi) *reinterpret_cast<volatile unsigned long long*>(a.flags_hi + 0) = epoch;
+    __threadfence_system();
+    if (a.flags_lo) p2p_wait(a.flags + 0, epoch, a.timeout_cycles, a.flags + 4);
+    if (a.flags_hi) p2p_wait(a.flags + 1, epoch, a.timeout_cycles, a.flags + 4);
+    __threadfence_system();
+}
+
+}  // namespace
+
+bool HaloComm::p2p_init(void* const* buffers, int nbuffers, int z_first_lo, int z_first_hi, cudaStream_t stream) {
+    if (nranks <= 1 || nbuffers <= 0 || nbuffers > HaloP2P::kMaxBuffers) return false;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return true;
+        g_err = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    };
+    HaloP2P h;
+    h.nbuf = nbuffers;
+    h.z_first_lo = z_first_lo;
+    h.z_first_hi = z_first_hi;
+    // 2 MiB so that the flag words are an allocation of their own (an IPC handle maps a whole allocation)
+    if (!cuda_ok(cudaMalloc((void**)&h.flags, 2u << 20), "cudaMalloc(flags)")) return false;
+    if (!cuda_ok(cudaMemset(h.flags, 0, 2u << 20), "cudaMemset(flags)")) return false;
+    // handles of this rank: the field buffers, then the flag words
+    const int nh = nbuffers + 1;
+    std::vector<cudaIpcMemHandle_t> mine(nh), from_lo(nh), from_hi(nh);
+    for (int i = 0; i < nbuffers; ++i) {
+        h.local[i] = buffers[i];
+        if (!cuda_ok(cudaIpcGetMemHandle(&mine[i], buffers[i]), "cudaIpcGetMemHandle")) return false;
+    }
+    if (!cuda_ok(cudaIpcGetMemHandle(&mine[nbuffers], h.flags), "cudaIpcGetMemHandle(flags)")) return false;
+    // ship them to both neighbours over the communicator that already exists (device staging buffers)
+    const size_t bytes = (size_t)nh * sizeof(cudaIpcMemHandle_t);
+    char* stage = nullptr;
+    if (!cuda_ok(cudaMalloc((void**)&stage, 3 * bytes), "cudaMalloc(stage)")) return false;
+    bool good = cuda_ok(cudaMemcpyAsync(stage, mine.data(), bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync");
+    good = good && ok(g_api.group_start(), "ncclGroupStart");
+    if (good && rank > 0) {
+        good = good && ok(g_api.send(stage, bytes, kNcclInt8, rank - 1, comm, stream), "ncclSend");
+        good = good && ok(g_api.recv(stage + bytes, bytes, kNcclInt8, rank - 1, comm, stream), "ncclRecv");
+    }
+    if (good && rank < nranks - 1) {
+        good = good && ok(g_api.send(stage, bytes, kNcclInt8, rank + 1, comm, stream), "ncclSend");
+        good = good && ok(g_api.recv(stage + 2 * bytes, bytes, kNcclInt8, rank + 1, comm, stream), "ncclRecv");
+    }
+    good = ok(g_api.group_end(), "ncclGroupEnd") && good;
+    good = good && cuda_ok(cudaMemcpyAsync(from_lo.data(), stage + bytes, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync");
+    good = good && cuda_ok(cudaMemcpyAsync(from_hi.data(), stage + 2 * bytes, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync");
+    good = good && cuda_ok(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    cudaFree(stage);
+    if (!good) return false;
+    for (int i = 0; i < nh; ++i) {
+        void** lo = i < nbuffers ? &h.peer_lo[i] : (void**)&h.flags_lo;
+        void** hi = i < nbuffers ? &h.peer_hi[i] : (void**)&h.flags_hi;
+        if (rank > 0 && !cuda_ok(cudaIpcOpenMemHandle(lo, from_lo[i], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+            return false;
+        if (rank < nranks - 1 &&
+            !cuda_ok(cudaIpcOpenMemHandle(hi, from_hi[i], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+            return false;
+    }
+    h.enabled = true;
+    p2p = h;
+    return true;
+}
+
+int HaloComm::p2p_timed_out() const {
+    if (!p2p.enabled) return 0;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, p2p.flags + 4, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    return v != 0ull;
 }
 
 // Exchanges `depth` planes of every listed field with the z-1 and z+1 neighbours.
 bool HaloComm::exchange(const Domain& d, const HaloField* fields, int nfields, cudaStream_t stream) {
     if (nranks <= 1) return true;
+    if (p2p.enabled) {
+        P2PArgs a;
+        a.njobs = 0;
+        a.vec = 16;
+        a.flags = p2p.flags;
+        a.flags_lo = rank > 0 ? p2p.flags_lo : nullptr;
+        a.flags_hi = rank < nranks - 1 ? p2p.flags_hi : nullptr;
+        // A neighbour may legitimately be seconds behind (host-side work between steps differs per rank), so the
+        // wait is generous; it only exists so that a broken run ends with an error instead of a hung device.
+        static const long long timeout_s = getenv("FXB_P2P_TIMEOUT_S") ? atoll(getenv("FXB_P2P_TIMEOUT_S")) : 30;
+        a.timeout_cycles = timeout_s * 2000000000ll;
+        size_t total = 0;
+        for (int i = 0; i < nfields; ++i) {
+            const HaloField& f = fields[i];
+            int b = -1;
+            for (int k = 0; k < p2p.nbuf; ++k)
+                if (p2p.local[k] == f.base) b = k;
+            if (b < 0 || a.njobs + 2 > 8) {
+                g_err = "p2p exchange: field buffer was not registered";
+                return false;
+            }
+            const char* base = static_cast<const char*>(f.base);
+            const size_t pb = f.plane_bytes, n = pb * f.depth;
+            const long long own0 = d.z_own0 - d.z_first, own1 = d.z_own1 - d.z_first;
+            if (rank > 0) {  // my lowest planes are rank - 1's upper halo: global planes [z_own0, z_own0 + depth)
+                P2PJob& j = a.job[a.njobs++];
+                j.src = base + own0 * pb;
+                j.dst = static_cast<char*>(p2p.peer_lo[b]) + (size_t)(d.z_own0 - p2p.z_first_lo) * pb;
+                j.bytes = n;
+            }
+            if (rank < nranks - 1) {  // my highest planes are rank + 1's lower halo: [z_own1 - depth, z_own1)
+                P2PJob& j = a.job[a.njobs++];
+                j.src = base + (own1 - f.depth) * pb;
+                j.dst = static_cast<char*>(p2p.peer_hi[b]) + (size_t)(d.z_own1 - f.depth - p2p.z_first_hi) * pb;
+                j.bytes = n;
+            }
+            total += 2 * n;
+        }
+        for (int j = 0; j < a.njobs; ++j)
+            while (a.vec > 4 && (((size_t)a.job[j].src | (size_t)a.job[j].dst | (size_t)a.job[j].bytes) % a.vec) != 0) a.vec >>= 1;
+        int grid = (int)(total / (256 * 64));  // about 64 copy elements' worth of bytes per thread
+        grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);
+        halo_p2p_kernel<<<grid, 256, 0, stream>>>(a);
+        if (cudaGetLastError() != cudaSuccess) {
+            g_err = "halo_p2p_kernel launch failed";
+            return false;
+        }
+        return true;
+    }
     if (!ok(g_api.group_start(), "ncclGroupStart")) return false;
     bool good = true;
     for (int i = 0; i < nfields && good; ++i) {

@@ -15,13 +15,36 @@ struct HaloField {
     int depth;           // planes exchanged on each interior face
 };
 
+// Peer-memory backend of the exchange (experimental, FXB_P2P=1): the neighbours' field buffers are mapped through
+// CUDA IPC and one kernel per exchange stores this rank's face planes straight into their halo planes over NVLink,
+// publishes an epoch flag in their memory and waits for theirs — no NCCL call on the step's critical path.
+struct HaloP2P {
+    static constexpr int kMaxBuffers = 12;
+    bool enabled = false;
+    int nbuf = 0;
+    void* local[kMaxBuffers] = {};
+    void* peer_lo[kMaxBuffers] = {};   // the same buffers of rank - 1 / rank + 1, mapped into this process
+    void* peer_hi[kMaxBuffers] = {};
+    unsigned long long* flags = nullptr;      // [8] in this rank's memory: [0] epoch published by rank - 1, [1] by
+                                              // rank + 1, [2] this rank's exchange counter, [3] finished CTAs, [4] timeout
+    unsigned long long* flags_lo = nullptr;   // the flag words of rank - 1 / rank + 1
+    unsigned long long* flags_hi = nullptr;
+    int z_first_lo = 0, z_first_hi = 0;       // Domain::z_first of the neighbours
+};
+
 struct HaloComm {
     void* comm = nullptr;  // ncclComm_t
     int rank = 0, nranks = 1;
+    HaloP2P p2p;
     bool init(const void* unique_id128, int rank, int nranks);
     void destroy();
     bool exchange(const Domain& d, const HaloField* fields, int nfields, cudaStream_t stream);
     bool all_reduce_sum_u64(void* buf, size_t count, cudaStream_t stream);
+    // Maps the listed device buffers (cudaMalloc'ed, one per exchanged field) of both z neighbours; the handles travel
+    // over the NCCL communicator.  z_first_lo / z_first_hi: global plane of local plane 0 on rank - 1 / rank + 1.
+    bool p2p_init(void* const* buffers, int nbuffers, int z_first_lo, int z_first_hi, cudaStream_t stream);
+    // 1 when a wait of the peer-memory exchange gave up (a neighbour never published its epoch); sticky.
+    int p2p_timed_out() const;
 };
 
 bool halo_unique_id(void* out128);

@@ -58,3 +58,18 @@ def test_ranks_with_tail_schedule(nproc, grid):
         pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (nproc, nproc))
     rc, log = _run(nproc, {"FXB_TEST_GRID": grid, "FXB_TEST_T": "2", "FXB_TEST_TAIL": "1"})
     assert rc == 0 and "MGPU_OK" in log, log[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="the peer-memory halo exchange has not run on GPUs yet: FXB_TEST_EXPERIMENTAL=1 enables it")
+@pytest.mark.parametrize("nproc,grid,tail", [(2, "64,64,96", "0"), (2, "72,72,64", "0"), (4, "128,128,128", "0"),
+                                             (2, "64,64,96", "1")])
+def test_ranks_with_peer_memory_halos(nproc, grid, tail):
+    """FXB_P2P=1: face planes are stored straight into the neighbours' halo planes (CUDA IPC + NVLink) by one kernel
+    per exchange that also publishes / awaits an epoch flag; results must stay bit-identical to a single GPU."""
+    import torch
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (nproc, nproc))
+    rc, log = _run(nproc, {"FXB_TEST_GRID": grid, "FXB_TEST_T": "2", "FXB_P2P": "1", "FXB_TEST_TAIL": tail})
+    assert rc == 0 and "MGPU_OK" in log, log[-3000:]
