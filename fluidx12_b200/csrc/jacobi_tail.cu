@@ -101,6 +101,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
             state->sweeps_done = s0 + P.levels;
             state->tail_launches += 1;
             state->tail_bricks += (unsigned long long)n_relax;
+            state->bricks_processed += (unsigned long long)n_relax;  // one HBM pass of the brick, like a bulk pass
             state->bricks_copied += (unsigned long long)n_copy;
         }
     }

@@ -75,7 +75,7 @@ typedef struct fxb_stats {
     uint64_t active_after_first_sweep; /* cells still active after sweep 1, last step (this rank) */
     uint64_t total_sweeps;     /* cumulative s_exec over all steps */
     uint64_t total_passes;     /* cumulative jacobi_passes over all steps */
-    uint64_t bricks_processed; /* cumulative bricks relaxed by fused passes (frozen bricks are skipped) */
+    uint64_t bricks_processed; /* cumulative brick passes: bricks relaxed by a fused pass or a tail launch (frozen bricks are skipped) */
     uint64_t bricks_copied;    /* cumulative frozen bricks copied once into the other pressure buffer */
     uint64_t brick_cells;      /* output cells per brick (120 x (32-2T) x bz) */
     uint64_t bricks_per_pass;  /* bricks in the grid of one pass */
