@@ -13,6 +13,7 @@
 //   * the 14 lerps of the 7 used channels run as packed FADD2/FFMA2 on (x,y) and (z,w) pairs;
 //   * a back-trace that lands exactly on a texel centre (still-quiescent voxels) needs 2 loads, not 16.
 // Algorithmic traffic: 32 B/voxel (velocity in 8 + colour in 8 + velocity out 8 + colour out 8).
+#include "advect_body.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -66,23 +67,15 @@ __device__ __noinline__ int2 wrapped_pair(float t, int w, int clamp_mode) {
 
 // WHAT: 3 = velocity and colour in one pass; 1 = velocity only; 2 = colour only.  The colour field is not an
 // input of the projection, so the step advects it on a side branch of the graph, under the Jacobi passes.
-enum { kAdvectVelocity = 1, kAdvectColour = 2, kAdvectBoth = 3 };
+enum { kAdvectVelocity = 1, kAdvectColour = 2, kAdvectBoth = 3, kAdvectSecondKernel = 4 };
 
+// One voxel, any case (taps inside or outside the grid, either sampler addressing mode).
 template <int WHAT>
-__global__ void __launch_bounds__(512, 2)
-advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in,
-              uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
-              uint2* __restrict__ vel_out, Emitter em, int clamp_mode, StepState* __restrict__ state) {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 4 + threadIdx.y;
-    const int z = d.z_own0 + blockIdx.z * 4 + threadIdx.z;  // global plane
-    if (x >= d.nx || y >= d.ny || z >= d.z_own1) return;
-
-    const float dt = frame->dt;
-    const int parity = frame->parity;
-    const uint2* __restrict__ col_in = parity ? col0 : col1;  // colour[!parity] (Fluid.cpp:372)
-    uint2* __restrict__ col_out = parity ? col1 : col0;       // colour[parity]
-
+__device__ __forceinline__ void advect_voxel(const Domain& d, const AxisTables& tab, const float dt,
+                                             const uint2* __restrict__ vel_in, const uint2* __restrict__ col_in,
+                                             uint2* __restrict__ col_out, uint2* __restrict__ vel_out, const Emitter& em,
+                                             const int clamp_mode, StepState* __restrict__ state, const int x,
+                                             const int y, const int z) {
     const float px = __ldg(tab.pos[0] + x), py = __ldg(tab.pos[1] + y), pz = __ldg(tab.pos[2] + z);
     const float fnx = (float)d.nx, fny = (float)d.ny, fnz = (float)d.nz;
 
@@ -187,7 +180,57 @@ advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, c
     }
 }
 
-// what: 1 = velocity only, 2 = colour only, 3 = both (see the enum above)
+template <int WHAT>
+__global__ void __launch_bounds__(512, 2)
+advect_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in,
+              uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
+              uint2* __restrict__ vel_out, Emitter em, int clamp_mode, StepState* __restrict__ state) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int z = d.z_own0 + blockIdx.z * 4 + threadIdx.z;  // global plane
+    if (x >= d.nx || y >= d.ny || z >= d.z_own1) return;
+
+    const float dt = frame->dt;
+    const int parity = frame->parity;
+    const uint2* __restrict__ col_in = parity ? col0 : col1;  // colour[!parity] (Fluid.cpp:372)
+    uint2* __restrict__ col_out = parity ? col1 : col0;       // colour[parity]
+    advect_voxel<WHAT>(d, tab, dt, vel_in, col_in, col_out, vel_out, em, clamp_mode, state, x, y, z);
+}
+
+// Second kernel (experimental, FXB_ADVECT=2): voxels whose taps all lie inside the grid — the bulk of every grid —
+// take the leaner interior path of advect_body.cuh (row pointers, all loads in flight, no convert of velocity .w,
+// colour-free shortcut); the shell of voxels whose back-trace reaches a face runs the code above, out of line.
+template <int WHAT>
+__device__ __noinline__ void advect_voxel_cold(const Domain& d, const AxisTables& tab, const float dt,
+                                               const uint2* __restrict__ vel_in, const uint2* __restrict__ col_in,
+                                               uint2* __restrict__ col_out, uint2* __restrict__ vel_out,
+                                               const Emitter& em, const int clamp_mode, StepState* __restrict__ state,
+                                               const int x, const int y, const int z) {
+    advect_voxel<WHAT>(d, tab, dt, vel_in, col_in, col_out, vel_out, em, clamp_mode, state, x, y, z);
+}
+
+__global__ void __launch_bounds__(512, 2)
+advect2_kernel(Domain d, AxisTables tab, const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in,
+               uint2* col0, uint2* col1, uint2* __restrict__ vel_out, Emitter em, int clamp_mode,
+               StepState* __restrict__ state) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int z = d.z_own0 + blockIdx.z * 4 + threadIdx.z;  // global plane
+    if (x >= d.nx || y >= d.ny || z >= d.z_own1) return;
+    const float dt = frame->dt;
+    const int parity = frame->parity;
+    const uint2* __restrict__ col_in = parity ? col0 : col1;  // colour[!parity] (Fluid.cpp:372)
+    uint2* __restrict__ col_out = parity ? col1 : col0;       // colour[parity]
+    AdvectGeom g;
+    g.nx = d.nx; g.ny = d.ny; g.nz = d.nz; g.z_first = d.z_first; g.nz_alloc = d.nz_alloc;
+    g.pos[0] = tab.pos[0]; g.pos[1] = tab.pos[1]; g.pos[2] = tab.pos[2];
+    g.ex0 = em.x0; g.ey0 = em.y0; g.ez0 = em.z0; g.ex1 = em.x1; g.ey1 = em.y1; g.ez1 = em.z1;
+    g.basis = em.basis;
+    if (advect_interior_voxel(g, dt, vel_in, col_in, vel_out, col_out, x, y, z)) return;
+    advect_voxel_cold<kAdvectBoth>(d, tab, dt, vel_in, col_in, col_out, vel_out, em, clamp_mode, state, x, y, z);
+}
+
+// what: 1 = velocity only, 2 = colour only, 3 = both, 3 | 4 = both with the second kernel (see the enum above)
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
                    void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int what,
                    cudaStream_t stream) {
@@ -195,9 +238,11 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
     const dim3 grid((d.nx + 31) / 32, (d.ny + 3) / 4, (d.z_own1 - d.z_own0 + 3) / 4);
     auto* v = (const uint2*)vel_in;
     auto *c0 = (uint2*)col[0], *c1 = (uint2*)col[1], *vo = (uint2*)vel_out;
-    if (what == kAdvectVelocity)
+    if (what == (kAdvectBoth | kAdvectSecondKernel) && d.nz > 1)
+        advect2_kernel<<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
+    else if ((what & 3) == kAdvectVelocity)
         advect_kernel<kAdvectVelocity><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
-    else if (what == kAdvectColour)
+    else if ((what & 3) == kAdvectColour)
         advect_kernel<kAdvectColour><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);
     else
         advect_kernel<kAdvectBoth><<<grid, block, 0, stream>>>(d, tab, frame, v, c0, c1, vo, em, clamp_mode, state);

@@ -88,6 +88,7 @@ struct fxb_sim {
     // 0..tail_mains-1 interleaved with tail launches (jacobi_tail.cu), then tail launches only.
     bool tail = false;
     int tail_mains = 5;
+    bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
 
@@ -219,7 +220,7 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
             }
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
             fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
-                               s->d_state, 3, st);
+                               s->d_state, s->advect2 ? 3 | 4 : 3, st);
             launches = 1;
             break;
         case PH_DIVERGENCE:
@@ -518,6 +519,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
     if (getenv("FXB_OVERLAP_COLOUR")) s->overlap_colour = true;
+    if (const char* v = getenv("FXB_ADVECT")) s->advect2 = atoi(v) == 2;
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess)
         return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));

@@ -125,3 +125,38 @@ def test_tail_same_bits_as_default_schedule(oracle_mod):
         assert np.array_equal(a.get_field(fld), b.get_field(fld)), fld
     assert b.tail_stats()["tail_launches_last_step"] > 0
     a.close(); b.close()
+
+
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="the second advection kernel has not run on a GPU yet: FXB_TEST_EXPERIMENTAL=1 enables the test")
+@pytest.mark.parametrize("n,mode", [((64, 64, 64), 0), ((50, 50, 30), 0), ((48, 48, 48), 1), ((128, 128, 40), 0)])
+def test_second_advection_kernel(oracle_mod, n, mode):
+    """FXB_ADVECT=2 (advect_body.cuh, emulated on the CPU by tests/test_advect_emu.py) against the oracle."""
+    import fluidx12_b200 as fx
+    old = os.environ.get("FXB_ADVECT")
+    os.environ["FXB_ADVECT"] = "2"
+    try:
+        f = fx.Fluid()
+        assert f.Init(gridSize=n, address_mode=mode), f.last_error
+    finally:
+        if old is None:
+            os.environ.pop("FXB_ADVECT", None)
+        else:
+            os.environ["FXB_ADVECT"] = old
+    o = oracle_mod.FluidOracle(*n, address_mode=mode)
+    vel, col, p = smooth_state(*n, seed=21, umax=2.0)
+    for gf, of, a in ((fx.FIELD_VELOCITY, oracle_mod.FIELD_VEL, vel), (fx.FIELD_COLOR, oracle_mod.FIELD_COLOR, col),
+                      (fx.FIELD_PRESSURE, oracle_mod.FIELD_PRESSURE, p)):
+        f.set_field(gf, a)
+        o.set_field(of, a)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(10):
+        f.step(dt)
+        o.step(dt)
+    for name, gf, of in (("velocity", fx.FIELD_VELOCITY, oracle_mod.FIELD_VEL), ("colour", fx.FIELD_COLOR, oracle_mod.FIELD_COLOR),
+                         ("pressure", fx.FIELD_PRESSURE, oracle_mod.FIELD_PRESSURE)):
+        a, b = f.get_field(gf), o.get_field(of)
+        if name == "velocity":
+            a, b = a[..., :3], b[..., :3]
+        assert np.array_equal(a, b), (name, int((a != b).sum()))
+    f.close()
