@@ -87,7 +87,7 @@ struct fxb_sim {
     // Dynamic schedule (FXB_TAIL=1, single GPU; experimental until measured on B200 — DESIGN.md §5): bulk passes
     // 0..tail_mains-1 interleaved with tail launches (jacobi_tail.cu), then tail launches only.
     bool tail = false;
-    int tail_mains = 5;
+    int tail_mains = 8;
     bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
@@ -562,7 +562,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (e != cudaSuccess)
                 return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
             s->jac.dynamic = true;
-            s->jac.tail_threshold = 8192;
+            s->jac.tail_threshold = 1024;  // bricks; above it the z-marching bulk kernel is the better tool (estimate)
             s->jac.tail_grid = s->jac.num_sms * 8;
             if (const char* v = getenv("FXB_TAIL_THRESHOLD")) s->jac.tail_threshold = atoi(v);
             if (const char* v = getenv("FXB_TAIL_GRID")) s->jac.tail_grid = std::max(1, atoi(v));
