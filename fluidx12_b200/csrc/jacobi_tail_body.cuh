@@ -387,9 +387,9 @@ FXT_FN float tail_cell(float c, float l, float r, float u, float d, float f, flo
     acc = b + acc;
     const float xn = acc * kTailInv6;
     const float diff = FXT_FMA(acc, kTailInv6, -c);
-    if (!(act & bit)) return c;
-    if (fabsf(diff) < eps) act &= ~bit;
-    return xn;
+    const bool is_active = (act & bit) != 0u;
+    act &= (is_active && fabsf(diff) < eps) ? ~bit : ~0u;  // branch-free: selects, not jumps
+    return is_active ? xn : c;
 }
 
 // ---- phase A of sweep s (1-based): new values of the column into registers (reads shared memory only) ------------

@@ -126,6 +126,7 @@ def main():
     timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
                                           ("tail_grid592", {"FXB_TAIL_GRID": 592}),
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1}),
+                                          ("tail_thr8192_m5", {"FXB_TAIL_THRESHOLD": 8192, "FXB_TAIL_MAINS": 5}),
                                           ("tail_cpasync", {"FXB_TAIL_CPASYNC": 1}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
                                           ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
