@@ -568,6 +568,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (const char* v = getenv("FXB_TAIL_GRID")) s->jac.tail_grid = std::max(1, atoi(v));
             if (const char* v = getenv("FXB_TAIL_MAINS")) s->tail_mains = std::max(1, atoi(v));
             if (const char* v = getenv("FXB_TAIL_SPARSE_CAP")) s->jac.tail_sparse_cap = atoi(v);
+            if (const char* v = getenv("FXB_TAIL_DENSE")) s->jac.tail_dense_mode = atoi(v);
             if (const char* v = getenv("FXB_TAIL_CPASYNC")) s->jac.tail_cp_async = atoi(v) != 0;
             s->tail = true;
         }

@@ -140,6 +140,7 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
     L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = TailS::TT;
     L.P.sparse_cap = J.tail_sparse_cap < 0 || J.tail_sparse_cap > TailS::kListCap ? TailS::kListCap : J.tail_sparse_cap;
     L.P.cp_async = J.tail_cp_async;
+    L.P.dense_mode = J.tail_dense_mode == 2 ? 2 : 1;
     L.iters = iters;
     L.threshold = threshold;
     L.run_all = run_all ? 1 : 0;

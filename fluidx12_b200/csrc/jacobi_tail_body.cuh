@@ -138,6 +138,11 @@ struct TailShape {
     // stages the right-hand side of the whole window
     static constexpr int kListCap = (kRhsFloats * 4 / 12) / 32 * 32;
     static constexpr int kScanWords = kThreads + kThreads / 32;
+    // second dense path: the quads that can be relaxed at all (window planes 1..LZ-2, rows 1..LY-2), a fixed share per
+    // thread; their new values go to a side array that takes the place of the staged right-hand side
+    static constexpr int kQuads = (LZ - 2) * (LY - 2) * LXQ;
+    static constexpr int kQuadsPerThread = (kQuads + kThreads - 1) / kThreads;
+    static_assert(kQuads * 4 <= kRhsFloats, "side array of the second dense path");
     static_assert(kPFloats <= (1 << 14), "list entries keep the window index in 14 bits");
     static_assert(kNibBytes % 4 == 0, "flag bytes are cleared with 32-bit atomics");
     static constexpr size_t kBytes =
@@ -167,6 +172,7 @@ struct TailParams {
     int levels;          // sweeps to apply (<= TT)
     int sparse_cap;      // windows with at most this many relaxable active cells take the sparse path (<= kListCap)
     int cp_async;        // 1: the sparse path stages its window with cp.async; 0: through registers
+    int dense_mode;      // crowded windows: 1 = register z-columns, 2 = two-phase update of all quads (side array)
 };
 
 // Shared-memory view.
@@ -209,6 +215,7 @@ struct TailThread {
     bool used;          // owns a column at all
     bool in_xy;         // column lies inside the grid
     bool own_xy;        // column belongs to the output region
+    Quad rq[S::kQuadsPerThread];  // second dense path: right-hand sides of the thread's quads (loaded once per item)
     int nlist;          // active cells of the column that can be relaxed (sparse path: its list entries)
     unsigned okx;       // 0x11111111 * (4-bit mask of the column's cells that can be relaxed as far as x and y go)
 };
@@ -492,7 +499,7 @@ FXT_FN void tail_sparse_scan(int tid, const TailShared<S>& sh) {
 // ---- sparse phase 2: window values -> shared memory, flags -> nibble array, active cells -> list -------------------
 template <class S>
 FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
-                              const TailParams& P, const float* __restrict__ p_in) {
+                              const TailParams& P, const float* __restrict__ p_in, const bool with_list = true) {
     if (!t.used) return;
     if (P.cp_async) {
         // global -> shared without passing through registers: all planes of the column are in flight at once
@@ -518,7 +525,7 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
     }
 #pragma unroll
     for (int z = 0; z < S::LZ; ++z) sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
-    if (t.nlist == 0) {
+    if (t.nlist == 0 || !with_list) {
         if (P.cp_async) FXT_CP_ASYNC_WAIT();
         return;
     }
@@ -658,6 +665,107 @@ FXT_FN void tail_sparse_store(TailThread<S>& t, const TailShared<S>& sh, const T
     }
 }
 
+// =====================================================================================================================
+// Second dense path (crowded windows): every thread relaxes a fixed share of the window's quads, new values go to a
+// side array and are committed after a barrier — no register-resident columns, so no spills, and the same two-phase
+// structure as the sparse path.  The window and the flag nibbles are staged by tail_sparse_build (without a list).
+// =====================================================================================================================
+
+// quad number q -> window coordinates (planes 1..LZ-2, rows 1..LY-2, every quad of a row)
+template <class S>
+FXT_FN void tail_quad_coords(int q, int& z, int& y, int& qx) {
+    z = 1 + q / ((S::LY - 2) * S::LXQ);
+    const int r = q - (z - 1) * ((S::LY - 2) * S::LXQ);
+    y = 1 + r / S::LXQ;
+    qx = r - (y - 1) * S::LXQ;
+}
+
+// ---- right-hand sides of the thread's quads -> registers (all loads in flight; quads outside the grid read rhs[0..3]) --
+template <class S>
+FXT_FN void tail_dense2_load_rhs(int tid, TailThread<S>& t, const TailItem<S>& it, const TailParams& P,
+                                 const float* __restrict__ rhs) {
+#pragma unroll
+    for (int k = 0; k < S::kQuadsPerThread; ++k) {
+        const int q = tid + k * S::kThreads;
+        int z, y, qx;
+        tail_quad_coords<S>(q < S::kQuads ? q : 0, z, y, qx);
+        const int gx = it.wx + 4 * qx, gy = it.wy + y;
+        const bool in = q < S::kQuads && gx >= 0 && gx < P.nx && gy >= 0 && gy < P.ny && z >= it.zvl && z < it.zvh;
+        t.rq[k] = *reinterpret_cast<const Quad*>(in ? rhs + ((size_t)(it.wz + z) * P.ny + gy) * P.nx + gx : rhs);
+    }
+}
+
+// Is quad (z, y) relaxed in sweep s?  (the rows and planes that are still valid inputs, as in tail_phase_relax)
+template <class S>
+FXT_FN bool tail_dense2_in_range(const TailItem<S>& it, int z, int y, int s) {
+    const int yc0 = it.ylo_face ? it.yvl : it.yvl + s, yc1 = it.yhi_face ? it.yvh : it.yvh - s;
+    const int zc0 = it.zlo_face ? it.zvl : it.zvl + s, zc1 = it.zhi_face ? it.zvh : it.zvh - s;
+    return y >= yc0 && y < yc1 && z >= zc0 && z < zc1;
+}
+
+// ---- phase A of sweep s: new values of the thread's quads -> side array; new flags -> high nibble of the flag byte ---
+template <class S>
+FXT_FN void tail_dense2_relax(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
+                              const TailParams& P, int s) {
+    const float eps = P.early_exit ? kTailEps : -1.0f;
+    Quad* side = reinterpret_cast<Quad*>(sh.rhs);
+#pragma unroll
+    for (int k = 0; k < S::kQuadsPerThread; ++k) {
+        const int q = tid + k * S::kThreads;
+        if (q >= S::kQuads) continue;
+        int z, y, qx;
+        tail_quad_coords<S>(q, z, y, qx);
+        const int nb = (z * S::LY + y) * S::LXQ + qx;
+        unsigned a = sh.nib[nb] & 0xFu;
+        if (a == 0u || !tail_dense2_in_range<S>(it, z, y, s)) continue;
+        const int gx = it.wx + 4 * qx, gy = it.wy + y, gz = it.wz + z;
+        const float* pl = sh.p + z * S::kPlane;
+        const int col = y * S::LX + 4 * qx;
+        const Quad c = *reinterpret_cast<const Quad*>(pl + col);
+        // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); at a window edge that is not a face the cell is
+        // its own neighbour, which only spoils cells that are no longer valid anyway
+        const Quad u = *reinterpret_cast<const Quad*>(pl + (gy == 0 ? col : col - S::LX));
+        const Quad d = *reinterpret_cast<const Quad*>(pl + (gy == P.ny - 1 ? col : col + S::LX));
+        const Quad f = *reinterpret_cast<const Quad*>(gz == P.z_face_lo ? pl + col : pl - S::kPlane + col);
+        const Quad b = *reinterpret_cast<const Quad*>(gz == P.z_face_hi - 1 ? pl + col : pl + S::kPlane + col);
+        const float left = (qx == 0 || gx == 0) ? c.x : pl[col - 1];
+        const float right = (qx == S::LXQ - 1 || gx + 4 == P.nx) ? c.w : pl[col + 4];
+        const Quad r = t.rq[k];
+        Quad n;
+        n.x = tail_cell(c.x, left, c.y, u.x, d.x, f.x, b.x, r.x, 1u, eps, a);
+        n.y = tail_cell(c.y, c.x, c.z, u.y, d.y, f.y, b.y, r.y, 2u, eps, a);
+        n.z = tail_cell(c.z, c.y, c.w, u.z, d.z, f.z, b.z, r.z, 4u, eps, a);
+        n.w = tail_cell(c.w, c.z, right, u.w, d.w, f.w, b.w, r.w, 8u, eps, a);
+        side[q] = n;
+        sh.nib[nb] = (unsigned char)((sh.nib[nb] & 0xFu) | (a << 4));  // old flags stay in the low nibble until the commit
+    }
+}
+
+// ---- phase B of sweep s: commit the quads relaxed in phase A, count the own cells that are still active -------------
+template <class S>
+FXT_FN void tail_dense2_commit(int tid, const TailShared<S>& sh, const TailItem<S>& it, int s) {
+    const Quad* side = reinterpret_cast<const Quad*>(sh.rhs);
+    unsigned live = 0;
+#pragma unroll
+    for (int k = 0; k < S::kQuadsPerThread; ++k) {
+        const int q = tid + k * S::kThreads;
+        if (q >= S::kQuads) continue;
+        int z, y, qx;
+        tail_quad_coords<S>(q, z, y, qx);
+        const int nb = (z * S::LY + y) * S::LXQ + qx;
+        const unsigned byte = sh.nib[nb];
+        const bool own = qx >= 1 && 4 * (qx - 1) < it.ex && y >= S::TT && y - S::TT < it.ey && z >= S::TT && z - S::TT < it.ez;
+        if ((byte & 0xFu) != 0u && tail_dense2_in_range<S>(it, z, y, s)) {  // the same predicate as in phase A
+            *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + y * S::LX + 4 * qx) = side[q];
+            sh.nib[nb] = (unsigned char)(byte >> 4);
+            if (own) live += FXT_POPC(byte >> 4);
+        } else if (own) {
+            live += FXT_POPC(byte & 0xFu);
+        }
+    }
+    if (live) FXT_ATOMIC_ADD_U32(&sh.ctrl[s], live);
+}
+
 // Work lists of one launch (same lists as jacobi_fused.cu: bricks that still hold an active cell, and bricks that
 // froze in the previous kernel and need one copy into the other pressure buffer).
 struct TailWork {
@@ -742,6 +850,20 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                 FXT_PHASE(tail_sparse_relax<S>(tid, sh, it, P, n_list, s));
                 FXT_SYNC();
                 FXT_PHASE(tail_sparse_commit<S>(tid, sh, n_list, s));
+                FXT_SYNC();
+            }
+            FXT_MARK(5);
+            FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
+            FXT_MARK(6);
+        } else if (P.dense_mode == 2) {  // crowded window: two-phase update of all quads
+            path = 2;
+            FXT_PHASE(tail_sparse_build<S>(tid, t, sh, it, P, p_in, false); tail_dense2_load_rhs<S>(tid, t, it, P, rhs));
+            FXT_SYNC();
+            FXT_MARK(3);
+            for (int s = 1; s <= P.levels; ++s) {
+                FXT_PHASE(tail_dense2_relax<S>(tid, t, sh, it, P, s));
+                FXT_SYNC();
+                FXT_PHASE(tail_dense2_commit<S>(tid, sh, it, s));
                 FXT_SYNC();
             }
             FXT_MARK(5);

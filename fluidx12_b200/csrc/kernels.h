@@ -51,6 +51,7 @@ struct FusedJacobi {
     int tail_grid = 0;                            // CTAs of a tail launch
     int tail_cp_async = 0;                        // 1 (FXB_TAIL_CPASYNC=1): the sparse path stages its window with cp.async;
                                                   // not yet run on a GPU, hence off by default
+    int tail_dense_mode = 1;                      // crowded windows: 1 = register z-columns (ran on B200), 2 = two-phase quads
     int tail_sparse_cap = -1;                     // active cells per window up to which the sparse path is taken (-1: capacity)
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer

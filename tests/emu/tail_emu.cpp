@@ -39,7 +39,7 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
 extern "C" {
 
 // geom = {nx, ny, nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1, bx, by, bz}
-// flags = {first, early_exit, levels, tt, sparse_cap (-1: the compiled capacity), cp_async}
+// flags = {first, early_exit, levels, tt, sparse_cap (-1: the compiled capacity), cp_async, dense_mode}
 // Returns the number of work items processed, or -1 for an unsupported shape.
 int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float* p_out, const float* rhs,
                     const unsigned char* m_in, unsigned char* m_out, const int* relax_in, int n_relax,
@@ -58,6 +58,7 @@ int tail_emu_launch(const int* geom, const int* flags, const float* p_in, float*
     const int cap = tt == 4 ? S4::kListCap : S2::kListCap;
     P.sparse_cap = flags[4] < 0 || flags[4] > cap ? cap : flags[4];
     P.cp_async = flags[5];
+    P.dense_mode = flags[6];
     if (P.bx % S4::OX != 0 || P.by > S4::OY || P.bz > S4::OZ || P.nx % 8 != 0 || P.levels > tt) return -1;
     P.nsub = P.bx / S4::OX;
     TailWork W;

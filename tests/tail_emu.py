@@ -59,7 +59,7 @@ def paths():
 
 
 def launch(g: BrickGrid, p_in, p_out, rhs, m_in, m_out, relax_in, copy_in, brick_state, hist_s0, first, early_exit=True,
-           levels=4, tt=4, sparse_cap=-1, cp_async=1, slab=None):
+           levels=4, tt=4, sparse_cap=-1, cp_async=1, slab=None, dense_mode=1):
     """One emulated launch.  Returns (relax_out, copy_out).  p_out / m_out / brick_state / hist_s0 are updated in place.
 
     slab = (nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1) in local plane indices for a z-slab window (the arrays then
@@ -67,7 +67,7 @@ def launch(g: BrickGrid, p_in, p_out, rhs, m_in, m_out, relax_in, copy_in, brick
     nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1 = slab if slab else (g.nz, 0, g.nz, 0, g.nz)
     assert p_in.shape[0] == nz_alloc and z_out1 - z_out0 == g.nz
     geom = np.array([g.nx, g.ny, nz_alloc, z_face_lo, z_face_hi, z_out0, z_out1, g.bx, g.by, g.bz], np.int32)
-    flags = np.array([int(first), int(early_exit), levels, tt, sparse_cap, cp_async], np.int32)
+    flags = np.array([int(first), int(early_exit), levels, tt, sparse_cap, cp_async, dense_mode], np.int32)
     relax_in = np.ascontiguousarray(relax_in, np.int32)
     copy_in = np.ascontiguousarray(copy_in, np.int32)
     relax_out, copy_out = np.full(g.n, -1, np.int32), np.full(g.n, -1, np.int32)

@@ -12,7 +12,7 @@ from tests.util import smooth_state
 
 
 def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True, sparse_cap=-1,
-                    cp_async=1):
+                    cp_async=1, dense_mode=1):
     """Whole pressure solve by emulated tail launches only (first launch: every brick, every cell active).
     Returns (p, s_exec, launches).  After every launch the output buffer must equal the oracle's state everywhere."""
     nz, ny, nx = s2.shape
@@ -31,7 +31,7 @@ def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=Tr
         src, dst = seq & 1, (seq + 1) & 1
         relax, copy_next = E.launch(g, p[src], p[dst], rhs, m[src], m[dst], relax, copy, brick_state, hist[done:],
                                     first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt,
-                                    sparse_cap=sparse_cap, cp_async=cp_async)
+                                    sparse_cap=sparse_cap, cp_async=cp_async, dense_mode=dense_mode)
         p_ref, act_ref, counts = oracle_mod.jacobi_sweeps_slab(s2, p_ref, act_ref, levels, nz, 0, 0, nz, early_exit)
         done += levels
         seq += 1
@@ -77,13 +77,15 @@ def thread_order(request):
 
 
 @pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
-@pytest.mark.parametrize("sparse_cap", [-1, 0, 300])
-def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, thread_order):
-    """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve."""
+@pytest.mark.parametrize("sparse_cap,dense_mode", [(-1, 1), (0, 1), (300, 1), (0, 2), (300, 2)])
+def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, dense_mode, thread_order):
+    """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve.
+    dense_mode 1: register z-columns; 2: two-phase update of all quads."""
     s2, p0 = developed_state(oracle_mod, n, steps)
     p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, 64, True)
     E.paths()
-    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), sparse_cap=sparse_cap)
+    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), sparse_cap=sparse_cap,
+                                             dense_mode=dense_mode)
     assert np.array_equal(p_got, p_want)
     assert s_got == s_want
     assert launches == -(-s_want // 4)
@@ -101,7 +103,7 @@ def test_tail_random_field_no_early_exit(oracle_mod, thread_order):
     rng = np.random.default_rng(5)
     s2 = (rng.integers(-2 ** 20, 2 ** 20, size=p0.shape) * 2.0 ** -24).astype(np.float32)
     p_want, _, _, _ = oracle_mod.jacobi(s2, p0, 10, False)
-    p_got, _, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), iters=10, early_exit=False)
+    p_got, _, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), iters=10, early_exit=False, dense_mode=2)
     assert launches == 3
     assert np.array_equal(p_got, p_want)
 

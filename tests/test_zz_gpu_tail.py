@@ -88,6 +88,14 @@ def test_tail_dense_path_only(oracle_mod):
     assert ts["tail_subblocks_dense"] == ts["tail_subblocks_relaxed"] > 0
 
 
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="the second dense path has not run on a GPU yet: FXB_TEST_EXPERIMENTAL=1 enables the test")
+def test_tail_second_dense_path(oracle_mod):
+    """FXB_TAIL_DENSE=2 with FXB_TAIL_SPARSE_CAP=0: every active window takes the two-phase all-quads path."""
+    _, ts = run_pair(oracle_mod, (64, 64, 40), 6, {"FXB_TAIL_SPARSE_CAP": 0, "FXB_TAIL_DENSE": 2})
+    assert ts["tail_subblocks_dense"] == ts["tail_subblocks_relaxed"] > 0
+
+
 def test_tail_takes_over_right_after_pass_zero(oracle_mod):
     launches, _ = run_pair(oracle_mod, (64, 64, 64), 8, {"FXB_TAIL_MAINS": 1}, inject_seed=11)
     assert launches > 0
