@@ -364,7 +364,9 @@ def run_ours(args):
                    "sweeps_per_step": round(sweeps, 2), "jacobi_passes_per_step": round(passes, 2),
                    "bytes_per_voxel_step": round(work_bytes / voxels, 2), "kernel_path": args.kernel_path,
                    "jacobi_fused": int(st1.jacobi_fused), "bricks_relaxed_per_step": round(proc / args.steps, 1),
-                   "bricks_copied_per_step": round(cop / args.steps, 1), "brick_cells": int(st1.brick_cells)},
+                   "bricks_copied_per_step": round(cop / args.steps, 1), "brick_cells": int(st1.brick_cells),
+                   # opt-in variants of the same bit-exact step that were switched on through the environment
+                   "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("FXB_")}},
         "step_roofline": {"bound": "hbm", "achieved": round(work_gbs, 1), "peak": peak * world, "unit": "GB/s",
                           "frac": round(work_gbs / (peak * world), 4), "peak_source": peak_src,
                           "definition": "(64 B x voxels + Jacobi bytes of the bricks actually relaxed/copied) / t_step",
