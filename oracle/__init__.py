@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY — imported by ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.  The product package
-``fluidx12_b200`` never imports this module.  Parity is unpinned (see the header of
-``fluid_oracle.cpp``): the reference ships no tests or golden vectors and cannot run here.
+``fluidx12_b200`` never imports this module.  Parity is pinned to the reference's shipped DXBC (interpreted:
+``tests/golden/dxbc_interp.py``, ``tests/test_dxbc_golden.py``) and unpinned for the D3D platform semantics
+(see the header of ``fluid_oracle.cpp``): the reference ships no tests or golden vectors and cannot run here.
 """
 from __future__ import annotations
 

@@ -4,10 +4,15 @@
 // tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it,
 // and only as the checker or as the reported CPU baseline.
 //
-// PARITY UNPINNED: the reference (Windows + D3D12 + closed XUSG.dll) ships no tests, golden
-// vectors or CPU path, and cannot be built or run here.  This file therefore *defines* the
-// deterministic semantics of the path from the HLSL source and from the operation order /
-// folded constants of the shipped DXBC blobs:
+// PARITY: PINNED TO THE SHIPPED BYTECODE, UNPINNED FOR THE PLATFORM.  The reference (Windows + D3D12 + closed
+// XUSG.dll) ships no tests, golden vectors or CPU path and cannot be built or run here.  What it does ship is the
+// fxc-compiled DXBC of its shaders; tests/golden/dxbc_interp.py executes those blobs (operation order, swizzles,
+// folded constants and control flow come from the bytecode) and tests/test_dxbc_golden.py requires this file to
+// reproduce the resulting vectors bit for bit (3D, 2D, MIRROR, CLAMP, paused frame, zero start).  What no file of the
+// reference defines — D3D's sampler and format conversions, exp2, and the thread interleaving of the racy
+// relaxation loop — is restated (decisions below) in the interpreter exactly as it is here, so those remain
+// unpinned.  This file states the deterministic semantics of the path from the HLSL source and the DXBC
+// (SURVEY.md Appendix A, B, D):
 //
 //   CSAdvect      FluidX12/Content/Shaders/CSAdvect.hlsl:41-79   (+ Simulation.hlsli:8-19,
 //                 Impulse.hlsli:8-18; sampler LINEAR_MIRROR Content/Fluid.cpp:452,
