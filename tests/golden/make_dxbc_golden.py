@@ -28,6 +28,8 @@ CASES = {
     "emitter3d_from_zero": ((16, 16, 16), None, 3, False, None),
     "smooth3d_clamp_pause": ((16, 16, 8), 77, 3, True, 1),
     "smooth2d": ((32, 32, 1), 5, 2, False, None),
+    "emitter3d_32_cubed": ((32, 32, 32), None, 8, False, None),
+    "emitter2d_from_zero": ((64, 64, 1), None, 6, False, None),
 }
 
 
