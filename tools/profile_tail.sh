@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 python tools/gpu_shot.py > gpurun_out/tail_shot.log 2>&1; cp gpurun_out/shot.jsonl gpurun_out/tail_shot.jsonl
 export FXB_TAIL=1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/tail_launches.csv \
-    -k regex:"jacobi_tail|jacobi_pass" -s 2100 -c 42 python tools/profile_step.py --grid 256 256 256 --steps 103 > /dev/null 2>&1
+    -k regex:"jacobi_tail|jacobi_pass" -s 2400 -c 48 python tools/profile_step.py --grid 256 256 256 --steps 103 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:jacobi_tail -s 1600 -c 1 -o gpurun_out/tail_first -f \
     python tools/profile_step.py --grid 256 256 256 --steps 101 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:jacobi_tail -s 1605 -c 1 -o gpurun_out/tail_mid -f \
