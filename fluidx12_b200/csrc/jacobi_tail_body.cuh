@@ -290,7 +290,8 @@ FXT_FN void tail_set_nib(unsigned (&fl)[2], int z, unsigned n) {
 // ---- phase 0: thread geometry, freeze flags of the column, "is anything in the own region still active" ----------
 template <class S>
 FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
-                             const TailParams& P, const unsigned char* __restrict__ m_in) {
+                             const TailParams& P, const unsigned char* __restrict__ m_in,
+                             const float* __restrict__ p_in) {
     t.used = tid < S::kUsed;
     t.qx = tid % S::LXQ;
     t.y = tid / S::LXQ;
@@ -301,6 +302,16 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
     t.fl[0] = t.fl[1] = 0u;
     t.own[0] = t.own[1] = 0u;
     t.dirty = 0u;
+    if (P.cp_async && t.used) {
+        // cp.async mode: the window is requested here, together with the flags, so that every path of the item
+        // (copy, sparse, dense) finds it in shared memory after ONE memory round trip; no register is involved
+#pragma unroll
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            FXT_CP_ASYNC_16(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx,
+                            in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in, in);
+        }
+    }
     const int nxb = P.nx >> 3;
     // All flag bytes of the column are requested before the first one is decoded (an in-order core would otherwise
     // pay one memory round trip per plane); planes outside the grid re-read byte 0 of the mask and are ignored.
@@ -333,11 +344,12 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
     t.nlist = nl;
     sh.scan[tid] = nl;
     if (nl) FXT_ATOMIC_ADD_U32(&sh.ctrl[S::kCtrlTotal], (unsigned)nl);
+    if (P.cp_async) FXT_CP_ASYNC_WAIT();  // the window has landed before the barrier that follows this phase
 }
 
 // ---- copy path: no active cell in the own region, so the output equals the input ---------------------------------
 template <class S>
-FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailParams& P,
+FXT_FN void tail_phase_copy(TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it, const TailParams& P,
                             const float* __restrict__ p_in, float* __restrict__ p_out,
                             unsigned char* __restrict__ m_out) {
     if (!t.own_xy) return;
@@ -346,7 +358,9 @@ FXT_FN void tail_phase_copy(TailThread<S>& t, const TailItem<S>& it, const TailP
 #pragma unroll
     for (int z = S::TT; z < S::TT + S::OZ; ++z) {
         const int zz = z - S::TT < it.ez ? z : S::TT;
-        q[z - S::TT] = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + zz) * P.ny + t.gy) * P.nx + t.gx);
+        q[z - S::TT] = P.cp_async  // cp.async mode: the window is already in shared memory
+                           ? *reinterpret_cast<const Quad*>(sh.p + zz * S::kPlane + t.y * S::LX + 4 * t.qx)
+                           : *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + zz) * P.ny + t.gy) * P.nx + t.gx);
     }
 #pragma unroll
     for (int z = S::TT; z < S::TT + S::OZ; ++z) {
@@ -365,6 +379,10 @@ FXT_FN void tail_phase_load(TailThread<S>& t, const TailShared<S>& sh, const Tai
     const Quad zero = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int z = 0; z < S::LZ; ++z) {
+        if (P.cp_async) {  // the flags phase has staged the window: only the register copy is missing
+            t.v[z] = *reinterpret_cast<const Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx);
+            continue;
+        }
         Quad q = zero;
         if (t.in_xy && z >= it.zvl && z < it.zvh)
             q = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
@@ -501,15 +519,7 @@ template <class S>
 FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
                               const TailParams& P, const float* __restrict__ p_in, const bool with_list = true) {
     if (!t.used) return;
-    if (P.cp_async) {
-        // global -> shared without passing through registers: all planes of the column are in flight at once
-#pragma unroll
-        for (int z = 0; z < S::LZ; ++z) {
-            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
-            FXT_CP_ASYNC_16(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx,
-                            in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in, in);
-        }
-    } else {
+    if (!P.cp_async) {  // (in cp.async mode the flags phase has staged the window already)
         const Quad zero = {0.f, 0.f, 0.f, 0.f};
         Quad q[S::LZ];  // cells outside the grid read p_in[0..3] and store zero
 #pragma unroll
@@ -525,10 +535,7 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
     }
 #pragma unroll
     for (int z = 0; z < S::LZ; ++z) sh.nib[(z * S::LY + t.y) * S::LXQ + t.qx] = (unsigned char)tail_nib(t.fl, z);
-    if (t.nlist == 0 || !with_list) {
-        if (P.cp_async) FXT_CP_ASYNC_WAIT();
-        return;
-    }
+    if (t.nlist == 0 || !with_list) return;
     int at = 0;  // entries of the threads before this one
     for (int w = 0; w < (tid >> 5); ++w) at += sh.scan[S::kThreads + w];
     for (int l = tid & ~31; l < tid; ++l) at += sh.scan[l];
@@ -545,7 +552,6 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
                             (own ? kTailOwn : 0u);
         }
     }
-    if (P.cp_async) FXT_CP_ASYNC_WAIT();  // the copies land before the barrier that follows this phase
 }
 
 // ---- sparse phase 3: right-hand sides of the listed cells -> side array (eight independent loads in flight) --------
@@ -828,12 +834,12 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
     FXT_SYNC();
     FXT_MARK(0);
     if (it.ex > 0) {
-        FXT_PHASE(tail_phase_flags<S>(tid, t, sh, it, P, m_in));
+        FXT_PHASE(tail_phase_flags<S>(tid, t, sh, it, P, m_in, p_in));
         FXT_SYNC();
         FXT_MARK(1);
         const int n_list = (int)sh.ctrl[S::kCtrlTotal];
         if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
-            FXT_PHASE(tail_phase_copy<S>(t, it, P, p_in, p_out, m_out));
+            FXT_PHASE(tail_phase_copy<S>(t, sh, it, P, p_in, p_out, m_out));
             FXT_MARK(6);
         } else if (n_list <= P.sparse_cap) {  // relax a compacted list of the active cells
             path = 1;

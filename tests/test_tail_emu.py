@@ -77,15 +77,16 @@ def thread_order(request):
 
 
 @pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
+@pytest.mark.parametrize("cp_async", [0, 1])
 @pytest.mark.parametrize("sparse_cap,dense_mode", [(-1, 1), (0, 1), (300, 1), (0, 2), (300, 2)])
-def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, dense_mode, thread_order):
+def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, dense_mode, thread_order, cp_async):
     """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve.
     dense_mode 1: register z-columns; 2: two-phase update of all quads."""
     s2, p0 = developed_state(oracle_mod, n, steps)
     p_want, s_want, hist_want, _ = oracle_mod.jacobi(s2, p0, 64, True)
     E.paths()
     p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), sparse_cap=sparse_cap,
-                                             dense_mode=dense_mode)
+                                             dense_mode=dense_mode, cp_async=cp_async)
     assert np.array_equal(p_got, p_want)
     assert s_got == s_want
     assert launches == -(-s_want // 4)
