@@ -257,16 +257,19 @@ class Texture:
 
 
 class Machine:
-    def __init__(self, blob: bytes, grid, cb0, srv, uav, clamp=False):
+    def __init__(self, blob: bytes, grid, cb0, srv, uav, clamp=False, threads=None):
         """grid = (nx, ny, nz): one thread per voxel.  cb0: 4 raw uint32 words of cb[0][0].  srv / uav: dicts slot ->
-        Texture (UAV contents are modified in place)."""
+        Texture (UAV contents are modified in place).  threads: optional [n, 3] array of the (x, y, z) thread ids to run
+        (default: the whole dispatch) — running thread groups one after the other models a GPU that does NOT execute
+        the relaxation loop in lock-step (tools/dxbc_schedule_sensitivity.py)."""
         self.decls, self.code = decode(blob)
         nx, ny, nz = grid
         gx, gy, gz = self.decls["group"]
         assert nx % gx == 0 and ny % gy == 0 and nz % gz == 0, "fixtures use grids the dispatch covers exactly"
         z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-        self.n = nx * ny * nz
-        self.tid = np.stack([x.reshape(-1), y.reshape(-1), z.reshape(-1), np.zeros(self.n, np.int64)], 1).astype(U32)
+        ids = np.stack([x.reshape(-1), y.reshape(-1), z.reshape(-1)], 1) if threads is None else np.asarray(threads)
+        self.n = len(ids)
+        self.tid = np.concatenate([ids, np.zeros((self.n, 1), ids.dtype)], 1).astype(U32)
         self.r = np.zeros((self.decls["temps"], self.n, 4), U32)
         self.cb0 = np.asarray(cb0, U32)
         self.srv, self.uav, self.clamp = srv, uav, clamp
