@@ -132,15 +132,20 @@ __global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepS
 }
 
 // Dynamic schedule (jacobi_tail.cu): the relax kernels counted their own ping-pong flips in StepState::seq.
-__global__ void finish_solve_dynamic_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state,
-                                            int iters) {
-    if (threadIdx.x != 0) return;
-    int s = 0;
-    if (0.0f < frame->dt && iters > 0) {
-        s = 1;
-        while (s < iters && state->active_after[s - 1] != 0ull) ++s;
-    }
-    const int flips = 0.0f < frame->dt ? state->seq : 0;
+__global__ void __launch_bounds__(128) finish_solve_dynamic_kernel(const FrameParams* __restrict__ frame,
+                                                                   StepState* __restrict__ state, int iters) {
+    // s_exec = 1 + the number of leading non-zero entries of active_after[0 .. iters-2]; one thread per entry instead
+    // of finish_solve_kernel's serial walk (a dependent global load per sweep, ~10 us per step)
+    __shared__ int first_zero;
+    const int k = threadIdx.x;
+    if (k == 0) first_zero = 127;
+    __syncthreads();
+    if (k >= iters - 1 || state->active_after[k] == 0ull) atomicMin(&first_zero, k);
+    __syncthreads();
+    if (k != 0) return;
+    const bool live = 0.0f < frame->dt && iters > 0;
+    const int s = live ? min(first_zero + 1, iters) : 0;
+    const int flips = live ? state->seq : 0;
     state->s_exec = s;
     state->passes = flips;
     state->p_cur = (state->p_cur + flips) & 1;
@@ -218,7 +223,7 @@ void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, 
 }
 
 void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream) {
-    finish_solve_dynamic_kernel<<<1, 32, 0, stream>>>(frame, state, iters);
+    finish_solve_dynamic_kernel<<<1, 128, 0, stream>>>(frame, state, iters);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,
