@@ -39,7 +39,12 @@ def _exchange(arr, faces, z_first):
         dst[...] = recv.numpy().view(arr.dtype).reshape(dst.shape)
 
 
-def _worker(rank, world, port, grid, steps, fuse_t, h_adv, group, out):
+def _faces(nz, rank, world, depth):
+    from fluidx12_b200.slab import _faces as faces
+    return faces(nz, rank, world, depth)
+
+
+def _worker(rank, world, port, grid, steps, fuse_t, h_adv, group, out, tail=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -67,7 +72,22 @@ def _worker(rank, world, port, grid, steps, fuse_t, h_adv, group, out):
         _exchange(s, plan.jacobi, zf)
         active = np.ones(s.shape, np.uint8)
         counts = np.zeros(npass * fuse_t, np.int64)
-        for k in range(npass):
+        if tail:
+            # dynamic schedule on slabs (csrc/fxb_api.cu): bulk pass 0 (T sweeps), then tail launches of 4 sweeps; one
+            # exchange before every launch, as deep as the launch's sweeps; the right-hand side once, 4 planes deep
+            _exchange(s, _faces(nz, rank, world, 4), zf)
+            done, launch = 0, 0
+            while done < iters:
+                n = min(fuse_t if launch == 0 else 4, iters - done)
+                depth = fuse_t if launch == 0 else 4
+                _exchange(p, _faces(nz, rank, world, depth), zf)
+                if launch:
+                    _exchange(active, _faces(nz, rank, world, depth), zf)
+                p, active, c = O.jacobi_sweeps_slab(s, p, active, n, nz, zf, own.start, own.stop)
+                counts[done:done + n] = c
+                done += n
+                launch += 1
+        for k in range(0 if tail else npass):
             if k % plan.group == 0:  # group*T planes every `group` passes; the window is relaxed whole in between
                 _exchange(p, plan.jacobi, zf)
                 if k:
@@ -109,6 +129,23 @@ def test_slab_decomposition_matches_single_domain(world, grid, fuse_t, h_adv, gr
     out = ctx.Queue()
     port = 29700 + world * 10 + fuse_t + 3 * group
     procs = [ctx.Process(target=_worker, args=(r, world, port, grid, 3, fuse_t, h_adv, group, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=300)
+        assert pr.exitcode == 0
+    assert out.get(timeout=10) is True
+
+
+@pytest.mark.parametrize("world,grid", [(2, (16, 16, 24)), (3, (16, 16, 36))])
+def test_slab_decomposition_with_the_dynamic_schedule(world, grid):
+    """The exchange plan of the dynamic pressure-solve schedule on slabs (bulk pass 0, then launches of 4 sweeps with
+    4-plane halos: 17 exchanges per step instead of 33) at oracle level over gloo."""
+    import oracle
+    oracle.build()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29790 + world, grid, 3, 2, 5, 1, out, True)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
