@@ -37,7 +37,7 @@ struct TailLaunch {
     int* brick_state;
 };
 
-template <class S>
+template <class S, int DENSE>
 __global__ void __launch_bounds__(S::kThreads, 2)
 jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                    const float* __restrict__ rhs, unsigned char* m0, unsigned char* m1,
@@ -81,7 +81,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
             continue;
         }
         const int r = item - n_copy;
-        const int path = tail_run_item<S>(tid, sh, P, W, W.relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out,
+        const int path = tail_run_item<S, DENSE>(tid, sh, P, W, W.relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out,
                                           state->active_after + s0, state->active_after + 64);
         if (tid == 0 && path != 0) {
             ++relaxed;
@@ -122,8 +122,11 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
                                int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(jacobi_tail_kernel<TailS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(jacobi_tail_kernel<TailS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)TailS::kBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(jacobi_tail_kernel<TailS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)TailS::kBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -149,8 +152,12 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
     const int np = FusedJacobi::kMaxPasses + 1;
     L.relax_count = J.work_count; L.copy_count = J.work_count + np;
     L.brick_state = J.brick_state;
-    jacobi_tail_kernel<TailS><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
-        frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+    if (L.P.dense_mode == 2)
+        jacobi_tail_kernel<TailS, 2><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
+            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+    else
+        jacobi_tail_kernel<TailS, 1><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
+            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
     return cudaGetLastError();
 }
 

@@ -819,7 +819,9 @@ struct TailEmu {
 
 // ---- one work item of the relax list: sub-block `sub` of `brick`, all phases and barriers ---------------------------
 // Returns the path taken: 0 = nothing active in the own region (copy) or empty sub-block, 1 = sparse, 2 = dense.
-template <class S>
+// DENSE: which dense path is compiled in — 1 or 2 — or 0 for both with P.dense_mode choosing (the emulation; the
+// CUDA build instantiates one kernel per dense path so that neither carries the other's register pressure).
+template <class S, int DENSE = 0>
 FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& P, const TailWork& W, const int brick,
                          const int sub, const float* __restrict__ p_in, float* __restrict__ p_out,
                          const float* __restrict__ rhs, const unsigned char* __restrict__ m_in,
@@ -861,7 +863,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_MARK(5);
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
             FXT_MARK(6);
-        } else if (P.dense_mode == 2) {  // crowded window: two-phase update of all quads
+        } else if (DENSE == 2 || (DENSE == 0 && P.dense_mode == 2)) {  // crowded window: two-phase update of all quads
             path = 2;
             FXT_PHASE(tail_sparse_build<S>(tid, t, sh, it, P, p_in, false); tail_dense2_load_rhs<S>(tid, t, it, P, rhs));
             FXT_SYNC();
