@@ -89,6 +89,7 @@ struct fxb_sim {
     bool tail = false;
     int tail_mains = 8;
     bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
+    bool pass0_tail = false;  // FXB_PASS0=2 (with FXB_TAIL=1, T = 2): pass 0 by the block-resident kernel (experimental)
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
 
@@ -256,7 +257,9 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                                                      {s->jac.mask[seq & 1], s->plane_voxels() / 8, depth}};
                         s->comm.exchange(d, f, seq == 0 ? 1 : 2, st);
                     }
-                    if (kind >= 0)
+                    if (kind == 0 && s->pass0_tail && s->fuse_t == 2)
+                        fxb::launch_jacobi_pass0_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit, st);
+                    else if (kind >= 0)
                         fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, kind, iters, s->cfg.early_exit,
                                                       s->multi(), 0, 0, st);
                     else
@@ -569,6 +572,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (const char* v = getenv("FXB_TAIL_MAINS")) s->tail_mains = std::max(1, atoi(v));
             if (const char* v = getenv("FXB_TAIL_SPARSE_CAP")) s->jac.tail_sparse_cap = atoi(v);
             if (const char* v = getenv("FXB_TAIL_DENSE")) s->jac.tail_dense_mode = atoi(v);
+            if (const char* v = getenv("FXB_PASS0")) s->pass0_tail = atoi(v) == 2;
             if (const char* v = getenv("FXB_TAIL_CPASYNC")) s->jac.tail_cp_async = atoi(v) != 0;
             s->tail = true;
         }

@@ -24,12 +24,17 @@ namespace fxb {
 namespace {
 
 using TailS = TailShape<4, 10, 12, 8>;  // 4 sweeps, sub-block 40 x 12 x 8, window 48 x 20 x 16, 256 threads
+// Experimental pass-0 kernel (FXB_PASS0=2): the same body with 2 sweeps, every cell active and no flags to read; every
+// window takes the second dense path.  Per quad update it executes about a third of the instructions of the z-marching
+// bulk kernel (estimate from the SASS; unmeasured), at the price of loading each window with its halo (2.4x the cells).
+using TailP0 = TailShape<2, 10, 12, 8>;  // window 48 x 16 x 12, 192 threads
 
 struct TailLaunch {
     TailParams P;      // levels / first are filled in on the device
     int iters;         // ITER
     int threshold;     // run only when at most this many bricks are listed; < 0: always
     int run_all;       // multi-GPU: never end the solve on this rank's own freeze counters
+    int first;         // 1: this launch is pass 0 of the frame (no lists, no flags: every brick, every cell active)
     int nbricks;
     int* list[2];      // [2 * bricks] per parity of seq: bricks to relax, then bricks to copy (jacobi_fused.cu)
     int* relax_count;  // [seq]
@@ -38,21 +43,25 @@ struct TailLaunch {
 };
 
 template <class S, int DENSE>
-__global__ void __launch_bounds__(S::kThreads, 2)
+__global__ void __launch_bounds__(S::kThreads, S::kBytes > 80 * 1024 ? 2 : 3)
 jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                    const float* __restrict__ rhs, unsigned char* m0, unsigned char* m1,
                    const __grid_constant__ TailLaunch L) {
     const float dt = frame->dt;
     const int seq = state->seq, s0 = state->sweeps_done, p_cur = state->p_cur;
     if (!(0.0f < dt)) return;
-    if (seq == 0 || s0 <= 0 || s0 >= L.iters) return;         // bulk pass 0 builds the lists; nothing left to do
-    if (!L.run_all && state->active_after[s0 - 1] == 0ull) return;  // every cell is frozen: the solve is over
-    const int n_relax = L.relax_count[seq], n_copy = L.copy_count[seq];
-    if (L.threshold >= 0 && n_relax > L.threshold) return;     // too many bricks: the bulk kernel is the better tool
+    if (L.first) {
+        if (seq != 0 || s0 != 0 || L.iters <= 0) return;
+    } else {
+        if (seq == 0 || s0 <= 0 || s0 >= L.iters) return;         // pass 0 builds the lists; nothing left to do
+        if (!L.run_all && state->active_after[s0 - 1] == 0ull) return;  // every cell is frozen: the solve is over
+    }
+    const int n_relax = L.first ? L.nbricks : L.relax_count[seq], n_copy = L.first ? 0 : L.copy_count[seq];
+    if (!L.first && L.threshold >= 0 && n_relax > L.threshold) return;  // too many bricks: the bulk kernel is the better tool
 
     TailParams P = L.P;
     P.levels = min(S::TT, L.iters - s0);
-    P.first = 0;
+    P.first = L.first;
     const int sel = (p_cur + seq) & 1;
     const float* p_in = sel ? p1 : p0;
     float* p_out = sel ? p0 : p1;
@@ -81,7 +90,8 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
             continue;
         }
         const int r = item - n_copy;
-        const int path = tail_run_item<S, DENSE>(tid, sh, P, W, W.relax_in[r / P.nsub], r % P.nsub, p_in, p_out, rhs, m_in, m_out,
+        const int path = tail_run_item<S, DENSE>(tid, sh, P, W, L.first ? r / P.nsub : W.relax_in[r / P.nsub], r % P.nsub,
+                                                 p_in, p_out, rhs, m_in, m_out,
                                           state->active_after + s0, state->active_after + 64);
         if (tid == 0 && path != 0) {
             ++relaxed;
@@ -118,6 +128,38 @@ bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d) {
            ext[0] / TailS::OX <= 200;
 }
 
+namespace {
+
+// Everything of TailLaunch that does not depend on the shape.
+TailLaunch tail_launch_params(const FusedJacobi& J, const Domain& d, int iters, int early_exit) {
+    int ext[3];
+    fused_jacobi_brick_extent(J, ext);
+    TailLaunch L;
+    L.P.nx = d.nx; L.P.ny = d.ny; L.P.nz_alloc = d.nz_alloc;
+    L.P.z_face_lo = 0 - d.z_first;
+    L.P.z_face_hi = d.nz - d.z_first;
+    L.P.z_out0 = d.z_own0 - d.z_first; L.P.z_out1 = d.z_own1 - d.z_first;
+    L.P.bx = ext[0]; L.P.by = ext[1]; L.P.bz = ext[2];
+    L.P.ntx = J.ntx; L.P.nty = J.nty;
+    L.P.nsub = ext[0] / TailS::OX;  // TailP0 has the same sub-block width
+    L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = 0;
+    L.P.sparse_cap = 0;
+    L.P.cp_async = J.tail_cp_async;
+    L.P.dense_mode = J.tail_dense_mode == 2 ? 2 : 1;
+    L.iters = iters;
+    L.threshold = -1;
+    L.run_all = 0;
+    L.first = 0;
+    L.nbricks = J.ntx * J.nty * J.nzc;
+    L.list[0] = J.work_list[0]; L.list[1] = J.work_list[1];
+    const int np = FusedJacobi::kMaxPasses + 1;
+    L.relax_count = J.work_count; L.copy_count = J.work_count + np;
+    L.brick_state = J.brick_state;
+    return L;
+}
+
+}  // namespace
+
 cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream) {
     static bool attr_set = false;
@@ -130,34 +172,39 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    int ext[3];
-    fused_jacobi_brick_extent(J, ext);
-    TailLaunch L;
-    L.P.nx = d.nx; L.P.ny = d.ny; L.P.nz_alloc = d.nz_alloc;
-    L.P.z_face_lo = 0 - d.z_first;
-    L.P.z_face_hi = d.nz - d.z_first;
-    L.P.z_out0 = d.z_own0 - d.z_first; L.P.z_out1 = d.z_own1 - d.z_first;
-    L.P.bx = ext[0]; L.P.by = ext[1]; L.P.bz = ext[2];
-    L.P.ntx = J.ntx; L.P.nty = J.nty;
-    L.P.nsub = ext[0] / TailS::OX;
-    L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = TailS::TT;
+    TailLaunch L = tail_launch_params(J, d, iters, early_exit);
+    L.P.levels = TailS::TT;
     L.P.sparse_cap = J.tail_sparse_cap < 0 || J.tail_sparse_cap > TailS::kListCap ? TailS::kListCap : J.tail_sparse_cap;
-    L.P.cp_async = J.tail_cp_async;
-    L.P.dense_mode = J.tail_dense_mode == 2 ? 2 : 1;
-    L.iters = iters;
     L.threshold = threshold;
     L.run_all = run_all ? 1 : 0;
-    L.nbricks = J.ntx * J.nty * J.nzc;
-    L.list[0] = J.work_list[0]; L.list[1] = J.work_list[1];
-    const int np = FusedJacobi::kMaxPasses + 1;
-    L.relax_count = J.work_count; L.copy_count = J.work_count + np;
-    L.brick_state = J.brick_state;
     if (L.P.dense_mode == 2)
         jacobi_tail_kernel<TailS, 2><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
             frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
     else
         jacobi_tail_kernel<TailS, 1><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
             frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+    return cudaGetLastError();
+}
+
+// Pass 0 of the frame by the block-resident kernel (experimental, FXB_PASS0=2): every brick, every cell active.
+cudaError_t launch_jacobi_pass0_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                     int iters, int early_exit, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(jacobi_tail_kernel<TailP0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TailP0::kBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    TailLaunch L = tail_launch_params(J, d, iters, early_exit);
+    L.P.levels = TailP0::TT;
+    L.P.sparse_cap = 0;      // nothing is sparse in pass 0
+    L.P.dense_mode = 2;
+    L.first = 1;
+    const int items = L.nbricks * L.P.nsub;
+    const int slots = J.num_sms * 12;  // three CTAs per SM resident; a few rounds per launch keep the tail short
+    jacobi_tail_kernel<TailP0, 2><<<items < slots ? items : slots, TailP0::kThreads, TailP0::kBytes, stream>>>(
+        frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
     return cudaGetLastError();
 }
 

@@ -119,6 +119,7 @@ template <int TT_, int OXQ_, int OY_, int OZ_>
 struct TailShape {
     static constexpr int TT = TT_, OXQ = OXQ_, OY = OY_, OZ = OZ_;
     static_assert(TT_ >= 1 && TT_ <= 4, "the x halo is one quad");
+    static_assert(OXQ_ % 2 == 0, "a sub-block owns whole bytes of the bit-packed masks: its x extent is a multiple of 8 cells");
     static constexpr int OX = 4 * OXQ_;
     static constexpr int LXQ = OXQ_ + 2, LX = 4 * LXQ;  // window: one halo quad per side in x
     static constexpr int LY = OY_ + 2 * TT_, LZ = OZ_ + 2 * TT_;

@@ -73,6 +73,9 @@ int jacobi_tail_sweeps();
 // run_all (multi-GPU): the launch runs and flips the ping-pong even when this rank has nothing left to relax.
 cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream);
+// Experimental (FXB_PASS0=2, dynamic schedule only): pass 0 of the frame by the block-resident kernel.
+cudaError_t launch_jacobi_pass0_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                     int iters, int early_exit, cudaStream_t stream);
 void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 
 }  // namespace fxb

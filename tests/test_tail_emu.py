@@ -12,7 +12,7 @@ from tests.util import smooth_state
 
 
 def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=True, check_each=True, sparse_cap=-1,
-                    cp_async=1, dense_mode=1):
+                    cp_async=1, dense_mode=1, pass0_kernel=False):
     """Whole pressure solve by emulated tail launches only (first launch: every brick, every cell active).
     Returns (p, s_exec, launches).  After every launch the output buffer must equal the oracle's state everywhere."""
     nz, ny, nx = s2.shape
@@ -27,11 +27,14 @@ def solve_with_tail(oracle_mod, s2, p_start, grid, iters=64, tt=4, early_exit=Tr
     relax, copy = np.arange(g.n, dtype=np.int32), np.zeros(0, np.int32)
     done, seq = 0, 0
     while done < iters:
-        levels = min(tt, iters - done)
+        # pass0_kernel: the first launch is the experimental pass-0 kernel (TailShape<2, 10, 12, 8>: two sweeps, every
+        # cell active, second dense path)
+        wide = pass0_kernel and seq == 0
+        levels = min(2 if wide else tt, iters - done)
         src, dst = seq & 1, (seq + 1) & 1
         relax, copy_next = E.launch(g, p[src], p[dst], rhs, m[src], m[dst], relax, copy, brick_state, hist[done:],
-                                    first=(seq == 0), early_exit=early_exit, levels=levels, tt=tt,
-                                    sparse_cap=sparse_cap, cp_async=cp_async, dense_mode=dense_mode)
+                                    first=(seq == 0), early_exit=early_exit, levels=levels, tt=2 if wide else tt,
+                                    sparse_cap=sparse_cap, cp_async=cp_async, dense_mode=2 if wide else dense_mode)
         p_ref, act_ref, counts = oracle_mod.jacobi_sweeps_slab(s2, p_ref, act_ref, levels, nz, 0, 0, nz, early_exit)
         done += levels
         seq += 1
@@ -95,6 +98,18 @@ def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, dense_
     assert (n_sparse > 0) == (sparse_cap != 0) and (n_dense > 0) == (sparse_cap != -1 or n_dense > 0)
     if sparse_cap == 300:
         assert n_sparse > 0 and n_dense > 0
+
+
+@pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6), ((248, 248, 16), 3)])
+def test_pass0_kernel_then_tail_launches(oracle_mod, n, steps, thread_order):
+    """The experimental pass-0 kernel (TailShape<2, 10, 12, 8>, every cell active, no flags yet, second dense path)
+    followed by ordinary tail launches: the whole solve must equal the oracle."""
+    s2, p0 = developed_state(oracle_mod, n, steps)
+    p_want, s_want, _, _ = oracle_mod.jacobi(s2, p0, 64, True)
+    p_got, s_got, launches = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), pass0_kernel=True)
+    assert np.array_equal(p_got, p_want)
+    assert s_got == s_want
+    assert launches == 1 + -(-(s_want - 2) // 4)
 
 
 def test_tail_random_field_no_early_exit(oracle_mod, thread_order):

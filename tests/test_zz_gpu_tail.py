@@ -96,6 +96,15 @@ def test_tail_second_dense_path(oracle_mod):
     assert ts["tail_subblocks_dense"] == ts["tail_subblocks_relaxed"] > 0
 
 
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="the block-resident pass-0 kernel has not run on a GPU yet: FXB_TEST_EXPERIMENTAL=1 enables the test")
+@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 24)])
+def test_pass0_by_the_block_resident_kernel(oracle_mod, n):
+    """FXB_PASS0=2: pass 0 of every frame runs on jacobi_tail_kernel<TailShape<2, 10, 12, 8>> instead of the bulk kernel."""
+    launches, _ = run_pair(oracle_mod, n, 8, {"FXB_PASS0": 2}, inject_seed=17)
+    assert launches > 0
+
+
 def test_tail_takes_over_right_after_pass_zero(oracle_mod):
     launches, _ = run_pair(oracle_mod, (64, 64, 64), 8, {"FXB_TAIL_MAINS": 1}, inject_seed=11)
     assert launches > 0
