@@ -167,6 +167,13 @@ def test_sass_shows_blackwell_native_paths(fx):
     assert "FADD2" in adv and "FFMA2" in adv
     for banned in ("HMMA", "UTCHMMA", "UTCQMMA", "HGMMA"):
         assert banned not in sass
+    # the opt-in kernels are built too: the block-resident tail kernel (both dense paths and the pass-0 shape, its
+    # cp.async staging shows as LDGSTS), the second advection kernel, the peer-memory halo kernel
+    tail = [k for k in kernels if "jacobi_tail_kernel" in k]
+    assert len(tail) == 3, tail
+    assert any("LDGSTS" in l for k in tail for l in kernels[k])
+    assert any("advect2_kernel" in k for k in kernels) and any("halo_p2p_kernel" in k for k in kernels)
+    assert any("finish_solve_dynamic_kernel" in k for k in kernels)
 
 
 @pytest.mark.parametrize("n", [(64, 64, 64), (150, 150, 150), (256, 256, 1), (512, 512, 1), (128, 128, 40), (30, 30, 18),
