@@ -573,7 +573,9 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (const char* v = getenv("FXB_TAIL_SPARSE_CAP")) s->jac.tail_sparse_cap = atoi(v);
             if (const char* v = getenv("FXB_TAIL_DENSE")) s->jac.tail_dense_mode = atoi(v);
             if (const char* v = getenv("FXB_PASS0")) s->pass0_tail = atoi(v) == 2;
-            if (const char* v = getenv("FXB_TAIL_CPASYNC")) s->jac.tail_cp_async = atoi(v) != 0;
+            if (const char* v = getenv("FXB_TAIL_CPASYNC")) s->jac.tail_cp_async = atoi(v);  // 0 registers, 1 cp.async, 2 TMA
+            if (s->jac.tail_cp_async == 2 && !fxb::jacobi_tail_make_window_maps(&s->jac, s->dom))
+                return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed (tail window)"));
             s->tail = true;
         }
     }

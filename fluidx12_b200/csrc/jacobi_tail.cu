@@ -15,6 +15,8 @@
 // when StepState::sweeps_done equals the sweep count its static index stands for.  Both kernels use the same work
 // lists, freeze masks and ping-pong buffers, indexed by StepState::seq (relax kernels executed so far in the frame).
 // Results are bit-identical whichever kernel relaxes a brick.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "jacobi_tail_body.cuh"
 #include "kernels.h"
@@ -46,7 +48,8 @@ template <class S, int DENSE>
 __global__ void __launch_bounds__(S::kThreads, S::kBytes > 80 * 1024 ? 2 : 3)
 jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                    const float* __restrict__ rhs, unsigned char* m0, unsigned char* m1,
-                   const __grid_constant__ TailLaunch L) {
+                   const __grid_constant__ TailLaunch L, const __grid_constant__ CUtensorMap win0,
+                   const __grid_constant__ CUtensorMap win1) {
     const float dt = frame->dt;
     const int seq = state->seq, s0 = state->sweeps_done, p_cur = state->p_cur;
     if (!(0.0f < dt)) return;
@@ -78,8 +81,19 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
     W.copy_out_count = L.copy_count + seq + 1;
     W.brick_state = L.brick_state;
 
-    extern __shared__ __align__(16) float tail_sm[];
+    extern __shared__ __align__(128) float tail_sm[];  // a TMA destination needs 128-byte alignment
     const TailShared<S> sh = tail_shared<S>(tail_sm);
+    TailTma tma;
+    tma.map = sel ? &win1 : &win0;
+    tma.bar = reinterpret_cast<unsigned long long*>(sh.ctrl + S::kCtrlBar);
+    if (P.cp_async == 2) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(tma.bar)), "r"(1)
+                         : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     const int tid = threadIdx.x;
     const int items = n_copy + n_relax * P.nsub;
@@ -92,7 +106,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
         const int r = item - n_copy;
         const int path = tail_run_item<S, DENSE>(tid, sh, P, W, L.first ? r / P.nsub : W.relax_in[r / P.nsub], r % P.nsub,
                                                  p_in, p_out, rhs, m_in, m_out,
-                                          state->active_after + s0, state->active_after + 64);
+                                                 state->active_after + s0, state->active_after + 64, tma);
         if (tid == 0 && path != 0) {
             ++relaxed;
             if (path == 2) ++dense;
@@ -121,6 +135,13 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
 
 int jacobi_tail_sweeps() { return TailS::TT; }
 
+bool jacobi_tail_make_window_maps(FusedJacobi* J, const Domain& d) {
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    J->win_maps = fused_make_box_map(J->map_win[0], J->p[0], d.nx, d.ny, d.nz_alloc, TailS::LX, TailS::LY, TailS::LZ) &&
+                  fused_make_box_map(J->map_win[1], J->p[1], d.nx, d.ny, d.nz_alloc, TailS::LX, TailS::LY, TailS::LZ);
+    return J->win_maps;
+}
+
 bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d) {
     int ext[3];
     fused_jacobi_brick_extent(J, ext);
@@ -144,7 +165,7 @@ TailLaunch tail_launch_params(const FusedJacobi& J, const Domain& d, int iters, 
     L.P.nsub = ext[0] / TailS::OX;  // TailP0 has the same sub-block width
     L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = 0;
     L.P.sparse_cap = 0;
-    L.P.cp_async = J.tail_cp_async;
+    L.P.cp_async = J.tail_cp_async == 2 ? (J.win_maps ? 2 : 1) : (J.tail_cp_async ? 1 : 0);
     L.P.dense_mode = J.tail_dense_mode == 2 ? 2 : 1;
     L.iters = iters;
     L.threshold = -1;
@@ -177,12 +198,14 @@ cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const Fram
     L.P.sparse_cap = J.tail_sparse_cap < 0 || J.tail_sparse_cap > TailS::kListCap ? TailS::kListCap : J.tail_sparse_cap;
     L.threshold = threshold;
     L.run_all = run_all ? 1 : 0;
+    const CUtensorMap& w0 = *reinterpret_cast<const CUtensorMap*>(J.map_win[0]);
+    const CUtensorMap& w1 = *reinterpret_cast<const CUtensorMap*>(J.map_win[1]);
     if (L.P.dense_mode == 2)
         jacobi_tail_kernel<TailS, 2><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
-            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L, w0, w1);
     else
         jacobi_tail_kernel<TailS, 1><<<J.tail_grid, TailS::kThreads, TailS::kBytes, stream>>>(
-            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+            frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L, w0, w1);
     return cudaGetLastError();
 }
 
@@ -200,11 +223,13 @@ cudaError_t launch_jacobi_pass0_tail(const FusedJacobi& J, const Domain& d, cons
     L.P.levels = TailP0::TT;
     L.P.sparse_cap = 0;      // nothing is sparse in pass 0
     L.P.dense_mode = 2;
+    if (L.P.cp_async == 2) L.P.cp_async = 1;  // the window maps are built for the 4-sweep shape only
     L.first = 1;
     const int items = L.nbricks * L.P.nsub;
     const int slots = J.num_sms * 12;  // three CTAs per SM resident; a few rounds per launch keep the tail short
     jacobi_tail_kernel<TailP0, 2><<<items < slots ? items : slots, TailP0::kThreads, TailP0::kBytes, stream>>>(
-        frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L);
+        frame, state, J.p[0], J.p[1], J.rhs, J.mask[0], J.mask[1], L, *reinterpret_cast<const CUtensorMap*>(J.map_win[0]),
+        *reinterpret_cast<const CUtensorMap*>(J.map_win[1]));
     return cudaGetLastError();
 }
 

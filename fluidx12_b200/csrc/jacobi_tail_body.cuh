@@ -45,6 +45,35 @@
                  "l"(src), "r"((valid) ? 16 : 0)                                                               \
                  : "memory")
 #define FXT_CP_ASYNC_WAIT() asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory")
+// TMA staging of a whole window (cp_async mode 2): ONE cp.async.bulk.tensor.3d, issued by one thread, brings the
+// 48 x 20 x 16 box into shared memory — cells outside the array are zero-filled by the copy engine, which is exactly
+// the window's definition — and completes on an mbarrier every thread then waits on.
+#define FXT_TMA_ISSUE(tma, dst, x, y, z, bytes, p_in, P, it)                                                          \
+    do {                                                                                                               \
+        const unsigned bar_ = (unsigned)__cvta_generic_to_shared((tma).bar);                                           \
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_), "r"((unsigned)(bytes))      \
+                     : "memory");                                                                                      \
+        asm volatile(                                                                                                  \
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" \
+            ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"((tma).map), "r"(x), "r"(y), "r"(z), "r"(bar_)          \
+            : "memory");                                                                                               \
+    } while (0)
+#define FXT_TMA_WAIT(tma)                                                                            \
+    do {                                                                                             \
+        const unsigned bar_ = (unsigned)__cvta_generic_to_shared((tma).bar);                         \
+        const unsigned parity_ = (tma).uses & 1u;                                                    \
+        asm volatile(                                                                                \
+            "{\n"                                                                                    \
+            ".reg .pred p;\n"                                                                        \
+            "FXT_TMA_WAIT_LOOP:\n"                                                                   \
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"                                \
+            "@p bra FXT_TMA_WAIT_DONE;\n"                                                            \
+            "bra FXT_TMA_WAIT_LOOP;\n"                                                               \
+            "FXT_TMA_WAIT_DONE:\n"                                                                   \
+            "}\n" ::"r"(bar_),                                                                       \
+            "r"(parity_)                                                                             \
+            : "memory");                                                                             \
+    } while (0)
 // A work item is a sequence of phases separated by barriers (tail_run_item).  Under nvcc a phase is just the
 // statement, executed by the calling thread `tid` with its state `t`.
 #define FXT_CTX(S) const int tid
@@ -92,6 +121,9 @@ static inline int fxt_fetch_add_i32(int* p, int v) { const int o = *p; *p = o + 
         *reinterpret_cast<fxb::Quad*>(dst) = (valid) ? *reinterpret_cast<const fxb::Quad*>(src) : zero_; \
     } while (0)
 #define FXT_CP_ASYNC_WAIT() (void)0
+// TMA staging, emulated: the box copy with zero fill outside the array, done by the issuing thread
+#define FXT_TMA_ISSUE(tma, dst, x, y, z, bytes, p_in, P, it) fxb::tail_emulated_box_copy<S>(dst, p_in, P, x, y, z)
+#define FXT_TMA_WAIT(tma) (void)0
 // Emulation: phases are queued and run at the next barrier, thread after thread — every thread runs ALL phases of
 // the barrier-free segment before the next thread starts (in ascending or descending thread order).  That is the
 // most skewed interleaving a missing __syncthreads() would permit, so a phase that needs another thread's result
@@ -135,6 +167,7 @@ struct TailShape {
     static constexpr int kNibBytes = LZ * LY * LXQ;
     static constexpr int kCtrlWords = 8 + TT_;  // any-own flag, per-level counters, listable-cell count, spare
     static constexpr int kCtrlTotal = TT_ + 1;  // ctrl index of the number of active cells that can be relaxed at all
+    static constexpr int kCtrlBar = (TT_ + 3) & ~1;  // ctrl index (even: 8-byte aligned) of the TMA mbarrier; never reset
     // sparse path: list entries (u32) + their right-hand sides (f32) + new values (f32) live where the dense path
     // stages the right-hand side of the whole window
     static constexpr int kListCap = (kRhsFloats * 4 / 12) / 32 * 32;
@@ -172,9 +205,23 @@ struct TailParams {
     int early_exit;
     int levels;          // sweeps to apply (<= TT)
     int sparse_cap;      // windows with at most this many relaxable active cells take the sparse path (<= kListCap)
-    int cp_async;        // 1: the sparse path stages its window with cp.async; 0: through registers
+    int cp_async;        // window staging: 0 through registers; 1 cp.async, requested together with the flags; 2 TMA box copy
     int dense_mode;      // crowded windows: 1 = register z-columns, 2 = two-phase update of all quads (side array)
 };
+
+// TMA staging state (mode 2): the tensor map of the pressure buffer that is this launch's input, the mbarrier in shared
+// memory, and how many copies have completed on it so far (its phase parity).
+struct TailTma {
+    const void* map = nullptr;
+    unsigned long long* bar = nullptr;
+    unsigned uses = 0;
+};
+
+#if !defined(__CUDACC__)
+// What the copy engine does for a box at (x0, y0, z0): elements outside the array [0,nx) x [0,ny) x [0,nz_alloc) are 0.
+template <class S>
+inline void tail_emulated_box_copy(float* dst, const float* p_in, const TailParams& P, int x0, int y0, int z0);
+#endif
 
 // Shared-memory view.
 template <class S>
@@ -203,6 +250,19 @@ FXT_FN TailShared<S> tail_shared(void* base) {
     sh.rhsv = sh.newv + S::kListCap;
     return sh;
 }
+
+#if !defined(__CUDACC__)
+template <class S>
+inline void tail_emulated_box_copy(float* dst, const float* p_in, const TailParams& P, int x0, int y0, int z0) {
+    for (int z = 0; z < S::LZ; ++z)
+        for (int y = 0; y < S::LY; ++y)
+            for (int x = 0; x < S::LX; ++x) {
+                const int gx = x0 + x, gy = y0 + y, gz = z0 + z;
+                const bool in = gx >= 0 && gx < P.nx && gy >= 0 && gy < P.ny && gz >= 0 && gz < P.nz_alloc;
+                dst[(z * S::LY + y) * S::LX + x] = in ? p_in[((size_t)gz * P.ny + gy) * P.nx + gx] : 0.0f;
+            }
+}
+#endif
 
 // Per-thread state that lives across phases (registers under nvcc).
 template <class S>
@@ -303,7 +363,7 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
     t.fl[0] = t.fl[1] = 0u;
     t.own[0] = t.own[1] = 0u;
     t.dirty = 0u;
-    if (P.cp_async && t.used) {
+    if (P.cp_async == 1 && t.used) {
         // cp.async mode: the window is requested here, together with the flags, so that every path of the item
         // (copy, sparse, dense) finds it in shared memory after ONE memory round trip; no register is involved
 #pragma unroll
@@ -345,7 +405,7 @@ FXT_FN void tail_phase_flags(int tid, TailThread<S>& t, const TailShared<S>& sh,
     t.nlist = nl;
     sh.scan[tid] = nl;
     if (nl) FXT_ATOMIC_ADD_U32(&sh.ctrl[S::kCtrlTotal], (unsigned)nl);
-    if (P.cp_async) FXT_CP_ASYNC_WAIT();  // the window has landed before the barrier that follows this phase
+    if (P.cp_async == 1) FXT_CP_ASYNC_WAIT();  // the window has landed before the barrier that follows this phase
 }
 
 // ---- copy path: no active cell in the own region, so the output equals the input ---------------------------------
@@ -827,17 +887,23 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                          const int sub, const float* __restrict__ p_in, float* __restrict__ p_out,
                          const float* __restrict__ rhs, const unsigned char* __restrict__ m_in,
                          unsigned char* __restrict__ m_out, unsigned long long* active_after_s0,
-                         unsigned long long* marks) {
+                         unsigned long long* marks, TailTma& tma) {
     const TailItem<S> it = tail_item<S>(P, brick, sub);
     FXT_THREAD_STATE(S);
     FXT_MARK_BEGIN();
     int path = 0;
     FXT_SYNC();  // the previous item is finished with shared memory
-    FXT_PHASE(if (tid < S::kCtrlWords) sh.ctrl[tid] = 0u);
+    FXT_PHASE(if (tid < S::kCtrlBar) sh.ctrl[tid] = 0u);  // (the words from kCtrlBar on hold the TMA mbarrier)
     FXT_SYNC();
     FXT_MARK(0);
     if (it.ex > 0) {
+        if (P.cp_async == 2)
+            FXT_PHASE(if (tid == 0) FXT_TMA_ISSUE(tma, sh.p, it.wx, it.wy, it.wz, S::kPFloats * 4, p_in, P, it));
         FXT_PHASE(tail_phase_flags<S>(tid, t, sh, it, P, m_in, p_in));
+        if (P.cp_async == 2) {
+            FXT_PHASE(FXT_TMA_WAIT(tma));
+            tma.uses += 1u;
+        }
         FXT_SYNC();
         FXT_MARK(1);
         const int n_list = (int)sh.ctrl[S::kCtrlTotal];

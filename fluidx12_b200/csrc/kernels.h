@@ -56,12 +56,15 @@ struct FusedJacobi {
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
+    alignas(64) unsigned char map_win[2][128];    // tail kernel, TMA staging (FXB_TAIL_CPASYNC=2): its window box on p[0] / p[1]
+    bool win_maps = false;
 };
 bool fused_jacobi_supported(const Domain& d);
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);
+bool fused_make_box_map(void* map128, float* base, int nx, int ny, int nz_alloc, int box_x, int box_y, int box_z);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
                                      cudaStream_t stream);
@@ -70,6 +73,7 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
 // are still active (dynamic schedule only).  threshold < 0: run whatever the list length.
 bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d);
 int jacobi_tail_sweeps();
+bool jacobi_tail_make_window_maps(FusedJacobi* J, const Domain& d);  // for FXB_TAIL_CPASYNC=2
 // run_all (multi-GPU): the launch runs and flips the ping-pong even when this rank has nothing left to relax.
 cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream);

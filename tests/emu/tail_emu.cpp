@@ -30,7 +30,8 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
     for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0xDEADBEEFu;
     TailEmu<S> emu;
     emu.descending = g_descending;
-    const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0, nullptr);
+    TailTma tma;
+    const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0, nullptr, tma);
     ++g_paths[path];
 }
 

@@ -172,6 +172,7 @@ def test_sass_shows_blackwell_native_paths(fx):
     tail = [k for k in kernels if "jacobi_tail_kernel" in k]
     assert len(tail) == 3, tail
     assert any("LDGSTS" in l for k in tail for l in kernels[k])
+    assert any("UTMALDG" in l for k in tail for l in kernels[k])  # FXB_TAIL_CPASYNC=2: the window as one TMA box copy
     assert any("advect2_kernel" in k for k in kernels) and any("halo_p2p_kernel" in k for k in kernels)
     assert any("finish_solve_dynamic_kernel" in k for k in kernels)
 

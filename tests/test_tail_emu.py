@@ -80,7 +80,7 @@ def thread_order(request):
 
 
 @pytest.mark.parametrize("n,steps", [((64, 64, 64), 12), ((136, 136, 24), 6)])
-@pytest.mark.parametrize("cp_async", [0, 1])
+@pytest.mark.parametrize("cp_async", [0, 1, 2])
 @pytest.mark.parametrize("sparse_cap,dense_mode", [(-1, 1), (0, 1), (300, 1), (0, 2), (300, 2)])
 def test_tail_only_solve_matches_oracle(oracle_mod, n, steps, sparse_cap, dense_mode, thread_order, cp_async):
     """sparse_cap -1: sparse path wherever the list fits; 0: dense path only; 300: both in one solve.

@@ -82,6 +82,15 @@ def test_tail_window_staged_with_cp_async(oracle_mod):
     assert launches > 0
 
 
+@pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
+                    reason="TMA staging of the tail window has not run on a GPU yet: FXB_TEST_EXPERIMENTAL=1 enables the test")
+@pytest.mark.parametrize("n", [(128, 128, 40), (136, 136, 24)])
+def test_tail_window_staged_with_tma(oracle_mod, n):
+    """FXB_TAIL_CPASYNC=2: one cp.async.bulk.tensor.3d per window (zero fill outside the array by the copy engine)."""
+    launches, _ = run_pair(oracle_mod, n, 8, {"FXB_TAIL_CPASYNC": 2}, inject_seed=16)
+    assert launches > 0
+
+
 def test_tail_dense_path_only(oracle_mod):
     """FXB_TAIL_SPARSE_CAP=0: every window that holds an active cell takes the register-column path."""
     _, ts = run_pair(oracle_mod, (64, 64, 40), 6, {"FXB_TAIL_SPARSE_CAP": 0})

@@ -128,6 +128,7 @@ def main():
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1}),
                                           ("tail_thr8192_m5", {"FXB_TAIL_THRESHOLD": 8192, "FXB_TAIL_MAINS": 5}),
                                           ("tail_cpasync", {"FXB_TAIL_CPASYNC": 1}),
+                                          ("tail_tma", {"FXB_TAIL_CPASYNC": 2}),
                                           ("tail_dense2", {"FXB_TAIL_DENSE": 2}),
                                           ("tail_pass0", {"FXB_PASS0": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
