@@ -6,6 +6,10 @@
 # launch of a developed 256^3 step), tail_probe.txt (in-kernel phase cycles; needs the timing build, done here).
 set -x
 mkdir -p gpurun_out
+# every opt-in variant against the oracle first (the gated tests: cp.async / TMA staging, second dense path, pass-0 kernel,
+# second advection kernel), then parity + timing of the variants side by side
+FXB_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_gpu_tail.py tests/test_zy_gpu_golden.py -m gpu -q \
+    > gpurun_out/tail_tests.log 2>&1; tail -3 gpurun_out/tail_tests.log
 python tools/gpu_shot.py > gpurun_out/tail_shot.log 2>&1; cp gpurun_out/shot.jsonl gpurun_out/tail_shot.jsonl
 export FXB_TAIL=1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/tail_launches.csv \
