@@ -132,10 +132,11 @@ def main():
                                           ("tail_dense2", {"FXB_TAIL_DENSE": 2}),
                                           ("tail_pass0", {"FXB_PASS0": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
+                                          ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
                                           ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
                                           ("tail_thr1024", {"FXB_TAIL_THRESHOLD": 1024, "FXB_TAIL_MAINS": 12})],
            all_fields=True)
-    timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("tail_advect2", {"FXB_ADVECT": 2}), ("tail_pass0", {"FXB_PASS0": 2}), ("tail_thr2048", {"FXB_TAIL_THRESHOLD": 2048, "FXB_TAIL_MAINS": 12})])
+    timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}), ("tail_pass0", {"FXB_PASS0": 2}), ("tail_thr2048", {"FXB_TAIL_THRESHOLD": 2048, "FXB_TAIL_MAINS": 12})])
     oracle_check(fx, "default", None)
     emit(stage="done")
 
