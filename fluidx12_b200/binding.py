@@ -16,7 +16,7 @@ FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_
 EXPORTS = (
     "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
-    "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+    "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
 )
 
 
@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         L.fxb_get_stats.argtypes = [vp, C.POINTER(FxbStats)]
         L.fxb_get_tail_stats.argtypes = [vp, vp, C.c_int]
         L.fxb_plan_pressure_solve.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]
+        L.fxb_p2p_plan.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int64)]
         L.fxb_emitter_box.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
         L.fxb_get_freeze_histogram.argtypes = [vp, vp, C.c_int]
         L.fxb_profile_step.argtypes = [vp, C.POINTER(C.c_float), C.c_int]

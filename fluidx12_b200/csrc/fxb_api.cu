@@ -790,6 +790,21 @@ int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_
     return (int)plan.size();
 }
 
+int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t depth, int64_t* out4) {
+    if (!out4 || nz < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > nz || halo < 0 || depth < 1)
+        return fail(FXB_ERR_INVALID, "fxb_p2p_plan: bad argument");
+    auto z_first = [&](int r) { return std::max(r * nz / nranks - halo, 0); };
+    fxb::Domain d{};
+    d.nz = nz;
+    d.z_own0 = rank * nz / nranks;
+    d.z_own1 = (rank + 1) * nz / nranks;
+    d.z_first = z_first(rank);
+    d.nz_alloc = std::min(d.z_own1 + halo, nz) - d.z_first;
+    const fxb::P2PPlanes q = fxb::p2p_planes(d, depth, rank > 0 ? z_first(rank - 1) : 0, rank < nranks - 1 ? z_first(rank + 1) : 0);
+    out4[0] = q.send_lo; out4[1] = q.dst_lo; out4[2] = q.send_hi; out4[3] = q.dst_hi;
+    return FXB_OK;
+}
+
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {
     if (!out6 || nx == 0 || ny == 0 || nz == 0) return fail(FXB_ERR_INVALID, "fxb_emitter_box: bad argument");
     int lo[3], hi[3];

@@ -191,6 +191,17 @@ __global__ void __launch_bounds__(256) halo_p2p_kernel(const __grid_constant__ P
 
 }  // namespace
 
+P2PPlanes p2p_planes(const Domain& d, int depth, int z_first_lo, int z_first_hi) {
+    P2PPlanes q;
+    // my lowest planes are rank - 1's upper halo: global planes [z_own0, z_own0 + depth)
+    q.send_lo = d.z_own0 - d.z_first;
+    q.dst_lo = d.z_own0 - z_first_lo;
+    // my highest planes are rank + 1's lower halo: global planes [z_own1 - depth, z_own1)
+    q.send_hi = d.z_own1 - depth - d.z_first;
+    q.dst_hi = d.z_own1 - depth - z_first_hi;
+    return q;
+}
+
 bool HaloComm::p2p_init(void* const* buffers, int nbuffers, int z_first_lo, int z_first_hi, cudaStream_t stream) {
     if (nranks <= 1 || nbuffers <= 0 || nbuffers > HaloP2P::kMaxBuffers) return false;
     auto cuda_ok = [&](cudaError_t e, const char* what) {
@@ -280,17 +291,17 @@ bool HaloComm::exchange(const Domain& d, const HaloField* fields, int nfields, c
             }
             const char* base = static_cast<const char*>(f.base);
             const size_t pb = f.plane_bytes, n = pb * f.depth;
-            const long long own0 = d.z_own0 - d.z_first, own1 = d.z_own1 - d.z_first;
-            if (rank > 0) {  // my lowest planes are rank - 1's upper halo: global planes [z_own0, z_own0 + depth)
+            const P2PPlanes q = p2p_planes(d, f.depth, p2p.z_first_lo, p2p.z_first_hi);
+            if (rank > 0) {
                 P2PJob& j = a.job[a.njobs++];
-                j.src = base + own0 * pb;
-                j.dst = static_cast<char*>(p2p.peer_lo[b]) + (size_t)(d.z_own0 - p2p.z_first_lo) * pb;
+                j.src = base + q.send_lo * (long long)pb;
+                j.dst = static_cast<char*>(p2p.peer_lo[b]) + q.dst_lo * (long long)pb;
                 j.bytes = n;
             }
-            if (rank < nranks - 1) {  // my highest planes are rank + 1's lower halo: [z_own1 - depth, z_own1)
+            if (rank < nranks - 1) {
                 P2PJob& j = a.job[a.njobs++];
-                j.src = base + (own1 - f.depth) * pb;
-                j.dst = static_cast<char*>(p2p.peer_hi[b]) + (size_t)(d.z_own1 - f.depth - p2p.z_first_hi) * pb;
+                j.src = base + q.send_hi * (long long)pb;
+                j.dst = static_cast<char*>(p2p.peer_hi[b]) + q.dst_hi * (long long)pb;
                 j.bytes = n;
             }
             total += 2 * n;

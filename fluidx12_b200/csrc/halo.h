@@ -32,6 +32,14 @@ struct HaloP2P {
     int z_first_lo = 0, z_first_hi = 0;       // Domain::z_first of the neighbours
 };
 
+// Where one face exchange of `depth` planes reads and writes, in LOCAL plane indices (pure arithmetic, no GPU):
+// this rank sends its planes [send_lo, send_lo + depth) into rank - 1's array at [dst_lo, ...) and its planes
+// [send_hi, send_hi + depth) into rank + 1's array at [dst_hi, ...).  z_first_*: global plane of local plane 0.
+struct P2PPlanes {
+    long long send_lo, dst_lo, send_hi, dst_hi;
+};
+P2PPlanes p2p_planes(const Domain& d, int depth, int z_first_lo, int z_first_hi);
+
 struct HaloComm {
     void* comm = nullptr;  // ncclComm_t
     int rank = 0, nranks = 1;

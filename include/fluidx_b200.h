@@ -135,6 +135,12 @@ int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out, int n);
  * written), or a negative fxb_status. */
 int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_t* kinds, int32_t capacity);
 
+/* Diagnostic, needs no GPU: the plane arithmetic of the peer-memory halo exchange (FXB_P2P=1) for `rank` of `nranks`
+ * z-slabs with `halo` allocated planes and an exchange `depth` planes deep.  out4 = {first local plane sent to rank-1,
+ * first local plane of rank-1's array it lands in, first local plane sent to rank+1, first local plane of rank+1's
+ * array it lands in} (entries for a missing neighbour are meaningless). */
+int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t depth, int64_t* out4);
+
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);

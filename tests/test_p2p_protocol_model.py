@@ -103,3 +103,33 @@ def test_the_model_detects_a_schedule_that_is_not_safe():
     with pytest.raises(AssertionError):
         for seed in range(200):
             run(program, 3, seed)
+
+
+@pytest.mark.parametrize("nz,nranks,halo", [(96, 2, 9), (128, 4, 13), (1024, 8, 13), (100, 3, 5), (64, 8, 4)])
+def test_p2p_plane_arithmetic_matches_the_slab_plan(nz, nranks, halo):
+    """The source / destination planes the peer-memory exchange computes (csrc/halo.cu p2p_planes, exported as
+    fxb_p2p_plan) against the slab rules of fluidx12_b200/slab.py: what rank r stores into its neighbour's array must be
+    exactly the planes that neighbour's exchange record says it receives, at the right local index."""
+    import ctypes as C
+
+    import fluidx12_b200 as fx
+    from fluidx12_b200.slab import _faces, slab_range
+
+    L = fx.lib()
+
+    def z_first(r):
+        return max(slab_range(nz, r, nranks)[0] - halo, 0)
+
+    for depth in (1, 2, 4, min(halo, 9)):
+        for r in range(nranks):
+            out = (C.c_int64 * 4)()
+            assert L.fxb_p2p_plan(nz, nranks, r, halo, depth, out) == 0
+            send_lo, dst_lo, send_hi, dst_hi = out
+            for e in _faces(nz, r, nranks, depth):
+                # e: rank r sends own planes [send0, send1) to e.peer; the peer's record holds the matching receive
+                back = [x for x in _faces(nz, e.peer, nranks, depth) if x.peer == r][0]
+                assert (back.recv0, back.recv1) == (e.send0, e.send1)
+                if e.peer == r - 1:
+                    assert send_lo + z_first(r) == e.send0 and dst_lo + z_first(r - 1) == back.recv0
+                else:
+                    assert send_hi + z_first(r) == e.send0 and dst_hi + z_first(r + 1) == back.recv0
