@@ -908,6 +908,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
         FXT_MARK(1);
         const int n_list = (int)sh.ctrl[S::kCtrlTotal];
         if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));  // (its atomics overlap the copy)
             FXT_PHASE(tail_phase_copy<S>(t, sh, it, P, p_in, p_out, m_out));
             FXT_MARK(6);
         } else if (n_list <= P.sparse_cap) {  // relax a compacted list of the active cells
@@ -928,6 +929,9 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                 FXT_SYNC();
             }
             FXT_MARK(5);
+            // the counters are final: thread 0 starts the brick's bookkeeping (two dependent atomics) while the other
+            // warps store the result
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
             FXT_MARK(6);
         } else if (DENSE == 2 || (DENSE == 0 && P.dense_mode == 2)) {  // crowded window: two-phase update of all quads
@@ -942,6 +946,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                 FXT_SYNC();
             }
             FXT_MARK(5);
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
             FXT_MARK(6);
         } else {  // crowded window: register columns
@@ -956,13 +961,15 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                 FXT_SYNC();
             }
             FXT_MARK(5);
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
             FXT_PHASE(tail_phase_store<S>(t, sh, it, P, p_out));
             FXT_SYNC();
             FXT_PHASE(tail_phase_store_mask<S>(t, sh, it, P, m_out));
             FXT_MARK(6);
         }
+    } else {
+        FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));  // an empty sub-block (outside the grid) still casts its brick's vote
     }
-    FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
     FXT_MARK(7);
     FXT_MARK_END(marks, path);
     FXT_END();
