@@ -2,7 +2,7 @@
 
 Thread 0 of every CTA accumulates the cycles between the marks of tail_run_item (jacobi_tail_body.cuh) per path;
 this prints the average per work item.  Marks: 0 ctrl reset, 1 flags, 2 scan, 3 window load / list build, 4 rhs gather,
-5 the sweeps, 6 store (or copy), 7 finish (atomics, list append).  Debug aid, not a benchmark."""
+5 the sweeps, 6 thread 0's brick bookkeeping (atomics, list append) followed by its share of the store (or copy), 7 (unused).  Debug aid, not a benchmark."""
 import os
 import sys
 
@@ -23,7 +23,7 @@ for _ in range(steps):
 f.sync()
 m = f.freeze_histogram(128).astype(np.int64)[64:96]
 print("tail stats", f.tail_stats(), "s_exec", f.stats().s_exec)
-names = ("ctrl", "flags", "scan", "load/build", "gather", "sweeps", "store/copy", "finish")
+names = ("ctrl", "flags", "scan", "load/build", "gather", "sweeps", "bookkeeping+store", "-")
 for path, label in enumerate(("copy", "sparse", "dense")):
     n = int(m[24 + path])
     if n == 0:
