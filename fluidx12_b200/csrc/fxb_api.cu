@@ -245,17 +245,19 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 // tail launches are unconditional), so the position in the relax sequence — hence the ping-pong side and
                 // the mask buffer whose halo must be exchanged — is the launch index on every rank.
                 const bool mg = s->multi() && s->dt > 0.0f;
-                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, deep enough for a tail launch
-                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, std::max(TT, s->fuse_t)}};
-                    s->comm.exchange(d, f, 1, st);
-                }
                 int seq = 0;
                 for (const int kind : plan_pressure_solve(iters, s->fuse_t, TT, s->multi() ? 1 : s->tail_mains)) {
                     if (mg) {
+                        // before launch 0: the pass input pressure and, in the same exchange, the right-hand side
+                        // (constant over the sweeps: once per step, deep enough for a tail launch); before every later
+                        // launch: its input pressure and freeze mask
                         const int depth = kind >= 0 ? s->fuse_t : TT;
-                        const fxb::HaloField f[2] = {{s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, depth},
-                                                     {s->jac.mask[seq & 1], s->plane_voxels() / 8, depth}};
-                        s->comm.exchange(d, f, seq == 0 ? 1 : 2, st);
+                        const fxb::HaloField p_halo = {s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, depth};
+                        const fxb::HaloField second =
+                            seq == 0 ? fxb::HaloField{s->rhs, s->plane_voxels() * 4, std::max(TT, s->fuse_t)}
+                                     : fxb::HaloField{s->jac.mask[seq & 1], s->plane_voxels() / 8, depth};
+                        const fxb::HaloField f[2] = {p_halo, second};
+                        s->comm.exchange(d, f, 2, st);
                     }
                     if (kind == 0 && s->pass0_tail && s->fuse_t == 2)
                         fxb::launch_jacobi_pass0_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit, st);

@@ -12,8 +12,9 @@ import random
 import pytest
 
 
-def build_steps(nsteps, launches, p_cur=0):
-    """launches: relax kernels per step (32 fused passes, or 17 = bulk pass 0 + 16 tail launches)."""
+def build_steps(nsteps, launches, p_cur=0, merged_rhs=False):
+    """launches: relax kernels per step (32 fused passes, or 17 = bulk pass 0 + 16 tail launches).
+    merged_rhs: the dynamic schedule on slabs sends the right-hand side together with launch 0's pressure halo."""
     prog = []
     parity = 0
     for _ in range(nsteps):
@@ -21,11 +22,12 @@ def build_steps(nsteps, launches, p_cur=0):
         col_in, col_out = ("colA", "colB") if parity else ("colB", "colA")
         prog.append((("vel0", col_in), ("vel0", col_in), ("vel1", col_out)))          # advect
         prog.append((("vel1",), ("vel1",), ("rhs",)))                                 # divergence
-        prog.append((("rhs",), (), ()))                                               # rhs halo, no kernel of its own
+        if not merged_rhs:
+            prog.append((("rhs",), (), ()))                                           # rhs halo, no kernel of its own
         for k in range(launches):
             p_in, p_out = "p%d" % ((p_cur + k) & 1), "p%d" % ((p_cur + k + 1) & 1)
             m_in, m_out = "m%d" % (k & 1), "m%d" % ((k + 1) & 1)
-            exch = (p_in,) if k == 0 else (p_in, m_in)
+            exch = ((p_in, "rhs") if merged_rhs else (p_in,)) if k == 0 else (p_in, m_in)
             reads = (p_in, "rhs") if k == 0 else (p_in, m_in, "rhs")
             prog.append((exch, reads, (p_out, m_out)))                                # relax kernel k
         p_cur = (p_cur + launches) & 1
@@ -92,7 +94,7 @@ def run(program, nranks, seed):
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 @pytest.mark.parametrize("launches", [32, 17, 16, 1])
 def test_unacknowledged_halo_stores_are_safe(nranks, launches):
-    program = build_steps(3, launches)
+    program = build_steps(3, launches, merged_rhs=(launches == 17))
     for seed in range(300 if nranks < 8 else 60):
         run(program, nranks, seed)
 
