@@ -197,3 +197,14 @@ def test_tail_on_z_slabs_matches_single_domain(oracle_mod, nranks, n):
     assert np.array_equal(got, p_want)
     total = sum(k.hist[:iters].astype(np.int64) for k in ranks)
     assert np.array_equal(total[:s_want - 1], hist_want[1:s_want])
+
+
+@pytest.mark.parametrize("n,steps", [((72, 72, 24), 5), ((8, 8, 8), 6), ((24, 24, 9), 7), ((40, 40, 17), 9)])
+@pytest.mark.parametrize("cp_async,dense_mode,sparse_cap,pass0", [(1, 2, 200, False), (2, 1, 0, True)])
+def test_tail_odd_grids_and_mode_combinations(oracle_mod, n, steps, cp_async, dense_mode, sparse_cap, pass0, thread_order):
+    """Grids that are smaller than a window, not multiples of the brick, or a single brick thick, under mixed modes."""
+    s2, p0 = developed_state(oracle_mod, n, steps)
+    p_want, s_want, _, _ = oracle_mod.jacobi(s2, p0, 64, True)
+    p_got, s_got, _ = solve_with_tail(oracle_mod, s2, p0, (120, 12, 8), cp_async=cp_async, dense_mode=dense_mode,
+                                      sparse_cap=sparse_cap, pass0_kernel=pass0)
+    assert np.array_equal(p_got, p_want) and s_got == s_want
