@@ -118,6 +118,14 @@ struct WorkLists {
     int* copy_count;   // [pass]
 };
 
+// Position of a launch in the frame's relax sequence: the static schedule keeps it in the launch parameters (constant
+// bank), the dynamic one (DYN) reads it from StepState::seq at run time.
+template <bool DYN>
+__device__ __forceinline__ int pass_of(const PassParams& P, const int seq) {
+    if constexpr (DYN) return seq;
+    else return P.pass;
+}
+
 // A brick whose cells all froze during pass p-1 holds its final values in that pass's output buffer only.  Pass p
 // copies its own region once into the other buffer (and clears the other mask buffer), after which the brick is
 // final in both ping-pong buffers and is never touched again in this frame.  Pure streaming (8 B/cell), eight
@@ -197,12 +205,13 @@ __device__ __forceinline__ void relax_tail(const float4 head, const float4 hi, c
 }
 
 // Relaxes one brick: T fused sweeps over its 120 x (TILE_Y - 2T) x (ze - zs) output cells (see the file header).
-template <class S>
+template <class S, bool DYN = false>
 __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUtensorMap* map_rhs_p,
                                          float* __restrict__ p_out, const unsigned char* __restrict__ m_in,
                                          unsigned char* __restrict__ m_out, StepState* __restrict__ state,
                                          const WorkLists& W, const PassParams& P, const int brick, const int tx,
-                                         const int ty, const int zs, const int ze, const int levels, const int s0) {
+                                         const int ty, const int zs, const int ze, const int levels, const int s0,
+                                         const int seq = 0) {
     FXB_SHAPE_CONSTANTS(S);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kOutY = kTileY - 2 * T;
@@ -267,13 +276,13 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
     // Freeze flags of the level-0 planes (the previous pass's output mask).  The raw bytes are fetched two
     // iterations ahead and only decoded when their plane is consumed, so the load latency stays hidden.
     auto fetch_flag_bytes = [&](int z, unsigned (&raw)[kRows]) {
-        if (P.pass == 0 || z >= zl1) return;
+        if (pass_of<DYN>(P, seq) == 0 || z >= zl1) return;
 #pragma unroll
         for (int r = 0; r < kRows; ++r)
             if ((dom_bits >> (4 * r)) & 1u) raw[r] = __ldg(m_in + ((size_t)z * P.ny + (gyb + r)) * nxb + (gx >> 3));
     };
     auto decode_flags = [&](const unsigned (&raw)[kRows]) -> unsigned {
-        if (P.pass == 0) return dom_bits;
+        if (pass_of<DYN>(P, seq) == 0) return dom_bits;
         unsigned f = 0;
 #pragma unroll
         for (int r = 0; r < kRows; ++r) f |= ((raw[r] >> (gx & 4)) & 0xFu) << (4 * r);
@@ -516,8 +525,8 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
     }
     if (tid == 0) {
         // still active -> relax again next pass; just frozen -> one copy into the other pressure buffer next pass
-        if (s_cnt[levels - 1] != 0u) W.relax[(P.pass + 1) & 1][atomicAdd(&W.relax_count[P.pass + 1], 1)] = brick;
-        else W.copy[(P.pass + 1) & 1][atomicAdd(&W.copy_count[P.pass + 1], 1)] = brick;
+        if (s_cnt[levels - 1] != 0u) W.relax[(pass_of<DYN>(P, seq) + 1) & 1][atomicAdd(&W.relax_count[pass_of<DYN>(P, seq) + 1], 1)] = brick;
+        else W.copy[(pass_of<DYN>(P, seq) + 1) & 1][atomicAdd(&W.copy_count[pass_of<DYN>(P, seq) + 1], 1)] = brick;
         atomicAdd(&state->bricks_processed, 1ull);
     }
 }
@@ -525,28 +534,28 @@ __device__ __forceinline__ void relax_brick(const CUtensorMap* map_in, const CUt
 // One fused pass.  P.pass is the position in the frame's relax sequence (it selects the work lists, the freeze masks
 // and the side of the pressure ping-pong), s0 the number of sweeps completed before it.  Returns the sweeps applied
 // (0 when the pass had nothing to do).
-template <class S>
+template <class S, bool DYN = false>
 __device__ __forceinline__ int jacobi_pass_body(const CUtensorMap& map_p0, const CUtensorMap& map_p1,
                                                 const CUtensorMap& map_rhs, const FrameParams* __restrict__ frame,
                                                 StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0,
                                                 unsigned char* m1, const WorkLists& W, const PassParams& P,
-                                                const int s0) {
+                                                const int s0, const int seq = 0) {
     FXB_SHAPE_CONSTANTS(S);
     // independent loads first (one round trip instead of a chain), then the decisions
     const float dt = frame->dt;
     const int p_cur = state->p_cur;
-    const unsigned long long still = P.pass > 0 ? state->active_after[s0 - 1] : 1ull;
-    const int n_relax = W.relax_count[P.pass], n_copy = W.copy_count[P.pass];
+    const unsigned long long still = pass_of<DYN>(P, seq) > 0 ? state->active_after[s0 - 1] : 1ull;
+    const int n_relax = W.relax_count[pass_of<DYN>(P, seq)], n_copy = W.copy_count[pass_of<DYN>(P, seq)];
     if (!(0.0f < dt)) return 0;
-    if (P.pass > 0 && !P.run_all && still == 0ull) return 0;
+    if (pass_of<DYN>(P, seq) > 0 && !P.run_all && still == 0ull) return 0;
     const int levels = min(T, P.levels_total - s0);
 
-    const int sel = (p_cur + P.pass) & 1;
+    const int sel = (p_cur + pass_of<DYN>(P, seq)) & 1;
     const CUtensorMap* map_in = sel ? &map_p1 : &map_p0;
     const float* p_in = sel ? p1 : p0;
     float* p_out = sel ? p0 : p1;
-    const unsigned char* m_in = (P.pass & 1) ? m1 : m0;
-    unsigned char* m_out = (P.pass & 1) ? m0 : m1;
+    const unsigned char* m_in = (pass_of<DYN>(P, seq) & 1) ? m1 : m0;
+    unsigned char* m_out = (pass_of<DYN>(P, seq) & 1) ? m0 : m1;
 
     const int tid = threadIdx.x;
     extern __shared__ __align__(1024) float sm[];
@@ -558,13 +567,13 @@ __device__ __forceinline__ int jacobi_pass_body(const CUtensorMap& map_p0, const
     // copy each) and the bricks that still hold an active cell (relaxed again).  CTAs are persistent
     // (kCtasPerSm per SM) and take list entries round-robin, so that the entry index — and in pass 0 the brick
     // coordinates — stay warp-uniform values.
-    if (P.pass > 0) {
-        const int* __restrict__ copy_list = W.copy[P.pass & 1];
+    if (pass_of<DYN>(P, seq) > 0) {
+        const int* __restrict__ copy_list = W.copy[pass_of<DYN>(P, seq) & 1];
         for (int w = blockIdx.x; w < n_copy; w += gridDim.x) copy_frozen_brick<S>(p_in, p_out, m_out, P, copy_list[w]);
         if (tid == 0 && blockIdx.x == 0 && n_copy) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
     }
-    const int n_work = P.pass == 0 ? P.ntx * P.nty * P.nzc : n_relax;
-    const int* __restrict__ list_in = W.relax[P.pass & 1];
+    const int n_work = pass_of<DYN>(P, seq) == 0 ? P.ntx * P.nty * P.nzc : n_relax;
+    const int* __restrict__ list_in = W.relax[pass_of<DYN>(P, seq) & 1];
     bool bars_live = false;
 
     for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
@@ -582,11 +591,11 @@ __device__ __forceinline__ int jacobi_pass_body(const CUtensorMap& map_p0, const
         bars_live = true;
         if (tid < T) s_cnt[tid] = 0;
         __syncthreads();
-        const int brick = P.pass == 0 ? work : list_in[work];
+        const int brick = pass_of<DYN>(P, seq) == 0 ? work : list_in[work];
         const int tx = brick % P.ntx, ty = (brick / P.ntx) % P.nty, zc_idx = brick / (P.ntx * P.nty);
         const int zs = P.z_out0 + zc_idx * P.bz;
-        relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, brick, tx, ty, zs, min(zs + P.bz, P.z_out1),
-                       levels, s0);
+        relax_brick<S, DYN>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, brick, tx, ty, zs, min(zs + P.bz, P.z_out1),
+                            levels, s0, seq);
     }
 
     // Multi-GPU: the pressure halo is exchanged only every few passes, deep enough that in between the planes next
@@ -618,7 +627,8 @@ __device__ __forceinline__ int jacobi_pass_body(const CUtensorMap& map_p0, const
             zs = P.z_out1 + (chunk - lo_chunks) * P.bz;
             ze = min(zs + P.bz, P.z_out1 + P.ext_hi);
         }
-        relax_brick<S>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, -1, tile % P.ntx, tile / P.ntx, zs, ze, levels, s0);
+        relax_brick<S, DYN>(map_in, &map_rhs, p_out, m_in, m_out, state, W, P, -1, tile % P.ntx, tile / P.ntx, zs, ze, levels,
+                            s0, seq);
     }
     return levels;
 }
@@ -638,9 +648,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     } else {
         const int seq = state->seq, s0 = state->sweeps_done;
         if (s0 != P.pass * S::T) return;
-        PassParams Q = P;
-        Q.pass = seq;
-        const int levels = jacobi_pass_body<S>(map_p0, map_p1, map_rhs, frame, state, p0, p1, m0, m1, W, Q, s0);
+        const int levels = jacobi_pass_body<S, true>(map_p0, map_p1, map_rhs, frame, state, p0, p1, m0, m1, W, P, s0, seq);
         if (levels == 0) return;
         // the last CTA to finish advances the shared schedule (every CTA has read it long before)
         __syncthreads();
