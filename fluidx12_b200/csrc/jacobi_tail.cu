@@ -62,9 +62,8 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
     const int n_relax = L.first ? L.nbricks : L.relax_count[seq], n_copy = L.first ? 0 : L.copy_count[seq];
     if (!L.first && L.threshold >= 0 && n_relax > L.threshold) return;  // too many bricks: the bulk kernel is the better tool
 
-    TailParams P = L.P;
-    P.levels = min(S::TT, L.iters - s0);
-    P.first = L.first;
+    const TailParams& P = L.P;  // stays in the constant bank; only the sweep count is a run-time value
+    const int levels = min(S::TT, L.iters - s0);
     const int sel = (p_cur + seq) & 1;
     const float* p_in = sel ? p1 : p0;
     float* p_out = sel ? p0 : p1;
@@ -106,7 +105,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
         const int r = item - n_copy;
         const int path = tail_run_item<S, DENSE>(tid, sh, P, W, L.first ? r / P.nsub : W.relax_in[r / P.nsub], r % P.nsub,
                                                  p_in, p_out, rhs, m_in, m_out,
-                                                 state->active_after + s0, state->active_after + 64, tma);
+                                                 state->active_after + s0, state->active_after + 64, tma, levels);
         if (tid == 0 && path != 0) {
             ++relaxed;
             if (path == 2) ++dense;
@@ -122,7 +121,7 @@ jacobi_tail_kernel(const FrameParams* __restrict__ frame, StepState* __restrict_
         if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
             state->done_ctas = 0;
             state->seq = seq + 1;
-            state->sweeps_done = s0 + P.levels;
+            state->sweeps_done = s0 + levels;
             state->tail_launches += 1;
             state->tail_bricks += (unsigned long long)n_relax;
             state->bricks_processed += (unsigned long long)n_relax;  // one HBM pass of the brick, like a bulk pass
@@ -163,7 +162,7 @@ TailLaunch tail_launch_params(const FusedJacobi& J, const Domain& d, int iters, 
     L.P.bx = ext[0]; L.P.by = ext[1]; L.P.bz = ext[2];
     L.P.ntx = J.ntx; L.P.nty = J.nty;
     L.P.nsub = ext[0] / TailS::OX;  // TailP0 has the same sub-block width
-    L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = 0;
+    L.P.first = 0; L.P.early_exit = early_exit; L.P.levels = 0;  // (levels: computed on the device)
     L.P.sparse_cap = 0;
     L.P.cp_async = J.tail_cp_async == 2 ? (J.win_maps ? 2 : 1) : (J.tail_cp_async ? 1 : 0);
     L.P.dense_mode = J.tail_dense_mode == 2 ? 2 : 1;
@@ -225,6 +224,7 @@ cudaError_t launch_jacobi_pass0_tail(const FusedJacobi& J, const Domain& d, cons
     L.P.dense_mode = 2;
     if (L.P.cp_async == 2) L.P.cp_async = 1;  // the window maps are built for the 4-sweep shape only
     L.first = 1;
+    L.P.first = 1;
     const int items = L.nbricks * L.P.nsub;
     const int slots = J.num_sms * 12;  // three CTAs per SM resident; a few rounds per launch keep the tail short
     jacobi_tail_kernel<TailP0, 2><<<items < slots ? items : slots, TailP0::kThreads, TailP0::kBytes, stream>>>(

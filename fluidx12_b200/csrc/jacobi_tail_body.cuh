@@ -203,7 +203,7 @@ struct TailParams {
     int nsub;            // sub-blocks per brick in x
     int first;           // 1: no flags exist yet (first kernel of a frame): every cell is active
     int early_exit;
-    int levels;          // sweeps to apply (<= TT)
+    int levels;          // sweeps to apply (<= TT); the CUDA kernel passes the run-time value separately
     int sparse_cap;      // windows with at most this many relaxable active cells take the sparse path (<= kListCap)
     int cp_async;        // window staging: 0 through registers; 1 cp.async, requested together with the flags; 2 TMA box copy
     int dense_mode;      // crowded windows: 1 = register z-columns, 2 = two-phase update of all quads (side array)
@@ -849,10 +849,10 @@ struct TailWork {
 // ---- after the last phase of a relax item (one thread): histogram, and the brick's entry in the next lists --------
 template <class S>
 FXT_FN void tail_finish_item(const TailShared<S>& sh, const TailParams& P, const TailWork& W, int brick,
-                             unsigned long long* active_after_s0) {
-    for (int l = 0; l < P.levels; ++l)
+                             unsigned long long* active_after_s0, const int levels) {
+    for (int l = 0; l < levels; ++l)
         if (sh.ctrl[1 + l]) FXT_ATOMIC_ADD_U64(&active_after_s0[l], (unsigned long long)sh.ctrl[1 + l]);
-    const bool active = sh.ctrl[P.levels] != 0u;
+    const bool active = sh.ctrl[levels] != 0u;
     const int old = FXT_ATOMIC_ADD_I32(&W.brick_state[brick], 1 + (active ? 256 : 0));
     if ((old & 255) == P.nsub - 1) {  // last sub-block of the brick: all votes are in
         W.brick_state[brick] = 0;
@@ -887,7 +887,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
                          const int sub, const float* __restrict__ p_in, float* __restrict__ p_out,
                          const float* __restrict__ rhs, const unsigned char* __restrict__ m_in,
                          unsigned char* __restrict__ m_out, unsigned long long* active_after_s0,
-                         unsigned long long* marks, TailTma& tma) {
+                         unsigned long long* marks, TailTma& tma, const int levels) {
     const TailItem<S> it = tail_item<S>(P, brick, sub);
     FXT_THREAD_STATE(S);
     FXT_MARK_BEGIN();
@@ -908,7 +908,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
         FXT_MARK(1);
         const int n_list = (int)sh.ctrl[S::kCtrlTotal];
         if (sh.ctrl[0] == 0u) {  // nothing active in the own region: the output equals the input
-            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));  // (its atomics overlap the copy)
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0, levels));  // (its atomics overlap the copy)
             FXT_PHASE(tail_phase_copy<S>(t, sh, it, P, p_in, p_out, m_out));
             FXT_MARK(6);
         } else if (n_list <= P.sparse_cap) {  // relax a compacted list of the active cells
@@ -922,7 +922,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_PHASE(tail_sparse_gather<S>(tid, sh, it, P, rhs, n_list));
             FXT_SYNC();
             FXT_MARK(4);
-            for (int s = 1; s <= P.levels; ++s) {
+            for (int s = 1; s <= levels; ++s) {
                 FXT_PHASE(tail_sparse_relax<S>(tid, sh, it, P, n_list, s));
                 FXT_SYNC();
                 FXT_PHASE(tail_sparse_commit<S>(tid, sh, n_list, s));
@@ -931,7 +931,7 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_MARK(5);
             // the counters are final: thread 0 starts the brick's bookkeeping (two dependent atomics) while the other
             // warps store the result
-            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0, levels));
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
             FXT_MARK(6);
         } else if (DENSE == 2 || (DENSE == 0 && P.dense_mode == 2)) {  // crowded window: two-phase update of all quads
@@ -939,14 +939,14 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_PHASE(tail_sparse_build<S>(tid, t, sh, it, P, p_in, false); tail_dense2_load_rhs<S>(tid, t, it, P, rhs));
             FXT_SYNC();
             FXT_MARK(3);
-            for (int s = 1; s <= P.levels; ++s) {
+            for (int s = 1; s <= levels; ++s) {
                 FXT_PHASE(tail_dense2_relax<S>(tid, t, sh, it, P, s));
                 FXT_SYNC();
                 FXT_PHASE(tail_dense2_commit<S>(tid, sh, it, s));
                 FXT_SYNC();
             }
             FXT_MARK(5);
-            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0, levels));
             FXT_PHASE(tail_sparse_store<S>(t, sh, it, P, p_out, m_out));
             FXT_MARK(6);
         } else {  // crowded window: register columns
@@ -954,21 +954,21 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_PHASE(tail_phase_load<S>(t, sh, it, P, p_in, rhs));
             FXT_SYNC();
             FXT_MARK(3);
-            for (int s = 1; s <= P.levels; ++s) {
+            for (int s = 1; s <= levels; ++s) {
                 FXT_PHASE(tail_phase_relax<S>(t, sh, it, P, s));
                 FXT_SYNC();
-                FXT_PHASE(tail_phase_publish<S>(t, sh, s, s == P.levels));
+                FXT_PHASE(tail_phase_publish<S>(t, sh, s, s == levels));
                 FXT_SYNC();
             }
             FXT_MARK(5);
-            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));
+            FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0, levels));
             FXT_PHASE(tail_phase_store<S>(t, sh, it, P, p_out));
             FXT_SYNC();
             FXT_PHASE(tail_phase_store_mask<S>(t, sh, it, P, m_out));
             FXT_MARK(6);
         }
     } else {
-        FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0));  // an empty sub-block (outside the grid) still casts its brick's vote
+        FXT_PHASE(if (tid == 0) tail_finish_item<S>(sh, P, W, brick, active_after_s0, levels));  // an empty sub-block (outside the grid) still casts its brick's vote
     }
     FXT_MARK(7);
     FXT_MARK_END(marks, path);

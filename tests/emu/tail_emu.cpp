@@ -31,7 +31,7 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
     TailEmu<S> emu;
     emu.descending = g_descending;
     TailTma tma;
-    const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0, nullptr, tma);
+    const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0, nullptr, tma, P.levels);
     ++g_paths[path];
 }
 
