@@ -416,12 +416,18 @@ FXT_FN void tail_phase_copy(TailThread<S>& t, const TailShared<S>& sh, const Tai
     if (!t.own_xy) return;
     const int nxb = P.nx >> 3;
     Quad q[S::OZ];  // all loads in flight before the first store (planes past the end re-read the first one)
+    if (P.cp_async) {  // the window is already in shared memory
 #pragma unroll
-    for (int z = S::TT; z < S::TT + S::OZ; ++z) {
-        const int zz = z - S::TT < it.ez ? z : S::TT;
-        q[z - S::TT] = P.cp_async  // cp.async mode: the window is already in shared memory
-                           ? *reinterpret_cast<const Quad*>(sh.p + zz * S::kPlane + t.y * S::LX + 4 * t.qx)
-                           : *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + zz) * P.ny + t.gy) * P.nx + t.gx);
+        for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+            const int zz = z - S::TT < it.ez ? z : S::TT;
+            q[z - S::TT] = *reinterpret_cast<const Quad*>(sh.p + zz * S::kPlane + t.y * S::LX + 4 * t.qx);
+        }
+    } else {
+#pragma unroll
+        for (int z = S::TT; z < S::TT + S::OZ; ++z) {
+            const int zz = z - S::TT < it.ez ? z : S::TT;
+            q[z - S::TT] = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + zz) * P.ny + t.gy) * P.nx + t.gx);
+        }
     }
 #pragma unroll
     for (int z = S::TT; z < S::TT + S::OZ; ++z) {
@@ -438,17 +444,22 @@ FXT_FN void tail_phase_load(TailThread<S>& t, const TailShared<S>& sh, const Tai
                             const float* __restrict__ p_in, const float* __restrict__ rhs) {
     if (!t.used) return;
     const Quad zero = {0.f, 0.f, 0.f, 0.f};
+    if (P.cp_async) {  // the flags phase has staged the window: only the register copy is missing
 #pragma unroll
-    for (int z = 0; z < S::LZ; ++z) {
-        if (P.cp_async) {  // the flags phase has staged the window: only the register copy is missing
+        for (int z = 0; z < S::LZ; ++z)
             t.v[z] = *reinterpret_cast<const Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx);
-            continue;
+    } else {  // (the mode test stays outside the loop so that the sixteen loads are issued back to back)
+#pragma unroll
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            t.v[z] = *reinterpret_cast<const Quad*>(in ? p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx : p_in);
         }
-        Quad q = zero;
-        if (t.in_xy && z >= it.zvl && z < it.zvh)
-            q = *reinterpret_cast<const Quad*>(p_in + ((size_t)(it.wz + z) * P.ny + t.gy) * P.nx + t.gx);
-        t.v[z] = q;
-        *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = q;
+#pragma unroll
+        for (int z = 0; z < S::LZ; ++z) {
+            const bool in = t.in_xy && z >= it.zvl && z < it.zvh;
+            if (!in) t.v[z] = zero;
+            *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + t.y * S::LX + 4 * t.qx) = t.v[z];
+        }
     }
     if (t.y >= 1 && t.y <= S::LY - 2) {
 #pragma unroll
