@@ -189,6 +189,7 @@ constexpr int kTailDepthShift = 14;        // 3 bits: sweeps for which the cell 
 constexpr unsigned kTailOwn = 1u << 17;     // the cell belongs to the CTA's output region
 constexpr unsigned kTailFresh = 1u << 18;   // a new value waits in the side array
 constexpr unsigned kTailFroze = 1u << 19;   // ... and the cell froze with it
+constexpr int kTailClampShift = 20;         // 6 bits: the L, R, U, D, F, B neighbour is the cell itself (grid face)
 constexpr unsigned kTailDead = 0xFFFFFFFFu;
 
 // What one launch needs to know (uniform over the grid).
@@ -620,8 +621,13 @@ FXT_FN void tail_sparse_build(int tid, TailThread<S>& t, const TailShared<S>& sh
             const int z = 8 * w + (bit >> 2), j = bit & 3;
             const bool own = t.own_xy && z >= S::TT && z - S::TT < it.ez;
             const int depth = tail_depth<S>(it, 4 * t.qx + j, t.y, z);
+            // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83), decided once per entry
+            const int gx = t.gx + j, gz = it.wz + z;
+            const unsigned clamp = (gx == 0 ? 1u : 0u) | (gx == P.nx - 1 ? 2u : 0u) | (t.gy == 0 ? 4u : 0u) |
+                                   (t.gy == P.ny - 1 ? 8u : 0u) | (gz == P.z_face_lo ? 16u : 0u) |
+                                   (gz == P.z_face_hi - 1 ? 32u : 0u);
             sh.list[at++] = (unsigned)(z * S::kPlane + t.y * S::LX + 4 * t.qx + j) | ((unsigned)depth << kTailDepthShift) |
-                            (own ? kTailOwn : 0u);
+                            (own ? kTailOwn : 0u) | (clamp << kTailClampShift);
         }
     }
 }
@@ -667,16 +673,15 @@ FXT_FN void tail_sparse_relax(int tid, const TailShared<S>& sh, const TailItem<S
             if (ent[u] == kTailDead) continue;
             const int e = base + u * S::kThreads;
             const int idx = (int)(ent[u] & kTailIdxMask);
-            const int z = idx / S::kPlane, r = idx - z * S::kPlane, y = r / S::LX, x = r - y * S::LX;
-            const int gx = it.wx + x, gy = it.wy + y, gz = it.wz + z;
+            const unsigned open_ = ~(ent[u] >> kTailClampShift);  // bit k set: neighbour k is a different cell
             const float c = sh.p[idx];
-            // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); elsewhere the neighbour is inside the window
-            const float l = gx == 0 ? c : sh.p[idx - 1];
-            const float rr = gx == P.nx - 1 ? c : sh.p[idx + 1];
-            const float up = gy == 0 ? c : sh.p[idx - S::LX];
-            const float dn = gy == P.ny - 1 ? c : sh.p[idx + S::LX];
-            const float f = gz == P.z_face_lo ? c : sh.p[idx - S::kPlane];
-            const float b = gz == P.z_face_hi - 1 ? c : sh.p[idx + S::kPlane];
+            // a clamped neighbour is the cell itself (offset 0); elsewhere the neighbour is inside the window
+            const float l = sh.p[idx - (int)(open_ & 1u)];
+            const float rr = sh.p[idx + (int)((open_ >> 1) & 1u)];
+            const float up = sh.p[idx - S::LX * (int)((open_ >> 2) & 1u)];
+            const float dn = sh.p[idx + S::LX * (int)((open_ >> 3) & 1u)];
+            const float f = sh.p[idx - S::kPlane * (int)((open_ >> 4) & 1u)];
+            const float b = sh.p[idx + S::kPlane * (int)((open_ >> 5) & 1u)];
             unsigned act = 1u;
             nv[u] = tail_cell(c, l, rr, up, dn, f, b, sh.rhsv[e], 1u, eps, act);
             ent[u] |= kTailFresh | (act ? 0u : kTailFroze);
