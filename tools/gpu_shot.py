@@ -124,6 +124,9 @@ def main():
     oracle_check(fx, "tail", {})
     oracle_check(fx, "tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}, n=(64, 64, 40), steps=4)
     timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_cap1024", {"FXB_TAIL_SPARSE_CAP": 1024}),
+                                          ("tail_cap2048", {"FXB_TAIL_SPARSE_CAP": 2048}),
+                                          ("tail_cap2048_dense2", {"FXB_TAIL_SPARSE_CAP": 2048, "FXB_TAIL_DENSE": 2}),
                                           ("tail_grid592", {"FXB_TAIL_GRID": 592}),
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1}),
                                           ("tail_thr8192_m5", {"FXB_TAIL_THRESHOLD": 8192, "FXB_TAIL_MAINS": 5}),
