@@ -133,6 +133,8 @@ def main():
                                           ("tail_cpasync", {"FXB_TAIL_CPASYNC": 1}),
                                           ("tail_tma", {"FXB_TAIL_CPASYNC": 2}),
                                           ("tail_dense2", {"FXB_TAIL_DENSE": 2}),
+                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_dense2_only_tma", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0, "FXB_TAIL_CPASYNC": 2}),
                                           ("tail_pass0", {"FXB_PASS0": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
                                           ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
