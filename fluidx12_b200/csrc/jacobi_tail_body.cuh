@@ -278,6 +278,7 @@ struct TailThread {
     bool in_xy;         // column lies inside the grid
     bool own_xy;        // column belongs to the output region
     Quad rq[S::kQuadsPerThread];  // second dense path: right-hand sides of the thread's quads (loaded once per item)
+    unsigned qinfo[S::kQuadsPerThread];  // ... and what the sweeps need to know about each of them (see kQuad* below)
     int nlist;          // active cells of the column that can be relaxed (sparse path: its list entries)
     unsigned okx;       // 0x11111111 * (4-bit mask of the column's cells that can be relaxed as far as x and y go)
 };
@@ -763,86 +764,89 @@ FXT_FN void tail_quad_coords(int q, int& z, int& y, int& qx) {
     qx = r - (y - 1) * S::LXQ;
 }
 
-// ---- right-hand sides of the thread's quads -> registers (all loads in flight; quads outside the grid read rhs[0..3]) --
+// Per-quad word computed once per item: quad index in the window (= index into the nibble array; x4 = float index),
+// the sweeps for which the quad is a valid output (its y/z distance to window edges that are not grid faces), which
+// neighbours are clamped to the cell itself (grid faces; for L/R also the window's x edges, whose cells are spoilt
+// anyway), whether the quad belongs to the output region, and whether the slot holds a quad at all.
+constexpr unsigned kQuadIdxMask = 0xFFFu;
+constexpr int kQuadDepthShift = 12, kQuadClampShift = 15;
+constexpr unsigned kQuadOwn = 1u << 21, kQuadValid = 1u << 22;
+
+// ---- right-hand sides of the thread's quads -> registers (all loads in flight; quads outside the grid read rhs[0..3]);
+// ---- the per-quad words ------------------------------------------------------------------------------------------------
 template <class S>
 FXT_FN void tail_dense2_load_rhs(int tid, TailThread<S>& t, const TailItem<S>& it, const TailParams& P,
                                  const float* __restrict__ rhs) {
+    static_assert(S::LZ * S::LY * S::LXQ <= 4096, "quad index field");
 #pragma unroll
     for (int k = 0; k < S::kQuadsPerThread; ++k) {
         const int q = tid + k * S::kThreads;
         int z, y, qx;
         tail_quad_coords<S>(q < S::kQuads ? q : 0, z, y, qx);
-        const int gx = it.wx + 4 * qx, gy = it.wy + y;
+        const int gx = it.wx + 4 * qx, gy = it.wy + y, gz = it.wz + z;
         const bool in = q < S::kQuads && gx >= 0 && gx < P.nx && gy >= 0 && gy < P.ny && z >= it.zvl && z < it.zvh;
-        t.rq[k] = *reinterpret_cast<const Quad*>(in ? rhs + ((size_t)(it.wz + z) * P.ny + gy) * P.nx + gx : rhs);
+        t.rq[k] = *reinterpret_cast<const Quad*>(in ? rhs + ((size_t)gz * P.ny + gy) * P.nx + gx : rhs);
+        const unsigned clamp = ((qx == 0 || gx == 0) ? 1u : 0u) | ((qx == S::LXQ - 1 || gx + 4 == P.nx) ? 2u : 0u) |
+                               (gy == 0 ? 4u : 0u) | (gy == P.ny - 1 ? 8u : 0u) | (gz == P.z_face_lo ? 16u : 0u) |
+                               (gz == P.z_face_hi - 1 ? 32u : 0u);
+        const bool own = qx >= 1 && 4 * (qx - 1) < it.ex && y >= S::TT && y - S::TT < it.ey && z >= S::TT && z - S::TT < it.ez;
+        const int depth = tail_depth<S>(it, S::TT, y, z);  // x = TT: no limit from the x edges (handled by the clamps)
+        t.qinfo[k] = (unsigned)((z * S::LY + y) * S::LXQ + qx) | ((unsigned)(depth < 0 ? 0 : depth) << kQuadDepthShift) |
+                     (clamp << kQuadClampShift) | (own ? kQuadOwn : 0u) | (in ? kQuadValid : 0u);
     }
-}
-
-// Is quad (z, y) relaxed in sweep s?  (the rows and planes that are still valid inputs, as in tail_phase_relax)
-template <class S>
-FXT_FN bool tail_dense2_in_range(const TailItem<S>& it, int z, int y, int s) {
-    const int yc0 = it.ylo_face ? it.yvl : it.yvl + s, yc1 = it.yhi_face ? it.yvh : it.yvh - s;
-    const int zc0 = it.zlo_face ? it.zvl : it.zvl + s, zc1 = it.zhi_face ? it.zvh : it.zvh - s;
-    return y >= yc0 && y < yc1 && z >= zc0 && z < zc1;
 }
 
 // ---- phase A of sweep s: new values of the thread's quads -> side array; new flags -> high nibble of the flag byte ---
 template <class S>
-FXT_FN void tail_dense2_relax(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailItem<S>& it,
-                              const TailParams& P, int s) {
+FXT_FN void tail_dense2_relax(int tid, TailThread<S>& t, const TailShared<S>& sh, const TailParams& P, int s) {
     const float eps = P.early_exit ? kTailEps : -1.0f;
     Quad* side = reinterpret_cast<Quad*>(sh.rhs);
-#pragma unroll
+    // not unrolled: the per-quad words and right-hand sides are indexed at run time (they live in local memory, which
+    // L1 serves), in exchange the loop body keeps its temporaries in registers
+#pragma unroll 1
     for (int k = 0; k < S::kQuadsPerThread; ++k) {
-        const int q = tid + k * S::kThreads;
-        if (q >= S::kQuads) continue;
-        int z, y, qx;
-        tail_quad_coords<S>(q, z, y, qx);
-        const int nb = (z * S::LY + y) * S::LXQ + qx;
+        const unsigned info = t.qinfo[k];
+        if (!(info & kQuadValid) || (int)((info >> kQuadDepthShift) & 7u) < s) continue;
+        const int nb = (int)(info & kQuadIdxMask);
         unsigned a = sh.nib[nb] & 0xFu;
-        if (a == 0u || !tail_dense2_in_range<S>(it, z, y, s)) continue;
-        const int gx = it.wx + 4 * qx, gy = it.wy + y, gz = it.wz + z;
-        const float* pl = sh.p + z * S::kPlane;
-        const int col = y * S::LX + 4 * qx;
-        const Quad c = *reinterpret_cast<const Quad*>(pl + col);
-        // clamp-to-edge at the grid faces (CSProject3D.hlsl:76-83); at a window edge that is not a face the cell is
-        // its own neighbour, which only spoils cells that are no longer valid anyway
-        const Quad u = *reinterpret_cast<const Quad*>(pl + (gy == 0 ? col : col - S::LX));
-        const Quad d = *reinterpret_cast<const Quad*>(pl + (gy == P.ny - 1 ? col : col + S::LX));
-        const Quad f = *reinterpret_cast<const Quad*>(gz == P.z_face_lo ? pl + col : pl - S::kPlane + col);
-        const Quad b = *reinterpret_cast<const Quad*>(gz == P.z_face_hi - 1 ? pl + col : pl + S::kPlane + col);
-        const float left = (qx == 0 || gx == 0) ? c.x : pl[col - 1];
-        const float right = (qx == S::LXQ - 1 || gx + 4 == P.nx) ? c.w : pl[col + 4];
+        if (a == 0u) continue;
+        const unsigned open_ = ~(info >> kQuadClampShift);  // bit k set: neighbour k is a different cell
+        const float* pc = sh.p + 4 * nb;
+        const Quad c = *reinterpret_cast<const Quad*>(pc);
+        // a clamped neighbour is the cell itself: offset 0 (CSProject3D.hlsl:76-83)
+        const Quad u = *reinterpret_cast<const Quad*>(pc - S::LX * (int)((open_ >> 2) & 1u));
+        const Quad d = *reinterpret_cast<const Quad*>(pc + S::LX * (int)((open_ >> 3) & 1u));
+        const Quad f = *reinterpret_cast<const Quad*>(pc - S::kPlane * (int)((open_ >> 4) & 1u));
+        const Quad b = *reinterpret_cast<const Quad*>(pc + S::kPlane * (int)((open_ >> 5) & 1u));
+        const float left = pc[-(int)(open_ & 1u)];
+        const float right = pc[3 + (int)((open_ >> 1) & 1u)];
         const Quad r = t.rq[k];
         Quad n;
         n.x = tail_cell(c.x, left, c.y, u.x, d.x, f.x, b.x, r.x, 1u, eps, a);
         n.y = tail_cell(c.y, c.x, c.z, u.y, d.y, f.y, b.y, r.y, 2u, eps, a);
         n.z = tail_cell(c.z, c.y, c.w, u.z, d.z, f.z, b.z, r.z, 4u, eps, a);
         n.w = tail_cell(c.w, c.z, right, u.w, d.w, f.w, b.w, r.w, 8u, eps, a);
-        side[q] = n;
+        side[tid + k * S::kThreads] = n;
         sh.nib[nb] = (unsigned char)((sh.nib[nb] & 0xFu) | (a << 4));  // old flags stay in the low nibble until the commit
     }
 }
 
 // ---- phase B of sweep s: commit the quads relaxed in phase A, count the own cells that are still active -------------
 template <class S>
-FXT_FN void tail_dense2_commit(int tid, const TailShared<S>& sh, const TailItem<S>& it, int s) {
+FXT_FN void tail_dense2_commit(int tid, TailThread<S>& t, const TailShared<S>& sh, int s) {
     const Quad* side = reinterpret_cast<const Quad*>(sh.rhs);
     unsigned live = 0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < S::kQuadsPerThread; ++k) {
-        const int q = tid + k * S::kThreads;
-        if (q >= S::kQuads) continue;
-        int z, y, qx;
-        tail_quad_coords<S>(q, z, y, qx);
-        const int nb = (z * S::LY + y) * S::LXQ + qx;
+        const unsigned info = t.qinfo[k];
+        if (!(info & kQuadValid)) continue;
+        const int nb = (int)(info & kQuadIdxMask);
         const unsigned byte = sh.nib[nb];
-        const bool own = qx >= 1 && 4 * (qx - 1) < it.ex && y >= S::TT && y - S::TT < it.ey && z >= S::TT && z - S::TT < it.ez;
-        if ((byte & 0xFu) != 0u && tail_dense2_in_range<S>(it, z, y, s)) {  // the same predicate as in phase A
-            *reinterpret_cast<Quad*>(sh.p + z * S::kPlane + y * S::LX + 4 * qx) = side[q];
+        if ((byte & 0xFu) != 0u && (int)((info >> kQuadDepthShift) & 7u) >= s) {  // the same predicate as in phase A
+            *reinterpret_cast<Quad*>(sh.p + 4 * nb) = side[tid + k * S::kThreads];
             sh.nib[nb] = (unsigned char)(byte >> 4);
-            if (own) live += FXT_POPC(byte >> 4);
-        } else if (own) {
+            if (info & kQuadOwn) live += FXT_POPC(byte >> 4);
+        } else if (info & kQuadOwn) {
             live += FXT_POPC(byte & 0xFu);
         }
     }
@@ -956,9 +960,9 @@ FXT_FN int tail_run_item(FXT_CTX(S), const TailShared<S>& sh, const TailParams& 
             FXT_SYNC();
             FXT_MARK(3);
             for (int s = 1; s <= levels; ++s) {
-                FXT_PHASE(tail_dense2_relax<S>(tid, t, sh, it, P, s));
+                FXT_PHASE(tail_dense2_relax<S>(tid, t, sh, P, s));
                 FXT_SYNC();
-                FXT_PHASE(tail_dense2_commit<S>(tid, sh, it, s));
+                FXT_PHASE(tail_dense2_commit<S>(tid, t, sh, s));
                 FXT_SYNC();
             }
             FXT_MARK(5);
