@@ -1,0 +1,124 @@
+"""bench.py's host-side helpers that need no GPU: the child-process runner of the experiments stage (own process
+group, hard time limit), the parsing of what the children report, and the state checksum."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_run_child_returns_output_and_kills_its_group_on_timeout(tmp_path):
+    rc, out = bench.run_child([sys.executable, "-c", "print('hello')"], dict(os.environ), 30)
+    assert rc == 0 and "hello" in out
+    # a child that starts a grandchild and hangs: both must be gone after the limit
+    marker = tmp_path / "alive"
+    grandchild = tmp_path / "grandchild.py"
+    grandchild.write_text("import time\nwhile True:\n    open(%r, 'w').write(str(time.time()))\n    time.sleep(0.05)\n" % str(marker))
+    child = tmp_path / "child.py"
+    child.write_text("import subprocess, sys, time\nsubprocess.Popen([sys.executable, %r])\ntime.sleep(60)\n" % str(grandchild))
+    t0 = time.time()
+    rc, out = bench.run_child([sys.executable, str(child)], dict(os.environ), 1.5)
+    assert rc is None and time.time() - t0 < 10
+    assert marker.exists(), "the grandchild never ran"
+    time.sleep(0.3)
+    stamp = marker.read_text()
+    time.sleep(0.4)
+    assert marker.read_text() == stamp, "the grandchild is still running"
+
+
+def test_child_env_drops_the_launcher_variables(monkeypatch):
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("MASTER_PORT", "1234")
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", "x")
+    monkeypatch.setenv("FXB_KEEP", "1")
+    env = bench.child_env({"FXB_P2P": 1})
+    assert "RANK" not in env and "MASTER_PORT" not in env and "TORCHELASTIC_RUN_ID" not in env
+    assert env["FXB_KEEP"] == "1" and env["FXB_P2P"] == "1"
+
+
+def test_single_gpu_experiments_are_summarised_from_the_childs_records(monkeypatch):
+    rows = [
+        {"stage": "import"},
+        {"stage": "timing", "grid": [256, 256, 256], "default": 1.49, "default_phases": {"jacobi": 1.18, "advect": 0.29}},
+        {"stage": "timing", "grid": [256, 256, 256], "variant": "tail", "ms": 1.40, "phases": {"jacobi": 1.0, "advect": 0.29},
+         "tail": {"tail_launches_last_step": 13}, "passes": 17, "s_exec": 64,
+         "mismatch_vs_default": {"0": 0, "1": 0, "2": 0}},
+        {"stage": "timing", "grid": [256, 256, 256], "variant": "broken", "error": "RuntimeError('x')"},
+    ]
+
+    def fake(cmd, env, timeout_s):
+        assert cmd[-1] == "--bench" and "FXB_SHOT_OUT" in env
+        with open(env["FXB_SHOT_OUT"], "w") as fh:
+            fh.write("".join(json.dumps(r) + "\n" for r in rows))
+        return 0, ""
+
+    monkeypatch.setattr(bench, "run_child", fake)
+    res = bench.experiments_single_gpu(5)
+    assert res["exit"] == 0 and len(res["results"]) == 3
+    d, t, b = res["results"]
+    assert d == {"grid": "256x256x256", "variant": "default", "ms_per_step": 1.49, "jacobi_ms": 1.18, "advect_ms": 0.29}
+    assert t["variant"] == "tail" and t["mismatched_elements_vs_default"] == 0 and t["tail_launches"] == 13
+    assert b["variant"] == "broken" and "error" in b
+
+
+def test_multi_gpu_experiments_compare_state_checksums(monkeypatch):
+    calls = []
+
+    def fake(cmd, env, timeout_s):
+        calls.append((cmd, env))
+        assert "--no-experiments" in cmd and "--checksum" in cmd and cmd[cmd.index("--nproc-per-node") + 1] == "4"
+        if env.get("FXB_TAIL") == "1" and "FXB_P2P" not in env:
+            return None, "hung"
+        line = {"metric": "voxel_updates_per_s", "ms_per_step": 8.0 if "FXB_P2P" not in env else 5.0, "value": 1.0,
+                "phase_ms": {"halo": 0.0, "jacobi": 3.0},
+                "state_checksum": 77 if env.get("FXB_TAIL") != "1" else 78}
+        return 0, "noise\n[rank0]: " + json.dumps(line) + "\n"
+
+    monkeypatch.setattr(bench, "run_child", fake)
+    monkeypatch.setenv("MASTER_PORT", "29500")
+
+    class A:
+        grid = None
+
+    res = bench.experiments_multi_gpu(A(), 4, 120.0)["results"]
+    assert [r["variant"] for r in res] == ["default", "p2p_halos", "tail_p2p", "tail"]
+    assert res[0]["state_equals_default_variant"] is True and res[1]["state_equals_default_variant"] is True
+    assert res[1]["ms_per_step"] == 5.0
+    assert res[2]["state_equals_default_variant"] is False
+    assert res[3]["error"] == "timeout"
+    ports = [c[0][c[0].index("--master-port") + 1] for c in calls]
+    assert len(set(ports)) == 4 and "29500" not in ports
+
+
+def test_state_checksum_sees_a_moved_or_changed_word():
+    class FX:
+        FIELD_VELOCITY, FIELD_COLOR, FIELD_PRESSURE = 0, 1, 2
+
+    class F:
+        slab = (4, 3)
+
+        def __init__(self, seed, tweak=None):
+            r = np.random.default_rng(seed)
+            self.a = {0: r.standard_normal((3, 5, 8, 4)).astype(np.float16),
+                      1: r.standard_normal((3, 5, 8, 4)).astype(np.float16),
+                      2: r.standard_normal((3, 5, 8)).astype(np.float32)}
+            if tweak == "w":
+                self.a[0][..., 3] = 9.0   # velocity .w is a don't-care
+            if tweak == "bit":
+                self.a[2].view(np.uint32)[1, 2, 3] ^= 1
+            if tweak == "swap":
+                self.a[1][[0, 1]] = self.a[1][[1, 0]]
+
+        def get_field(self, fld):
+            return self.a[fld]
+
+    base = bench.state_checksum(None, None, F(1), FX, 1)
+    assert base == bench.state_checksum(None, None, F(1, "w"), FX, 1)
+    assert base != bench.state_checksum(None, None, F(1, "bit"), FX, 1)
+    assert base != bench.state_checksum(None, None, F(1, "swap"), FX, 1)
+    assert 0 <= base < 1 << 62

@@ -12,7 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-OUT = os.path.join(ROOT, "gpurun_out", "shot.jsonl")
+OUT = os.environ.get("FXB_SHOT_OUT") or os.path.join(ROOT, "gpurun_out", "shot.jsonl")
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 T0 = time.time()
 
@@ -118,9 +118,31 @@ def timing(fx, n, spin, steps, variants, all_fields=False):
             emit(stage="timing", grid=n, variant=label, error=repr(e))
 
 
+def bench_mode(fx):
+    """The short list bench.py runs (in a child process, after its own measurement) so that every default bench run
+    also times the opt-in variants: most informative first, nothing that can spin on the device (no TMA-staged
+    window), every variant compared bit for bit with the default schedule's fields (the oracle is not used here)."""
+    timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
+                                          ("tail_advect2", {"FXB_ADVECT": 2}),
+                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_cap2048_dense2", {"FXB_TAIL_SPARSE_CAP": 2048, "FXB_TAIL_DENSE": 2}),
+                                          ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_cpasync", {"FXB_TAIL_CPASYNC": 1}),
+                                          ("tail_pass0", {"FXB_PASS0": 2}),
+                                          ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
+                                          ("tail_mains1", {"FXB_TAIL_MAINS": 1})], all_fields=True)
+    timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
+                                          ("tail_advect2", {"FXB_ADVECT": 2}),
+                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_pass0", {"FXB_PASS0": 2})], all_fields=True)
+    emit(stage="done")
+
+
 def main():
     import fluidx12_b200 as fx
     emit(stage="import")
+    if "--bench" in sys.argv:
+        return bench_mode(fx)
     oracle_check(fx, "tail", {})
     oracle_check(fx, "tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}, n=(64, 64, 40), steps=4)
     timing(fx, (256, 256, 256), 100, 40, [("tail", {}), ("tail_dense_only", {"FXB_TAIL_SPARSE_CAP": 0}),
