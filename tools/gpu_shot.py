@@ -133,8 +133,8 @@ def bench_mode(fx):
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1})], all_fields=True)
     timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
-                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0}),
-                                          ("tail_pass0", {"FXB_PASS0": 2})], all_fields=True)
+                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0})],
+           all_fields=True)
     emit(stage="done")
 
 
