@@ -19,15 +19,17 @@ from .binding import (  # noqa: F401
     FluidError,
     FxbConfig,
     FxbStats,
+    FxbVolumeHeader,
     dt_for_grid,
     lib,
     lib_path,
 )
 from .fluid import Fluid, FluidEZ  # noqa: F401
 from .slab import slab_range, halo_plan  # noqa: F401
+from . import volume  # noqa: F401
 
 __all__ = [
-    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan",
+    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
     "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV",
 ]

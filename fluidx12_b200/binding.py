@@ -10,13 +10,14 @@ _LIB_NAME = "libfluidx_b200.so"
 ADDRESS_MIRROR, ADDRESS_CLAMP = 0, 1
 FIELD_VELOCITY, FIELD_COLOR, FIELD_PRESSURE, FIELD_VELOCITY_ADVECTED, FIELD_COLOR_PREV = range(5)
 
-FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_OVERFLOW = 0, -1, -2, -3, -4, -5
+FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_OVERFLOW, FXB_ERR_IO = 0, -1, -2, -3, -4, -5, -6
 
 # Every symbol include/fluidx_b200.h declares (tests check the library exports exactly these).
 EXPORTS = (
     "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
     "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+    "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
 )
 
 
@@ -64,6 +65,23 @@ class FxbStats(C.Structure):
     ]
 
 
+class FxbVolumeHeader(C.Structure):
+    """fxb_volume_header: the 64-byte header of a volume file (include/fluidx_b200.h)."""
+    _fields_ = [
+        ("magic", C.c_char * 4),
+        ("version", C.c_uint32),
+        ("nx", C.c_uint32), ("ny", C.c_uint32), ("nz", C.c_uint32),
+        ("z0", C.c_uint32), ("nz_local", C.c_uint32),
+        ("field", C.c_uint32),
+        ("format", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("frame", C.c_uint64),
+        ("dt", C.c_float),
+        ("frame_parity", C.c_uint32),
+        ("payload_bytes", C.c_uint64),
+    ]
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, _LIB_NAME)
 
@@ -101,6 +119,10 @@ def lib() -> C.CDLL:
         L.fxb_get_freeze_histogram.argtypes = [vp, vp, C.c_int]
         L.fxb_profile_step.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
         L.fxb_nccl_unique_id.argtypes = [vp]
+        L.fxb_volume_write.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader), vp]
+        L.fxb_volume_read_header.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader)]
+        L.fxb_volume_read.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader), vp, C.c_size_t]
+        L.fxb_export_field.argtypes = [vp, C.c_int, C.c_char_p]
         L.fxb_last_error.restype = C.c_char_p
         L.fxb_abi_version.restype = C.c_int
         _lib = L

@@ -807,6 +807,91 @@ int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t
     return FXB_OK;
 }
 
+// ---- volume files (include/fluidx_b200.h: the renderer hand-off format) --------------------------
+namespace {
+static_assert(sizeof(fxb_volume_header) == 64, "fxb_volume_header is a 64-byte wire structure");
+
+int check_volume_header(const fxb_volume_header& h, const char* who) {
+    const std::string w(who);
+    if (memcmp(h.magic, FXB_VOLUME_MAGIC, 4) != 0) return fail(FXB_ERR_IO, w + ": not a volume file (magic)");
+    if (h.version != FXB_VOLUME_VERSION) return fail(FXB_ERR_IO, w + ": unsupported volume file version");
+    if (h.format != 1 && h.format != 2) return fail(FXB_ERR_IO, w + ": unknown element format");
+    if (h.nx == 0 || h.ny == 0 || h.nz == 0 || h.nz_local == 0 || (uint64_t)h.z0 + h.nz_local > h.nz)
+        return fail(FXB_ERR_IO, w + ": bad grid / slab extent");
+    if (h.field > FXB_FIELD_COLOR_PREV || (h.format == 2) != (h.field == FXB_FIELD_PRESSURE))
+        return fail(FXB_ERR_IO, w + ": field and element format do not match");
+    if (h.payload_bytes != (uint64_t)h.nx * h.ny * h.nz_local * (h.format == 1 ? 8u : 4u))
+        return fail(FXB_ERR_IO, w + ": payload size does not match the extent");
+    return FXB_OK;
+}
+}  // namespace
+
+int fxb_volume_write(const char* path, const fxb_volume_header* hdr, const void* data) {
+    if (!path || !*path || !hdr || !data) return fail(FXB_ERR_INVALID, "fxb_volume_write: null argument");
+    fxb_volume_header h = *hdr;
+    memcpy(h.magic, FXB_VOLUME_MAGIC, 4);
+    h.version = FXB_VOLUME_VERSION;
+    if (const int rc = check_volume_header(h, "fxb_volume_write")) return rc == FXB_ERR_IO ? FXB_ERR_INVALID : rc;
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return fail(FXB_ERR_IO, "fxb_volume_write: cannot create " + tmp);
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(data, 1, h.payload_bytes, fp) == h.payload_bytes;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return fail(FXB_ERR_IO, std::string("fxb_volume_write: writing ") + path + " failed");
+    }
+    return FXB_OK;
+}
+
+int fxb_volume_read_header(const char* path, fxb_volume_header* out) {
+    if (!path || !out) return fail(FXB_ERR_INVALID, "fxb_volume_read_header: null argument");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read_header: cannot open ") + path);
+    const bool ok = fread(out, sizeof *out, 1, fp) == 1;
+    fclose(fp);
+    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read_header: file shorter than a header");
+    return check_volume_header(*out, "fxb_volume_read_header");
+}
+
+int fxb_volume_read(const char* path, fxb_volume_header* out, void* data, size_t capacity) {
+    if (!data) return fail(FXB_ERR_INVALID, "fxb_volume_read: null argument");
+    if (const int rc = fxb_volume_read_header(path, out)) return rc;
+    if (capacity < out->payload_bytes) return fail(FXB_ERR_SIZE, "fxb_volume_read: buffer smaller than the payload");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read: cannot open ") + path);
+    bool ok = fseek(fp, (long)sizeof *out, SEEK_SET) == 0 && fread(data, 1, out->payload_bytes, fp) == out->payload_bytes;
+    ok = ok && fgetc(fp) == EOF;  // nothing may follow the payload
+    fclose(fp);
+    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read: payload truncated or followed by extra bytes");
+    return FXB_OK;
+}
+
+int fxb_export_field(fxb_sim* s, int field, const char* path) {
+    if (!s || !path) return fail(FXB_ERR_INVALID, "fxb_export_field: null argument");
+    size_t eb; int err;
+    if (!field_device_ptr(s, field, &eb, &err)) return fail(err, "fxb_export_field: bad field");
+    fxb_volume_header h = {};
+    h.nx = s->cfg.nx; h.ny = s->cfg.ny; h.nz = s->cfg.nz;
+    h.z0 = (uint32_t)s->dom.z_own0;
+    h.nz_local = (uint32_t)(s->dom.z_own1 - s->dom.z_own0);
+    h.field = (uint32_t)field;
+    h.format = eb == 8 ? 1u : 2u;
+    h.flags = (field == FXB_FIELD_COLOR || field == FXB_FIELD_COLOR_PREV) ? FXB_VOLUME_FLAG_PREMULTIPLIED : 0u;
+    h.frame = s->steps;
+    h.dt = s->dt;
+    h.frame_parity = (uint32_t)s->parity;
+    h.payload_bytes = (uint64_t)s->own_voxels() * eb;
+    std::vector<char> host;
+    try {
+        host.resize(h.payload_bytes);
+    } catch (const std::bad_alloc&) {
+        return fail(FXB_ERR_IO, "fxb_export_field: no host memory for the staging buffer");
+    }
+    if (const int rc = fxb_get_field(s, field, host.data(), host.size())) return rc;
+    return fxb_volume_write(path, &h, host.data());
+}
+
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {
     if (!out6 || nx == 0 || ny == 0 || nz == 0) return fail(FXB_ERR_INVALID, "fxb_emitter_box: bad argument");
     int lo[3], hi[3];

@@ -131,6 +131,11 @@ class Fluid:
         stream = C.c_void_p(int(stream)) if stream else C.c_void_p(0)
         B.check(B.lib().fxb_get_field_async(self._handle(), field, C.c_void_p(host_ptr), nbytes, stream))
 
+    def export(self, path: str, field: int = B.FIELD_COLOR) -> None:
+        """Writes this rank's slab of ``field`` as a volume file (fluidx12_b200/volume.py): by default the colour
+        field ``Fluid::Render`` would sample, m_colors[m_frameParity] (Fluid.cpp:760-770, 841)."""
+        B.check(B.lib().fxb_export_field(self._handle(), field, path.encode()))
+
     def stats(self) -> B.FxbStats:
         st = B.FxbStats()
         B.check(B.lib().fxb_get_stats(self._handle(), C.byref(st)))

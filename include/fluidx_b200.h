@@ -30,7 +30,8 @@ typedef enum fxb_status {
     FXB_ERR_CUDA = -2,         /* CUDA runtime/driver failure, or no sm_100 device */
     FXB_ERR_NCCL = -3,         /* NCCL failure or NCCL not loadable when nranks > 1 */
     FXB_ERR_SIZE = -4,         /* host buffer size does not match the field */
-    FXB_ERR_HALO_OVERFLOW = -5 /* a back-trace left the exchanged z-halo (multi-GPU only; sticky) */
+    FXB_ERR_HALO_OVERFLOW = -5,/* a back-trace left the exchanged z-halo (multi-GPU only; sticky) */
+    FXB_ERR_IO = -6            /* a volume file could not be written / read or is not a valid one */
 } fxb_status;
 
 /* Sampler addressing of the advection fetches: Fluid uses LINEAR_MIRROR (Fluid.cpp:452),
@@ -153,6 +154,43 @@ int fxb_get_freeze_histogram(fxb_sim* sim, uint64_t* out, int n);
  * ms[2]=all Jacobi passes, ms[3]=gradient-subtract, ms[4]=halo exchange (0 when nranks == 1),
  * ms[5]=whole step.  The caller must have called fxb_update_frame. */
 int fxb_profile_step(fxb_sim* sim, float* ms, int n);
+
+/* ---- Volume files: the hand-off format of a field to a renderer ------------------------------
+ * The reference never leaves the GPU: Fluid::Render binds m_colors[m_frameParity] as a Texture3D SRV
+ * (Fluid.cpp:760-770, 841/870/897) and its ray marchers sample it as premultiplied RGBA with the density in .w
+ * (RayMarch.hlsli:62-68 GetSample; CSRayMarch.hlsl:157; _PRE_MULTIPLIED_, Common.hlsli:5) at
+ * uvw = pos * 0.5 + 0.5 (RayMarch.hlsli LocalToTex3DSpace), texel (x, y, z) centred at ((x, y, z) + 0.5) / N.
+ * A volume file is that texture's logical contents: a 64-byte little-endian header followed by the dense payload,
+ * x fastest, [z][y][x][4] IEEE half (format 1, R16G16B16A16_FLOAT) or [z][y][x] float (format 2, R32_FLOAT) — the
+ * byte layout of fxb_get_field.  A rank of a multi-GPU run writes its own z-slab (z0, nz_local); a reader assembles
+ * the slabs by z0. */
+#define FXB_VOLUME_MAGIC "FXBV"
+#define FXB_VOLUME_VERSION 1u
+#define FXB_VOLUME_FLAG_PREMULTIPLIED 1u /* colour fields: rgb already multiplied by the density in .w */
+typedef struct fxb_volume_header {
+    char magic[4];          /* "FXBV" */
+    uint32_t version;       /* FXB_VOLUME_VERSION */
+    uint32_t nx, ny, nz;    /* global grid */
+    uint32_t z0, nz_local;  /* planes [z0, z0 + nz_local) are stored in this file */
+    uint32_t field;         /* fxb_field */
+    uint32_t format;        /* 1 = half x 4 (8 bytes/voxel), 2 = float (4 bytes/voxel) */
+    uint32_t flags;         /* FXB_VOLUME_FLAG_* */
+    uint64_t frame;         /* fxb_simulate calls that produced the contents */
+    float dt;               /* time step of the last frame (0 = paused) */
+    uint32_t frame_parity;  /* m_frameParity when written */
+    uint64_t payload_bytes; /* = nx * ny * nz_local * (8 or 4) */
+} fxb_volume_header;        /* 64 bytes */
+
+/* Host-only (no GPU needed).  fxb_volume_write validates the header (magic and version are filled in), writes
+ * header + payload to `path`.tmp and renames it over `path`.  fxb_volume_read_header reads and validates a header.
+ * fxb_volume_read also reads the payload into `data` (`capacity` >= payload_bytes, else FXB_ERR_SIZE) and fails
+ * with FXB_ERR_IO on a truncated file. */
+int fxb_volume_write(const char* path, const fxb_volume_header* hdr, const void* data);
+int fxb_volume_read_header(const char* path, fxb_volume_header* out);
+int fxb_volume_read(const char* path, fxb_volume_header* out, void* data, size_t capacity);
+
+/* Copies `field` of this rank's slab to the host (synchronously) and writes it as a volume file. */
+int fxb_export_field(fxb_sim* sim, int field, const char* path);
 
 /* Writes a fresh 128-byte ncclUniqueId (rank 0 calls this, then ships it to the other ranks). */
 int fxb_nccl_unique_id(void* out128);
