@@ -68,6 +68,14 @@ public:
         return dt;
     }
 
+    // No counterpart in the reference, whose renderer binds m_colors[m_frameParity] in place (Fluid.cpp:760-770, 841):
+    // writes the field as a volume file for a renderer outside the process (fluidx_b200.h, fxb_volume_header).
+    bool Export(const char* path, int field = FXB_FIELD_COLOR) {
+        if (fxb_export_field(m_sim, field, path) == FXB_OK) return true;
+        m_error = fxb_last_error();
+        return false;
+    }
+
     fxb_sim* handle() const { return m_sim; }
     const std::string& last_error() const { return m_error; }
     uint8_t frameParity() const { return m_frameParity; }

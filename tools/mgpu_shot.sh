@@ -13,7 +13,7 @@ unset FXB_TEST_EXPERIMENTAL
 run() {  # label, env...
     label=$1; shift
     env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-        --master-port 29655 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline --no-c3 --no-experiments \
+        --master-port 29655 bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline --no-c3 --no-experiments --no-export-e2e \
         > gpurun_out/mgpu_${N}_${label}.log 2>&1
     tail -1 gpurun_out/mgpu_${N}_${label}.log | cut -c1-400
 }
