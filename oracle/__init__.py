@@ -67,6 +67,10 @@ def lib() -> C.CDLL:
         L.fxo_emitter_basis.restype = f32
         L.fxo_emitter_basis.argtypes = [i32] * 6
         L.fxo_constants.argtypes = [f32p, i32]
+        L.fxo_light_map.argtypes = [i32, i32, i32, u16p, vp, vp]
+        L.fxo_light_map.restype = None
+        L.fxo_pack_r11g11b10.argtypes = [f32, f32, f32]
+        L.fxo_pack_r11g11b10.restype = C.c_uint32
         _lib = L
     return _lib
 
@@ -218,6 +222,26 @@ def sample_trilinear(field, cx, cy, cz, address_mode=ADDRESS_MIRROR):
     out = np.empty(4, np.float32)
     lib().fxo_sample_trilinear(_ptr(field), nx, ny, nz, address_mode, cx, cy, cz, _ptr(out))
     return out
+
+
+class LightParams(C.Structure):
+    """The light-map pass's constants (CSRayMarchL.hlsl; = fxb_light_params of include/fluidx_b200.h)."""
+    _fields_ = [("light_pt", C.c_float * 3), ("light_color", C.c_float * 4), ("ambient", C.c_float * 4),
+                ("world_i", C.c_float * 12), ("world", C.c_float * 12), ("num_samples", C.c_uint32),
+                ("has_light_probes", C.c_uint32), ("sh", (C.c_float * 3) * 9)]
+
+
+def light_map(colour, params: LightParams) -> np.ndarray:
+    """Packed R11G11B10_FLOAT light map [nz][ny][nx] of a colour field [nz][ny][nx][4] half."""
+    nz, ny, nx, _ = colour.shape
+    colour = np.ascontiguousarray(colour, np.float16)
+    out = np.empty((nz, ny, nx), np.uint32)
+    lib().fxo_light_map(nx, ny, nz, _ptr(colour), C.byref(params), _ptr(out))
+    return out
+
+
+def pack_r11g11b10(r, g, b) -> int:
+    return int(lib().fxo_pack_r11g11b10(r, g, b))
 
 
 def constants() -> np.ndarray:

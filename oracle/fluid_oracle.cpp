@@ -343,6 +343,163 @@ void gradient(const Grid& g, const uint16_t* vel_in, const float* p, uint16_t* v
             }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Light-map pass: CSRayMarchL.hlsl:15-80 with RayMarch.hlsli:62-68 (GetSample), :75-98
+// (GetDensityGradient), :203-210 (LocalToTex3DSpace), :215-228 (GetStep), :233-268 (CastLightRay) and the order-3 SH
+// irradiance of XUSG's SHIrradiance.hlsli (not in the reference tree: restated from the shipped bytecode, whose five
+// constants are Ramamoorthi & Hanrahan's c1..c5 — 0.429043, 2*0.511664 = 1.023328, 2*0.429043 = 0.858086, 0.886227,
+// 0.247708).  Operation order, fused mads and folded constants follow Bin/CSRayMarchL.cso instruction by instruction
+// (tests/golden/dxbc_interp.py executes that blob; tests/test_lightmap.py requires this function to reproduce it).
+// Restated because no file of the reference defines them: the LINEAR_CLAMP sampler (Fluid.cpp:475) as in
+// sample_trilinear above, with the instruction's texel offsets added to both taps before clamping; `rsq` as
+// 1 / sqrt(x), both correctly rounded; min16float arithmetic carried out in fp32; the R11G11B10_FLOAT store
+// (Fluid.cpp:225-227) truncating toward zero, negative -> 0, finite overflow -> largest finite value.
+// ---------------------------------------------------------------------------------------------
+struct LightParams {      // = fxb_light_params of include/fluidx_b200.h
+    float light_pt[3];    // cbPerFrame g_lightPt, cb1[1].xyz (Fluid.cpp:304)
+    float light_color[4]; // cb1[2] (Fluid.cpp:305)
+    float ambient[4];     // cb1[3] (Fluid.cpp:306)
+    float world_i[12];    // cbPerObject g_worldI, cb0[8..10] as XMStoreFloat3x4 wrote them (Fluid.cpp:318)
+    float world[12];      // g_world, cb0[11..13] (Fluid.cpp:319)
+    uint32_t num_samples; // cbSampleRes g_numSamples = m_maxLightSamples (Fluid.cpp:872)
+    uint32_t has_light_probes;  // (Fluid.cpp:873)
+    float sh[9][3];       // g_roSHCoeffs (Fluid.cpp:874)
+};
+
+inline uint32_t pack_r11g11b10(const float rgb[3]) {
+    uint32_t out = 0;
+    const int mbits[3] = {6, 6, 5}, shift[3] = {0, 11, 22};
+    for (int k = 0; k < 3; ++k) {
+        uint32_t w;
+        std::memcpy(&w, &rgb[k], 4);
+        const uint32_t sign = w >> 31, e = (w >> 23) & 0xFFu, m = w & 0x7FFFFFu;
+        const int mb = mbits[k], drop = 23 - mb;
+        const uint32_t maxfin = (30u << mb) | ((1u << mb) - 1u);
+        uint32_t r;
+        if (e == 0xFFu) r = m ? ((31u << mb) | ((1u << mb) - 1u)) : (sign ? 0u : (31u << mb));
+        else if (sign) r = 0u;
+        else if (e >= 143u) r = maxfin;
+        else if (e >= 113u) r = ((e - 112u) << mb) | (m >> drop);
+        else { const uint32_t sh = std::min(113u - e, 24u); r = ((m | 0x800000u) >> sh) >> drop; }
+        out |= r << shift[k];
+    }
+    return out;
+}
+
+// colour.w at normalised (cx, cy, cz) + integer texel offset, LINEAR_CLAMP
+inline float sample_density(const uint16_t* col, const Grid& g, float cx, float cy, float cz, int ox, int oy, int oz) {
+    const float tx = std::fmaf(cx, (float)g.nx, -0.5f), ty = std::fmaf(cy, (float)g.ny, -0.5f);
+    const float tz = std::fmaf(cz, (float)g.nz, -0.5f);
+    const int ix = floor_to_tap(tx) + ox, iy = floor_to_tap(ty) + oy, iz = floor_to_tap(tz) + oz;
+    const float fx = tx - std::floor(tx), fy = ty - std::floor(ty), fz = tz - std::floor(tz);
+    const int x0 = address_tap(ix, g.nx, ADDRESS_CLAMP), x1 = address_tap(ix + 1, g.nx, ADDRESS_CLAMP);
+    const int y0 = address_tap(iy, g.ny, ADDRESS_CLAMP), y1 = address_tap(iy + 1, g.ny, ADDRESS_CLAMP);
+    const int z0 = address_tap(iz, g.nz, ADDRESS_CLAMP), z1 = address_tap(iz + 1, g.nz, ADDRESS_CLAMP);
+    auto w = [&](int x, int y, int z) { return half_to_float(col[4 * g.idx(x, y, z) + 3]); };
+    const float a000 = w(x0, y0, z0), a100 = w(x1, y0, z0), a010 = w(x0, y1, z0), a110 = w(x1, y1, z0);
+    const float a001 = w(x0, y0, z1), a101 = w(x1, y0, z1), a011 = w(x0, y1, z1), a111 = w(x1, y1, z1);
+    const float x00 = std::fmaf(fx, a100 - a000, a000), x10 = std::fmaf(fx, a110 - a010, a010);
+    const float x01 = std::fmaf(fx, a101 - a001, a001), x11 = std::fmaf(fx, a111 - a011, a011);
+    const float y0v = std::fmaf(fy, x10 - x00, x00), y1v = std::fmaf(fy, x11 - x01, x01);
+    return std::fmaf(fz, y1v - y0v, y0v);
+}
+
+inline float dp3(const float a[3], const float b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+inline float rsq(float v) { return 1.0f / std::sqrt(v); }
+
+// CastLightRay (RayMarch.hlsli:233-268) as compiled: returns the transmittance along `dir` from `o`.
+inline float cast_light_ray(const uint16_t* col, const Grid& g, const float o[3], const float dir[3], float step,
+                            uint32_t num_samples) {
+    float transm = 1.0f, t = step, prev = 0.0f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        float pos[3];
+        for (int k = 0; k < 3; ++k) pos[k] = std::fmaf(dir[k], t, o[k]);
+        if (1.0f < std::fabs(pos[0]) || 1.0f < std::fabs(pos[1]) || 1.0f < std::fabs(pos[2])) break;
+        const float d = sample_density(col, g, std::fmaf(pos[0], 0.5f, 0.5f), std::fmaf(pos[1], 0.5f, 0.5f),
+                                       std::fmaf(pos[2], 0.5f, 0.5f), 0, 0, 0);
+        const float tr = std::fmaf(-d, 0.8f, 1.0f) * transm;
+        if (tr < 0.01f) return tr;
+        const float ev = std::fmin(0.00390625f / std::fabs(-prev + d), 2.0f);
+        const float ui = std::fmin(-d + 1.0f, 1.0f);
+        const float th = -transm + 1.0f;
+        const float grow = std::fmax(th * (ui * (ev * 1.5f)), 1.0f);
+        t = std::fmaf(step, grow, t);
+        transm = tr;
+        prev = d;
+    }
+    return transm;
+}
+
+void light_map(const Grid& g, const uint16_t* col, const LightParams& P, uint32_t* out) {
+    const float fn[3] = {(float)g.nx, (float)g.ny, (float)g.nz};
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int z = 0; z < g.nz; ++z)
+        for (int y = 0; y < g.ny; ++y)
+            for (int x = 0; x < g.nx; ++x) {
+                const int id[3] = {x, y, z};
+                float o[3], uvw[3];
+                for (int k = 0; k < 3; ++k) {
+                    o[k] = std::fmaf(((float)id[k] + 0.5f) / fn[k], 2.0f, -1.0f);
+                    uvw[k] = std::fmaf(o[k], 0.5f, 0.5f);
+                }
+                float shadow = 1.0f, ao = 1.0f, irr[3] = {0.0f, 0.0f, 0.0f};
+                if (sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 0, 0) >= 0.01f) {
+                    const float step = 3.464101552963257f / (float)P.num_samples;  // 0x405db3d7 = 2 sqrt(3)
+                    float L[3], dir[3];
+                    for (int k = 0; k < 3; ++k) L[k] = dp3(P.light_pt, P.world_i + 4 * k);
+                    const float inv = rsq(dp3(L, L));
+                    for (int k = 0; k < 3; ++k) dir[k] = inv * L[k];
+                    shadow = cast_light_ray(col, g, o, dir, step, P.num_samples);
+                    if (P.has_light_probes) {
+                        const float q0 = sample_density(col, g, uvw[0], uvw[1], uvw[2], -1, 0, 0);
+                        const float q1 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 1, 0, 0);
+                        const float q2 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, -1, 0);
+                        const float q3 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 1, 0);
+                        const float q4 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 0, -1);
+                        const float q5 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 0, 1);
+                        const float grad[3] = {-q0 + q1, -q2 + q3, -q4 + q5};
+                        const bool any = 0.0f < std::fabs(grad[0]) || 0.0f < std::fabs(grad[1]) || 0.0f < std::fabs(grad[2]);
+                        float rd[3], wd[3], n[3];
+                        for (int k = 0; k < 3; ++k) rd[k] = any ? -grad[k] : o[k];
+                        for (int k = 0; k < 3; ++k) wd[k] = dp3(rd, P.world + 4 * k);
+                        const float winv = rsq(dp3(wd, wd));
+                        for (int k = 0; k < 3; ++k) n[k] = winv * wd[k];
+                        const float yy = n[1] * n[1], zz = n[2] * n[2];
+                        const float a = std::fmaf(n[0], n[0], -yy) * 0.4290427565574646f;   // 0x3edbab7e
+                        const float b = std::fmaf(zz, 3.0f, -1.0f) * 0.24770796298980713f;    // 0x3e7da728
+                        for (int c = 0; c < 3; ++c) {
+                            float r10 = P.sh[6][c] * b;
+                            r10 = std::fmaf(a, P.sh[8][c], r10);
+                            float r3 = std::fmaf(P.sh[0][c], 0.8862269520759583f, r10);     // 0x3f62dfc5
+                            float r8 = P.sh[4][c] * -n[0];
+                            r10 = P.sh[7][c] * -n[0];
+                            r10 = n[2] * r10;
+                            r8 = std::fmaf(r8, -n[1], r10);
+                            const float r9 = P.sh[5][c] * -n[1];
+                            r8 = std::fmaf(r9, n[2], r8);
+                            r3 = std::fmaf(r8, 0.8580855131149292f, r3);                    // 0x3f5bab7e
+                            float r4 = P.sh[1][c] * -n[1];
+                            r4 = std::fmaf(P.sh[3][c], -n[0], r4);
+                            r4 = std::fmaf(P.sh[2][c], n[2], r4);
+                            r3 = std::fmaf(r4, 1.0233267545700073f, r3);                    // 0x3f82fc5f
+                            irr[c] = std::fmax(r3, 0.0f);
+                        }
+                        const float rinv = rsq(dp3(rd, rd));
+                        float rdn[3];
+                        for (int k = 0; k < 3; ++k) rdn[k] = rinv * rd[k];
+                        ao = cast_light_ray(col, g, o, rdn, step, P.num_samples);
+                    }
+                }
+                float rgb[3];
+                for (int c = 0; c < 3; ++c) {
+                    const float lc = P.light_color[3] * P.light_color[c];
+                    const float amb = P.has_light_probes ? ao * irr[c] : P.ambient[3] * P.ambient[c];
+                    rgb[c] = std::fmaf(shadow, lc, amb);
+                }
+                out[g.idx(x, y, z)] = pack_r11g11b10(rgb);
+            }
+}
+
 struct Oracle {
     Grid g;
     int address_mode, early_exit, iters;
@@ -506,6 +663,16 @@ void fxo_gradient_slab(int nx, int ny, int nz, int nzg, int z0, const uint16_t* 
 }
 
 // ---- unit helpers -----------------------------------------------------------------------------
+// Light-map pass on a whole grid: colour = [nz][ny][nx][4] half, params = LightParams, out = [nz][ny][nx] packed
+// R11G11B10_FLOAT words.
+void fxo_light_map(int nx, int ny, int nz, const uint16_t* colour, const void* params, uint32_t* out) {
+    light_map(Grid{nx, ny, nz}, colour, *static_cast<const LightParams*>(params), out);
+}
+uint32_t fxo_pack_r11g11b10(float r, float g, float b) {
+    const float rgb[3] = {r, g, b};
+    return pack_r11g11b10(rgb);
+}
+
 uint16_t fxo_f32_to_f16(float f) { return float_to_half(f); }
 float fxo_f16_to_f32(uint16_t h) { return half_to_float(h); }
 int fxo_address_tap(int i, int w, int mode) { return address_tap(i, w, mode); }

@@ -33,7 +33,8 @@ import numpy as np
 
 F32, U32, I32 = np.float32, np.uint32, np.int32
 
-OPCODES = {0: "add", 1: "and", 2: "break", 3: "breakc", 14: "div", 16: "dp3", 21: "endif", 22: "endloop", 25: "exp",
+OPCODES = {0: "add", 1: "and", 2: "break", 3: "breakc", 14: "div", 16: "dp3", 18: "else", 21: "endif", 22: "endloop", 25: "exp",
+           60: "or", 68: "rsq", 162: "dcl_resource_structured", 167: "ld_structured",
            29: "ge", 30: "iadd", 31: "if", 45: "ld", 48: "loop", 49: "lt", 50: "mad", 51: "min", 52: "max", 54: "mov",
            55: "movc", 56: "mul", 61: "resinfo", 62: "ret", 72: "sample_l", 80: "uge", 83: "umax", 84: "umin", 86: "utof",
            88: "dcl_resource", 89: "dcl_constant_buffer", 90: "dcl_sampler", 95: "dcl_input", 104: "dcl_temps",
@@ -86,9 +87,12 @@ class Instr:
     resinfo_type: int = 0
     operands: List[Operand] = field(default_factory=list)
     raw0: int = 0
+    offset: tuple = (0, 0, 0)    # aoffimmi of a sample instruction
 
     def text(self) -> str:
         name = self.op + ("_sat" if self.sat else "")
+        if self.offset != (0, 0, 0):
+            name += "_aoffimmi(%d,%d,%d)" % self.offset
         if self.op in ("if", "breakc"):
             name += "_nz" if self.test_nz else "_z"
         return (name + " " + ", ".join(o.text() for o in self.operands)).strip()
@@ -150,8 +154,12 @@ def decode(blob: bytes):
         name = OPCODES[opc]
         p = pos + 1
         ext = t0 >> 31
-        while ext:  # extended opcode tokens (sample offsets, resource dimension, return type): not needed here
-            ext = tok[p] >> 31
+        offset = (0, 0, 0)
+        while ext:  # extended opcode tokens: sample offsets are kept; resource dimension / return type are not needed
+            e = tok[p]
+            if e & 0x3F == 1:  # D3D10_SB_EXTENDED_OPCODE_SAMPLE_CONTROLS: three signed 4-bit texel offsets
+                offset = tuple(((e >> sh & 0xF) ^ 8) - 8 for sh in (9, 13, 17))
+            ext = e >> 31
             p += 1
         end = pos + length
         if name.startswith("dcl_"):
@@ -162,12 +170,13 @@ def decode(blob: bytes):
             elif name == "dcl_uav_typed":
                 o, _ = _decode_operand(tok, p)
                 decls["uav"][o.index[0]] = {"glc": bool(t0 >> 16 & 1)}
-            elif name == "dcl_resource":
+            elif name in ("dcl_resource", "dcl_resource_structured"):
                 o, _ = _decode_operand(tok, p)
                 decls["srv"].append(o.index[0])
             pos = end
             continue
-        ins = Instr(op=name, sat=bool(t0 >> 13 & 1), test_nz=bool(t0 >> 18 & 1), resinfo_type=t0 >> 11 & 3, raw0=t0)
+        ins = Instr(op=name, sat=bool(t0 >> 13 & 1), test_nz=bool(t0 >> 18 & 1), resinfo_type=t0 >> 11 & 3, raw0=t0,
+                    offset=offset)
         while p < end:
             o, p = _decode_operand(tok, p)
             ins.operands.append(o)
@@ -212,15 +221,16 @@ def mirror_tap(i, w):
     return np.where(m < w, m, 2 * w - 1 - m)
 
 
-def sample_linear(tex_f32, coord, clamp=False):
-    """tex_f32: [nz, ny, nx, 4] fp32 texel values; coord: [N, 3] normalised (x, y, z).  Returns [N, 4] fp32."""
+def sample_linear(tex_f32, coord, clamp=False, offset=(0, 0, 0)):
+    """tex_f32: [nz, ny, nx, 4] fp32 texel values; coord: [N, 3] normalised (x, y, z).  Returns [N, 4] fp32.
+    offset: the instruction's integer texel offsets (aoffimmi), added to both taps before the addressing mode."""
     nz, ny, nx, _ = tex_f32.shape
     idx, frac = [], []
     for axis, w in enumerate((nx, ny, nz)):
         t = fma32(coord[:, axis], F32(w), F32(-0.5))
         i0 = np.floor(t)
         frac.append((t - i0).astype(F32))
-        i0 = i0.astype(np.int64)
+        i0 = i0.astype(np.int64) + int(offset[axis])
         tap = (lambda i, w=w: np.clip(i, 0, w - 1)) if clamp else (lambda i, w=w: mirror_tap(i, w))
         idx.append((tap(i0), tap(i0 + 1)))
     (x0, x1), (y0, y1), (z0, z1) = idx
@@ -236,9 +246,35 @@ def sample_linear(tex_f32, coord, clamp=False):
     return lerp(lerp(x00, x10, fy), lerp(x01, x11, fy), fz)
 
 
+def pack_r11g11b10(rgb):
+    """fp32 [N, 3] -> DXGI_FORMAT_R11G11B10_FLOAT words (R in bits 0-10, G 11-21, B 22-31; 5-bit exponent of bias 15,
+    6 / 6 / 5 mantissa bits, no sign).  Restated conversion (the blob only holds `store_uav_typed`): negative values and
+    -0 become 0, NaN becomes the all-ones NaN, values at or above 2^16 become the largest finite value's successor INF
+    only for +INF itself (finite overflow clamps to the largest finite value), everything else is TRUNCATED toward
+    zero, denormals included."""
+    v = np.ascontiguousarray(rgb, F32).view(U32).astype(np.uint64)
+    out = np.zeros(v.shape[0], np.uint64)
+    for k, (mbits, shift) in enumerate(((6, 0), (6, 11), (5, 22))):
+        w = v[:, k]
+        sign, e, m = w >> np.uint64(31), (w >> np.uint64(23)) & np.uint64(0xFF), w & np.uint64(0x7FFFFF)
+        drop = np.uint64(23 - mbits)
+        maxfin = np.uint64((30 << mbits) | ((1 << mbits) - 1))
+        normal = ((e - np.uint64(112)) << np.uint64(mbits)) | (m >> drop)      # valid for 113 <= e <= 142
+        sh = np.minimum(np.uint64(113) - np.minimum(e, np.uint64(113)), np.uint64(24))
+        den = ((m | np.uint64(0x800000)) >> sh) >> drop                          # e <= 112: denormal or zero
+        r = np.where(e >= np.uint64(113), np.minimum(normal, maxfin), den)
+        r = np.where(e >= np.uint64(143), maxfin, r)
+        r = np.where((e == np.uint64(0xFF)) & (m == 0), np.uint64(31 << mbits), r)              # +INF
+        r = np.where(sign != 0, np.uint64(0), r)
+        r = np.where((e == np.uint64(0xFF)) & (m != 0), np.uint64((31 << mbits) | ((1 << mbits) - 1)), r)  # NaN
+        out |= r << np.uint64(shift)
+    return out.astype(U32)
+
+
 # ---- the machine ------------------------------------------------------------------------------------------------------
 class Texture:
-    """A 3D texture / typed UAV.  fmt 'rgba16f': data [nz, ny, nx, 4] float16; 'r32f': data [nz, ny, nx] float32."""
+    """A 3D texture / typed UAV.  fmt 'rgba16f': data [nz, ny, nx, 4] float16; 'r32f': data [nz, ny, nx] float32;
+    'r11g11b10f': data [nz, ny, nx] uint32 (written only)."""
 
     def __init__(self, data, fmt):
         self.data, self.fmt = data, fmt
@@ -271,7 +307,9 @@ class Machine:
         self.n = len(ids)
         self.tid = np.concatenate([ids, np.zeros((self.n, 1), ids.dtype)], 1).astype(U32)
         self.r = np.zeros((self.decls["temps"], self.n, 4), U32)
-        self.cb0 = np.asarray(cb0, U32)
+        # cb0: the 4 words of cb[0][0], or {slot: [rows, 4] uint32} when a shader reads several constant buffers
+        self.cb = {k: np.asarray(v, U32).reshape(-1, 4) for k, v in cb0.items()} if isinstance(cb0, dict) else \
+            {0: np.asarray(cb0, U32).reshape(1, 4)}
         self.srv, self.uav, self.clamp = srv, uav, clamp
         self.iterations = 0     # trips of the relaxation loop in which at least one thread was inside
         self.active_entering = []  # threads inside the loop at the start of each trip
@@ -287,8 +325,7 @@ class Machine:
             elif o.kind == "vThreadID":
                 base = self.tid
             elif o.kind == "cb":
-                assert o.index == [0, 0]
-                base = np.broadcast_to(self.cb0, (self.n, 4))
+                base = np.broadcast_to(self.cb[o.index[0]][o.index[1]], (self.n, 4))
             else:
                 raise ValueError(o.kind)
             sw = o.swizzle if o.mode in ("swizzle", "select1") else [0, 1, 2, 3]
@@ -327,10 +364,19 @@ class Machine:
                     break
                 elif op == "if":
                     c = self.read(ops[0])[:, 0] != 0
-                    stack.append(("if", M.copy()))
+                    M0 = M.copy()
                     M = M & (c if ins.test_nz else ~c)
+                    stack.append(("if", M0, M.copy()))
+                elif op == "else":
+                    kind, saved, taken = stack[-1]
+                    assert kind == "if"
+                    broken = np.zeros(self.n, bool)
+                    for fr in stack:
+                        if fr[0] == "loop":
+                            broken = broken | fr[3]
+                    M = saved & ~taken & ~broken
                 elif op == "endif":
-                    kind, saved = stack.pop()
+                    kind, saved, _ = stack.pop()
                     assert kind == "if"
                     broken = np.zeros(self.n, bool)
                     for fr in stack:
@@ -388,6 +434,24 @@ class Machine:
                 elif op == "uge":
                     a, b = self.read(ops[1]), self.read(ops[2])
                     self.write(ops[0], np.where(a >= b, true_, false_), M)
+                elif op in ("or", "and"):
+                    a, b = self.read(ops[1]), self.read(ops[2])
+                    self.write(ops[0], (a | b) if op == "or" else (a & b), M)
+                elif op == "rsq":  # restated: 1 / sqrt(x), both correctly rounded (real hardware approximates)
+                    a = f(self.read(ops[1]))
+                    self.write(ops[0], u((F32(1.0) / np.sqrt(a).astype(F32)).astype(F32)), M, ins.sat)
+                elif op == "ld_structured":
+                    buf = self.srv[ops[3].index[0]]  # [elements, words] uint32
+                    e = self.read(ops[1])[:, 0].astype(np.int64)
+                    w0 = self.read(ops[2])[:, 0].astype(np.int64) // 4
+                    sw = ops[3].swizzle if ops[3].mode != "mask" else [0, 1, 2, 3]
+                    inside = e < buf.shape[0]
+                    val = np.zeros((self.n, 4), U32)
+                    for k in range(4):
+                        w = w0 + sw[k]
+                        ok = inside & (w < buf.shape[1])
+                        val[ok, k] = buf[e[ok], w[ok]]
+                    self.write(ops[0], val, M)
                 elif op in ("umax", "umin"):
                     a, b = self.read(ops[1]), self.read(ops[2])
                     self.write(ops[0], np.maximum(a, b) if op == "umax" else np.minimum(a, b), M)
@@ -397,7 +461,7 @@ class Machine:
                 elif op == "utof":
                     self.write(ops[0], u(self.read(ops[1]).astype(F32)), M)
                 elif op == "resinfo":
-                    w, h, d = self.srv[ops[2].index[0]].dims
+                    w, h, d = (self.uav if ops[2].kind == "u" else self.srv)[ops[2].index[0]].dims
                     dims = np.array([w, h, d, 1], np.int64)
                     raw = dims.astype(U32) if ins.resinfo_type == 2 else dims.astype(F32).view(U32)
                     assert ins.resinfo_type in (0, 2)
@@ -412,7 +476,7 @@ class Machine:
                 elif op == "sample_l":
                     coord = f(self.read(ops[1]))[:, :3]
                     tex = self.srv[ops[2].index[0]]
-                    texels = sample_linear(tex.texels_f32(), coord, self.clamp)
+                    texels = sample_linear(tex.texels_f32(), coord, self.clamp, ins.offset)
                     sw = ops[2].swizzle if ops[2].mode != "mask" else [0, 1, 2, 3]
                     self.write(ops[0], u(texels[:, sw]), M, ins.sat)
                 elif op == "store_uav_typed":
@@ -425,7 +489,9 @@ class Machine:
                         target = pending.setdefault(slot, tex.data.copy())
                     else:
                         target = tex.data
-                    if tex.fmt == "rgba16f":
+                    if tex.fmt == "r11g11b10f":
+                        target[c[:, 2], c[:, 1], c[:, 0]] = pack_r11g11b10(v[:, :3])
+                    elif tex.fmt == "rgba16f":
                         target[c[:, 2], c[:, 1], c[:, 0]] = v.astype(np.float16)  # round to nearest even
                     else:
                         target[c[:, 2], c[:, 1], c[:, 0]] = v[:, 0]
