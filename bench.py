@@ -306,6 +306,12 @@ def experiments_single_gpu(budget_s):
     try:
         for ln in open(path):
             r = json.loads(ln)
+            if r.get("stage") == "light_map":
+                r.pop("stage"); r.pop("t", None)
+                r["grid"] = "x".join(map(str, r["grid"]))
+                r["variant"] = "light_map_pass"
+                rows.append(r)
+                continue
             if r.get("stage") != "timing":
                 continue
             row = {"grid": "x".join(map(str, r["grid"])), "variant": r.get("variant", "default")}
@@ -637,7 +643,7 @@ def main():
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-experiments", action="store_true",
                     help="skip the child-process runs of the opt-in variants after the measurement (use under ncu)")
-    ap.add_argument("--experiments-budget", type=float, default=60.0, help="seconds (twice that for N > 1)")
+    ap.add_argument("--experiments-budget", type=float, default=75.0, help="seconds (twice that for N > 1)")
     ap.add_argument("--checksum", action="store_true", help="add a checksum of the final state to the line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -18,6 +18,7 @@ from .binding import (  # noqa: F401
     FIELD_VELOCITY_ADVECTED,
     FluidError,
     FxbConfig,
+    FxbLightParams,
     FxbStats,
     FxbVolumeHeader,
     dt_for_grid,
@@ -29,7 +30,7 @@ from .slab import slab_range, halo_plan  # noqa: F401
 from . import volume  # noqa: F401
 
 __all__ = [
-    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader",
+    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader", "FxbLightParams",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
     "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV",
 ]

@@ -18,6 +18,7 @@ EXPORTS = (
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
     "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
     "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
+    "fxb_light_map", "fxb_get_light_map",
 )
 
 
@@ -63,6 +64,27 @@ class FxbStats(C.Structure):
         ("jacobi_fused", C.c_int32),
         ("reserved", C.c_int32),
     ]
+
+
+class FxbLightParams(C.Structure):
+    """fxb_light_params: the constants CSRayMarchL reads (include/fluidx_b200.h); defaults = the reference's
+    (Fluid.cpp:171-175, 182: light at (75, 75, -75), colour (1, .7, .3) x 3 pi, ambient (1, 1, 1) x 1.5 pi, volume
+    scaled by 10, 64 light samples, no light probe)."""
+    _fields_ = [("light_pt", C.c_float * 3), ("light_color", C.c_float * 4), ("ambient", C.c_float * 4),
+                ("world_i", C.c_float * 12), ("world", C.c_float * 12), ("num_samples", C.c_uint32),
+                ("has_light_probes", C.c_uint32), ("sh", (C.c_float * 3) * 9)]
+
+    @classmethod
+    def reference_defaults(cls) -> "FxbLightParams":
+        import math
+        p = cls()
+        p.light_pt[:] = [75.0, 75.0, -75.0]
+        p.light_color[:] = [1.0, 0.7, 0.3, math.pi * 3.0]
+        p.ambient[:] = [1.0, 1.0, 1.0, math.pi * 1.5]
+        p.world[:] = [10.0, 0, 0, 0, 0, 10.0, 0, 0, 0, 0, 10.0, 0]
+        p.world_i[:] = [0.1, 0, 0, 0, 0, 0.1, 0, 0, 0, 0, 0.1, 0]
+        p.num_samples, p.has_light_probes = 64, 0
+        return p
 
 
 class FxbVolumeHeader(C.Structure):
@@ -123,6 +145,8 @@ def lib() -> C.CDLL:
         L.fxb_volume_read_header.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader)]
         L.fxb_volume_read.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader), vp, C.c_size_t]
         L.fxb_export_field.argtypes = [vp, C.c_int, C.c_char_p]
+        L.fxb_light_map.argtypes = [vp, C.POINTER(FxbLightParams), vp]
+        L.fxb_get_light_map.argtypes = [vp, vp, C.c_size_t]
         L.fxb_last_error.restype = C.c_char_p
         L.fxb_abi_version.restype = C.c_int
         _lib = L

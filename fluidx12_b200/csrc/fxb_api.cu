@@ -90,6 +90,8 @@ struct fxb_sim {
     int tail_mains = 8;
     bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
     bool pass0_tail = false;  // FXB_PASS0=2 (with FXB_TAIL=1, T = 2): pass 0 by the block-resident kernel (experimental)
+    unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
+    unsigned short* light_density = nullptr;  // colour.w of every voxel, the channel the light-map pass samples
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
 
@@ -639,6 +641,8 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.work_list[1]);
     cudaFree(s->jac.work_count);
     cudaFree(s->jac.brick_state);
+    cudaFree(s->light_map);
+    cudaFree(s->light_density);
     cudaFree(s->emitter_basis);
     cudaFree(s->axis_tables);
     cudaFree(s->d_frame);
@@ -804,6 +808,35 @@ int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t
     d.nz_alloc = std::min(d.z_own1 + halo, nz) - d.z_first;
     const fxb::P2PPlanes q = fxb::p2p_planes(d, depth, rank > 0 ? z_first(rank - 1) : 0, rank < nranks - 1 ? z_first(rank + 1) : 0);
     out4[0] = q.send_lo; out4[1] = q.dst_lo; out4[2] = q.send_hi; out4[3] = q.dst_hi;
+    return FXB_OK;
+}
+
+// ---- light-map pass (Fluid::rayMarchL, Fluid.cpp:857-878; kernels in lightmap.cu) ---------------------------------
+static_assert(sizeof(fxb_light_params) == 4 * (3 + 4 + 4 + 12 + 12 + 2 + 27), "fxb_light_params is passed to the kernel as is");
+
+int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream) {
+    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_light_map: null argument");
+    if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_light_map: 3D grids only (the reference renders none other, Fluid.cpp:296)");
+    if (s->multi()) return fail(FXB_ERR_INVALID, "fxb_light_map: nranks > 1 is not supported (a light ray crosses every z-slab)");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (!s->light_map) {
+        FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
+        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->own_voxels() + 4) * sizeof(unsigned short)));
+    }
+    // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
+    FXB_CUDA(fxb::launch_light_map(s->dom, s->col[s->parity], s->light_density, s->light_map, params,
+                                   (cudaStream_t)cuda_stream));
+    s->last_stream = (cudaStream_t)cuda_stream;
+    return FXB_OK;
+}
+
+int fxb_get_light_map(fxb_sim* s, void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_light_map: null argument");
+    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_get_light_map: fxb_light_map has not run");
+    if (bytes != s->own_voxels() * sizeof(unsigned)) return fail(FXB_ERR_SIZE, "fxb_get_light_map: size mismatch");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    FXB_CUDA(cudaMemcpy(host, s->light_map, bytes, cudaMemcpyDeviceToHost));
     return FXB_OK;
 }
 

@@ -12,6 +12,10 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
                    void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int what,
                    cudaStream_t stream);
 
+// lightmap.cu — the light-map pass after the step (CSRayMarchL); consts = fxb_light_params
+cudaError_t launch_light_map(const Domain& d, const void* colour, unsigned short* dens, unsigned* out,
+                             const void* consts, cudaStream_t stream);
+
 // project_simple.cu — one kernel per logical pass (cross-check path, kernel_path = 1)
 void launch_begin_step(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 void launch_divergence(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, cudaStream_t stream);

@@ -131,6 +131,20 @@ class Fluid:
         stream = C.c_void_p(int(stream)) if stream else C.c_void_p(0)
         B.check(B.lib().fxb_get_field_async(self._handle(), field, C.c_void_p(host_ptr), nbytes, stream))
 
+    # -- Fluid::rayMarchL (Fluid.cpp:857-878): the light-map pass of Fluid::Render's default mode ------------------
+    def RayMarchL(self, params: "B.FxbLightParams" = None, pCommandList=None) -> None:
+        """Enqueues CSRayMarchL over m_colors[m_frameParity] on the CUDA stream ``pCommandList``."""
+        params = params if params is not None else B.FxbLightParams.reference_defaults()
+        stream = C.c_void_p(int(pCommandList)) if pCommandList else C.c_void_p(0)
+        B.check(B.lib().fxb_light_map(self._handle(), C.byref(params), stream))
+
+    def get_light_map(self) -> np.ndarray:
+        """m_lightMap as [z][y][x] uint32 words in R11G11B10_FLOAT packing."""
+        nx, ny, nz = self.m_gridSize
+        a = np.empty((nz, ny, nx), np.uint32)
+        B.check(B.lib().fxb_get_light_map(self._handle(), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
     def export(self, path: str, field: int = B.FIELD_COLOR) -> None:
         """Writes this rank's slab of ``field`` as a volume file (fluidx12_b200/volume.py): by default the colour
         field ``Fluid::Render`` would sample, m_colors[m_frameParity] (Fluid.cpp:760-770, 841)."""

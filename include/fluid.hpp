@@ -68,6 +68,9 @@ public:
         return dt;
     }
 
+    // Fluid::rayMarchL (Fluid.cpp:857-878), the light-map pass of Fluid::Render: CSRayMarchL over m_colors[m_frameParity].
+    int RayMarchL(const fxb_light_params& params, void* stream = nullptr) { return fxb_light_map(m_sim, &params, stream); }
+
     // No counterpart in the reference, whose renderer binds m_colors[m_frameParity] in place (Fluid.cpp:760-770, 841):
     // writes the field as a volume file for a renderer outside the process (fluidx_b200.h, fxb_volume_header).
     bool Export(const char* path, int field = FXB_FIELD_COLOR) {

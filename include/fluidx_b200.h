@@ -155,6 +155,30 @@ int fxb_get_freeze_histogram(fxb_sim* sim, uint64_t* out, int n);
  * ms[5]=whole step.  The caller must have called fxb_update_frame. */
 int fxb_profile_step(fxb_sim* sim, float* ms, int n);
 
+/* ---- Light-map pass ---------------------------------------------------------------------------
+ * The pass that follows Fluid::Simulate in the reference's default render mode: Fluid::rayMarchL (Fluid.cpp:857-878)
+ * runs CSRayMarchL.hlsl:15-80 over m_colors[m_frameParity] and writes one R11G11B10_FLOAT texel per voxel into
+ * m_lightMap (Fluid.cpp:223-227): transmittance towards the light x light colour + ambient, or with light probes
+ * ambient-occlusion x SH irradiance.  fxb_light_params holds the constants that shader reads, register for register. */
+typedef struct fxb_light_params {
+    float light_pt[3];         /* cbPerFrame g_lightPt = m_lightPt (Fluid.cpp:304; default (75, 75, -75), :171) */
+    float light_color[4];      /* g_lightColor: rgb, intensity (Fluid.cpp:305; default (1, .7, .3, 3 pi), :172) */
+    float ambient[4];          /* g_ambient (Fluid.cpp:306; default (1, 1, 1, 1.5 pi), :173); used iff !has_light_probes */
+    float world_i[12];         /* cbPerObject g_worldI: three float4 registers as XMStoreFloat3x4 writes them (Fluid.cpp:318) */
+    float world[12];           /* g_world (Fluid.cpp:319; default scaling by 10, :182) */
+    uint32_t num_samples;      /* cbSampleRes g_numSamples = m_maxLightSamples (Fluid.cpp:872; default 64, :175) */
+    uint32_t has_light_probes; /* m_coeffSH ? 1 : 0 (Fluid.cpp:873) */
+    float sh[9][3];            /* g_roSHCoeffs: nine float3 order-3 SH coefficients (Fluid::SetSH, Fluid.cpp:278-281, 874) */
+} fxb_light_params;
+
+/* Replaces Fluid::rayMarchL: enqueues the pass on `cuda_stream` over the current colour field (so after an
+ * fxb_simulate on the same stream it sees that step's result).  3D grids, nranks == 1 (a light ray crosses every
+ * z-slab; the multi-GPU version is not built).  The light map is allocated on first use. */
+int fxb_light_map(fxb_sim* sim, const fxb_light_params* params, void* cuda_stream);
+/* Synchronous copy of the light map to the host: [z][y][x] uint32, DXGI_FORMAT_R11G11B10_FLOAT packing (R in bits
+ * 0-10, G 11-21, B 22-31); bytes = nx*ny*nz*4.  Fails if fxb_light_map has not run. */
+int fxb_get_light_map(fxb_sim* sim, void* host, size_t bytes);
+
 /* ---- Volume files: the hand-off format of a field to a renderer ------------------------------
  * The reference never leaves the GPU: Fluid::Render binds m_colors[m_frameParity] as a Texture3D SRV
  * (Fluid.cpp:760-770, 841/870/897) and its ray marchers sample it as premultiplied RGBA with the density in .w

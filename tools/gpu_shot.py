@@ -118,6 +118,39 @@ def timing(fx, n, spin, steps, variants, all_fields=False):
             emit(stage="timing", grid=n, variant=label, error=repr(e))
 
 
+def light_map_timing(fx, n, spin=100, reps=5):
+    """The light-map pass (fxb_light_map) on a developed plume: host-timed launches, reference default
+    constants, without and with light probes (seeded SH coefficients)."""
+    try:
+        f = make(fx, n, False)
+        dt = fx.dt_for_grid(*n)
+        for _ in range(spin):
+            f.step(dt)
+        f.sync()
+        lit = int((f.get_field(fx.FIELD_COLOR)[..., 3].astype(np.float32) >= 0.01).sum())
+        for probes in (0, 1):
+            p = fx.FxbLightParams.reference_defaults()
+            p.has_light_probes = probes
+            sh = np.random.default_rng(1).standard_normal((9, 3)) * 0.3
+            sh[0] = np.abs(sh[0]) + 0.8
+            for i in range(9):
+                p.sh[i][:] = sh[i].tolist()
+            f.RayMarchL(p)
+            f.sync()
+            t = time.perf_counter()
+            for _ in range(reps):
+                f.RayMarchL(p)
+            f.sync()
+            ms = (time.perf_counter() - t) / reps * 1e3
+            vox = n[0] * n[1] * n[2]
+            emit(stage="light_map", grid=n, probes=probes, ms=round(ms, 4), voxels_with_smoke=lit,
+                 gvoxels_per_s=round(vox / ms / 1e6, 2), algorithmic_gbs=round(12.0 * vox / ms / 1e6, 1),
+                 words_distinct=int(len(np.unique(f.get_light_map()[::4, ::4, ::4]))))
+        f.close()
+    except Exception as e:
+        emit(stage="light_map", grid=n, error=repr(e))
+
+
 def bench_mode(fx):
     """The short list bench.py runs (in a child process, after its own measurement) so that every default bench run
     also times the opt-in variants: most informative first, nothing that can spin on the device (no TMA-staged
@@ -135,6 +168,8 @@ def bench_mode(fx):
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
                                           ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0})],
            all_fields=True)
+    light_map_timing(fx, (256, 256, 256))
+    light_map_timing(fx, (512, 512, 512))
     emit(stage="done")
 
 
