@@ -1,6 +1,6 @@
 """Light-map pass (CSRayMarchL.hlsl): the oracle's restatement against golden vectors produced by
 executing the reference's own Bin/CSRayMarchL.cso (tests/golden/make_lightmap_golden.py), the R11G11B10_FLOAT
-packing, and known answers that need no bytecode.  The CUDA path's tests are in tests/test_zx_gpu_lightmap.py."""
+packing, and known answers that need no bytecode.  The CUDA path's tests are in tests/test_zzz_gpu_lightmap.py."""
 import hashlib
 import os
 import sys

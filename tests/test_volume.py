@@ -1,5 +1,6 @@
 """Volume files: the renderer hand-off format.  Host-only entry points of the C library, the
-independent numpy reader, slab assembly and the error behaviour need no GPU; the export of a live field does."""
+independent numpy reader, slab assembly and the error behaviour need no GPU; the export of a live field does
+(tests/test_zzy_gpu_volume.py)."""
 import ctypes as C
 import os
 
@@ -102,27 +103,3 @@ def test_errors(tmp_path):
     small = np.empty(a.size - 1, np.float16)                                        # buffer too small
     assert L.fxb_volume_read(p.encode(), C.byref(h), small.ctypes.data_as(C.c_void_p), small.nbytes) == B.FXB_ERR_SIZE
     assert L.fxb_export_field(None, 1, p.encode()) == B.FXB_ERR_INVALID
-
-
-@pytest.mark.gpu
-def test_export_of_a_live_field_is_what_get_field_returns(tmp_path):
-    n = (64, 64, 24)
-    f = fx.Fluid()
-    assert f.Init(gridSize=n), f.last_error
-    dt = fx.dt_for_grid(*n)
-    for _ in range(7):
-        f.step(dt)
-    f.step(0.0)  # a paused frame: dt = 0 is recorded, the parity does not flip
-    for fld, name in ((fx.FIELD_COLOR, "c"), (fx.FIELD_VELOCITY, "v"), (fx.FIELD_PRESSURE, "p")):
-        p = str(tmp_path / (name + ".fxbv"))
-        f.export(p, fld)
-        a, h = volume.read_numpy(p)
-        want = f.get_field(fld)
-        assert a.dtype == want.dtype and a.tobytes() == want.tobytes()
-        assert (h["nx"], h["ny"], h["nz"], h["z0"], h["nz_local"]) == (64, 64, 24, 0, 24)
-        assert h["frame"] == 8 and h["dt"] == 0.0 and h["frame_parity"] == f.stats().frame_parity == 1
-        assert h["flags"] == (volume.FLAG_PREMULTIPLIED if fld == fx.FIELD_COLOR else 0)
-    assert np.abs(f.get_field(fx.FIELD_COLOR).astype(np.float32)).max() > 0
-    with pytest.raises(fx.FluidError):
-        f.export(str(tmp_path / "bad.fxbv"), 99)
-    f.close()
