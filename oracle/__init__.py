@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
         L.fxo_constants.argtypes = [f32p, i32]
         L.fxo_light_map.argtypes = [i32, i32, i32, u16p, vp, vp]
         L.fxo_light_map.restype = None
+        L.fxo_ray_march_v.argtypes = [i32, i32, i32, u16p, vp, vp, vp]
+        L.fxo_ray_march_v.restype = None
+        L.fxo_unpack_r11g11b10.argtypes = [C.c_uint32, f32p]
+        L.fxo_unpack_r11g11b10.restype = None
         L.fxo_pack_r11g11b10.argtypes = [f32, f32, f32]
         L.fxo_pack_r11g11b10.restype = C.c_uint32
         _lib = L
@@ -237,6 +241,29 @@ def light_map(colour, params: LightParams) -> np.ndarray:
     colour = np.ascontiguousarray(colour, np.float16)
     out = np.empty((nz, ny, nx), np.uint32)
     lib().fxo_light_map(nx, ny, nz, _ptr(colour), C.byref(params), _ptr(out))
+    return out
+
+
+class ViewParams(C.Structure):
+    """The cube-map ray march's constants (CSRayMarchV; = fxb_view_params of include/fluidx_b200.h)."""
+    _fields_ = [("eye_pt", C.c_float * 3), ("world_i", C.c_float * 12), ("num_samples", C.c_uint32),
+                ("visibility_mask", C.c_uint32), ("cube_size", C.c_uint32)]
+
+
+def ray_march_v(colour, light_map_words, params: ViewParams, cube=None) -> np.ndarray:
+    """[6][S][S][4] UNORM8 cube map; `cube` (optional) holds the previous contents, kept where nothing is written."""
+    nz, ny, nx, _ = colour.shape
+    colour = np.ascontiguousarray(colour, np.float16)
+    lm = np.ascontiguousarray(light_map_words, np.uint32)
+    s = int(params.cube_size)
+    out = np.zeros((6, s, s, 4), np.uint8) if cube is None else np.ascontiguousarray(cube, np.uint8).copy()
+    lib().fxo_ray_march_v(nx, ny, nz, _ptr(colour), _ptr(lm), C.byref(params), _ptr(out))
+    return out
+
+
+def unpack_r11g11b10(word: int) -> np.ndarray:
+    out = np.zeros(3, np.float32)
+    lib().fxo_unpack_r11g11b10(int(word), _ptr(out))
     return out
 
 

@@ -500,6 +500,169 @@ void light_map(const Grid& g, const uint16_t* col, const LightParams& P, uint32_
             }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cube-map-space ray march with the separate light pass: CSRayMarchV.hlsl (= CSRayMarch.hlsl:98-196
+// compiled with _LIGHT_PASS_), GetLocalPos :40-66, ComputeRayOrigin RayMarch.hlsli:146-177, ComputeTargetHit
+// :182-187, GetLight (light-map fetch) :273-278; dispatched by Fluid::rayMarchV (Fluid.cpp:880-908) into mip
+// m_cubeMapLOD of the R8G8B8A8_UNORM cube map (Fluid.cpp:229-232).  Follows Bin/CSRayMarchV.cso instruction by
+// instruction (the shipped blob is built with _CPU_CUBE_FACE_CULL_ == 1: a face is marched iff its bit is set in the
+// visibility mask, Fluid.cpp:51-63).  Restated platform semantics as for the light map, plus: the light map is sampled
+// LINEAR_CLAMP on its decoded fp32 values; the UNORM8 store = NaN -> 0, clamp to [0, 1], * 255, + 0.5, truncate.
+// A texel whose face is culled or whose ray misses the volume is NOT written (the reference leaves stale contents).
+// ---------------------------------------------------------------------------------------------
+struct ViewParams {          // = fxb_view_params of include/fluidx_b200.h
+    float eye_pt[3];         // cbPerFrame g_eyePt, cb1[0].xyz (Fluid.cpp:302)
+    float world_i[12];       // cbPerObject g_worldI, cb0[8..10] (Fluid.cpp:318)
+    uint32_t num_samples;    // cbSampleRes g_numSamples = m_raySampleCount (Fluid.cpp:898)
+    uint32_t visibility_mask;  // (Fluid.cpp:900)
+    uint32_t cube_size;      // m_gridSize.x >> m_cubeMapLOD (Fluid.cpp:906)
+};
+
+inline void unpack_r11g11b10(uint32_t w, float out[3]) {
+    const int mbits[3] = {6, 6, 5}, shift[3] = {0, 11, 22};
+    for (int k = 0; k < 3; ++k) {
+        const int mb = mbits[k];
+        const uint32_t f = (w >> shift[k]) & ((1u << (mb + 5)) - 1u), e = f >> mb, m = f & ((1u << mb) - 1u);
+        uint32_t bits;
+        if (e == 31u) bits = 0x7F800000u | (m << (23 - mb));
+        else if (e != 0u) bits = ((e + 112u) << 23) | (m << (23 - mb));
+        else if (m == 0u) bits = 0u;
+        else {  // denormal: normalise
+            int sh = 0;
+            uint32_t mm = m;
+            while (!(mm & (1u << mb))) { mm <<= 1; ++sh; }
+            bits = ((113u - sh) << 23) | ((mm & ((1u << mb) - 1u)) << (23 - mb));
+        }
+        std::memcpy(&out[k], &bits, 4);
+    }
+}
+
+struct Taps { int x0, x1, y0, y1, z0, z1; float fx, fy, fz; };
+inline Taps clamp_taps(const Grid& g, float cx, float cy, float cz) {
+    const float tx = std::fmaf(cx, (float)g.nx, -0.5f), ty = std::fmaf(cy, (float)g.ny, -0.5f);
+    const float tz = std::fmaf(cz, (float)g.nz, -0.5f);
+    const int ix = floor_to_tap(tx), iy = floor_to_tap(ty), iz = floor_to_tap(tz);
+    Taps t;
+    t.fx = tx - std::floor(tx); t.fy = ty - std::floor(ty); t.fz = tz - std::floor(tz);
+    t.x0 = address_tap(ix, g.nx, ADDRESS_CLAMP); t.x1 = address_tap(ix + 1, g.nx, ADDRESS_CLAMP);
+    t.y0 = address_tap(iy, g.ny, ADDRESS_CLAMP); t.y1 = address_tap(iy + 1, g.ny, ADDRESS_CLAMP);
+    t.z0 = address_tap(iz, g.nz, ADDRESS_CLAMP); t.z1 = address_tap(iz + 1, g.nz, ADDRESS_CLAMP);
+    return t;
+}
+inline float trilerp(const Taps& t, const float a[8]) {  // a[k]: tap k = x + 2 y + 4 z
+    const float x00 = std::fmaf(t.fx, a[1] - a[0], a[0]), x10 = std::fmaf(t.fx, a[3] - a[2], a[2]);
+    const float x01 = std::fmaf(t.fx, a[5] - a[4], a[4]), x11 = std::fmaf(t.fx, a[7] - a[6], a[6]);
+    const float y0v = std::fmaf(t.fy, x10 - x00, x00), y1v = std::fmaf(t.fy, x11 - x01, x01);
+    return std::fmaf(t.fz, y1v - y0v, y0v);
+}
+
+void ray_march_v(const Grid& g, const uint16_t* col, const uint32_t* lmap, const ViewParams& P, uint8_t* cube) {
+    const int S = (int)P.cube_size;
+    const float FMAX = 3.402823466e+38f;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
+    for (int face = 0; face < 6; ++face)
+        for (int y = 0; y < S; ++y)
+            for (int x = 0; x < S; ++x) {
+                if (((1u << face) & P.visibility_mask) == 0u) continue;
+                float ro[3];
+                for (int k = 0; k < 3; ++k) {
+                    const float* w = P.world_i + 4 * k;
+                    ro[k] = ((P.eye_pt[0] * w[0] + P.eye_pt[1] * w[1]) + P.eye_pt[2] * w[2]) + 1.0f * w[3];
+                }
+                const float X = std::fmaf(((float)x + 0.5f) / (float)S, 2.0f, -1.0f);
+                const float Z = std::fmaf(((float)y + 0.5f) / (float)S, 2.0f, -1.0f);
+                float tg[3];
+                switch (face) {
+                    case 0: tg[0] = 1.0f; tg[1] = -Z; tg[2] = -X; break;
+                    case 1: tg[0] = -1.0f; tg[1] = -Z; tg[2] = X; break;
+                    case 2: tg[0] = X; tg[1] = 1.0f; tg[2] = Z; break;
+                    case 3: tg[0] = X * 1.0f; tg[1] = -1.0f; tg[2] = Z * -1.0f; break;
+                    case 4: tg[0] = X * 1.0f; tg[1] = Z * -1.0f; tg[2] = 1.0f; break;
+                    default: tg[0] = -X; tg[1] = -Z; tg[2] = -1.0f; break;
+                }
+                float d[3], dir[3];
+                for (int k = 0; k < 3; ++k) d[k] = -ro[k] + tg[k];
+                const float inv = rsq(dp3(d, d));
+                for (int k = 0; k < 3; ++k) dir[k] = inv * d[k];
+                bool hit = true;
+                if (!(1.0f >= std::fabs(ro[0]) && 1.0f >= std::fabs(ro[1]) && 1.0f >= std::fabs(ro[2]))) {
+                    float r3[3], u[3];
+                    for (int k = 0; k < 3; ++k) {
+                        const int sg = (0.0f < dir[k] ? -1 : 0) - (dir[k] < 0.0f ? -1 : 0);  // = -sign(dir)
+                        r3[k] = -ro[k] + (float)sg;
+                    }
+                    u[0] = r3[0] / dir[0];
+                    u[1] = r3[1] / dir[1];
+                    float U = FMAX;
+                    hit = false;
+                    if (u[0] >= 0.0f && 1.0f >= std::fabs(std::fmaf(dir[1], u[0], ro[1]))) {
+                        if (1.0f >= std::fabs(std::fmaf(dir[2], u[0], ro[2]))) { hit = u[0] < FMAX; U = std::fmin(u[0], FMAX); }
+                    }
+                    if (u[1] >= 0.0f && 1.0f >= std::fabs(std::fmaf(dir[2], u[1], ro[2]))) {
+                        const bool bb = 1.0f >= std::fabs(std::fmaf(dir[0], u[1], ro[0]));
+                        if (bb && u[1] < U) { U = u[1]; hit = true; }
+                    }
+                    u[2] = r3[2] / dir[2];
+                    if (u[2] >= 0.0f && 1.0f >= std::fabs(std::fmaf(dir[0], u[2], ro[0]))) {
+                        const bool bb = 1.0f >= std::fabs(std::fmaf(dir[1], u[2], ro[1]));
+                        if (bb && u[2] < U) { U = u[2]; hit = true; }
+                    }
+                    for (int k = 0; k < 3; ++k) ro[k] = std::fmin(std::fmax(std::fmaf(dir[k], U, ro[k]), -1.0f), 1.0f);
+                }
+                if (!hit) continue;
+                const float step = 3.464101552963257f / (float)P.num_samples;
+                float tm[3];
+                for (int k = 0; k < 3; ++k) tm[k] = (tg[k] + -ro[k]) / dir[k];
+                const float tmax = std::fmax(tm[2], std::fmax(tm[1], tm[0]));
+                float sc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, t = 0.0f, prev = 0.0f;
+                for (uint32_t i = 0; i < P.num_samples; ++i) {
+                    float pos[3];
+                    for (int k = 0; k < 3; ++k) pos[k] = std::fmaf(dir[k], t, ro[k]);
+                    if (1.0f < std::fabs(pos[0]) || 1.0f < std::fabs(pos[1]) || 1.0f < std::fabs(pos[2])) break;
+                    const Taps tp = clamp_taps(g, std::fmaf(pos[0], 0.5f, 0.5f), std::fmaf(pos[1], 0.5f, 0.5f),
+                                               std::fmaf(pos[2], 0.5f, 0.5f));
+                    const size_t idx[8] = {g.idx(tp.x0, tp.y0, tp.z0), g.idx(tp.x1, tp.y0, tp.z0), g.idx(tp.x0, tp.y1, tp.z0),
+                                           g.idx(tp.x1, tp.y1, tp.z0), g.idx(tp.x0, tp.y0, tp.z1), g.idx(tp.x1, tp.y0, tp.z1),
+                                           g.idx(tp.x0, tp.y1, tp.z1), g.idx(tp.x1, tp.y1, tp.z1)};
+                    float c[4], a[8];
+                    for (int ch = 0; ch < 4; ++ch) {
+                        for (int k = 0; k < 8; ++k) a[k] = half_to_float(col[4 * idx[k] + ch]);
+                        c[ch] = trilerp(tp, a);
+                    }
+                    float r5[4], new_step;
+                    if (0.01f < c[3]) {
+                        float L[3], tex[8][3];
+                        for (int k = 0; k < 8; ++k) unpack_r11g11b10(lmap[idx[k]], tex[k]);
+                        for (int ch = 0; ch < 3; ++ch) {
+                            for (int k = 0; k < 8; ++k) a[k] = tex[k][ch];
+                            L[ch] = trilerp(tp, a);
+                        }
+                        const float transm = -sc[3] + 1.0f;
+                        const float ev = std::fmin(0.00390625f / std::fabs(-prev + c[3]), 2.0f);
+                        const float ui = std::fmin(-c[3] + 1.0f, 1.0f);
+                        const float th = -transm + 1.0f;
+                        new_step = std::fmax(th * (ui * (ev * 1.5f)), 1.0f) * step;
+                        for (int ch = 0; ch < 3; ++ch) r5[ch] = std::fmaf(transm * (L[ch] * c[ch]), 0.8f, sc[ch]);
+                        r5[3] = std::fmaf(0.8f * c[3], transm, sc[3]);
+                        if (transm < 0.01f) { std::memcpy(sc, r5, sizeof sc); break; }
+                        prev = c[3];
+                    } else {
+                        std::memcpy(r5, sc, sizeof sc);
+                        new_step = step;
+                    }
+                    t = t + new_step;
+                    std::memcpy(sc, r5, sizeof sc);
+                    if (tmax < t) break;
+                }
+                uint8_t* o = cube + 4 * (((size_t)face * S + y) * S + x);
+                for (int ch = 0; ch < 4; ++ch) {
+                    float v = ch < 3 ? sc[ch] * 0.15915493667125702f : sc[ch];  // 0x3e22f983 = 1 / (2 pi)
+                    v = std::isnan(v) ? 0.0f : std::fmin(std::fmax(v, 0.0f), 1.0f);
+                    o[ch] = (uint8_t)(v * 255.0f + 0.5f);
+                }
+            }
+}
+
 struct Oracle {
     Grid g;
     int address_mode, early_exit, iters;
@@ -668,6 +831,13 @@ void fxo_gradient_slab(int nx, int ny, int nz, int nzg, int z0, const uint16_t* 
 void fxo_light_map(int nx, int ny, int nz, const uint16_t* colour, const void* params, uint32_t* out) {
     light_map(Grid{nx, ny, nz}, colour, *static_cast<const LightParams*>(params), out);
 }
+// Cube-map ray march: light_map = fxo_light_map's output; cube = [6][S][S][4] UNORM8, S = params.cube_size; texels of
+// culled faces / rays that miss the volume are left untouched.
+void fxo_ray_march_v(int nx, int ny, int nz, const uint16_t* colour, const uint32_t* light_map, const void* params,
+                     uint8_t* cube) {
+    ray_march_v(Grid{nx, ny, nz}, colour, light_map, *static_cast<const ViewParams*>(params), cube);
+}
+void fxo_unpack_r11g11b10(uint32_t w, float* out3) { unpack_r11g11b10(w, out3); }
 uint32_t fxo_pack_r11g11b10(float r, float g, float b) {
     const float rgb[3] = {r, g, b};
     return pack_r11g11b10(rgb);

@@ -33,7 +33,8 @@ import numpy as np
 
 F32, U32, I32 = np.float32, np.uint32, np.int32
 
-OPCODES = {0: "add", 1: "and", 2: "break", 3: "breakc", 14: "div", 16: "dp3", 18: "else", 21: "endif", 22: "endloop", 25: "exp",
+OPCODES = {0: "add", 1: "and", 2: "break", 3: "breakc", 6: "case", 10: "default", 14: "div", 16: "dp3", 17: "dp4", 18: "else",
+           23: "endswitch", 41: "ishl", 43: "itof", 76: "switch", 21: "endif", 22: "endloop", 25: "exp",
            60: "or", 68: "rsq", 162: "dcl_resource_structured", 167: "ld_structured",
            29: "ge", 30: "iadd", 31: "if", 45: "ld", 48: "loop", 49: "lt", 50: "mad", 51: "min", 52: "max", 54: "mov",
            55: "movc", 56: "mul", 61: "resinfo", 62: "ret", 72: "sample_l", 80: "uge", 83: "umax", 84: "umin", 86: "utof",
@@ -271,10 +272,31 @@ def pack_r11g11b10(rgb):
     return out.astype(U32)
 
 
+def unpack_r11g11b10(words):
+    """DXGI_FORMAT_R11G11B10_FLOAT words -> fp32 [..., 3] (exact: every such value is an fp32)."""
+    w = np.asarray(words, U32)
+    out = np.zeros(w.shape + (3,), F32)
+    for k, (mb, sh) in enumerate(((6, 0), (6, 11), (5, 22))):
+        f = (w >> U32(sh)) & U32((1 << (mb + 5)) - 1)
+        e, m = (f >> U32(mb)).astype(np.int64), (f & U32((1 << mb) - 1)).astype(np.float64)
+        v = np.where(e == 0, m * 2.0 ** (-14 - mb), (1 + m / (1 << mb)) * 2.0 ** (e - 15.0))
+        v = np.where(e == 31, np.where(m == 0, np.inf, np.nan), v)
+        out[..., k] = v.astype(F32)
+    return out
+
+
+def float_to_unorm8(v):
+    """fp32 -> UNORM8 as D3D converts on a typed UAV store (restated): NaN -> 0, clamp to [0, 1], scale by 255, add
+    0.5, truncate."""
+    v = np.asarray(v, F32)
+    c = np.where(np.isnan(v), F32(0), np.clip(v, F32(0), F32(1))).astype(F32)
+    return ((c * F32(255.0)).astype(F32) + F32(0.5)).astype(F32).astype(np.uint8)
+
+
 # ---- the machine ------------------------------------------------------------------------------------------------------
 class Texture:
     """A 3D texture / typed UAV.  fmt 'rgba16f': data [nz, ny, nx, 4] float16; 'r32f': data [nz, ny, nx] float32;
-    'r11g11b10f': data [nz, ny, nx] uint32 (written only)."""
+    'r11g11b10f': data [nz, ny, nx] uint32; 'rgba8unorm': data [slices, ny, nx, 4] uint8 (a Texture2DArray UAV)."""
 
     def __init__(self, data, fmt):
         self.data, self.fmt = data, fmt
@@ -286,6 +308,10 @@ class Texture:
     def texels_f32(self):
         if self.fmt == "rgba16f":
             return self.data.astype(F32)
+        if self.fmt == "r11g11b10f":
+            out = np.ones(self.data.shape + (4,), F32)
+            out[..., :3] = unpack_r11g11b10(self.data)
+            return out
         out = np.zeros(self.data.shape + (4,), F32)
         out[..., 0] = self.data
         out[..., 3] = 1.0
@@ -311,6 +337,7 @@ class Machine:
         self.cb = {k: np.asarray(v, U32).reshape(-1, 4) for k, v in cb0.items()} if isinstance(cb0, dict) else \
             {0: np.asarray(cb0, U32).reshape(1, 4)}
         self.srv, self.uav, self.clamp = srv, uav, clamp
+        self.retired = np.zeros(self.n, bool)  # threads that executed `ret` inside control flow
         self.iterations = 0     # trips of the relaxation loop in which at least one thread was inside
         self.active_entering = []  # threads inside the loop at the start of each trip
 
@@ -335,6 +362,13 @@ class Machine:
         if o.neg:
             v = v ^ U32(0x80000000)
         return np.ascontiguousarray(v, U32)
+
+    def read_int(self, o: Operand) -> np.ndarray:
+        """Operand of an integer instruction: the `-` modifier is two's-complement negation there."""
+        if not o.neg:
+            return self.read(o)
+        plain = Operand(kind=o.kind, index=o.index, ncomp=o.ncomp, mode=o.mode, mask=o.mask, swizzle=o.swizzle, imm=o.imm)
+        return (~self.read(plain) + U32(1)).astype(U32)
 
     def write(self, o: Operand, value_u32, mask_threads, sat=False):
         assert o.kind == "r" and o.mode == "mask"
@@ -361,7 +395,28 @@ class Machine:
             pc += 1
             with np.errstate(all="ignore"):
                 if op == "ret":
-                    break
+                    if not stack:
+                        break
+                    self.retired |= M
+                    M = M & ~self.retired
+                elif op == "switch":
+                    # frame: kind, mask on entry, selector, threads that matched a case so far, threads that left
+                    stack.append(["switch", M.copy(), self.read(ops[0])[:, 0].copy(), np.zeros(self.n, bool),
+                                  np.zeros(self.n, bool)])
+                    M = np.zeros(self.n, bool)
+                elif op in ("case", "default"):
+                    fr = stack[-1]
+                    assert fr[0] == "switch"
+                    if op == "case":
+                        hit = fr[1] & ~fr[4] & (fr[2] == U32(ops[0].imm[0]))
+                    else:
+                        hit = fr[1] & ~fr[4] & ~fr[3]
+                    fr[3] |= hit
+                    M = (M | hit) & ~self.retired  # threads falling through from the previous case keep running
+                elif op == "endswitch":
+                    fr = stack.pop()
+                    assert fr[0] == "switch"
+                    M = fr[1] & ~self.retired
                 elif op == "if":
                     c = self.read(ops[0])[:, 0] != 0
                     M0 = M.copy()
@@ -374,7 +429,9 @@ class Machine:
                     for fr in stack:
                         if fr[0] == "loop":
                             broken = broken | fr[3]
-                    M = saved & ~taken & ~broken
+                        elif fr[0] == "switch":
+                            broken = broken | fr[4]
+                    M = saved & ~taken & ~broken & ~self.retired
                 elif op == "endif":
                     kind, saved, _ = stack.pop()
                     assert kind == "if"
@@ -382,14 +439,16 @@ class Machine:
                     for fr in stack:
                         if fr[0] == "loop":
                             broken = broken | fr[3]
-                    M = saved & ~broken
+                        elif fr[0] == "switch":
+                            broken = broken | fr[4]
+                    M = saved & ~broken & ~self.retired
                 elif op == "loop":
                     stack.append(["loop", pc, M.copy(), np.zeros(self.n, bool)])
                     self.active_entering.append(int(M.sum()))
                 elif op in ("breakc", "break"):
-                    fr = [s for s in stack if s[0] == "loop"][-1]
+                    fr = [s for s in stack if s[0] in ("loop", "switch")][-1]
                     c = np.ones(self.n, bool) if op == "break" else (self.read(ops[0])[:, 0] != 0) == ins.test_nz
-                    fr[3] |= M & c
+                    fr[4 if fr[0] == "switch" else 3] |= M & c
                     M = M & ~c
                 elif op == "endloop":
                     fr = stack[-1]
@@ -403,7 +462,7 @@ class Machine:
                         pc = fr[1]
                     else:
                         stack.pop()
-                        M = fr[2]
+                        M = fr[2] & ~self.retired
                 elif op == "sync":
                     for slot, arr in pending.items():
                         self.uav[slot].data[...] = arr
@@ -455,8 +514,19 @@ class Machine:
                 elif op in ("umax", "umin"):
                     a, b = self.read(ops[1]), self.read(ops[2])
                     self.write(ops[0], np.maximum(a, b) if op == "umax" else np.minimum(a, b), M)
-                elif op == "iadd":
+                elif op == "dp4":
+                    a, b = f(self.read(ops[1])), f(self.read(ops[2]))
+                    d = ((a[:, 0] * b[:, 0]).astype(F32) + (a[:, 1] * b[:, 1]).astype(F32)).astype(F32)
+                    d = (d + (a[:, 2] * b[:, 2]).astype(F32)).astype(F32)
+                    d = (d + (a[:, 3] * b[:, 3]).astype(F32)).astype(F32)
+                    self.write(ops[0], u(np.repeat(d[:, None], 4, 1)), M, ins.sat)
+                elif op == "ishl":
                     a, b = self.read(ops[1]), self.read(ops[2])
+                    self.write(ops[0], (a.astype(np.uint64) << (b & U32(31)).astype(np.uint64)).astype(U32), M)
+                elif op == "itof":
+                    self.write(ops[0], u(self.read(ops[1]).view(I32).astype(F32)), M)
+                elif op == "iadd":
+                    a, b = (self.read_int(o) for o in ops[1:3])
                     self.write(ops[0], (a.astype(np.uint64) + b.astype(np.uint64)).astype(U32), M)
                 elif op == "utof":
                     self.write(ops[0], u(self.read(ops[1]).astype(F32)), M)
@@ -491,6 +561,8 @@ class Machine:
                         target = tex.data
                     if tex.fmt == "r11g11b10f":
                         target[c[:, 2], c[:, 1], c[:, 0]] = pack_r11g11b10(v[:, :3])
+                    elif tex.fmt == "rgba8unorm":
+                        target[c[:, 2], c[:, 1], c[:, 0]] = float_to_unorm8(v)
                     elif tex.fmt == "rgba16f":
                         target[c[:, 2], c[:, 1], c[:, 0]] = v.astype(np.float16)  # round to nearest even
                     else:

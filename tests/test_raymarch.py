@@ -1,0 +1,102 @@
+"""Cube-map ray march with the separate light pass (CSRayMarchV): the oracle's restatement against
+golden vectors produced by executing the reference's own Bin/CSRayMarchL.cso + Bin/CSRayMarchV.cso
+(tests/golden/make_raymarch_golden.py), plus known answers.  CUDA path: tests/test_zzz_gpu_raymarch.py."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.test_lightmap import oracle_params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_lightmap_golden import colour_field, light_constants  # noqa: E402
+from make_raymarch_golden import CASES, view_constants, visibility_mask  # noqa: E402
+
+GOLDEN = os.path.join(HERE, "golden", "raymarch_golden.npz")
+
+
+def view_params(plain) -> oracle.ViewParams:
+    p = oracle.ViewParams()
+    p.eye_pt[:] = plain["eye_pt"].tolist()
+    p.world_i[:] = plain["world_i"].reshape(-1).tolist()
+    p.num_samples, p.visibility_mask, p.cube_size = plain["num_samples"], plain["visibility_mask"], plain["cube_size"]
+    return p
+
+
+def case_inputs(golden, name):
+    """(colour, light constants, view constants) exactly as make_raymarch_golden.run_case builds them."""
+    grid, seed, light_samples, probes, ray_samples, cube_size, eye, faces_off = CASES[name]
+    col = colour_field(grid, seed)
+    col[..., :3] = (col[..., :3].astype(np.float32) * 1.5).astype(np.float16)
+    cbs_l, plain_l = light_constants(light_samples, probes, (75.0, 75.0, -75.0), seed)
+    plain_l["light_color"][3] = 2.0
+    plain_l["ambient"][3] = 0.5
+    _, plain_v = view_constants(cbs_l, plain_l, ray_samples, cube_size, eye, faces_off)
+    digest = hashlib.sha256(col.tobytes() + plain_l["sh"].tobytes()).digest()
+    assert bytes(golden[name + "/input_sha256"]) == digest, "the seeded inputs are not the ones the vectors were made from"
+    return col, plain_l, plain_v
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_the_interpreted_bytecode(golden, name):
+    col, plain_l, plain_v = case_inputs(golden, name)
+    lmap = oracle.light_map(col, oracle_params(plain_l))
+    assert np.array_equal(lmap, golden[name + "/light_map"])
+    got = oracle.ray_march_v(col, lmap, view_params(plain_v))
+    want = golden[name + "/cube_map"]
+    assert got.shape == want.shape and np.array_equal(got, want), (name, int((got != want).sum()))
+    assert (want[..., 3] > 0).sum() > 50 and len(np.unique(want.reshape(-1, 4), axis=0)) > 50
+
+
+def test_unpack_is_the_inverse_of_pack_on_every_word_class():
+    r = np.random.default_rng(3)
+    words = np.concatenate([r.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32),
+                            np.array([0, 1, 1 << 6, 63, 0x7FF, 31 << 6, (31 << 6) | 1, 0xFFFFFFFF, 1 << 22, 31 << 27], np.uint32)])
+    import dxbc_interp as D
+    ref = D.unpack_r11g11b10(words)
+    for w, want in zip(words.tolist(), ref):
+        got = oracle.unpack_r11g11b10(w)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) or (np.isnan(got) == np.isnan(want)).all(), hex(w)
+        if np.isfinite(got).all():
+            assert oracle.pack_r11g11b10(*map(float, got)) == w
+
+
+def test_known_answers_without_bytecode():
+    n = 8
+    col = np.zeros((n, n, n, 4), np.float16)
+    _, plain_l = light_constants(16, 0, (0.0, 100.0, 0.0), 1)
+    plain_l["world_i"][:] = 0
+    plain_l["world_i"][[0, 1, 2], [0, 1, 2]] = 0.1
+    lmap = oracle.light_map(col, oracle_params(plain_l))
+    eye = (0.0, 0.0, -30.0)
+    plain_v = {"eye_pt": np.array(eye, np.float32), "world_i": plain_l["world_i"], "num_samples": 32,
+               "visibility_mask": visibility_mask(plain_l["world_i"], eye), "cube_size": 8}
+    # The cube map holds what is seen THROUGH the volume on the far side: a ray runs from the eye to its texel on a cube
+    # face, so an eye in front of the -z face marches every face but -z itself (IsCubeFaceVisible, Fluid.cpp:41-46).
+    # An empty volume scatters nothing: every marched texel is written as 0, previous contents survive elsewhere.
+    assert plain_v["visibility_mask"] == 0b011111
+    prev = np.full((6, 8, 8, 4), 7, np.uint8)
+    out = oracle.ray_march_v(col, lmap, view_params(plain_v), cube=prev)
+    assert np.all(out[5] == 7)                          # -z face culled: untouched
+    assert np.all(out[4] == 0)                          # +z face: every ray crosses the box
+    # a uniform medium lit from +y: nearly opaque at the centre, mirror-symmetric in x, brighter towards the light
+    col[..., 3] = 0.5
+    col[..., :3] = 0.25
+    lmap = oracle.light_map(col, oracle_params(plain_l))
+    out = oracle.ray_march_v(col, lmap, view_params(plain_v))
+    centre = out[4, 3:5, 3:5]
+    assert np.all(centre[..., 3] > 200) and np.array_equal(centre[:, 0], centre[:, 1])
+    assert np.all(centre[0, 0, :3] > centre[1, 0, :3])   # texel row 3 is above row 4 (pos.y = -y, CSRayMarch.hlsl:46)
+    # fewer samples -> less accumulated opacity
+    plain_v["num_samples"] = 2
+    out2 = oracle.ray_march_v(col, lmap, view_params(plain_v))
+    assert out2[4, 3, 3, 3] < out[4, 3, 3, 3]
