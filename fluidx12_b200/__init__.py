@@ -20,6 +20,7 @@ from .binding import (  # noqa: F401
     FxbConfig,
     FxbLightParams,
     FxbStats,
+    FxbViewParams,
     FxbVolumeHeader,
     dt_for_grid,
     lib,
@@ -30,7 +31,7 @@ from .slab import slab_range, halo_plan  # noqa: F401
 from . import volume  # noqa: F401
 
 __all__ = [
-    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader", "FxbLightParams",
+    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader", "FxbLightParams", "FxbViewParams",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
     "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV",
 ]

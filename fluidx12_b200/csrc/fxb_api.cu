@@ -91,6 +91,8 @@ struct fxb_sim {
     bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
     bool pass0_tail = false;  // FXB_PASS0=2 (with FXB_TAIL=1, T = 2): pass 0 by the block-resident kernel (experimental)
     unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
+    unsigned* cube_map = nullptr;          // one mip of m_cubeMap (Fluid.cpp:229-232): [6][S][S] RGBA8 words
+    uint32_t cube_size = 0;
     unsigned short* light_density = nullptr;  // colour.w of every voxel, the channel the light-map pass samples
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};
@@ -642,6 +644,7 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.work_count);
     cudaFree(s->jac.brick_state);
     cudaFree(s->light_map);
+    cudaFree(s->cube_map);
     cudaFree(s->light_density);
     cudaFree(s->emitter_basis);
     cudaFree(s->axis_tables);
@@ -837,6 +840,52 @@ int fxb_get_light_map(fxb_sim* s, void* host, size_t bytes) {
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     FXB_CUDA(cudaDeviceSynchronize());
     FXB_CUDA(cudaMemcpy(host, s->light_map, bytes, cudaMemcpyDeviceToHost));
+    return FXB_OK;
+}
+
+// ---- cube-map ray march (Fluid::rayMarchV, Fluid.cpp:880-908; kernel in raymarch.cu) --------------------------------
+static_assert(sizeof(fxb_view_params) == 4 * (3 + 12 + 3), "fxb_view_params is passed to the kernel as is");
+
+int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask) {
+    if (!world_i || !eye_pt || !mask) return fail(FXB_ERR_INVALID, "fxb_cube_visibility_mask: null argument");
+    uint32_t m = 0;
+    for (int face = 0; face < 6; ++face) {
+        const float* w = world_i + 4 * (face >> 1);
+        const float v = ((eye_pt[0] * w[0] + eye_pt[1] * w[1]) + eye_pt[2] * w[2]) + w[3];
+        m |= (uint32_t)((face & 1) ? v > -1.0f : v < 1.0f) << face;  // IsCubeFaceVisible, Fluid.cpp:41-46
+    }
+    *mask = m;
+    return FXB_OK;
+}
+
+int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
+    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");
+    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids on one GPU only");
+    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: fxb_light_map has not run (the light map is an input)");
+    if (params->cube_size < 1 || params->cube_size > 4096) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: cube_size out of range");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (s->cube_size != params->cube_size) {
+        FXB_CUDA(cudaDeviceSynchronize());
+        cudaFree(s->cube_map);
+        s->cube_map = nullptr;
+        s->cube_size = 0;
+        const size_t bytes = (size_t)6 * params->cube_size * params->cube_size * sizeof(unsigned);
+        FXB_CUDA(cudaMalloc((void**)&s->cube_map, bytes));
+        FXB_CUDA(cudaMemset(s->cube_map, 0, bytes));
+        s->cube_size = params->cube_size;
+    }
+    FXB_CUDA(fxb::launch_ray_march_v(s->dom, s->col[s->parity], s->light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
+    s->last_stream = (cudaStream_t)cuda_stream;
+    return FXB_OK;
+}
+
+int fxb_get_cube_map(fxb_sim* s, void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: null argument");
+    if (!s->cube_map) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: fxb_ray_march_v has not run");
+    if (bytes != (size_t)6 * s->cube_size * s->cube_size * 4) return fail(FXB_ERR_SIZE, "fxb_get_cube_map: size mismatch");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    FXB_CUDA(cudaMemcpy(host, s->cube_map, bytes, cudaMemcpyDeviceToHost));
     return FXB_OK;
 }
 

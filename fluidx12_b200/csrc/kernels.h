@@ -16,6 +16,10 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
 cudaError_t launch_light_map(const Domain& d, const void* colour, unsigned short* dens, unsigned* out,
                              const void* consts, cudaStream_t stream);
 
+// raymarch.cu — the view-ray march into the cube map (CSRayMarchV); consts = fxb_view_params
+cudaError_t launch_ray_march_v(const Domain& d, const void* colour, const unsigned* light_map, unsigned* cube,
+                               const void* consts, cudaStream_t stream);
+
 // project_simple.cu — one kernel per logical pass (cross-check path, kernel_path = 1)
 void launch_begin_step(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 void launch_divergence(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, cudaStream_t stream);

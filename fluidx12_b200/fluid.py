@@ -145,6 +145,20 @@ class Fluid:
         B.check(B.lib().fxb_get_light_map(self._handle(), a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 
+    # -- Fluid::rayMarchV (Fluid.cpp:880-908): view rays into one mip of the cube map -------------------------------
+    def RayMarchV(self, params: "B.FxbViewParams", pCommandList=None) -> None:
+        """Enqueues CSRayMarchV (needs the light map of ``RayMarchL``) on the CUDA stream ``pCommandList``."""
+        stream = C.c_void_p(int(pCommandList)) if pCommandList else C.c_void_p(0)
+        B.check(B.lib().fxb_ray_march_v(self._handle(), C.byref(params), stream))
+        self._cube_size = int(params.cube_size)
+
+    def get_cube_map(self) -> np.ndarray:
+        """The cube-map mip last written: [6][S][S][4] UNORM8 (faces +X, -X, +Y, -Y, +Z, -Z)."""
+        s = getattr(self, "_cube_size", 0)
+        a = np.empty((6, s, s, 4), np.uint8)
+        B.check(B.lib().fxb_get_cube_map(self._handle(), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return a
+
     def export(self, path: str, field: int = B.FIELD_COLOR) -> None:
         """Writes this rank's slab of ``field`` as a volume file (fluidx12_b200/volume.py): by default the colour
         field ``Fluid::Render`` would sample, m_colors[m_frameParity] (Fluid.cpp:760-770, 841)."""

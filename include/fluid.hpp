@@ -71,6 +71,9 @@ public:
     // Fluid::rayMarchL (Fluid.cpp:857-878), the light-map pass of Fluid::Render: CSRayMarchL over m_colors[m_frameParity].
     int RayMarchL(const fxb_light_params& params, void* stream = nullptr) { return fxb_light_map(m_sim, &params, stream); }
 
+    // Fluid::rayMarchV (Fluid.cpp:880-908): CSRayMarchV into one mip of the cube map, lit by RayMarchL's light map.
+    int RayMarchV(const fxb_view_params& params, void* stream = nullptr) { return fxb_ray_march_v(m_sim, &params, stream); }
+
     // No counterpart in the reference, whose renderer binds m_colors[m_frameParity] in place (Fluid.cpp:760-770, 841):
     // writes the field as a volume file for a renderer outside the process (fluidx_b200.h, fxb_volume_header).
     bool Export(const char* path, int field = FXB_FIELD_COLOR) {

@@ -179,6 +179,29 @@ int fxb_light_map(fxb_sim* sim, const fxb_light_params* params, void* cuda_strea
  * 0-10, G 11-21, B 22-31); bytes = nx*ny*nz*4.  Fails if fxb_light_map has not run. */
 int fxb_get_light_map(fxb_sim* sim, void* host, size_t bytes);
 
+/* ---- Cube-map ray march with the separate light pass ------------------------------------------
+ * Fluid::rayMarchV (Fluid.cpp:880-908): CSRayMarchV (= CSRayMarch.hlsl:98-196 with _LIGHT_PASS_) marches one view ray
+ * per texel of the six faces of mip m_cubeMapLOD of the R8G8B8A8_UNORM cube map (Fluid.cpp:229-232) through
+ * m_colors[m_frameParity], lit by the light map of fxb_light_map.  The shipped shader culls faces by a host-computed
+ * mask (_CPU_CUBE_FACE_CULL_ == 1, Fluid.cpp:51-63, 900). */
+typedef struct fxb_view_params {
+    float eye_pt[3];          /* cbPerFrame g_eyePt (Fluid.cpp:302) */
+    float world_i[12];        /* cbPerObject g_worldI, three float4 registers (Fluid.cpp:318) */
+    uint32_t num_samples;     /* cbSampleRes g_numSamples = m_raySampleCount (Fluid.cpp:324-327, 898; at most 192, :174) */
+    uint32_t visibility_mask; /* bit i: face i (+X, -X, +Y, -Y, +Z, -Z) is marched; fxb_cube_visibility_mask */
+    uint32_t cube_size;       /* edge of the cube-map mip written: m_gridSize.x >> m_cubeMapLOD (Fluid.cpp:906) */
+} fxb_view_params;
+
+/* GenVisibilityMask (Fluid.cpp:51-63), no GPU needed: a face is marched iff the eye, in volume space, is on the inner
+ * side of its plane (the cube map holds what is seen THROUGH the volume on the far faces). */
+int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask);
+/* Replaces Fluid::rayMarchV: enqueues the march on `cuda_stream`.  fxb_light_map must have run (the light map is an
+ * input).  Texels of culled faces and of rays that miss the volume keep their previous contents, as in the reference
+ * (zero after allocation or after a change of cube_size).  1 <= cube_size <= 4096.  3D grids, nranks == 1. */
+int fxb_ray_march_v(fxb_sim* sim, const fxb_view_params* params, void* cuda_stream);
+/* Synchronous copy of the cube map written by the last fxb_ray_march_v: [6][S][S][4] bytes (R, G, B, A UNORM8). */
+int fxb_get_cube_map(fxb_sim* sim, void* host, size_t bytes);
+
 /* ---- Volume files: the hand-off format of a field to a renderer ------------------------------
  * The reference never leaves the GPU: Fluid::Render binds m_colors[m_frameParity] as a Texture3D SRV
  * (Fluid.cpp:760-770, 841/870/897) and its ray marchers sample it as premultiplied RGBA with the density in .w

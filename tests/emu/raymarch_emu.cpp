@@ -1,0 +1,25 @@
+// raymarch_emu.cpp — CPU run of the cube-map ray-march kernel's per-texel body (raymarch_body.cuh).  TEST
+// INFRASTRUCTURE: compared bit for bit with the oracle and the golden vectors by tests/test_raymarch_emu.py.
+#include <cstdint>
+
+#include "../../fluidx12_b200/csrc/raymarch_body.cuh"
+
+extern "C" {
+
+// colour: [nz][ny][nx] 8-byte texels; light_map: [nz][ny][nx] words; params: fxb::ViewConsts; cube: [6][S][S] words
+void raymarch_emu_run(int nx, int ny, int nz, const uint64_t* colour, const uint32_t* light_map, const void* params,
+                      uint32_t* cube) {
+    using namespace fxb;
+    const LightGeom g{nx, ny, nz};
+    const ViewConsts& P = *static_cast<const ViewConsts*>(params);
+    const int S = (int)P.cube_size;
+    for (int face = 0; face < 6; ++face)
+        for (int y = 0; y < S; ++y)
+            for (int x = 0; x < S; ++x) {
+                unsigned w;
+                if (ray_march_texel(reinterpret_cast<const RU2*>(colour), light_map, g, P, x, y, face, &w))
+                    cube[((size_t)face * S + y) * S + x] = w;
+            }
+}
+
+}  // extern "C"

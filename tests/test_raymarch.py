@@ -100,3 +100,22 @@ def test_known_answers_without_bytecode():
     plain_v["num_samples"] = 2
     out2 = oracle.ray_march_v(col, lmap, view_params(plain_v))
     assert out2[4, 3, 3, 3] < out[4, 3, 3, 3]
+
+
+def test_visibility_mask_of_the_library_is_the_references_rule():
+    """fxb_cube_visibility_mask (host code of the product, needs no GPU) = GenVisibilityMask (Fluid.cpp:51-63)."""
+    import ctypes as C
+
+    import fluidx12_b200 as fx
+    L = fx.lib()
+    r = np.random.default_rng(8)
+    fp = C.POINTER(C.c_float)
+    for _ in range(200):
+        wi = (r.standard_normal((3, 4)) * 0.1).astype(np.float32)
+        eye = (r.standard_normal(3) * 20).astype(np.float32)
+        m = C.c_uint32()
+        assert L.fxb_cube_visibility_mask(wi.ctypes.data_as(fp), eye.ctypes.data_as(fp), C.byref(m)) == 0
+        assert m.value == visibility_mask(wi, eye), (wi, eye)
+    assert L.fxb_cube_visibility_mask(None, None, None) == fx.binding.FXB_ERR_INVALID
+    assert L.fxb_ray_march_v(None, None, None) == fx.binding.FXB_ERR_INVALID
+    assert L.fxb_get_cube_map(None, None, 0) == fx.binding.FXB_ERR_INVALID

@@ -146,6 +146,25 @@ def light_map_timing(fx, n, spin=100, reps=5):
             emit(stage="light_map", grid=n, probes=probes, ms=round(ms, 4), voxels_with_smoke=lit,
                  gvoxels_per_s=round(vox / ms / 1e6, 2), algorithmic_gbs=round(12.0 * vox / ms / 1e6, 1),
                  words_distinct=int(len(np.unique(f.get_light_map()[::4, ::4, ::4]))))
+        # the view-ray march into the cube map (fxb_ray_march_v), lit by the light map just written
+        import ctypes as C
+        v = fx.FxbViewParams()
+        v.eye_pt[:] = [4.0, 16.0, -40.0]
+        v.world_i[:] = [0.1, 0, 0, 0, 0, 0.1, 0, 0, 0, 0, 0.1, 0]
+        v.num_samples, v.cube_size = 192, n[0]
+        mask = C.c_uint32()
+        fx.lib().fxb_cube_visibility_mask(v.world_i, v.eye_pt, C.byref(mask))
+        v.visibility_mask = mask.value
+        f.RayMarchV(v)
+        f.sync()
+        t = time.perf_counter()
+        for _ in range(reps):
+            f.RayMarchV(v)
+        f.sync()
+        ms = (time.perf_counter() - t) / reps * 1e3
+        cube = f.get_cube_map()
+        emit(stage="light_map", grid=n, pass_="ray_march_v", cube_size=n[0], ray_samples=192, ms=round(ms, 4),
+             mrays_per_s=round(6 * n[0] * n[0] / ms / 1e3, 2), texels_with_smoke=int((cube[..., 3] > 0).sum()))
         f.close()
     except Exception as e:
         emit(stage="light_map", grid=n, error=repr(e))
