@@ -27,11 +27,11 @@ from .binding import (  # noqa: F401
     lib_path,
 )
 from .fluid import Fluid, FluidEZ  # noqa: F401
-from .slab import slab_range, halo_plan  # noqa: F401
+from .slab import gather_plan, halo_plan, slab_range  # noqa: F401
 from . import volume  # noqa: F401
 
 __all__ = [
-    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "volume", "FxbVolumeHeader", "FxbLightParams", "FxbViewParams",
+    "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "gather_plan", "volume", "FxbVolumeHeader", "FxbLightParams", "FxbViewParams",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
     "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV",
 ]

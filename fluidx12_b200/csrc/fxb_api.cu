@@ -820,15 +820,21 @@ static_assert(sizeof(fxb_light_params) == 4 * (3 + 4 + 4 + 12 + 12 + 2 + 27), "f
 int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream) {
     if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_light_map: null argument");
     if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_light_map: 3D grids only (the reference renders none other, Fluid.cpp:296)");
-    if (s->multi()) return fail(FXB_ERR_INVALID, "fxb_light_map: nranks > 1 is not supported (a light ray crosses every z-slab)");
+    if (s->multi() && s->plane_voxels() % 4 != 0)  // 16-byte loads / 8-byte stores of the extraction start at a plane
+        return fail(FXB_ERR_INVALID, "fxb_light_map: with nranks > 1 nx * ny must be a multiple of 4");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     if (!s->light_map) {
+        // the light map covers the rank's own planes; the density scratch covers the WHOLE grid, because a light ray
+        // crosses every z-slab (2 bytes per voxel; the other ranks' planes arrive over NCCL inside the pass)
         FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
-        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->own_voxels() + 4) * sizeof(unsigned short)));
+        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
     }
     // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
-    FXB_CUDA(fxb::launch_light_map(s->dom, s->col[s->parity], s->light_density, s->light_map, params,
-                                   (cudaStream_t)cuda_stream));
+    const char* colour_own = static_cast<const char*>(s->col[s->parity]) + s->own_offset() * 8;
+    if (fxb::launch_light_map(s->dom, colour_own, s->light_density, s->light_map, params, &s->comm,
+                              (cudaStream_t)cuda_stream) != cudaSuccess)
+        return fail(s->multi() ? FXB_ERR_NCCL : FXB_ERR_CUDA, "fxb_light_map: launch failed: " +
+                    (s->multi() ? fxb::halo_last_error() : std::string(cudaGetErrorString(cudaGetLastError()))));
     s->last_stream = (cudaStream_t)cuda_stream;
     return FXB_OK;
 }

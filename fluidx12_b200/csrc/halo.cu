@@ -337,6 +337,22 @@ bool HaloComm::exchange(const Domain& d, const HaloField* fields, int nfields, c
     return good && ended;
 }
 
+bool HaloComm::all_gather_slabs(void* global_base, size_t plane_bytes, int nz, cudaStream_t stream) {
+    if (nranks <= 1) return true;
+    char* base = static_cast<char*>(global_base);
+    auto z_of = [&](int r) { return (long long)r * nz / nranks; };
+    const size_t mine = (size_t)(z_of(rank + 1) - z_of(rank)) * plane_bytes;
+    if (!ok(g_api.group_start(), "ncclGroupStart")) return false;
+    bool good = true;
+    for (int peer = 0; peer < nranks && good; ++peer) {
+        if (peer == rank) continue;
+        const size_t theirs = (size_t)(z_of(peer + 1) - z_of(peer)) * plane_bytes;
+        good = ok(g_api.send(base + (size_t)z_of(rank) * plane_bytes, mine, kNcclInt8, peer, comm, stream), "ncclSend") &&
+               ok(g_api.recv(base + (size_t)z_of(peer) * plane_bytes, theirs, kNcclInt8, peer, comm, stream), "ncclRecv");
+    }
+    return ok(g_api.group_end(), "ncclGroupEnd") && good;
+}
+
 bool HaloComm::all_reduce_sum_u64(void* buf, size_t count, cudaStream_t stream) {
     if (nranks <= 1) return true;
     return ok(g_api.all_reduce(buf, buf, count, kNcclUint64, kNcclSum, comm, stream), "ncclAllReduce");

@@ -48,6 +48,10 @@ struct HaloComm {
     void destroy();
     bool exchange(const Domain& d, const HaloField* fields, int nfields, cudaStream_t stream);
     bool all_reduce_sum_u64(void* buf, size_t count, cudaStream_t stream);
+    // Every rank's owned planes of a GLOBAL array (plane 0 = global plane 0; this rank's planes already in place) are
+    // sent to every other rank: one ncclSend/ncclRecv pair per peer inside one group.  Slab r owns planes
+    // [r nz / R, (r + 1) nz / R).  Used by the light-map pass, whose rays cross every slab.
+    bool all_gather_slabs(void* global_base, size_t plane_bytes, int nz, cudaStream_t stream);
     // Maps the listed device buffers (cudaMalloc'ed, one per exchanged field) of both z neighbours; the handles travel
     // over the NCCL communicator.  z_first_lo / z_first_hi: global plane of local plane 0 on rank - 1 / rank + 1.
     bool p2p_init(void* const* buffers, int nbuffers, int z_first_lo, int z_first_hi, cudaStream_t stream);

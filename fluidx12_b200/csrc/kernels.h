@@ -13,8 +13,9 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
                    cudaStream_t stream);
 
 // lightmap.cu — the light-map pass after the step (CSRayMarchL); consts = fxb_light_params
-cudaError_t launch_light_map(const Domain& d, const void* colour, unsigned short* dens, unsigned* out,
-                             const void* consts, cudaStream_t stream);
+struct HaloComm;
+cudaError_t launch_light_map(const Domain& d, const void* colour_own, unsigned short* dens, unsigned* out,
+                             const void* consts, HaloComm* comm, cudaStream_t stream);
 
 // raymarch.cu — the view-ray march into the cube map (CSRayMarchV); consts = fxb_view_params
 cudaError_t launch_ray_march_v(const Domain& d, const void* colour, const unsigned* light_map, unsigned* cube,

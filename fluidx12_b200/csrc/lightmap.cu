@@ -13,6 +13,7 @@
 // L1/L2 (the half array of a 256^3 grid is 32 MiB).  Work per voxel is data dependent (empty voxels leave after one
 // fetch), so this pass is latency/issue bound where the plume is and streaming elsewhere.
 #include "lightmap_body.cuh"
+#include "halo.h"
 #include "kernels.h"
 
 namespace fxb {
@@ -34,27 +35,38 @@ __global__ void __launch_bounds__(256) extract_density_kernel(const uint2* __res
     }
 }
 
+// dens: the density of the WHOLE grid; this launch writes the voxels of global planes [z0, z1) (the rank's slab),
+// out plane 0 = plane z0
 __global__ void __launch_bounds__(512) light_map_kernel(const unsigned short* __restrict__ dens,
-                                                        unsigned* __restrict__ out, const LightGeom g,
-                                                        const __grid_constant__ LightConsts P) {
+                                                        unsigned* __restrict__ out, const LightGeom g, const int z0,
+                                                        const int z1, const __grid_constant__ LightConsts P) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 4 + threadIdx.y;
-    const int z = blockIdx.z * 4 + threadIdx.z;
-    if (x >= g.nx || y >= g.ny || z >= g.nz) return;
-    out[((size_t)z * g.ny + y) * g.nx + x] = light_map_voxel(dens, g, P, x, y, z);
+    const int z = z0 + blockIdx.z * 4 + threadIdx.z;
+    if (x >= g.nx || y >= g.ny || z >= z1) return;
+    out[((size_t)(z - z0) * g.ny + y) * g.nx + x] = light_map_voxel(dens, g, P, x, y, z);
 }
 
 }  // namespace
 
-cudaError_t launch_light_map(const Domain& d, const void* colour, unsigned short* dens, unsigned* out,
-                             const void* consts, cudaStream_t stream) {
-    const size_t n = (size_t)d.nx * d.ny * d.nz;
+// colour_own: the rank's owned planes of the colour field; dens: density array of the whole grid (plane 0 = global
+// plane 0).  With several ranks the owned planes are extracted in place and every other slab arrives over NCCL
+// (2 bytes per voxel of the grid per rank: a light ray crosses every slab).
+cudaError_t launch_light_map(const Domain& d, const void* colour_own, unsigned short* dens, unsigned* out,
+                             const void* consts, HaloComm* comm, cudaStream_t stream) {
+    const size_t plane = (size_t)d.nx * d.ny;
+    const size_t n = plane * (d.z_own1 - d.z_own0);
     const size_t threads = n / 4 + 1;
-    extract_density_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(static_cast<const uint2*>(colour), dens, n);
+    // the 16-byte loads and 8-byte stores of the extraction start at a plane boundary of the allocations: fxb_light_map
+    // requires nx * ny % 4 == 0 when nranks > 1
+    extract_density_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(static_cast<const uint2*>(colour_own),
+                                                                                 dens + plane * d.z_own0, n);
+    if (comm && comm->nranks > 1 && !comm->all_gather_slabs(dens, plane * sizeof(unsigned short), d.nz, stream))
+        return cudaErrorUnknown;
     const LightGeom g{d.nx, d.ny, d.nz};
     const dim3 block(32, 4, 4);
-    const dim3 grid((d.nx + 31) / 32, (d.ny + 3) / 4, (d.nz + 3) / 4);
-    light_map_kernel<<<grid, block, 0, stream>>>(dens, out, g, *static_cast<const LightConsts*>(consts));
+    const dim3 grid((d.nx + 31) / 32, (d.ny + 3) / 4, (d.z_own1 - d.z_own0 + 3) / 4);
+    light_map_kernel<<<grid, block, 0, stream>>>(dens, out, g, d.z_own0, d.z_own1, *static_cast<const LightConsts*>(consts));
     return cudaGetLastError();
 }
 

@@ -139,9 +139,9 @@ class Fluid:
         B.check(B.lib().fxb_light_map(self._handle(), C.byref(params), stream))
 
     def get_light_map(self) -> np.ndarray:
-        """m_lightMap as [z][y][x] uint32 words in R11G11B10_FLOAT packing."""
-        nx, ny, nz = self.m_gridSize
-        a = np.empty((nz, ny, nx), np.uint32)
+        """m_lightMap (this rank's planes) as [z][y][x] uint32 words in R11G11B10_FLOAT packing."""
+        nx, ny, _ = self.m_gridSize
+        a = np.empty((self._slab[1], ny, nx), np.uint32)
         B.check(B.lib().fxb_get_light_map(self._handle(), a.ctypes.data_as(C.c_void_p), a.nbytes))
         return a
 

@@ -72,3 +72,11 @@ def halo_plan(nz: int, rank: int, nranks: int, fuse_t: int, h_adv: int = 0, grou
     return HaloPlan(z0, z1, z_first, z_last - z_first, halo,
                     _faces(nz, rank, nranks, h_adv + 1), _faces(nz, rank, nranks, 1),
                     _faces(nz, rank, nranks, group * fuse_t), group)
+
+
+def gather_plan(nz: int, rank: int, nranks: int) -> List[Exchange]:
+    """The light-map pass's exchange (csrc/halo.cu all_gather_slabs): a light ray crosses every slab, so every rank
+    sends its owned planes of the density channel to every other rank and receives theirs — one send/recv pair per
+    peer, all inside one group.  Global plane ranges."""
+    z0, z1 = slab_range(nz, rank, nranks)
+    return [Exchange(peer, z0, z1, *slab_range(nz, peer, nranks)) for peer in range(nranks) if peer != rank]

@@ -172,11 +172,13 @@ typedef struct fxb_light_params {
 } fxb_light_params;
 
 /* Replaces Fluid::rayMarchL: enqueues the pass on `cuda_stream` over the current colour field (so after an
- * fxb_simulate on the same stream it sees that step's result).  3D grids, nranks == 1 (a light ray crosses every
- * z-slab; the multi-GPU version is not built).  The light map is allocated on first use. */
+ * fxb_simulate on the same stream it sees that step's result).  3D grids.  With nranks > 1 every rank calls it: a light
+ * ray crosses every z-slab, so the ranks first exchange the density channel (2 bytes per voxel of the grid per rank,
+ * ncclSend/ncclRecv) and each then writes the light map of its own planes; needs nx * ny to be a multiple of 4.  Light map and density scratch are allocated on first use. */
 int fxb_light_map(fxb_sim* sim, const fxb_light_params* params, void* cuda_stream);
-/* Synchronous copy of the light map to the host: [z][y][x] uint32, DXGI_FORMAT_R11G11B10_FLOAT packing (R in bits
- * 0-10, G 11-21, B 22-31); bytes = nx*ny*nz*4.  Fails if fxb_light_map has not run. */
+/* Synchronous copy of the light map of this rank's planes to the host: [z][y][x] uint32,
+ * DXGI_FORMAT_R11G11B10_FLOAT packing (R in bits 0-10, G 11-21, B 22-31); bytes = nx*ny*count*4 (fxb_get_slab).
+ * Fails if fxb_light_map has not run. */
 int fxb_get_light_map(fxb_sim* sim, void* host, size_t bytes);
 
 /* ---- Cube-map ray march with the separate light pass ------------------------------------------

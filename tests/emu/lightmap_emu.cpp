@@ -22,4 +22,16 @@ void lightmap_emu_run(int nx, int ny, int nz, const uint16_t* colour, const void
             for (int x = 0; x < nx; ++x) out[((size_t)z * ny + y) * nx + x] = light_map_voxel(scratch, g, P, x, y, z);
 }
 
+// The z-slab form of the pass: `density` is the half array of the WHOLE grid (as gathered from all ranks), the voxels
+// of global planes [z0, z1) are written, out plane 0 = plane z0 — what light_map_kernel does on one rank.
+void lightmap_emu_run_slab(int nx, int ny, int nz, const uint16_t* density, const void* params, int z0, int z1,
+                           uint32_t* out) {
+    using namespace fxb;
+    const LightGeom g{nx, ny, nz};
+    const LightConsts& P = *static_cast<const LightConsts*>(params);
+    for (int z = z0; z < z1; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) out[((size_t)(z - z0) * ny + y) * nx + x] = light_map_voxel(density, g, P, x, y, z);
+}
+
 }  // extern "C"

@@ -77,6 +77,26 @@ def main():
             ok = ok and same
         else:
             dist.send(mine, dst=0)
+    if os.environ.get("FXB_TEST_LIGHTMAP") == "1":
+        # the light-map pass on z-slabs (density all-gathered over NCCL) against the single-GPU pass on rank 0
+        lp = fx.FxbLightParams.reference_defaults()
+        f.RayMarchL(lp)
+        mine = torch.from_numpy(f.get_light_map().view(np.uint8).reshape(-1).copy())
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([mine.numel()]))
+        if rank == 0:
+            bufs = [mine] + [torch.zeros(int(s.item()), dtype=torch.uint8) for s in sizes[1:]]
+            for r in range(1, world):
+                dist.recv(bufs[r], src=r)
+            ref.RayMarchL(lp)
+            want = ref.get_light_map()
+            got = torch.cat(bufs).numpy().view(np.uint32).reshape(want.shape)
+            same = np.array_equal(got, want)
+            print(f"light map: {'identical' if same else 'MISMATCH %d' % int((got != want).sum())}, "
+                  f"{len(np.unique(want))} distinct words")
+            ok = ok and same
+        else:
+            dist.send(mine, dst=0)
     if rank == 0:
         rs = ref.stats()
         print("s_exec", st.s_exec, rs.s_exec, "halo_overflow", st.halo_overflow)

@@ -152,3 +152,53 @@ def test_slab_decomposition_with_the_dynamic_schedule(world, grid):
         pr.join(timeout=300)
         assert pr.exitcode == 0
     assert out.get(timeout=10) is True
+
+
+def _lightmap_worker(rank, world, port, grid, out):
+    """Light-map pass on z-slabs (csrc/lightmap.cu with nranks > 1): every rank extracts the density channel of its own
+    planes, the ranks exchange them per slab.gather_plan, and each runs the kernel's per-voxel body (CPU emulation of
+    lightmap_body.cuh) on its planes over the gathered array."""
+    import ctypes as C
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from fluidx12_b200 import gather_plan, slab_range
+    from tests.test_lightmap import colour_field, light_constants, oracle_params
+    nx, ny, nz = grid
+    col = colour_field(grid, 21)
+    _, plain = light_constants(24, 1, (75.0, 75.0, -75.0), 6)
+    p = oracle_params(plain)
+    z0, z1 = slab_range(nz, rank, world)
+    dens = np.zeros((nz, ny, nx), np.uint16)              # the whole grid's density; only the own planes are known
+    dens[z0:z1] = col[z0:z1, ..., 3].view(np.uint16)
+    _exchange(dens, gather_plan(nz, rank, world), 0)
+    emu = C.CDLL(os.path.join(ROOT, "tests", "emu", "liblightmap_emu.so"))
+    emu.lightmap_emu_run_slab.restype = None
+    mine = np.empty((z1 - z0, ny, nx), np.uint32)
+    emu.lightmap_emu_run_slab(nx, ny, nz, dens.ctypes.data_as(C.c_void_p), C.byref(p), z0, z1, mine.ctypes.data_as(C.c_void_p))
+    want = O.light_map(col, p)
+    ok = bool(np.array_equal(dens.view(np.float16), col[..., 3])) and bool(np.array_equal(mine, want[z0:z1]))
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(bool(flag.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid", [(2, (16, 16, 12)), (3, (12, 12, 16))])
+def test_light_map_on_z_slabs_matches_single_domain(world, grid):
+    import subprocess
+
+    import oracle
+    oracle.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu"), "liblightmap_emu.so"])
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_lightmap_worker, args=(r, world, 29840 + world, grid, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=300)
+        assert pr.exitcode == 0
+    assert out.get(timeout=10) is True
