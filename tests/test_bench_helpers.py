@@ -49,6 +49,9 @@ def test_single_gpu_experiments_are_summarised_from_the_childs_records(monkeypat
          "tail": {"tail_launches_last_step": 13}, "passes": 17, "s_exec": 64,
          "mismatch_vs_default": {"0": 0, "1": 0, "2": 0}},
         {"stage": "timing", "grid": [256, 256, 256], "variant": "broken", "error": "RuntimeError('x')"},
+        {"stage": "light_map", "grid": [256, 256, 256], "probes": 1, "ms": 2.5, "voxels_with_smoke": 123, "t": 9.1},
+        {"stage": "light_map", "grid": [256, 256, 256], "pass_": "ray_march_v", "cube_size": 256, "ms": 0.4, "t": 9.3},
+        {"stage": "done"},
     ]
 
     def fake(cmd, env, timeout_s):
@@ -59,8 +62,10 @@ def test_single_gpu_experiments_are_summarised_from_the_childs_records(monkeypat
 
     monkeypatch.setattr(bench, "run_child", fake)
     res = bench.experiments_single_gpu(5)
-    assert res["exit"] == 0 and len(res["results"]) == 3
-    d, t, b = res["results"]
+    assert res["exit"] == 0 and len(res["results"]) == 5
+    d, t, b, lm, rm = res["results"]
+    assert lm == {"grid": "256x256x256", "probes": 1, "ms": 2.5, "voxels_with_smoke": 123, "variant": "light_map_pass"}
+    assert rm["pass_"] == "ray_march_v" and rm["variant"] == "light_map_pass" and "t" not in rm
     assert d == {"grid": "256x256x256", "variant": "default", "ms_per_step": 1.49, "jacobi_ms": 1.18, "advect_ms": 0.29}
     assert t["variant"] == "tail" and t["mismatched_elements_vs_default"] == 0 and t["tail_launches"] == 13
     assert b["variant"] == "broken" and "error" in b

@@ -183,11 +183,11 @@ def bench_mode(fx):
                                           ("tail_pass0", {"FXB_PASS0": 2}),
                                           ("tail_thr256", {"FXB_TAIL_THRESHOLD": 256, "FXB_TAIL_MAINS": 12}),
                                           ("tail_mains1", {"FXB_TAIL_MAINS": 1})], all_fields=True)
+    light_map_timing(fx, (256, 256, 256))
     timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
                                           ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0})],
            all_fields=True)
-    light_map_timing(fx, (256, 256, 256))
     light_map_timing(fx, (512, 512, 512))
     emit(stage="done")
 
