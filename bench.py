@@ -339,8 +339,8 @@ def experiments_multi_gpu(args, world, budget_s):
     port = int(os.environ.get("MASTER_PORT", "29500"))
     t_end = time.time() + budget_s
     rows, ref = [], None
-    for i, (label, extra) in enumerate((("default", {}), ("p2p_halos", {"FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 5}),
-                                        ("tail_p2p", {"FXB_TAIL": 1, "FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 5}),
+    for i, (label, extra) in enumerate((("default", {}), ("p2p_halos", {"FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 15}),
+                                        ("tail_p2p", {"FXB_TAIL": 1, "FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 15}),
                                         ("tail", {"FXB_TAIL": 1}))):
         left = t_end - time.time()
         if left < 20:
