@@ -563,8 +563,11 @@ def run_ours(args):
     f.close()
     if world > 1:
         dist.destroy_process_group()
+    # Single GPU: on by default (every variant's kernels are plain compute kernels without device-side waits; a fault
+    # in the child ends the child).  Several GPUs: opt-in (--experiments-multi) — the peer-memory halo exchange has
+    # never run on GPUs, and a misbehaving multi-rank child must not be able to disturb the scaling runs that follow.
     want_exp = (not args.no_experiments and os.environ.get("FXB_BENCH_EXPERIMENTS", "1") != "0" and rank == 0
-                and time.time() - t_bench0 < 300.0)
+                and time.time() - t_bench0 < 300.0 and (world == 1 or args.experiments_multi))
     if want_exp:
         # every rank has released its GPU memory and its communicators; ranks > 0 simply exit
         try:
@@ -643,6 +646,8 @@ def main():
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-experiments", action="store_true",
                     help="skip the child-process runs of the opt-in variants after the measurement (use under ncu)")
+    ap.add_argument("--experiments-multi", action="store_true",
+                    help="N > 1: also relaunch this bench with the multi-GPU switches (peer-memory halos, dynamic schedule)")
     ap.add_argument("--experiments-budget", type=float, default=75.0, help="seconds (twice that for N > 1)")
     ap.add_argument("--checksum", action="store_true", help="add a checksum of the final state to the line")
     args = ap.parse_args()

@@ -127,3 +127,8 @@ def test_state_checksum_sees_a_moved_or_changed_word():
     assert base != bench.state_checksum(None, None, F(1, "bit"), FX, 1)
     assert base != bench.state_checksum(None, None, F(1, "swap"), FX, 1)
     assert 0 <= base < 1 << 62
+
+
+def test_multi_gpu_experiments_are_opt_in():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "--experiments-multi" in src and "world == 1 or args.experiments_multi" in src
