@@ -17,26 +17,13 @@
 #include <string>
 #include <vector>
 
-#include "../../include/fluidx_b200.h"
-#include "common.cuh"
-#include "halo.h"
-#include "kernels.h"
+#include "fxb_internal.h"
 
 namespace {
 
 thread_local std::string g_last_error;
 
-int fail(int code, const std::string& msg) {
-    g_last_error = msg;
-    return code;
-}
-
-#define FXB_CUDA(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(FXB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
-    } while (0)
+int fail(int code, const std::string& msg) { return fxb::api_fail(code, msg); }
 
 __global__ void set_frame_kernel(fxb::FrameParams* frame, float dt, int parity) {
     frame->dt = dt;
@@ -45,63 +32,11 @@ __global__ void set_frame_kernel(fxb::FrameParams* frame, float dt, int parity) 
 
 }  // namespace
 
-struct fxb_sim {
-    fxb_config cfg{};
-    fxb::Domain dom{};
-    int fuse_t = 1;
-    int parity = 0;  // m_frameParity (Fluid.h:124)
-    float dt = 0.0f;  // m_timeStep (Fluid.h:126)
-    uint64_t steps = 0;
-    int kernels_per_step = 0;
+int fxb::api_fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
 
-    void* vel[2] = {nullptr, nullptr};  // m_velocities (Fluid.h:94), RGBA16F
-    void* col[2] = {nullptr, nullptr};  // m_colors (Fluid.h:95), RGBA16F
-    float* p[2] = {nullptr, nullptr};   // m_incompress (Fluid.h:93), R32F, ping-pong
-    float* rhs = nullptr;               // -0.5 * (2*divergence)
-    unsigned char* active = nullptr;    // per-cell freeze flags of the simple path
-    bool fused = false;                 // tuned Jacobi path in use
-    fxb::FusedJacobi jac;
-    float* emitter_basis = nullptr;
-    float* axis_tables = nullptr;       // pos / bp / wall per axis, one allocation
-    fxb::AxisTables tab{};
-    bool quad = false;                  // 4-cells-per-thread divergence / gradient kernels in use
-    fxb::Emitter emitter{};
-    fxb::FrameParams* d_frame = nullptr;
-    fxb::StepState* d_state = nullptr;
-
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t side_stream = nullptr;  // colour advection branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool overlap_colour = false;  // measured slower on B200 (profiles/README.md); FXB_OVERLAP_COLOUR=1 enables it
-    bool fork_colour_now = false;  // set by enqueue_step: the Jacobi phase should fork the colour branch
-    cudaStream_t last_stream = nullptr;
-    // One captured graph per (frame parity, pressure-buffer parity): both select pointers that the halo exchange
-    // of the multi-GPU step needs on the host side.  Single GPU uses slot [0][0] only (its kernels select on device).
-    cudaGraph_t graph[2][2] = {};
-    cudaGraphExec_t graph_exec[2][2] = {};
-    fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
-    int halo = 0;             // halo planes allocated on interior faces
-    int h_adv = 0;            // advection halo (back-trace reach in planes)
-    int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (FXB_JACOBI_GROUP; > 1 is experimental)
-    int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
-    // Dynamic schedule (FXB_TAIL=1, single GPU; experimental until measured on B200 — DESIGN.md §5): bulk passes
-    // 0..tail_mains-1 interleaved with tail launches (jacobi_tail.cu), then tail launches only.
-    bool tail = false;
-    int tail_mains = 8;
-    bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
-    bool pass0_tail = false;  // FXB_PASS0=2 (with FXB_TAIL=1, T = 2): pass 0 by the block-resident kernel (experimental)
-    unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
-    unsigned* cube_map = nullptr;          // one mip of m_cubeMap (Fluid.cpp:229-232): [6][S][S] RGBA8 words
-    uint32_t cube_size = 0;
-    unsigned short* light_density = nullptr;  // colour.w of every voxel, the channel the light-map pass samples
-    bool multi() const { return cfg.nranks > 1; }
-    cudaEvent_t ev[8] = {};
-
-    size_t plane_voxels() const { return (size_t)dom.nx * dom.ny; }
-    size_t alloc_voxels() const { return plane_voxels() * dom.nz_alloc; }
-    size_t own_voxels() const { return plane_voxels() * (dom.z_own1 - dom.z_own0); }
-    size_t own_offset() const { return plane_voxels() * (dom.z_own0 - dom.z_first); }
-};
 
 namespace {
 
@@ -389,7 +324,9 @@ int capture_graph(fxb_sim* s, int a, int b) {
     return FXB_OK;
 }
 
-void* field_device_ptr(fxb_sim* s, int field, size_t* elem_bytes, int* err) {
+}  // namespace
+
+void* fxb::field_device_ptr(fxb_sim* s, int field, size_t* elem_bytes, int* err) {
     *err = FXB_OK;
     switch (field) {
         case FXB_FIELD_VELOCITY: *elem_bytes = 8; return s->vel[0];
@@ -410,7 +347,7 @@ void* field_device_ptr(fxb_sim* s, int field, size_t* elem_bytes, int* err) {
     return nullptr;
 }
 
-}  // namespace
+using fxb::field_device_ptr;
 
 extern "C" {
 
@@ -812,172 +749,6 @@ int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t
     const fxb::P2PPlanes q = fxb::p2p_planes(d, depth, rank > 0 ? z_first(rank - 1) : 0, rank < nranks - 1 ? z_first(rank + 1) : 0);
     out4[0] = q.send_lo; out4[1] = q.dst_lo; out4[2] = q.send_hi; out4[3] = q.dst_hi;
     return FXB_OK;
-}
-
-// ---- light-map pass (Fluid::rayMarchL, Fluid.cpp:857-878; kernels in lightmap.cu) ---------------------------------
-static_assert(sizeof(fxb_light_params) == 4 * (3 + 4 + 4 + 12 + 12 + 2 + 27), "fxb_light_params is passed to the kernel as is");
-
-int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream) {
-    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_light_map: null argument");
-    if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_light_map: 3D grids only (the reference renders none other, Fluid.cpp:296)");
-    if (s->multi() && s->plane_voxels() % 4 != 0)  // 16-byte loads / 8-byte stores of the extraction start at a plane
-        return fail(FXB_ERR_INVALID, "fxb_light_map: with nranks > 1 nx * ny must be a multiple of 4");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    if (!s->light_map) {
-        // the light map covers the rank's own planes; the density scratch covers the WHOLE grid, because a light ray
-        // crosses every z-slab (2 bytes per voxel; the other ranks' planes arrive over NCCL inside the pass)
-        FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
-        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
-    }
-    // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
-    const char* colour_own = static_cast<const char*>(s->col[s->parity]) + s->own_offset() * 8;
-    if (fxb::launch_light_map(s->dom, colour_own, s->light_density, s->light_map, params, &s->comm,
-                              (cudaStream_t)cuda_stream) != cudaSuccess)
-        return fail(s->multi() ? FXB_ERR_NCCL : FXB_ERR_CUDA, "fxb_light_map: launch failed: " +
-                    (s->multi() ? fxb::halo_last_error() : std::string(cudaGetErrorString(cudaGetLastError()))));
-    s->last_stream = (cudaStream_t)cuda_stream;
-    return FXB_OK;
-}
-
-int fxb_get_light_map(fxb_sim* s, void* host, size_t bytes) {
-    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_light_map: null argument");
-    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_get_light_map: fxb_light_map has not run");
-    if (bytes != s->own_voxels() * sizeof(unsigned)) return fail(FXB_ERR_SIZE, "fxb_get_light_map: size mismatch");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    FXB_CUDA(cudaDeviceSynchronize());
-    FXB_CUDA(cudaMemcpy(host, s->light_map, bytes, cudaMemcpyDeviceToHost));
-    return FXB_OK;
-}
-
-// ---- cube-map ray march (Fluid::rayMarchV, Fluid.cpp:880-908; kernel in raymarch.cu) --------------------------------
-static_assert(sizeof(fxb_view_params) == 4 * (3 + 12 + 3), "fxb_view_params is passed to the kernel as is");
-
-int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask) {
-    if (!world_i || !eye_pt || !mask) return fail(FXB_ERR_INVALID, "fxb_cube_visibility_mask: null argument");
-    uint32_t m = 0;
-    for (int face = 0; face < 6; ++face) {
-        const float* w = world_i + 4 * (face >> 1);
-        const float v = ((eye_pt[0] * w[0] + eye_pt[1] * w[1]) + eye_pt[2] * w[2]) + w[3];
-        m |= (uint32_t)((face & 1) ? v > -1.0f : v < 1.0f) << face;  // IsCubeFaceVisible, Fluid.cpp:41-46
-    }
-    *mask = m;
-    return FXB_OK;
-}
-
-int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
-    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");
-    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids on one GPU only");
-    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: fxb_light_map has not run (the light map is an input)");
-    if (params->cube_size < 1 || params->cube_size > 4096) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: cube_size out of range");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    if (s->cube_size != params->cube_size) {
-        FXB_CUDA(cudaDeviceSynchronize());
-        cudaFree(s->cube_map);
-        s->cube_map = nullptr;
-        s->cube_size = 0;
-        const size_t bytes = (size_t)6 * params->cube_size * params->cube_size * sizeof(unsigned);
-        FXB_CUDA(cudaMalloc((void**)&s->cube_map, bytes));
-        FXB_CUDA(cudaMemset(s->cube_map, 0, bytes));
-        s->cube_size = params->cube_size;
-    }
-    FXB_CUDA(fxb::launch_ray_march_v(s->dom, s->col[s->parity], s->light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
-    s->last_stream = (cudaStream_t)cuda_stream;
-    return FXB_OK;
-}
-
-int fxb_get_cube_map(fxb_sim* s, void* host, size_t bytes) {
-    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: null argument");
-    if (!s->cube_map) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: fxb_ray_march_v has not run");
-    if (bytes != (size_t)6 * s->cube_size * s->cube_size * 4) return fail(FXB_ERR_SIZE, "fxb_get_cube_map: size mismatch");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    FXB_CUDA(cudaDeviceSynchronize());
-    FXB_CUDA(cudaMemcpy(host, s->cube_map, bytes, cudaMemcpyDeviceToHost));
-    return FXB_OK;
-}
-
-// ---- volume files (include/fluidx_b200.h: the renderer hand-off format) --------------------------
-namespace {
-static_assert(sizeof(fxb_volume_header) == 64, "fxb_volume_header is a 64-byte wire structure");
-
-int check_volume_header(const fxb_volume_header& h, const char* who) {
-    const std::string w(who);
-    if (memcmp(h.magic, FXB_VOLUME_MAGIC, 4) != 0) return fail(FXB_ERR_IO, w + ": not a volume file (magic)");
-    if (h.version != FXB_VOLUME_VERSION) return fail(FXB_ERR_IO, w + ": unsupported volume file version");
-    if (h.format != 1 && h.format != 2) return fail(FXB_ERR_IO, w + ": unknown element format");
-    if (h.nx == 0 || h.ny == 0 || h.nz == 0 || h.nz_local == 0 || (uint64_t)h.z0 + h.nz_local > h.nz)
-        return fail(FXB_ERR_IO, w + ": bad grid / slab extent");
-    if (h.field > FXB_FIELD_COLOR_PREV || (h.format == 2) != (h.field == FXB_FIELD_PRESSURE))
-        return fail(FXB_ERR_IO, w + ": field and element format do not match");
-    if (h.payload_bytes != (uint64_t)h.nx * h.ny * h.nz_local * (h.format == 1 ? 8u : 4u))
-        return fail(FXB_ERR_IO, w + ": payload size does not match the extent");
-    return FXB_OK;
-}
-}  // namespace
-
-int fxb_volume_write(const char* path, const fxb_volume_header* hdr, const void* data) {
-    if (!path || !*path || !hdr || !data) return fail(FXB_ERR_INVALID, "fxb_volume_write: null argument");
-    fxb_volume_header h = *hdr;
-    memcpy(h.magic, FXB_VOLUME_MAGIC, 4);
-    h.version = FXB_VOLUME_VERSION;
-    if (const int rc = check_volume_header(h, "fxb_volume_write")) return rc == FXB_ERR_IO ? FXB_ERR_INVALID : rc;
-    const std::string tmp = std::string(path) + ".tmp";
-    FILE* fp = fopen(tmp.c_str(), "wb");
-    if (!fp) return fail(FXB_ERR_IO, "fxb_volume_write: cannot create " + tmp);
-    bool ok = fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(data, 1, h.payload_bytes, fp) == h.payload_bytes;
-    ok = (fclose(fp) == 0) && ok;
-    if (!ok || rename(tmp.c_str(), path) != 0) {
-        remove(tmp.c_str());
-        return fail(FXB_ERR_IO, std::string("fxb_volume_write: writing ") + path + " failed");
-    }
-    return FXB_OK;
-}
-
-int fxb_volume_read_header(const char* path, fxb_volume_header* out) {
-    if (!path || !out) return fail(FXB_ERR_INVALID, "fxb_volume_read_header: null argument");
-    FILE* fp = fopen(path, "rb");
-    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read_header: cannot open ") + path);
-    const bool ok = fread(out, sizeof *out, 1, fp) == 1;
-    fclose(fp);
-    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read_header: file shorter than a header");
-    return check_volume_header(*out, "fxb_volume_read_header");
-}
-
-int fxb_volume_read(const char* path, fxb_volume_header* out, void* data, size_t capacity) {
-    if (!data) return fail(FXB_ERR_INVALID, "fxb_volume_read: null argument");
-    if (const int rc = fxb_volume_read_header(path, out)) return rc;
-    if (capacity < out->payload_bytes) return fail(FXB_ERR_SIZE, "fxb_volume_read: buffer smaller than the payload");
-    FILE* fp = fopen(path, "rb");
-    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read: cannot open ") + path);
-    bool ok = fseek(fp, (long)sizeof *out, SEEK_SET) == 0 && fread(data, 1, out->payload_bytes, fp) == out->payload_bytes;
-    ok = ok && fgetc(fp) == EOF;  // nothing may follow the payload
-    fclose(fp);
-    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read: payload truncated or followed by extra bytes");
-    return FXB_OK;
-}
-
-int fxb_export_field(fxb_sim* s, int field, const char* path) {
-    if (!s || !path) return fail(FXB_ERR_INVALID, "fxb_export_field: null argument");
-    size_t eb; int err;
-    if (!field_device_ptr(s, field, &eb, &err)) return fail(err, "fxb_export_field: bad field");
-    fxb_volume_header h = {};
-    h.nx = s->cfg.nx; h.ny = s->cfg.ny; h.nz = s->cfg.nz;
-    h.z0 = (uint32_t)s->dom.z_own0;
-    h.nz_local = (uint32_t)(s->dom.z_own1 - s->dom.z_own0);
-    h.field = (uint32_t)field;
-    h.format = eb == 8 ? 1u : 2u;
-    h.flags = (field == FXB_FIELD_COLOR || field == FXB_FIELD_COLOR_PREV) ? FXB_VOLUME_FLAG_PREMULTIPLIED : 0u;
-    h.frame = s->steps;
-    h.dt = s->dt;
-    h.frame_parity = (uint32_t)s->parity;
-    h.payload_bytes = (uint64_t)s->own_voxels() * eb;
-    std::vector<char> host;
-    try {
-        host.resize(h.payload_bytes);
-    } catch (const std::bad_alloc&) {
-        return fail(FXB_ERR_IO, "fxb_export_field: no host memory for the staging buffer");
-    }
-    if (const int rc = fxb_get_field(s, field, host.data(), host.size())) return rc;
-    return fxb_volume_write(path, &h, host.data());
 }
 
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {

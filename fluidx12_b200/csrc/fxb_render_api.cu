@@ -1,0 +1,185 @@
+// fxb_render_api.cu — the C ABI entry points of the rows past the simulation step: the light-map
+// pass (Fluid::rayMarchL), the cube-map ray march (Fluid::rayMarchV) and volume files (the renderer hand-off format).
+// Kernels: lightmap.cu, raymarch.cu.  The step itself (Init / UpdateFrame / Simulate, field I/O, statistics) is in
+// fxb_api.cu.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "fxb_internal.h"
+
+namespace {
+int fail(int code, const std::string& msg) { return fxb::api_fail(code, msg); }
+using fxb::field_device_ptr;
+}  // namespace
+
+extern "C" {
+
+// ---- light-map pass (Fluid::rayMarchL, Fluid.cpp:857-878; kernels in lightmap.cu) ---------------------------------
+static_assert(sizeof(fxb_light_params) == 4 * (3 + 4 + 4 + 12 + 12 + 2 + 27), "fxb_light_params is passed to the kernel as is");
+
+int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream) {
+    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_light_map: null argument");
+    if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_light_map: 3D grids only (the reference renders none other, Fluid.cpp:296)");
+    if (s->multi() && s->plane_voxels() % 4 != 0)  // 16-byte loads / 8-byte stores of the extraction start at a plane
+        return fail(FXB_ERR_INVALID, "fxb_light_map: with nranks > 1 nx * ny must be a multiple of 4");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (!s->light_map) {
+        // the light map covers the rank's own planes; the density scratch covers the WHOLE grid, because a light ray
+        // crosses every z-slab (2 bytes per voxel; the other ranks' planes arrive over NCCL inside the pass)
+        FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
+        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
+    }
+    // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
+    const char* colour_own = static_cast<const char*>(s->col[s->parity]) + s->own_offset() * 8;
+    if (fxb::launch_light_map(s->dom, colour_own, s->light_density, s->light_map, params, &s->comm,
+                              (cudaStream_t)cuda_stream) != cudaSuccess)
+        return fail(s->multi() ? FXB_ERR_NCCL : FXB_ERR_CUDA, "fxb_light_map: launch failed: " +
+                    (s->multi() ? fxb::halo_last_error() : std::string(cudaGetErrorString(cudaGetLastError()))));
+    s->last_stream = (cudaStream_t)cuda_stream;
+    return FXB_OK;
+}
+
+int fxb_get_light_map(fxb_sim* s, void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_light_map: null argument");
+    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_get_light_map: fxb_light_map has not run");
+    if (bytes != s->own_voxels() * sizeof(unsigned)) return fail(FXB_ERR_SIZE, "fxb_get_light_map: size mismatch");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    FXB_CUDA(cudaMemcpy(host, s->light_map, bytes, cudaMemcpyDeviceToHost));
+    return FXB_OK;
+}
+
+// ---- cube-map ray march (Fluid::rayMarchV, Fluid.cpp:880-908; kernel in raymarch.cu) --------------------------------
+static_assert(sizeof(fxb_view_params) == 4 * (3 + 12 + 3), "fxb_view_params is passed to the kernel as is");
+
+int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask) {
+    if (!world_i || !eye_pt || !mask) return fail(FXB_ERR_INVALID, "fxb_cube_visibility_mask: null argument");
+    uint32_t m = 0;
+    for (int face = 0; face < 6; ++face) {
+        const float* w = world_i + 4 * (face >> 1);
+        const float v = ((eye_pt[0] * w[0] + eye_pt[1] * w[1]) + eye_pt[2] * w[2]) + w[3];
+        m |= (uint32_t)((face & 1) ? v > -1.0f : v < 1.0f) << face;  // IsCubeFaceVisible, Fluid.cpp:41-46
+    }
+    *mask = m;
+    return FXB_OK;
+}
+
+int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
+    if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");
+    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids on one GPU only");
+    if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: fxb_light_map has not run (the light map is an input)");
+    if (params->cube_size < 1 || params->cube_size > 4096) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: cube_size out of range");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (s->cube_size != params->cube_size) {
+        FXB_CUDA(cudaDeviceSynchronize());
+        cudaFree(s->cube_map);
+        s->cube_map = nullptr;
+        s->cube_size = 0;
+        const size_t bytes = (size_t)6 * params->cube_size * params->cube_size * sizeof(unsigned);
+        FXB_CUDA(cudaMalloc((void**)&s->cube_map, bytes));
+        FXB_CUDA(cudaMemset(s->cube_map, 0, bytes));
+        s->cube_size = params->cube_size;
+    }
+    FXB_CUDA(fxb::launch_ray_march_v(s->dom, s->col[s->parity], s->light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
+    s->last_stream = (cudaStream_t)cuda_stream;
+    return FXB_OK;
+}
+
+int fxb_get_cube_map(fxb_sim* s, void* host, size_t bytes) {
+    if (!s || !host) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: null argument");
+    if (!s->cube_map) return fail(FXB_ERR_INVALID, "fxb_get_cube_map: fxb_ray_march_v has not run");
+    if (bytes != (size_t)6 * s->cube_size * s->cube_size * 4) return fail(FXB_ERR_SIZE, "fxb_get_cube_map: size mismatch");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    FXB_CUDA(cudaMemcpy(host, s->cube_map, bytes, cudaMemcpyDeviceToHost));
+    return FXB_OK;
+}
+
+// ---- volume files (include/fluidx_b200.h: the renderer hand-off format) --------------------------
+namespace {
+static_assert(sizeof(fxb_volume_header) == 64, "fxb_volume_header is a 64-byte wire structure");
+
+int check_volume_header(const fxb_volume_header& h, const char* who) {
+    const std::string w(who);
+    if (memcmp(h.magic, FXB_VOLUME_MAGIC, 4) != 0) return fail(FXB_ERR_IO, w + ": not a volume file (magic)");
+    if (h.version != FXB_VOLUME_VERSION) return fail(FXB_ERR_IO, w + ": unsupported volume file version");
+    if (h.format != 1 && h.format != 2) return fail(FXB_ERR_IO, w + ": unknown element format");
+    if (h.nx == 0 || h.ny == 0 || h.nz == 0 || h.nz_local == 0 || (uint64_t)h.z0 + h.nz_local > h.nz)
+        return fail(FXB_ERR_IO, w + ": bad grid / slab extent");
+    if (h.field > FXB_FIELD_COLOR_PREV || (h.format == 2) != (h.field == FXB_FIELD_PRESSURE))
+        return fail(FXB_ERR_IO, w + ": field and element format do not match");
+    if (h.payload_bytes != (uint64_t)h.nx * h.ny * h.nz_local * (h.format == 1 ? 8u : 4u))
+        return fail(FXB_ERR_IO, w + ": payload size does not match the extent");
+    return FXB_OK;
+}
+}  // namespace
+
+int fxb_volume_write(const char* path, const fxb_volume_header* hdr, const void* data) {
+    if (!path || !*path || !hdr || !data) return fail(FXB_ERR_INVALID, "fxb_volume_write: null argument");
+    fxb_volume_header h = *hdr;
+    memcpy(h.magic, FXB_VOLUME_MAGIC, 4);
+    h.version = FXB_VOLUME_VERSION;
+    if (const int rc = check_volume_header(h, "fxb_volume_write")) return rc == FXB_ERR_IO ? FXB_ERR_INVALID : rc;
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* fp = fopen(tmp.c_str(), "wb");
+    if (!fp) return fail(FXB_ERR_IO, "fxb_volume_write: cannot create " + tmp);
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1 && fwrite(data, 1, h.payload_bytes, fp) == h.payload_bytes;
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        return fail(FXB_ERR_IO, std::string("fxb_volume_write: writing ") + path + " failed");
+    }
+    return FXB_OK;
+}
+
+int fxb_volume_read_header(const char* path, fxb_volume_header* out) {
+    if (!path || !out) return fail(FXB_ERR_INVALID, "fxb_volume_read_header: null argument");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read_header: cannot open ") + path);
+    const bool ok = fread(out, sizeof *out, 1, fp) == 1;
+    fclose(fp);
+    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read_header: file shorter than a header");
+    return check_volume_header(*out, "fxb_volume_read_header");
+}
+
+int fxb_volume_read(const char* path, fxb_volume_header* out, void* data, size_t capacity) {
+    if (!data) return fail(FXB_ERR_INVALID, "fxb_volume_read: null argument");
+    if (const int rc = fxb_volume_read_header(path, out)) return rc;
+    if (capacity < out->payload_bytes) return fail(FXB_ERR_SIZE, "fxb_volume_read: buffer smaller than the payload");
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return fail(FXB_ERR_IO, std::string("fxb_volume_read: cannot open ") + path);
+    bool ok = fseek(fp, (long)sizeof *out, SEEK_SET) == 0 && fread(data, 1, out->payload_bytes, fp) == out->payload_bytes;
+    ok = ok && fgetc(fp) == EOF;  // nothing may follow the payload
+    fclose(fp);
+    if (!ok) return fail(FXB_ERR_IO, "fxb_volume_read: payload truncated or followed by extra bytes");
+    return FXB_OK;
+}
+
+int fxb_export_field(fxb_sim* s, int field, const char* path) {
+    if (!s || !path) return fail(FXB_ERR_INVALID, "fxb_export_field: null argument");
+    size_t eb; int err;
+    if (!field_device_ptr(s, field, &eb, &err)) return fail(err, "fxb_export_field: bad field");
+    fxb_volume_header h = {};
+    h.nx = s->cfg.nx; h.ny = s->cfg.ny; h.nz = s->cfg.nz;
+    h.z0 = (uint32_t)s->dom.z_own0;
+    h.nz_local = (uint32_t)(s->dom.z_own1 - s->dom.z_own0);
+    h.field = (uint32_t)field;
+    h.format = eb == 8 ? 1u : 2u;
+    h.flags = (field == FXB_FIELD_COLOR || field == FXB_FIELD_COLOR_PREV) ? FXB_VOLUME_FLAG_PREMULTIPLIED : 0u;
+    h.frame = s->steps;
+    h.dt = s->dt;
+    h.frame_parity = (uint32_t)s->parity;
+    h.payload_bytes = (uint64_t)s->own_voxels() * eb;
+    std::vector<char> host;
+    try {
+        host.resize(h.payload_bytes);
+    } catch (const std::bad_alloc&) {
+        return fail(FXB_ERR_IO, "fxb_export_field: no host memory for the staging buffer");
+    }
+    if (const int rc = fxb_get_field(s, field, host.data(), host.size())) return rc;
+    return fxb_volume_write(path, &h, host.data());
+}
+
+}  // extern "C"
