@@ -25,10 +25,10 @@ int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream)
     if (s->multi() && s->plane_voxels() % 4 != 0)  // 16-byte loads / 8-byte stores of the extraction start at a plane
         return fail(FXB_ERR_INVALID, "fxb_light_map: with nranks > 1 nx * ny must be a multiple of 4");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
-    if (!s->light_map) {
+    if (!s->light_map || !s->light_density) {
         // the light map covers the rank's own planes; the density scratch covers the WHOLE grid, because a light ray
         // crosses every z-slab (2 bytes per voxel; the other ranks' planes arrive over NCCL inside the pass)
-        FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
+        if (!s->light_map) FXB_CUDA(cudaMalloc((void**)&s->light_map, s->own_voxels() * sizeof(unsigned)));
         FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
     }
     // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
