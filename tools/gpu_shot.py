@@ -98,7 +98,9 @@ def timing(fx, n, spin, steps, variants, all_fields=False):
     res = {"default": round(time_steps(base, dt, steps), 4)}
     base.UpdateFrame(dt)
     res["default_phases"] = {k: round(v, 4) for k, v in base.profile_step().items()}
-    cmp_flds = flds if all_fields else (fx.FIELD_PRESSURE,)
+    # "pc": pressure and colour (the colour field is advected by the velocity, so the pair pins all three at 2/3 of
+    # the host traffic — used at 512^3 inside bench.py's time budget)
+    cmp_flds = (fx.FIELD_PRESSURE, fx.FIELD_COLOR) if all_fields == "pc" else flds if all_fields else (fx.FIELD_PRESSURE,)
     ref = {fld: base.get_field(fld) for fld in cmp_flds}
     emit(stage="timing", grid=n, **res)
     base.close()
@@ -186,8 +188,9 @@ def bench_mode(fx):
     light_map_timing(fx, (256, 256, 256))
     timing(fx, (512, 512, 512), 100, 20, [("tail", {}), ("advect2_only", {"FXB_TAIL": 0, "FXB_ADVECT": 2}),
                                           ("tail_advect2", {"FXB_ADVECT": 2}),
-                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0})],
-           all_fields=True)
+                                          ("tail_dense2_only", {"FXB_TAIL_DENSE": 2, "FXB_TAIL_SPARSE_CAP": 0}),
+                                          ("tail_pass0", {"FXB_PASS0": 2})],
+           all_fields="pc")
     light_map_timing(fx, (512, 512, 512))
     emit(stage="done")
 
