@@ -247,3 +247,24 @@ def test_dynamic_schedule_always_completes(t, iters):
             done, _ = _simulate_plan(plan, iters, t, tt, 3, frozen)
             assert frozen <= done <= min(iters, frozen + tt - 1)
     assert L.fxb_plan_pressure_solve(64, 9, 5, buf, 512) < 0  # bad fuse_t
+
+
+def test_config_validation_needs_no_device(fx):
+    """Empty grids, the 2^31-voxel limit of the kernels' 32-bit offsets and out-of-range options are rejected before
+    any CUDA call, with a message naming the option (the reference only asserts nx == ny, Fluid.cpp:201)."""
+    L = fx.lib()
+    cfg = fx.FxbConfig()
+    L.fxb_config_default(C.byref(cfg))
+    h = C.c_void_p()
+    for grid, text in (((0, 0, 0), b"empty grid"), ((64, 64, 0), b"empty grid"), ((2048, 2048, 512), b"2^31 voxels")):
+        cfg.nx, cfg.ny, cfg.nz = grid
+        assert L.fxb_create(C.byref(cfg), C.byref(h)) == -1 and text in L.fxb_last_error(), grid
+        assert not h.value
+    cfg.nx = cfg.ny = cfg.nz = 64
+    for key, value, text in (("jacobi_iters", -1, b"jacobi_iters"), ("jacobi_iters", 129, b"jacobi_iters"),
+                             ("address_mode", 7, b"address_mode"), ("nranks", 0, b"rank/nranks"), ("rank", 3, b"rank/nranks")):
+        old = getattr(cfg, key)
+        setattr(cfg, key, value)
+        assert L.fxb_create(C.byref(cfg), C.byref(h)) == -1 and text in L.fxb_last_error(), key
+        setattr(cfg, key, old)
+    assert L.fxb_create(None, C.byref(h)) == -1 and L.fxb_create(C.byref(cfg), None) == -1
