@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.fxo_light_map.restype = None
         L.fxo_ray_march_v.argtypes = [i32, i32, i32, u16p, vp, vp, vp]
         L.fxo_ray_march_v.restype = None
+        L.fxo_ray_march.argtypes = [i32, i32, i32, u16p, vp, vp, vp]
+        L.fxo_ray_march.restype = None
         L.fxo_unpack_r11g11b10.argtypes = [C.c_uint32, f32p]
         L.fxo_unpack_r11g11b10.restype = None
         L.fxo_pack_r11g11b10.argtypes = [f32, f32, f32]
@@ -258,6 +260,17 @@ def ray_march_v(colour, light_map_words, params: ViewParams, cube=None) -> np.nd
     s = int(params.cube_size)
     out = np.zeros((6, s, s, 4), np.uint8) if cube is None else np.ascontiguousarray(cube, np.uint8).copy()
     lib().fxo_ray_march_v(nx, ny, nz, _ptr(colour), _ptr(lm), C.byref(params), _ptr(out))
+    return out
+
+
+def ray_march(colour, view: ViewParams, light: LightParams, cube=None) -> np.ndarray:
+    """The non-separated march (CSRayMarch): the light is computed at every view sample; light.num_samples = light-ray
+    samples.  [6][S][S][4] UNORM8."""
+    nz, ny, nx, _ = colour.shape
+    colour = np.ascontiguousarray(colour, np.float16)
+    s = int(view.cube_size)
+    out = np.zeros((6, s, s, 4), np.uint8) if cube is None else np.ascontiguousarray(cube, np.uint8).copy()
+    lib().fxo_ray_march(nx, ny, nz, _ptr(colour), C.byref(view), C.byref(light), _ptr(out))
     return out
 
 

@@ -556,7 +556,64 @@ inline float trilerp(const Taps& t, const float a[8]) {  // a[k]: tap k = x + 2 
     return std::fmaf(t.fz, y1v - y0v, y0v);
 }
 
-void ray_march_v(const Grid& g, const uint16_t* col, const uint32_t* lmap, const ViewParams& P, uint8_t* cube) {
+// GetLight of the non-separated march (RayMarch.hlsli:280-313 with _HAS_LIGHT_PROBE_; Bin/CSRayMarch.cso instructions
+// 164-298): the light reaching `pos`, computed on the spot — the light ray (and, with probes, the occlusion ray along
+// the density gradient and the SH irradiance) cast with g_lightStep / g_numLightSamples — instead of read from the
+// light map.  `ldir`: the normalised light direction in volume space (per ray, instructions 136-141).
+inline void full_light(const uint16_t* col, const Grid& g, const LightParams& P, const float pos[3], const float uvw[3],
+                       const float ldir[3], float light[3]) {
+    const float lstep = 3.464101552963257f / (float)P.num_samples;
+    const float shadow = cast_light_ray(col, g, pos, ldir, lstep, P.num_samples);
+    float ao = 1.0f, irr[3] = {0.0f, 0.0f, 0.0f};
+    if (P.has_light_probes) {
+        const float q0 = sample_density(col, g, uvw[0], uvw[1], uvw[2], -1, 0, 0);
+        const float q1 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 1, 0, 0);
+        const float q2 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, -1, 0);
+        const float q3 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 1, 0);
+        const float q4 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 0, -1);
+        const float q5 = sample_density(col, g, uvw[0], uvw[1], uvw[2], 0, 0, 1);
+        const float grad[3] = {-q0 + q1, -q2 + q3, -q4 + q5};
+        const bool any = 0.0f < std::fabs(grad[0]) || 0.0f < std::fabs(grad[1]) || 0.0f < std::fabs(grad[2]);
+        float rd[3], wd[3], n[3];
+        for (int k = 0; k < 3; ++k) rd[k] = any ? -grad[k] : pos[k];
+        for (int k = 0; k < 3; ++k) wd[k] = dp3(rd, P.world + 4 * k);
+        const float winv = rsq(dp3(wd, wd));
+        for (int k = 0; k < 3; ++k) n[k] = winv * wd[k];
+        const float yy = n[1] * n[1], zz = n[2] * n[2];
+        const float a = std::fmaf(n[0], n[0], -yy) * 0.4290427565574646f;
+        const float b = std::fmaf(zz, 3.0f, -1.0f) * 0.24770796298980713f;
+        for (int c = 0; c < 3; ++c) {
+            float r10 = P.sh[6][c] * b;
+            r10 = std::fmaf(a, P.sh[8][c], r10);
+            float r3 = std::fmaf(P.sh[0][c], 0.8862269520759583f, r10);
+            float r8 = P.sh[4][c] * -n[0];
+            r10 = P.sh[7][c] * -n[0];
+            r10 = n[2] * r10;
+            r8 = std::fmaf(r8, -n[1], r10);
+            const float r9 = P.sh[5][c] * -n[1];
+            r8 = std::fmaf(r9, n[2], r8);
+            r3 = std::fmaf(r8, 0.8580855131149292f, r3);
+            float r4 = P.sh[1][c] * -n[1];
+            r4 = std::fmaf(P.sh[3][c], -n[0], r4);
+            r4 = std::fmaf(P.sh[2][c], n[2], r4);
+            r3 = std::fmaf(r4, 1.0233267545700073f, r3);
+            irr[c] = std::fmax(r3, 0.0f);
+        }
+        const float rinv = rsq(dp3(rd, rd));
+        float rdn[3];
+        for (int k = 0; k < 3; ++k) rdn[k] = rinv * rd[k];
+        ao = cast_light_ray(col, g, pos, rdn, lstep, P.num_samples);
+    }
+    for (int c = 0; c < 3; ++c) {
+        const float lc = P.light_color[3] * P.light_color[c];
+        const float amb = P.has_light_probes ? ao * irr[c] : P.ambient[3] * P.ambient[c];
+        light[c] = std::fmaf(lc, shadow, amb);
+    }
+}
+
+// lmap != nullptr: CSRayMarchV (light read from the light map); lmap == nullptr: CSRayMarch (light computed per sample, LP)
+void ray_march_v(const Grid& g, const uint16_t* col, const uint32_t* lmap, const ViewParams& P, uint8_t* cube,
+                 const LightParams* LP = nullptr) {
     const int S = (int)P.cube_size;
     const float FMAX = 3.402823466e+38f;
 #pragma omp parallel for collapse(2) schedule(dynamic, 4)
@@ -614,13 +671,21 @@ void ray_march_v(const Grid& g, const uint16_t* col, const uint32_t* lmap, const
                 float tm[3];
                 for (int k = 0; k < 3; ++k) tm[k] = (tg[k] + -ro[k]) / dir[k];
                 const float tmax = std::fmax(tm[2], std::fmax(tm[1], tm[0]));
+                float ldir[3] = {0.0f, 0.0f, 0.0f};
+                if (!lmap) {
+                    float Lv[3];
+                    for (int k = 0; k < 3; ++k) Lv[k] = dp3(LP->light_pt, LP->world_i + 4 * k);
+                    const float linv = rsq(dp3(Lv, Lv));
+                    for (int k = 0; k < 3; ++k) ldir[k] = linv * Lv[k];
+                }
                 float sc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, t = 0.0f, prev = 0.0f;
                 for (uint32_t i = 0; i < P.num_samples; ++i) {
                     float pos[3];
                     for (int k = 0; k < 3; ++k) pos[k] = std::fmaf(dir[k], t, ro[k]);
                     if (1.0f < std::fabs(pos[0]) || 1.0f < std::fabs(pos[1]) || 1.0f < std::fabs(pos[2])) break;
-                    const Taps tp = clamp_taps(g, std::fmaf(pos[0], 0.5f, 0.5f), std::fmaf(pos[1], 0.5f, 0.5f),
-                                               std::fmaf(pos[2], 0.5f, 0.5f));
+                    const float uvw[3] = {std::fmaf(pos[0], 0.5f, 0.5f), std::fmaf(pos[1], 0.5f, 0.5f),
+                                          std::fmaf(pos[2], 0.5f, 0.5f)};
+                    const Taps tp = clamp_taps(g, uvw[0], uvw[1], uvw[2]);
                     const size_t idx[8] = {g.idx(tp.x0, tp.y0, tp.z0), g.idx(tp.x1, tp.y0, tp.z0), g.idx(tp.x0, tp.y1, tp.z0),
                                            g.idx(tp.x1, tp.y1, tp.z0), g.idx(tp.x0, tp.y0, tp.z1), g.idx(tp.x1, tp.y0, tp.z1),
                                            g.idx(tp.x0, tp.y1, tp.z1), g.idx(tp.x1, tp.y1, tp.z1)};
@@ -632,10 +697,14 @@ void ray_march_v(const Grid& g, const uint16_t* col, const uint32_t* lmap, const
                     float r5[4], new_step;
                     if (0.01f < c[3]) {
                         float L[3], tex[8][3];
-                        for (int k = 0; k < 8; ++k) unpack_r11g11b10(lmap[idx[k]], tex[k]);
-                        for (int ch = 0; ch < 3; ++ch) {
-                            for (int k = 0; k < 8; ++k) a[k] = tex[k][ch];
-                            L[ch] = trilerp(tp, a);
+                        if (lmap) {
+                            for (int k = 0; k < 8; ++k) unpack_r11g11b10(lmap[idx[k]], tex[k]);
+                            for (int ch = 0; ch < 3; ++ch) {
+                                for (int k = 0; k < 8; ++k) a[k] = tex[k][ch];
+                                L[ch] = trilerp(tp, a);
+                            }
+                        } else {
+                            full_light(col, g, *LP, pos, uvw, ldir, L);
                         }
                         const float transm = -sc[3] + 1.0f;
                         const float ev = std::fmin(0.00390625f / std::fabs(-prev + c[3]), 2.0f);
@@ -836,6 +905,11 @@ void fxo_light_map(int nx, int ny, int nz, const uint16_t* colour, const void* p
 void fxo_ray_march_v(int nx, int ny, int nz, const uint16_t* colour, const uint32_t* light_map, const void* params,
                      uint8_t* cube) {
     ray_march_v(Grid{nx, ny, nz}, colour, light_map, *static_cast<const ViewParams*>(params), cube);
+}
+// The non-separated march (CSRayMarch): `light` = LightParams, whose num_samples is the light-ray sample count.
+void fxo_ray_march(int nx, int ny, int nz, const uint16_t* colour, const void* view, const void* light, uint8_t* cube) {
+    ray_march_v(Grid{nx, ny, nz}, colour, nullptr, *static_cast<const ViewParams*>(view), cube,
+                static_cast<const LightParams*>(light));
 }
 void fxo_unpack_r11g11b10(uint32_t w, float* out3) { unpack_r11g11b10(w, out3); }
 uint32_t fxo_pack_r11g11b10(float r, float g, float b) {

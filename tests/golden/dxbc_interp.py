@@ -34,14 +34,14 @@ import numpy as np
 F32, U32, I32 = np.float32, np.uint32, np.int32
 
 OPCODES = {0: "add", 1: "and", 2: "break", 3: "breakc", 6: "case", 10: "default", 14: "div", 16: "dp3", 17: "dp4", 18: "else",
-           23: "endswitch", 41: "ishl", 43: "itof", 76: "switch", 21: "endif", 22: "endloop", 25: "exp",
+           23: "endswitch", 41: "ishl", 43: "itof", 76: "switch", 105: "dcl_indexable_temp", 21: "endif", 22: "endloop", 25: "exp",
            60: "or", 68: "rsq", 162: "dcl_resource_structured", 167: "ld_structured",
            29: "ge", 30: "iadd", 31: "if", 45: "ld", 48: "loop", 49: "lt", 50: "mad", 51: "min", 52: "max", 54: "mov",
            55: "movc", 56: "mul", 61: "resinfo", 62: "ret", 72: "sample_l", 80: "uge", 83: "umax", 84: "umin", 86: "utof",
            88: "dcl_resource", 89: "dcl_constant_buffer", 90: "dcl_sampler", 95: "dcl_input", 104: "dcl_temps",
            106: "dcl_global_flags", 155: "dcl_thread_group", 156: "dcl_uav_typed", 163: "ld_uav_typed",
            164: "store_uav_typed", 190: "sync"}
-OPERAND_TYPES = {0: "r", 4: "l", 6: "s", 7: "t", 8: "cb", 30: "u", 32: "vThreadID"}
+OPERAND_TYPES = {0: "r", 3: "x", 4: "l", 6: "s", 7: "t", 8: "cb", 30: "u", 32: "vThreadID"}
 COMP = "xyzw"
 
 
@@ -64,6 +64,8 @@ class Operand:
         s = self.kind
         if self.kind == "cb":
             s += "[%d][%d]" % (self.index[0], self.index[1])
+        elif self.kind == "x":
+            s += "%d[%d]" % (self.index[0], self.index[1])
         elif self.kind != "vThreadID":
             s += str(self.index[0])
         if self.ncomp == 4:
@@ -338,6 +340,7 @@ class Machine:
             {0: np.asarray(cb0, U32).reshape(1, 4)}
         self.srv, self.uav, self.clamp = srv, uav, clamp
         self.retired = np.zeros(self.n, bool)  # threads that executed `ret` inside control flow
+        self.x = {}             # indexable temp arrays x#: [element, thread, component]
         self.iterations = 0     # trips of the relaxation loop in which at least one thread was inside
         self.active_entering = []  # threads inside the loop at the start of each trip
 
@@ -349,6 +352,8 @@ class Machine:
         else:
             if o.kind == "r":
                 base = self.r[o.index[0]]
+            elif o.kind == "x":  # indexable temp array x#[i], immediate index
+                base = self.x.setdefault(o.index[0], np.zeros((32, self.n, 4), U32))[o.index[1]]
             elif o.kind == "vThreadID":
                 base = self.tid
             elif o.kind == "cb":
@@ -371,13 +376,15 @@ class Machine:
         return (~self.read(plain) + U32(1)).astype(U32)
 
     def write(self, o: Operand, value_u32, mask_threads, sat=False):
-        assert o.kind == "r" and o.mode == "mask"
+        assert o.kind in ("r", "x") and o.mode == "mask"
         if sat:
             f = value_u32.view(F32)
             value_u32 = np.where(np.isnan(f), F32(0), np.clip(f, F32(0), F32(1))).astype(F32).view(U32)
+        reg = self.r[o.index[0]] if o.kind == "r" else \
+            self.x.setdefault(o.index[0], np.zeros((32, self.n, 4), U32))[o.index[1]]
         for k in range(4):
             if o.mask >> k & 1:
-                col = self.r[o.index[0]][:, k]
+                col = reg[:, k]
                 col[mask_threads] = value_u32[mask_threads, k]
 
     # -- run

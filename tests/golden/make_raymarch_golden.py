@@ -70,15 +70,29 @@ def run_case(blobs, grid, seed, light_samples, probes, ray_samples, cube_size, e
     m = D.Machine(blobs["CSRayMarchV"], (cube_size, cube_size, 6), cbs_v,
                   srv={0: D.Texture(col, "rgba16f"), 1: D.Texture(lmap, "r11g11b10f")},
                   uav={0: D.Texture(cube, "rgba8unorm")}, clamp=True).run()
-    return col, plain_l, plain_v, lmap, cube, m
+    # The non-separated march (Fluid::rayMarch, Fluid.cpp:825-855): CSRayMarch.cso casts the light (and occlusion) ray
+    # at every view sample instead of reading a light map; cbSampleRes = (ray samples, has probes, light samples).
+    cbs_f = dict(cbs_v)
+    cb2 = np.zeros((1, 4), U32)
+    cb2[0, 0], cb2[0, 1], cb2[0, 2] = ray_samples, probes, light_samples
+    cbs_f[2] = cb2
+    cube_full = np.zeros((6, cube_size, cube_size, 4), np.uint8)
+    D.Machine(blobs["CSRayMarch"], (cube_size, cube_size, 6), cbs_f,
+              srv={0: D.Texture(col, "rgba16f"), 1: plain_l["sh"].view(U32)},
+              uav={0: D.Texture(cube_full, "rgba8unorm")}, clamp=True).run()
+    return col, plain_l, plain_v, lmap, cube, m, cube_full
 
 
 def main():
-    blobs = {n: open(os.path.join(REF, n + ".cso"), "rb").read() for n in ("CSRayMarchL", "CSRayMarchV")}
+    blobs = {n: open(os.path.join(REF, n + ".cso"), "rb").read() for n in ("CSRayMarchL", "CSRayMarchV", "CSRayMarch")}
     res = {"blob_sha256/" + n: np.frombuffer(hashlib.sha256(b).digest(), np.uint8) for n, b in blobs.items()}
     for name, case in CASES.items():
-        col, plain_l, plain_v, lmap, cube, m = run_case(blobs, *case)
+        col, plain_l, plain_v, lmap, cube, m, cube_full = run_case(blobs, *case)
         res[name + "/cube_map"] = cube
+        res[name + "/cube_map_full"] = cube_full
+        diff = np.abs(cube.astype(int) - cube_full.astype(int))
+        print(name, "non-separated march: texels written", int((cube_full[..., 3] > 0).sum()), "max |difference| to the "
+              "light-map version", int(diff.max()), "texels differing", int((diff.max(-1) > 0).sum()))
         res[name + "/light_map"] = lmap
         res[name + "/input_sha256"] = np.frombuffer(hashlib.sha256(col.tobytes() + plain_l["sh"].tobytes()).digest(), np.uint8)
         a = cube[..., 3]

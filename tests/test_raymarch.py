@@ -57,6 +57,17 @@ def test_oracle_reproduces_the_interpreted_bytecode(golden, name):
     assert (want[..., 3] > 0).sum() > 50 and len(np.unique(want.reshape(-1, 4), axis=0)) > 50
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_the_interpreted_non_separated_march(golden, name):
+    """Bin/CSRayMarch.cso (Fluid::rayMarch, Fluid.cpp:825-855): light and occlusion rays cast at every view sample."""
+    col, plain_l, plain_v = case_inputs(golden, name)
+    got = oracle.ray_march(col, view_params(plain_v), oracle_params(plain_l))
+    want = golden[name + "/cube_map_full"]
+    assert np.array_equal(got, want), (name, int((got != want).sum()))
+    # and it is the same picture as the light-map version up to that map's quantisation and interpolation
+    assert np.abs(want.astype(int) - golden[name + "/cube_map"].astype(int)).max() < 48
+
+
 def test_unpack_is_the_inverse_of_pack_on_every_word_class():
     r = np.random.default_rng(3)
     words = np.concatenate([r.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32),
