@@ -66,23 +66,44 @@ int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uin
     return FXB_OK;
 }
 
+namespace {
+// (Re)allocates the cube-map mip for edge `size`, zero-filled like a new committed resource.
+int ensure_cube_map(fxb_sim* s, uint32_t size) {
+    if (size < 1 || size > 4096) return fail(FXB_ERR_INVALID, "cube_size out of range (1..4096)");
+    if (s->cube_size == size) return FXB_OK;
+    FXB_CUDA(cudaDeviceSynchronize());
+    cudaFree(s->cube_map);
+    s->cube_map = nullptr;
+    s->cube_size = 0;
+    const size_t bytes = (size_t)6 * size * size * sizeof(unsigned);
+    FXB_CUDA(cudaMalloc((void**)&s->cube_map, bytes));
+    FXB_CUDA(cudaMemset(s->cube_map, 0, bytes));
+    s->cube_size = size;
+    return FXB_OK;
+}
+}  // namespace
+
 int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
     if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");
     if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids on one GPU only");
     if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: fxb_light_map has not run (the light map is an input)");
-    if (params->cube_size < 1 || params->cube_size > 4096) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: cube_size out of range");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
-    if (s->cube_size != params->cube_size) {
-        FXB_CUDA(cudaDeviceSynchronize());
-        cudaFree(s->cube_map);
-        s->cube_map = nullptr;
-        s->cube_size = 0;
-        const size_t bytes = (size_t)6 * params->cube_size * params->cube_size * sizeof(unsigned);
-        FXB_CUDA(cudaMalloc((void**)&s->cube_map, bytes));
-        FXB_CUDA(cudaMemset(s->cube_map, 0, bytes));
-        s->cube_size = params->cube_size;
-    }
+    if (const int rc = ensure_cube_map(s, params->cube_size)) return rc;
     FXB_CUDA(fxb::launch_ray_march_v(s->dom, s->col[s->parity], s->light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
+    s->last_stream = (cudaStream_t)cuda_stream;
+    return FXB_OK;
+}
+
+int fxb_ray_march(fxb_sim* s, const fxb_view_params* view, const fxb_light_params* light, void* cuda_stream) {
+    if (!s || !view || !light) return fail(FXB_ERR_INVALID, "fxb_ray_march: null argument");
+    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march: 3D grids on one GPU only");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (const int rc = ensure_cube_map(s, view->cube_size)) return rc;
+    if (!s->light_density)
+        FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
+    FXB_CUDA(fxb::launch_extract_density(s->col[s->parity], s->light_density, s->own_voxels(), (cudaStream_t)cuda_stream));
+    FXB_CUDA(fxb::launch_ray_march(s->dom, s->col[s->parity], s->light_density, s->cube_map, view, light,
+                                   (cudaStream_t)cuda_stream));
     s->last_stream = (cudaStream_t)cuda_stream;
     return FXB_OK;
 }

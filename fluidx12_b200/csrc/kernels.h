@@ -17,7 +17,11 @@ struct HaloComm;
 cudaError_t launch_light_map(const Domain& d, const void* colour_own, unsigned short* dens, unsigned* out,
                              const void* consts, HaloComm* comm, cudaStream_t stream);
 
-// raymarch.cu — the view-ray march into the cube map (CSRayMarchV); consts = fxb_view_params
+cudaError_t launch_extract_density(const void* colour, unsigned short* dens, size_t n, cudaStream_t stream);
+
+// raymarch.cu — the view-ray march into the cube map (CSRayMarchV / CSRayMarch); consts = fxb_view_params
+cudaError_t launch_ray_march(const Domain& d, const void* colour, const unsigned short* dens, unsigned* cube,
+                             const void* view, const void* light, cudaStream_t stream);
 cudaError_t launch_ray_march_v(const Domain& d, const void* colour, const unsigned* light_map, unsigned* cube,
                                const void* consts, cudaStream_t stream);
 

@@ -49,6 +49,13 @@ __global__ void __launch_bounds__(512) light_map_kernel(const unsigned short* __
 
 }  // namespace
 
+// colour.w of n voxels into the compact half array (also used by the non-separated ray march, raymarch.cu)
+cudaError_t launch_extract_density(const void* colour, unsigned short* dens, size_t n, cudaStream_t stream) {
+    const size_t threads = n / 4 + 1;
+    extract_density_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(static_cast<const uint2*>(colour), dens, n);
+    return cudaGetLastError();
+}
+
 // colour_own: the rank's owned planes of the colour field; dens: density array of the whole grid (plane 0 = global
 // plane 0).  With several ranks the owned planes are extracted in place and every other slab arrives over NCCL
 // (2 bytes per voxel of the grid per rank: a light ray crosses every slab).

@@ -155,6 +155,72 @@ FXL_FN unsigned fxl_pack_r11g11b10(const float r, const float g, const float b) 
     return out;
 }
 
+// The light reaching the point o (volume space; u = its texture coordinate) where there is smoke — GetLight of
+// RayMarch.hlsli:280-313 / the body of CSRayMarchL.hlsl:44-77: transmittance towards the light, and with light probes
+// the occlusion ray along the density gradient times the SH irradiance instead of the constant ambient term.
+// l0..l2: the normalised light direction in volume space; step / num_samples: of the light rays.
+FXL_FN void fxl_light_at(const unsigned short* __restrict__ dens, const LightGeom& g, const LightConsts& P, const float o0,
+                         const float o1, const float o2, const float u0, const float u1, const float u2, const float l0,
+                         const float l1, const float l2, const float step, float& shadow, float& ao, float (&irr)[3]) {
+    shadow = fxl_cast_ray(dens, g, o0, o1, o2, l0, l1, l2, step, P.num_samples);
+    ao = 1.0f;
+    irr[0] = irr[1] = irr[2] = 0.0f;
+    if (P.has_light_probes) {
+        const float q0 = fxl_density(dens, g, u0, u1, u2, -1, 0, 0), q1 = fxl_density(dens, g, u0, u1, u2, 1, 0, 0);
+        const float q2 = fxl_density(dens, g, u0, u1, u2, 0, -1, 0), q3 = fxl_density(dens, g, u0, u1, u2, 0, 1, 0);
+        const float q4 = fxl_density(dens, g, u0, u1, u2, 0, 0, -1), q5 = fxl_density(dens, g, u0, u1, u2, 0, 0, 1);
+        const float g0 = -q0 + q1, g1 = -q2 + q3, g2 = -q4 + q5;
+        const bool any = 0.0f < fxl_abs(g0) || 0.0f < fxl_abs(g1) || 0.0f < fxl_abs(g2);
+        const float r0 = any ? -g0 : o0, r1 = any ? -g1 : o1, r2 = any ? -g2 : o2;  // uniform density: use the position
+        const float w0 = fxl_dp3(r0, r1, r2, P.world + 0), w1 = fxl_dp3(r0, r1, r2, P.world + 4);
+        const float w2 = fxl_dp3(r0, r1, r2, P.world + 8);
+        const float wv[3] = {w0, w1, w2};
+        const float winv = fxl_rsq(fxl_dp3(w0, w1, w2, wv));
+        const float n0 = winv * w0, n1 = winv * w1, n2 = winv * w2;
+        const float yy = n1 * n1, zz = n2 * n2;
+        const float a = fxl_fma(n0, n0, -yy) * 0.4290427565574646f;    // c1 (x^2 - y^2)
+        const float b = fxl_fma(zz, 3.0f, -1.0f) * 0.24770796298980713f;  // c5 (3 z^2 - 1)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float t10 = P.sh[6][c] * b;
+            t10 = fxl_fma(a, P.sh[8][c], t10);
+            float t3 = fxl_fma(P.sh[0][c], 0.8862269520759583f, t10);   // c4 L00
+            float t8 = P.sh[4][c] * -n0;
+            t10 = P.sh[7][c] * -n0;
+            t10 = n2 * t10;
+            t8 = fxl_fma(t8, -n1, t10);
+            const float t9 = P.sh[5][c] * -n1;
+            t8 = fxl_fma(t9, n2, t8);
+            t3 = fxl_fma(t8, 0.8580855131149292f, t3);                   // 2 c1 (xy, xz, yz terms)
+            float t4 = P.sh[1][c] * -n1;
+            t4 = fxl_fma(P.sh[3][c], -n0, t4);
+            t4 = fxl_fma(P.sh[2][c], n2, t4);
+            t3 = fxl_fma(t4, 1.0233267545700073f, t3);                   // 2 c2 (linear terms)
+            irr[c] = fxl_max(t3, 0.0f);
+        }
+        const float rv[3] = {r0, r1, r2};
+        const float rinv = fxl_rsq(fxl_dp3(r0, r1, r2, rv));
+        ao = fxl_cast_ray(dens, g, o0, o1, o2, rinv * r0, rinv * r1, rinv * r2, step, P.num_samples);
+    }
+}
+
+// light colour x shadow + (occlusion x irradiance | ambient), one channel
+FXL_FN float fxl_combine(const LightConsts& P, const int c, const float shadow, const float ao, const float irr) {
+    const float lc = P.light_color[3] * P.light_color[c];
+    const float amb = P.has_light_probes ? ao * irr : P.ambient[3] * P.ambient[c];
+    return fxl_fma(shadow, lc, amb);
+}
+
+// The normalised light direction in volume space (mul(g_lightPt, (float3x3)g_worldI), normalize)
+FXL_FN void fxl_light_dir(const LightConsts& P, float& l0, float& l1, float& l2) {
+    const float a0 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 0);
+    const float a1 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 4);
+    const float a2 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 8);
+    const float lv[3] = {a0, a1, a2};
+    const float inv = fxl_rsq(fxl_dp3(a0, a1, a2, lv));
+    l0 = inv * a0; l1 = inv * a1; l2 = inv * a2;
+}
+
 // The light-map word of voxel (x, y, z).
 FXL_FN unsigned light_map_voxel(const unsigned short* __restrict__ dens, const LightGeom& g, const LightConsts& P,
                                 const int x, const int y, const int z) {
@@ -165,58 +231,12 @@ FXL_FN unsigned light_map_voxel(const unsigned short* __restrict__ dens, const L
     float shadow = 1.0f, ao = 1.0f, irr[3] = {0.0f, 0.0f, 0.0f};
     if (fxl_density(dens, g, u0, u1, u2, 0, 0, 0) >= 0.01f) {
         const float step = 3.464101552963257f / (float)P.num_samples;  // g_maxDist = 2 sqrt(3) (RayMarch.hlsli:29-30)
-        const float l0 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 0);
-        const float l1 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 4);
-        const float l2 = fxl_dp3(P.light_pt[0], P.light_pt[1], P.light_pt[2], P.world_i + 8);
-        const float lv[3] = {l0, l1, l2};
-        const float inv = fxl_rsq(fxl_dp3(l0, l1, l2, lv));
-        shadow = fxl_cast_ray(dens, g, o0, o1, o2, inv * l0, inv * l1, inv * l2, step, P.num_samples);
-        if (P.has_light_probes) {
-            const float q0 = fxl_density(dens, g, u0, u1, u2, -1, 0, 0), q1 = fxl_density(dens, g, u0, u1, u2, 1, 0, 0);
-            const float q2 = fxl_density(dens, g, u0, u1, u2, 0, -1, 0), q3 = fxl_density(dens, g, u0, u1, u2, 0, 1, 0);
-            const float q4 = fxl_density(dens, g, u0, u1, u2, 0, 0, -1), q5 = fxl_density(dens, g, u0, u1, u2, 0, 0, 1);
-            const float g0 = -q0 + q1, g1 = -q2 + q3, g2 = -q4 + q5;
-            const bool any = 0.0f < fxl_abs(g0) || 0.0f < fxl_abs(g1) || 0.0f < fxl_abs(g2);
-            const float r0 = any ? -g0 : o0, r1 = any ? -g1 : o1, r2 = any ? -g2 : o2;  // uniform density: use the position
-            const float w0 = fxl_dp3(r0, r1, r2, P.world + 0), w1 = fxl_dp3(r0, r1, r2, P.world + 4);
-            const float w2 = fxl_dp3(r0, r1, r2, P.world + 8);
-            const float wv[3] = {w0, w1, w2};
-            const float winv = fxl_rsq(fxl_dp3(w0, w1, w2, wv));
-            const float n0 = winv * w0, n1 = winv * w1, n2 = winv * w2;
-            const float yy = n1 * n1, zz = n2 * n2;
-            const float a = fxl_fma(n0, n0, -yy) * 0.4290427565574646f;    // c1 (x^2 - y^2)
-            const float b = fxl_fma(zz, 3.0f, -1.0f) * 0.24770796298980713f;  // c5 (3 z^2 - 1)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float t10 = P.sh[6][c] * b;
-                t10 = fxl_fma(a, P.sh[8][c], t10);
-                float t3 = fxl_fma(P.sh[0][c], 0.8862269520759583f, t10);   // c4 L00
-                float t8 = P.sh[4][c] * -n0;
-                t10 = P.sh[7][c] * -n0;
-                t10 = n2 * t10;
-                t8 = fxl_fma(t8, -n1, t10);
-                const float t9 = P.sh[5][c] * -n1;
-                t8 = fxl_fma(t9, n2, t8);
-                t3 = fxl_fma(t8, 0.8580855131149292f, t3);                   // 2 c1 (xy, xz, yz terms)
-                float t4 = P.sh[1][c] * -n1;
-                t4 = fxl_fma(P.sh[3][c], -n0, t4);
-                t4 = fxl_fma(P.sh[2][c], n2, t4);
-                t3 = fxl_fma(t4, 1.0233267545700073f, t3);                   // 2 c2 (linear terms)
-                irr[c] = fxl_max(t3, 0.0f);
-            }
-            const float rv[3] = {r0, r1, r2};
-            const float rinv = fxl_rsq(fxl_dp3(r0, r1, r2, rv));
-            ao = fxl_cast_ray(dens, g, o0, o1, o2, rinv * r0, rinv * r1, rinv * r2, step, P.num_samples);
-        }
+        float l0, l1, l2;
+        fxl_light_dir(P, l0, l1, l2);
+        fxl_light_at(dens, g, P, o0, o1, o2, u0, u1, u2, l0, l1, l2, step, shadow, ao, irr);
     }
-    float rgb[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float lc = P.light_color[3] * P.light_color[c];
-        const float amb = P.has_light_probes ? ao * irr[c] : P.ambient[3] * P.ambient[c];
-        rgb[c] = fxl_fma(shadow, lc, amb);
-    }
-    return fxl_pack_r11g11b10(rgb[0], rgb[1], rgb[2]);
+    return fxl_pack_r11g11b10(fxl_combine(P, 0, shadow, ao, irr[0]), fxl_combine(P, 1, shadow, ao, irr[1]),
+                              fxl_combine(P, 2, shadow, ao, irr[2]));
 }
 
 }  // namespace fxb

@@ -67,8 +67,14 @@ FXL_FN float fxr_lerp3(const float fx, const float fy, const float fz, const flo
 }
 
 // Marches the ray of texel (x, y) of `face`; returns false when nothing is to be written.
-FXL_FN bool ray_march_texel(const RU2* __restrict__ col, const unsigned* __restrict__ lmap, const LightGeom& g,
-                            const ViewConsts& P, const int x, const int y, const int face, unsigned* rgba8) {
+// SEPARATE = true: CSRayMarchV — the light at a sample is fetched from the light map `lmap` (Fluid::rayMarchV after
+// Fluid::rayMarchL).  SEPARATE = false: CSRayMarch (Fluid::rayMarch, Fluid.cpp:825-855; Bin/CSRayMarch.cso) — the
+// light is computed on the spot by fxl_light_at over the compact density array `dens` with the light constants `LP`
+// (LP->num_samples = g_numLightSamples).
+template <bool SEPARATE>
+FXL_FN bool ray_march_texel(const RU2* __restrict__ col, const unsigned* __restrict__ lmap,
+                            const unsigned short* __restrict__ dens, const LightGeom& g, const ViewConsts& P,
+                            const LightConsts* LP, const int x, const int y, const int face, unsigned* rgba8) {
     if (((1u << face) & P.visibility_mask) == 0u) return false;
     float ro[3];
 #pragma unroll
@@ -128,13 +134,19 @@ FXL_FN bool ray_march_texel(const RU2* __restrict__ col, const unsigned* __restr
     }
     const float step = 3.464101552963257f / (float)P.num_samples;
     const float tmax = fxl_max((tg[2] + -ro[2]) / dir[2], fxl_max((tg[1] + -ro[1]) / dir[1], (tg[0] + -ro[0]) / dir[0]));
+    float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, lstep = 0.0f;
+    if (!SEPARATE) {
+        fxl_light_dir(*LP, l0, l1, l2);
+        lstep = 3.464101552963257f / (float)LP->num_samples;  // g_lightStep (RayMarch.hlsli:31)
+    }
     float sc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, t = 0.0f, prev = 0.0f;
     for (unsigned i = 0; i < P.num_samples; ++i) {
         const float p0 = fxl_fma(dir[0], t, ro[0]), p1 = fxl_fma(dir[1], t, ro[1]), p2 = fxl_fma(dir[2], t, ro[2]);
         if (1.0f < fxl_abs(p0) || 1.0f < fxl_abs(p1) || 1.0f < fxl_abs(p2)) break;
-        const float tx = fxl_fma(fxl_fma(p0, 0.5f, 0.5f), (float)g.nx, -0.5f);
-        const float ty = fxl_fma(fxl_fma(p1, 0.5f, 0.5f), (float)g.ny, -0.5f);
-        const float tz = fxl_fma(fxl_fma(p2, 0.5f, 0.5f), (float)g.nz, -0.5f);
+        const float uu0 = fxl_fma(p0, 0.5f, 0.5f), uu1 = fxl_fma(p1, 0.5f, 0.5f), uu2 = fxl_fma(p2, 0.5f, 0.5f);
+        const float tx = fxl_fma(uu0, (float)g.nx, -0.5f);
+        const float ty = fxl_fma(uu1, (float)g.ny, -0.5f);
+        const float tz = fxl_fma(uu2, (float)g.nz, -0.5f);
         const int ix = fxl_tap(tx), iy = fxl_tap(ty), iz = fxl_tap(tz);
         const float fx = tx - fxl_floor(tx), fy = ty - fxl_floor(ty), fz = tz - fxl_floor(tz);
         const int x0 = fxl_clamp(ix, g.nx), x1 = fxl_clamp(ix + 1, g.nx);
@@ -158,17 +170,24 @@ FXL_FN bool ray_march_texel(const RU2* __restrict__ col, const unsigned* __restr
         }
         float r5[4], new_step;
         if (0.01f < c[3]) {
-            unsigned lw[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) lw[k] = fxr_ld4(lmap + idx[k]);
             float L[3];
+            if (SEPARATE) {
+                unsigned lw[8];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
+                for (int k = 0; k < 8; ++k) lw[k] = fxr_ld4(lmap + idx[k]);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    a[k] = ch == 0 ? fxr_unpack(lw[k] & 0x7FFu, 6) : (ch == 1 ? fxr_unpack((lw[k] >> 11) & 0x7FFu, 6)
-                                                                              : fxr_unpack(lw[k] >> 22, 5));
-                L[ch] = fxr_lerp3(fx, fy, fz, a);
+                for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        a[k] = ch == 0 ? fxr_unpack(lw[k] & 0x7FFu, 6) : (ch == 1 ? fxr_unpack((lw[k] >> 11) & 0x7FFu, 6)
+                                                                                  : fxr_unpack(lw[k] >> 22, 5));
+                    L[ch] = fxr_lerp3(fx, fy, fz, a);
+                }
+            } else {
+                float shadow, ao, irr[3];
+                fxl_light_at(dens, g, *LP, p0, p1, p2, uu0, uu1, uu2, l0, l1, l2, lstep, shadow, ao, irr);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) L[ch] = fxl_combine(*LP, ch, shadow, ao, irr[ch]);
             }
             const float transm = -sc[3] + 1.0f;
             const float ev = fxl_min(0.00390625f / fxl_abs(-prev + c[3]), 2.0f);

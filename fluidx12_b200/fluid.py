@@ -152,6 +152,15 @@ class Fluid:
         B.check(B.lib().fxb_ray_march_v(self._handle(), C.byref(params), stream))
         self._cube_size = int(params.cube_size)
 
+    # -- Fluid::rayMarch (Fluid.cpp:825-855): the march without the separate light pass ------------------------------
+    def RayMarch(self, view: "B.FxbViewParams", light: "B.FxbLightParams" = None, pCommandList=None) -> None:
+        """Enqueues CSRayMarch: light (and occlusion) rays are cast at every view sample; ``light.num_samples`` is the
+        light-ray sample count."""
+        light = light if light is not None else B.FxbLightParams.reference_defaults()
+        stream = C.c_void_p(int(pCommandList)) if pCommandList else C.c_void_p(0)
+        B.check(B.lib().fxb_ray_march(self._handle(), C.byref(view), C.byref(light), stream))
+        self._cube_size = int(view.cube_size)
+
     def get_cube_map(self) -> np.ndarray:
         """The cube-map mip last written: [6][S][S][4] UNORM8 (faces +X, -X, +Y, -Y, +Z, -Z)."""
         s = getattr(self, "_cube_size", 0)

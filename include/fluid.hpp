@@ -74,6 +74,11 @@ public:
     // Fluid::rayMarchV (Fluid.cpp:880-908): CSRayMarchV into one mip of the cube map, lit by RayMarchL's light map.
     int RayMarchV(const fxb_view_params& params, void* stream = nullptr) { return fxb_ray_march_v(m_sim, &params, stream); }
 
+    // Fluid::rayMarch (Fluid.cpp:825-855): CSRayMarch, the march that computes the light at every view sample.
+    int RayMarch(const fxb_view_params& view, const fxb_light_params& light, void* stream = nullptr) {
+        return fxb_ray_march(m_sim, &view, &light, stream);
+    }
+
     // No counterpart in the reference, whose renderer binds m_colors[m_frameParity] in place (Fluid.cpp:760-770, 841):
     // writes the field as a volume file for a renderer outside the process (fluidx_b200.h, fxb_volume_header).
     bool Export(const char* path, int field = FXB_FIELD_COLOR) {

@@ -201,7 +201,12 @@ int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uin
  * input).  Texels of culled faces and of rays that miss the volume keep their previous contents, as in the reference
  * (zero after allocation or after a change of cube_size).  1 <= cube_size <= 4096.  3D grids, nranks == 1. */
 int fxb_ray_march_v(fxb_sim* sim, const fxb_view_params* params, void* cuda_stream);
-/* Synchronous copy of the cube map written by the last fxb_ray_march_v: [6][S][S][4] bytes (R, G, B, A UNORM8). */
+/* Replaces Fluid::rayMarch (Fluid.cpp:825-855), the mode without the separate light pass (Fluid::RAY_MARCH_CUBEMAP
+ * alone): CSRayMarch casts the light ray — and with light probes the occlusion ray plus the SH irradiance — at every
+ * view sample instead of reading the light map.  `light->num_samples` is g_numLightSamples (m_maxLightSamples,
+ * Fluid.cpp:844).  Needs no fxb_light_map; same cube map, same rules as fxb_ray_march_v. */
+int fxb_ray_march(fxb_sim* sim, const fxb_view_params* view, const fxb_light_params* light, void* cuda_stream);
+/* Synchronous copy of the cube map written by the last fxb_ray_march_v / fxb_ray_march: [6][S][S][4] bytes (R, G, B, A UNORM8). */
 int fxb_get_cube_map(fxb_sim* sim, void* host, size_t bytes);
 
 /* ---- Volume files: the hand-off format of a field to a renderer ------------------------------

@@ -43,6 +43,47 @@ def test_body_reproduces_the_interpreted_bytecode(emu, name):
     assert np.array_equal(got, want), (name, int((got != want).sum()))
 
 
+def run_body_full(emu, col, view, light):
+    nz, ny, nx, _ = col.shape
+    col = np.ascontiguousarray(col, np.float16)
+    dens = np.ascontiguousarray(col[..., 3]).view(np.uint16)
+    s = int(view.cube_size)
+    out = np.zeros((6, s, s, 4), np.uint8)
+    emu.raymarch_emu_run_full(nx, ny, nz, col.ctypes.data_as(C.c_void_p), dens.ctypes.data_as(C.c_void_p), C.byref(view),
+                              C.byref(light), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_non_separated_body_reproduces_the_interpreted_bytecode(emu, name):
+    golden = np.load(GOLDEN)
+    col, plain_l, plain_v = case_inputs(golden, name)
+    got = run_body_full(emu, col, view_params(plain_v), oracle_params(plain_l))
+    want = golden[name + "/cube_map_full"]
+    assert np.array_equal(got, want), (name, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("probes", [0, 1])
+def test_non_separated_body_matches_the_oracle_on_a_simulated_plume(emu, probes):
+    n = (24, 24, 16)
+    o = oracle.FluidOracle(*n)
+    dt = oracle.dt_for_grid(*n)
+    for _ in range(30):
+        o.step(dt)
+    col = o.get_field(oracle.FIELD_COLOR)
+    _, plain_l = light_constants(16, probes, (75.0, 75.0, -75.0), 3)
+    plain_l["light_color"][3] = 2.0
+    wi = plain_l["world_i"].copy()
+    wi[:, 3] = [0.01, 0.02, -0.03]
+    eye = (14.0, 22.0, -31.0)
+    plain_v = {"eye_pt": np.array(eye, np.float32), "world_i": wi, "num_samples": 48,
+               "visibility_mask": visibility_mask(wi, eye), "cube_size": 16}
+    pv, pl = view_params(plain_v), oracle_params(plain_l)
+    want = oracle.ray_march(col, pv, pl)
+    assert np.array_equal(run_body_full(emu, col, pv, pl), want)
+    assert (want[..., 3] > 0).sum() > 100
+
+
 @pytest.mark.parametrize("eye", [(14.0, 22.0, -31.0), (0.5, 1.0, -1.5), (-60.0, 0.0, 0.0)])
 def test_body_matches_the_oracle_on_a_simulated_plume(emu, eye):
     n = (32, 32, 24)

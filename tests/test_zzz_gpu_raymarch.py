@@ -34,6 +34,14 @@ def test_cuda_ray_march_reproduces_the_interpreted_bytecode(name):
     got, want = f.get_cube_map(), golden[name + "/cube_map"]
     assert np.array_equal(got, want), (name, int((got != want).sum()))
     f.close()
+    # the non-separated march (CSRayMarch) on a fresh handle: no light map needed, its own golden cube map
+    f = fx.Fluid()
+    assert f.Init(gridSize=CASES[name][0]), f.last_error
+    f.set_field(fx.FIELD_COLOR, col)
+    f.RayMarch(as_fx(view_params(plain_v), fx.FxbViewParams), as_fx(oracle_params(plain_l), fx.FxbLightParams))
+    got, want = f.get_cube_map(), golden[name + "/cube_map_full"]
+    assert np.array_equal(got, want), (name, "non-separated", int((got != want).sum()))
+    f.close()
 
 
 def test_cube_map_of_a_simulated_plume_matches_the_oracle():
