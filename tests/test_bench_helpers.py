@@ -132,3 +132,75 @@ def test_state_checksum_sees_a_moved_or_changed_word():
 def test_multi_gpu_experiments_are_opt_in():
     src = open(os.path.join(ROOT, "bench.py")).read()
     assert "--experiments-multi" in src and "world == 1 or args.experiments_multi" in src
+
+
+def test_gpu_shot_bench_mode_runs_to_the_end_on_a_fake_device(monkeypatch, tmp_path):
+    """tools/gpu_shot.py --bench (the child of bench.py's experiments stage) against a fake Fluid: every stage must
+    emit a record that bench.experiments_single_gpu can summarise — no typo may cost the one free measurement."""
+    import importlib
+    import types
+
+    import fluidx12_b200 as real
+
+    class F:
+        def Init(self, gridSize):
+            self.n, self.k, self.env = tuple(gridSize), 0, {k: v for k, v in os.environ.items() if k.startswith("FXB_")}
+            self.last_error = ""
+            return True
+
+        def step(self, dt):
+            self.k += 1
+
+        UpdateFrame = step
+
+        def sync(self):
+            pass
+
+        def close(self):
+            pass
+
+        def get_field(self, fld):
+            return np.full((2, 2, 2) + ((4,) if fld != real.FIELD_PRESSURE else ()), 0.25, np.float16 if fld != real.FIELD_PRESSURE else np.float32)
+
+        def set_field(self, fld, a):
+            pass
+
+        def profile_step(self):
+            return {"advect": 0.3, "divergence": 0.1, "jacobi": 1.0, "gradient": 0.1, "halo": 0.0, "step": 1.5}
+
+        def tail_stats(self):
+            return {"enabled": True, "tail_launches_last_step": 13, "tail_bricks": 1, "tail_subblocks_relaxed": 1,
+                    "tail_subblocks_dense": 0}
+
+        def stats(self):
+            return types.SimpleNamespace(jacobi_passes=17, s_exec=64)
+
+        def RayMarchL(self, p):
+            pass
+
+        def RayMarchV(self, v):
+            self.s = int(v.cube_size)
+
+        def get_light_map(self):
+            return np.arange(8 ** 3, dtype=np.uint32).reshape(8, 8, 8)
+
+        def get_cube_map(self):
+            return np.ones((6, 4, 4, 4), np.uint8)
+
+    fake = types.SimpleNamespace(Fluid=F, dt_for_grid=real.dt_for_grid, lib=real.lib, FxbLightParams=real.FxbLightParams,
+                                 FxbViewParams=real.FxbViewParams, FIELD_VELOCITY=0, FIELD_COLOR=1, FIELD_PRESSURE=2)
+    out = tmp_path / "shot.jsonl"
+    monkeypatch.setenv("FXB_SHOT_OUT", str(out))
+    monkeypatch.setattr(sys, "argv", ["gpu_shot.py", "--bench"])
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    shot = importlib.import_module("gpu_shot")
+    shot = importlib.reload(shot)          # picks up FXB_SHOT_OUT
+    shot.bench_mode(fake)
+    rows = [json.loads(ln) for ln in open(out)]
+    assert rows[-1]["stage"] == "done" and not any("error" in r for r in rows), [r for r in rows if "error" in r]
+    stages = [r["stage"] for r in rows]
+    assert stages.count("light_map") == 6 and stages.count("timing") == 2 + 10 + 5
+    monkeypatch.setattr(bench, "run_child", lambda cmd, env, t: (open(env["FXB_SHOT_OUT"], "w").write(open(out).read()), (0, ""))[1])
+    res = bench.experiments_single_gpu(5)
+    assert len(res["results"]) == 6 + 17 and {r["variant"] for r in res["results"]} >= {"default", "tail", "advect2_only",
+                                                                                        "tail_pass0", "light_map_pass"}
