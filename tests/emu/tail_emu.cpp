@@ -18,13 +18,19 @@ namespace {
 using namespace fxb;
 
 long long g_paths[3] = {0, 0, 0};  // items that took the copy / sparse / dense path
+long long g_smem_overruns = 0;     // work items that wrote outside the S::kBytes the CUDA launch requests
 bool g_descending = false;         // thread order inside a barrier-free segment
 
 template <class S>
 void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const float* p_in, float* p_out,
               const float* rhs, const unsigned char* m_in, unsigned char* m_out, unsigned long long* active_after_s0) {
-    std::vector<unsigned char> smem(S::kBytes + 64, 0);
-    const TailShared<S> sh = tail_shared<S>(smem.data());
+    // the kernel's dynamic shared memory is exactly S::kBytes: guard bands on both sides catch any write outside it
+    constexpr size_t kGuard = 4096;
+    std::vector<unsigned char> block(S::kBytes + 2 * kGuard + 16, 0xA5);
+    unsigned char* base = block.data() + kGuard;
+    base += (16 - reinterpret_cast<uintptr_t>(base) % 16) % 16;
+    std::fill(base, base + S::kBytes, (unsigned char)0);
+    const TailShared<S> sh = tail_shared<S>(base);
     // poison the staged data so that a read of something never written shows up as a mismatch
     for (int i = 0; i < S::kPFloats + S::kRhsFloats; ++i) sh.p[i] = 1.0e30f;
     for (int i = 0; i < S::kCtrlWords; ++i) sh.ctrl[i] = 0xDEADBEEFu;
@@ -33,6 +39,10 @@ void run_item(const TailParams& P, const TailWork& W, int brick, int sub, const 
     TailTma tma;
     const int path = tail_run_item<S>(emu, sh, P, W, brick, sub, p_in, p_out, rhs, m_in, m_out, active_after_s0, nullptr, tma, P.levels);
     ++g_paths[path];
+    bool clean = true;
+    for (unsigned char* q = block.data(); q < base; ++q) clean = clean && *q == 0xA5;
+    for (unsigned char* q = base + S::kBytes; q < block.data() + block.size(); ++q) clean = clean && *q == 0xA5;
+    if (!clean) ++g_smem_overruns;
 }
 
 }  // namespace
@@ -88,6 +98,13 @@ void tail_emu_thread_order(int descending) { g_descending = descending != 0; }
 // Items that took the copy / sparse / dense path since the last call (and resets the counters).
 void tail_emu_paths(long long* out3) {
     for (int i = 0; i < 3; ++i) { out3[i] = g_paths[i]; g_paths[i] = 0; }
+}
+
+// Work items that wrote outside the kernel's S::kBytes of shared memory since the last call (and resets the counter).
+long long tail_emu_smem_overruns() {
+    const long long n = g_smem_overruns;
+    g_smem_overruns = 0;
+    return n;
 }
 
 }  // extern "C"

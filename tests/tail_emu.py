@@ -76,4 +76,7 @@ def launch(g: BrickGrid, p_in, p_out, rhs, m_in, m_out, relax_in, copy_in, brick
                                C.c_int(relax_in.size), _p(copy_in), C.c_int(copy_in.size), _p(relax_out), _p(nr),
                                _p(copy_out), _p(nc), _p(brick_state), _p(hist_s0))
     assert rc >= 0, "unsupported shape"
+    lib().tail_emu_smem_overruns.restype = C.c_longlong
+    overruns = lib().tail_emu_smem_overruns()
+    assert overruns == 0, "%d work items wrote outside the shared memory the CUDA launch requests (S::kBytes)" % overruns
     return relax_out[:nr[0]].copy(), copy_out[:nc[0]].copy()
