@@ -582,6 +582,8 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.brick_state);
     cudaFree(s->light_map);
     cudaFree(s->cube_map);
+    cudaFree(s->whole_colour);
+    cudaFree(s->whole_light_map);
     cudaFree(s->light_density);
     cudaFree(s->emitter_basis);
     cudaFree(s->axis_tables);

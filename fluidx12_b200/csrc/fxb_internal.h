@@ -72,6 +72,8 @@ struct fxb_sim {
     unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
     unsigned* cube_map = nullptr;          // one mip of m_cubeMap (Fluid.cpp:229-232): [6][S][S] RGBA8 words
     uint32_t cube_size = 0;
+    void* whole_colour = nullptr;          // nranks > 1: the colour field / light map of the WHOLE grid, gathered from all
+    unsigned* whole_light_map = nullptr;   // ranks for the view-ray march (a view ray crosses every z-slab)
     unsigned short* light_density = nullptr;  // colour.w of every voxel, the channel the light-map pass samples
     bool multi() const { return cfg.nranks > 1; }
     cudaEvent_t ev[8] = {};

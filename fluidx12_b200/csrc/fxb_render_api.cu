@@ -81,29 +81,64 @@ int ensure_cube_map(fxb_sim* s, uint32_t size) {
     s->cube_size = size;
     return FXB_OK;
 }
+// The colour field (and, if asked, the light map) of the whole grid as the view-ray march needs them.  One GPU: the
+// fields themselves.  z-slabs: every rank copies its planes into a whole-grid array and the ranks exchange their slabs
+// (HaloComm::all_gather_slabs; 8 + 4 bytes per voxel of the grid per rank), after which every rank marches all 6 S^2
+// rays — a few hundred thousand, far cheaper than a second exchange of the cube map.
+int whole_fields(fxb_sim* s, bool need_light_map, cudaStream_t st, const void** colour, const unsigned** light_map) {
+    *colour = s->col[s->parity];
+    *light_map = s->light_map;
+    if (!s->multi()) return FXB_OK;
+    const size_t plane = s->plane_voxels(), whole = plane * s->cfg.nz, z0 = (size_t)s->dom.z_own0;
+    if (!s->whole_colour) FXB_CUDA(cudaMalloc(&s->whole_colour, whole * 8));
+    FXB_CUDA(cudaMemcpyAsync(static_cast<char*>(s->whole_colour) + plane * z0 * 8,
+                             static_cast<const char*>(s->col[s->parity]) + s->own_offset() * 8, s->own_voxels() * 8,
+                             cudaMemcpyDeviceToDevice, st));
+    if (!s->comm.all_gather_slabs(s->whole_colour, plane * 8, (int)s->cfg.nz, st))
+        return fail(FXB_ERR_NCCL, "colour gather failed: " + fxb::halo_last_error());
+    *colour = s->whole_colour;
+    if (need_light_map) {
+        if (!s->whole_light_map) FXB_CUDA(cudaMalloc((void**)&s->whole_light_map, whole * 4));
+        FXB_CUDA(cudaMemcpyAsync(s->whole_light_map + plane * z0, s->light_map, s->own_voxels() * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+        if (!s->comm.all_gather_slabs(s->whole_light_map, plane * 4, (int)s->cfg.nz, st))
+            return fail(FXB_ERR_NCCL, "light-map gather failed: " + fxb::halo_last_error());
+        *light_map = s->whole_light_map;
+    }
+    return FXB_OK;
+}
 }  // namespace
 
 int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
     if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");
-    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids on one GPU only");
+    if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: 3D grids only");
     if (!s->light_map) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: fxb_light_map has not run (the light map is an input)");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     if (const int rc = ensure_cube_map(s, params->cube_size)) return rc;
-    FXB_CUDA(fxb::launch_ray_march_v(s->dom, s->col[s->parity], s->light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
+    const void* colour;
+    const unsigned* light_map;
+    if (const int rc = whole_fields(s, true, (cudaStream_t)cuda_stream, &colour, &light_map)) return rc;
+    FXB_CUDA(fxb::launch_ray_march_v(s->dom, colour, light_map, s->cube_map, params, (cudaStream_t)cuda_stream));
     s->last_stream = (cudaStream_t)cuda_stream;
     return FXB_OK;
 }
 
 int fxb_ray_march(fxb_sim* s, const fxb_view_params* view, const fxb_light_params* light, void* cuda_stream) {
     if (!s || !view || !light) return fail(FXB_ERR_INVALID, "fxb_ray_march: null argument");
-    if (s->cfg.nz <= 1 || s->multi()) return fail(FXB_ERR_INVALID, "fxb_ray_march: 3D grids on one GPU only");
+    if (s->cfg.nz <= 1) return fail(FXB_ERR_INVALID, "fxb_ray_march: 3D grids only");
+    if (s->multi() && s->plane_voxels() % 4 != 0)
+        return fail(FXB_ERR_INVALID, "fxb_ray_march: with nranks > 1 nx * ny must be a multiple of 4");
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     if (const int rc = ensure_cube_map(s, view->cube_size)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const void* colour;
+    const unsigned* unused;
+    if (const int rc = whole_fields(s, false, st, &colour, &unused)) return rc;
     if (!s->light_density)
         FXB_CUDA(cudaMalloc((void**)&s->light_density, (s->plane_voxels() * s->cfg.nz + 4) * sizeof(unsigned short)));
-    FXB_CUDA(fxb::launch_extract_density(s->col[s->parity], s->light_density, s->own_voxels(), (cudaStream_t)cuda_stream));
-    FXB_CUDA(fxb::launch_ray_march(s->dom, s->col[s->parity], s->light_density, s->cube_map, view, light,
-                                   (cudaStream_t)cuda_stream));
+    // the density channel of the whole grid: extracted from the (gathered) colour field in one go
+    FXB_CUDA(fxb::launch_extract_density(colour, s->light_density, s->plane_voxels() * s->cfg.nz, st));
+    FXB_CUDA(fxb::launch_ray_march(s->dom, colour, s->light_density, s->cube_map, view, light, st));
     s->last_stream = (cudaStream_t)cuda_stream;
     return FXB_OK;
 }

@@ -199,7 +199,9 @@ typedef struct fxb_view_params {
 int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask);
 /* Replaces Fluid::rayMarchV: enqueues the march on `cuda_stream`.  fxb_light_map must have run (the light map is an
  * input).  Texels of culled faces and of rays that miss the volume keep their previous contents, as in the reference
- * (zero after allocation or after a change of cube_size).  1 <= cube_size <= 4096.  3D grids, nranks == 1. */
+ * (zero after allocation or after a change of cube_size).  1 <= cube_size <= 4096.  3D grids.  With nranks > 1 every
+ * rank calls it: a view ray crosses every z-slab, so the ranks first gather the colour field and the light map of the
+ * whole grid (8 + 4 bytes per voxel per rank, ncclSend/ncclRecv) and every rank then holds the complete cube map. */
 int fxb_ray_march_v(fxb_sim* sim, const fxb_view_params* params, void* cuda_stream);
 /* Replaces Fluid::rayMarch (Fluid.cpp:825-855), the mode without the separate light pass (Fluid::RAY_MARCH_CUBEMAP
  * alone): CSRayMarch casts the light ray — and with light probes the occlusion ray plus the SH irradiance — at every

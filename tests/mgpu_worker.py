@@ -97,6 +97,32 @@ def main():
             ok = ok and same
         else:
             dist.send(mine, dst=0)
+        # the cube-map marches on z-slabs (colour and light map of the whole grid gathered on every rank): every rank
+        # ends up with the complete cube map, which must be the single-GPU one
+        import ctypes as C
+        v = fx.FxbViewParams()
+        v.eye_pt[:] = [4.0, 16.0, -40.0]
+        v.world_i[:] = lp.world_i[:]
+        v.num_samples, v.cube_size = 96, 32
+        mask = C.c_uint32()
+        fx.lib().fxb_cube_visibility_mask(v.world_i, v.eye_pt, C.byref(mask))
+        v.visibility_mask = mask.value
+        f.RayMarchV(v)
+        cube_v = f.get_cube_map()
+        v.num_samples, v.cube_size = 32, 16
+        lp.num_samples = 16
+        f.RayMarch(v, lp)
+        cube_f = f.get_cube_map()
+        if rank == 0:
+            v.num_samples, v.cube_size = 96, 32
+            ref.RayMarchV(v)
+            same_v = np.array_equal(cube_v, ref.get_cube_map())
+            v.num_samples, v.cube_size = 32, 16
+            ref.RayMarch(v, lp)
+            same_f = np.array_equal(cube_f, ref.get_cube_map())
+            print(f"cube maps: {'identical' if same_v and same_f else 'MISMATCH'} "
+                  f"({int((cube_v[..., 3] > 0).sum())} / {int((cube_f[..., 3] > 0).sum())} texels with smoke)")
+            ok = ok and same_v and same_f
     if rank == 0:
         rs = ref.stats()
         print("s_exec", st.s_exec, rs.s_exec, "halo_overflow", st.halo_overflow)

@@ -77,11 +77,11 @@ def test_ranks_with_peer_memory_halos(nproc, grid, tail):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("FXB_TEST_EXPERIMENTAL") != "1",
-                    reason="the z-slab light-map pass has not run on GPUs yet (FXB_TEST_EXPERIMENTAL=1 enables it)")
+                    reason="the z-slab light-map pass and ray marches have not run on GPUs yet (FXB_TEST_EXPERIMENTAL=1 enables them)")
 @pytest.mark.parametrize("nproc,grid", [(2, "64,64,96"), (4, "128,128,128")])
-def test_ranks_light_map_pass_matches_single_gpu(nproc, grid):
+def test_ranks_light_map_and_ray_marches_match_single_gpu(nproc, grid):
     import torch
     if torch.cuda.device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
     rc, log = _run(nproc, {"FXB_TEST_GRID": grid, "FXB_TEST_T": "2", "FXB_TEST_LIGHTMAP": "1"})
-    assert rc == 0 and "MGPU_OK" in log and "light map: identical" in log, log[-3000:]
+    assert rc == 0 and "MGPU_OK" in log and "light map: identical" in log and "cube maps: identical" in log, log[-3000:]
