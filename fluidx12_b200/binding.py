@@ -16,7 +16,7 @@ FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_
 EXPORTS = (
     "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
-    "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+    "fxb_post_stats", "fxb_wait_stats", "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
     "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
     "fxb_light_map", "fxb_get_light_map", "fxb_cube_visibility_mask", "fxb_ray_march_v", "fxb_ray_march", "fxb_get_cube_map",
 )
@@ -140,6 +140,8 @@ def lib() -> C.CDLL:
         L.fxb_set_field.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.fxb_get_field_async.argtypes = [vp, C.c_int, vp, C.c_size_t, vp]
         L.fxb_get_stats.argtypes = [vp, C.POINTER(FxbStats)]
+        L.fxb_post_stats.argtypes = [vp, C.c_int]
+        L.fxb_wait_stats.argtypes = [vp, C.c_int, C.POINTER(FxbStats)]
         L.fxb_get_tail_stats.argtypes = [vp, vp, C.c_int]
         L.fxb_plan_pressure_solve.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]
         L.fxb_p2p_plan.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int64)]

@@ -582,6 +582,9 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.brick_state);
     cudaFree(s->light_map);
     cudaFree(s->cube_map);
+    if (s->stats_ring) cudaFreeHost(s->stats_ring);
+    for (int i = 0; i < fxb_sim::kStatsSlots; ++i)
+        if (s->stats_event[i]) cudaEventDestroy(s->stats_event[i]);
     cudaFree(s->whole_colour);
     cudaFree(s->whole_light_map);
     cudaFree(s->light_density);
@@ -690,21 +693,19 @@ int fxb_set_field(fxb_sim* s, int field, const void* host, size_t bytes) {
     return FXB_OK;
 }
 
-int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
-    if (!s || !out) return fail(FXB_ERR_INVALID, "fxb_get_stats: null argument");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    fxb::StepState st;
-    cudaStream_t stream = s->last_stream;
-    FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, stream));
-    FXB_CUDA(cudaStreamSynchronize(stream));
+}  // extern "C"
+
+namespace {
+// The public record of a step from a snapshot of the device-side counters.
+void fill_stats(const fxb_sim* s, const fxb::StepState& st, int parity, uint64_t steps, fxb_stats* out) {
     std::memset(out, 0, sizeof(*out));
     out->s_exec = st.s_exec;
     out->jacobi_passes = st.passes;
     out->fuse_t = s->fuse_t;
     out->halo_overflow = st.halo_overflow;
-    out->frame_parity = s->parity;
+    out->frame_parity = parity;
     out->kernels_per_step = s->kernels_per_step;
-    out->steps = s->steps;
+    out->steps = steps;
     out->active_after_first_sweep = st.active_after[0];
     out->total_sweeps = st.total_sweeps;
     out->total_passes = st.total_passes;
@@ -715,6 +716,44 @@ int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
         out->brick_cells = fxb::fused_jacobi_brick_cells(s->jac);
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);
     }
+}
+}  // namespace
+
+extern "C" {
+
+int fxb_get_stats(fxb_sim* s, fxb_stats* out) {
+    if (!s || !out) return fail(FXB_ERR_INVALID, "fxb_get_stats: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    fxb::StepState st;
+    cudaStream_t stream = s->last_stream;
+    FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, stream));
+    FXB_CUDA(cudaStreamSynchronize(stream));
+    fill_stats(s, st, s->parity, s->steps, out);
+    return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
+}
+
+int fxb_post_stats(fxb_sim* s, int slot) {
+    if (!s || slot < 0 || slot >= fxb_sim::kStatsSlots) return fail(FXB_ERR_INVALID, "fxb_post_stats: bad argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    if (!s->stats_ring) {
+        FXB_CUDA(cudaHostAlloc((void**)&s->stats_ring, fxb_sim::kStatsSlots * sizeof(fxb::StepState), cudaHostAllocDefault));
+        for (int i = 0; i < fxb_sim::kStatsSlots; ++i)
+            FXB_CUDA(cudaEventCreateWithFlags(&s->stats_event[i], cudaEventDisableTiming));
+    }
+    FXB_CUDA(cudaMemcpyAsync(&s->stats_ring[slot], s->d_state, sizeof(fxb::StepState), cudaMemcpyDeviceToHost, s->last_stream));
+    FXB_CUDA(cudaEventRecord(s->stats_event[slot], s->last_stream));
+    s->stats_steps[slot] = s->steps;
+    s->stats_parity[slot] = s->parity;
+    return FXB_OK;
+}
+
+int fxb_wait_stats(fxb_sim* s, int slot, fxb_stats* out) {
+    if (!s || !out || slot < 0 || slot >= fxb_sim::kStatsSlots) return fail(FXB_ERR_INVALID, "fxb_wait_stats: bad argument");
+    if (!s->stats_ring || s->stats_steps[slot] == 0) return fail(FXB_ERR_INVALID, "fxb_wait_stats: nothing was posted to this slot");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaEventSynchronize(s->stats_event[slot]));
+    const fxb::StepState& st = s->stats_ring[slot];
+    fill_stats(s, st, s->stats_parity[slot], s->stats_steps[slot], out);
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
 }
 

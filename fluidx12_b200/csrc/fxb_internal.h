@@ -72,6 +72,13 @@ struct fxb_sim {
     unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
     unsigned* cube_map = nullptr;          // one mip of m_cubeMap (Fluid.cpp:229-232): [6][S][S] RGBA8 words
     uint32_t cube_size = 0;
+    // fxb_post_stats / fxb_wait_stats: a ring of pinned snapshots of StepState with one event each, so that a frame
+    // loop can read step k's record while step k + 1 runs (the reference keeps FrameCount = 3 frames in flight, Fluid.h:35)
+    static constexpr int kStatsSlots = 4;
+    fxb::StepState* stats_ring = nullptr;  // pinned host memory, kStatsSlots entries
+    cudaEvent_t stats_event[kStatsSlots] = {};
+    uint64_t stats_steps[kStatsSlots] = {};
+    int stats_parity[kStatsSlots] = {};
     void* whole_colour = nullptr;          // nranks > 1: the colour field / light map of the WHOLE grid, gathered from all
     unsigned* whole_light_map = nullptr;   // ranks for the view-ray march (a view ray crosses every z-slab)
     unsigned short* light_density = nullptr;  // colour.w of every voxel, the channel the light-map pass samples

@@ -178,6 +178,16 @@ class Fluid:
         B.check(B.lib().fxb_get_stats(self._handle(), C.byref(st)))
         return st
 
+    def post_stats(self, slot: int) -> None:
+        """Enqueues a snapshot of the step record into pinned slot ``slot`` (0..3) behind the work enqueued so far."""
+        B.check(B.lib().fxb_post_stats(self._handle(), slot))
+
+    def wait_stats(self, slot: int) -> B.FxbStats:
+        """Blocks until the snapshot posted to ``slot`` has landed and returns it (the device keeps running)."""
+        st = B.FxbStats()
+        B.check(B.lib().fxb_wait_stats(self._handle(), slot, C.byref(st)))
+        return st
+
     def freeze_histogram(self, n: int = 64) -> np.ndarray:
         """Cells still active after sweep k+1 of the last step, k < n (the oracle's active_hist shifted by one)."""
         h = np.zeros(n, np.uint64)

@@ -122,6 +122,14 @@ int fxb_get_field_async(fxb_sim* sim, int field, void* host, size_t bytes, void*
 /* Reads back the device-side counters of the last step (synchronises the handle's stream). */
 int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 
+/* The same record without draining the pipeline: fxb_post_stats enqueues, behind everything the handle has enqueued so
+ * far, a copy of the counters into pinned slot `slot` (0..3) and an event; fxb_wait_stats blocks until that copy has
+ * landed and returns the record of the step that was last enqueued when it was posted.  A frame loop posts after every
+ * fxb_simulate and waits for the PREVIOUS frame's slot, so the device never idles — the reference keeps FrameCount = 3
+ * frames in flight the same way (Fluid.h:35, FluidX12.cpp:605-622). */
+int fxb_post_stats(fxb_sim* sim, int slot);
+int fxb_wait_stats(fxb_sim* sim, int slot, fxb_stats* out);
+
 /* Counters of the dynamic pressure-solve schedule (environment FXB_TAIL=1 at fxb_create; single GPU, default brick
  * shape).  Fills out[0..n), n <= 16: [0] = 1 when the schedule is in use, [1] = tail-kernel launches that did work in
  * the last step, [2] = cumulative bricks relaxed by tail launches (4 sweeps each), [3] = cumulative 40x12x8 sub-blocks

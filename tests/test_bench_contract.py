@@ -50,6 +50,13 @@ class FakeFluid:
         self.steps += 1
         return {"advect": 1.9, "divergence": 0.4, "jacobi": 2.9, "gradient": 0.5, "halo": 0.0, "step": 5.7}
 
+    def post_stats(self, slot):
+        self.posted = getattr(self, "posted", {})
+        self.posted[slot] = self.steps
+
+    def wait_stats(self, slot):
+        return FakeStats(self.posted[slot])
+
     def get_field_async(self, field, ptr, nbytes, stream=None):
         assert nbytes == self.m_gridSize[0] * self.m_gridSize[1] * self.m_gridSize[2] * 8
 
@@ -107,7 +114,7 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "c3", "experiments",
-                "e2e_export", "phase_roofline", "step_roofline"):
+                "e2e_export", "e2e_pipelined", "phase_roofline", "step_roofline"):
         assert key in line, key
     assert line["metric"] == "voxel_updates_per_s" and line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] == 3
     assert line["config"]["workload"].startswith("3D 32x32x32") and line["vs_baseline"] is None
