@@ -613,7 +613,7 @@ def run_ours(args):
         except Exception as e:
             line["experiments"] = {"error": repr(e)[:300]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=str), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
