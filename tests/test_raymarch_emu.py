@@ -118,3 +118,25 @@ def test_body_matches_the_oracle_on_edge_cases(emu):
                    "cube_size": s}
         p = view_params(plain_v)
         assert np.array_equal(run_body(emu, col, lmap, p), oracle.ray_march_v(col, lmap, p)), (eye, ns)
+
+
+def test_bodies_match_the_oracle_on_degenerate_constants(emu):
+    """Zero samples (an infinite step), a light at the origin or at infinity (NaN directions), a NaN eye: whatever the
+    reference's arithmetic makes of them, the kernel bodies and the oracle make the same of them."""
+    lm_emu = C.CDLL(os.path.join(_HERE, "liblightmap_emu.so"))
+    lm_emu.lightmap_emu_run.restype = None
+    r = np.random.default_rng(1)
+    col = (r.random((6, 6, 6, 4)) * np.array([1, 1, 1, 0.6])).astype(np.float16)
+    for light_samples, light_pt in ((0, (75.0, 75.0, -75.0)), (8, (0.0, 0.0, 0.0)), (8, (np.inf, 0.0, 0.0))):
+        _, plain_l = light_constants(light_samples, 1, light_pt, 2)
+        pl = oracle_params(plain_l)
+        scratch, got = np.empty((6, 6, 6), np.uint16), np.empty((6, 6, 6), np.uint32)
+        lm_emu.lightmap_emu_run(6, 6, 6, col.ctypes.data_as(C.c_void_p), C.byref(pl), scratch.ctypes.data_as(C.c_void_p),
+                                got.ctypes.data_as(C.c_void_p))
+        lmap = oracle.light_map(col, pl)
+        assert np.array_equal(got, lmap), (light_samples, light_pt)
+        for eye, ray_samples in (((14.0, 22.0, -31.0), 0), ((0.0, 0.0, 0.0), 16), ((np.nan, 1.0, 1.0), 16)):
+            pv = view_params({"eye_pt": np.array(eye, np.float32), "world_i": plain_l["world_i"], "num_samples": ray_samples,
+                              "visibility_mask": 63, "cube_size": 8})
+            assert np.array_equal(run_body(emu, col, lmap, pv), oracle.ray_march_v(col, lmap, pv)), (eye, ray_samples)
+            assert np.array_equal(run_body_full(emu, col, pv, pl), oracle.ray_march(col, pv, pl)), (eye, ray_samples)
