@@ -23,6 +23,11 @@
 //   schedule      FluidX12/Content/Fluid.cpp:283-291,344-345 (UpdateFrame), :348-410 (Simulate)
 //   dt rule       FluidX12/FluidX12.cpp:266-267
 //   formats       FluidX12/Content/Fluid.cpp:204-221 (RGBA16F velocity/colour, R32F pressure)
+// and, for the rows past the step (each pinned the same way, by executing the shipped blob —
+// tests/test_lightmap.py, tests/test_raymarch.py):
+//   CSRayMarchL   FluidX12/Content/Shaders/CSRayMarchL.hlsl:15-80 (+ RayMarch.hlsli)   light_map()
+//   CSRayMarchV   FluidX12/Content/Shaders/CSRayMarch.hlsl:98-196 with _LIGHT_PASS_     ray_march_v(lmap)
+//   CSRayMarch    the same file without it                                              ray_march_v(nullptr, LP)
 //
 // Decisions where the platform is implementation-defined:
 //   D1 pressure solve = synchronous double-buffered Jacobi, <=64 sweeps, per-cell freeze after the
