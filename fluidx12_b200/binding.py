@@ -18,7 +18,7 @@ EXPORTS = (
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
     "fxb_post_stats", "fxb_wait_stats", "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
     "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
-    "fxb_light_map", "fxb_get_light_map", "fxb_cube_visibility_mask", "fxb_ray_march_v", "fxb_ray_march", "fxb_get_cube_map",
+    "fxb_light_map", "fxb_get_light_map", "fxb_cube_visibility_mask", "fxb_estimate_cube_lod", "fxb_ray_march_v", "fxb_ray_march", "fxb_get_cube_map",
 )
 
 
@@ -156,6 +156,8 @@ def lib() -> C.CDLL:
         L.fxb_light_map.argtypes = [vp, C.POINTER(FxbLightParams), vp]
         L.fxb_get_light_map.argtypes = [vp, vp, C.c_size_t]
         L.fxb_cube_visibility_mask.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+        L.fxb_estimate_cube_lod.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.fxb_ray_march_v.argtypes = [vp, C.POINTER(FxbViewParams), vp]
         L.fxb_ray_march.argtypes = [vp, C.POINTER(FxbViewParams), C.POINTER(FxbLightParams), vp]
         L.fxb_get_cube_map.argtypes = [vp, vp, C.c_size_t]

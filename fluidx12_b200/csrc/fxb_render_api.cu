@@ -2,6 +2,8 @@
 // pass (Fluid::rayMarchL), the cube-map ray march (Fluid::rayMarchV) and volume files (the renderer hand-off format).
 // Kernels: lightmap.cu, raymarch.cu.  The step itself (Init / UpdateFrame / Simulate, field I/O, statistics) is in
 // fxb_api.cu.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -108,6 +110,40 @@ int whole_fields(fxb_sim* s, bool need_light_map, cudaStream_t st, const void** 
     return FXB_OK;
 }
 }  // namespace
+
+int fxb_estimate_cube_lod(const float m[16], float viewport_w, float viewport_h, uint32_t max_ray_samples,
+                          uint32_t num_mips, uint32_t cube_size0, uint32_t* ray_samples, uint32_t* lod) {
+    if (!m || !ray_samples || !lod || num_mips < 1 || cube_size0 < 1)
+        return fail(FXB_ERR_INVALID, "fxb_estimate_cube_lod: bad argument");
+    // ProjectToViewport (Fluid.cpp:86-106): the eight corners of [-1, 1]^3 through XMVector3TransformCoord (row vector
+    // times matrix, divided by w), to viewport pixels
+    static const float corner[8][3] = {{1, 1, 1}, {-1, 1, 1}, {1, -1, 1}, {-1, -1, 1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, -1}, {1, -1, -1}};
+    float px[8], py[8];
+    for (int i = 0; i < 8; ++i) {
+        const float x = corner[i][0], y = corner[i][1], z = corner[i][2];
+        const float rx = x * m[0] + y * m[4] + z * m[8] + m[12], ry = x * m[1] + y * m[5] + z * m[9] + m[13];
+        const float rw = x * m[3] + y * m[7] + z * m[11] + m[15];
+        px[i] = (rx / rw * 0.5f + 0.5f) * viewport_w;
+        py[i] = (ry / rw * -0.5f + 0.5f) * viewport_h;
+    }
+    // EstimateCubeEdgePixelSize (Fluid.cpp:108-139): the longest of the twelve projected edges
+    static const unsigned char edge[12][2] = {{0, 1}, {3, 2}, {1, 3}, {2, 0}, {4, 5}, {7, 6}, {5, 7}, {6, 4}, {1, 4}, {6, 3}, {5, 0}, {2, 7}};
+    float longest = 0.0f;
+    for (int i = 0; i < 12; ++i) {
+        const float ex = px[edge[i][1]] - px[edge[i][0]], ey = py[edge[i][1]] - py[edge[i][0]];
+        longest = std::max(std::sqrt(ex * ex + ey * ey), longest);
+    }
+    // EstimateCubeMapLOD (Fluid.cpp:141-166), upscale = 2, raySampleCountScale = 2
+    float s = longest / 2.0f;
+    float amount = 2.0f * s / std::sqrt(3.0f);
+    const uint32_t count = (uint32_t)std::ceil(amount);
+    *ray_samples = std::min(count, max_ray_samples);
+    amount = std::min(amount, (float)*ray_samples);
+    s = amount / 2.0f * std::sqrt(3.0f);
+    const float level = std::min(std::max(std::log2((float)cube_size0 / s), 0.0f), 255.0f);  // the reference casts to uint8_t
+    *lod = std::min<uint32_t>((uint32_t)(unsigned char)level, num_mips - 1);
+    return FXB_OK;
+}
 
 int fxb_ray_march_v(fxb_sim* s, const fxb_view_params* params, void* cuda_stream) {
     if (!s || !params) return fail(FXB_ERR_INVALID, "fxb_ray_march_v: null argument");

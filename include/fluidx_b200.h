@@ -205,6 +205,14 @@ typedef struct fxb_view_params {
 /* GenVisibilityMask (Fluid.cpp:51-63), no GPU needed: a face is marched iff the eye, in volume space, is on the inner
  * side of its plane (the cube map holds what is seen THROUGH the volume on the far faces). */
 int fxb_cube_visibility_mask(const float world_i[12], const float eye_pt[3], uint32_t* mask);
+/* EstimateCubeMapLOD (Fluid.cpp:141-166, with ProjectToViewport :86-106 and EstimateCubeEdgePixelSize :108-139), no GPU
+ * needed: from the row-major world-view-projection matrix (row vectors, as DirectXMath holds it before the transpose
+ * of Fluid.cpp:316) and the viewport size, the longest projected edge of the volume's cube gives the ideal ray sample
+ * count (clamped to max_ray_samples = m_maxRaySamples) and the cube-map mip to march (0 .. num_mips - 1; the reference
+ * uses 5 mips of a cube map of edge gridSize.x, Fluid.cpp:229-232).  *ray_samples is fxb_view_params.num_samples,
+ * cube_size0 >> *lod is fxb_view_params.cube_size. */
+int fxb_estimate_cube_lod(const float world_view_proj[16], float viewport_w, float viewport_h, uint32_t max_ray_samples,
+                          uint32_t num_mips, uint32_t cube_size0, uint32_t* ray_samples, uint32_t* lod);
 /* Replaces Fluid::rayMarchV: enqueues the march on `cuda_stream`.  fxb_light_map must have run (the light map is an
  * input).  Texels of culled faces and of rays that miss the volume keep their previous contents, as in the reference
  * (zero after allocation or after a change of cube_size).  1 <= cube_size <= 4096.  3D grids.  With nranks > 1 every

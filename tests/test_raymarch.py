@@ -130,3 +130,70 @@ def test_visibility_mask_of_the_library_is_the_references_rule():
     assert L.fxb_cube_visibility_mask(None, None, None) == fx.binding.FXB_ERR_INVALID
     assert L.fxb_ray_march_v(None, None, None) == fx.binding.FXB_ERR_INVALID
     assert L.fxb_get_cube_map(None, None, 0) == fx.binding.FXB_ERR_INVALID
+
+
+def test_cube_lod_estimate_follows_the_reference_host_code():
+    """fxb_estimate_cube_lod = EstimateCubeMapLOD (Fluid.cpp:141-166) with its two helpers, restated here in numpy
+    float32 with the same operation order: ideal ray-sample count from the longest projected cube edge, clamped by the
+    user's maximum, and the cube-map mip derived from it."""
+    import ctypes as C
+
+    import fluidx12_b200 as fx
+    L = fx.lib()
+    F = np.float32
+
+    def look_at_lh(eye, at, up):
+        z = (at - eye) / np.linalg.norm(at - eye)
+        x = np.cross(up, z)
+        x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        m = np.eye(4)
+        m[:3, 0], m[:3, 1], m[:3, 2] = x, y, z
+        m[3, :3] = [-x @ eye, -y @ eye, -z @ eye]
+        return m
+
+    def perspective_lh(fovy, aspect, zn, zf):
+        h = 1.0 / np.tan(fovy / 2)
+        m = np.zeros((4, 4))
+        m[0, 0], m[1, 1], m[2, 2], m[2, 3], m[3, 2] = h / aspect, h, zf / (zf - zn), 1.0, -zn * zf / (zf - zn)
+        return m
+
+    def restated(m, vw, vh, max_samples, mips, size0):
+        m = m.astype(F).reshape(-1)
+        corner = np.array([[1, 1, 1], [-1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, -1], [1, 1, -1], [-1, -1, -1], [1, -1, -1]], F)
+        px, py = [], []
+        for x, y, z in corner:
+            rx = F(F(F(x * m[0]) + F(y * m[4])) + F(z * m[8])) + m[12]
+            ry = F(F(F(x * m[1]) + F(y * m[5])) + F(z * m[9])) + m[13]
+            rw = F(F(F(x * m[3]) + F(y * m[7])) + F(z * m[11])) + m[15]
+            px.append(F(F(F(F(rx / rw) * F(0.5)) + F(0.5)) * F(vw)))
+            py.append(F(F(F(F(ry / rw) * F(-0.5)) + F(0.5)) * F(vh)))
+        edges = [(0, 1), (3, 2), (1, 3), (2, 0), (4, 5), (7, 6), (5, 7), (6, 4), (1, 4), (6, 3), (5, 0), (2, 7)]
+        longest = F(0)
+        for a, b in edges:
+            ex, ey = F(px[b] - px[a]), F(py[b] - py[a])
+            longest = max(np.sqrt(F(F(ex * ex) + F(ey * ey))), longest)
+        s = F(longest / F(2))
+        amount = F(F(F(2) * s) / np.sqrt(F(3)))
+        samples = min(int(np.ceil(amount)), max_samples)
+        amount = min(amount, F(samples))
+        s = F(F(amount / F(2)) * np.sqrt(F(3)))
+        level = max(np.log2(F(F(size0) / s)), F(0))
+        return samples, min(int(level), mips - 1)
+
+    r = np.random.default_rng(12)
+    seen = set()
+    for _ in range(300):
+        eye = r.standard_normal(3) * r.uniform(15, 120)
+        view = look_at_lh(eye, r.standard_normal(3) * 2, np.array([0.0, 1.0, 0.0]))
+        vw, vh = float(r.integers(320, 3840)), float(r.integers(240, 2160))
+        proj = perspective_lh(np.pi / 4, vw / vh, 1.0, 1000.0)
+        wvp = ((np.eye(4) * [10, 10, 10, 1]) @ view @ proj).astype(F)
+        size0 = int(r.choice([64, 128, 256, 512]))
+        want = restated(wvp, vw, vh, 192, 5, size0)
+        a, b = C.c_uint32(), C.c_uint32()
+        assert L.fxb_estimate_cube_lod(wvp.ctypes.data_as(C.POINTER(C.c_float)), vw, vh, 192, 5, size0, C.byref(a), C.byref(b)) == 0
+        assert (a.value, b.value) == want, (eye, vw, vh, size0)
+        seen.add(want)
+    assert len({s for s, _ in seen}) > 20 and {lvl for _, lvl in seen} >= {0, 1, 2}     # the cases are not all alike
+    assert L.fxb_estimate_cube_lod(None, 1.0, 1.0, 1, 1, 1, None, None) == fx.binding.FXB_ERR_INVALID
