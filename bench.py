@@ -652,6 +652,24 @@ def run_reference(args):
         o.step(dt)
     sec = time.perf_counter() - t0
     value = n ** 3 * args.steps / sec
+    # BASELINE.json configs[0] and [1] in full (they are small enough for the host): 2D 256^2 (Fluid2D.bat setup) and
+    # 3D 128^3, emitter-driven from the zero state, timed after a short spin-up
+    small = {}
+    for key, g, spin_s, steps_s in (("c1_2d_256x256", (256, 256, 1), 50, 200), ("c2_3d_128_cubed", (128, 128, 128), 30, 20)):
+        try:
+            oc = oracle.FluidOracle(*g)
+            cdt = oracle.dt_for_grid(*g)
+            for _ in range(spin_s):
+                oc.step(cdt)
+            tc = time.perf_counter()
+            for _ in range(steps_s):
+                oc.step(cdt)
+            tc = time.perf_counter() - tc
+            small[key] = {"grid": list(g), "steps": steps_s, "spinup": spin_s, "ms_per_step": round(1e3 * tc / steps_s, 4),
+                          "value": g[0] * g[1] * g[2] * steps_s / tc, "unit": UNIT, "s_exec_last": int(oc.s_exec)}
+            oc.close()
+        except Exception as e:
+            small[key] = {"error": repr(e)[:200]}
     grid = tuple(args.grid) if args.grid else WEAK_GRIDS.get(world, WEAK_GRIDS[1])
     sample = ("OpenMP C++ restatement of the reference HLSL (the reference needs Windows/D3D12 and cannot run "
               "here), %d threads, %d^3 sample of the workload, spun up %d steps" % (cores, n, spin))
@@ -664,6 +682,7 @@ def run_reference(args):
                    "sample_grid": [n, n, n]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "baseline_configs": small,
     }))
 
 
