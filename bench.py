@@ -549,26 +549,31 @@ def run_ours(args):
         line["cpu_baseline"] = cpu_baseline_sample(g, fx, cgrid, cdt)
         if g is not f:
             g.close()
-    if rank == 0 and world == 1 and not args.no_c3 and grid != (256, 256, 256):
-        g = make_sim(fx, (256, 256, 256), args, 0, 1, local_rank, None)
-        cdt = fx.dt_for_grid(256, 256, 256)
+    # BASELINE configs[2] (256^3: the roofline-characterisation config) and configs[1] (128^3, the reference's default
+    # grid, FluidX12.cpp:44) on the same GPU, same method as the main workload
+    for key, cn, label in (("c3", 256, "3D 256^3 (BASELINE config 3: roofline characterisation)"),
+                           ("c2", 128, "3D 128^3 (BASELINE config 2: the reference's default grid; fits in L2)")):
+        if not (rank == 0 and world == 1 and not args.no_c3 and grid != (cn, cn, cn)):
+            continue
+        g = make_sim(fx, (cn, cn, cn), args, 0, 1, local_rank, None)
+        cdt = fx.dt_for_grid(cn, cn, cn)
         for _ in range(args.spinup):
             g.UpdateFrame(cdt); g.Simulate(stream.cuda_stream)
         cms, c0, c1 = timed_run(torch, dist, g, cdt, args.steps, args.warmup, 1, stream)
-        cv = 256 ** 3
+        cv = cn ** 3
         cjb, cproc, ccop = jacobi_work_bytes(c0, c1, mask_bytes, cv)
         cwork = 64.0 * cv + cjb / args.steps
         cnom = bytes_per_voxel_step((c1.total_passes - c0.total_passes) / args.steps, mask_bytes)
         croof, cphase_roof, cph = phase_rooflines(g, cdt, cv, peak, peak_src, 5, mask_bytes)
         ct = cms * 1e-3 / args.steps
-        line["c3"] = {"workload": "3D 256^3 (BASELINE config 3: roofline characterisation)",
-                      "value": cv * args.steps / (cms * 1e-3), "ms_per_step": cms / args.steps,
-                      "jacobi_passes_per_step": round((c1.total_passes - c0.total_passes) / args.steps, 2),
-                      "sweeps_per_step": round((c1.total_sweeps - c0.total_sweeps) / args.steps, 2),
-                      "bytes_per_voxel_step": round(cwork / cv, 2),
-                      "step_roofline_frac": round(cwork / ct / 1e9 / peak, 4),
-                      "nominal_formula_frac": round(cnom * cv / ct / 1e9 / peak, 4),
-                      "roofline": croof, "phase_roofline": cphase_roof, "phase_ms": cph}
+        line[key] = {"workload": label,
+                     "value": cv * args.steps / (cms * 1e-3), "ms_per_step": cms / args.steps,
+                     "jacobi_passes_per_step": round((c1.total_passes - c0.total_passes) / args.steps, 2),
+                     "sweeps_per_step": round((c1.total_sweeps - c0.total_sweeps) / args.steps, 2),
+                     "bytes_per_voxel_step": round(cwork / cv, 2),
+                     "step_roofline_frac": round(cwork / ct / 1e9 / peak, 4),
+                     "nominal_formula_frac": round(cnom * cv / ct / 1e9 / peak, 4),
+                     "roofline": croof, "phase_roofline": cphase_roof, "phase_ms": cph}
         g.close()
     if not args.no_export_e2e and world == 1:
         # extras, after everything the contract needs has been measured.  First the e2e loop with the renderer

@@ -113,7 +113,7 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     assert len(out) == 1
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "c3", "experiments",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "c3", "c2", "experiments",
                 "e2e_export", "e2e_pipelined", "phase_roofline", "step_roofline"):
         assert key in line, key
     assert line["metric"] == "voxel_updates_per_s" and line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] == 3
