@@ -13,8 +13,11 @@ W warm-up steps, then exactly K timed steps.
 
 Grid: N = 1 -> 512^3 (BASELINE config "3D 512^3 ... at 1/2/4/8 B200", 1-GPU point; every field is far
 larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decomposed: 512x512x1024 (2),
-1024x1024x512 (4), 1024^3 (8, BASELINE config 5).  At N = 1 the line also carries "c3": the 256^3
-roofline-characterisation config.  --grid overrides.
+1024x1024x512 (4), 1024^3 (8, BASELINE config 5).  At N = 1 the line also carries "c3" (the 256^3
+roofline-characterisation config) and "c2" (128^3), two further host-timed loops ("e2e_pipelined": one frame in
+flight; "e2e_export": the colour field copied out every step) and "experiments": the opt-in variants of the step, the
+light-map pass and the ray march, timed in a child process with a hard time limit AFTER everything above (--no-experiments
+skips it; use that under ncu).  --grid overrides.  `--impl reference` also steps BASELINE's two small configs in full.
 """
 from __future__ import annotations
 
