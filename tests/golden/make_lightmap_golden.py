@@ -20,7 +20,7 @@ F32, U32 = np.float32, np.uint32
 CASES = {
     "plume_16_probes": ((16, 16, 16), 11, 24, 1, (75.0, 75.0, -75.0)),
     "plume_16_ambient": ((16, 16, 16), 11, 24, 0, (75.0, 75.0, -75.0)),
-    "slab_24x16x8_probes": ((24, 16, 8), 5, 64, 1, (-20.0, 90.0, 35.0)),
+    "slab_24x24x8_probes": ((24, 24, 8), 5, 64, 1, (-20.0, 90.0, 35.0)),
     "dense_12_few_samples": ((12, 12, 12), 7, 5, 1, (0.0, 100.0, 0.0)),
 }
 

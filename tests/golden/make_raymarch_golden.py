@@ -20,7 +20,7 @@ F32, U32 = np.float32, np.uint32
 CASES = {
     "outside_16": ((16, 16, 16), 11, 24, 1, 48, 16, (14.0, 9.0, -27.0), 0),
     "outside_ambient_lod1": ((16, 16, 16), 11, 24, 0, 32, 8, (-30.0, 4.0, 8.0), 0),
-    "inside_24x16x8": ((24, 16, 8), 5, 32, 1, 64, 16, (1.5, -2.0, 3.0), 0),
+    "inside_24x24x8": ((24, 24, 8), 5, 32, 1, 64, 16, (1.5, -2.0, 3.0), 0),
     "culled_faces_few_samples": ((12, 12, 12), 7, 5, 1, 6, 8, (40.0, 40.0, 40.0), 0b001001),
 }
 

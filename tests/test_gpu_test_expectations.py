@@ -1,0 +1,140 @@
+"""The late-added GPU tests (light map, ray marches, volume export, posted stats) run HERE against an oracle-backed
+stand-in for `fluidx12_b200.Fluid`: this checks the tests themselves — their expectations about parity flips, paused
+frames, cube-map persistence, error cases — not the CUDA path, so that a wrong expectation cannot show up for the first
+time on the GPU box.  (The stand-in exists only inside this test; the product has no CPU path.)"""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import fluidx12_b200 as fx
+import oracle
+from fluidx12_b200 import binding as B
+from fluidx12_b200 import volume
+
+
+class OracleBackedFluid:
+    last_error = ""
+
+    def Init(self, gridSize=(128, 128, 128), **kw):
+        self.m_gridSize = tuple(gridSize)
+        self.o = oracle.FluidOracle(*gridSize)
+        self.parity, self.steps, self.dt = 0, 0, 0.0
+        self.lmap = self.cube = None
+        self.posted = {}
+        return True
+
+    def step(self, dt):
+        self.o.step(dt)
+        self.dt, self.steps = dt, self.steps + 1
+        if dt > 0:
+            self.parity ^= 1
+
+    def sync(self):
+        pass
+
+    def close(self):
+        self.o.close()
+
+    def _of(self, fld):
+        return {fx.FIELD_VELOCITY: oracle.FIELD_VEL, fx.FIELD_COLOR: oracle.FIELD_COLOR, fx.FIELD_PRESSURE: oracle.FIELD_PRESSURE}[fld]
+
+    def get_field(self, fld):
+        if fld not in (fx.FIELD_VELOCITY, fx.FIELD_COLOR, fx.FIELD_PRESSURE):
+            raise fx.FluidError(B.FXB_ERR_INVALID, "bad field")
+        return self.o.get_field(self._of(fld))
+
+    def set_field(self, fld, a):
+        self.o.set_field(self._of(fld), a)
+
+    def stats(self):
+        st = fx.FxbStats()
+        st.s_exec, st.frame_parity, st.steps = self.o.s_exec, self.parity, self.steps
+        return st
+
+    def post_stats(self, slot):
+        if not 0 <= slot < 4:
+            raise fx.FluidError(B.FXB_ERR_INVALID, "bad slot")
+        self.posted[slot] = self.stats()
+
+    def wait_stats(self, slot):
+        if slot not in self.posted:
+            raise fx.FluidError(B.FXB_ERR_INVALID, "nothing posted")
+        return self.posted[slot]
+
+    @staticmethod
+    def _cast(p, cls):
+        q = cls()
+        C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+        return q
+
+    def RayMarchL(self, params=None):
+        if self.m_gridSize[2] <= 1:
+            raise fx.FluidError(B.FXB_ERR_INVALID, "3D only")
+        params = params if params is not None else fx.FxbLightParams.reference_defaults()
+        self.lmap = oracle.light_map(self.get_field(fx.FIELD_COLOR), self._cast(params, oracle.LightParams))
+
+    def get_light_map(self):
+        if self.lmap is None:
+            raise fx.FluidError(B.FXB_ERR_INVALID, "not run")
+        return self.lmap
+
+    def _cube(self, size):
+        if self.cube is None or self.cube.shape[1] != size:
+            self.cube = np.zeros((6, size, size, 4), np.uint8)
+        return self.cube
+
+    def RayMarchV(self, v):
+        if self.lmap is None:
+            raise fx.FluidError(B.FXB_ERR_INVALID, "light map first")
+        self.cube = oracle.ray_march_v(self.get_field(fx.FIELD_COLOR), self.lmap, self._cast(v, oracle.ViewParams),
+                                       cube=self._cube(int(v.cube_size)))
+
+    def RayMarch(self, v, light=None):
+        light = light if light is not None else fx.FxbLightParams.reference_defaults()
+        self.cube = oracle.ray_march(self.get_field(fx.FIELD_COLOR), self._cast(v, oracle.ViewParams),
+                                     self._cast(light, oracle.LightParams), cube=self._cube(int(v.cube_size)))
+
+    def get_cube_map(self):
+        return self.cube
+
+    def export(self, path, field=fx.FIELD_COLOR):
+        a = self.get_field(field)
+        volume.write(path, a, field=field, grid=self.m_gridSize, frame=self.steps, dt=self.dt, frame_parity=self.parity)
+
+
+@pytest.fixture()
+def stand_in(monkeypatch):
+    monkeypatch.setattr(fx, "Fluid", OracleBackedFluid)
+    return fx
+
+
+def _functions(module_name):
+    mod = importlib.import_module(module_name)
+    return mod, [getattr(mod, n) for n in dir(mod) if n.startswith("test_")]
+
+
+def test_light_map_gpu_tests_hold_on_the_stand_in(stand_in):
+    mod, _ = _functions("tests.test_zzz_gpu_lightmap")
+    for name in sorted(mod.CASES):
+        mod.test_cuda_light_map_reproduces_the_interpreted_bytecode(name)
+    for probes in (0, 1):
+        mod.test_light_map_of_a_simulated_plume_matches_the_oracle(probes)
+    mod.test_reference_defaults_ragged_grid_and_errors()
+
+
+def test_ray_march_gpu_tests_hold_on_the_stand_in(stand_in):
+    mod, _ = _functions("tests.test_zzz_gpu_raymarch")
+    for name in sorted(mod.CASES):
+        mod.test_cuda_ray_march_reproduces_the_interpreted_bytecode(name)
+    mod.test_cube_map_of_a_simulated_plume_matches_the_oracle()
+
+
+def test_volume_and_posted_stats_gpu_tests_hold_on_the_stand_in(stand_in, tmp_path):
+    mod, _ = _functions("tests.test_zzy_gpu_volume")
+    mod.test_export_of_a_live_field_is_what_get_field_returns(tmp_path)
+    mod, _ = _functions("tests.test_zzw_gpu_posted_stats")
+    mod.test_posted_stats_are_the_synchronous_ones_one_frame_late.__wrapped__(stand_in) if hasattr(
+        mod.test_posted_stats_are_the_synchronous_ones_one_frame_late, "__wrapped__") else \
+        mod.test_posted_stats_are_the_synchronous_ones_one_frame_late(stand_in)

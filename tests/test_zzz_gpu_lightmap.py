@@ -49,10 +49,14 @@ def test_light_map_of_a_simulated_plume_matches_the_oracle(probes):
     assert (col[..., 3].astype(np.float32) >= 0.01).sum() > 1000
     want = oracle.light_map(col, oracle_params(plain))
     assert np.array_equal(got, want), int((got != want).sum())
-    # a paused frame does not flip the parity: the pass still reads the same field
+    # A paused frame does not flip the parity, but its advection still rewrites m_colors[m_frameParity] from the other
+    # buffer (Fluid.cpp:345, 362, 372): the pass must read that buffer's NEW contents, whatever they are.
+    parity = f.stats().frame_parity
     f.step(0.0)
+    assert f.stats().frame_parity == parity
     f.RayMarchL(fx_params(plain))
-    assert np.array_equal(f.get_light_map(), want)
+    col2 = f.get_field(fx.FIELD_COLOR)
+    assert np.array_equal(f.get_light_map(), oracle.light_map(col2, oracle_params(plain)))
     f.close()
 
 
