@@ -26,7 +26,7 @@ def test_cuda_ray_march_reproduces_the_interpreted_bytecode(name):
     golden = np.load(GOLDEN)
     col, plain_l, plain_v = case_inputs(golden, name)
     f = fx.Fluid()
-    assert f.Init(gridSize=CASES[name][0]), f.last_error
+    assert f.Init(gridSize=CASES[name][0], kernel_path=1), f.last_error   # no step is taken: only the colour field is set
     f.set_field(fx.FIELD_COLOR, col)
     f.RayMarchL(as_fx(oracle_params(plain_l), fx.FxbLightParams))
     assert np.array_equal(f.get_light_map(), golden[name + "/light_map"])
@@ -36,7 +36,7 @@ def test_cuda_ray_march_reproduces_the_interpreted_bytecode(name):
     f.close()
     # the non-separated march (CSRayMarch) on a fresh handle: no light map needed, its own golden cube map
     f = fx.Fluid()
-    assert f.Init(gridSize=CASES[name][0]), f.last_error
+    assert f.Init(gridSize=CASES[name][0], kernel_path=1), f.last_error   # no step is taken: only the colour field is set
     f.set_field(fx.FIELD_COLOR, col)
     f.RayMarch(as_fx(view_params(plain_v), fx.FxbViewParams), as_fx(oracle_params(plain_l), fx.FxbLightParams))
     got, want = f.get_cube_map(), golden[name + "/cube_map_full"]
