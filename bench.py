@@ -17,7 +17,7 @@ larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decompos
 roofline-characterisation config) and "c2" (128^3), two further host-timed loops ("e2e_pipelined": one frame in
 flight; "e2e_export": the colour field copied out every step) and "experiments": the opt-in variants of the step, the
 light-map pass and the ray march, timed in a child process with a hard time limit AFTER everything above (--no-experiments
-skips it; use that under ncu).  --grid overrides.  `--impl reference` also steps BASELINE's two small configs in full.
+or FXB_BENCH_EXPERIMENTS=0 skips it; use that under ncu).  --grid overrides.  `--impl reference` also steps BASELINE's two small configs in full.
 """
 from __future__ import annotations
 
