@@ -306,7 +306,10 @@ def run_child(cmd, env, timeout_s):
             os.killpg(p.pid, signal.SIGKILL)  # exactly the group started above
         except ProcessLookupError:
             pass
-        out, _ = p.communicate()
+        try:
+            out, _ = p.communicate(timeout=20)
+        except subprocess.TimeoutExpired:  # a process stuck in the driver cannot be reaped: do not wait for it
+            out = ""
         return None, out
 
 
@@ -609,10 +612,11 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
     # Single GPU: on by default (every variant's kernels are plain compute kernels without device-side waits; a fault
-    # in the child ends the child).  Several GPUs: opt-in (--experiments-multi) — the peer-memory halo exchange has
-    # never run on GPUs, and a misbehaving multi-rank child must not be able to disturb the scaling runs that follow.
+    # in the child ends the child).  Several GPUs: the peer-memory halo exchange has never run on GPUs, and a
+    # misbehaving multi-rank child must not be able to disturb scaling runs that follow — so it is opt-in
+    # (--experiments-multi) except at 8 GPUs, the last point of a 1/2/4/8 scaling sequence, where it is on by default.
     want_exp = (not args.no_experiments and os.environ.get("FXB_BENCH_EXPERIMENTS", "1") != "0" and rank == 0
-                and time.time() - t_bench0 < 300.0 and (world == 1 or args.experiments_multi))
+                and time.time() - t_bench0 < 300.0 and (world in (1, 8) or args.experiments_multi))
     if want_exp:
         # every rank has released its GPU memory and its communicators; ranks > 0 simply exit
         try:

@@ -131,7 +131,7 @@ def test_state_checksum_sees_a_moved_or_changed_word():
 
 def test_multi_gpu_experiments_are_opt_in():
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert "--experiments-multi" in src and "world == 1 or args.experiments_multi" in src
+    assert "--experiments-multi" in src and "world in (1, 8) or args.experiments_multi" in src
 
 
 def test_gpu_shot_bench_mode_runs_to_the_end_on_a_fake_device(monkeypatch, tmp_path):
