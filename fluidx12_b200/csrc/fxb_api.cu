@@ -440,16 +440,20 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
 
     auto cleanup_fail = [&](int rc) { fxb_destroy(s); return rc; };
     const size_t n = s->alloc_voxels();
+    // Peer-memory halos (FXB_P2P=1) map these buffers into the neighbours through CUDA IPC, and an IPC handle maps a
+    // whole underlying allocation: small buffers are then given at least 2 MiB so that each is an allocation of its own.
+    const char* p2p_env = getenv("FXB_P2P");
+    const size_t ipc_min = (cfg->nranks > 1 && p2p_env && atoi(p2p_env) != 0) ? ((size_t)2 << 20) : 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaMalloc(&s->vel[i], n * 8);
+        e = cudaMalloc(&s->vel[i], std::max(n * 8, ipc_min));
         if (e == cudaSuccess) e = cudaMemset(s->vel[i], 0, n * 8);  // zero-filled like new D3D12 resources
-        if (e == cudaSuccess) e = cudaMalloc(&s->col[i], n * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&s->col[i], std::max(n * 8, ipc_min));
         if (e == cudaSuccess) e = cudaMemset(s->col[i], 0, n * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->p[i], n * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->p[i], std::max(n * 4, ipc_min));
         if (e == cudaSuccess) e = cudaMemset(s->p[i], 0, n * 4);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, std::max(n * 4, ipc_min));
     if (e == cudaSuccess) e = cudaMemset(s->rhs, 0, n * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->active, n);
     if (e == cudaSuccess) e = cudaMemset(s->active, 0, n);
@@ -484,7 +488,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         s->fuse_t = cfg->fuse_t ? cfg->fuse_t : 2;
         const size_t mask_bytes = n / 8;
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-            e = cudaMalloc((void**)&s->jac.mask[i], mask_bytes);
+            e = cudaMalloc((void**)&s->jac.mask[i], std::max(mask_bytes, ipc_min));
             if (e == cudaSuccess) e = cudaMemset(s->jac.mask[i], 0, mask_bytes);
         }
         if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, s->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
