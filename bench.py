@@ -1,29 +1,27 @@
 #!/usr/bin/env python
 """bench.py — voxel-updates/s of the smoke-solver step (advect + project) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (one JSON line)
-    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the CPU oracle on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # our CUDA path (one JSON line)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W    # the CPU oracle on the host cores
 
-A "step" is one full frame of the hot path: Fluid::UpdateFrame + Fluid::Simulate (CSAdvect, then
-divergence, <=64 Jacobi sweeps and gradient-subtract of CSProject3D) over the whole grid.
-Workload (BASELINE.json): synthetic emitter-driven smoke from the all-zero state, dt = 2/Ny, MIRROR
-addressing, ITER = 64 with the per-cell early exit.  The state is first spun up for --spinup steps
-(untimed state preparation: at step 0 nothing moves and the solver would be trivially cheap), then
-W warm-up steps, then exactly K timed steps.
+A "step" is one full frame of the hot path: Fluid::UpdateFrame + Fluid::Simulate (CSAdvect, then divergence, <= 64
+Jacobi sweeps and gradient-subtract of CSProject3D) over the whole grid.  Workload (BASELINE.json): synthetic
+emitter-driven smoke from the all-zero state, dt = 2/Ny, MIRROR addressing, ITER = 64 with the per-cell early exit.
+The state is first spun up for --spinup steps (untimed state preparation: at step 0 nothing moves and the solver would
+be trivially cheap), then W warm-up steps, then exactly K timed steps (CUDA events on the launching stream, max over
+ranks).
 
-Grid: N = 1 -> 512^3 (BASELINE config "3D 512^3 ... at 1/2/4/8 B200", 1-GPU point; every field is far
-larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decomposed: 512x512x1024 (2),
-1024x1024x512 (4), 1024^3 (8, BASELINE config 5).  At N = 1 the line also carries "c3" (the 256^3
-roofline-characterisation config) and "c2" (128^3), two further host-timed loops ("e2e_pipelined": one frame in
-flight; "e2e_export": the colour field copied out every step) and "experiments": the opt-in variants of the step, the
-light-map pass and the ray march, timed in a child process with a hard time limit AFTER everything above (--no-experiments
-or FXB_BENCH_EXPERIMENTS=0 skips it; use that under ncu).  --grid overrides.  `--impl reference` also steps BASELINE's two small configs in full.
+Grid: N = 1 -> 512^3 (BASELINE config 4, its 1-GPU point: the largest single-GPU configuration; every field is far
+larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decomposed: 512x512x1024 (2), 1024x1024x512 (4),
+1024^3 (8, BASELINE config 5); `--scaling strong` keeps 512^3 at every N (config 4).  The per-phase device times and
+the roofline come from phase marks INSIDE the timed steps (fxb_get_phase_times).  At N = 1 the line also carries "c3"
+(the 256^3 roofline-characterisation config) and "c2" (128^3) and the CPU baseline; at N > 1 (weak) it carries
+"c4_strong": config 4 on the same N ranks, whose state checksum must equal the N = 1 line's.  --grid overrides.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -34,8 +32,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WEAK_GRIDS = {1: (512, 512, 512), 2: (512, 512, 1024), 4: (1024, 1024, 512), 8: (1024, 1024, 1024)}
+STRONG_GRID = (512, 512, 512)
+CPU_SAMPLE_GRID = (256, 256, 256)  # the same sample at every N and in both arms
 METRIC = "voxel_updates_per_s"
 UNIT = "voxel-updates/s"
+# algorithmic bytes per voxel per launch
+PHASE_BYTES = {"advect": 32.0, "divergence": 12.0, "gradient": 20.0}
+PHASE_KERNEL = {"advect": "advect_kernel", "divergence": "divergence_quad_kernel", "jacobi": "jacobi_pass_kernel",
+                "gradient": "gradient_quad_kernel"}
 
 
 def measured_peak_gbs():
@@ -47,8 +51,8 @@ def measured_peak_gbs():
 
 
 def bytes_per_voxel_step(passes: float, mask_bytes_per_pass: float) -> float:
-    """Algorithmic HBM bytes per voxel per step (SURVEY.md §8d / BASELINE.md §3): advect 32 + divergence 12
-    + per executed Jacobi pass 12 (+ freeze mask) + gradient-subtract 20."""
+    """Nominal HBM bytes per voxel per step (SURVEY.md §8d / BASELINE.md §3): advect 32 + divergence 12
+    + per executed Jacobi pass 12 (+ freeze mask) + gradient-subtract 20 — as if every pass touched every voxel."""
     return 32.0 + 12.0 + passes * (12.0 + mask_bytes_per_pass) + 20.0
 
 
@@ -113,18 +117,22 @@ def make_sim(fx, grid, args, rank, world, local_rank, uid):
     f = fx.Fluid()
     ok = f.Init(gridSize=grid, address_mode=fx.ADDRESS_MIRROR, early_exit=bool(args.early_exit), jacobi_iters=64,
                 fuse_t=args.fuse_t, device=local_rank, rank=rank, nranks=world, use_graph=True,
-                kernel_path=args.kernel_path, nccl_unique_id=uid)
+                kernel_path=args.kernel_path, phase_timing=True,
+                halo_backend=fx.HALO_NCCL if args.halo == "nccl" else fx.HALO_PEER, jacobi_group=args.jacobi_group,
+                nccl_unique_id=uid)
     if not ok:
         raise RuntimeError("fluidx_b200 Init failed: " + f.last_error)
     return f
 
 
 def timed_run(torch, dist, f, dt, steps, warmup, world, stream):
-    """W warm-up + K timed steps, device-timed with CUDA events on the launching stream; max over ranks."""
+    """W warm-up + K timed steps, device-timed with CUDA events on the launching stream; max over ranks.  Also returns
+    the per-phase device times accumulated by the phase marks inside those K steps (ms per step, this rank)."""
     for _ in range(warmup):
         f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
     stream.synchronize()
     st0 = f.stats()
+    f.phase_times(reset=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -143,7 +151,8 @@ def timed_run(torch, dist, f, dt, steps, warmup, world, stream):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     st1 = f.stats()
-    return ms, st0, st1
+    phases = {k: v / max(steps, 1) for k, v in f.phase_times().items()}
+    return ms, st0, st1, phases
 
 
 def e2e_run(torch, dist, f, fx, dt, steps, world, stream, export):
@@ -182,33 +191,6 @@ def e2e_run(torch, dist, f, fx, dt, steps, world, stream, export):
     return sec, 8, stats_bytes + nbytes
 
 
-def e2e_pipelined_run(torch, f, dt, steps, stream):
-    """The frame loop with one frame in flight, as the reference keeps its own (FrameCount = 3, Fluid.h:35): per step the
-    frame constants go in, the step is enqueued, a snapshot of its result record is posted (fxb_post_stats: async copy
-    into pinned memory + event) and the host then waits for the PREVIOUS step's record — every step's record is read,
-    each exactly once, and the device never idles."""
-    cb = torch.zeros(2, dtype=torch.float32).pin_memory()
-    cb[0] = dt
-    torch.cuda.synchronize()
-    read = 0
-    t0 = time.perf_counter()
-    for k in range(steps):
-        f.UpdateFrame(float(cb[0]))
-        f.Simulate(stream.cuda_stream)
-        f.post_stats(k & 1)
-        if k > 0:
-            read += int(f.wait_stats((k - 1) & 1).s_exec >= 0)
-    read += int(f.wait_stats((steps - 1) & 1).s_exec >= 0)
-    torch.cuda.synchronize()
-    sec = time.perf_counter() - t0
-    assert read == steps
-    return sec
-
-
-def voxels_local_of(f):
-    return f.m_gridSize[0] * f.m_gridSize[1] * f.slab[1]
-
-
 def jacobi_work_bytes(st0, st1, mask_bytes, voxels_local):
     """Bytes the Jacobi passes between two stats snapshots really had to move: a relaxed brick reads p + rhs and
     writes p (+ 2/8 B of freeze flags) per cell, a frozen brick is copied once (p in, p out), every other brick is
@@ -220,45 +202,52 @@ def jacobi_work_bytes(st0, st1, mask_bytes, voxels_local):
     return (st1.total_passes - st0.total_passes) * (12.0 + mask_bytes) * voxels_local, 0, 0
 
 
-def phase_rooflines(f, dt, voxels_local, peak, peak_src, reps, mask_bytes):
-    """Per-phase device time measured live with CUDA events between the kernels of un-graphed steps
-    (fxb_profile_step) against each phase's algorithmic bytes.  The Jacobi passes are the dominant
-    kernel: their bytes are counted from the bricks actually relaxed / copied during these very steps."""
-    st0 = f.stats()
-    phases = {}
-    for _ in range(reps):
-        f.UpdateFrame(dt)
-        for k, v in f.profile_step().items():
-            phases[k] = phases.get(k, 0.0) + v / reps
-    st1 = f.stats()
+def ncu_traffic(grid, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this grid (profiles/traffic.json, written by tools/summarize_profiles.py), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get("%dx%dx%d" % tuple(grid), {}).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def rooflines(grid, phases, st0, st1, steps, voxels_local, peak, peak_src):
+    """Per-phase rooflines from the phase marks of the timed steps, and the `roofline` object of the dominant kernel:
+    algorithmic bytes per launch / average launch duration.  Advect, divergence and gradient are one launch per step;
+    the Jacobi phase is `launches` launches of one kernel (its bytes: the bricks those very steps relaxed / copied)."""
+    mask_bytes = 0.25 if st1.jacobi_fused else 2.0
     jb, proc, cop = jacobi_work_bytes(st0, st1, mask_bytes, voxels_local)
-    jb /= reps
-    launches = (st1.total_passes - st0.total_passes) / reps  # one kernel per executed pass
-    per = {"advect": 32.0 * voxels_local, "divergence": 12.0 * voxels_local, "jacobi": jb,
-           "gradient": 20.0 * voxels_local}
-    out = {}
-    for k, nbytes in per.items():
-        gbs = nbytes / max(phases[k] * 1e-3, 1e-12) / 1e9
-        out[k] = {"ms": round(phases[k], 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1),
+    jb /= max(steps, 1)
+    launches = (st1.total_passes - st0.total_passes) / max(steps, 1)
+    nbytes = {k: v * voxels_local for k, v in PHASE_BYTES.items()}
+    nbytes["jacobi"] = jb
+    per = {}
+    for k in ("advect", "divergence", "jacobi", "gradient"):
+        ms = phases.get(k, 0.0)
+        gbs = nbytes[k] / max(ms * 1e-3, 1e-12) / 1e9
+        per[k] = {"ms": round(ms, 4), "algorithmic_bytes": nbytes[k], "achieved_gbs": round(gbs, 1),
                   "frac": round(gbs / peak, 4)}
-    j = out["jacobi"]
-    roof = {"bound": "hbm", "kernel": "jacobi_pass_kernel (average over the executed passes of a step; the one-time "
-                                      "copies of frozen bricks run inside it)",
-            "achieved": j["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": j["frac"], "peak_source": peak_src,
-            "traffic": None, "bytes_per_launch": round(jb / max(launches, 1e-9)),
-            "avg_launch_ms": round(j["ms"] / max(launches, 1e-9), 5), "bytes_per_step": jb, "ms_per_step": j["ms"],
-            "launches_per_step": round(launches, 1),
-            "bricks_relaxed_per_step": round(proc / reps, 1), "bricks_copied_per_step": round(cop / reps, 1),
-            "note": "issue/latency-bound, not HBM-bound: see DESIGN.md §5 and profiles/"}
-    return roof, out, {k: round(v, 4) for k, v in phases.items()}
+    per["jacobi"].update(launches_per_step=round(launches, 1), bricks_relaxed_per_step=round(proc / max(steps, 1), 1),
+                         bricks_copied_per_step=round(cop / max(steps, 1), 1))
+    dom = max(per, key=lambda k: per[k]["ms"])
+    n_launch = launches if dom == "jacobi" else 1.0
+    roof = {"bound": "hbm", "kernel": PHASE_KERNEL[dom], "phase": dom,
+            "achieved": per[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per[dom]["frac"],
+            "peak_source": peak_src, "traffic": ncu_traffic(grid, PHASE_KERNEL[dom]),
+            "bytes_per_launch": round(nbytes[dom] / max(n_launch, 1e-9)),
+            "avg_launch_ms": round(per[dom]["ms"] / max(n_launch, 1e-9), 5), "launches_per_step": round(n_launch, 1),
+            "how": "phase marks inside the timed graph-launched steps (fxb_get_phase_times); bytes of the same steps"}
+    return roof, per, jb, proc, cop
 
 
 def cpu_baseline_sample(f, fx, grid, dt, budget_s=25.0):
     """Times the OpenMP oracle on the host cores on a bounded sample of the same workload: the developed GPU
-    state is copied into the oracle (whole grid when it is small enough, else not run at this size) and
-    stepped for a few frames; the result is also compared with the GPU (full-size parity spot check)."""
+    state is copied into the oracle and stepped for a few frames; the result is also compared with the GPU
+    (full-size parity spot check)."""
     import numpy as np
     import oracle
+    cores = oracle.threads(os.cpu_count() or 1)
     nx, ny, nz = grid
     o = oracle.FluidOracle(nx, ny, nz)
     for gf, of in ((fx.FIELD_VELOCITY, oracle.FIELD_VEL), (fx.FIELD_COLOR, oracle.FIELD_COLOR),
@@ -281,150 +270,69 @@ def cpu_baseline_sample(f, fx, grid, dt, budget_s=25.0):
         if gf == fx.FIELD_VELOCITY:
             a, b = a[..., :3], b[..., :3]
         worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)))
-    cores = os.cpu_count() or 1
     return {"value": nx * ny * nz * n_steps / t_total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d oracle steps of the same %dx%dx%d developed state (OpenMP, %d threads, %.1f s)" %
-                      (n_steps, nx, ny, nz, cores, t_total),
+            "sample": "%d oracle steps of the %dx%dx%d developed state (100 GPU steps from zero), OpenMP, %d threads, "
+                      "%.1f s" % (n_steps, nx, ny, nz, cores, t_total),
             "parity_max_abs_rel_vs_gpu": worst}
 
 
-
-# ------------------------------------------------------------------------------------------------
-# experiments: after the measurement above, the opt-in variants of the same bit-exact step are timed in CHILD
-# processes (own process group, hard time limit), so that every bench run also says what they would do.  Nothing
-# here touches `value` / `e2e` / `roofline`: those were taken before, on the default path.
-# ------------------------------------------------------------------------------------------------
-def run_child(cmd, env, timeout_s):
-    import signal
-    p = subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                         start_new_session=True)
-    try:
-        out, _ = p.communicate(timeout=timeout_s)
-        return p.returncode, out
-    except subprocess.TimeoutExpired:
-        try:
-            os.killpg(p.pid, signal.SIGKILL)  # exactly the group started above
-        except ProcessLookupError:
-            pass
-        try:
-            out, _ = p.communicate(timeout=20)
-        except subprocess.TimeoutExpired:  # a process stuck in the driver cannot be reaped: do not wait for it
-            out = ""
-        return None, out
-
-
-def child_env(extra):
-    drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK",
-            "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT")
-    env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC_")}
-    env.update({k: str(v) for k, v in extra.items()})
-    return env
-
-
-def experiments_single_gpu(budget_s):
-    """tools/gpu_shot.py --bench: 256^3 and 512^3, state copied from a 100-step spin-up of the default schedule into
-    each variant, host-timed graph-launched steps, every field compared bit for bit with the default schedule's."""
-    path = os.path.join(ROOT, "gpurun_out", "bench_experiments.jsonl")
-    os.makedirs(os.path.dirname(path), exist_ok=True)
-    if os.path.exists(path):
-        os.remove(path)
-    t0 = time.time()
-    rc, out = run_child([sys.executable, os.path.join("tools", "gpu_shot.py"), "--bench"],
-                        child_env({"FXB_SHOT_OUT": path}), budget_s)
-    rows = []
-    try:
-        for ln in open(path):
-            r = json.loads(ln)
-            if r.get("stage") == "light_map":
-                r.pop("stage"); r.pop("t", None)
-                r["grid"] = "x".join(map(str, r["grid"]))
-                r["variant"] = "light_map_pass"
-                rows.append(r)
-                continue
-            if r.get("stage") != "timing":
-                continue
-            row = {"grid": "x".join(map(str, r["grid"])), "variant": r.get("variant", "default")}
-            if "error" in r:
-                row["error"] = r["error"][:200]
-            elif "variant" in r:
-                row.update(ms_per_step=r["ms"], jacobi_ms=r["phases"].get("jacobi"), advect_ms=r["phases"].get("advect"),
-                           mismatched_elements_vs_default=sum(r["mismatch_vs_default"].values()),
-                           tail_launches=r["tail"].get("tail_launches_last_step"))
-            else:
-                row.update(ms_per_step=r["default"], jacobi_ms=r["default_phases"].get("jacobi"),
-                           advect_ms=r["default_phases"].get("advect"))
-            rows.append(row)
-    except Exception as e:  # the child wrote nothing usable
-        rows.append({"error": repr(e)[:200]})
-    return {"what": "opt-in variants (environment switches, DESIGN.md §5) timed in a child process after the measurement; "
-                    "host-timed graph launches, same developed state for every variant; not the headline path",
-            "seconds": round(time.time() - t0, 1), "exit": "timeout" if rc is None else rc, "results": rows,
-            "child_tail": out[-400:] if rc not in (0,) else ""}
-
-
-def experiments_multi_gpu(args, world, budget_s):
-    """This same bench (short, without its extras) relaunched under torchrun with the multi-GPU switches; the state
-    checksum of each variant must equal the default variant's (same number of steps from the same zero state)."""
-    port = int(os.environ.get("MASTER_PORT", "29500"))
-    t_end = time.time() + budget_s
-    rows, ref = [], None
-    for i, (label, extra) in enumerate((("default", {}), ("p2p_halos", {"FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 15}),
-                                        ("tail_p2p", {"FXB_TAIL": 1, "FXB_P2P": 1, "FXB_P2P_TIMEOUT_S": 15}),
-                                        ("tail", {"FXB_TAIL": 1}))):
-        left = t_end - time.time()
-        if left < 20:
-            rows.append({"variant": label, "skipped": "time budget"})
-            continue
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-               "--master-addr", "127.0.0.1", "--master-port", str(port + 101 + i), os.path.join(ROOT, "bench.py"),
-               "--gpus", str(world), "--steps", "20", "--warmup", "3", "--no-cpu-baseline", "--no-c3",
-               "--no-experiments", "--checksum"]
-        if args.grid:
-            cmd += ["--grid"] + [str(v) for v in args.grid]
-        rc, out = run_child(cmd, child_env(extra), min(left, 90.0))
-        row = {"variant": label}
-        got = None
-        for ln in out.splitlines():
-            if "{" in ln and '"metric"' in ln:  # torchrun may prefix a worker's output
-                try:
-                    got = json.loads(ln[ln.index("{"):])
-                except Exception:
-                    pass
-        if got is None:
-            row.update(error="timeout" if rc is None else "exit %s" % rc, child_tail=out[-300:])
-        else:
-            row.update(ms_per_step=round(got["ms_per_step"], 4), value=got["value"],
-                       halo_ms=got.get("phase_ms", {}).get("halo"), jacobi_ms=got.get("phase_ms", {}).get("jacobi"))
-            if label == "default":
-                ref = got.get("state_checksum")
-            row["state_equals_default_variant"] = (got.get("state_checksum") == ref) if ref is not None else None
-        rows.append(row)
-    return {"what": "multi-GPU opt-in variants (DESIGN.md §6): this bench relaunched in child torchrun jobs, 20 steps, "
-                    "after the measurement; not the headline path", "results": rows}
-
-
-def state_checksum(torch, dist, f, fx, world):
-    """Order-sensitive 62-bit checksum of the rank's velocity.xyz, colour and pressure words, summed over ranks."""
-    import numpy as np
-    z0 = f.slab[0]
-    total = 0
-    for k, fld in enumerate((fx.FIELD_VELOCITY, fx.FIELD_COLOR, fx.FIELD_PRESSURE)):
-        a = f.get_field(fld)
-        w = a.view(np.uint16) if a.dtype == np.float16 else a.view(np.uint32)
-        if fld == fx.FIELD_VELOCITY:
-            w = w[..., :3]
-        per_plane = np.add.reduce(w.reshape(w.shape[0], -1), axis=1, dtype=np.uint64)
-        for j, v in enumerate(per_plane.tolist()):
-            total = (total + (k + 1) * (z0 + j + 1) * (v % (1 << 40))) % (1 << 62)
+def global_checksum(torch, dist, f, world):
+    """Decomposition-independent checksum of the state: per field the sum over ranks (mod 2^64) of fxb_state_checksum."""
+    words = list(f.state_checksum())
     if world > 1:
-        t = torch.tensor([total >> 31, total & ((1 << 31) - 1)], device="cuda", dtype=torch.int64)
+        # 64-bit wrap-around sums do not fit a signed all-reduce: add 16-bit limbs, then recombine mod 2^64
+        limbs = [(w >> (16 * i)) & 0xffff for w in words for i in range(4)]
+        t = torch.tensor(limbs, device="cuda", dtype=torch.int64)
         dist.all_reduce(t)
-        total = ((int(t[0].item()) << 31) + int(t[1].item())) % (1 << 62)
-    return total
+        limbs = [int(v) for v in t.tolist()]
+        words = [sum(limbs[4 * k + i] << (16 * i) for i in range(4)) & ((1 << 64) - 1) for k in range(3)]
+    return "%016x-%016x-%016x" % tuple(words)
+
+
+def measure_config(torch, dist, fx, args, grid, rank, world, local_rank, uid, stream, peak, peak_src, sampler=None):
+    """Spin-up + warm-up + timed steps of one grid; returns (sim, record)."""
+    nx, ny, nz = grid
+    voxels = nx * ny * nz
+    dt = fx.dt_for_grid(*grid)
+    f = make_sim(fx, grid, args, rank, world, local_rank, uid)
+    for _ in range(args.spinup):
+        f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
+    stream.synchronize()
+    if sampler is not None:
+        sampler.start()
+    ms, st0, st1, phases = timed_run(torch, dist, f, dt, args.steps, args.warmup, world, stream)
+    checksum = global_checksum(torch, dist, f, world)  # state after spinup + warmup + steps frames from zero
+    if st1.halo_overflow:
+        raise SystemExit("advection back-trace left the z-halo: raise h_adv")
+    voxels_local = nx * ny * f.slab[1]
+    roof, per, jb, proc, cop = rooflines(grid, phases, st0, st1, args.steps, voxels_local, peak, peak_src)
+    if world > 1:
+        t = torch.tensor([jb, proc, cop], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        jb, proc, cop = (float(v) for v in t.tolist())
+    passes = (st1.total_passes - st0.total_passes) / max(args.steps, 1)
+    sweeps = (st1.total_sweeps - st0.total_sweeps) / max(args.steps, 1)
+    t_step = ms * 1e-3 / args.steps
+    work_bytes = 64.0 * voxels + jb
+    nominal_bpv = bytes_per_voxel_step(passes, 0.25 if st1.jacobi_fused else 2.0)
+    rec = {"value": voxels * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps, "state_checksum": checksum,
+           "frames_from_zero": args.spinup + args.warmup + args.steps,
+           "fuse_t": int(st1.fuse_t), "sweeps_per_step": round(sweeps, 2), "jacobi_passes_per_step": round(passes, 2),
+           "bytes_per_voxel_step": round(work_bytes / voxels, 2), "jacobi_fused": int(st1.jacobi_fused),
+           "bricks_relaxed_per_step": round(proc / args.steps, 1), "bricks_copied_per_step": round(cop / args.steps, 1),
+           "brick_cells": int(st1.brick_cells), "kernels_per_step": int(st1.kernels_per_step),
+           "step_roofline": {"bound": "hbm", "achieved": round(work_bytes / t_step / 1e9, 1), "peak": peak * world,
+                             "unit": "GB/s", "frac": round(work_bytes / t_step / 1e9 / (peak * world), 4),
+                             "peak_source": peak_src,
+                             "definition": "(64 B x voxels + Jacobi bytes of the bricks actually relaxed/copied) / t_step",
+                             "nominal_formula_frac": round(nominal_bpv * voxels / t_step / 1e9 / (peak * world), 4),
+                             "nominal_note": "BASELINE.md formula 32+12+ceil(S/T)*12+20 assumes every pass touches "
+                                             "every voxel; frozen bricks are skipped here, so it over-counts"},
+           "roofline": roof, "phase_roofline": per, "phase_ms": {k: round(v, 4) for k, v in phases.items()}}
+    return f, rec
 
 
 def run_ours(args):
-    t_bench0 = time.time()
     import torch
     import torch.distributed as dist
     import fluidx12_b200 as fx
@@ -451,7 +359,8 @@ def run_ours(args):
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
 
-    grid = tuple(args.grid) if args.grid else WEAK_GRIDS.get(world)
+    strong = args.scaling == "strong"
+    grid = tuple(args.grid) if args.grid else (STRONG_GRID if strong else WEAK_GRIDS.get(world))
     if grid is None:
         raise SystemExit("--gpus must be 1, 2, 4 or 8 (or pass --grid)")
     nx, ny, nz = grid
@@ -460,15 +369,8 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     stream = torch.cuda.Stream()
 
-    f = make_sim(fx, grid, args, rank, world, local_rank, uid)
-    for _ in range(args.spinup):
-        f.UpdateFrame(dt); f.Simulate(stream.cuda_stream)
-    stream.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms, st0, st1 = timed_run(torch, dist, f, dt, args.steps, args.warmup, world, stream)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    f, rec = measure_config(torch, dist, fx, args, grid, rank, world, local_rank, uid, stream, peak, peak_src, sampler)
     if rank == 0 and world == 1:
         # a very short timed region can end before nvidia-smi has answered once: keep the same load running
         # (untimed) until a few samples exist
@@ -481,149 +383,68 @@ def run_ours(args):
 
     sec_e2e, h2d, d2h = e2e_run(torch, dist, f, fx, dt, args.steps, world, stream, export=False)
 
-    passes = (st1.total_passes - st0.total_passes) / max(args.steps, 1)
-    sweeps = (st1.total_sweeps - st0.total_sweeps) / max(args.steps, 1)
-    fuse_t = st1.fuse_t
-    mask_bytes = 0.25 if st1.jacobi_fused else 2.0
-    voxels_local = nx * ny * f.slab[1]
-    value = voxels * args.steps / (ms * 1e-3)
-    t_step = ms * 1e-3 / args.steps
-    # bytes the step really needs (whole job): advect 32 + divergence 12 + gradient 20 per voxel + the Jacobi work
-    jb, proc, cop = jacobi_work_bytes(st0, st1, mask_bytes, voxels_local)
-    if world > 1:
-        t = torch.tensor([jb, proc, cop], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        jb, proc, cop = (float(v) for v in t.tolist())
-    work_bytes = 64.0 * voxels + jb / args.steps
-    work_gbs = work_bytes / t_step / 1e9
-    nominal_bpv = bytes_per_voxel_step(passes, mask_bytes)
-    nominal_gbs = nominal_bpv * voxels / t_step / 1e9
-
-    roof, phase_roof, phases = phase_rooflines(f, dt, voxels_local, peak, peak_src, 5, mask_bytes)
-    # `traffic` stays null: the ncu capture in profiles/ is of pass 0 alone (every brick relaxed), while `achieved`
-    # averages over all passes of a step; the capture is quoted next to it instead.
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roof["ncu_pass0_capture"] = json.load(open(prof)).get("%dx%dx%d" % grid, {}).get("jacobi")
-        except Exception:
-            pass
-    if st1.halo_overflow:
-        raise SystemExit("advection back-trace left the z-halo: raise h_adv")
-
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "3D %dx%dx%d emitter-driven smoke, dt=2/Ny, MIRROR, ITER=64%s, spun up %d steps from "
                                "the zero state; fields (%.0f MiB) far larger than L2, no L2 flush needed" %
                                (nx, ny, nz, " with per-cell early exit" if args.early_exit else ", early exit OFF",
                                 args.spinup, voxels * 44 / 2 ** 20),
-                   "grid": list(grid), "parallelism": "z-slab x%d" % world, "fuse_t": fuse_t,
-                   "sweeps_per_step": round(sweeps, 2), "jacobi_passes_per_step": round(passes, 2),
-                   "bytes_per_voxel_step": round(work_bytes / voxels, 2), "kernel_path": args.kernel_path,
-                   "jacobi_fused": int(st1.jacobi_fused), "bricks_relaxed_per_step": round(proc / args.steps, 1),
-                   "bricks_copied_per_step": round(cop / args.steps, 1), "brick_cells": int(st1.brick_cells),
-                   # opt-in variants of the same bit-exact step that were switched on through the environment
+                   "grid": list(grid), "parallelism": "z-slab x%d" % world,
+                   "halo_backend": (args.halo if world > 1 else None), "jacobi_group": args.jacobi_group,
+                   "kernel_path": args.kernel_path,
+                   **{k: rec[k] for k in ("fuse_t", "sweeps_per_step", "jacobi_passes_per_step", "bytes_per_voxel_step",
+                                          "jacobi_fused", "bricks_relaxed_per_step", "bricks_copied_per_step",
+                                          "brick_cells")},
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("FXB_")}},
-        "step_roofline": {"bound": "hbm", "achieved": round(work_gbs, 1), "peak": peak * world, "unit": "GB/s",
-                          "frac": round(work_gbs / (peak * world), 4), "peak_source": peak_src,
-                          "definition": "(64 B x voxels + Jacobi bytes of the bricks actually relaxed/copied) / t_step",
-                          "nominal_bytes_step_formula": {
-                              "bytes_per_voxel": round(nominal_bpv, 2), "achieved": round(nominal_gbs, 1),
-                              "frac": round(nominal_gbs / (peak * world), 4),
-                              "note": "BASELINE.md formula 32+12+ceil(S/T)*12+20: assumes every pass touches every "
-                                      "voxel; frozen bricks are skipped here, so it over-counts the bytes moved"}},
-        "roofline": roof,
-        "phase_roofline": phase_roof,
-        "phase_ms": phases,
+        "state_checksum": rec["state_checksum"], "frames_from_zero": rec["frames_from_zero"],
+        "step_roofline": rec["step_roofline"], "roofline": rec["roofline"], "phase_roofline": rec["phase_roofline"],
+        "phase_ms": rec["phase_ms"],
         "e2e": {"value": voxels * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_e2e / args.steps,
                 "what": "UpdateFrame(dt from pinned CB) + Simulate + fxb_get_stats readback, host-timed"},
-        "gpu_launches": st1.kernels_per_step * args.steps,
+        "gpu_launches": rec["kernels_per_step"] * args.steps,
         "clocks": clocks,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # CPU baseline on a bounded sample: the 256^3 (or smaller) version of the same workload.
-        cgrid = grid if voxels <= 256 ** 3 else (256, 256, 256)
+        # CPU baseline on a bounded sample: the 256^3 version of the same workload, developed on the GPU
+        cgrid = CPU_SAMPLE_GRID
         g = make_sim(fx, cgrid, args, 0, 1, local_rank, None) if cgrid != grid else f
         cdt = fx.dt_for_grid(*cgrid)
         if g is not f:
-            for _ in range(args.spinup):
+            for _ in range(100):
                 g.step(cdt)
         line["cpu_baseline"] = cpu_baseline_sample(g, fx, cgrid, cdt)
         if g is not f:
             g.close()
+    if args.export_e2e and world == 1:
+        # the e2e loop with the renderer hand-off inside it: the colour field copied to pinned host memory every step
+        k = min(args.steps, 20)
+        sec_exp, _, d2h_exp = e2e_run(torch, dist, f, fx, dt, k, world, stream, export=True)
+        line["e2e_export"] = {"value": voxels * k / sec_exp, "unit": UNIT, "d2h_bytes_per_step": d2h_exp,
+                              "what": "as e2e plus the colour field copied to pinned host memory every step"}
+    f.close()
     # BASELINE configs[2] (256^3: the roofline-characterisation config) and configs[1] (128^3, the reference's default
     # grid, FluidX12.cpp:44) on the same GPU, same method as the main workload
     for key, cn, label in (("c3", 256, "3D 256^3 (BASELINE config 3: roofline characterisation)"),
                            ("c2", 128, "3D 128^3 (BASELINE config 2: the reference's default grid; fits in L2)")):
-        if not (rank == 0 and world == 1 and not args.no_c3 and grid != (cn, cn, cn)):
+        if not (world == 1 and not args.no_c3 and grid != (cn, cn, cn)):
             continue
-        g = make_sim(fx, (cn, cn, cn), args, 0, 1, local_rank, None)
-        cdt = fx.dt_for_grid(cn, cn, cn)
-        for _ in range(args.spinup):
-            g.UpdateFrame(cdt); g.Simulate(stream.cuda_stream)
-        cms, c0, c1 = timed_run(torch, dist, g, cdt, args.steps, args.warmup, 1, stream)
-        cv = cn ** 3
-        cjb, cproc, ccop = jacobi_work_bytes(c0, c1, mask_bytes, cv)
-        cwork = 64.0 * cv + cjb / args.steps
-        cnom = bytes_per_voxel_step((c1.total_passes - c0.total_passes) / args.steps, mask_bytes)
-        croof, cphase_roof, cph = phase_rooflines(g, cdt, cv, peak, peak_src, 5, mask_bytes)
-        ct = cms * 1e-3 / args.steps
-        line[key] = {"workload": label,
-                     "value": cv * args.steps / (cms * 1e-3), "ms_per_step": cms / args.steps,
-                     "jacobi_passes_per_step": round((c1.total_passes - c0.total_passes) / args.steps, 2),
-                     "sweeps_per_step": round((c1.total_sweeps - c0.total_sweeps) / args.steps, 2),
-                     "bytes_per_voxel_step": round(cwork / cv, 2),
-                     "step_roofline_frac": round(cwork / ct / 1e9 / peak, 4),
-                     "nominal_formula_frac": round(cnom * cv / ct / 1e9 / peak, 4),
-                     "roofline": croof, "phase_roofline": cphase_roof, "phase_ms": cph}
+        g, crec = measure_config(torch, dist, fx, args, (cn, cn, cn), 0, 1, local_rank, None, stream, peak, peak_src)
         g.close()
-    if not args.no_export_e2e and world == 1:
-        # extras, after everything the contract needs has been measured.  First the e2e loop with the renderer
-        # hand-off inside it: the colour field copied to pinned host memory every step
-        try:
-            k = min(args.steps, 20)
-            sec_exp, _, d2h_exp = e2e_run(torch, dist, f, fx, dt, k, world, stream, export=True)
-            line["e2e_export"] = {"value": voxels * k / sec_exp, "unit": UNIT, "d2h_bytes_per_step": d2h_exp,
-                                  "what": "as e2e plus the colour field copied to pinned host memory every step"}
-        except Exception as e:
-            line["e2e_export"] = {"error": repr(e)[:200]}
-    if world == 1:
-        # then the frame loop with one frame in flight
-        try:
-            import ctypes as C
-            sec_pipe = e2e_pipelined_run(torch, f, dt, args.steps, stream)
-            line["e2e_pipelined"] = {"value": voxels * args.steps / sec_pipe, "unit": UNIT, "h2d_bytes_per_step": 8,
-                                     "d2h_bytes_per_step": C.sizeof(fx.FxbStats), "ms_per_step": 1e3 * sec_pipe / args.steps,
-                                     "what": "as e2e, but the host waits for the PREVIOUS step's result record (posted "
-                                             "asynchronously into pinned memory) while the current step runs: one "
-                                             "frame in flight, every record still read every step"}
-        except Exception as e:  # an extra: the line is complete without it
-            line["e2e_pipelined"] = {"error": repr(e)[:200]}
-    if args.checksum:
-        line["state_checksum"] = state_checksum(torch, dist, f, fx, world)
-    try:
-        f.close()
-    except Exception:
-        pass
+        crec["workload"] = label
+        line[key] = crec
+    # config 4 (512^3 strong scaling) on the same N ranks: its checksum must equal the N = 1 line's state_checksum
+    if world > 1 and not strong and not args.grid and not args.no_c4:
+        g, crec = measure_config(torch, dist, fx, args, STRONG_GRID, rank, world, local_rank, uid, stream, peak, peak_src)
+        g.close()
+        crec["workload"] = "3D 512^3 (BASELINE config 4) strong-scaled on %d ranks" % world
+        line["c4_strong"] = {k: crec[k] for k in ("workload", "value", "ms_per_step", "state_checksum",
+                                                  "frames_from_zero", "phase_ms", "sweeps_per_step")}
     if world > 1:
         dist.destroy_process_group()
-    # Single GPU: on by default (every variant's kernels are plain compute kernels without device-side waits; a fault
-    # in the child ends the child).  Several GPUs: the peer-memory halo exchange has never run on GPUs, and a
-    # misbehaving multi-rank child must not be able to disturb scaling runs that follow — so it is opt-in
-    # (--experiments-multi) except at 8 GPUs, the last point of a 1/2/4/8 scaling sequence, where it is on by default.
-    want_exp = (not args.no_experiments and os.environ.get("FXB_BENCH_EXPERIMENTS", "1") != "0" and rank == 0
-                and time.time() - t_bench0 < 300.0 and (world in (1, 8) or args.experiments_multi))
-    if want_exp:
-        # every rank has released its GPU memory and its communicators; ranks > 0 simply exit
-        try:
-            line["experiments"] = (experiments_single_gpu(args.experiments_budget) if world == 1 else
-                                   experiments_multi_gpu(args, world, 2.0 * args.experiments_budget))
-        except Exception as e:
-            line["experiments"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(line, default=str), flush=True)
 
@@ -637,26 +458,12 @@ def run_reference(args):
         return
     import oracle
     oracle.build()
-    cores = os.cpu_count() or 1
-    total = args.steps + args.warmup
-    # Bounded sample: the same emitter-driven workload on the largest cubic grid whose K+W steps fit ~150 s.
-    probe = oracle.FluidOracle(64, 64, 64)
-    pdt = oracle.dt_for_grid(64, 64, 64)
-    for _ in range(20):
-        probe.step(pdt)
-    t0 = time.perf_counter()
-    for _ in range(5):
-        probe.step(pdt)
-    per_voxel_step = (time.perf_counter() - t0) / 5 / 64 ** 3
-    n = 64
-    for cand in (512, 384, 256, 192, 128, 96):
-        spin = min(args.spinup, 100)
-        if per_voxel_step * cand ** 3 * (total + spin) * 1.5 <= 150.0:
-            n = cand
-            break
+    # torch.distributed.run exports OMP_NUM_THREADS=1: ask for every host core explicitly and report what we got
+    cores = oracle.threads(os.cpu_count() or 1)
+    n = CPU_SAMPLE_GRID[0]
+    spin = 100
     o = oracle.FluidOracle(n, n, n)
     dt = oracle.dt_for_grid(n, n, n)
-    spin = min(args.spinup, 100)
     for _ in range(spin + args.warmup):
         o.step(dt)
     t0 = time.perf_counter()
@@ -682,12 +489,14 @@ def run_reference(args):
             oc.close()
         except Exception as e:
             small[key] = {"error": repr(e)[:200]}
-    grid = tuple(args.grid) if args.grid else WEAK_GRIDS.get(world, WEAK_GRIDS[1])
+    strong = args.scaling == "strong"
+    grid = tuple(args.grid) if args.grid else (STRONG_GRID if strong else WEAK_GRIDS.get(world, WEAK_GRIDS[1]))
     sample = ("OpenMP C++ restatement of the reference HLSL (the reference needs Windows/D3D12 and cannot run "
-              "here), %d threads, %d^3 sample of the workload, spun up %d steps" % (cores, n, spin))
+              "here), %d threads (omp_get_max_threads), %d^3 sample of the workload, spun up %d steps" % (cores, n, spin))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "3D %dx%dx%d emitter-driven smoke (timed on a %d^3 sample), dt=2/Ny, MIRROR, ITER=64 "
                                "with per-cell early exit" % (grid + (n,)), "grid": list(grid),
@@ -705,19 +514,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 134 M voxels per GPU (default); strong = 512^3 at every N (BASELINE config 4)")
     ap.add_argument("--spinup", type=int, default=100)
     ap.add_argument("--fuse-t", type=int, default=0)
     ap.add_argument("--early-exit", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
-    ap.add_argument("--no-export-e2e", action="store_true", help="skip the e2e variant that also copies the colour field out")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange backend")
+    ap.add_argument("--jacobi-group", type=int, default=0, help="N > 1: fused passes per pressure-halo exchange (0 = default)")
+    ap.add_argument("--export-e2e", action="store_true", help="also time the e2e variant that copies the colour field out")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
-    ap.add_argument("--no-experiments", action="store_true",
-                    help="skip the child-process runs of the opt-in variants after the measurement (use under ncu)")
-    ap.add_argument("--experiments-multi", action="store_true",
-                    help="N > 1: also relaunch this bench with the multi-GPU switches (peer-memory halos, dynamic schedule)")
-    ap.add_argument("--experiments-budget", type=float, default=75.0, help="seconds (twice that for N > 1)")
-    ap.add_argument("--checksum", action="store_true", help="add a checksum of the final state to the line")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 512^3 strong-scaling sub-run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

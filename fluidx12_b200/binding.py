@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libfluidx_b200.so"
 
 ADDRESS_MIRROR, ADDRESS_CLAMP = 0, 1
+HALO_PEER, HALO_NCCL = 0, 1
 FIELD_VELOCITY, FIELD_COLOR, FIELD_PRESSURE, FIELD_VELOCITY_ADVECTED, FIELD_COLOR_PREV = range(5)
 
 FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_OVERFLOW, FXB_ERR_IO = 0, -1, -2, -3, -4, -5, -6
@@ -16,7 +17,7 @@ FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_
 EXPORTS = (
     "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
-    "fxb_post_stats", "fxb_wait_stats", "fxb_get_tail_stats", "fxb_plan_pressure_solve", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+    "fxb_post_stats", "fxb_wait_stats", "fxb_p2p_plan", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_get_phase_times", "fxb_state_checksum", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
     "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
     "fxb_light_map", "fxb_get_light_map", "fxb_cube_visibility_mask", "fxb_estimate_cube_lod", "fxb_ray_march_v", "fxb_ray_march", "fxb_get_cube_map",
 )
@@ -41,6 +42,9 @@ class FxbConfig(C.Structure):
         ("h_adv", C.c_int32),
         ("use_graph", C.c_int32),
         ("kernel_path", C.c_int32),
+        ("phase_timing", C.c_int32),
+        ("halo_backend", C.c_int32),
+        ("jacobi_group", C.c_int32),
         ("nccl_unique_id", C.c_void_p),
     ]
 
@@ -142,12 +146,12 @@ def lib() -> C.CDLL:
         L.fxb_get_stats.argtypes = [vp, C.POINTER(FxbStats)]
         L.fxb_post_stats.argtypes = [vp, C.c_int]
         L.fxb_wait_stats.argtypes = [vp, C.c_int, C.POINTER(FxbStats)]
-        L.fxb_get_tail_stats.argtypes = [vp, vp, C.c_int]
-        L.fxb_plan_pressure_solve.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32]
         L.fxb_p2p_plan.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int64)]
         L.fxb_emitter_box.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
         L.fxb_get_freeze_histogram.argtypes = [vp, vp, C.c_int]
         L.fxb_profile_step.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+        L.fxb_state_checksum.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.fxb_get_phase_times.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int]
         L.fxb_nccl_unique_id.argtypes = [vp]
         L.fxb_volume_write.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader), vp]
         L.fxb_volume_read_header.argtypes = [C.c_char_p, C.POINTER(FxbVolumeHeader)]

@@ -16,6 +16,8 @@ namespace fxb {
 // index lz holds global plane z = z_first + lz.  Single GPU: z_first = 0, nz_alloc = nz.
 struct Domain {
     int nx, ny, nz;      // global grid
+    int pitch;           // voxels per row in memory (>= nx, a multiple of 8 on the tuned path): row y of plane lz starts
+                         // at element (lz * ny + y) * pitch of every field
     int z_first;         // global z of local plane 0 (may be negative: halo below the global face)
     int nz_alloc;        // planes allocated locally (owned + halos)
     int z_own0, z_own1;  // owned global planes [z_own0, z_own1)
@@ -40,15 +42,19 @@ struct StepState {
     unsigned long long bricks_processed;  // cumulative: bricks fully relaxed by fused passes
     unsigned long long bricks_copied;     // cumulative: frozen bricks copied once to the other buffer
     unsigned long long active_after[128];  // [k] = cells still active after sweep k (this rank)
-    // dynamic schedule (bulk passes + tail launches, jacobi_tail.cu); reset by begin_step_kernel
-    int seq;                             // relax kernels executed so far in this frame (= pressure ping-pong flips)
-    int sweeps_done;                     // sweeps completed so far in this frame
-    int done_ctas;                       // CTAs of the running relax kernel that have finished
-    int tail_launches;                   // tail launches that did work in the last step
-    unsigned long long tail_bricks;      // cumulative: bricks relaxed by tail launches (TT sweeps each)
-    unsigned long long tail_subblocks_relaxed;  // cumulative: sub-blocks that held an active cell (the rest are copies)
-    unsigned long long tail_subblocks_dense;    // cumulative: ... of which took the dense (register-column) path
+    unsigned long long phase_ns[8];      // cumulative device time per phase (phase marks; fxb_config.phase_timing)
+    unsigned long long mark_ns;          // %globaltimer of the last phase mark
 };
+
+// Phase marks: the device time since the previous mark is added to StepState::phase_ns[slot] (slot < 0: start of a
+// step).  The step's own one-thread kernels (frame constants, begin-step, finish-solve) carry three of the five marks;
+// with fxb_config.phase_timing two more one-thread kernels close the divergence and the gradient phase.
+__device__ __forceinline__ void phase_mark(StepState* state, int slot) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (slot >= 0) state->phase_ns[slot] += now - state->mark_ns;
+    state->mark_ns = now;
+}
 
 // Static emitter table (Impulse.hlsli:14-18 is time-independent): basis values of the voxels in a
 // conservative bounding box of the sphere basis >= exp(-4).  Computed on the host at fxb_create

@@ -25,9 +25,10 @@ thread_local std::string g_last_error;
 
 int fail(int code, const std::string& msg) { return fxb::api_fail(code, msg); }
 
-__global__ void set_frame_kernel(fxb::FrameParams* frame, float dt, int parity) {
+__global__ void set_frame_kernel(fxb::FrameParams* frame, fxb::StepState* state, float dt, int parity) {
     frame->dt = dt;
     frame->parity = parity;
+    fxb::phase_mark(state, -1);  // a step starts here
 }
 
 }  // namespace
@@ -113,120 +114,113 @@ int build_axis_tables(fxb_sim* s) {
     return FXB_OK;
 }
 
-// Static launch sequence of the dynamic pressure-solve schedule.  Entry k >= 0: bulk pass with
-// static index k (runs iff exactly k*T sweeps are done); kTailIfFew: tail launch that runs iff few enough bricks are
-// listed; kTailAlways: tail launch that runs whatever the list length.  Bulk pass 0 comes first; then groups of one
-// conditional tail launch and the TT/T bulk passes that cover the same sweeps, up to bulk pass mains-1; then as many
-// unconditional tail launches as the worst case (no conditional tail launch ever ran: mains*T sweeps done) needs.
-// Every group advances the solve by at least its bulk passes' sweeps, and a tail launch that ran once keeps
-// qualifying (the brick list only shrinks), so the sequence always reaches `iters` sweeps unless the solve ends early.
-enum { kTailIfFew = -1, kTailAlways = -2 };
-std::vector<int> plan_pressure_solve(int iters, int T, int TT, int mains) {
-    std::vector<int> plan;
-    if (iters <= 0 || T <= 0 || TT <= 0) return plan;
-    const int npass = (iters + T - 1) / T;
-    mains = std::min(std::max(mains, 1), npass);
-    plan.push_back(0);
-    for (int k = 1; k < mains;) {
-        plan.push_back(kTailIfFew);
-        for (int j = 0; j < std::max(TT / T, 1) && k < mains; ++j, ++k) plan.push_back(k);
-    }
-    for (int done = mains * T; done < iters; done += TT) plan.push_back(kTailAlways);
-    return plan;
-}
-
 // Pressure ping-pong flips of one (dt > 0) step as the HOST must know them (multi-GPU: they select the buffers whose
-// halos are exchanged): every launch of the plan flips once there, because every rank runs every launch.
+// halos are exchanged): every rank runs every pass, and every pass flips once.
 int flips_per_step(const fxb_sim* s) {
     if (!s->fused) return 0;
-    if (s->tail) return (int)plan_pressure_solve(s->cfg.jacobi_iters, s->fuse_t, fxb::jacobi_tail_sweeps(), 1).size();
     return (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
 }
 
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 
-void fork_colour(fxb_sim* s, cudaStream_t st);
+// Phase marks (common.cuh): with fxb_config.phase_timing a one-thread kernel closes the divergence and the gradient
+// phase (the other marks ride on the step's own one-thread kernels), so the per-phase device times of the very steps a
+// caller times are available afterwards (fxb_get_phase_times) — also when the step runs as a captured graph.
+__global__ void phase_mark_kernel(fxb::StepState* state, int slot) { fxb::phase_mark(state, slot); }
 
-// Enqueues one phase of the step; returns the number of kernels launched.
-int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
-    const fxb::Domain& d = s->dom;
+// State checksum (fxb_state_checksum): per field the wrap-around sum over the rank's own voxels of a 64-bit mix of the
+// voxel's GLOBAL linear index and its bits, so the sums of all ranks of a z-slab run add up to the single-GPU value.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) checksum_kernel(fxb::Domain d, const uint2* __restrict__ vel,
+                                                       const uint2* __restrict__ col, const float* __restrict__ p,
+                                                       unsigned long long* __restrict__ out) {
+    const size_t n = (size_t)d.nx * d.ny * (d.z_own1 - d.z_own0);
+    unsigned long long a = 0, b = 0, c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % d.nx), y = (int)((i / d.nx) % d.ny), lz = (int)(i / ((size_t)d.nx * d.ny));
+        const size_t at = ((size_t)(d.z_own0 - d.z_first + lz) * d.ny + y) * d.pitch + x;
+        const unsigned long long g = ((unsigned long long)(d.z_own0 + lz) * d.ny + y) * d.nx + x;
+        const uint2 v = vel[at], k = col[at];
+        a += mix64(g * 3 + 0 + (((unsigned long long)(v.y & 0xffffu) << 32 | v.x) << 20));  // velocity .w is a don't-care
+        b += mix64(g * 3 + 1 + (((unsigned long long)k.y << 32 | k.x) << 20) + (unsigned long long)(k.y >> 12));
+        c += mix64(g * 3 + 2 + ((unsigned long long)__float_as_uint(p[at]) << 24));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c += __shfl_down_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], a);
+        atomicAdd(&out[1], b);
+        atomicAdd(&out[2], c);
+    }
+}
+
+struct Enqueue {
+    fxb_sim* s;
+    cudaStream_t st;
     int launches = 0;
+    bool ok = true;
+    std::string err;
+    void halo(const fxb::HaloField* f, int n) {
+        if (ok && !s->comm.exchange(s->dom, f, n, st)) { ok = false; err = "halo exchange: " + fxb::halo_last_error(); }
+        if (s->comm.p2p.enabled) ++launches;
+    }
+    void launched(cudaError_t e, const char* what, int n = 1) {
+        if (ok && e != cudaSuccess) { ok = false; err = std::string(what) + ": " + cudaGetErrorString(e); }
+        launches += n;
+    }
+    void mark(int slot) {
+        if (!s->cfg.phase_timing) return;
+        phase_mark_kernel<<<1, 1, 0, st>>>(s->d_state, slot);
+        launched(cudaGetLastError(), "phase_mark_kernel");
+    }
+};
+
+// Enqueues one phase of the step.
+void enqueue_phase(Enqueue& q, int phase) {
+    fxb_sim* s = q.s;
+    cudaStream_t st = q.st;
+    const fxb::Domain& d = s->dom;
     switch (phase) {
         case PH_ADVECT:
             if (s->multi()) {  // back-trace reach + 1 tap of the inputs
                 const fxb::HaloField f[2] = {{s->vel[0], s->plane_voxels() * 8, s->h_adv + 1},
                                              {s->col[!s->parity], s->plane_voxels() * 8, s->h_adv + 1}};
-                s->comm.exchange(d, f, 2, st);
+                q.halo(f, 2);
             }
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
             fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
-                               s->d_state, s->advect2 ? 3 | 4 : 3, st);
-            launches = 1;
+                               s->d_state, s->h_adv, st);
+            fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);  // also the advection phase's mark
+            q.launched(cudaGetLastError(), "advect_kernel", 2);
             break;
         case PH_DIVERGENCE:
             if (s->multi() && s->dt > 0.0f) {  // z neighbours of the advected velocity
                 const fxb::HaloField f[1] = {{s->vel[1], s->plane_voxels() * 8, 1}};
-                s->comm.exchange(d, f, 1, st);
+                q.halo(f, 1);
             }
-            fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);
             if (s->quad) fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, st);
             else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
-            launches = 2;
+            q.launched(cudaGetLastError(), "divergence_kernel");
+            q.mark(1);
             break;
         case PH_JACOBI:
-            if (s->fused && s->tail) {
-                // Dynamic schedule: which kernel relaxes is decided on the device (jacobi_tail.cu).  A group is one
-                // tail launch (TT sweeps) followed by the TT/T bulk passes that cover the same sweeps; the tail
-                // launch of a group runs iff few enough bricks are listed, the bulk passes run iff it did not.
-                const int iters = s->cfg.jacobi_iters, TT = fxb::jacobi_tail_sweeps();
-                cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
-                // Multi-GPU (experimental): every rank runs every launch of the plan (tail_mains is forced to 1 and the
-                // tail launches are unconditional), so the position in the relax sequence — hence the ping-pong side and
-                // the mask buffer whose halo must be exchanged — is the launch index on every rank.
-                const bool mg = s->multi() && s->dt > 0.0f;
-                int seq = 0;
-                for (const int kind : plan_pressure_solve(iters, s->fuse_t, TT, s->multi() ? 1 : s->tail_mains)) {
-                    if (mg) {
-                        // before launch 0: the pass input pressure and, in the same exchange, the right-hand side
-                        // (constant over the sweeps: once per step, deep enough for a tail launch); before every later
-                        // launch: its input pressure and freeze mask
-                        const int depth = kind >= 0 ? s->fuse_t : TT;
-                        const fxb::HaloField p_halo = {s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, depth};
-                        const fxb::HaloField second =
-                            seq == 0 ? fxb::HaloField{s->rhs, s->plane_voxels() * 4, std::max(TT, s->fuse_t)}
-                                     : fxb::HaloField{s->jac.mask[seq & 1], s->plane_voxels() / 8, depth};
-                        const fxb::HaloField f[2] = {p_halo, second};
-                        s->comm.exchange(d, f, 2, st);
-                    }
-                    if (kind == 0 && s->pass0_tail && s->fuse_t == 2)
-                        fxb::launch_jacobi_pass0_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit, st);
-                    else if (kind >= 0)
-                        fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, kind, iters, s->cfg.early_exit,
-                                                      s->multi(), 0, 0, st);
-                    else
-                        fxb::launch_jacobi_tail(s->jac, d, s->d_frame, s->d_state, iters, s->cfg.early_exit,
-                                                kind == kTailIfFew && !s->multi() ? s->jac.tail_threshold : -1, s->multi(),
-                                                st);
-                    ++launches;
-                    ++seq;
-                }
-                if (mg) s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st);  // global s_exec (as below)
-                fxb::launch_finish_solve_dynamic(s->d_frame, s->d_state, iters, st);
-                ++launches;
-                if (mg) {  // z neighbours of the final pressure for the gradient
-                    const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + seq) & 1], s->plane_voxels() * 4, 1}};
-                    s->comm.exchange(d, f, 1, st);
-                }
-            } else if (s->fused) {
+            if (s->fused) {
                 const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
-                cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st);
+                if (cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st) != cudaSuccess)
+                    q.launched(cudaGetLastError(), "cudaMemsetAsync(work_count)", 0);
                 const bool mg = s->multi() && s->dt > 0.0f;
                 // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
                 // between, pass j of a group also relaxes the (G-1-j)*T halo planes next to each interior face.
                 const int G = s->multi() ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
                 if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the group
                     const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * s->fuse_t}};
-                    s->comm.exchange(d, f, 1, st);
+                    q.halo(f, 1);
                 }
                 for (int k = 0; k < npass; ++k) {
                     int ext_lo = 0, ext_hi = 0;
@@ -235,34 +229,37 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                             const fxb::HaloField f[2] = {
                                 {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * s->fuse_t},
                                 {s->jac.mask[k & 1], s->plane_voxels() / 8, G * s->fuse_t}};
-                            s->comm.exchange(d, f, k == 0 ? 1 : 2, st);
+                            q.halo(f, k == 0 ? 1 : 2);
                         }
                         const int ext = (G - 1 - k % G) * s->fuse_t;
                         ext_lo = s->cfg.rank > 0 ? ext : 0;
                         ext_hi = s->cfg.rank < s->cfg.nranks - 1 ? ext : 0;
                     }
-                    fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
-                                                  s->cfg.early_exit, s->multi(), ext_lo, ext_hi, st);
-                    if (s->fork_colour_now && (k == 1 || k == npass - 1)) fork_colour(s, st);
+                    q.launched(fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
+                                                             s->cfg.early_exit, s->multi(), ext_lo, ext_hi, st),
+                               "jacobi_pass_kernel");
                 }
                 if (mg) {
                     // freeze counters are per rank: sum them so that s_exec is the global figure; every rank runs
                     // all passes (a pass without active cells only copies), so the buffer parity stays in step
-                    s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st);
+                    if (q.ok && !s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st)) {
+                        q.ok = false;
+                        q.err = "all-reduce of the freeze counters: " + fxb::halo_last_error();
+                    }
                 }
                 fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t,
                                          s->multi() ? npass : -1, st);
+                q.launched(cudaGetLastError(), "finish_solve_kernel");
                 if (mg) {  // z neighbours of the final pressure for the gradient
                     const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + npass) & 1], s->plane_voxels() * 4, 1}};
-                    s->comm.exchange(d, f, 1, st);
+                    q.halo(f, 1);
                 }
-                launches = npass + 1;  // npass fused passes + finish
             } else {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
                                                     s->cfg.early_exit, st);
                 fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, -1, st);
-                launches = s->cfg.jacobi_iters + 1;
+                q.launched(cudaGetLastError(), "jacobi_sweep_simple_kernel", s->cfg.jacobi_iters + 1);
             }
             break;
         case PH_GRADIENT:
@@ -271,54 +268,35 @@ int enqueue_phase(fxb_sim* s, int phase, cudaStream_t st) {
                 fxb::launch_gradient_quad(d, s->tab, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
             else
                 fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
-            launches = 1;
+            q.launched(cudaGetLastError(), "gradient_kernel");
+            q.mark(3);
             break;
     }
-    return launches;
 }
 
-void fork_colour(fxb_sim* s, cudaStream_t st) {
-    cudaEventRecord(s->ev_fork, st);
-    cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-    fxb::launch_advect(s->dom, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
-                       s->d_state, 2, s->side_stream);
-    cudaEventRecord(s->ev_join, s->side_stream);
-    s->fork_colour_now = false;
-}
-
-// The whole step.  The colour field is not an input of the projection (CSProject3D reads velocity and pressure
-// only), so its advection runs on a side stream — a parallel branch of the captured graph — under the divergence and
-// the latency-bound Jacobi passes, and is joined before the gradient kernel overwrites vel[0] (its back-trace input).
-int enqueue_step(fxb_sim* s, cudaStream_t st) {
-    if (!s->overlap_colour) {
-        int launches = 0;
-        for (int ph = 0; ph < PH_COUNT; ++ph) launches += enqueue_phase(s, ph, st);
-        return launches;
-    }
-    const fxb::Domain& d = s->dom;
-    if (s->multi()) {  // both halo exchanges stay on the main stream: one NCCL communicator, one order on every rank
-        const fxb::HaloField f[2] = {{s->vel[0], s->plane_voxels() * 8, s->h_adv + 1},
-                                     {s->col[!s->parity], s->plane_voxels() * 8, s->h_adv + 1}};
-        s->comm.exchange(d, f, 2, st);
-    }
-    fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode, s->d_state,
-                       1, st);
-    int launches = 2;
-    launches += enqueue_phase(s, PH_DIVERGENCE, st);
-    s->fork_colour_now = true;  // PH_JACOBI forks the colour branch after its second pass (the heavy ones are over)
-    launches += enqueue_phase(s, PH_JACOBI, st);
-    if (s->fork_colour_now) fork_colour(s, st);  // no fused passes on this grid: fork here
-    cudaStreamWaitEvent(st, s->ev_join, 0);
-    launches += enqueue_phase(s, PH_GRADIENT, st);
-    return launches;
+// The whole step: advect -> divergence -> Jacobi passes -> gradient-subtract, with a phase mark after each.
+// Returns FXB_OK or the first failure (NCCL or launch); `launches` receives the number of kernels enqueued.
+int enqueue_step(fxb_sim* s, cudaStream_t st, int* launches) {
+    Enqueue q{s, st};
+    for (int ph = 0; ph < PH_COUNT && q.ok; ++ph) enqueue_phase(q, ph);
+    if (launches) *launches = q.launches;
+    if (!q.ok) return fail(s->multi() && q.err.compare(0, 4, "halo") == 0 ? FXB_ERR_NCCL : FXB_ERR_CUDA, "fxb_simulate: " + q.err);
+    return FXB_OK;
 }
 
 // Captures the step for the current (frame parity, pressure parity) key; single GPU always uses key [0][0].
 int capture_graph(fxb_sim* s, int a, int b) {
     FXB_CUDA(cudaStreamBeginCapture(s->own_stream, cudaStreamCaptureModeThreadLocal));
-    const int launches = enqueue_step(s, s->own_stream);
-    cudaError_t e = cudaStreamEndCapture(s->own_stream, &s->graph[a][b]);
+    int launches = 0;
+    const int rc = enqueue_step(s, s->own_stream, &launches);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->own_stream, &g);  // always end the capture, also after a failure
+    if (rc != FXB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
     if (e != cudaSuccess) return fail(FXB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    s->graph[a][b] = g;
     FXB_CUDA(cudaGraphInstantiate(&s->graph_exec[a][b], s->graph[a][b], 0));
     s->kernels_per_step = launches + 1;  // + set_frame_kernel
     return FXB_OK;
@@ -370,6 +348,9 @@ int fxb_config_default(fxb_config* cfg) {
     cfg->h_adv = 0;
     cfg->use_graph = 1;
     cfg->kernel_path = 0;
+    cfg->phase_timing = 0;
+    cfg->halo_backend = FXB_HALO_PEER;
+    cfg->jacobi_group = 0;
     cfg->nccl_unique_id = nullptr;
     return FXB_OK;
 }
@@ -417,14 +398,15 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     s->dom.nx = (int)cfg->nx; s->dom.ny = (int)cfg->ny; s->dom.nz = (int)cfg->nz;
     s->dom.z_first = 0; s->dom.nz_alloc = (int)cfg->nz;
     s->dom.z_own0 = 0; s->dom.z_own1 = (int)cfg->nz;
+    s->dom.pitch = (int)cfg->nx;
     s->fuse_t = 1;
     if (cfg->nranks > 1) {
         // z-slab decomposition (fluidx12_b200/slab.py states the same rules): rank r owns planes
         // [r*nz/R, (r+1)*nz/R); interior faces carry `halo` extra planes, the grid's own faces none
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
         const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
-        s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 12;  // 2|u_z| voxels; |u_z| stayed below 3 in every run so far
-        if (const char* e = getenv("FXB_JACOBI_GROUP")) s->jacobi_group = std::max(1, atoi(e));
+        s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;  // 2|u_z| voxels; |u_z| stayed below 3 in every run
+        s->jacobi_group = cfg->jacobi_group > 0 ? cfg->jacobi_group : 1;
         s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
         int thinnest = nz;
         for (int q = 0; q < R; ++q) thinnest = std::min(thinnest, (q + 1) * nz / R - q * nz / R);
@@ -442,8 +424,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     const size_t n = s->alloc_voxels();
     // Peer-memory halos (FXB_P2P=1) map these buffers into the neighbours through CUDA IPC, and an IPC handle maps a
     // whole underlying allocation: small buffers are then given at least 2 MiB so that each is an allocation of its own.
-    const char* p2p_env = getenv("FXB_P2P");
-    const size_t ipc_min = (cfg->nranks > 1 && p2p_env && atoi(p2p_env) != 0) ? ((size_t)2 << 20) : 0;
+    const bool peer_halos = cfg->nranks > 1 && cfg->halo_backend == FXB_HALO_PEER;
+    const size_t ipc_min = peer_halos ? ((size_t)2 << 20) : 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaMalloc(&s->vel[i], std::max(n * 8, ipc_min));
@@ -461,15 +443,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (e == cudaSuccess) e = cudaMemset(s->d_frame, 0, sizeof(fxb::FrameParams));
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_state, sizeof(fxb::StepState));
     if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, sizeof(fxb::StepState));
-    int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    // the latency-critical chain (Jacobi passes) outranks the colour branch that fills the idle SMs
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->own_stream, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, prio_lo);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
-    if (getenv("FXB_OVERLAP_COLOUR")) s->overlap_colour = true;
-    if (const char* v = getenv("FXB_ADVECT")) s->advect2 = atoi(v) == 2;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess)
         return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));
@@ -493,51 +467,20 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         }
         if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, s->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
             return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
-        const size_t nb = fxb::fused_jacobi_bricks(s->jac);
         const size_t nc = 3 * (fxb::FusedJacobi::kMaxPasses + 1);
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i)
-            e = cudaMalloc((void**)&s->jac.work_list[i], 2 * nb * sizeof(int));
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaMalloc((void**)&s->jac.work_list[i], 2 * (size_t)s->jac.list_stride * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemset(s->jac.work_list[i], 0, 2 * (size_t)s->jac.list_stride * sizeof(int));
+        }
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.work_count, nc * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(s->jac.work_count, 0, nc * sizeof(int));
         if (e != cudaSuccess)
             return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
         s->fused = true;
-        const char* tail_env = getenv("FXB_TAIL");
-        // multi-GPU: needs a pressure/mask halo as deep as a tail launch and the per-pass exchange (no grouping)
-        const bool tail_ok_multi = !s->multi() || (s->halo >= fxb::jacobi_tail_sweeps() && s->jacobi_group == 1);
-        if (tail_env && atoi(tail_env) != 0 && tail_ok_multi && s->jac.variant == 0 &&
-            fxb::jacobi_tail_supported(s->jac, s->dom)) {
-            e = cudaMalloc((void**)&s->jac.brick_state, nb * sizeof(int));
-            if (e == cudaSuccess) e = cudaMemset(s->jac.brick_state, 0, nb * sizeof(int));
-            if (e != cudaSuccess)
-                return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: ") + cudaGetErrorString(e)));
-            s->jac.dynamic = true;
-            s->jac.tail_threshold = 1024;  // bricks; above it the z-marching bulk kernel is the better tool (estimate)
-            s->jac.tail_grid = s->jac.num_sms * 8;
-            if (const char* v = getenv("FXB_TAIL_THRESHOLD")) s->jac.tail_threshold = atoi(v);
-            if (const char* v = getenv("FXB_TAIL_GRID")) s->jac.tail_grid = std::max(1, atoi(v));
-            if (const char* v = getenv("FXB_TAIL_MAINS")) s->tail_mains = std::max(1, atoi(v));
-            if (const char* v = getenv("FXB_TAIL_SPARSE_CAP")) s->jac.tail_sparse_cap = atoi(v);
-            if (const char* v = getenv("FXB_TAIL_DENSE")) s->jac.tail_dense_mode = atoi(v);
-            if (const char* v = getenv("FXB_PASS0")) s->pass0_tail = atoi(v) == 2;
-            if (const char* v = getenv("FXB_TAIL_CPASYNC")) s->jac.tail_cp_async = atoi(v);  // 0 registers, 1 cp.async, 2 TMA
-            if (s->jac.tail_cp_async == 2 && !fxb::jacobi_tail_make_window_maps(&s->jac, s->dom))
-                return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed (tail window)"));
-            s->tail = true;
-        }
     }
-    if (s->cfg.use_graph && !s->multi()) {
-        rc = capture_graph(s, 0, 0);
-        if (rc != FXB_OK) return cleanup_fail(rc);
-    } else {
-        int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
-        if (s->tail)
-            jl = (int)plan_pressure_solve(s->cfg.jacobi_iters, s->fuse_t, fxb::jacobi_tail_sweeps(), s->tail_mains).size();
-        s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1;
-    }
-    if (s->multi() && getenv("FXB_P2P") && atoi(getenv("FXB_P2P")) != 0) {
-        // Experimental: halos through peer memory (CUDA IPC + one store/flag kernel per exchange) instead of NCCL
-        // send/recv; the all-reduce of the freeze counters stays on NCCL.
+    if (peer_halos) {
+        // Halos through peer memory (CUDA IPC + one store/flag kernel per exchange) instead of NCCL send/recv; the
+        // all-reduce of the freeze counters stays on NCCL.
         std::vector<void*> bufs = {s->vel[0], s->vel[1], s->col[0], s->col[1], (void*)s->p[0], (void*)s->p[1], (void*)s->rhs};
         if (s->fused) { bufs.push_back(s->jac.mask[0]); bufs.push_back(s->jac.mask[1]); }
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
@@ -545,6 +488,13 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         const int zf_hi = r < R - 1 ? std::max((r + 1) * nz / R - s->halo, 0) : 0;
         if (!s->comm.p2p_init(bufs.data(), (int)bufs.size(), zf_lo, zf_hi, s->own_stream))
             return cleanup_fail(fail(FXB_ERR_NCCL, "fxb_create: peer-memory halo setup failed: " + fxb::halo_last_error()));
+    }
+    if (s->cfg.use_graph && !s->multi()) {
+        rc = capture_graph(s, 0, 0);
+        if (rc != FXB_OK) return cleanup_fail(rc);
+    } else {
+        const int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
+        s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1 + (s->cfg.phase_timing ? 2 : 0);
     }
     if (s->multi()) {
         // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
@@ -583,7 +533,6 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.work_list[0]);
     cudaFree(s->jac.work_list[1]);
     cudaFree(s->jac.work_count);
-    cudaFree(s->jac.brick_state);
     cudaFree(s->light_map);
     cudaFree(s->cube_map);
     if (s->stats_ring) cudaFreeHost(s->stats_ring);
@@ -599,9 +548,6 @@ void fxb_destroy(fxb_sim* s) {
     for (int i = 0; i < 8; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
-    if (s->side_stream) cudaStreamDestroy(s->side_stream);
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_join) cudaEventDestroy(s->ev_join);
     delete s;
 }
 
@@ -616,7 +562,7 @@ int fxb_simulate(fxb_sim* s, void* cuda_stream) {
     if (!s) return fail(FXB_ERR_INVALID, "fxb_simulate: null handle");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     FXB_CUDA(cudaSetDevice(s->cfg.device));
-    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
     const int npass = flips_per_step(s);
     if (s->multi()) {
         // the exchanges depend on dt > 0, the frame parity and the pressure parity: one graph per key, captured on
@@ -629,15 +575,15 @@ int fxb_simulate(fxb_sim* s, void* cuda_stream) {
             }
             FXB_CUDA(cudaGraphLaunch(s->graph_exec[a][b], st));
         } else {
-            enqueue_step(s, st);
-            FXB_CUDA(cudaGetLastError());
+            const int rc = enqueue_step(s, st, nullptr);
+            if (rc != FXB_OK) return rc;
         }
         if (s->dt > 0.0f) s->p_cur_host = (s->p_cur_host + npass) & 1;
     } else if (s->graph_exec[0][0]) {
         FXB_CUDA(cudaGraphLaunch(s->graph_exec[0][0], st));
     } else {
-        enqueue_step(s, st);
-        FXB_CUDA(cudaGetLastError());
+        const int rc = enqueue_step(s, st, nullptr);
+        if (rc != FXB_OK) return rc;
     }
     s->last_stream = st;
     ++s->steps;
@@ -761,26 +707,6 @@ int fxb_wait_stats(fxb_sim* s, int slot, fxb_stats* out) {
     return st.halo_overflow ? fail(FXB_ERR_HALO_OVERFLOW, "advection back-trace left the z-halo") : FXB_OK;
 }
 
-int fxb_get_tail_stats(fxb_sim* s, uint64_t* out, int n) {
-    if (!s || !out || n < 0 || n > 16) return fail(FXB_ERR_INVALID, "fxb_get_tail_stats: bad argument");
-    FXB_CUDA(cudaSetDevice(s->cfg.device));
-    fxb::StepState st;
-    FXB_CUDA(cudaMemcpyAsync(&st, s->d_state, sizeof(st), cudaMemcpyDeviceToHost, s->last_stream));
-    FXB_CUDA(cudaStreamSynchronize(s->last_stream));
-    const uint64_t v[5] = {s->tail ? 1ull : 0ull, (uint64_t)st.tail_launches, st.tail_bricks, st.tail_subblocks_relaxed,
-                           st.tail_subblocks_dense};
-    for (int i = 0; i < n; ++i) out[i] = i < 5 ? v[i] : 0;
-    return FXB_OK;
-}
-
-int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_t* kinds, int32_t capacity) {
-    if (iters < 0 || iters > 128 || fuse_t < 1 || fuse_t > 4 || !kinds || capacity < 0)
-        return fail(FXB_ERR_INVALID, "fxb_plan_pressure_solve: bad argument");
-    const std::vector<int> plan = plan_pressure_solve(iters, fuse_t, fxb::jacobi_tail_sweeps(), mains);
-    for (size_t i = 0; i < plan.size() && (int)i < capacity; ++i) kinds[i] = plan[i];
-    return (int)plan.size();
-}
-
 int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t depth, int64_t* out4) {
     if (!out4 || nz < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > nz || halo < 0 || depth < 1)
         return fail(FXB_ERR_INVALID, "fxb_p2p_plan: bad argument");
@@ -817,13 +743,15 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     cudaStream_t st = s->own_stream;
     FXB_CUDA(cudaDeviceSynchronize());
-    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->dt, s->parity);
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity);
     FXB_CUDA(cudaEventRecord(s->ev[0], st));
+    Enqueue q{s, st};
     for (int ph = 0; ph < PH_COUNT; ++ph) {
-        enqueue_phase(s, ph, st);
+        enqueue_phase(q, ph);
         FXB_CUDA(cudaEventRecord(s->ev[ph + 1], st));
     }
     FXB_CUDA(cudaStreamSynchronize(st));
+    if (!q.ok) return fail(FXB_ERR_CUDA, "fxb_profile_step: " + q.err);
     FXB_CUDA(cudaGetLastError());
     for (int ph = 0; ph < PH_COUNT; ++ph) FXB_CUDA(cudaEventElapsedTime(&ms[ph], s->ev[ph], s->ev[ph + 1]));
     ms[4] = 0.0f;
@@ -831,6 +759,39 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     if (s->multi() && s->fused && s->dt > 0.0f) s->p_cur_host = (s->p_cur_host + flips_per_step(s)) & 1;
     s->last_stream = st;
     ++s->steps;
+    return FXB_OK;
+}
+
+int fxb_state_checksum(fxb_sim* s, uint64_t* out3) {
+    if (!s || !out3) return fail(FXB_ERR_INVALID, "fxb_state_checksum: null argument");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    int p_cur = 0;
+    FXB_CUDA(cudaMemcpy(&p_cur, &s->d_state->p_cur, sizeof(int), cudaMemcpyDeviceToHost));
+    unsigned long long* d_out = nullptr;
+    FXB_CUDA(cudaMalloc((void**)&d_out, 3 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d_out, 0, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        checksum_kernel<<<1184, 256>>>(s->dom, (const uint2*)s->vel[0], (const uint2*)s->col[s->parity], s->p[p_cur & 1], d_out);
+        e = cudaGetLastError();
+    }
+    unsigned long long h[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(FXB_ERR_CUDA, std::string("fxb_state_checksum: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 3; ++i) out3[i] = h[i];
+    return FXB_OK;
+}
+
+int fxb_get_phase_times(fxb_sim* s, double* ms, int n, int reset) {
+    if (!s || !ms || n < 4) return fail(FXB_ERR_INVALID, "fxb_get_phase_times: need ms[4]");
+    if (!s->cfg.phase_timing) return fail(FXB_ERR_INVALID, "fxb_get_phase_times: the handle was created without phase_timing");
+    FXB_CUDA(cudaSetDevice(s->cfg.device));
+    FXB_CUDA(cudaDeviceSynchronize());
+    unsigned long long ns[8];
+    FXB_CUDA(cudaMemcpy(ns, s->d_state->phase_ns, sizeof(ns), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) ms[i] = (double)ns[i] * 1e-6;
+    if (reset) FXB_CUDA(cudaMemset(s->d_state->phase_ns, 0, sizeof(ns)));
     return FXB_OK;
 }
 

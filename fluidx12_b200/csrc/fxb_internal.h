@@ -49,10 +49,6 @@ struct fxb_sim {
     fxb::StepState* d_state = nullptr;
 
     cudaStream_t own_stream = nullptr;
-    cudaStream_t side_stream = nullptr;  // colour advection branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool overlap_colour = false;  // measured slower on B200 (profiles/README.md); FXB_OVERLAP_COLOUR=1 enables it
-    bool fork_colour_now = false;  // set by enqueue_step: the Jacobi phase should fork the colour branch
     cudaStream_t last_stream = nullptr;
     // One captured graph per (frame parity, pressure-buffer parity): both select pointers that the halo exchange
     // of the multi-GPU step needs on the host side.  Single GPU uses slot [0][0] only (its kernels select on device).
@@ -61,14 +57,8 @@ struct fxb_sim {
     fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
     int halo = 0;             // halo planes allocated on interior faces
     int h_adv = 0;            // advection halo (back-trace reach in planes)
-    int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (FXB_JACOBI_GROUP; > 1 is experimental)
+    int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (fxb_config.jacobi_group)
     int p_cur_host = 0;       // host mirror of StepState::p_cur (multi-GPU: the pass count per step is fixed)
-    // Dynamic schedule (FXB_TAIL=1, single GPU; experimental until measured on B200 — DESIGN.md §5): bulk passes
-    // 0..tail_mains-1 interleaved with tail launches (jacobi_tail.cu), then tail launches only.
-    bool tail = false;
-    int tail_mains = 8;
-    bool advect2 = false;     // FXB_ADVECT=2: second advection kernel (advect_body.cuh; experimental)
-    bool pass0_tail = false;  // FXB_PASS0=2 (with FXB_TAIL=1, T = 2): pass 0 by the block-resident kernel (experimental)
     unsigned* light_map = nullptr;         // m_lightMap (Fluid.h), R11G11B10_FLOAT words; allocated by fxb_light_map
     unsigned* cube_map = nullptr;          // one mip of m_cubeMap (Fluid.cpp:229-232): [6][S][S] RGBA8 words
     uint32_t cube_size = 0;

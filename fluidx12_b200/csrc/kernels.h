@@ -9,7 +9,7 @@ namespace fxb {
 
 // advect.cu
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
-                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int what,
+                   void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int h_adv,
                    cudaStream_t stream);
 
 // lightmap.cu — the light-map pass after the step (CSRayMarchL); consts = fxb_light_params
@@ -47,52 +47,27 @@ void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FramePar
 // jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
 struct FusedJacobi {
     int T = 0;                 // sweeps fused per pass (1..4)
-    int variant = 0;           // kernel shape (rows per thread, warps, TMA depth); see jacobi_fused.cu
-    int tile_y = 32;           // rows of the xy tile
+    bool narrow = false;       // tile 64 x 32 (a warp covers two row pairs) instead of 128 x 16
+    int tile_x = 128, tile_y = 16;
     int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
     float* p[2] = {nullptr, nullptr};
     float* rhs = nullptr;
     unsigned char* mask[2] = {nullptr, nullptr};  // bit-packed freeze flags, ping-pong by pass parity
-    int* work_list[2] = {nullptr, nullptr};       // [2 * bricks] per pass parity: bricks to relax, then bricks to copy
+    int* work_list[2] = {nullptr, nullptr};       // [2 * list_stride] per pass parity: bricks to relax, then bricks to copy
+    int list_stride = 0;                          // entries per list (bricks + padding for the kernel's look-ahead)
     int* work_count = nullptr;                    // [3][kMaxPasses + 1]: relax count and copy count per pass (+ spare)
     int num_sms = 0;
-    // Dynamic schedule (FXB_TAIL=1, single GPU): bulk passes and tail launches share the relax sequence through
-    // StepState::seq / sweeps_done; see jacobi_tail.cu.
-    bool dynamic = false;
-    int* brick_state = nullptr;                   // [bricks] sub-block arrivals of the tail kernel; zero between launches
-    int tail_threshold = 0;                       // a tail launch takes over once at most this many bricks are listed
-    int tail_grid = 0;                            // CTAs of a tail launch
-    int tail_cp_async = 0;                        // 1 (FXB_TAIL_CPASYNC=1): the sparse path stages its window with cp.async;
-                                                  // not yet run on a GPU, hence off by default
-    int tail_dense_mode = 1;                      // crowded windows: 1 = register z-columns (ran on B200), 2 = two-phase quads
-    int tail_sparse_cap = -1;                     // active cells per window up to which the sparse path is taken (-1: capacity)
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
-    alignas(64) unsigned char map_win[2][128];    // tail kernel, TMA staging (FXB_TAIL_CPASYNC=2): its window box on p[0] / p[1]
-    bool win_maps = false;
 };
 bool fused_jacobi_supported(const Domain& d);
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);
-bool fused_make_box_map(void* map128, float* base, int nx, int ny, int nz_alloc, int box_x, int box_y, int box_z);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
                                      cudaStream_t stream);
-
-// jacobi_tail.cu — TT = 4 sweeps per launch on sub-blocks kept on chip, for the tail of the solve in which few bricks
-// are still active (dynamic schedule only).  threshold < 0: run whatever the list length.
-bool jacobi_tail_supported(const FusedJacobi& J, const Domain& d);
-int jacobi_tail_sweeps();
-bool jacobi_tail_make_window_maps(FusedJacobi* J, const Domain& d);  // for FXB_TAIL_CPASYNC=2
-// run_all (multi-GPU): the launch runs and flips the ping-pong even when this rank has nothing left to relax.
-cudaError_t launch_jacobi_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                               int iters, int early_exit, int threshold, bool run_all, cudaStream_t stream);
-// Experimental (FXB_PASS0=2, dynamic schedule only): pass 0 of the frame by the block-resident kernel.
-cudaError_t launch_jacobi_pass0_tail(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                     int iters, int early_exit, cudaStream_t stream);
-void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 
 }  // namespace fxb

@@ -45,7 +45,7 @@ __global__ void begin_step_kernel(const FrameParams* __restrict__ frame, StepSta
     if (k < iters && k < 128) state->active_after[k] = 0ull;
     if (k == 0) {
         state->s_exec = 0; state->passes = 0;
-        state->seq = 0; state->sweeps_done = 0; state->done_ctas = 0; state->tail_launches = 0;
+        phase_mark(state, 0);  // the advection phase ends here
     }
 }
 
@@ -129,28 +129,7 @@ __global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepS
     state->p_cur = (state->p_cur + passes) & 1;
     state->total_sweeps += (unsigned long long)s;
     state->total_passes += (unsigned long long)passes;
-}
-
-// Dynamic schedule (jacobi_tail.cu): the relax kernels counted their own ping-pong flips in StepState::seq.
-__global__ void __launch_bounds__(128) finish_solve_dynamic_kernel(const FrameParams* __restrict__ frame,
-                                                                   StepState* __restrict__ state, int iters) {
-    // s_exec = 1 + the number of leading non-zero entries of active_after[0 .. iters-2]; one thread per entry instead
-    // of finish_solve_kernel's serial walk (a dependent global load per sweep, ~10 us per step)
-    __shared__ int first_zero;
-    const int k = threadIdx.x;
-    if (k == 0) first_zero = 127;
-    __syncthreads();
-    if (k >= iters - 1 || state->active_after[k] == 0ull) atomicMin(&first_zero, k);
-    __syncthreads();
-    if (k != 0) return;
-    const bool live = 0.0f < frame->dt && iters > 0;
-    const int s = live ? min(first_zero + 1, iters) : 0;
-    const int flips = live ? state->seq : 0;
-    state->s_exec = s;
-    state->passes = flips;
-    state->p_cur = (state->p_cur + flips) & 1;
-    state->total_sweeps += (unsigned long long)s;
-    state->total_passes += (unsigned long long)flips;
+    phase_mark(state, 2);  // the pressure solve ends here
 }
 
 __global__ void __launch_bounds__(256) gradient_kernel(Domain d, const FrameParams* __restrict__ frame,
@@ -220,10 +199,6 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
 void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int sweeps_per_flip, int force_passes,
                          cudaStream_t stream) {
     finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, sweeps_per_flip, force_passes);
-}
-
-void launch_finish_solve_dynamic(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream) {
-    finish_solve_dynamic_kernel<<<1, 128, 0, stream>>>(frame, state, iters);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,

@@ -31,7 +31,9 @@ class Fluid:
              rtFormat=None, dsFormat=None, gridSize: Sequence[int] = (128, 128, 128), *,
              address_mode: int = B.ADDRESS_MIRROR, early_exit: bool = True, jacobi_iters: int = 64,
              fuse_t: int = 0, device: int = 0, rank: int = 0, nranks: int = 1, h_adv: int = 0,
-             use_graph: bool = True, kernel_path: int = 0, nccl_unique_id: Optional[bytes] = None) -> bool:
+             use_graph: bool = True, kernel_path: int = 0, phase_timing: bool = False,
+             halo_backend: int = B.HALO_PEER, jacobi_group: int = 0,
+             nccl_unique_id: Optional[bytes] = None) -> bool:
         """Returns False on failure like the reference (XUSG_N_RETURN); ``last_error`` says why."""
         L = B.lib()
         if self._h:
@@ -48,6 +50,9 @@ class Fluid:
         cfg.h_adv = h_adv
         cfg.use_graph = int(use_graph)
         cfg.kernel_path = kernel_path
+        cfg.phase_timing = int(phase_timing)
+        cfg.halo_backend = halo_backend
+        cfg.jacobi_group = jacobi_group
         self._uid_buf = None
         if nccl_unique_id is not None:
             self._uid_buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
@@ -194,19 +199,25 @@ class Fluid:
         B.check(B.lib().fxb_get_freeze_histogram(self._handle(), h.ctypes.data_as(C.c_void_p), n))
         return h
 
-    def tail_stats(self) -> dict:
-        """Counters of the dynamic pressure-solve schedule (FXB_TAIL=1): see fxb_get_tail_stats."""
-        out = np.zeros(5, np.uint64)
-        B.check(B.lib().fxb_get_tail_stats(self._handle(), out.ctypes.data_as(C.c_void_p), 5))
-        return {"enabled": bool(out[0]), "tail_launches_last_step": int(out[1]), "tail_bricks": int(out[2]),
-                "tail_subblocks_relaxed": int(out[3]), "tail_subblocks_dense": int(out[4])}
-
     def profile_step(self):
         """One un-graphed step timed per phase: dict of milliseconds."""
         ms = (C.c_float * 6)()
         B.check(B.lib().fxb_profile_step(self._handle(), ms, 6))
         keys = ("advect", "divergence", "jacobi", "gradient", "halo", "step")
         return {k: float(ms[i]) for i, k in enumerate(keys)}
+
+    def state_checksum(self) -> tuple:
+        """Three 64-bit words (velocity.xyz, colour, pressure) of this rank's slab; rank sums mod 2^64 are
+        decomposition-independent (fxb_state_checksum)."""
+        out = (C.c_uint64 * 3)()
+        B.check(B.lib().fxb_state_checksum(self._handle(), out))
+        return tuple(int(v) for v in out)
+
+    def phase_times(self, reset: bool = False) -> dict:
+        """Device time per phase accumulated over the steps run so far (needs ``phase_timing=True`` at Init): ms."""
+        ms = (C.c_double * 4)()
+        B.check(B.lib().fxb_get_phase_times(self._handle(), ms, 4, int(reset)))
+        return {k: float(ms[i]) for i, k in enumerate(("advect", "divergence", "jacobi", "gradient"))}
 
 
 class FluidEZ(Fluid):

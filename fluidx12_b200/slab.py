@@ -11,7 +11,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Tuple
 
-DEFAULT_H_ADV = 12  # advection back-trace reach in planes (2*|u_z| voxels) before the +1 tap
+DEFAULT_H_ADV = 8  # advection back-trace reach in planes (2*|u_z| voxels) before the +1 tap
 DEFAULT_JACOBI_GROUP = 1  # fused passes per pressure-halo exchange; > 1 relaxes the halo planes in between redundantly (experimental)
 
 

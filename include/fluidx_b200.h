@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FXB_ABI_VERSION 1
+#define FXB_ABI_VERSION 2
 
 typedef struct fxb_sim fxb_sim;
 
@@ -50,6 +50,12 @@ typedef enum fxb_field {
     FXB_FIELD_COLOR_PREV = 4         /* m_colors[!m_frameParity] */
 } fxb_field;
 
+/* How z-slab face halos travel between neighbouring ranks (nranks > 1). */
+typedef enum fxb_halo_backend {
+    FXB_HALO_PEER = 0, /* one kernel per exchange stores the face planes straight into the neighbours' memory (CUDA IPC over NVLink) */
+    FXB_HALO_NCCL = 1  /* grouped ncclSend / ncclRecv pairs */
+} fxb_halo_backend;
+
 typedef struct fxb_config {
     uint32_t struct_size;   /* = sizeof(fxb_config); set by fxb_config_default */
     uint32_t nx, ny, nz;    /* GLOBAL grid (gridSize of Fluid::Init, Fluid.cpp:189-201); nz == 1 selects the 2D path */
@@ -59,9 +65,12 @@ typedef struct fxb_config {
     int32_t fuse_t;         /* Jacobi sweeps fused per HBM pass; 0 = library default */
     int32_t device;         /* CUDA device ordinal */
     int32_t rank, nranks;   /* z-slab decomposition: this rank owns planes [rank*nz/nranks, (rank+1)*nz/nranks) */
-    int32_t h_adv;          /* advection z-halo in planes (multi-GPU); 0 = default 12 */
+    int32_t h_adv;          /* advection z-halo in planes (multi-GPU); 0 = default 8 */
     int32_t use_graph;      /* 1 (default): the step is a captured CUDA graph; 0: plain stream launches */
     int32_t kernel_path;    /* 0 = tuned kernels (default); 1 = one simple kernel per logical pass (cross-check path) */
+    int32_t phase_timing;   /* 1: a one-thread kernel after every phase accumulates the phase's device time (fxb_get_phase_times) */
+    int32_t halo_backend;   /* fxb_halo_backend (multi-GPU); default FXB_HALO_PEER */
+    int32_t jacobi_group;   /* multi-GPU: fused passes per pressure-halo exchange; 0 = library default (1) */
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; required iff nranks > 1 */
 } fxb_config;
 
@@ -76,9 +85,9 @@ typedef struct fxb_stats {
     uint64_t active_after_first_sweep; /* cells still active after sweep 1, last step (this rank) */
     uint64_t total_sweeps;     /* cumulative s_exec over all steps */
     uint64_t total_passes;     /* cumulative jacobi_passes over all steps */
-    uint64_t bricks_processed; /* cumulative brick passes: bricks relaxed by a fused pass or a tail launch (frozen bricks are skipped) */
+    uint64_t bricks_processed; /* cumulative brick passes: bricks relaxed by a fused pass (frozen bricks are skipped) */
     uint64_t bricks_copied;    /* cumulative frozen bricks copied once into the other pressure buffer */
-    uint64_t brick_cells;      /* output cells per brick (120 x (32-2T) x bz) */
+    uint64_t brick_cells;      /* output cells per brick (tile minus halo, x bz planes) */
     uint64_t bricks_per_pass;  /* bricks in the grid of one pass */
     int32_t jacobi_fused;      /* 1 when the fused Jacobi kernel is in use, 0 for one sweep per launch */
     int32_t reserved;
@@ -130,21 +139,7 @@ int fxb_get_stats(fxb_sim* sim, fxb_stats* out);
 int fxb_post_stats(fxb_sim* sim, int slot);
 int fxb_wait_stats(fxb_sim* sim, int slot, fxb_stats* out);
 
-/* Counters of the dynamic pressure-solve schedule (environment FXB_TAIL=1 at fxb_create; single GPU, default brick
- * shape).  Fills out[0..n), n <= 16: [0] = 1 when the schedule is in use, [1] = tail-kernel launches that did work in
- * the last step, [2] = cumulative bricks relaxed by tail launches (4 sweeps each), [3] = cumulative 40x12x8 sub-blocks
- * among them that still held an active cell, [4] = cumulative sub-blocks of [3] that took the dense path; the rest 0.
- * Synchronises the handle's stream. */
-int fxb_get_tail_stats(fxb_sim* sim, uint64_t* out, int n);
-
-/* Diagnostic, needs no GPU: the static launch sequence of the dynamic pressure-solve schedule for ITER = iters, T =
- * fuse_t and `mains` bulk passes.  kinds[i] >= 0: bulk pass with that static index (runs iff exactly kinds[i] * T
- * sweeps are done); -1: tail launch (4 sweeps) that runs iff few enough bricks are listed; -2: tail launch that
- * always runs.  Returns the length of the sequence (which may exceed `capacity`; only `capacity` entries are
- * written), or a negative fxb_status. */
-int fxb_plan_pressure_solve(int32_t iters, int32_t fuse_t, int32_t mains, int32_t* kinds, int32_t capacity);
-
-/* Diagnostic, needs no GPU: the plane arithmetic of the peer-memory halo exchange (FXB_P2P=1) for `rank` of `nranks`
+/* Diagnostic, needs no GPU: the plane arithmetic of the peer-memory halo exchange (FXB_HALO_PEER) for `rank` of `nranks`
  * z-slabs with `halo` allocated planes and an exchange `depth` planes deep.  out4 = {first local plane sent to rank-1,
  * first local plane of rank-1's array it lands in, first local plane sent to rank+1, first local plane of rank+1's
  * array it lands in} (entries for a missing neighbour are meaningless). */
@@ -162,6 +157,16 @@ int fxb_get_freeze_histogram(fxb_sim* sim, uint64_t* out, int n);
  * ms[2]=all Jacobi passes, ms[3]=gradient-subtract, ms[4]=halo exchange (0 when nranks == 1),
  * ms[5]=whole step.  The caller must have called fxb_update_frame. */
 int fxb_profile_step(fxb_sim* sim, float* ms, int n);
+
+/* Checksums of the current state, one 64-bit word per field (out3[0] velocity.xyz, [1] colour, [2] pressure): the
+ * wrap-around sum over this rank's own voxels of a mix of the voxel's global index and its bits.  The sums of all ranks
+ * of a z-slab run add up (mod 2^64) to the value a single GPU reports for the same state.  Synchronises the device. */
+int fxb_state_checksum(fxb_sim* sim, uint64_t* out3);
+
+/* Device time per phase accumulated by the phase marks since creation (or the last reset): ms[0]=advect (with its halo
+ * exchange), ms[1]=divergence, ms[2]=all Jacobi passes, ms[3]=gradient-subtract.  Needs fxb_config.phase_timing = 1;
+ * works for graph-launched steps, so the times belong to the very steps the caller timed.  Synchronises the device. */
+int fxb_get_phase_times(fxb_sim* sim, double* ms, int n, int reset);
 
 /* ---- Light-map pass ---------------------------------------------------------------------------
  * The pass that follows Fluid::Simulate in the reference's default render mode: Fluid::rayMarchL (Fluid.cpp:857-878)

@@ -86,6 +86,14 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def threads(n: int = 0) -> int:
+    """OpenMP threads the oracle uses: ``n > 0`` sets the count; returns the count in effect."""
+    L = lib()
+    L.fxo_threads.argtypes = [C.c_int]
+    L.fxo_threads.restype = C.c_int
+    return int(L.fxo_threads(int(n)))
+
+
 def dt_for_grid(nx: int, ny: int, nz: int) -> float:
     return float(lib().fxo_dt_for_grid(nx, ny, nz))
 

@@ -39,6 +39,9 @@
 //
 // Build: g++ -O2 -fopenmp -ffp-contract=off -fno-fast-math -march=x86-64-v3 (see oracle/Makefile).
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -752,6 +755,19 @@ struct Oracle {
 }  // namespace
 
 extern "C" {
+
+// OpenMP thread count used by every entry point below: n > 0 sets it; returns the count now in effect.  (Under
+// torch.distributed.run the environment says OMP_NUM_THREADS=1, so callers that time the oracle set it explicitly.)
+int fxo_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 
 enum { FXO_VEL = 0, FXO_COLOR = 1, FXO_PRESSURE = 2, FXO_VEL_ADVECTED = 3, FXO_COLOR_PREV = 4 };
 

@@ -31,11 +31,10 @@ def main():
         uid = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
     dist.broadcast(uid, 0)
     f = fx.Fluid()
-    if os.environ.get("FXB_TEST_TAIL") == "1":  # dynamic pressure-solve schedule on the slabs only, not on the reference
-        os.environ["FXB_TAIL"] = "1"
+    backend = fx.HALO_NCCL if os.environ.get("FXB_TEST_BACKEND", "peer") == "nccl" else fx.HALO_PEER
     assert f.Init(gridSize=grid, device=local, rank=rank, nranks=world, fuse_t=fuse_t, h_adv=int(os.environ.get("FXB_TEST_HADV", "8")),
+                  halo_backend=backend, jacobi_group=int(os.environ.get("FXB_TEST_GROUP", "0")),
                   nccl_unique_id=uid.numpy().tobytes(), use_graph=bool(int(os.environ.get("FXB_TEST_GRAPH", "1")))), f.last_error
-    os.environ.pop("FXB_TAIL", None)
     z0, cnt = f.slab
     ref = None
     if rank == 0:

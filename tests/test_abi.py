@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(fx):
     assert sorted(binding.EXPORTS) == syms
     for s in syms:
         assert hasattr(L, s), s
-    assert L.fxb_abi_version() == 1
+    assert L.fxb_abi_version() == 2
 
 
 def test_library_is_sm100a_only(fx):
@@ -101,8 +101,8 @@ def test_slab_plan():
     from fluidx12_b200 import halo_plan, slab_range
     assert [slab_range(512, r, 8) for r in (0, 7)] == [(0, 64), (448, 512)]
     assert slab_range(150, 1, 4) == (37, 75)
-    p = halo_plan(512, 0, 8, fuse_t=4)  # default advection halo: 12 planes (+1 for the second tap)
-    assert (p.z_first, p.nz_alloc, p.halo, p.group) == (0, 64 + 13, 13, 1) and len(p.advect) == 1
+    p = halo_plan(512, 0, 8, fuse_t=4)  # default advection halo: 8 planes (+1 for the second tap)
+    assert (p.z_first, p.nz_alloc, p.halo, p.group) == (0, 64 + 9, 9, 1) and len(p.advect) == 1
     q = halo_plan(512, 3, 8, fuse_t=4, h_adv=8)
     assert (q.z_first, q.nz_alloc) == (192 - 9, 64 + 18)
     lo, hi = q.advect
@@ -167,14 +167,7 @@ def test_sass_shows_blackwell_native_paths(fx):
     assert "FADD2" in adv and "FFMA2" in adv
     for banned in ("HMMA", "UTCHMMA", "UTCQMMA", "HGMMA"):
         assert banned not in sass
-    # the opt-in kernels are built too: the block-resident tail kernel (both dense paths and the pass-0 shape, its
-    # cp.async staging shows as LDGSTS), the second advection kernel, the peer-memory halo kernel
-    tail = [k for k in kernels if "jacobi_tail_kernel" in k]
-    assert len(tail) == 3, tail
-    assert any("LDGSTS" in l for k in tail for l in kernels[k])
-    assert any("UTMALDG" in l for k in tail for l in kernels[k])  # FXB_TAIL_CPASYNC=2: the window as one TMA box copy
-    assert any("advect2_kernel" in k for k in kernels) and any("halo_p2p_kernel" in k for k in kernels)
-    assert any("finish_solve_dynamic_kernel" in k for k in kernels)
+    assert any("halo_p2p_kernel" in k for k in kernels)  # the peer-memory halo exchange (multi-GPU default)
 
 
 @pytest.mark.parametrize("n", [(64, 64, 64), (150, 150, 150), (256, 256, 1), (512, 512, 1), (128, 128, 40), (30, 30, 18),
@@ -198,55 +191,6 @@ def test_emitter_box_contains_every_emitting_voxel(fx, n):
         assert xx.min() >= x0 and xx.max() < x1 and yy.min() >= y0 and yy.max() < y1 and zz.min() >= z0 and zz.max() < z1
     assert 0 <= x0 <= x1 <= nx and 0 <= y0 <= y1 <= ny and 0 <= z0 <= z1 <= nz
     assert (x1 - x0) * (y1 - y0) * (z1 - z0) <= max(64, 8 * emitting.sum() + 4096)  # and it is not wastefully large
-
-
-def _simulate_plan(plan, iters, t, tt, qualifies_from_sweep, frozen_at_sweep):
-    """Device-side rules of the dynamic schedule (jacobi_fused.cu DYN / jacobi_tail.cu) replayed on the host:
-    a bulk pass k runs iff exactly k*t sweeps are done; a conditional tail launch runs iff the brick list is short
-    enough (modelled: from `qualifies_from_sweep` sweeps on — the list only shrinks); an unconditional one always;
-    nothing runs once every cell is frozen (`frozen_at_sweep`).  Returns (sweeps done, kernels that ran)."""
-    done = ran = 0
-    for kind in plan:
-        if done >= iters or done >= frozen_at_sweep:
-            continue
-        if kind >= 0:
-            if done != kind * t:
-                continue
-            done += min(t, iters - done)
-        else:
-            if done == 0 or (kind == -1 and done < qualifies_from_sweep):
-                continue
-            done += min(tt, iters - done)
-        ran += 1
-    return done, ran
-
-
-@pytest.mark.parametrize("t", [1, 2])
-@pytest.mark.parametrize("iters", [1, 2, 7, 23, 64, 128])
-def test_dynamic_schedule_always_completes(t, iters):
-    """The static launch sequence (fxb_plan_pressure_solve, no GPU needed) reaches ITER sweeps whatever the moment the
-    tail kernel takes over, never overshoots, and stops early when the solve is over."""
-    import ctypes as C
-
-    import fluidx12_b200 as fx
-
-    L, tt = fx.lib(), 4
-    for mains in (1, 2, 3, 5, 8, 200):
-        buf = (C.c_int32 * 512)()
-        n = L.fxb_plan_pressure_solve(iters, t, mains, buf, 512)
-        assert 0 < n <= 512
-        plan = list(buf[:n])
-        assert plan[0] == 0 and all(k >= -2 for k in plan)
-        bulk = [k for k in plan if k >= 0]
-        assert bulk == list(range(len(bulk)))  # bulk passes appear in order, each once
-        for q in list(range(0, iters + 2)) + [10 ** 6]:
-            done, ran = _simulate_plan(plan, iters, t, tt, q, 10 ** 6)
-            assert done == iters, (mains, q, done, plan)
-            assert ran <= n
-        for frozen in range(1, iters + 1):
-            done, _ = _simulate_plan(plan, iters, t, tt, 3, frozen)
-            assert frozen <= done <= min(iters, frozen + tt - 1)
-    assert L.fxb_plan_pressure_solve(64, 9, 5, buf, 512) < 0  # bad fuse_t
 
 
 def test_config_validation_needs_no_device(fx):

@@ -1,5 +1,5 @@
 """bench.py's whole `ours` flow on a fake device: the JSON line it prints must carry every key of the bench contract
-(metric, value, e2e, roofline, cpu-side extras, clocks, gpu_launches, c3, experiments) — a typo in the code that runs
+(metric, value, e2e, roofline, cpu-side extras, clocks, gpu_launches, c3, state checksum) — a typo in the code that runs
 after the timed region would otherwise only show on the GPU box.  Nothing numerical is checked here."""
 import contextlib
 import json
@@ -50,12 +50,12 @@ class FakeFluid:
         self.steps += 1
         return {"advect": 1.9, "divergence": 0.4, "jacobi": 2.9, "gradient": 0.5, "halo": 0.0, "step": 5.7}
 
-    def post_stats(self, slot):
-        self.posted = getattr(self, "posted", {})
-        self.posted[slot] = self.steps
+    def phase_times(self, reset=False):
+        return {"advect": 1.9 * self.steps, "divergence": 0.4 * self.steps, "jacobi": 2.9 * self.steps,
+                "gradient": 0.5 * self.steps}
 
-    def wait_stats(self, slot):
-        return FakeStats(self.posted[slot])
+    def state_checksum(self):
+        return (1, 2, 3)
 
     def get_field_async(self, field, ptr, nbytes, stream=None):
         assert nbytes == self.m_gridSize[0] * self.m_gridSize[1] * self.m_gridSize[2] * 8
@@ -86,7 +86,8 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     import ctypes as C
 
     import torch
-    fake_fx = types.SimpleNamespace(Fluid=FakeFluid, ADDRESS_MIRROR=0, FIELD_COLOR=1, dt_for_grid=lambda *g: 2.0 / g[1],
+    fake_fx = types.SimpleNamespace(Fluid=FakeFluid, ADDRESS_MIRROR=0, FIELD_COLOR=1, HALO_PEER=0, HALO_NCCL=1,
+                                    dt_for_grid=lambda *g: 2.0 / g[1],
                                     FxbStats=type("S", (C.Structure,), {"_fields_": [("x", C.c_int * 24)]}))
     monkeypatch.setitem(sys.modules, "fluidx12_b200", fake_fx)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
@@ -99,22 +100,15 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
 
-    def fake_child(cmd, env, timeout_s):
-        with open(env["FXB_SHOT_OUT"], "w") as fh:
-            fh.write(json.dumps({"stage": "timing", "grid": [256, 256, 256], "default": 1.5,
-                                 "default_phases": {"jacobi": 1.2, "advect": 0.3}}) + "\n")
-        return 0, ""
-
-    monkeypatch.setattr(bench, "run_child", fake_child)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "3", "--spinup", "2", "--grid", "32", "32", "32",
-                                      "--no-cpu-baseline"])
+                                      "--no-cpu-baseline", "--export-e2e"])
     bench.main()
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
-                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "c3", "c2", "experiments",
-                "e2e_export", "e2e_pipelined", "phase_roofline", "step_roofline"):
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "c3", "c2",
+                "e2e_export", "phase_roofline", "step_roofline", "state_checksum", "phase_ms"):
         assert key in line, key
     assert line["metric"] == "voxel_updates_per_s" and line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] == 3
     assert line["config"]["workload"].startswith("3D 32x32x32") and line["vs_baseline"] is None
@@ -122,5 +116,6 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["e2e_export"]["d2h_bytes_per_step"] > 32 * 32 * 32 * 8
     assert line["gpu_launches"] == 38 * 4
-    assert line["experiments"]["results"][0]["variant"] == "default"
+    assert line["roofline"]["kernel"] == "jacobi_pass_kernel" and line["state_checksum"].count("-") == 2
+    assert "experiments" not in line
     assert np.isclose(line["value"], 32 ** 3 * 4 / 12.5e-3)

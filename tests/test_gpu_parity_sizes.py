@@ -1,0 +1,57 @@
+"""GPU parity at the sizes BASELINE.json names (configs[1] 128^3, configs[2] 256^3) and at the reference's own shipped
+demo grid (150^3, /root/reference/Bin/FluidGI.bat:1): 100 emitter-driven frames from the zero state against the CPU
+oracle — the north star's 100-step gate (relative L2 <= 1e-3 per field) and, in practice, bit-exactness of the whole
+trajectory including the number of relaxation sweeps (S_exec) of every 10th frame."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.test_gpu_parity import TOL_100STEP, TOL_1STEP, compare, make_pair
+from tests.util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import fluidx12_b200 as fx
+    fx.lib()
+    return fx
+
+
+@pytest.mark.parametrize("n,steps", [((128, 128, 128), 100), ((256, 256, 256), 100), ((150, 150, 150), 40)])
+def test_emitter_driven_frames_at_baseline_sizes(fx, oracle_mod, n, steps):
+    oracle_mod.threads(os.cpu_count() or 1)
+    f, o = make_pair(fx, oracle_mod, n)
+    dt = fx.dt_for_grid(*n)
+    for k in range(steps):
+        f.step(dt); o.step(dt)
+        if k % 10 == 9:
+            assert f.stats().s_exec == o.s_exec, (k, f.stats().s_exec, o.s_exec)
+    hist = f.freeze_histogram(64)
+    compare(fx, oracle_mod, f, o, TOL_100STEP, metric=rel_l2)
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    assert f.stats().halo_overflow == 0 and hist[0] > 0
+
+
+def test_state_checksum_is_position_dependent_and_decomposition_ready(fx):
+    """fxb_state_checksum: equal states give equal words, a one-ulp change of one voxel or a swap of two planes changes
+    them (the multi-GPU bench compares the rank sum with the single-GPU value)."""
+    n = (32, 32, 32)
+    a, b = fx.Fluid(), fx.Fluid()
+    assert a.Init(gridSize=n) and b.Init(gridSize=n)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(6):
+        a.step(dt); b.step(dt)
+    assert a.state_checksum() == b.state_checksum()
+    p = b.get_field(fx.FIELD_PRESSURE)
+    q = p.copy()
+    q[3, 4, 5] = np.nextafter(q[3, 4, 5], np.float32(1e9))
+    b.set_field(fx.FIELD_PRESSURE, q)
+    ca, cb = a.state_checksum(), b.state_checksum()
+    assert ca[:2] == cb[:2] and ca[2] != cb[2]
+    q = p.copy()
+    q[[3, 4]] = q[[4, 3]]
+    b.set_field(fx.FIELD_PRESSURE, q)
+    assert (q != p).any() and a.state_checksum()[2] != b.state_checksum()[2]

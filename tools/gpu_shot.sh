@@ -1,0 +1,25 @@
+#!/bin/bash
+# One gpurun call of the build -> measure loop: GPU tests, smoke, the bench line, launch lists and ncu captures.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_shot.sh [tests|notests] [tag]'
+# Everything lands in gpurun_out/ (scratch); tools/summarize_profiles.py turns it into profiles/.
+what=${1:-tests}; tag=${2:-r2}
+out=gpurun_out; mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader > $out/${tag}_gpu.txt 2>&1
+if [ "$what" = tests ]; then
+  timeout 1100 python -m pytest tests -x -q -m gpu -p no:cacheprovider > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
+  tail -5 $out/${tag}_pytest.log
+  timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> $out/${tag}_smoke.log
+  tail -3 $out/${tag}_smoke.log
+fi
+timeout 600 python bench.py --steps 30 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+python tools/benchsum.py $out/${tag}_bench.json 2>/dev/null | head -40
+K=38   # kernels per un-graphed step without phase marks
+for g in 256 512; do
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s $((100*K)) -c $((2*K)) --csv --log-file $out/${tag}_launches_$g.csv \
+      python tools/profile_step.py --grid $g $g $g --steps 102 > $out/${tag}_launches_$g.log 2>&1
+done
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:jacobi_pass -s 3200 -c 3 -o $out/${tag}_jacobi_256 -f \
+    python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_j.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"advect_kernel|divergence_quad|gradient_quad" -s 300 -c 3 -o $out/${tag}_adg_256 -f \
+    python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_a.log 2>&1
+ls -la $out | tail -15
