@@ -473,7 +473,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                         st = relax_quad(c0v, f0, b0, up, c1v, l0, r0, rhs0, act & 0xFu, eps, out[0]);
                         st |= relax_quad(c1v, f1, b1, c0v, dn, l1, r1, rhs1, act >> 4, eps, out[1]) << 4;
                         fix_ghosts(out);
-                        if (z >= zs && z < ze) {
+                        if (z >= zs && z < ze && it.brick >= 0) {  // halo bricks are counted by their owner
                             tot[l] += __popc(st & own_bits);
                             if (l == levels) alive |= st & own_bits;
                         }
