@@ -118,7 +118,7 @@ int build_axis_tables(fxb_sim* s) {
 // halos are exchanged): every rank runs every pass, and every pass flips once.
 int flips_per_step(const fxb_sim* s) {
     if (!s->fused) return 0;
-    return (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
+    return fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters);
 }
 
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
@@ -211,27 +211,30 @@ void enqueue_phase(Enqueue& q, int phase) {
             break;
         case PH_JACOBI:
             if (s->fused) {
-                const int npass = (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t;
+                const int npass = fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters);
                 if (cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st) != cudaSuccess)
                     q.launched(cudaGetLastError(), "cudaMemsetAsync(work_count)", 0);
                 const bool mg = s->multi() && s->dt > 0.0f;
                 // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
                 // between, pass j of a group also relaxes the (G-1-j)*T halo planes next to each interior face.
-                const int G = s->multi() ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
-                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the group
-                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * s->fuse_t}};
+                // (grouping needs a uniform T; the mixed schedule exchanges before every pass, as deep as that pass fuses)
+                const int G = s->multi() && !s->jac.mixed ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
+                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the deepest pass
+                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * std::max(s->jac.T, s->jac.T_late)}};
                     q.halo(f, 1);
                 }
                 for (int k = 0; k < npass; ++k) {
                     int ext_lo = 0, ext_hi = 0;
                     if (mg) {
+                        int Tk, s0k;
+                        fxb::fused_jacobi_pass_spec(s->jac, k, &Tk, &s0k);
                         if (k % G == 0) {
                             const fxb::HaloField f[2] = {
-                                {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * s->fuse_t},
-                                {s->jac.mask[k & 1], s->plane_voxels() / 8, G * s->fuse_t}};
+                                {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * Tk},
+                                {s->jac.mask[k & 1], s->plane_voxels() / 8, G * Tk}};
                             q.halo(f, k == 0 ? 1 : 2);
                         }
-                        const int ext = (G - 1 - k % G) * s->fuse_t;
+                        const int ext = (G - 1 - k % G) * Tk;
                         ext_lo = s->cfg.rank > 0 ? ext : 0;
                         ext_hi = s->cfg.rank < s->cfg.nranks - 1 ? ext : 0;
                     }
@@ -247,7 +250,7 @@ void enqueue_phase(Enqueue& q, int phase) {
                         q.err = "all-reduce of the freeze counters: " + fxb::halo_last_error();
                     }
                 }
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->fuse_t,
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->jac.T, s->jac.T_late,
                                          s->multi() ? npass : -1, st);
                 q.launched(cudaGetLastError(), "finish_solve_kernel");
                 if (mg) {  // z neighbours of the final pressure for the gradient
@@ -258,7 +261,7 @@ void enqueue_phase(Enqueue& q, int phase) {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
                                                     s->cfg.early_exit, st);
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, -1, st);
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, 1, -1, st);
                 q.launched(cudaGetLastError(), "jacobi_sweep_simple_kernel", s->cfg.jacobi_iters + 1);
             }
             break;
@@ -404,7 +407,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         // z-slab decomposition (fluidx12_b200/slab.py states the same rules): rank r owns planes
         // [r*nz/R, (r+1)*nz/R); interior faces carry `halo` extra planes, the grid's own faces none
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
-        const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
+        const int fuse = cfg->fuse_t ? cfg->fuse_t : 4;  // the deepest pass of the default schedule
         s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;  // 2|u_z| voxels; |u_z| stayed below 3 in every run
         s->jacobi_group = cfg->jacobi_group > 0 ? cfg->jacobi_group : 1;
         s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
@@ -459,14 +462,14 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (s->cfg.kernel_path == 0 && fxb::fused_jacobi_supported(s->dom) && s->cfg.jacobi_iters > 0) {
         // Tuned path: T sweeps fused per HBM pass.  Grids whose nx is not a multiple of 8 (e.g. the 150^3 of
         // Bin/FluidGI.bat) and the 2D path use the one-sweep-per-launch kernels instead.
-        s->fuse_t = cfg->fuse_t ? cfg->fuse_t : 2;
         const size_t mask_bytes = n / 8;
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&s->jac.mask[i], std::max(mask_bytes, ipc_min));
             if (e == cudaSuccess) e = cudaMemset(s->jac.mask[i], 0, mask_bytes);
         }
-        if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, s->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
+        if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, cfg->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
             return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
+        s->fuse_t = s->jac.T_late;  // what fxb_stats reports: sweeps per pass after the first
         const size_t nc = 3 * (fxb::FusedJacobi::kMaxPasses + 1);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&s->jac.work_list[i], 2 * (size_t)s->jac.list_stride * sizeof(int));
@@ -493,7 +496,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         rc = capture_graph(s, 0, 0);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
-        const int jl = s->fused ? (s->cfg.jacobi_iters + s->fuse_t - 1) / s->fuse_t : s->cfg.jacobi_iters;
+        const int jl = s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) : s->cfg.jacobi_iters;
         s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1 + (s->cfg.phase_timing ? 2 : 0);
     }
     if (s->multi()) {

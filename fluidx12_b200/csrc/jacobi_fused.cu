@@ -593,10 +593,17 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int pitch, in
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// The shapes in use.  Wide: tile 128 x 16 (one warp per row pair); narrow: tile 64 x 32 (a warp covers two row pairs),
-// chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as possible.
-template <int T> using Wide = Shape<T, 32, 8, 2, (T <= 2 ? 2 : 1)>;
-template <int T> using Narrow = Shape<T, 16, 8, 2, (T <= 2 ? 2 : 1)>;
+// The shapes in use.  Wide: tile rows of 32 lanes (128 cells, one warp per row pair); narrow: 16 lanes (64 cells, a warp
+// covers two row pairs), chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as
+// possible.  The default schedule mixes two kernels over ONE brick grid (own region 120 x 12 or 56 x 28 cells):
+//   first pass   T = 2, two CTAs per SM, TMA depth 3 — every brick is relaxed, throughput matters;
+//   later passes T = 4, one CTA per SM, TMA depth 4, one / two more warps for the deeper y halo — few bricks are left,
+//                what matters is the latency of one brick chain and the number of launches (16 instead of 31).
+// A uniform schedule (fxb_config.fuse_t = 1..4) uses the two-CTA shape for T <= 2 and the one-CTA shape above.
+template <int T> using WideU = Shape<T, 32, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
+template <int T> using NarrowU = Shape<T, 16, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
+using WideLate = Shape<4, 32, 10, 4, 1>;    // tile 128 x 20: own rows 12, as the T = 2 tile 128 x 16
+using NarrowLate = Shape<4, 16, 9, 4, 1>;   // tile 64 x 36: own rows 28, as the T = 2 tile 64 x 32
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
@@ -627,17 +634,13 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
     W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np;
+    const bool late = S::kTileY != J.tile_y;  // the later passes' kernel of the mixed schedule stages a taller tile
     jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
-        *reinterpret_cast<const CUtensorMap*>(J.map_p[0]), *reinterpret_cast<const CUtensorMap*>(J.map_p[1]),
-        *reinterpret_cast<const CUtensorMap*>(J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P);
+        *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[0] : J.map_p[0]),
+        *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[1] : J.map_p[1]),
+        *reinterpret_cast<const CUtensorMap*>(late ? J.map_rhs_late : J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0],
+        J.mask[1], W, P);
     return cudaGetLastError();
-}
-
-template <int T>
-cudaError_t launch_T(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass, int s0,
-                     int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
-    if (J.narrow) return launch_shape<Narrow<T>>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
-    return launch_shape<Wide<T>>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
 }
 
 // Tiles needed to cover n cells with own regions of `out` cells.
@@ -649,15 +652,19 @@ bool fused_jacobi_supported(const Domain& d) { return d.nz > 1 && d.nx >= 8 && (
 
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs) {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
-    J->T = fuse_t;
+    // fuse_t = 0: the mixed schedule (T = 2, then T = 4 on the same bricks); otherwise T = fuse_t throughout
+    J->mixed = fuse_t == 0;
+    J->T = J->mixed ? 2 : fuse_t;
+    J->T_late = J->mixed ? 4 : fuse_t;
+    const int T = J->T;
     // tile shape: the one whose tiles cover the least area beyond the grid (compute and staging are per tile cell)
-    const long long wide = (long long)tiles_for(d.nx, 120) * 128 * tiles_for(d.ny, 16 - 2 * fuse_t) * 16;
-    const long long narrow = (long long)tiles_for(d.nx, 56) * 64 * tiles_for(d.ny, 32 - 2 * fuse_t) * 32;
+    const long long wide = (long long)tiles_for(d.nx, 120) * 128 * tiles_for(d.ny, 16 - 2 * T) * 16;
+    const long long narrow = (long long)tiles_for(d.nx, 56) * 64 * tiles_for(d.ny, 32 - 2 * T) * 32;
     J->narrow = narrow < wide;
     if (const char* e = getenv("FXB_TILE")) J->narrow = atoi(e) == 64;  // tuning knob: 64 or 128
     J->tile_x = J->narrow ? 64 : 128;
-    J->tile_y = J->narrow ? 32 : 16;
-    const int out_x = J->tile_x - 2 * kHaloX, out_y = J->tile_y - 2 * fuse_t;
+    J->tile_y = J->narrow ? 32 : 16;  // of the first pass's kernel
+    const int out_x = J->tile_x - 2 * kHaloX, out_y = J->tile_y - 2 * T;
     J->ntx = tiles_for(d.nx, out_x);
     J->nty = tiles_for(d.ny, out_y);
     const int nz_out = d.z_own1 - d.z_own0;
@@ -668,15 +675,32 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     }
     J->nzc = (nz_out + J->bz - 1) / J->bz;
     J->p[0] = p0; J->p[1] = p1; J->rhs = rhs;
-    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
-    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[1]), p1, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
-    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
+    float* base[3] = {p0, p1, rhs};
+    for (int i = 0; i < 3; ++i) {
+        unsigned char* first = i < 2 ? J->map_p[i] : J->map_rhs;
+        unsigned char* late = i < 2 ? J->map_p_late[i] : J->map_rhs_late;
+        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(first), base[i], d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
+        // the later passes' tile: the same own region under a halo of T_late rows
+        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(late), base[i], d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x,
+                            out_y + 2 * J->T_late)) return -1;
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&J->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     // the kernel prefetches list entries up to two grid strides ahead: the lists are padded accordingly
     J->list_stride = (int)fused_jacobi_bricks(*J) + 4 * J->num_sms + 8;
     return 0;
+}
+
+int fused_jacobi_passes(const FusedJacobi& J, int iters) {
+    if (iters <= 0) return 0;
+    if (iters <= J.T) return 1;
+    return 1 + (iters - J.T + J.T_late - 1) / J.T_late;
+}
+
+void fused_jacobi_pass_spec(const FusedJacobi& J, int pass, int* T, int* s0) {
+    *T = pass == 0 ? J.T : J.T_late;
+    *s0 = pass == 0 ? 0 : J.T + (pass - 1) * J.T_late;
 }
 
 size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty * J.nzc; }
@@ -690,13 +714,20 @@ void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
                                      cudaStream_t stream) {
-    const int s0 = pass * J.T;
-    switch (J.T) {
-        case 1: return launch_T<1>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
-        case 2: return launch_T<2>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
-        case 3: return launch_T<3>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
-        case 4: return launch_T<4>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream);
+    int T, s0;
+    fused_jacobi_pass_spec(J, pass, &T, &s0);
+#define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream)
+    if (J.mixed && pass > 0) {
+        if (J.narrow) FXB_LAUNCH(NarrowLate);
+        FXB_LAUNCH(WideLate);
     }
+    switch (T) {
+        case 1: if (J.narrow) FXB_LAUNCH(NarrowU<1>); FXB_LAUNCH(WideU<1>);
+        case 2: if (J.narrow) FXB_LAUNCH(NarrowU<2>); FXB_LAUNCH(WideU<2>);
+        case 3: if (J.narrow) FXB_LAUNCH(NarrowU<3>); FXB_LAUNCH(WideU<3>);
+        case 4: if (J.narrow) FXB_LAUNCH(NarrowU<4>); FXB_LAUNCH(WideU<4>);
+    }
+#undef FXB_LAUNCH
     return cudaErrorInvalidValue;
 }
 

@@ -112,17 +112,17 @@ __global__ void __launch_bounds__(256) jacobi_sweep_simple_kernel(Domain d, cons
     if (threadIdx.x == 0 && threadIdx.y == 0 && cnt) atomicAdd(&state->active_after[sweep], (unsigned long long)cnt);
 }
 
-// sweeps_per_flip: 1 for the simple path, T for the fused path (the pressure ping-pong flips once per pass).
-// force_passes >= 0 (multi-GPU): every rank ran exactly that many passes, whatever the freeze counters say.
+// t_first / t_late: sweeps per pressure ping-pong flip of the first / every later pass (1, 1 for the simple path; the
+// fused passes' T).  force_passes >= 0 (multi-GPU): every rank ran exactly that many passes, whatever the counters say.
 __global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters,
-                                    int sweeps_per_flip, int force_passes) {
+                                    int t_first, int t_late, int force_passes) {
     if (threadIdx.x != 0) return;
     int s = 0;
     if (0.0f < frame->dt && iters > 0) {
         s = 1;
         while (s < iters && state->active_after[s - 1] != 0ull) ++s;
     }
-    int passes = (s + sweeps_per_flip - 1) / sweeps_per_flip;
+    int passes = s <= t_first ? (s > 0 ? 1 : 0) : 1 + (s - t_first + t_late - 1) / t_late;
     if (force_passes >= 0 && 0.0f < frame->dt) passes = force_passes;
     state->s_exec = s;
     state->passes = passes;
@@ -196,9 +196,9 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
                                                                           early_exit);
 }
 
-void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int sweeps_per_flip, int force_passes,
-                         cudaStream_t stream) {
-    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, sweeps_per_flip, force_passes);
+void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int t_first, int t_late,
+                         int force_passes, cudaStream_t stream) {
+    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, t_first, t_late, force_passes);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,

@@ -160,6 +160,40 @@ def test_fused_jacobi_every_T_and_ragged_tiles(fx, oracle_mod, n, fuse_t):
         compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
 
 
+@pytest.mark.parametrize("tile", ["64", "128"])
+@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3)])
+def test_default_schedule_on_both_tile_widths(fx, oracle_mod, monkeypatch, n, tile):
+    """The default schedule (first pass T = 2, later passes T = 4 with the latency-optimised kernel shape, one brick
+    grid for both) with the tile width forced to 64 and to 128 cells (normally chosen per grid)."""
+    monkeypatch.setenv("FXB_TILE", tile)
+    f, o = make_pair(fx, oracle_mod, n)
+    monkeypatch.delenv("FXB_TILE")
+    st = f.stats()
+    assert st.jacobi_fused == 1 and st.fuse_t == 4 and st.brick_cells in (56 * 28 * min(8, n[2]), 120 * 12 * min(8, n[2]))
+    inject(fx, oracle_mod, f, o, n, seed=33)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(4):
+        f.step(dt); o.step(dt)
+        assert f.stats().s_exec == o.s_exec
+        assert f.stats().jacobi_passes == (1 + -(-(o.s_exec - 2) // 4) if o.s_exec > 2 else 1)
+        compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    # cells still active after sweep k + 1 (GPU) = cells entering sweep k + 1 (oracle)
+    s = o.s_exec
+    assert np.array_equal(f.freeze_histogram(64)[:s - 1].astype(np.int64), o.active_hist()[1:s])
+
+
+@pytest.mark.parametrize("early,iters", [(False, 64), (False, 7), (True, 5), (True, 1), (True, 64), (True, 3)])
+def test_default_schedule_partial_passes(fx, oracle_mod, early, iters):
+    n = (72, 72, 40)
+    f, o = make_pair(fx, oracle_mod, n, early_exit=early, iters=iters)
+    inject(fx, oracle_mod, f, o, n, seed=4)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(2):
+        f.step(dt); o.step(dt)
+    assert f.stats().s_exec == o.s_exec
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
 @pytest.mark.parametrize("early,iters", [(False, 64), (False, 7), (True, 5), (True, 1), (True, 64)])
 def test_fused_jacobi_partial_last_pass_and_no_early_exit(fx, oracle_mod, early, iters):
     n = (72, 72, 40)
