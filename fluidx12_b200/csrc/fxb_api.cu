@@ -117,8 +117,7 @@ int build_axis_tables(fxb_sim* s) {
 // Pressure ping-pong flips of one (dt > 0) step as the HOST must know them (multi-GPU: they select the buffers whose
 // halos are exchanged): every rank runs every pass, and every pass flips once.
 int flips_per_step(const fxb_sim* s) {
-    if (!s->fused) return 0;
-    return fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters);
+    return s->fused && s->cfg.jacobi_iters > 0 ? 1 : 0;  // to the first pass's output buffer (jacobi_settle_kernel)
 }
 
 enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
@@ -212,8 +211,9 @@ void enqueue_phase(Enqueue& q, int phase) {
         case PH_JACOBI:
             if (s->fused) {
                 const int npass = fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters);
-                if (cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st) != cudaSuccess)
-                    q.launched(cudaGetLastError(), "cudaMemsetAsync(work_count)", 0);
+                if (cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st) != cudaSuccess ||
+                    cudaMemsetAsync(s->jac.brick_flag, 0, fxb::fused_jacobi_bricks(s->jac) * sizeof(int), st) != cudaSuccess)
+                    q.launched(cudaGetLastError(), "cudaMemsetAsync(work lists)", 0);
                 const bool mg = s->multi() && s->dt > 0.0f;
                 // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
                 // between, pass j of a group also relaxes the (G-1-j)*T halo planes next to each interior face.
@@ -250,18 +250,17 @@ void enqueue_phase(Enqueue& q, int phase) {
                         q.err = "all-reduce of the freeze counters: " + fxb::halo_last_error();
                     }
                 }
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->jac.T, s->jac.T_late,
-                                         s->multi() ? npass : -1, st);
-                q.launched(cudaGetLastError(), "finish_solve_kernel");
-                if (mg) {  // z neighbours of the final pressure for the gradient
-                    const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + npass) & 1], s->plane_voxels() * 4, 1}};
+                q.launched(fxb::launch_jacobi_settle(s->jac, d, s->d_frame, s->d_state, s->cfg.jacobi_iters,
+                                                     s->multi() ? npass : -1, st), "jacobi_settle_kernel", 2);
+                if (mg) {  // z neighbours of the final pressure (the first pass's output buffer) for the gradient
+                    const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + 1) & 1], s->plane_voxels() * 4, 1}};
                     q.halo(f, 1);
                 }
             } else {
                 for (int k = 0; k < s->cfg.jacobi_iters; ++k)
                     fxb::launch_jacobi_sweep_simple(d, s->d_frame, s->rhs, s->p[0], s->p[1], s->active, s->d_state, k,
                                                     s->cfg.early_exit, st);
-                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, 1, 1, -1, st);
+                fxb::launch_finish_solve(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);
                 q.launched(cudaGetLastError(), "jacobi_sweep_simple_kernel", s->cfg.jacobi_iters + 1);
             }
             break;
@@ -475,6 +474,10 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             e = cudaMalloc((void**)&s->jac.work_list[i], 2 * (size_t)s->jac.list_stride * sizeof(int));
             if (e == cudaSuccess) e = cudaMemset(s->jac.work_list[i], 0, 2 * (size_t)s->jac.list_stride * sizeof(int));
         }
+        const size_t nbricks = fxb::fused_jacobi_bricks(s->jac);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.brick_flag, nbricks * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(s->jac.brick_flag, 0, nbricks * sizeof(int));
+        s->jac.copy_all = s->multi() && s->jacobi_group > 1;
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.work_count, nc * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(s->jac.work_count, 0, nc * sizeof(int));
         if (e != cudaSuccess)
@@ -497,7 +500,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
         const int jl = s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) : s->cfg.jacobi_iters;
-        s->kernels_per_step = 1 + 1 + 2 + jl + 1 + 1 + (s->cfg.phase_timing ? 2 : 0);
+        s->kernels_per_step = 1 + 1 + 2 + jl + (s->fused ? 2 : 1) + 1 + (s->cfg.phase_timing ? 2 : 0);
     }
     if (s->multi()) {
         // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
@@ -536,6 +539,7 @@ void fxb_destroy(fxb_sim* s) {
     cudaFree(s->jac.work_list[0]);
     cudaFree(s->jac.work_list[1]);
     cudaFree(s->jac.work_count);
+    cudaFree(s->jac.brick_flag);
     cudaFree(s->light_map);
     cudaFree(s->cube_map);
     if (s->stats_ring) cudaFreeHost(s->stats_ring);

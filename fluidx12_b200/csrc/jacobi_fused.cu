@@ -30,6 +30,7 @@
 // Algorithmic traffic per relaxed cell per pass: p in 4 + rhs in 4 + p out 4 (+ 2/8 mask) bytes; 8 per copied cell.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -112,6 +113,8 @@ struct PassParams {
     int early_exit;
     int run_all;           // multi-GPU: never end the solve on this rank's own freeze counters
     int ext_lo, ext_hi;    // multi-GPU: planes below / above the owned range to relax redundantly in this pass
+    int copy_all;          // 1: every brick that froze in the first pass is copied; 0: only those next to an active brick
+    int keep_lo, keep_hi;  // multi-GPU: bricks of the lowest / highest layer are always copied (a neighbour rank reads them)
 };
 
 struct WorkLists {
@@ -119,6 +122,7 @@ struct WorkLists {
     int* copy[2];      // bricks that froze in the previous pass: one copy into the other pressure buffer
     int* relax_count;  // [pass]
     int* copy_count;   // [pass]
+    int* brick_flag;   // [bricks] first pass: bit 0 = all cells froze, bit 1 = a brick next to it is still active
 };
 
 // One work item of a pass: a brick of this rank's own planes (brick >= 0; tracked in the work lists and the freeze
@@ -273,8 +277,36 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // the frozen bricks of the previous pass: one copy each
-    if (n_copy > 0) {
+    // The frozen bricks of the previous pass: one copy each into the other pressure buffer.  Of the bricks that froze
+    // in the FIRST pass (the far field: most of a large grid) only those within reach of a still-active brick are ever
+    // read again in this frame, so only those are copied (brick_flag == 3); the others stay final in the first pass's
+    // output buffer, which jacobi_settle_kernel makes the frame's final buffer.
+    if (pass == 1) {
+        __shared__ int s_copied;
+        if (tid == 0) s_copied = 0;
+        __syncthreads();
+        const int nbricks = P.ntx * P.nty * P.nzc, layer = P.ntx * P.nty;
+        for (int b0 = blockIdx.x; b0 < nbricks; b0 += gridDim.x * 32) {
+            // 32 candidate bricks of this CTA at a time: one coalesced-ish round trip for their flags
+            int b = b0 + (tid & 31) * gridDim.x;
+            int f = (tid < 32 && b < nbricks) ? W.brick_flag[b] : 0;
+            const bool edge = (P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer);
+            const bool want = (f & 1) && ((f & 2) || P.copy_all || edge);
+            const unsigned todo = __ballot_sync(kFull, tid < 32 && want);
+            __shared__ unsigned s_todo;
+            if (tid == 0) s_todo = todo;
+            __syncthreads();
+            unsigned m = s_todo;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                copy_frozen_brick<S>(p_in, p_out, m_out, P, b0 + j * gridDim.x);
+                if (tid == 0) ++s_copied;
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && s_copied) atomicAdd(&state->bricks_copied, (unsigned long long)s_copied);
+    } else if (n_copy > 0) {
         const int* __restrict__ copy_list = W.copy[pass & 1];
         for (int w = blockIdx.x; w < n_copy; w += gridDim.x) copy_frozen_brick<S>(p_in, p_out, m_out, P, copy_list[w]);
         if (tid == 0 && blockIdx.x == 0) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
@@ -528,7 +560,19 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         // ---- brick state: still active -> relax again next pass; just frozen -> one copy next pass ----
         if (it.brick >= 0) {
             const int any_alive = __syncthreads_or(alive != 0u);
-            if (tid == 0) {
+            if (pass == 0) {
+                // first pass: a frozen brick is only flagged; a still-active one flags the 26 bricks around it (their
+                // cells are within reach of its tile in x, y or z), which pass 1 then copies if they froze
+                if (!any_alive) {
+                    if (tid == 0) atomicOr(&W.brick_flag[it.brick], 1);
+                } else if (tid < 27) {
+                    const int tx = it.brick % P.ntx, ty = (it.brick / P.ntx) % P.nty, tz = it.brick / (P.ntx * P.nty);
+                    const int nx_ = tx + tid % 3 - 1, ny_ = ty + (tid / 3) % 3 - 1, nz_ = tz + tid / 9 - 1;
+                    if (tid != 13 && nx_ >= 0 && nx_ < P.ntx && ny_ >= 0 && ny_ < P.nty && nz_ >= 0 && nz_ < P.nzc)
+                        atomicOr(&W.brick_flag[(nz_ * P.nty + ny_) * P.ntx + nx_], 2);
+                }
+            }
+            if (tid == 0 && (any_alive || pass > 0)) {
                 if (pend_brick >= 0) pend_list[pend_slot] = pend_brick;
                 pend_brick = it.brick;
                 if (any_alive) {
@@ -561,6 +605,53 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (v) atomicAdd(&state->active_after[s0 + tid], (unsigned long long)v);
     }
     if (tid == 0 && n_done) atomicAdd(&state->bricks_processed, (unsigned long long)n_done);
+}
+
+// After the last pass.  The frame's final pressure must be complete in ONE buffer: the first pass's output buffer Y,
+// the only one that holds the bricks that froze in the first pass and were never copied.  Every later brick is final
+// in both buffers once copied — except the bricks relaxed by the last executed pass L when that pass wrote the other
+// buffer (L odd): those (pass L + 1's relax and copy lists) are copied into Y here.  Also the solve's bookkeeping that
+// finish_solve_kernel does for the per-sweep path: s_exec, pass count, which buffer holds P.
+template <class S>
+__global__ void __launch_bounds__(S::kThreads)
+jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
+                     unsigned char* m0, unsigned char* m1, const __grid_constant__ WorkLists W,
+                     const __grid_constant__ PassParams P, const int t_first, const int n_early, const int t_late,
+                     const int force_passes) {
+    const int iters = P.levels_total;
+    const bool live = 0.0f < frame->dt && iters > 0;
+    int s = 0;
+    if (live) {
+        s = 1;
+        while (s < iters && state->active_after[s - 1] != 0ull) ++s;
+    }
+    int passes = s <= n_early * t_first ? (s + t_first - 1) / t_first : n_early + (s - n_early * t_first + t_late - 1) / t_late;
+    if (force_passes >= 0 && live) passes = force_passes;
+    const int p_cur = state->p_cur;  // still the frame's input buffer X; Y is the other one
+    if (passes > 0 && ((passes - 1) & 1)) {
+        const int L = passes - 1;
+        const float* src = p_cur ? p1 : p0;   // out(L) = X for odd L
+        float* dst = p_cur ? p0 : p1;
+        unsigned char* m_dst = ((L + 1) & 1) ? m0 : m1;  // as pass L + 1 would have cleared it (unused after the frame)
+        const int n_r = W.relax_count[L + 1], n_c = W.copy_count[L + 1];
+        const int* __restrict__ lr = W.relax[(L + 1) & 1];
+        const int* __restrict__ lc = W.copy[(L + 1) & 1];
+        for (int w = blockIdx.x; w < n_r + n_c; w += gridDim.x)
+            copy_frozen_brick<S>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // (p_cur itself is flipped by the next kernel: other CTAs still read it)
+        state->s_exec = s;
+        state->passes = passes;
+        state->total_sweeps += (unsigned long long)s;
+        state->total_passes += (unsigned long long)passes;
+    }
+}
+
+// p_cur flips once per frame with a pressure solve (to the first pass's output buffer); a kernel of its own so that
+// no CTA of jacobi_settle_kernel can observe the new value.
+__global__ void jacobi_flip_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters) {
+    if (0.0f < frame->dt && iters > 0 && state->passes > 0) state->p_cur ^= 1;
+    phase_mark(state, 2);  // the pressure solve ends here
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -626,6 +717,9 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
     P.pass = pass; P.s0 = s0; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
     P.ext_lo = ext_lo; P.ext_hi = ext_hi;
+    P.copy_all = J.copy_all ? 1 : 0;
+    P.keep_lo = d.z_own0 > 0 ? 1 : 0;
+    P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
     const int nbricks = J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
     const int grid = nbricks < slots ? nbricks : slots;
@@ -634,6 +728,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
     W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np;
+    W.brick_flag = J.brick_flag;
     const bool late = S::kTileY != J.tile_y;  // the later passes' kernel of the mixed schedule stages a taller tile
     jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
         *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[0] : J.map_p[0]),
@@ -656,6 +751,10 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     J->mixed = fuse_t == 0;
     J->T = J->mixed ? 2 : fuse_t;
     J->T_late = J->mixed ? 4 : fuse_t;
+    // the first passes still relax many bricks (throughput: two CTAs per SM, T = 2); afterwards one brick chain per SM
+    // sets the pace (latency: T = 4 halves the number of launches)
+    J->n_early = J->mixed ? 4 : 1;
+    if (const char* e = getenv("FXB_EARLY")) J->n_early = std::max(1, atoi(e));  // tuning knob
     const int T = J->T;
     // tile shape: the one whose tiles cover the least area beyond the grid (compute and staging are per tile cell)
     const long long wide = (long long)tiles_for(d.nx, 120) * 128 * tiles_for(d.ny, 16 - 2 * T) * 16;
@@ -694,13 +793,13 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
 
 int fused_jacobi_passes(const FusedJacobi& J, int iters) {
     if (iters <= 0) return 0;
-    if (iters <= J.T) return 1;
-    return 1 + (iters - J.T + J.T_late - 1) / J.T_late;
+    if (iters <= J.n_early * J.T) return (iters + J.T - 1) / J.T;
+    return J.n_early + (iters - J.n_early * J.T + J.T_late - 1) / J.T_late;
 }
 
 void fused_jacobi_pass_spec(const FusedJacobi& J, int pass, int* T, int* s0) {
-    *T = pass == 0 ? J.T : J.T_late;
-    *s0 = pass == 0 ? 0 : J.T + (pass - 1) * J.T_late;
+    *T = pass < J.n_early ? J.T : J.T_late;
+    *s0 = pass < J.n_early ? pass * J.T : J.n_early * J.T + (pass - J.n_early) * J.T_late;
 }
 
 size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty * J.nzc; }
@@ -717,7 +816,7 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
     int T, s0;
     fused_jacobi_pass_spec(J, pass, &T, &s0);
 #define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream)
-    if (J.mixed && pass > 0) {
+    if (J.mixed && pass >= J.n_early) {
         if (J.narrow) FXB_LAUNCH(NarrowLate);
         FXB_LAUNCH(WideLate);
     }
@@ -729,6 +828,42 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
     }
 #undef FXB_LAUNCH
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                 int iters, int force_passes, cudaStream_t stream) {
+    PassParams P{};
+    P.nx = d.nx; P.ny = d.ny; P.pitch = d.pitch; P.nz_alloc = d.nz_alloc;
+    P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
+    P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
+    P.levels_total = iters;
+    WorkLists W;
+    const int np = FusedJacobi::kMaxPasses + 1;
+    W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
+    W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
+    W.relax_count = J.work_count; W.copy_count = J.work_count + np;
+    W.brick_flag = J.brick_flag;
+    const int grid = J.num_sms * 2;
+    // geometry of the own region only (shared by every shape of the schedule)
+    if (J.narrow) {
+        switch (J.T) {
+            case 1: jacobi_settle_kernel<NarrowU<1>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 2: jacobi_settle_kernel<NarrowU<2>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 3: jacobi_settle_kernel<NarrowU<3>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            default: jacobi_settle_kernel<NarrowU<4>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+        }
+    } else {
+        switch (J.T) {
+            case 1: jacobi_settle_kernel<WideU<1>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 2: jacobi_settle_kernel<WideU<2>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 3: jacobi_settle_kernel<WideU<3>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            default: jacobi_settle_kernel<WideU<4>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    jacobi_flip_kernel<<<1, 1, 0, stream>>>(frame, state, iters);
+    return cudaGetLastError();
 }
 
 }  // namespace fxb

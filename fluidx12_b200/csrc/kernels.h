@@ -31,8 +31,7 @@ void launch_divergence(const Domain& d, const FrameParams* frame, const void* ve
 void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const float* rhs, float* p0, float* p1,
                                 unsigned char* active, StepState* state, int sweep, int early_exit,
                                 cudaStream_t stream);
-void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int fuse_t, int fuse_t_late,
-                         int force_passes, cudaStream_t stream);
+void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,
                      void* vel_out, const StepState* state, cudaStream_t stream);
 
@@ -49,6 +48,10 @@ struct FusedJacobi {
     int T = 0;                 // sweeps fused by the first pass (1..4)
     int T_late = 0;            // sweeps fused by every later pass (the mixed default schedule: 2, then 4)
     bool mixed = false;        // default schedule: the later passes run the latency-optimised kernel shape
+    int n_early = 1;           // passes that fuse T sweeps; every later pass fuses T_late
+    bool copy_all = false;     // copy every brick that froze in the first pass (grouped multi-GPU exchange), not only those
+                               // next to an active brick
+    int* brick_flag = nullptr; // [bricks] per frame: bit 0 = froze in the first pass, bit 1 = next to a still-active brick
     bool narrow = false;       // tile 64 x 32 (a warp covers two row pairs) instead of 128 x 16
     int tile_x = 128, tile_y = 16;  // tile of the first pass
     int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
@@ -72,6 +75,9 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);
+// After the last pass: copies what the last executed pass left in the wrong buffer, s_exec / pass count, flips p_cur.
+cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                 int iters, int force_passes, cudaStream_t stream);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
                                      cudaStream_t stream);

@@ -52,7 +52,7 @@ __device__ __forceinline__ Rows rows_of(const Domain& d, int x0, int y, int z) {
 // plane below and the whole texels of the centre plane in registers, so every texel is fetched from L2/HBM once
 // (plus the chunk's two end planes); only the y neighbours (rows y-1, y+1 of the centre plane, loaded a moment
 // earlier by the neighbouring threads of the CTA) and the two x-edge texels come through L1 again.
-constexpr int kDivPlanes = 16;
+constexpr int kDivPlanes = 8;
 
 __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const FrameParams* __restrict__ frame,
                                                               const uint2* __restrict__ vel,
@@ -76,12 +76,30 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const Fr
     Quad8 below = load_quad8(vel, zoff(max(z_begin, 1) - 1) + row_c);
     float fz[4] = {h_lo(below.a.y), h_lo(below.a.w), h_lo(below.b.y), h_lo(below.b.w)};
     Quad8 c = load_quad8(vel, zoff(z_begin) + row_c);
+    // Software pipeline: everything plane z needs besides `c` (the plane above, the rows y-1 / y+1 and the two x-edge
+    // texels of plane z) is fetched one iteration ahead, so a thread always has a full plane of loads in flight.
+    struct Fetch {
+        Quad8 b, u, dn;
+        unsigned short el, er;
+    };
+    auto fetch = [&](int z) {
+        Fetch f;
+        const unsigned zc = zoff(z);
+        f.b = load_quad8(vel, zoff(min(z + 1, d.nz - 1)) + row_c);  // plane above (clamped)
+        f.u = load_quad8(vel, zc + row_u);
+        f.dn = load_quad8(vel, zc + row_d);
+        f.el = __ldg(vs + 4 * (size_t)(zc + row0 + xl));
+        f.er = __ldg(vs + 4 * (size_t)(zc + row0 + xr));
+        return f;
+    };
+    Fetch cur = fetch(z_begin);
     for (int z = z_begin; z < z_end; ++z) {
         const unsigned zc = zoff(z);
-        const Quad8 b = load_quad8(vel, zoff(min(z + 1, d.nz - 1)) + row_c);  // plane above (clamped)
-        const Quad8 u = load_quad8(vel, zc + row_u), dn = load_quad8(vel, zc + row_d);
-        const float vx[6] = {half_bits_to_float(__ldg(vs + 4 * (size_t)(zc + row0 + xl))), h_lo(c.a.x), h_lo(c.a.z),
-                             h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(__ldg(vs + 4 * (size_t)(zc + row0 + xr)))};
+        Fetch nxt = cur;
+        if (z + 1 < z_end) nxt = fetch(z + 1);
+        const Quad8 &b = cur.b, &u = cur.u, &dn = cur.dn;
+        const float vx[6] = {half_bits_to_float(cur.el), h_lo(c.a.x), h_lo(c.a.z),
+                             h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(cur.er)};
         const float uy[4] = {h_hi(u.a.x), h_hi(u.a.z), h_hi(u.b.x), h_hi(u.b.z)};
         const float dy[4] = {h_hi(dn.a.x), h_hi(dn.a.z), h_hi(dn.b.x), h_hi(dn.b.z)};
         const float bz[4] = {h_lo(b.a.y), h_lo(b.a.w), h_lo(b.b.y), h_lo(b.b.w)};
@@ -98,7 +116,8 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const Fr
         *reinterpret_cast<float4*>(rhs + zc + row_c) = make_float4(out[0], out[1], out[2], out[3]);
         // march: the centre plane becomes the plane below, the plane above becomes the centre
         fz[0] = h_lo(c.a.y); fz[1] = h_lo(c.a.w); fz[2] = h_lo(c.b.y); fz[3] = h_lo(c.b.w);
-        c = b;
+        c = cur.b;
+        cur = nxt;
     }
 }
 

@@ -112,23 +112,19 @@ __global__ void __launch_bounds__(256) jacobi_sweep_simple_kernel(Domain d, cons
     if (threadIdx.x == 0 && threadIdx.y == 0 && cnt) atomicAdd(&state->active_after[sweep], (unsigned long long)cnt);
 }
 
-// t_first / t_late: sweeps per pressure ping-pong flip of the first / every later pass (1, 1 for the simple path; the
-// fused passes' T).  force_passes >= 0 (multi-GPU): every rank ran exactly that many passes, whatever the counters say.
-__global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters,
-                                    int t_first, int t_late, int force_passes) {
+// The per-sweep path flips the pressure ping-pong once per sweep.
+__global__ void finish_solve_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters) {
     if (threadIdx.x != 0) return;
     int s = 0;
     if (0.0f < frame->dt && iters > 0) {
         s = 1;
         while (s < iters && state->active_after[s - 1] != 0ull) ++s;
     }
-    int passes = s <= t_first ? (s > 0 ? 1 : 0) : 1 + (s - t_first + t_late - 1) / t_late;
-    if (force_passes >= 0 && 0.0f < frame->dt) passes = force_passes;
     state->s_exec = s;
-    state->passes = passes;
-    state->p_cur = (state->p_cur + passes) & 1;
+    state->passes = s;
+    state->p_cur = (state->p_cur + s) & 1;
     state->total_sweeps += (unsigned long long)s;
-    state->total_passes += (unsigned long long)passes;
+    state->total_passes += (unsigned long long)s;
     phase_mark(state, 2);  // the pressure solve ends here
 }
 
@@ -196,9 +192,8 @@ void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const
                                                                           early_exit);
 }
 
-void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, int t_first, int t_late,
-                         int force_passes, cudaStream_t stream) {
-    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters, t_first, t_late, force_passes);
+void launch_finish_solve(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream) {
+    finish_solve_kernel<<<1, 32, 0, stream>>>(frame, state, iters);
 }
 
 void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_in, const float* p0, const float* p1,

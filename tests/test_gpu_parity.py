@@ -163,8 +163,8 @@ def test_fused_jacobi_every_T_and_ragged_tiles(fx, oracle_mod, n, fuse_t):
 @pytest.mark.parametrize("tile", ["64", "128"])
 @pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3)])
 def test_default_schedule_on_both_tile_widths(fx, oracle_mod, monkeypatch, n, tile):
-    """The default schedule (first pass T = 2, later passes T = 4 with the latency-optimised kernel shape, one brick
-    grid for both) with the tile width forced to 64 and to 128 cells (normally chosen per grid)."""
+    """The default schedule (four passes of T = 2, later passes T = 4 with the latency-optimised kernel shape, one
+    brick grid for both; bricks that froze in the first pass are copied only next to active bricks) with the tile width forced to 64 and to 128 cells (normally chosen per grid)."""
     monkeypatch.setenv("FXB_TILE", tile)
     f, o = make_pair(fx, oracle_mod, n)
     monkeypatch.delenv("FXB_TILE")
@@ -175,7 +175,8 @@ def test_default_schedule_on_both_tile_widths(fx, oracle_mod, monkeypatch, n, ti
     for _ in range(4):
         f.step(dt); o.step(dt)
         assert f.stats().s_exec == o.s_exec
-        assert f.stats().jacobi_passes == (1 + -(-(o.s_exec - 2) // 4) if o.s_exec > 2 else 1)
+        want = -(-o.s_exec // 2) if o.s_exec <= 8 else 4 + -(-(o.s_exec - 8) // 4)  # four passes of 2 sweeps, then 4 each
+        assert f.stats().jacobi_passes == want, (f.stats().jacobi_passes, o.s_exec)
         compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
     # cells still active after sweep k + 1 (GPU) = cells entering sweep k + 1 (oracle)
     s = o.s_exec
