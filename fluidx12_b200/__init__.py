@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     FIELD_PRESSURE,
     FIELD_VELOCITY,
     FIELD_VELOCITY_ADVECTED,
+    HALO_FUSED,
     HALO_NCCL,
     HALO_PEER,
     FluidError,
@@ -35,5 +36,5 @@ from . import volume  # noqa: F401
 __all__ = [
     "Fluid", "FluidEZ", "FluidError", "FxbConfig", "FxbStats", "dt_for_grid", "lib", "lib_path", "slab_range", "halo_plan", "gather_plan", "volume", "FxbVolumeHeader", "FxbLightParams", "FxbViewParams",
     "ADDRESS_MIRROR", "ADDRESS_CLAMP", "FIELD_VELOCITY", "FIELD_COLOR", "FIELD_PRESSURE",
-    "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV", "HALO_PEER", "HALO_NCCL",
+    "FIELD_VELOCITY_ADVECTED", "FIELD_COLOR_PREV", "HALO_PEER", "HALO_NCCL", "HALO_FUSED",
 ]

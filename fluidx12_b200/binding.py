@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libfluidx_b200.so"
 
 ADDRESS_MIRROR, ADDRESS_CLAMP = 0, 1
-HALO_PEER, HALO_NCCL = 0, 1
+HALO_PEER, HALO_NCCL, HALO_FUSED = 0, 1, 2
 FIELD_VELOCITY, FIELD_COLOR, FIELD_PRESSURE, FIELD_VELOCITY_ADVECTED, FIELD_COLOR_PREV = range(5)
 
 FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_OVERFLOW, FXB_ERR_IO = 0, -1, -2, -3, -4, -5, -6

@@ -76,16 +76,24 @@ struct AdvectArgs {
     Emitter em;
     int clamp_mode;
     int zv0, zv1;  // global planes [zv0, zv1) hold valid input: the owned planes plus the exchanged halo (or the grid's faces)
+    // fused halos (common.cuh PeerView): planes within `reach` of an interior face read halo planes, and the same
+    // planes of the colour output (the first / last plane of the velocity output) are also stored into the neighbour
+    int reach;
+    uint2 *vel_out_lo, *vel_out_hi;  // the neighbours' m_velocities[1]
+    uint2 *col_lo[2], *col_hi[2];    // the neighbours' m_colors[0], m_colors[1]
+};
+
+struct Texels {
+    uint2 vel, col;
 };
 
 // One voxel, any case (taps inside or outside the grid, either sampler addressing mode).  `sv` / `sc`: the voxel's
 // own velocity / colour texel (already loaded).
-__device__ __forceinline__ void advect_voxel(const AdvectArgs& A, const float dt, const float atten,
-                                             const uint2* __restrict__ vel_in, const uint2* __restrict__ col_in,
-                                             uint2* __restrict__ col_out, uint2* __restrict__ vel_out,
-                                             StepState* __restrict__ state, const int x, const int y, const int z,
-                                             const float px, const float py, const unsigned self, const uint2 sv,
-                                             const uint2 sc) {
+__device__ __forceinline__ Texels advect_voxel(const AdvectArgs& A, const float dt, const float atten,
+                                               const uint2* __restrict__ vel_in, const uint2* __restrict__ col_in,
+                                               StepState* __restrict__ state, const int x, const int y, const int z,
+                                               const float px, const float py, const unsigned self, const uint2 sv,
+                                               const uint2 sc) {
     const Domain& d = A.d;
     const float pz = __ldg(A.tab.pos[2] + z);
     const float fnx = (float)d.nx, fny = (float)d.ny, fnz = (float)d.nz;
@@ -187,22 +195,31 @@ __device__ __forceinline__ void advect_voxel(const AdvectArgs& A, const float dt
 
     const float2 at2 = make_float2(atten, atten);
     u.lo = mul2(u.lo, at2);
-    vel_out[self] = pack_texel4(u.lo.x, u.lo.y, u.hi.x * atten, 0.0f);
     c.lo = mul2(c.lo, at2);
     c.hi = mul2(c.hi, at2);
-    col_out[self] = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
+    Texels out;
+    out.vel = pack_texel4(u.lo.x, u.lo.y, u.hi.x * atten, 0.0f);
+    out.col = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
+    return out;
 }
 
 __global__ void __launch_bounds__(256, 4)
-advect_kernel(const __grid_constant__ AdvectArgs A, const FrameParams* __restrict__ frame,
-              const uint2* __restrict__ vel_in, uint2* col0, uint2* col1,  // m_colors[0], m_colors[1]
+advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ PeerView pv,
+              const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in, uint2* col0,
+              uint2* col1,  // m_colors[0], m_colors[1]
               uint2* __restrict__ vel_out, StepState* __restrict__ state) {
     const Domain& d = A.d;
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int z0 = d.z_own0 + blockIdx.z * kZ;  // global plane
-    if (x >= d.nx || y >= d.ny) return;
     const int z1 = min(z0 + kZ, d.z_own1);
+    // fused halos: the planes next to an interior face wait for the neighbour's previous frame (event m = 0)
+    const bool near_lo = pv.has_lo && z0 < d.z_own0 + A.reach, near_hi = pv.has_hi && z1 > d.z_own1 - A.reach;
+    if (near_lo || near_hi) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) peer_wait(pv, frame->epoch_base, near_lo, near_hi);
+        __syncthreads();
+    }
+    if (x >= d.nx || y >= d.ny) return;
 
     const float dt = frame->dt;
     const int parity = frame->parity;
@@ -212,6 +229,7 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const FrameParams* __restric
     const float atten = fmaxf(__fmaf_rn(-dt, 0.200000003f, 1.0f), 0.0f);
     const unsigned plane = (unsigned)d.pitch * d.ny;
     unsigned self = ((unsigned)(z0 - d.z_first) * d.ny + y) * d.pitch + x;
+    // the field is written by the neighbours between frames (fused halos): no non-coherent loads of halo planes
     uint2 sv = __ldg(vel_in + self), sc = __ldg(col_in + self);
     for (int z = z0; z < z1; ++z) {
         uint2 nv = sv, nc = sc;
@@ -219,7 +237,19 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const FrameParams* __restric
             nv = __ldg(vel_in + self + plane);
             nc = __ldg(col_in + self + plane);
         }
-        advect_voxel(A, dt, atten, vel_in, col_in, col_out, vel_out, state, x, y, z, px, py, self, sv, sc);
+        const Texels t = advect_voxel(A, dt, atten, vel_in, col_in, state, x, y, z, px, py, self, sv, sc);
+        vel_out[self] = t.vel;
+        col_out[self] = t.col;
+        if (near_lo) {
+            const long long at = (long long)self + (long long)pv.dz_lo * plane;
+            if (z == d.z_own0) A.vel_out_lo[at] = t.vel;
+            if (z < d.z_own0 + A.reach) A.col_lo[parity][at] = t.col;
+        }
+        if (near_hi) {
+            const long long at = (long long)self + (long long)pv.dz_hi * plane;
+            if (z == d.z_own1 - 1) A.vel_out_hi[at] = t.vel;
+            if (z >= d.z_own1 - A.reach) A.col_hi[parity][at] = t.col;
+        }
         sv = nv;
         sc = nc;
         self += plane;
@@ -230,7 +260,7 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const FrameParams* __restric
 
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
                    void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int h_adv,
-                   cudaStream_t stream) {
+                   const PeerView& pv, const AdvectPeers& peers, cudaStream_t stream) {
     AdvectArgs A;
     A.d = d; A.tab = tab; A.em = em; A.clamp_mode = clamp_mode;
     // valid input planes: the owned ones plus the h_adv + 1 exchanged on each interior face (clipped to the grid)
@@ -238,9 +268,15 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
     A.zv1 = d.z_own1 < d.nz ? (d.z_own1 + h_adv + 1 < d.nz ? d.z_own1 + h_adv + 1 : d.nz) : d.nz;
     if (A.zv0 < d.z_first) A.zv0 = d.z_first;
     if (A.zv1 > d.z_first + d.nz_alloc) A.zv1 = d.z_first + d.nz_alloc;
+    A.reach = h_adv + 1;
+    A.vel_out_lo = (uint2*)peers.vel_out[0]; A.vel_out_hi = (uint2*)peers.vel_out[1];
+    for (int i = 0; i < 2; ++i) {
+        A.col_lo[i] = (uint2*)peers.col[0][i];
+        A.col_hi[i] = (uint2*)peers.col[1][i];
+    }
     const dim3 block(32, 8, 1);
     const dim3 grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.z_own1 - d.z_own0 + kZ - 1) / kZ);
-    advect_kernel<<<grid, block, 0, stream>>>(A, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
+    advect_kernel<<<grid, block, 0, stream>>>(A, pv, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
                                               (uint2*)vel_out, state);
 }
 

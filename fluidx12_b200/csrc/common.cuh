@@ -29,6 +29,7 @@ struct Domain {
 struct FrameParams {
     float dt;
     int parity;  // m_frameParity: advect writes colour[parity], reads colour[!parity]
+    unsigned long long epoch_base;  // multi-GPU: kEventsPerFrame x the frame's index (see PeerView)
 };
 
 // Device-side per-step solver state and counters.
@@ -42,9 +43,58 @@ struct StepState {
     unsigned long long bricks_processed;  // cumulative: bricks fully relaxed by fused passes
     unsigned long long bricks_copied;     // cumulative: frozen bricks copied once to the other buffer
     unsigned long long active_after[128];  // [k] = cells still active after sweep k (this rank)
+    int done_ctas;                       // CTAs of the running fused pass that have finished (multi-GPU event publish)
+    int pad0;
     unsigned long long phase_ns[8];      // cumulative device time per phase (phase marks; fxb_config.phase_timing)
     unsigned long long mark_ns;          // %globaltimer of the last phase mark
 };
+
+// ---- fused halos (multi-GPU, fxb_config.halo_backend = FXB_HALO_FUSED) ------------------------------------------
+// Every kernel of the step writes the planes next to an interior slab face twice: into its own array and — the same
+// store instruction stream, over NVLink — into the halo planes of the neighbouring rank's array (mapped through CUDA
+// IPC).  There is no exchange kernel and no collective on the data path.  Ordering uses ONE monotone event counter per
+// rank: the kernels of a frame are numbered m = 0 (advect), 1 (divergence), 2 + k (fused pass k), 2 + n (settle),
+// 3 + n (gradient), the same on every rank; a rank publishes epoch_base + m + 1 into both neighbours' memory when
+// kernel m has completed (the gradient publishes the next frame's base), and the parts of kernel m that read halo
+// planes or write into a neighbour wait until that neighbour's counter has reached epoch_base + m: the neighbour has
+// then finished kernel m - 1, i.e. its pushes into this rank's halos have landed and it no longer reads the halo planes
+// this kernel is about to overwrite.  Everything away from the slab faces runs without waiting.
+constexpr unsigned long long kEventsPerFrame = 128;
+
+struct PeerView {
+    int has_lo, has_hi;          // an interior face below / above (both 0 on a single GPU: all of this is skipped)
+    int dz_lo, dz_hi;            // local plane index in the neighbour's arrays = local plane index here + dz
+    unsigned long long* events;  // [2] in this rank's memory: the counters rank - 1 / rank + 1 publish
+    unsigned long long* ev_lo;   // rank - 1's event words (this rank writes [1] there: it is its upper neighbour)
+    unsigned long long* ev_hi;   // rank + 1's event words (this rank writes [0])
+    unsigned long long* error;   // sticky time-out flag (this rank's memory)
+    long long timeout_cycles;
+};
+
+// One thread waits until the neighbours named have completed every kernel before `need`.  Never hangs the device: a
+// wait that exceeds the limit records the failure (fxb_sync reports it) and goes on.
+__device__ __forceinline__ void peer_wait(const PeerView& pv, const unsigned long long need, const bool lo, const bool hi) {
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? (lo && pv.has_lo) : (hi && pv.has_hi))) continue;
+        volatile unsigned long long* w = pv.events + side;
+        while (*w < need) {
+            if (clock64() - t0 > pv.timeout_cycles) {
+                *pv.error = 1ull;
+                break;
+            }
+            __nanosleep(32);
+        }
+    }
+    __threadfence_system();  // acquire: what the neighbour wrote before publishing is visible to what follows
+}
+
+// One thread, after everything the kernel wrote (here and into the neighbours) is complete.
+__device__ __forceinline__ void peer_publish(const PeerView& pv, const unsigned long long value) {
+    __threadfence_system();
+    if (pv.has_lo) *reinterpret_cast<volatile unsigned long long*>(pv.ev_lo + 1) = value;
+    if (pv.has_hi) *reinterpret_cast<volatile unsigned long long*>(pv.ev_hi + 0) = value;
+}
 
 // Phase marks: the device time since the previous mark is added to StepState::phase_ns[slot] (slot < 0: start of a
 // step).  The step's own one-thread kernels (frame constants, begin-step, finish-solve) carry three of the five marks;

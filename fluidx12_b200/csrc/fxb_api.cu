@@ -25,9 +25,11 @@ thread_local std::string g_last_error;
 
 int fail(int code, const std::string& msg) { return fxb::api_fail(code, msg); }
 
-__global__ void set_frame_kernel(fxb::FrameParams* frame, fxb::StepState* state, float dt, int parity) {
+__global__ void set_frame_kernel(fxb::FrameParams* frame, fxb::StepState* state, float dt, int parity,
+                                 unsigned long long frame_index) {
     frame->dt = dt;
     frame->parity = parity;
+    frame->epoch_base = frame_index * fxb::kEventsPerFrame;  // fused halos: the event numbers of this frame's kernels
     fxb::phase_mark(state, -1);  // a step starts here
 }
 
@@ -125,7 +127,13 @@ enum Phase { PH_ADVECT = 0, PH_DIVERGENCE, PH_JACOBI, PH_GRADIENT, PH_COUNT };
 // Phase marks (common.cuh): with fxb_config.phase_timing a one-thread kernel closes the divergence and the gradient
 // phase (the other marks ride on the step's own one-thread kernels), so the per-phase device times of the very steps a
 // caller times are available afterwards (fxb_get_phase_times) — also when the step runs as a captured graph.
-__global__ void phase_mark_kernel(fxb::StepState* state, int slot) { fxb::phase_mark(state, slot); }
+// With fused halos the same kernel publishes the event of the kernel before it (divergence: epoch_base + 2, gradient:
+// the next frame's base).
+__global__ void phase_mark_kernel(fxb::StepState* state, int slot, const fxb::FrameParams* frame,
+                                  const __grid_constant__ fxb::PeerView pv, unsigned long long event_offset) {
+    if (slot >= 0) fxb::phase_mark(state, slot);
+    if (pv.has_lo || pv.has_hi) fxb::peer_publish(pv, frame->epoch_base + event_offset);
+}
 
 // State checksum (fxb_state_checksum): per field the wrap-around sum over the rank's own voxels of a 64-bit mix of the
 // voxel's GLOBAL linear index and its bits, so the sums of all ranks of a z-slab run add up to the single-GPU value.
@@ -166,6 +174,7 @@ struct Enqueue {
     bool ok = true;
     std::string err;
     void halo(const fxb::HaloField* f, int n) {
+        if (fused()) return;  // every kernel stores its face planes into the neighbours itself (common.cuh PeerView)
         if (ok && !s->comm.exchange(s->dom, f, n, st)) { ok = false; err = "halo exchange: " + fxb::halo_last_error(); }
         if (s->comm.p2p.enabled) ++launches;
     }
@@ -173,9 +182,11 @@ struct Enqueue {
         if (ok && e != cudaSuccess) { ok = false; err = std::string(what) + ": " + cudaGetErrorString(e); }
         launches += n;
     }
-    void mark(int slot) {
-        if (!s->cfg.phase_timing) return;
-        phase_mark_kernel<<<1, 1, 0, st>>>(s->d_state, slot);
+    bool fused() const { return s->multi() && s->cfg.halo_backend == FXB_HALO_FUSED; }
+    // closes a phase: the phase mark (fxb_config.phase_timing) and, with fused halos, the event of the kernel before it
+    void mark(int slot, unsigned long long event_offset) {
+        if (!s->cfg.phase_timing && !fused()) return;
+        phase_mark_kernel<<<1, 1, 0, st>>>(s->d_state, s->cfg.phase_timing ? slot : -1, s->d_frame, s->pv, event_offset);
         launched(cudaGetLastError(), "phase_mark_kernel");
     }
 };
@@ -194,8 +205,9 @@ void enqueue_phase(Enqueue& q, int phase) {
             }
             // Fluid.cpp:358-375: vel[0], colour[!p] -> vel[1], colour[p]
             fxb::launch_advect(d, s->tab, s->d_frame, s->vel[0], s->col, s->vel[1], s->emitter, s->cfg.address_mode,
-                               s->d_state, s->h_adv, st);
-            fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, st);  // also the advection phase's mark
+                               s->d_state, s->h_adv, s->pv, s->advect_peers, st);
+            // also the advection phase's mark and, with fused halos, the event "advect complete"
+            fxb::launch_begin_step(s->d_frame, s->d_state, s->cfg.jacobi_iters, s->pv, st);
             q.launched(cudaGetLastError(), "advect_kernel", 2);
             break;
         case PH_DIVERGENCE:
@@ -203,10 +215,12 @@ void enqueue_phase(Enqueue& q, int phase) {
                 const fxb::HaloField f[1] = {{s->vel[1], s->plane_voxels() * 8, 1}};
                 q.halo(f, 1);
             }
-            if (s->quad) fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, st);
+            if (s->quad)
+                fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, s->pv, (float*)s->comm.peer_of(s->rhs, 0),
+                                            (float*)s->comm.peer_of(s->rhs, 1), std::max(s->jac.T, s->jac.T_late), st);
             else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
             q.launched(cudaGetLastError(), "divergence_kernel");
-            q.mark(1);
+            q.mark(1, 2);
             break;
         case PH_JACOBI:
             if (s->fused) {
@@ -239,7 +253,7 @@ void enqueue_phase(Enqueue& q, int phase) {
                         ext_hi = s->cfg.rank < s->cfg.nranks - 1 ? ext : 0;
                     }
                     q.launched(fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
-                                                             s->cfg.early_exit, s->multi(), ext_lo, ext_hi, st),
+                                                             s->cfg.early_exit, s->multi(), ext_lo, ext_hi, s->pv, st),
                                "jacobi_pass_kernel");
                 }
                 if (mg) {
@@ -251,7 +265,7 @@ void enqueue_phase(Enqueue& q, int phase) {
                     }
                 }
                 q.launched(fxb::launch_jacobi_settle(s->jac, d, s->d_frame, s->d_state, s->cfg.jacobi_iters,
-                                                     s->multi() ? npass : -1, st), "jacobi_settle_kernel", 2);
+                                                     s->multi() ? npass : -1, s->pv, st), "jacobi_settle_kernel", 2);
                 if (mg) {  // z neighbours of the final pressure (the first pass's output buffer) for the gradient
                     const fxb::HaloField f[1] = {{s->p[(s->p_cur_host + 1) & 1], s->plane_voxels() * 4, 1}};
                     q.halo(f, 1);
@@ -267,11 +281,13 @@ void enqueue_phase(Enqueue& q, int phase) {
         case PH_GRADIENT:
             // Fluid.cpp:378-408: vel[1] -> vel[0]
             if (s->quad)
-                fxb::launch_gradient_quad(d, s->tab, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
+                fxb::launch_gradient_quad(d, s->tab, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, s->pv,
+                                          s->comm.peer_of(s->vel[0], 0), s->comm.peer_of(s->vel[0], 1), s->h_adv + 1,
+                                          3 + (s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) : 0), st);
             else
                 fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
             q.launched(cudaGetLastError(), "gradient_kernel");
-            q.mark(3);
+            q.mark(3, fxb::kEventsPerFrame);
             break;
     }
 }
@@ -351,7 +367,7 @@ int fxb_config_default(fxb_config* cfg) {
     cfg->use_graph = 1;
     cfg->kernel_path = 0;
     cfg->phase_timing = 0;
-    cfg->halo_backend = FXB_HALO_PEER;
+    cfg->halo_backend = FXB_HALO_FUSED;
     cfg->jacobi_group = 0;
     cfg->nccl_unique_id = nullptr;
     return FXB_OK;
@@ -426,7 +442,11 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     const size_t n = s->alloc_voxels();
     // Peer-memory halos (FXB_P2P=1) map these buffers into the neighbours through CUDA IPC, and an IPC handle maps a
     // whole underlying allocation: small buffers are then given at least 2 MiB so that each is an allocation of its own.
-    const bool peer_halos = cfg->nranks > 1 && cfg->halo_backend == FXB_HALO_PEER;
+    if (cfg->halo_backend != FXB_HALO_FUSED && cfg->halo_backend != FXB_HALO_PEER && cfg->halo_backend != FXB_HALO_NCCL) {
+        delete s;
+        return fail(FXB_ERR_INVALID, "fxb_create: bad halo_backend");
+    }
+    const bool peer_halos = cfg->nranks > 1 && cfg->halo_backend != FXB_HALO_NCCL;
     const size_t ipc_min = peer_halos ? ((size_t)2 << 20) : 0;
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -494,13 +514,26 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         const int zf_hi = r < R - 1 ? std::max((r + 1) * nz / R - s->halo, 0) : 0;
         if (!s->comm.p2p_init(bufs.data(), (int)bufs.size(), zf_lo, zf_hi, s->own_stream))
             return cleanup_fail(fail(FXB_ERR_NCCL, "fxb_create: peer-memory halo setup failed: " + fxb::halo_last_error()));
+        if (cfg->halo_backend == FXB_HALO_FUSED) {
+            // fused halos: every kernel also stores its face planes into the neighbours' arrays (common.cuh PeerView)
+            s->pv = s->comm.peer_view(s->dom);
+            for (int side = 0; side < 2; ++side) {
+                s->advect_peers.vel_out[side] = s->comm.peer_of(s->vel[1], side);
+                for (int i = 0; i < 2; ++i) {
+                    s->advect_peers.col[side][i] = s->comm.peer_of(s->col[i], side);
+                    s->jac.peer_p[side][i] = (float*)s->comm.peer_of(s->p[i], side);
+                    s->jac.peer_m[side][i] = (unsigned char*)s->comm.peer_of(s->jac.mask[i], side);
+                }
+            }
+        }
     }
-    if (s->cfg.use_graph && !s->multi()) {
+    const bool one_graph = !s->multi() || cfg->halo_backend == FXB_HALO_FUSED;  // no host-side buffer selection in the step
+    if (s->cfg.use_graph && one_graph) {
         rc = capture_graph(s, 0, 0);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
         const int jl = s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) : s->cfg.jacobi_iters;
-        s->kernels_per_step = 1 + 1 + 2 + jl + (s->fused ? 2 : 1) + 1 + (s->cfg.phase_timing ? 2 : 0);
+        s->kernels_per_step = 1 + 1 + 2 + jl + (s->fused ? 2 : 1) + 1 + ((s->cfg.phase_timing || (s->multi() && cfg->halo_backend == FXB_HALO_FUSED)) ? 2 : 0);
     }
     if (s->multi()) {
         // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
@@ -569,9 +602,20 @@ int fxb_simulate(fxb_sim* s, void* cuda_stream) {
     if (!s) return fail(FXB_ERR_INVALID, "fxb_simulate: null handle");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     FXB_CUDA(cudaSetDevice(s->cfg.device));
-    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity);  // the CBSimulation upload (Fluid.cpp:288-290)
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity, s->steps);  // the CBSimulation upload (Fluid.cpp:288-290)
     const int npass = flips_per_step(s);
-    if (s->multi()) {
+    const bool fused_halos = s->multi() && s->cfg.halo_backend == FXB_HALO_FUSED;
+    if (fused_halos && s->halo_stale) {
+        // fxb_set_field changed own planes behind the neighbours' back: one plain exchange of everything a step reads
+        // from its halos before the step's own stores refresh them
+        const fxb::HaloField f[5] = {{s->vel[0], s->plane_voxels() * 8, s->halo}, {s->col[0], s->plane_voxels() * 8, s->halo},
+                                     {s->col[1], s->plane_voxels() * 8, s->halo}, {s->p[0], s->plane_voxels() * 4, s->halo},
+                                     {s->p[1], s->plane_voxels() * 4, s->halo}};
+        if (!s->comm.exchange(s->dom, f, 3, st) || !s->comm.exchange(s->dom, f + 3, 2, st))
+            return fail(FXB_ERR_NCCL, "fxb_simulate: halo refresh: " + fxb::halo_last_error());
+        s->halo_stale = false;
+    }
+    if (s->multi() && !fused_halos) {
         // the exchanges depend on dt > 0, the frame parity and the pressure parity: one graph per key, captured on
         // first use; a paused frame (dt <= 0) is enqueued directly
         const int a = s->parity, b = s->p_cur_host;
@@ -647,6 +691,7 @@ int fxb_set_field(fxb_sim* s, int field, const void* host, size_t bytes) {
     if (!dst) return fail(err, "fxb_set_field: bad field");
     if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_set_field: size mismatch");
     FXB_CUDA(cudaMemcpy(dst + s->own_offset() * eb, host, bytes, cudaMemcpyHostToDevice));
+    s->halo_stale = true;
     return FXB_OK;
 }
 
@@ -750,7 +795,7 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     FXB_CUDA(cudaSetDevice(s->cfg.device));
     cudaStream_t st = s->own_stream;
     FXB_CUDA(cudaDeviceSynchronize());
-    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity);
+    set_frame_kernel<<<1, 1, 0, st>>>(s->d_frame, s->d_state, s->dt, s->parity, s->steps);
     FXB_CUDA(cudaEventRecord(s->ev[0], st));
     Enqueue q{s, st};
     for (int ph = 0; ph < PH_COUNT; ++ph) {

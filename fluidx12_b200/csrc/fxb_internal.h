@@ -55,6 +55,9 @@ struct fxb_sim {
     cudaGraph_t graph[2][2] = {};
     cudaGraphExec_t graph_exec[2][2] = {};
     fxb::HaloComm comm;       // z-slab neighbours (nranks > 1)
+    fxb::PeerView pv{};       // fused halos (FXB_HALO_FUSED): neighbours' event words and plane offsets; zero otherwise
+    fxb::AdvectPeers advect_peers;
+    bool halo_stale = false;  // fxb_set_field since the last step: the neighbours' halo copies need one plain exchange
     int halo = 0;             // halo planes allocated on interior faces
     int h_adv = 0;            // advection halo (back-trace reach in planes)
     int jacobi_group = 1;     // multi-GPU: fused passes per pressure-halo exchange (fxb_config.jacobi_group)

@@ -265,6 +265,29 @@ int HaloComm::p2p_timed_out() const {
     return v != 0ull;
 }
 
+PeerView HaloComm::peer_view(const Domain& d) const {
+    PeerView pv{};
+    if (!p2p.enabled) return pv;
+    pv.has_lo = rank > 0 ? 1 : 0;
+    pv.has_hi = rank < nranks - 1 ? 1 : 0;
+    pv.dz_lo = d.z_first - p2p.z_first_lo;
+    pv.dz_hi = d.z_first - p2p.z_first_hi;
+    pv.events = p2p.flags + 8;
+    pv.ev_lo = pv.has_lo ? p2p.flags_lo + 8 : nullptr;
+    pv.ev_hi = pv.has_hi ? p2p.flags_hi + 8 : nullptr;
+    pv.error = p2p.flags + 4;
+    static const long long timeout_s = getenv("FXB_P2P_TIMEOUT_S") ? atoll(getenv("FXB_P2P_TIMEOUT_S")) : 30;
+    pv.timeout_cycles = timeout_s * 2000000000ll;
+    return pv;
+}
+
+void* HaloComm::peer_of(const void* local, int side) const {
+    if (!p2p.enabled) return nullptr;
+    for (int k = 0; k < p2p.nbuf; ++k)
+        if (p2p.local[k] == local) return side == 0 ? p2p.peer_lo[k] : p2p.peer_hi[k];
+    return nullptr;
+}
+
 // Exchanges `depth` planes of every listed field with the z-1 and z+1 neighbours.
 bool HaloComm::exchange(const Domain& d, const HaloField* fields, int nfields, cudaStream_t stream) {
     if (nranks <= 1) return true;

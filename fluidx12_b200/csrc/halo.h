@@ -57,6 +57,10 @@ struct HaloComm {
     bool p2p_init(void* const* buffers, int nbuffers, int z_first_lo, int z_first_hi, cudaStream_t stream);
     // 1 when a wait of the peer-memory exchange gave up (a neighbour never published its epoch); sticky.
     int p2p_timed_out() const;
+    // Fused halos (common.cuh PeerView): the event words live next to the exchange's flag words ([8], [9]); the
+    // neighbours' copy of a registered local buffer (side 0: rank - 1, side 1: rank + 1), nullptr at a grid face.
+    PeerView peer_view(const Domain& d) const;
+    void* peer_of(const void* local, int side) const;
 };
 
 bool halo_unique_id(void* out128);

@@ -43,17 +43,18 @@ namespace {
 
 constexpr float kInv6 = 0.166666672f;
 constexpr float kEps = 0.00100000005f;
-constexpr int kRows = 2;   // rows per thread
 constexpr int kHaloX = 4;  // one quad
 
 // Compile-time shape of one kernel variant.
 //   T     sweeps fused per pass;  LX lanes per tile row (32: tile 128 wide, 16: tile 64 wide; a warp then covers
-//   32/LX row pairs);  WARPS warps per CTA;  DEPTH TMA bundles in flight ahead of the one being consumed.
-template <int T_, int LX_, int WARPS_, int DEPTH_, int CTAS_>
+//   32/LX row groups);  WARPS warps per CTA;  DEPTH TMA bundles in flight ahead of the one being consumed;  ROWS rows
+//   per thread (2: fewer instructions per cell, for the passes that relax many bricks; 1: twice the warps on a tile,
+//   half the dependent work per warp, for the passes in which one brick chain per SM sets the pace).
+template <int T_, int LX_, int WARPS_, int DEPTH_, int CTAS_, int ROWS_ = 2>
 struct Shape {
-    static constexpr int T = T_, LX = LX_, kWarps = WARPS_, kDepth = DEPTH_, kCtasPerSm = CTAS_;
-    static constexpr int kSub = 32 / LX_;               // row pairs per warp
-    static constexpr int kWarpRows = kRows * kSub;
+    static constexpr int T = T_, LX = LX_, kWarps = WARPS_, kDepth = DEPTH_, kCtasPerSm = CTAS_, kRows = ROWS_;
+    static constexpr int kSub = 32 / LX_;               // row groups per warp
+    static constexpr int kWarpRows = ROWS_ * kSub;
     static constexpr int kThreads = 32 * WARPS_;
     static constexpr int kTileX = 4 * LX_, kTileY = WARPS_ * kWarpRows;
     static constexpr int kOutX = kTileX - 2 * kHaloX, kOutY = kTileY - 2 * T_;
@@ -65,6 +66,7 @@ struct Shape {
     static constexpr size_t kFloats = (size_t)(kPSlots + kRSlots + kPubPlanes) * kPlane;
     static constexpr size_t kBytes = kFloats * sizeof(float) + 64;  // + barriers
     static_assert(LX_ == 32 || LX_ == 16, "tile rows are 32 or 16 lanes wide");
+    static_assert(ROWS_ == 1 || ROWS_ == 2, "rows per thread");
     static_assert(kBars <= 8, "barrier slots");
     static_assert((kBytes + 1024) * CTAS_ <= 233472, "shared memory budget (228 KB per SM, 1 KB reserved per CTA)");
     static_assert(kOutY > 0 && kOutX % 8 == 0, "own region must be a whole number of mask bytes wide");
@@ -115,6 +117,8 @@ struct PassParams {
     int ext_lo, ext_hi;    // multi-GPU: planes below / above the owned range to relax redundantly in this pass
     int copy_all;          // 1: every brick that froze in the first pass is copied; 0: only those next to an active brick
     int keep_lo, keep_hi;  // multi-GPU: bricks of the lowest / highest layer are always copied (a neighbour rank reads them)
+    int event;             // fused halos: this kernel's number m in the frame (common.cuh PeerView)
+    int push_depth;        // fused halos: own planes next to an interior face that are also stored into the neighbour
 };
 
 struct WorkLists {
@@ -123,6 +127,13 @@ struct WorkLists {
     int* relax_count;  // [pass]
     int* copy_count;   // [pass]
     int* brick_flag;   // [bricks] first pass: bit 0 = all cells froze, bit 1 = a brick next to it is still active
+};
+
+// Fused halos: the neighbours' copies of the pressure and freeze-mask ping-pong buffers ([side][buffer], side 0 =
+// rank - 1, side 1 = rank + 1; nullptr at a grid face / on a single GPU).
+struct JacobiPeers {
+    float* p[2][2];
+    unsigned char* m[2][2];
 };
 
 // One work item of a pass: a brick of this rank's own planes (brick >= 0; tracked in the work lists and the freeze
@@ -161,38 +172,58 @@ __device__ __forceinline__ Item ext_item(const PassParams& P, const int e) {
     return it;
 }
 
+// Where the stores of plane z of a pass's output also go (fused halos): side 0 / 1 when the plane is within
+// push_depth of the interior face below / above.
+__device__ __forceinline__ bool pushes_lo(const PeerView& pv, const PassParams& P, int z) {
+    return pv.has_lo && z < P.z_out0 + P.push_depth;
+}
+__device__ __forceinline__ bool pushes_hi(const PeerView& pv, const PassParams& P, int z) {
+    return pv.has_hi && z >= P.z_out1 - P.push_depth;
+}
+
 // A brick whose cells all froze during pass p-1 holds its final values in that pass's output buffer only.  Pass p
 // copies its own region once into the other buffer (and clears the other mask buffer), after which the brick is
 // final in both ping-pong buffers and is never touched again in this frame.  Pure streaming (8 B/cell), eight
-// independent 16-byte loads in flight per thread.
+// independent 16-byte loads in flight per thread.  Planes next to an interior slab face go to the neighbour as well.
 template <class S>
 __device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, float* __restrict__ p_out,
-                                               unsigned char* __restrict__ m_out, const PassParams& P,
-                                               const int brick) {
+                                               unsigned char* __restrict__ m_out, const PassParams& P, const int brick,
+                                               const PeerView& pv, const JacobiPeers& peers, const int pi,
+                                               const int mi) {  // pi / mi: which of the neighbours' p / mask buffers
     const int tid = threadIdx.x, nxb = P.pitch >> 3;
     const Item it = own_item<S>(P, brick);
     const int x_lo = it.gx0 + kHaloX, y_lo = it.gy0 + S::T;
     const int rows = min(S::kOutY, P.ny - y_lo), planes = it.ze - it.zs;
     const int qpr = (min(S::kOutX, P.nx - x_lo) + 3) >> 2;  // float4 per row (the last one may reach into the row padding)
     const int total = planes * rows * qpr;
+    const long long plane_f = (long long)P.ny * P.pitch, plane_b = (long long)P.ny * nxb;
     for (int base = tid; base < total; base += 8 * S::kThreads) {
         float4 v[8];
         size_t at[8];
+        int zz[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = base + u * S::kThreads;
             const int xq = i % qpr, rz = i / qpr;
-            at[u] = ((size_t)(it.zs + rz / rows) * P.ny + (y_lo + rz % rows)) * P.pitch + x_lo + 4 * xq;
+            zz[u] = it.zs + rz / rows;
+            at[u] = ((size_t)zz[u] * P.ny + (y_lo + rz % rows)) * P.pitch + x_lo + 4 * xq;
             if (i < total) v[u] = __ldcs(reinterpret_cast<const float4*>(p_in + at[u]));
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (base + u * S::kThreads < total) *reinterpret_cast<float4*>(p_out + at[u]) = v[u];
+            if (base + u * S::kThreads < total) {
+                *reinterpret_cast<float4*>(p_out + at[u]) = v[u];
+                if (pushes_lo(pv, P, zz[u])) *reinterpret_cast<float4*>(peers.p[0][pi] + (long long)at[u] + pv.dz_lo * plane_f) = v[u];
+                if (pushes_hi(pv, P, zz[u])) *reinterpret_cast<float4*>(peers.p[1][pi] + (long long)at[u] + pv.dz_hi * plane_f) = v[u];
+            }
     }
     const int bpr = (qpr + 1) >> 1;  // mask bytes per row
     for (int i = tid; i < planes * rows * bpr; i += S::kThreads) {
-        const int xb = i % bpr, rz = i / bpr;
-        m_out[((size_t)(it.zs + rz / rows) * P.ny + (y_lo + rz % rows)) * nxb + (x_lo >> 3) + xb] = 0;
+        const int xb = i % bpr, rz = i / bpr, z = it.zs + rz / rows;
+        const size_t at = ((size_t)z * P.ny + (y_lo + rz % rows)) * nxb + (x_lo >> 3) + xb;
+        m_out[at] = 0;
+        if (pushes_lo(pv, P, z)) peers.m[0][mi][(long long)at + pv.dz_lo * plane_b] = 0;
+        if (pushes_hi(pv, P, z)) peers.m[1][mi][(long long)at + pv.dz_hi * plane_b] = 0;
     }
 }
 
@@ -237,8 +268,9 @@ __global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
 jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
                    const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
                    StepState* __restrict__ state, float* p0, float* p1, unsigned char* m0, unsigned char* m1,
-                   const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P) {
-    constexpr int T = S::T, LX = S::LX, kTileX = S::kTileX, kTileY = S::kTileY, kPlane = S::kPlane;
+                   const __grid_constant__ WorkLists W, const __grid_constant__ PassParams P,
+                   const __grid_constant__ PeerView pv, const __grid_constant__ JacobiPeers peers) {
+    constexpr int T = S::T, LX = S::LX, kRows = S::kRows, kTileX = S::kTileX, kTileY = S::kTileY, kPlane = S::kPlane;
     constexpr unsigned kFull = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & (LX - 1), sub = lane / LX;
@@ -246,6 +278,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     // independent loads first (one round trip instead of a chain), then the decisions
     const int pass = P.pass, s0 = P.s0;
     const float dt = frame->dt;
+    const unsigned long long need = frame->epoch_base + (unsigned long long)P.event;
     const int p_cur = state->p_cur;
     const unsigned long long still_prev = pass > 0 ? state->active_after[s0 - 1] : 1ull;
     const int n_relax = pass > 0 ? W.relax_count[pass] : P.ntx * P.nty * P.nzc;
@@ -254,8 +287,23 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     // speculative: the first two list entries of this CTA (garbage beyond n_relax, then unused)
     int pre_a = pass > 0 ? list_in[blockIdx.x] : (int)blockIdx.x;
     int pre_b = pass > 0 ? list_in[blockIdx.x + gridDim.x] : (int)(blockIdx.x + gridDim.x);
-    if (!(0.0f < dt)) return;
-    if (pass > 0 && !P.run_all && still_prev == 0ull) return;
+    const bool fused_halos = pv.has_lo || pv.has_hi;
+    // Fused halos: when the last CTA is done, this kernel's event is published to the neighbours — on every path.
+    auto finish = [&]() {
+        if (!fused_halos) return;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
+                state->done_ctas = 0;
+                peer_publish(pv, need + 1ull);
+            }
+        }
+    };
+    if (!(0.0f < dt) || (pass > 0 && !P.run_all && still_prev == 0ull)) {
+        finish();
+        return;
+    }
     const int levels = min(T, P.levels_total - s0);
 
     const int sel = (p_cur + pass) & 1;
@@ -264,6 +312,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     float* p_out = sel ? p0 : p1;
     const unsigned char* m_in = (pass & 1) ? m1 : m0;
     unsigned char* m_out = (pass & 1) ? m0 : m1;
+    const int pi = sel ? 0 : 1, mi = (pass & 1) ? 0 : 1;  // the neighbours' copies of the two output buffers
 
     extern __shared__ __align__(1024) float sm[];                   // TMA destinations need 128-byte alignment
     float* sm_p = sm;                                               // [kPSlots][kPlane]  level-0 planes (TMA)
@@ -277,30 +326,53 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
+    // Fused halos: a brick of the lowest / highest layer reads halo planes the neighbour's previous kernel wrote and
+    // stores into the neighbour's halo planes that its previous kernel still read: wait for that kernel (once per side).
+    bool waited_lo = !pv.has_lo, waited_hi = !pv.has_hi;
+    auto peer_sync = [&](const bool lo, const bool hi) {  // uniform; thread 0 polls
+        const bool wl = lo && !waited_lo, wh = hi && !waited_hi;
+        if (!(wl || wh)) return;
+        if (tid == 0) peer_wait(pv, need, wl, wh);
+        waited_lo |= wl;
+        waited_hi |= wh;
+    };
+    const int layer = P.ntx * P.nty;
+    auto brick_faces = [&](const int brick, bool& lo, bool& hi) {
+        lo = pv.has_lo && brick < layer;
+        hi = pv.has_hi && brick >= layer * (P.nzc - 1);
+    };
+
     // The frozen bricks of the previous pass: one copy each into the other pressure buffer.  Of the bricks that froze
     // in the FIRST pass (the far field: most of a large grid) only those within reach of a still-active brick are ever
     // read again in this frame, so only those are copied (brick_flag == 3); the others stay final in the first pass's
     // output buffer, which jacobi_settle_kernel makes the frame's final buffer.
     if (pass == 1) {
         __shared__ int s_copied;
+        __shared__ unsigned s_todo;
         if (tid == 0) s_copied = 0;
         __syncthreads();
-        const int nbricks = P.ntx * P.nty * P.nzc, layer = P.ntx * P.nty;
+        const int nbricks = layer * P.nzc;
         for (int b0 = blockIdx.x; b0 < nbricks; b0 += gridDim.x * 32) {
-            // 32 candidate bricks of this CTA at a time: one coalesced-ish round trip for their flags
-            int b = b0 + (tid & 31) * gridDim.x;
-            int f = (tid < 32 && b < nbricks) ? W.brick_flag[b] : 0;
+            // 32 candidate bricks of this CTA at a time: one round trip for their flags
+            const int b = b0 + (tid & 31) * gridDim.x;
+            const int f = (tid < 32 && b < nbricks) ? W.brick_flag[b] : 0;
             const bool edge = (P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer);
             const bool want = (f & 1) && ((f & 2) || P.copy_all || edge);
             const unsigned todo = __ballot_sync(kFull, tid < 32 && want);
-            __shared__ unsigned s_todo;
             if (tid == 0) s_todo = todo;
             __syncthreads();
             unsigned m = s_todo;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                copy_frozen_brick<S>(p_in, p_out, m_out, P, b0 + j * gridDim.x);
+                const int brick = b0 + j * gridDim.x;
+                bool lo, hi;
+                brick_faces(brick, lo, hi);
+                if (lo || hi) {
+                    peer_sync(lo, hi);
+                    __syncthreads();
+                }
+                copy_frozen_brick<S>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
                 if (tid == 0) ++s_copied;
             }
             __syncthreads();
@@ -308,7 +380,16 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (tid == 0 && s_copied) atomicAdd(&state->bricks_copied, (unsigned long long)s_copied);
     } else if (n_copy > 0) {
         const int* __restrict__ copy_list = W.copy[pass & 1];
-        for (int w = blockIdx.x; w < n_copy; w += gridDim.x) copy_frozen_brick<S>(p_in, p_out, m_out, P, copy_list[w]);
+        for (int w = blockIdx.x; w < n_copy; w += gridDim.x) {
+            const int brick = copy_list[w];
+            bool lo, hi;
+            brick_faces(brick, lo, hi);
+            if (lo || hi) {
+                peer_sync(lo, hi);
+                __syncthreads();
+            }
+            copy_frozen_brick<S>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
+        }
         if (tid == 0 && blockIdx.x == 0) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
     }
     __syncthreads();  // barriers initialised
@@ -329,9 +410,16 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     int p_listed_next = pre_b;
     Item pit = item_of(pw < n_work ? pw : 0, p_listed);
     int pk = max(pit.zs - T, 0), pk_end = min(pit.ze + T, P.nz_alloc);
+    bool p_first = true;       // the next bundle is the first of its work item
     unsigned issued = 0;       // bundles issued so far
     auto issue_next = [&]() {  // uniform in every thread; thread 0 talks to the copy engine
         if (pw >= n_work) return;
+        if (fused_halos && p_first && pit.brick >= 0) {  // before anything of a face brick is staged: the neighbour's data is there
+            bool lo, hi;
+            brick_faces(pit.brick, lo, hi);
+            peer_sync(lo, hi);
+        }
+        p_first = false;
         if (tid == 0) {
             uint64_t* bar = &bars[issued % S::kBars];
             mbar_expect_tx(bar, 2u * kPlane * 4u);
@@ -341,6 +429,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         ++issued;
         if (++pk == pk_end) {
             pw += gridDim.x;
+            p_first = true;
             p_listed = p_listed_next;
             const int w2 = pw + gridDim.x;
             p_listed_next = (pass > 0 && w2 < n_relax) ? list_in[w2] : w2;
@@ -353,6 +442,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     };
 #pragma unroll
     for (int i = 0; i < S::kDepth; ++i) issue_next();
+    if (fused_halos) __syncthreads();  // thread 0's waits above come before anybody's loads of the neighbours' data
 
     // ---- consumer ------------------------------------------------------------------------------------------------
     unsigned consumed = 0;        // bundles consumed so far = flat index of the next bundle
@@ -379,48 +469,52 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         // ---- per-thread geometry of this tile ----
         const int gx = it.gx0 + 4 * li;
         const int ry0 = S::kWarpRows * warp + kRows * sub;  // tile row of this thread's row 0
-        const int gyb = it.gy0 + ry0;                       // grid y of this thread's row 0; row 1 is gyb + 1
+        const int gyb = it.gy0 + ry0;                       // grid y of this thread's row 0; row r is gyb + r
         const int xe = (gx < P.nx && gx + 4 > P.nx) ? P.nx - gx : 0;  // cells of a quad cut by the grid's x face
         const unsigned qmask = gx >= 0 && gx < P.nx ? (xe ? (1u << xe) - 1u : 0xFu) : 0u;
         unsigned dom_bits = 0, own_bits = 0;  // bit (4r + j): cell j of row r lies inside the grid / is this brick's output
-        if (gyb >= 0 && gyb < P.ny) dom_bits |= qmask;
-        if (gyb + 1 >= 0 && gyb + 1 < P.ny) dom_bits |= qmask << 4;
-        if (li >= 1 && li <= LX - 2) {
-            if (ry0 >= T && ry0 < kTileY - T) own_bits |= 0x0Fu;
-            if (ry0 + 1 >= T && ry0 + 1 < kTileY - T) own_bits |= 0xF0u;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            if (gyb + r >= 0 && gyb + r < P.ny) dom_bits |= qmask << (4 * r);
+            if (li >= 1 && li <= LX - 2 && ry0 + r >= T && ry0 + r < kTileY - T) own_bits |= 0xFu << (4 * r);
         }
         own_bits &= dom_bits;
-        const int off0 = ry0 * kTileX + 4 * li;  // own quad of row 0 inside a staged plane; row 1: + kTileX
-        const bool clamp_u = ry0 == 0 || gyb <= 0;                       // no row above inside the grid / tile
-        const bool clamp_d = ry0 + 1 == kTileY - 1 || gyb + 1 >= P.ny - 1;  // no row below
+        int off0 = ry0 * kTileX + 4 * li;  // own quad of row 0 inside a staged plane; row r: + r * kTileX
+        const bool clamp_u = ry0 == 0 || gyb <= 0;                                       // no row above inside the grid / tile
+        const bool clamp_d = ry0 + kRows - 1 == kTileY - 1 || gyb + kRows - 1 >= P.ny - 1;  // no row below
         int off_up = clamp_u ? off0 : off0 - kTileX;
-        int off_dn = clamp_d ? off0 + kTileX : off0 + 2 * kTileX;
+        int off_dn = clamp_d ? off0 + (kRows - 1) * kTileX : off0 + kRows * kTileX;
         const bool clamp_l = li == 0 || gx == 0;
         const bool clamp_r = li == LX - 1 || gx + 4 >= P.nx;
         // per-thread constants of the brick the compiler would otherwise re-derive from the thread index at every use
         asm volatile("" : "+r"(off_up), "+r"(off_dn), "+r"(own_bits), "+r"(dom_bits));
-        // the grid's faces may cut through this thread's two rows / four cells: ghosts mirror the adjacent inside
+        // the grid's faces may cut through this thread's rows / four cells: ghosts mirror the adjacent inside
         // row / cell after every update so that the in-register neighbours obey the clamp rule
-        const bool y_ghost_lo = gyb == -1, y_ghost_hi = gyb == P.ny - 1;
+        const bool y_ghost_lo = kRows == 2 && gyb == -1, y_ghost_hi = kRows == 2 && gyb == P.ny - 1;
         const bool any_ghost = y_ghost_lo || y_ghost_hi || xe != 0;
         auto fix_ghosts = [&](float4 (&v)[kRows]) {
             if (any_ghost) {
-                if (y_ghost_lo) v[0] = v[1];
-                if (y_ghost_hi) v[1] = v[0];
-                if (xe == 1) { v[0].y = v[0].x; v[1].y = v[1].x; }
-                if (xe == 2) { v[0].z = v[0].y; v[1].z = v[1].y; }
-                if (xe == 3) { v[0].w = v[0].z; v[1].w = v[1].z; }
+                if constexpr (kRows == 2) {
+                    if (y_ghost_lo) v[0] = v[1];
+                    if (y_ghost_hi) v[1] = v[0];
+                }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    if (xe == 1) v[r].y = v[r].x;
+                    if (xe == 2) v[r].z = v[r].y;
+                    if (xe == 3) v[r].w = v[r].z;
+                }
             }
         };
 
         // Freeze flags of the level-0 planes (the previous pass's output mask): raw bytes are fetched two iterations
-        // ahead and decoded when their plane is consumed.
+        // ahead and decoded when their plane is consumed.  (L2 loads: a neighbour rank may have written halo planes.)
         const size_t mrow0 = (size_t)max(gyb, 0) * nxb + (max(gx, 0) >> 3);
         const size_t mplane = (size_t)P.ny * nxb;
         auto fetch_flags = [&](const int z, unsigned& raw0, unsigned& raw1) {
             if (pass == 0 || z >= zl1) return;
-            if (dom_bits & 0x0Fu) raw0 = __ldg(m_in + (size_t)z * mplane + mrow0);
-            if (dom_bits & 0xF0u) raw1 = __ldg(m_in + (size_t)z * mplane + mrow0 + ((dom_bits & 0x0Fu) ? nxb : 0));
+            if (dom_bits & 0x0Fu) raw0 = __ldcg(m_in + (size_t)z * mplane + mrow0);
+            if (kRows == 2 && (dom_bits & 0xF0u)) raw1 = __ldcg(m_in + (size_t)z * mplane + mrow0 + ((dom_bits & 0x0Fu) ? nxb : 0));
         };
         const int nib_shift = gx & 4;
         unsigned raw_a0 = 0, raw_a1 = 0, raw_b0 = 0, raw_b1 = 0;  // bytes of the plane consumed next / the one after
@@ -462,8 +556,8 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                 issue_next();
                 mbar_wait(&bars[consumed % S::kBars], (consumed / S::kBars) & 1u);
                 const float* src = sm_p + po_new + off0;
-                nw[0] = *reinterpret_cast<const float4*>(src);
-                nw[1] = *reinterpret_cast<const float4*>(src + kTileX);
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) nw[r] = *reinterpret_cast<const float4*>(src + r * kTileX);
                 fix_ghosts(nw);
                 nfl = pass == 0 ? dom_bits
                                 : ((((raw_a0 >> nib_shift) & 0xFu) | (((raw_a1 >> nib_shift) & 0xFu) << 4)) & dom_bits);
@@ -472,14 +566,17 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                 fetch_flags(k + 2, raw_b0, raw_b1);
                 ++consumed;
             } else {
-                nw[0] = nw[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) nw[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
 
             auto level = [&](auto lc) {
                 constexpr int l = decltype(lc)::value;
                 const int z = k - l;
                 const bool run = z >= lo_of[l] && z < hi_of[l];
-                float4 out[kRows] = {nw[0], nw[1]};
+                float4 out[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) out[r] = nw[r];
                 unsigned st = 0;
                 if (run) {
                     const unsigned act = (l <= levels) ? qf[l - 1] : 0u;
@@ -489,43 +586,64 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                         const float4 up = *reinterpret_cast<const float4*>(nb + off_up);
                         const float4 dn = *reinterpret_cast<const float4*>(nb + off_dn);
                         const float* rb = sm_rhs + ro[l] + off0;
-                        const float4 rhs0 = *reinterpret_cast<const float4*>(rb);
-                        const float4 rhs1 = *reinterpret_cast<const float4*>(rb + kTileX);
+                        float4 rhs[kRows];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) rhs[r] = *reinterpret_cast<const float4*>(rb + r * kTileX);
                         // clamp rule at the grid's z faces: the missing neighbour plane is the centre plane itself (the
                         // overwritten queue entries are dead: no plane follows the face, none precedes it)
-                        if (z == P.z_face_lo) { qp[l - 1][0] = qc[l - 1][0]; qp[l - 1][1] = qc[l - 1][1]; }
-                        if (z + 1 == P.z_face_hi) { nw[0] = qc[l - 1][0]; nw[1] = qc[l - 1][1]; }
-                        const float4 c0v = qc[l - 1][0], c1v = qc[l - 1][1];
-                        const float4 f0 = qp[l - 1][0], f1 = qp[l - 1][1];
-                        const float4 b0 = nw[0], b1 = nw[1];
-                        float l0 = __shfl_up_sync(kFull, c0v.w, 1, LX), r0 = __shfl_down_sync(kFull, c0v.x, 1, LX);
-                        float l1 = __shfl_up_sync(kFull, c1v.w, 1, LX), r1 = __shfl_down_sync(kFull, c1v.x, 1, LX);
-                        if (clamp_l) { l0 = c0v.x; l1 = c1v.x; }
-                        if (clamp_r) { r0 = c0v.w; r1 = c1v.w; }
-                        st = relax_quad(c0v, f0, b0, up, c1v, l0, r0, rhs0, act & 0xFu, eps, out[0]);
-                        st |= relax_quad(c1v, f1, b1, c0v, dn, l1, r1, rhs1, act >> 4, eps, out[1]) << 4;
+                        if (z == P.z_face_lo) {
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) qp[l - 1][r] = qc[l - 1][r];
+                        }
+                        if (z + 1 == P.z_face_hi) {
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) nw[r] = qc[l - 1][r];
+                        }
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) {
+                            const float4 c = qc[l - 1][r];
+                            float left = __shfl_up_sync(kFull, c.w, 1, LX), right = __shfl_down_sync(kFull, c.x, 1, LX);
+                            if (clamp_l) left = c.x;
+                            if (clamp_r) right = c.w;
+                            const float4 u = r == 0 ? up : qc[l - 1][r > 0 ? r - 1 : 0];
+                            const float4 d = r == kRows - 1 ? dn : qc[l - 1][r < kRows - 1 ? r + 1 : r];
+                            st |= relax_quad(c, qp[l - 1][r], nw[r], u, d, left, right, rhs[r], (act >> (4 * r)) & 0xFu, eps,
+                                             out[r]) << (4 * r);
+                        }
                         fix_ghosts(out);
                         if (z >= zs && z < ze && it.brick >= 0) {  // halo bricks are counted by their owner
                             tot[l] += __popc(st & own_bits);
                             if (l == levels) alive |= st & own_bits;
                         }
                     } else {
-                        out[0] = qc[l - 1][0];
-                        out[1] = qc[l - 1][1];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) out[r] = qc[l - 1][r];
                     }
                     if constexpr (l < T) {  // publish the new plane for the rows above / below (read next iteration)
                         float* dst = sm_pub + ((l - 1) * 2 + pub_w) * kPlane + off0;
-                        *reinterpret_cast<float4*>(dst) = out[0];
-                        *reinterpret_cast<float4*>(dst + kTileX) = out[1];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) *reinterpret_cast<float4*>(dst + r * kTileX) = out[r];
                     } else if (z >= zs && z < ze) {  // level T: the pass's output
+                        const bool to_lo = fused_halos && it.brick >= 0 && pushes_lo(pv, P, z);
+                        const bool to_hi = fused_halos && it.brick >= 0 && pushes_hi(pv, P, z);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) {
                             const bool mine = (own_bits >> (4 * r)) & 1u;
-                            if (mine) *reinterpret_cast<float4*>(p_out + ((size_t)z * P.ny + (gyb + r)) * P.pitch + gx) = out[r];
+                            const size_t at = ((size_t)z * P.ny + (gyb + r)) * P.pitch + gx;
+                            if (mine) *reinterpret_cast<float4*>(p_out + at) = out[r];
                             // bit-packed freeze flags: two quads (8 cells) per byte, written by the odd lane
                             const unsigned nib = (st >> (4 * r)) & 0xFu;
                             const unsigned hi = __shfl_down_sync(kFull, nib, 1, LX);
-                            if (mine && (li & 1)) m_out[((size_t)z * P.ny + (gyb + r)) * nxb + (gx >> 3)] = (unsigned char)(nib | (hi << 4));
+                            const size_t mat = ((size_t)z * P.ny + (gyb + r)) * nxb + (gx >> 3);
+                            const unsigned char byte = (unsigned char)(nib | (hi << 4));
+                            if (mine && (li & 1)) m_out[mat] = byte;
+                            if (to_lo || to_hi) {  // the same stores into the neighbour's halo planes
+                                const long long plane_f = (long long)P.ny * P.pitch, plane_b = (long long)P.ny * nxb;
+                                if (mine && to_lo) *reinterpret_cast<float4*>(peers.p[0][pi] + (long long)at + pv.dz_lo * plane_f) = out[r];
+                                if (mine && to_hi) *reinterpret_cast<float4*>(peers.p[1][pi] + (long long)at + pv.dz_hi * plane_f) = out[r];
+                                if (mine && (li & 1) && to_lo) peers.m[0][mi][(long long)mat + pv.dz_lo * plane_b] = byte;
+                                if (mine && (li & 1) && to_hi) peers.m[1][mi][(long long)mat + pv.dz_hi * plane_b] = byte;
+                            }
                         }
                     }
                 }
@@ -538,8 +656,8 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                     }
                     qf[l - 1] = nfl;
                 }
-                nw[0] = out[0];
-                nw[1] = out[1];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) nw[r] = out[r];
                 nfl = st;
                 have = run;
             };
@@ -605,19 +723,21 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (v) atomicAdd(&state->active_after[s0 + tid], (unsigned long long)v);
     }
     if (tid == 0 && n_done) atomicAdd(&state->bricks_processed, (unsigned long long)n_done);
+    finish();
 }
 
 // After the last pass.  The frame's final pressure must be complete in ONE buffer: the first pass's output buffer Y,
 // the only one that holds the bricks that froze in the first pass and were never copied.  Every later brick is final
 // in both buffers once copied — except the bricks relaxed by the last executed pass L when that pass wrote the other
 // buffer (L odd): those (pass L + 1's relax and copy lists) are copied into Y here.  Also the solve's bookkeeping that
-// finish_solve_kernel does for the per-sweep path: s_exec, pass count, which buffer holds P.
+// finish_solve_kernel does for the per-sweep path: s_exec, pass count (which buffer holds P: jacobi_flip_kernel).
 template <class S>
 __global__ void __launch_bounds__(S::kThreads)
 jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                      unsigned char* m0, unsigned char* m1, const __grid_constant__ WorkLists W,
                      const __grid_constant__ PassParams P, const int t_first, const int n_early, const int t_late,
-                     const int force_passes) {
+                     const int force_passes, const __grid_constant__ PeerView pv,
+                     const __grid_constant__ JacobiPeers peers) {
     const int iters = P.levels_total;
     const bool live = 0.0f < frame->dt && iters > 0;
     int s = 0;
@@ -633,11 +753,16 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
         const float* src = p_cur ? p1 : p0;   // out(L) = X for odd L
         float* dst = p_cur ? p0 : p1;
         unsigned char* m_dst = ((L + 1) & 1) ? m0 : m1;  // as pass L + 1 would have cleared it (unused after the frame)
+        const int pi = p_cur ? 0 : 1, mi = ((L + 1) & 1) ? 0 : 1;
         const int n_r = W.relax_count[L + 1], n_c = W.copy_count[L + 1];
         const int* __restrict__ lr = W.relax[(L + 1) & 1];
         const int* __restrict__ lc = W.copy[(L + 1) & 1];
+        if ((pv.has_lo || pv.has_hi) && n_r + n_c > 0) {  // the neighbours' last pass no longer reads the halos written here
+            if (threadIdx.x == 0) peer_wait(pv, frame->epoch_base + (unsigned long long)P.event, true, true);
+            __syncthreads();
+        }
         for (int w = blockIdx.x; w < n_r + n_c; w += gridDim.x)
-            copy_frozen_brick<S>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r]);
+            copy_frozen_brick<S>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r], pv, peers, pi, mi);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // (p_cur itself is flipped by the next kernel: other CTAs still read it)
         state->s_exec = s;
@@ -648,10 +773,12 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
 }
 
 // p_cur flips once per frame with a pressure solve (to the first pass's output buffer); a kernel of its own so that
-// no CTA of jacobi_settle_kernel can observe the new value.
-__global__ void jacobi_flip_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters) {
+// no CTA of jacobi_settle_kernel can observe the new value.  Fused halos: the settle step's event.
+__global__ void jacobi_flip_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters,
+                                   const __grid_constant__ PeerView pv, int event) {
     if (0.0f < frame->dt && iters > 0 && state->passes > 0) state->p_cur ^= 1;
     phase_mark(state, 2);  // the pressure solve ends here
+    if (pv.has_lo || pv.has_hi) peer_publish(pv, frame->epoch_base + (unsigned long long)event + 1ull);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -684,21 +811,22 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int pitch, in
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// The shapes in use.  Wide: tile rows of 32 lanes (128 cells, one warp per row pair); narrow: 16 lanes (64 cells, a warp
-// covers two row pairs), chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as
-// possible.  The default schedule mixes two kernels over ONE brick grid (own region 120 x 12 or 56 x 28 cells):
-//   first pass   T = 2, two CTAs per SM, TMA depth 3 — every brick is relaxed, throughput matters;
-//   later passes T = 4, one CTA per SM, TMA depth 4, one / two more warps for the deeper y halo — few bricks are left,
-//                what matters is the latency of one brick chain and the number of launches (16 instead of 31).
-// A uniform schedule (fxb_config.fuse_t = 1..4) uses the two-CTA shape for T <= 2 and the one-CTA shape above.
+// The shapes in use.  Wide: tile rows of 32 lanes (128 cells); narrow: 16 lanes (64 cells, a warp covers two row groups),
+// chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as possible.  The default
+// schedule runs T = 2 throughout on one brick grid (own region 120 x 12 or 56 x 28 cells) with two kernel shapes:
+//   the first passes (many bricks to relax: throughput)  2 rows per thread,  8 warps, two CTAs per SM, TMA depth 3;
+//   the later passes (one brick chain per SM sets the pace: latency)  1 row per thread, 16 warps on the same tile, one CTA
+//   per SM, TMA depth 4 — half the dependent work per warp and twice the warps to interleave.
+// A uniform schedule (fxb_config.fuse_t = 1..4) uses the two-CTA shape for T <= 2 and a one-CTA shape above.
 template <int T> using WideU = Shape<T, 32, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
 template <int T> using NarrowU = Shape<T, 16, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
-using WideLate = Shape<4, 32, 10, 4, 1>;    // tile 128 x 20: own rows 12, as the T = 2 tile 128 x 16
-using NarrowLate = Shape<4, 16, 9, 4, 1>;   // tile 64 x 36: own rows 28, as the T = 2 tile 64 x 32
+using WideLate = Shape<2, 32, 16, 4, 1, 1>;    // tile 128 x 16, as WideU<2>
+using NarrowLate = Shape<2, 16, 16, 4, 1, 1>;  // tile 64 x 32, as NarrowU<2>
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                         int s0, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, cudaStream_t stream) {
+                         int s0, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, const PeerView& pv,
+                         cudaStream_t stream) {
     // the opt-in above the 48 KB default is per device: set it whenever the device changes (cheap, idempotent)
     static int attr_device = -1;
     int dev = 0;
@@ -720,6 +848,14 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     P.copy_all = J.copy_all ? 1 : 0;
     P.keep_lo = d.z_own0 > 0 ? 1 : 0;
     P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
+    P.event = 2 + pass;
+    P.push_depth = std::max(J.T, J.T_late);
+    JacobiPeers peers;
+    for (int side = 0; side < 2; ++side)
+        for (int i = 0; i < 2; ++i) {
+            peers.p[side][i] = J.peer_p[side][i];
+            peers.m[side][i] = J.peer_m[side][i];
+        }
     const int nbricks = J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
     const int grid = nbricks < slots ? nbricks : slots;
@@ -734,7 +870,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
         *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[0] : J.map_p[0]),
         *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[1] : J.map_p[1]),
         *reinterpret_cast<const CUtensorMap*>(late ? J.map_rhs_late : J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0],
-        J.mask[1], W, P);
+        J.mask[1], W, P, pv, peers);
     return cudaGetLastError();
 }
 
@@ -750,9 +886,9 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     // fuse_t = 0: the mixed schedule (T = 2, then T = 4 on the same bricks); otherwise T = fuse_t throughout
     J->mixed = fuse_t == 0;
     J->T = J->mixed ? 2 : fuse_t;
-    J->T_late = J->mixed ? 4 : fuse_t;
-    // the first passes still relax many bricks (throughput: two CTAs per SM, T = 2); afterwards one brick chain per SM
-    // sets the pace (latency: T = 4 halves the number of launches)
+    J->T_late = J->T;
+    // the first passes still relax many bricks (throughput shape); afterwards one brick chain per SM sets the pace
+    // (latency shape: same T, same tile, twice the warps)
     J->n_early = J->mixed ? 4 : 1;
     if (const char* e = getenv("FXB_EARLY")) J->n_early = std::max(1, atoi(e));  // tuning knob
     const int T = J->T;
@@ -812,10 +948,10 @@ void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
 
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
-                                     cudaStream_t stream) {
+                                     const PeerView& pv, cudaStream_t stream) {
     int T, s0;
     fused_jacobi_pass_spec(J, pass, &T, &s0);
-#define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, stream)
+#define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream)
     if (J.mixed && pass >= J.n_early) {
         if (J.narrow) FXB_LAUNCH(NarrowLate);
         FXB_LAUNCH(WideLate);
@@ -831,12 +967,21 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
 }
 
 cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                 int iters, int force_passes, cudaStream_t stream) {
+                                 int iters, int force_passes, const PeerView& pv, cudaStream_t stream) {
     PassParams P{};
     P.nx = d.nx; P.ny = d.ny; P.pitch = d.pitch; P.nz_alloc = d.nz_alloc;
     P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
     P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
     P.levels_total = iters;
+    const int npass = fused_jacobi_passes(J, iters);
+    P.event = 2 + npass;
+    P.push_depth = std::max(J.T, J.T_late);
+    JacobiPeers peers;
+    for (int side = 0; side < 2; ++side)
+        for (int i = 0; i < 2; ++i) {
+            peers.p[side][i] = J.peer_p[side][i];
+            peers.m[side][i] = J.peer_m[side][i];
+        }
     WorkLists W;
     const int np = FusedJacobi::kMaxPasses + 1;
     W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
@@ -845,24 +990,26 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
     W.brick_flag = J.brick_flag;
     const int grid = J.num_sms * 2;
     // geometry of the own region only (shared by every shape of the schedule)
+#define FXB_SETTLE(S) jacobi_settle_kernel<S><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes, pv, peers)
     if (J.narrow) {
         switch (J.T) {
-            case 1: jacobi_settle_kernel<NarrowU<1>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            case 2: jacobi_settle_kernel<NarrowU<2>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            case 3: jacobi_settle_kernel<NarrowU<3>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            default: jacobi_settle_kernel<NarrowU<4>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 1: FXB_SETTLE(NarrowU<1>); break;
+            case 2: FXB_SETTLE(NarrowU<2>); break;
+            case 3: FXB_SETTLE(NarrowU<3>); break;
+            default: FXB_SETTLE(NarrowU<4>); break;
         }
     } else {
         switch (J.T) {
-            case 1: jacobi_settle_kernel<WideU<1>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            case 2: jacobi_settle_kernel<WideU<2>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            case 3: jacobi_settle_kernel<WideU<3>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
-            default: jacobi_settle_kernel<WideU<4>><<<grid, 256, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes); break;
+            case 1: FXB_SETTLE(WideU<1>); break;
+            case 2: FXB_SETTLE(WideU<2>); break;
+            case 3: FXB_SETTLE(WideU<3>); break;
+            default: FXB_SETTLE(WideU<4>); break;
         }
     }
+#undef FXB_SETTLE
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    jacobi_flip_kernel<<<1, 1, 0, stream>>>(frame, state, iters);
+    jacobi_flip_kernel<<<1, 1, 0, stream>>>(frame, state, iters, pv, 2 + npass);
     return cudaGetLastError();
 }
 

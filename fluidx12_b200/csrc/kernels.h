@@ -8,9 +8,15 @@
 namespace fxb {
 
 // advect.cu
+// Fused halos (common.cuh PeerView): the neighbours' copies of the arrays a kernel also stores into, [0] = rank - 1,
+// [1] = rank + 1 (nullptr at a grid face / on a single GPU).
+struct AdvectPeers {
+    void* vel_out[2] = {nullptr, nullptr};                       // m_velocities[1]
+    void* col[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][m_colors index]
+};
 void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
                    void* const col[2], void* vel_out, const Emitter& em, int clamp_mode, StepState* state, int h_adv,
-                   cudaStream_t stream);
+                   const PeerView& pv, const AdvectPeers& peers, cudaStream_t stream);
 
 // lightmap.cu — the light-map pass after the step (CSRayMarchL); consts = fxb_light_params
 struct HaloComm;
@@ -26,7 +32,7 @@ cudaError_t launch_ray_march_v(const Domain& d, const void* colour, const unsign
                                const void* consts, cudaStream_t stream);
 
 // project_simple.cu — one kernel per logical pass (cross-check path, kernel_path = 1)
-void launch_begin_step(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream);
+void launch_begin_step(const FrameParams* frame, StepState* state, int iters, const PeerView& pv, cudaStream_t stream);
 void launch_divergence(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, cudaStream_t stream);
 void launch_jacobi_sweep_simple(const Domain& d, const FrameParams* frame, const float* rhs, float* p0, float* p1,
                                 unsigned char* active, StepState* state, int sweep, int early_exit,
@@ -37,11 +43,11 @@ void launch_gradient(const Domain& d, const FrameParams* frame, const void* vel_
 
 // project_quad.cu — 4 cells per thread (tuned path; 3D grids with nx % 8 == 0)
 bool quad_kernels_supported(const Domain& d);
-void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs,
-                            cudaStream_t stream);
+void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, const PeerView& pv,
+                            float* rhs_lo, float* rhs_hi, int push_depth, cudaStream_t stream);
 void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
-                          const float* p0, const float* p1, void* vel_out, const StepState* state,
-                          cudaStream_t stream);
+                          const float* p0, const float* p1, void* vel_out, const StepState* state, const PeerView& pv,
+                          void* vel_out_lo, void* vel_out_hi, int reach, int event, cudaStream_t stream);
 
 // jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
 struct FusedJacobi {
@@ -52,6 +58,9 @@ struct FusedJacobi {
     bool copy_all = false;     // copy every brick that froze in the first pass (grouped multi-GPU exchange), not only those
                                // next to an active brick
     int* brick_flag = nullptr; // [bricks] per frame: bit 0 = froze in the first pass, bit 1 = next to a still-active brick
+    // fused halos: the neighbours' copies of p[] / mask[] ([side][buffer]; nullptr at a grid face / on a single GPU)
+    float* peer_p[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    unsigned char* peer_m[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     bool narrow = false;       // tile 64 x 32 (a warp covers two row pairs) instead of 128 x 16
     int tile_x = 128, tile_y = 16;  // tile of the first pass
     int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
@@ -77,9 +86,9 @@ size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);
 // After the last pass: copies what the last executed pass left in the wrong buffer, s_exec / pass count, flips p_cur.
 cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
-                                 int iters, int force_passes, cudaStream_t stream);
+                                 int iters, int force_passes, const PeerView& pv, cudaStream_t stream);
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
-                                     cudaStream_t stream);
+                                     const PeerView& pv, cudaStream_t stream);
 
 }  // namespace fxb

@@ -40,12 +40,14 @@ __device__ __forceinline__ float comp(const uint2* __restrict__ vel, size_t i, i
     return half_bits_to_float(__ldg(h + c));
 }
 
-__global__ void begin_step_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters) {
+__global__ void begin_step_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, int iters,
+                                  const __grid_constant__ PeerView pv) {
     const int k = threadIdx.x;
     if (k < iters && k < 128) state->active_after[k] = 0ull;
     if (k == 0) {
         state->s_exec = 0; state->passes = 0;
         phase_mark(state, 0);  // the advection phase ends here
+        if (pv.has_lo || pv.has_hi) peer_publish(pv, frame->epoch_base + 1ull);  // fused halos: advect (m = 0) is complete
     }
 }
 
@@ -177,8 +179,8 @@ inline dim3 plane_grid(const Domain& d) { return dim3((d.nx + 31) / 32, (d.ny + 
 
 }  // namespace
 
-void launch_begin_step(const FrameParams* frame, StepState* state, int iters, cudaStream_t stream) {
-    begin_step_kernel<<<1, 128, 0, stream>>>(frame, state, iters);
+void launch_begin_step(const FrameParams* frame, StepState* state, int iters, const PeerView& pv, cudaStream_t stream) {
+    begin_step_kernel<<<1, 128, 0, stream>>>(frame, state, iters, pv);
 }
 
 void launch_divergence(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, cudaStream_t stream) {

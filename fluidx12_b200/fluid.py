@@ -32,7 +32,7 @@ class Fluid:
              address_mode: int = B.ADDRESS_MIRROR, early_exit: bool = True, jacobi_iters: int = 64,
              fuse_t: int = 0, device: int = 0, rank: int = 0, nranks: int = 1, h_adv: int = 0,
              use_graph: bool = True, kernel_path: int = 0, phase_timing: bool = False,
-             halo_backend: int = B.HALO_PEER, jacobi_group: int = 0,
+             halo_backend: int = B.HALO_FUSED, jacobi_group: int = 0,
              nccl_unique_id: Optional[bytes] = None) -> bool:
         """Returns False on failure like the reference (XUSG_N_RETURN); ``last_error`` says why."""
         L = B.lib()

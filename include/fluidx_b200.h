@@ -52,8 +52,10 @@ typedef enum fxb_field {
 
 /* How z-slab face halos travel between neighbouring ranks (nranks > 1). */
 typedef enum fxb_halo_backend {
-    FXB_HALO_PEER = 0, /* one kernel per exchange stores the face planes straight into the neighbours' memory (CUDA IPC over NVLink) */
-    FXB_HALO_NCCL = 1  /* grouped ncclSend / ncclRecv pairs */
+    FXB_HALO_PEER = 0,  /* one kernel per exchange stores the face planes straight into the neighbours' memory (CUDA IPC over NVLink) */
+    FXB_HALO_NCCL = 1,  /* grouped ncclSend / ncclRecv pairs */
+    FXB_HALO_FUSED = 2  /* no exchange at all: every kernel of the step stores the planes next to a slab face into the
+                           neighbour's halo as well, ordered by one event counter per rank (default) */
 } fxb_halo_backend;
 
 typedef struct fxb_config {
@@ -69,7 +71,7 @@ typedef struct fxb_config {
     int32_t use_graph;      /* 1 (default): the step is a captured CUDA graph; 0: plain stream launches */
     int32_t kernel_path;    /* 0 = tuned kernels (default); 1 = one simple kernel per logical pass (cross-check path) */
     int32_t phase_timing;   /* 1: a one-thread kernel after every phase accumulates the phase's device time (fxb_get_phase_times) */
-    int32_t halo_backend;   /* fxb_halo_backend (multi-GPU); default FXB_HALO_PEER */
+    int32_t halo_backend;   /* fxb_halo_backend (multi-GPU); default FXB_HALO_FUSED */
     int32_t jacobi_group;   /* multi-GPU: fused passes per pressure-halo exchange; 0 = library default (1) */
     const void* nccl_unique_id; /* 128-byte ncclUniqueId shared by all ranks; required iff nranks > 1 */
 } fxb_config;
