@@ -39,8 +39,6 @@ __device__ __forceinline__ Pair4 widen(const uint2 r) {
     return t;
 }
 
-__device__ __forceinline__ Pair4 load_pairs(const uint2* __restrict__ f, unsigned i) { return widen(__ldg(f + i)); }
-
 __device__ __forceinline__ float2 lerp2(float2 f, float2 a, float2 b) { return fma2(f, sub2(b, a), a); }
 
 // x, then y, then z; each lerp is fma(f, b - a, a)
@@ -203,6 +201,8 @@ __device__ __forceinline__ Texels advect_voxel(const AdvectArgs& A, const float 
     return out;
 }
 
+// FUSED: the multi-GPU instantiation with fused halos (common.cuh PeerView); the single-GPU one carries none of it.
+template <bool FUSED>
 __global__ void __launch_bounds__(256, 4)
 advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ PeerView pv,
               const FrameParams* __restrict__ frame, const uint2* __restrict__ vel_in, uint2* col0,
@@ -214,8 +214,9 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
     const int z0 = d.z_own0 + blockIdx.z * kZ;  // global plane
     const int z1 = min(z0 + kZ, d.z_own1);
     // fused halos: the planes next to an interior face wait for the neighbour's previous frame (event m = 0)
-    const bool near_lo = pv.has_lo && z0 < d.z_own0 + A.reach, near_hi = pv.has_hi && z1 > d.z_own1 - A.reach;
-    if (near_lo || near_hi) {
+    const bool near_lo = FUSED && pv.has_lo && z0 < d.z_own0 + A.reach;
+    const bool near_hi = FUSED && pv.has_hi && z1 > d.z_own1 - A.reach;
+    if (FUSED && (near_lo || near_hi)) {
         if (threadIdx.x == 0 && threadIdx.y == 0) peer_wait(pv, frame->epoch_base, near_lo, near_hi);
         __syncthreads();
     }
@@ -240,12 +241,12 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
         const Texels t = advect_voxel(A, dt, atten, vel_in, col_in, state, x, y, z, px, py, self, sv, sc);
         vel_out[self] = t.vel;
         col_out[self] = t.col;
-        if (near_lo) {
+        if (FUSED && near_lo) {
             const long long at = (long long)self + (long long)pv.dz_lo * plane;
             if (z == d.z_own0) A.vel_out_lo[at] = t.vel;
             if (z < d.z_own0 + A.reach) A.col_lo[parity][at] = t.col;
         }
-        if (near_hi) {
+        if (FUSED && near_hi) {
             const long long at = (long long)self + (long long)pv.dz_hi * plane;
             if (z == d.z_own1 - 1) A.vel_out_hi[at] = t.vel;
             if (z >= d.z_own1 - A.reach) A.col_hi[parity][at] = t.col;
@@ -276,8 +277,12 @@ void launch_advect(const Domain& d, const AxisTables& tab, const FrameParams* fr
     }
     const dim3 block(32, 8, 1);
     const dim3 grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.z_own1 - d.z_own0 + kZ - 1) / kZ);
-    advect_kernel<<<grid, block, 0, stream>>>(A, pv, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
-                                              (uint2*)vel_out, state);
+    if (pv.has_lo || pv.has_hi)
+        advect_kernel<true><<<grid, block, 0, stream>>>(A, pv, frame, (const uint2*)vel_in, (uint2*)col[0], (uint2*)col[1],
+                                                        (uint2*)vel_out, state);
+    else
+        advect_kernel<false><<<grid, block, 0, stream>>>(A, pv, frame, (const uint2*)vel_in, (uint2*)col[0],
+                                                         (uint2*)col[1], (uint2*)vel_out, state);
 }
 
 }  // namespace fxb

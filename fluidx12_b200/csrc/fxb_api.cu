@@ -217,7 +217,7 @@ void enqueue_phase(Enqueue& q, int phase) {
             }
             if (s->quad)
                 fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, s->pv, (float*)s->comm.peer_of(s->rhs, 0),
-                                            (float*)s->comm.peer_of(s->rhs, 1), std::max(s->jac.T, s->jac.T_late), st);
+                                            (float*)s->comm.peer_of(s->rhs, 1), s->jac.T, st);
             else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
             q.launched(cudaGetLastError(), "divergence_kernel");
             q.mark(1, 2);
@@ -231,17 +231,15 @@ void enqueue_phase(Enqueue& q, int phase) {
                 const bool mg = s->multi() && s->dt > 0.0f;
                 // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
                 // between, pass j of a group also relaxes the (G-1-j)*T halo planes next to each interior face.
-                // (grouping needs a uniform T; the mixed schedule exchanges before every pass, as deep as that pass fuses)
-                const int G = s->multi() && !s->jac.mixed ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
-                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the deepest pass
-                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * std::max(s->jac.T, s->jac.T_late)}};
+                const int G = s->multi() ? std::max(1, std::min(s->jacobi_group, s->halo / s->fuse_t)) : 1;
+                if (mg) {  // the right-hand side is constant over the sweeps: one exchange, as deep as the group
+                    const fxb::HaloField f[1] = {{s->rhs, s->plane_voxels() * 4, G * s->fuse_t}};
                     q.halo(f, 1);
                 }
                 for (int k = 0; k < npass; ++k) {
                     int ext_lo = 0, ext_hi = 0;
                     if (mg) {
-                        int Tk, s0k;
-                        fxb::fused_jacobi_pass_spec(s->jac, k, &Tk, &s0k);
+                        const int Tk = s->fuse_t;
                         if (k % G == 0) {
                             const fxb::HaloField f[2] = {
                                 {s->p[(s->p_cur_host + k) & 1], s->plane_voxels() * 4, G * Tk},
@@ -422,7 +420,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         // z-slab decomposition (fluidx12_b200/slab.py states the same rules): rank r owns planes
         // [r*nz/R, (r+1)*nz/R); interior faces carry `halo` extra planes, the grid's own faces none
         const int nz = (int)cfg->nz, R = cfg->nranks, r = cfg->rank;
-        const int fuse = cfg->fuse_t ? cfg->fuse_t : 4;  // the deepest pass of the default schedule
+        const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
         s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;  // 2|u_z| voxels; |u_z| stayed below 3 in every run
         s->jacobi_group = cfg->jacobi_group > 0 ? cfg->jacobi_group : 1;
         s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
@@ -488,7 +486,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         }
         if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, cfg->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
             return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
-        s->fuse_t = s->jac.T_late;  // what fxb_stats reports: sweeps per pass after the first
+        s->fuse_t = s->jac.T;
         const size_t nc = 3 * (fxb::FusedJacobi::kMaxPasses + 1);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&s->jac.work_list[i], 2 * (size_t)s->jac.list_stride * sizeof(int));

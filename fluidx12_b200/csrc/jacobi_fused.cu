@@ -185,7 +185,7 @@ __device__ __forceinline__ bool pushes_hi(const PeerView& pv, const PassParams& 
 // copies its own region once into the other buffer (and clears the other mask buffer), after which the brick is
 // final in both ping-pong buffers and is never touched again in this frame.  Pure streaming (8 B/cell), eight
 // independent 16-byte loads in flight per thread.  Planes next to an interior slab face go to the neighbour as well.
-template <class S>
+template <class S, bool FUSED>
 __device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, float* __restrict__ p_out,
                                                unsigned char* __restrict__ m_out, const PassParams& P, const int brick,
                                                const PeerView& pv, const JacobiPeers& peers, const int pi,
@@ -213,6 +213,7 @@ __device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, f
         for (int u = 0; u < 8; ++u)
             if (base + u * S::kThreads < total) {
                 *reinterpret_cast<float4*>(p_out + at[u]) = v[u];
+                if constexpr (!FUSED) continue;
                 if (pushes_lo(pv, P, zz[u])) *reinterpret_cast<float4*>(peers.p[0][pi] + (long long)at[u] + pv.dz_lo * plane_f) = v[u];
                 if (pushes_hi(pv, P, zz[u])) *reinterpret_cast<float4*>(peers.p[1][pi] + (long long)at[u] + pv.dz_hi * plane_f) = v[u];
             }
@@ -222,6 +223,7 @@ __device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, f
         const int xb = i % bpr, rz = i / bpr, z = it.zs + rz / rows;
         const size_t at = ((size_t)z * P.ny + (y_lo + rz % rows)) * nxb + (x_lo >> 3) + xb;
         m_out[at] = 0;
+        if constexpr (!FUSED) continue;
         if (pushes_lo(pv, P, z)) peers.m[0][mi][(long long)at + pv.dz_lo * plane_b] = 0;
         if (pushes_hi(pv, P, z)) peers.m[1][mi][(long long)at + pv.dz_hi * plane_b] = 0;
     }
@@ -262,8 +264,9 @@ __device__ __forceinline__ unsigned relax_quad(const float4 c, const float4 lo, 
     return s;
 }
 
-// One fused pass (see the file header).
-template <class S>
+// One fused pass (see the file header).  FUSED: the multi-GPU instantiation with fused halos (common.cuh PeerView);
+// the single-GPU one carries none of that code.
+template <class S, bool FUSED>
 __global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
 jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
                    const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
@@ -287,10 +290,10 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     // speculative: the first two list entries of this CTA (garbage beyond n_relax, then unused)
     int pre_a = pass > 0 ? list_in[blockIdx.x] : (int)blockIdx.x;
     int pre_b = pass > 0 ? list_in[blockIdx.x + gridDim.x] : (int)(blockIdx.x + gridDim.x);
-    const bool fused_halos = pv.has_lo || pv.has_hi;
+    constexpr bool fused_halos = FUSED;
     // Fused halos: when the last CTA is done, this kernel's event is published to the neighbours — on every path.
     auto finish = [&]() {
-        if (!fused_halos) return;
+        if constexpr (!FUSED) return;
         __syncthreads();
         if (tid == 0) {
             __threadfence_system();
@@ -328,8 +331,9 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
 
     // Fused halos: a brick of the lowest / highest layer reads halo planes the neighbour's previous kernel wrote and
     // stores into the neighbour's halo planes that its previous kernel still read: wait for that kernel (once per side).
-    bool waited_lo = !pv.has_lo, waited_hi = !pv.has_hi;
+    bool waited_lo = !FUSED || !pv.has_lo, waited_hi = !FUSED || !pv.has_hi;
     auto peer_sync = [&](const bool lo, const bool hi) {  // uniform; thread 0 polls
+        if constexpr (!FUSED) return;
         const bool wl = lo && !waited_lo, wh = hi && !waited_hi;
         if (!(wl || wh)) return;
         if (tid == 0) peer_wait(pv, need, wl, wh);
@@ -338,8 +342,8 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     };
     const int layer = P.ntx * P.nty;
     auto brick_faces = [&](const int brick, bool& lo, bool& hi) {
-        lo = pv.has_lo && brick < layer;
-        hi = pv.has_hi && brick >= layer * (P.nzc - 1);
+        lo = FUSED && pv.has_lo && brick < layer;
+        hi = FUSED && pv.has_hi && brick >= layer * (P.nzc - 1);
     };
 
     // The frozen bricks of the previous pass: one copy each into the other pressure buffer.  Of the bricks that froze
@@ -372,7 +376,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                     peer_sync(lo, hi);
                     __syncthreads();
                 }
-                copy_frozen_brick<S>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
+                copy_frozen_brick<S, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
                 if (tid == 0) ++s_copied;
             }
             __syncthreads();
@@ -388,7 +392,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                 peer_sync(lo, hi);
                 __syncthreads();
             }
-            copy_frozen_brick<S>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
+            copy_frozen_brick<S, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
         }
         if (tid == 0 && blockIdx.x == 0) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
     }
@@ -442,7 +446,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     };
 #pragma unroll
     for (int i = 0; i < S::kDepth; ++i) issue_next();
-    if (fused_halos) __syncthreads();  // thread 0's waits above come before anybody's loads of the neighbours' data
+    if constexpr (FUSED) __syncthreads();  // thread 0's waits above come before anybody's loads of the neighbours' data
 
     // ---- consumer ------------------------------------------------------------------------------------------------
     unsigned consumed = 0;        // bundles consumed so far = flat index of the next bundle
@@ -637,7 +641,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                             const size_t mat = ((size_t)z * P.ny + (gyb + r)) * nxb + (gx >> 3);
                             const unsigned char byte = (unsigned char)(nib | (hi << 4));
                             if (mine && (li & 1)) m_out[mat] = byte;
-                            if (to_lo || to_hi) {  // the same stores into the neighbour's halo planes
+                            if (FUSED && (to_lo || to_hi)) {  // the same stores into the neighbour's halo planes
                                 const long long plane_f = (long long)P.ny * P.pitch, plane_b = (long long)P.ny * nxb;
                                 if (mine && to_lo) *reinterpret_cast<float4*>(peers.p[0][pi] + (long long)at + pv.dz_lo * plane_f) = out[r];
                                 if (mine && to_hi) *reinterpret_cast<float4*>(peers.p[1][pi] + (long long)at + pv.dz_hi * plane_f) = out[r];
@@ -731,12 +735,12 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
 // in both buffers once copied — except the bricks relaxed by the last executed pass L when that pass wrote the other
 // buffer (L odd): those (pass L + 1's relax and copy lists) are copied into Y here.  Also the solve's bookkeeping that
 // finish_solve_kernel does for the per-sweep path: s_exec, pass count (which buffer holds P: jacobi_flip_kernel).
-template <class S>
+template <class S, bool FUSED>
 __global__ void __launch_bounds__(S::kThreads)
 jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                      unsigned char* m0, unsigned char* m1, const __grid_constant__ WorkLists W,
-                     const __grid_constant__ PassParams P, const int t_first, const int n_early, const int t_late,
-                     const int force_passes, const __grid_constant__ PeerView pv,
+                     const __grid_constant__ PassParams P, const int fuse_t, const int force_passes,
+                     const __grid_constant__ PeerView pv,
                      const __grid_constant__ JacobiPeers peers) {
     const int iters = P.levels_total;
     const bool live = 0.0f < frame->dt && iters > 0;
@@ -745,7 +749,7 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
         s = 1;
         while (s < iters && state->active_after[s - 1] != 0ull) ++s;
     }
-    int passes = s <= n_early * t_first ? (s + t_first - 1) / t_first : n_early + (s - n_early * t_first + t_late - 1) / t_late;
+    int passes = (s + fuse_t - 1) / fuse_t;
     if (force_passes >= 0 && live) passes = force_passes;
     const int p_cur = state->p_cur;  // still the frame's input buffer X; Y is the other one
     if (passes > 0 && ((passes - 1) & 1)) {
@@ -757,12 +761,12 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
         const int n_r = W.relax_count[L + 1], n_c = W.copy_count[L + 1];
         const int* __restrict__ lr = W.relax[(L + 1) & 1];
         const int* __restrict__ lc = W.copy[(L + 1) & 1];
-        if ((pv.has_lo || pv.has_hi) && n_r + n_c > 0) {  // the neighbours' last pass no longer reads the halos written here
+        if (FUSED && n_r + n_c > 0) {  // the neighbours' last pass no longer reads the halos written here
             if (threadIdx.x == 0) peer_wait(pv, frame->epoch_base + (unsigned long long)P.event, true, true);
             __syncthreads();
         }
         for (int w = blockIdx.x; w < n_r + n_c; w += gridDim.x)
-            copy_frozen_brick<S>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r], pv, peers, pi, mi);
+            copy_frozen_brick<S, FUSED>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r], pv, peers, pi, mi);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // (p_cur itself is flipped by the next kernel: other CTAs still read it)
         state->s_exec = s;
@@ -812,16 +816,12 @@ bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int pitch, in
 }
 
 // The shapes in use.  Wide: tile rows of 32 lanes (128 cells); narrow: 16 lanes (64 cells, a warp covers two row groups),
-// chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as possible.  The default
-// schedule runs T = 2 throughout on one brick grid (own region 120 x 12 or 56 x 28 cells) with two kernel shapes:
-//   the first passes (many bricks to relax: throughput)  2 rows per thread,  8 warps, two CTAs per SM, TMA depth 3;
-//   the later passes (one brick chain per SM sets the pace: latency)  1 row per thread, 16 warps on the same tile, one CTA
-//   per SM, TMA depth 4 — half the dependent work per warp and twice the warps to interleave.
-// A uniform schedule (fxb_config.fuse_t = 1..4) uses the two-CTA shape for T <= 2 and a one-CTA shape above.
+// chosen per grid by fused_jacobi_plan so that the tiles overhang the grid's faces as little as possible.  T <= 2: two
+// rows per thread, 8 warps, two CTAs per SM, TMA depth 3 (the default, T = 2); T > 2: one CTA per SM.  Measured on B200
+// (profiles/): fusing 4 sweeps in the later passes, or spreading a tile over 16 one-row warps there, made the
+// latency-bound tail of the solve slower, not faster, so one shape runs every pass.
 template <int T> using WideU = Shape<T, 32, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
 template <int T> using NarrowU = Shape<T, 16, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 : 1)>;
-using WideLate = Shape<2, 32, 16, 4, 1, 1>;    // tile 128 x 16, as WideU<2>
-using NarrowLate = Shape<2, 16, 16, 4, 1, 1>;  // tile 64 x 32, as NarrowU<2>
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
@@ -832,8 +832,10 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_device != dev) {
-        cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)S::kBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(jacobi_pass_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
         if (e != cudaSuccess) return e;
         attr_device = dev;
     }
@@ -849,7 +851,7 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     P.keep_lo = d.z_own0 > 0 ? 1 : 0;
     P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
     P.event = 2 + pass;
-    P.push_depth = std::max(J.T, J.T_late);
+    P.push_depth = J.T;
     JacobiPeers peers;
     for (int side = 0; side < 2; ++side)
         for (int i = 0; i < 2; ++i) {
@@ -865,12 +867,15 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np;
     W.brick_flag = J.brick_flag;
-    const bool late = S::kTileY != J.tile_y;  // the later passes' kernel of the mixed schedule stages a taller tile
-    jacobi_pass_kernel<S><<<grid, S::kThreads, S::kBytes, stream>>>(
-        *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[0] : J.map_p[0]),
-        *reinterpret_cast<const CUtensorMap*>(late ? J.map_p_late[1] : J.map_p[1]),
-        *reinterpret_cast<const CUtensorMap*>(late ? J.map_rhs_late : J.map_rhs), frame, state, J.p[0], J.p[1], J.mask[0],
-        J.mask[1], W, P, pv, peers);
+    const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map_p[0]);
+    const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map_p[1]);
+    const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map_rhs);
+    if (pv.has_lo || pv.has_hi)
+        jacobi_pass_kernel<S, true><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], J.p[1],
+                                                                              J.mask[0], J.mask[1], W, P, pv, peers);
+    else
+        jacobi_pass_kernel<S, false><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], J.p[1],
+                                                                               J.mask[0], J.mask[1], W, P, pv, peers);
     return cudaGetLastError();
 }
 
@@ -883,14 +888,7 @@ bool fused_jacobi_supported(const Domain& d) { return d.nz > 1 && d.nx >= 8 && (
 
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs) {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
-    // fuse_t = 0: the mixed schedule (T = 2, then T = 4 on the same bricks); otherwise T = fuse_t throughout
-    J->mixed = fuse_t == 0;
-    J->T = J->mixed ? 2 : fuse_t;
-    J->T_late = J->T;
-    // the first passes still relax many bricks (throughput shape); afterwards one brick chain per SM sets the pace
-    // (latency shape: same T, same tile, twice the warps)
-    J->n_early = J->mixed ? 4 : 1;
-    if (const char* e = getenv("FXB_EARLY")) J->n_early = std::max(1, atoi(e));  // tuning knob
+    J->T = fuse_t == 0 ? 2 : fuse_t;  // 0 = library default
     const int T = J->T;
     // tile shape: the one whose tiles cover the least area beyond the grid (compute and staging are per tile cell)
     const long long wide = (long long)tiles_for(d.nx, 120) * 128 * tiles_for(d.ny, 16 - 2 * T) * 16;
@@ -910,15 +908,9 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     }
     J->nzc = (nz_out + J->bz - 1) / J->bz;
     J->p[0] = p0; J->p[1] = p1; J->rhs = rhs;
-    float* base[3] = {p0, p1, rhs};
-    for (int i = 0; i < 3; ++i) {
-        unsigned char* first = i < 2 ? J->map_p[i] : J->map_rhs;
-        unsigned char* late = i < 2 ? J->map_p_late[i] : J->map_rhs_late;
-        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(first), base[i], d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
-        // the later passes' tile: the same own region under a halo of T_late rows
-        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(late), base[i], d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x,
-                            out_y + 2 * J->T_late)) return -1;
-    }
+    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
+    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[1]), p1, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
+    if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&J->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
@@ -927,16 +919,7 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     return 0;
 }
 
-int fused_jacobi_passes(const FusedJacobi& J, int iters) {
-    if (iters <= 0) return 0;
-    if (iters <= J.n_early * J.T) return (iters + J.T - 1) / J.T;
-    return J.n_early + (iters - J.n_early * J.T + J.T_late - 1) / J.T_late;
-}
-
-void fused_jacobi_pass_spec(const FusedJacobi& J, int pass, int* T, int* s0) {
-    *T = pass < J.n_early ? J.T : J.T_late;
-    *s0 = pass < J.n_early ? pass * J.T : J.n_early * J.T + (pass - J.n_early) * J.T_late;
-}
+int fused_jacobi_passes(const FusedJacobi& J, int iters) { return iters <= 0 ? 0 : (iters + J.T - 1) / J.T; }
 
 size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty * J.nzc; }
 
@@ -949,14 +932,9 @@ void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
                                      const PeerView& pv, cudaStream_t stream) {
-    int T, s0;
-    fused_jacobi_pass_spec(J, pass, &T, &s0);
+    const int s0 = pass * J.T;
 #define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream)
-    if (J.mixed && pass >= J.n_early) {
-        if (J.narrow) FXB_LAUNCH(NarrowLate);
-        FXB_LAUNCH(WideLate);
-    }
-    switch (T) {
+    switch (J.T) {
         case 1: if (J.narrow) FXB_LAUNCH(NarrowU<1>); FXB_LAUNCH(WideU<1>);
         case 2: if (J.narrow) FXB_LAUNCH(NarrowU<2>); FXB_LAUNCH(WideU<2>);
         case 3: if (J.narrow) FXB_LAUNCH(NarrowU<3>); FXB_LAUNCH(WideU<3>);
@@ -975,7 +953,7 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
     P.levels_total = iters;
     const int npass = fused_jacobi_passes(J, iters);
     P.event = 2 + npass;
-    P.push_depth = std::max(J.T, J.T_late);
+    P.push_depth = J.T;
     JacobiPeers peers;
     for (int side = 0; side < 2; ++side)
         for (int i = 0; i < 2; ++i) {
@@ -990,7 +968,11 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
     W.brick_flag = J.brick_flag;
     const int grid = J.num_sms * 2;
     // geometry of the own region only (shared by every shape of the schedule)
-#define FXB_SETTLE(S) jacobi_settle_kernel<S><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.n_early, J.T_late, force_passes, pv, peers)
+#define FXB_SETTLE(S)                                                                                                     \
+    if (pv.has_lo || pv.has_hi)                                                                                           \
+        jacobi_settle_kernel<S, true><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, force_passes, pv, peers); \
+    else                                                                                                                  \
+        jacobi_settle_kernel<S, false><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, force_passes, pv, peers)
     if (J.narrow) {
         switch (J.T) {
             case 1: FXB_SETTLE(NarrowU<1>); break;

@@ -51,10 +51,7 @@ void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FramePar
 
 // jacobi_fused.cu — T sweeps fused per HBM pass (tuned path, kernel_path = 0)
 struct FusedJacobi {
-    int T = 0;                 // sweeps fused by the first pass (1..4)
-    int T_late = 0;            // sweeps fused by every later pass (the mixed default schedule: 2, then 4)
-    bool mixed = false;        // default schedule: the later passes run the latency-optimised kernel shape
-    int n_early = 1;           // passes that fuse T sweeps; every later pass fuses T_late
+    int T = 0;                 // sweeps fused per pass (1..4)
     bool copy_all = false;     // copy every brick that froze in the first pass (grouped multi-GPU exchange), not only those
                                // next to an active brick
     int* brick_flag = nullptr; // [bricks] per frame: bit 0 = froze in the first pass, bit 1 = next to a still-active brick
@@ -62,7 +59,7 @@ struct FusedJacobi {
     float* peer_p[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     unsigned char* peer_m[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     bool narrow = false;       // tile 64 x 32 (a warp covers two row pairs) instead of 128 x 16
-    int tile_x = 128, tile_y = 16;  // tile of the first pass
+    int tile_x = 128, tile_y = 16;
     int ntx = 0, nty = 0, nzc = 0, bz = 0;  // brick grid and planes per brick
     float* p[2] = {nullptr, nullptr};
     float* rhs = nullptr;
@@ -74,11 +71,8 @@ struct FusedJacobi {
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
-    alignas(64) unsigned char map_p_late[2][128];  // the same arrays under the later passes' (taller) tile
-    alignas(64) unsigned char map_rhs_late[128];
 };
-int fused_jacobi_passes(const FusedJacobi& J, int iters);                      // launches per frame
-void fused_jacobi_pass_spec(const FusedJacobi& J, int pass, int* T, int* s0);  // sweeps fused by / completed before a pass
+int fused_jacobi_passes(const FusedJacobi& J, int iters);  // launches per frame
 bool fused_jacobi_supported(const Domain& d);
 int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
 size_t fused_jacobi_bricks(const FusedJacobi& J);

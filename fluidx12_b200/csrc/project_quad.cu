@@ -54,6 +54,7 @@ __device__ __forceinline__ Rows rows_of(const Domain& d, int x0, int y, int z) {
 // earlier by the neighbouring threads of the CTA) and the two x-edge texels come through L1 again.
 constexpr int kDivPlanes = 8;
 
+template <bool FUSED>  // FUSED: multi-GPU with fused halos (common.cuh PeerView)
 __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __grid_constant__ PeerView pv,
                                                               const FrameParams* __restrict__ frame,
                                                               const uint2* __restrict__ vel, float* __restrict__ rhs,
@@ -65,8 +66,9 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
     const int z_end = min(z_begin + kDivPlanes, d.z_own1);
     // fused halos (common.cuh PeerView): the chunks at an interior face read the neighbour's first / last plane of the
     // advected velocity and store their right-hand side into the neighbour's halo as well (event m = 1)
-    const bool near_lo = pv.has_lo && z_begin < d.z_own0 + push_depth, near_hi = pv.has_hi && z_end > d.z_own1 - push_depth;
-    if (near_lo || near_hi) {
+    const bool near_lo = FUSED && pv.has_lo && z_begin < d.z_own0 + push_depth;
+    const bool near_hi = FUSED && pv.has_hi && z_end > d.z_own1 - push_depth;
+    if (FUSED && (near_lo || near_hi)) {
         if (threadIdx.x == 0 && threadIdx.y == 0) peer_wait(pv, frame->epoch_base + 1, near_lo, near_hi);
         __syncthreads();
     }
@@ -123,9 +125,9 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
         }
         const float4 res = make_float4(out[0], out[1], out[2], out[3]);
         *reinterpret_cast<float4*>(rhs + zc + row_c) = res;
-        if (near_lo && z < d.z_own0 + push_depth)
+        if (FUSED && near_lo && z < d.z_own0 + push_depth)
             *reinterpret_cast<float4*>(rhs_lo + (long long)zc + (long long)pv.dz_lo * plane + row_c) = res;
-        if (near_hi && z >= d.z_own1 - push_depth)
+        if (FUSED && near_hi && z >= d.z_own1 - push_depth)
             *reinterpret_cast<float4*>(rhs_hi + (long long)zc + (long long)pv.dz_hi * plane + row_c) = res;
         // march: the centre plane becomes the plane below, the plane above becomes the centre
         fz[0] = h_lo(c.a.y); fz[1] = h_lo(c.a.w); fz[2] = h_lo(c.b.y); fz[3] = h_lo(c.b.w);
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
     }
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables tab,
                                                             const __grid_constant__ PeerView pv,
                                                             const FrameParams* __restrict__ frame,
@@ -146,8 +149,8 @@ __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables
     const int z = d.z_own0 + blockIdx.z;
     // fused halos (common.cuh PeerView): the first / last plane reads the neighbour's pressure plane, and the planes the
     // neighbour's next advection can reach are stored into its halo as well
-    const bool near_lo = pv.has_lo && z < d.z_own0 + reach, near_hi = pv.has_hi && z >= d.z_own1 - reach;
-    if (near_lo || near_hi) {
+    const bool near_lo = FUSED && pv.has_lo && z < d.z_own0 + reach, near_hi = FUSED && pv.has_hi && z >= d.z_own1 - reach;
+    if (FUSED && (near_lo || near_hi)) {
         if (threadIdx.x == 0 && threadIdx.y == 0) peer_wait(pv, frame->epoch_base + event, near_lo, near_hi);
         __syncthreads();
     }
@@ -162,8 +165,9 @@ __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables
         const float4 pc = __ldg(reinterpret_cast<const float4*>(p + r.c));
         const float4 pu = __ldg(reinterpret_cast<const float4*>(p + r.u));
         const float4 pd = __ldg(reinterpret_cast<const float4*>(p + r.d));
-        const float4 pf = __ldcg(reinterpret_cast<const float4*>(p + r.f));  // may be a halo plane a neighbour wrote
-        const float4 pb = __ldcg(reinterpret_cast<const float4*>(p + r.b));
+        // (fused halos: these may be halo planes a neighbour wrote during this frame: no non-coherent load)
+        const float4 pf = FUSED ? __ldcg(reinterpret_cast<const float4*>(p + r.f)) : __ldg(reinterpret_cast<const float4*>(p + r.f));
+        const float4 pb = FUSED ? __ldcg(reinterpret_cast<const float4*>(p + r.b)) : __ldg(reinterpret_cast<const float4*>(p + r.b));
         const unsigned row = r.c - x0;
         const float px[6] = {__ldg(p + row + r.xl), pc.x, pc.y, pc.z, pc.w, __ldg(p + row + r.xr)};
         const float pU[4] = {pu.x, pu.y, pu.z, pu.w}, pD[4] = {pd.x, pd.y, pd.z, pd.w};
@@ -197,12 +201,12 @@ __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables
     o[0] = oa;
     o[1] = ob;
     const long long plane = (long long)d.nx * d.ny;
-    if (near_lo) {
+    if (FUSED && near_lo) {
         uint4* q = reinterpret_cast<uint4*>(vel_out_lo + (long long)r.c + pv.dz_lo * plane);
         q[0] = oa;
         q[1] = ob;
     }
-    if (near_hi) {
+    if (FUSED && near_hi) {
         uint4* q = reinterpret_cast<uint4*>(vel_out_hi + (long long)r.c + pv.dz_hi * plane);
         q[0] = oa;
         q[1] = ob;
@@ -218,16 +222,25 @@ bool quad_kernels_supported(const Domain& d) { return d.nz > 1 && (d.nx % 8) == 
 void launch_divergence_quad(const Domain& d, const FrameParams* frame, const void* vel, float* rhs, const PeerView& pv,
                             float* rhs_lo, float* rhs_hi, int push_depth, cudaStream_t stream) {
     const dim3 grid((d.nx / 4 + 31) / 32, (d.ny + 7) / 8, (d.z_own1 - d.z_own0 + kDivPlanes - 1) / kDivPlanes);
-    divergence_quad_kernel<<<grid, dim3(32, 8), 0, stream>>>(d, pv, frame, (const uint2*)vel, rhs, rhs_lo, rhs_hi,
-                                                             push_depth);
+    if (pv.has_lo || pv.has_hi)
+        divergence_quad_kernel<true><<<grid, dim3(32, 8), 0, stream>>>(d, pv, frame, (const uint2*)vel, rhs, rhs_lo, rhs_hi,
+                                                                       push_depth);
+    else
+        divergence_quad_kernel<false><<<grid, dim3(32, 8), 0, stream>>>(d, pv, frame, (const uint2*)vel, rhs, rhs_lo,
+                                                                        rhs_hi, push_depth);
 }
 
 void launch_gradient_quad(const Domain& d, const AxisTables& tab, const FrameParams* frame, const void* vel_in,
                           const float* p0, const float* p1, void* vel_out, const StepState* state, const PeerView& pv,
                           void* vel_out_lo, void* vel_out_hi, int reach, int event, cudaStream_t stream) {
-    gradient_quad_kernel<<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, tab, pv, frame, (const uint2*)vel_in, p0, p1,
-                                                                   (uint2*)vel_out, state, (uint2*)vel_out_lo,
-                                                                   (uint2*)vel_out_hi, reach, event);
+    if (pv.has_lo || pv.has_hi)
+        gradient_quad_kernel<true><<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, tab, pv, frame, (const uint2*)vel_in, p0, p1,
+                                                                             (uint2*)vel_out, state, (uint2*)vel_out_lo,
+                                                                             (uint2*)vel_out_hi, reach, event);
+    else
+        gradient_quad_kernel<false><<<quad_grid(d), dim3(32, 8), 0, stream>>>(d, tab, pv, frame, (const uint2*)vel_in, p0,
+                                                                              p1, (uint2*)vel_out, state, (uint2*)vel_out_lo,
+                                                                              (uint2*)vel_out_hi, reach, event);
 }
 
 }  // namespace fxb
