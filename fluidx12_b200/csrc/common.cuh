@@ -47,6 +47,9 @@ struct StepState {
     int pad0;
     unsigned long long phase_ns[8];      // cumulative device time per phase (phase marks; fxb_config.phase_timing)
     unsigned long long mark_ns;          // %globaltimer of the last phase mark
+#ifdef FXB_TIMING
+    long long dbg[128];                  // debug build: cycle stamps (jacobi_fused.cu FXB_STAMP)
+#endif
 };
 
 // ---- fused halos (multi-GPU, fxb_config.halo_backend = FXB_HALO_FUSED) ------------------------------------------

@@ -812,6 +812,14 @@ int fxb_profile_step(fxb_sim* s, float* ms, int n) {
     return FXB_OK;
 }
 
+#ifdef FXB_TIMING
+int fxb_debug_stamps(fxb_sim* s, long long* out, int n) {  // debug build only (not in the header)
+    if (!s || !out || n > 128) return FXB_ERR_INVALID;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, s->d_state->dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? FXB_OK : FXB_ERR_CUDA;
+}
+#endif
+
 int fxb_state_checksum(fxb_sim* s, uint64_t* out3) {
     if (!s || !out3) return fail(FXB_ERR_INVALID, "fxb_state_checksum: null argument");
     FXB_CUDA(cudaSetDevice(s->cfg.device));

@@ -277,6 +277,10 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     constexpr unsigned kFull = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = lane & (LX - 1), sub = lane / LX;
+    // (A ninth warp that only feeds the TMA stream was measured on B200: it takes the ~300 cycles a bundle costs its
+    // issuing thread off the relaxing warps' path, but 9 warps per CTA split unevenly over the 4 SM sub-partitions and
+    // cap the kernel at 96 registers — spills, 2x slower.  Thread 0 issues.)
+    constexpr bool producer = false;
 
     // independent loads first (one round trip instead of a chain), then the decisions
     const int pass = P.pass, s0 = P.s0;
@@ -291,6 +295,14 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     int pre_a = pass > 0 ? list_in[blockIdx.x] : (int)blockIdx.x;
     int pre_b = pass > 0 ? list_in[blockIdx.x + gridDim.x] : (int)(blockIdx.x + gridDim.x);
     constexpr bool fused_halos = FUSED;
+#ifdef FXB_TIMING
+    // debug build: cycle stamps of the first CTA's first brick into StepState::dbg (tools/timing_probe.py)
+    int dbg_n = 0;
+#define FXB_STAMP() do { if (tid == 0 && blockIdx.x == 0 && pass == FXB_TIMING && dbg_n < 120) state->dbg[dbg_n++] = clock64(); } while (0)
+#else
+#define FXB_STAMP() do {} while (0)
+#endif
+    FXB_STAMP();
     // Fused halos: when the last CTA is done, this kernel's event is published to the neighbours — on every path.
     auto finish = [&]() {
         if constexpr (!FUSED) return;
@@ -384,7 +396,8 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (tid == 0 && s_copied) atomicAdd(&state->bricks_copied, (unsigned long long)s_copied);
     } else if (n_copy > 0) {
         const int* __restrict__ copy_list = W.copy[pass & 1];
-        for (int w = blockIdx.x; w < n_copy; w += gridDim.x) {
+        // handed out from the LAST CTA down: in the late passes the first CTAs are the ones that relax bricks
+        for (int w = gridDim.x - 1 - blockIdx.x; w < n_copy; w += gridDim.x) {
             const int brick = copy_list[w];
             bool lo, hi;
             brick_faces(brick, lo, hi);
@@ -397,6 +410,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (tid == 0 && blockIdx.x == 0) atomicAdd(&state->bricks_copied, (unsigned long long)n_copy);
     }
     __syncthreads();  // barriers initialised
+    FXB_STAMP();
 
     const int n_ext = P.ntx * P.nty * ((P.ext_lo + P.bz - 1) / P.bz + (P.ext_hi + P.bz - 1) / P.bz);
     const int n_work = n_relax + n_ext;
@@ -482,6 +496,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
             if (gyb + r >= 0 && gyb + r < P.ny) dom_bits |= qmask << (4 * r);
             if (li >= 1 && li <= LX - 2 && ry0 + r >= T && ry0 + r < kTileY - T) own_bits |= 0xFu << (4 * r);
         }
+        if (producer) dom_bits = 0;  // (its row index lies outside the tile)
         own_bits &= dom_bits;
         int off0 = ry0 * kTileX + 4 * li;  // own quad of row 0 inside a staged plane; row r: + r * kTileX
         const bool clamp_u = ry0 == 0 || gyb <= 0;                                       // no row above inside the grid / tile
@@ -522,8 +537,10 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         };
         const int nib_shift = gx & 4;
         unsigned raw_a0 = 0, raw_a1 = 0, raw_b0 = 0, raw_b1 = 0;  // bytes of the plane consumed next / the one after
-        fetch_flags(zl0, raw_a0, raw_a1);
-        fetch_flags(zl0 + 1, raw_b0, raw_b1);
+        if (!producer) {
+            fetch_flags(zl0, raw_a0, raw_a1);
+            fetch_flags(zl0 + 1, raw_b0, raw_b1);
+        }
 
         // z queue: level l (0..T-1) keeps the previous and the centre plane of this thread's column, with the flags of
         // the centre plane
@@ -556,18 +573,24 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
             float4 nw[kRows];   // the plane the level below produced in this iteration
             unsigned nfl = 0;
             bool have = k < zl1;
+            FXB_STAMP();
             if (have) {
                 issue_next();
-                mbar_wait(&bars[consumed % S::kBars], (consumed / S::kBars) & 1u);
-                const float* src = sm_p + po_new + off0;
+                FXB_STAMP();
+                if (!producer) {
+                    mbar_wait(&bars[consumed % S::kBars], (consumed / S::kBars) & 1u);
+                    FXB_STAMP();
+                    const float* src = sm_p + po_new + off0;
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) nw[r] = *reinterpret_cast<const float4*>(src + r * kTileX);
-                fix_ghosts(nw);
-                nfl = pass == 0 ? dom_bits
-                                : ((((raw_a0 >> nib_shift) & 0xFu) | (((raw_a1 >> nib_shift) & 0xFu) << 4)) & dom_bits);
-                raw_a0 = raw_b0;
-                raw_a1 = raw_b1;
-                fetch_flags(k + 2, raw_b0, raw_b1);
+                    for (int r = 0; r < kRows; ++r) nw[r] = *reinterpret_cast<const float4*>(src + r * kTileX);
+                    fix_ghosts(nw);
+                    nfl = pass == 0 ? dom_bits
+                                    : ((((raw_a0 >> nib_shift) & 0xFu) | (((raw_a1 >> nib_shift) & 0xFu) << 4)) & dom_bits);
+                    raw_a0 = raw_b0;
+                    raw_a1 = raw_b1;
+                    FXB_STAMP();
+                    fetch_flags(k + 2, raw_b0, raw_b1);
+                }
                 ++consumed;
             } else {
 #pragma unroll
@@ -665,10 +688,12 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
                 nfl = st;
                 have = run;
             };
-            level(std::integral_constant<int, 1>{});
-            if constexpr (T >= 2) level(std::integral_constant<int, 2>{});
-            if constexpr (T >= 3) level(std::integral_constant<int, 3>{});
-            if constexpr (T >= 4) level(std::integral_constant<int, 4>{});
+            if (!producer) {
+                level(std::integral_constant<int, 1>{});
+                if constexpr (T >= 2) level(std::integral_constant<int, 2>{});
+                if constexpr (T >= 3) level(std::integral_constant<int, 3>{});
+                if constexpr (T >= 4) level(std::integral_constant<int, 4>{});
+            }
             // ring positions of the next iteration
             po_prev = po_new;
             po_new = po_new + kPlane == S::kPSlots * kPlane ? 0 : po_new + kPlane;
@@ -676,6 +701,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
             for (int l = T; l >= 1; --l) ro[l] = ro[l - 1];
             ro[0] = ro[0] + kPlane == S::kRSlots * kPlane ? 0 : ro[0] + kPlane;
             pub_w ^= 1;
+            FXB_STAMP();
             __syncthreads();
         }
 
