@@ -98,7 +98,6 @@ def main():
             dist.send(mine, dst=0)
         # the cube-map marches on z-slabs (colour and light map of the whole grid gathered on every rank): every rank
         # ends up with the complete cube map, which must be the single-GPU one
-        import ctypes as C
         v = fx.FxbViewParams()
         v.eye_pt[:] = [4.0, 16.0, -40.0]
         v.world_i[:] = lp.world_i[:]
