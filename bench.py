@@ -118,7 +118,8 @@ def make_sim(fx, grid, args, rank, world, local_rank, uid):
     ok = f.Init(gridSize=grid, address_mode=fx.ADDRESS_MIRROR, early_exit=bool(args.early_exit), jacobi_iters=64,
                 fuse_t=args.fuse_t, device=local_rank, rank=rank, nranks=world, use_graph=True,
                 kernel_path=args.kernel_path, phase_timing=True,
-                halo_backend=fx.HALO_NCCL if args.halo == "nccl" else fx.HALO_PEER, jacobi_group=args.jacobi_group,
+                halo_backend={"nccl": fx.HALO_NCCL, "peer": fx.HALO_PEER, "fused": fx.HALO_FUSED}[args.halo],
+                jacobi_group=args.jacobi_group,
                 nccl_unique_id=uid)
     if not ok:
         raise RuntimeError("fluidx_b200 Init failed: " + f.last_error)
@@ -520,7 +521,8 @@ def main():
     ap.add_argument("--fuse-t", type=int, default=0)
     ap.add_argument("--early-exit", type=int, default=1)
     ap.add_argument("--kernel-path", type=int, default=0)
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange backend")
+    ap.add_argument("--halo", default="fused", choices=["fused", "peer", "nccl"],
+                    help="N > 1: how slab-face halos travel (fused: stored by the kernels themselves; peer / nccl: exchanges)")
     ap.add_argument("--jacobi-group", type=int, default=0, help="N > 1: fused passes per pressure-halo exchange (0 = default)")
     ap.add_argument("--export-e2e", action="store_true", help="also time the e2e variant that copies the colour field out")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -86,7 +86,7 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     import ctypes as C
 
     import torch
-    fake_fx = types.SimpleNamespace(Fluid=FakeFluid, ADDRESS_MIRROR=0, FIELD_COLOR=1, HALO_PEER=0, HALO_NCCL=1,
+    fake_fx = types.SimpleNamespace(Fluid=FakeFluid, ADDRESS_MIRROR=0, FIELD_COLOR=1, HALO_PEER=0, HALO_NCCL=1, HALO_FUSED=2,
                                     dt_for_grid=lambda *g: 2.0 / g[1],
                                     FxbStats=type("S", (C.Structure,), {"_fields_": [("x", C.c_int * 24)]}))
     monkeypatch.setitem(sys.modules, "fluidx12_b200", fake_fx)
