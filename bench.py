@@ -345,10 +345,14 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
-    uid = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def fresh_uid():
+        """A new ncclUniqueId from rank 0 for every simulator (an id serves one communicator)."""
+        if world == 1:
+            return None
         import ctypes as C
         buf = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -358,7 +362,7 @@ def run_ours(args):
             buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
         buf = buf.cuda()
         dist.broadcast(buf, 0)
-        uid = bytes(buf.cpu().numpy().tobytes())
+        return bytes(buf.cpu().numpy().tobytes())
 
     strong = args.scaling == "strong"
     grid = tuple(args.grid) if args.grid else (STRONG_GRID if strong else WEAK_GRIDS.get(world))
@@ -371,7 +375,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    f, rec = measure_config(torch, dist, fx, args, grid, rank, world, local_rank, uid, stream, peak, peak_src, sampler)
+    f, rec = measure_config(torch, dist, fx, args, grid, rank, world, local_rank, fresh_uid(), stream, peak, peak_src, sampler)
     if rank == 0 and world == 1:
         # a very short timed region can end before nvidia-smi has answered once: keep the same load running
         # (untimed) until a few samples exist
@@ -439,7 +443,7 @@ def run_ours(args):
         line[key] = crec
     # config 4 (512^3 strong scaling) on the same N ranks: its checksum must equal the N = 1 line's state_checksum
     if world > 1 and not strong and not args.grid and not args.no_c4:
-        g, crec = measure_config(torch, dist, fx, args, STRONG_GRID, rank, world, local_rank, uid, stream, peak, peak_src)
+        g, crec = measure_config(torch, dist, fx, args, STRONG_GRID, rank, world, local_rank, fresh_uid(), stream, peak, peak_src)
         g.close()
         crec["workload"] = "3D 512^3 (BASELINE config 4) strong-scaled on %d ranks" % world
         line["c4_strong"] = {k: crec[k] for k in ("workload", "value", "ms_per_step", "state_checksum",
