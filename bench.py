@@ -307,7 +307,17 @@ def measure_config(torch, dist, fx, args, grid, rank, world, local_rank, uid, st
         raise SystemExit("advection back-trace left the z-halo: raise h_adv")
     voxels_local = nx * ny * f.slab[1]
     roof, per, jb, proc, cop = rooflines(grid, phases, st0, st1, args.steps, voxels_local, peak, peak_src)
+    per_rank = None
     if world > 1:
+        # every rank's own phase times and Jacobi work: the slab that holds the plume sets the pace of the step
+        mine = torch.tensor([phases.get(k, 0.0) for k in ("advect", "divergence", "jacobi", "gradient")] +
+                            [proc / max(args.steps, 1), cop / max(args.steps, 1)], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"advect_ms": round(float(v[0]), 4), "divergence_ms": round(float(v[1]), 4),
+                     "jacobi_ms": round(float(v[2]), 4), "gradient_ms": round(float(v[3]), 4),
+                     "bricks_relaxed_per_step": round(float(v[4]), 1), "bricks_copied_per_step": round(float(v[5]), 1)}
+                    for v in allr]
         t = torch.tensor([jb, proc, cop], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         jb, proc, cop = (float(v) for v in t.tolist())
@@ -330,6 +340,8 @@ def measure_config(torch, dist, fx, args, grid, rank, world, local_rank, uid, st
                              "nominal_note": "BASELINE.md formula 32+12+ceil(S/T)*12+20 assumes every pass touches "
                                              "every voxel; frozen bricks are skipped here, so it over-counts"},
            "roofline": roof, "phase_roofline": per, "phase_ms": {k: round(v, 4) for k, v in phases.items()}}
+    if per_rank is not None:
+        rec["per_rank"] = per_rank
     return f, rec
 
 
@@ -405,7 +417,7 @@ def run_ours(args):
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("FXB_")}},
         "state_checksum": rec["state_checksum"], "frames_from_zero": rec["frames_from_zero"],
         "step_roofline": rec["step_roofline"], "roofline": rec["roofline"], "phase_roofline": rec["phase_roofline"],
-        "phase_ms": rec["phase_ms"],
+        "phase_ms": rec["phase_ms"], "per_rank": rec.get("per_rank"),
         "e2e": {"value": voxels * args.steps / sec_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * sec_e2e / args.steps,
                 "what": "UpdateFrame(dt from pinned CB) + Simulate + fxb_get_stats readback, host-timed"},

@@ -16,6 +16,9 @@ for line in src:
           d["phase_ms"], "passes", d["config"]["jacobi_passes_per_step"], "step_roof", d["step_roofline"]["frac"],
           "dominant", d["roofline"]["kernel"], d["roofline"]["frac"], "e2e %.2f" % (d["e2e"]["value"] / 1e9), "checksum", d["state_checksum"])
     print("   phase fracs", {k: v["frac"] for k, v in d["phase_roofline"].items()}, "bricks", d["config"]["bricks_relaxed_per_step"], d["config"]["bricks_copied_per_step"], "clocks", d["clocks"])
+    if d.get("per_rank"):
+        for r, pr in enumerate(d["per_rank"]):
+            print("   rank %d" % r, pr)
     for key in ("c3", "c2", "c4_strong"):
         if key in d:
             c = d[key]
