@@ -115,7 +115,8 @@ class FxbVolumeHeader(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # FXB_LIB: another build of the same library (tools/timing_probe.py loads the -DFXB_TIMING debug build)
+    return os.environ.get("FXB_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None

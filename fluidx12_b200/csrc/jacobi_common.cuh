@@ -7,6 +7,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace fxb {
 
@@ -178,7 +179,7 @@ __device__ __noinline__ void copy_frozen_brick(const float* __restrict__ p_in, f
             const int xq = i % qpr, rz = i / qpr;
             zz[u] = it.zs + rz / rows;
             at[u] = ((size_t)zz[u] * P.ny + (y_lo + rz % rows)) * P.pitch + x_lo + 4 * xq;
-            if (i < total) v[u] = __ldcs(reinterpret_cast<const float4*>(p_in + at[u]));
+            if (i < total) v[u] = __ldcg(reinterpret_cast<const float4*>(p_in + at[u]));  // L2: written by another CTA, possibly in this launch
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -233,6 +234,45 @@ __device__ __forceinline__ unsigned relax_quad(const float4 c, const float4 lo, 
     out.z = (act & 4u) ? nb.x : c.z;
     out.w = (act & 8u) ? nb.y : c.w;
     return s;
+}
+
+// ---- host side: the kernel arguments of one pass, shared by the launchers of both kernels ----
+inline PassParams make_pass_params(const FusedJacobi& J, const Domain& d, int pass, int iters, int early_exit, bool run_all,
+                                   int ext_lo, int ext_hi) {
+    PassParams P;
+    P.nx = d.nx; P.ny = d.ny; P.pitch = d.pitch; P.nz_alloc = d.nz_alloc;
+    P.z_face_lo = 0 - d.z_first;
+    P.z_face_hi = d.nz - d.z_first;
+    P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
+    P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
+    P.pass = pass; P.s0 = pass * J.T; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
+    P.ext_lo = ext_lo; P.ext_hi = ext_hi;
+    P.copy_all = J.copy_all ? 1 : 0;
+    P.keep_lo = d.z_own0 > 0 ? 1 : 0;
+    P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
+    P.event = 2 + pass;
+    P.push_depth = J.T;
+    return P;
+}
+
+inline JacobiPeers make_jacobi_peers(const FusedJacobi& J) {
+    JacobiPeers peers;
+    for (int side = 0; side < 2; ++side)
+        for (int i = 0; i < 2; ++i) {
+            peers.p[side][i] = J.peer_p[side][i];
+            peers.m[side][i] = J.peer_m[side][i];
+        }
+    return peers;
+}
+
+inline WorkLists make_work_lists(const FusedJacobi& J) {
+    WorkLists W;
+    const int np = FusedJacobi::kMaxPasses + 1;
+    W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
+    W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
+    W.relax_count = J.work_count; W.copy_count = J.work_count + np;
+    W.brick_flag = J.brick_flag;
+    return W;
 }
 
 }  // namespace

@@ -607,12 +607,13 @@ EncodeTiledFn encode_fn() {
 
 // Tensor map of a pitched [nz_alloc][ny][pitch] float array seen as (nx, ny, nz_alloc): elements beyond nx / ny (and
 // tile parts at negative coordinates) arrive as zeros; the kernel never uses them (clamp by index).
-bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int pitch, int nz_alloc, int tile_x, int tile_y) {
+bool make_plane_map(CUtensorMap* map, float* base, int nx, int ny, int pitch, int nz_alloc, int tile_x, int tile_y,
+                    int tile_z = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz_alloc};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * ny * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)tile_x, (cuuint32_t)tile_y, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)tile_x, (cuuint32_t)tile_y, (cuuint32_t)tile_z};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -643,34 +644,12 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
         if (e != cudaSuccess) return e;
         attr_device = dev;
     }
-    PassParams P;
-    P.nx = d.nx; P.ny = d.ny; P.pitch = d.pitch; P.nz_alloc = d.nz_alloc;
-    P.z_face_lo = 0 - d.z_first;
-    P.z_face_hi = d.nz - d.z_first;
-    P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
-    P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
-    P.pass = pass; P.s0 = s0; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
-    P.ext_lo = ext_lo; P.ext_hi = ext_hi;
-    P.copy_all = J.copy_all ? 1 : 0;
-    P.keep_lo = d.z_own0 > 0 ? 1 : 0;
-    P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
-    P.event = 2 + pass;
-    P.push_depth = J.T;
-    JacobiPeers peers;
-    for (int side = 0; side < 2; ++side)
-        for (int i = 0; i < 2; ++i) {
-            peers.p[side][i] = J.peer_p[side][i];
-            peers.m[side][i] = J.peer_m[side][i];
-        }
+    const PassParams P = make_pass_params(J, d, pass, iters, early_exit, run_all, ext_lo, ext_hi);
+    const JacobiPeers peers = make_jacobi_peers(J);
     const int nbricks = J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
     const int grid = nbricks < slots ? nbricks : slots;
-    WorkLists W;
-    const int np = FusedJacobi::kMaxPasses + 1;
-    W.relax[0] = J.work_list[0]; W.relax[1] = J.work_list[1];
-    W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
-    W.relax_count = J.work_count; W.copy_count = J.work_count + np;
-    W.brick_flag = J.brick_flag;
+    const WorkLists W = make_work_lists(J);
     const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map_p[0]);
     const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map_p[1]);
     const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map_rhs);
@@ -715,6 +694,18 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
     if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[1]), p1, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
     if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
+    // Brick-resident form for the latency-bound part of the solve.  Measured on B200 (profiles/): from the second pass
+    // on the resident form is the faster one at 128^3, 256^3 and 512^3 (the first pass, every brick dense, is not).
+    J->resident_from = FusedJacobi::kMaxPasses + 1;
+    if (resident_jacobi_supported(*J)) {
+        const int planes = resident_jacobi_window_planes(*J);
+        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
+        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_p[1]), p1, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
+        if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
+        J->resident_from = 1;
+        if (const char* e = getenv("FXB_RESIDENT_FROM")) J->resident_from = atoi(e);  // tuning knob: first resident pass
+        if (const char* e = getenv("FXB_PDL")) J->pdl = atoi(e) != 0;                 // tuning knob: dependent launch on / off
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&J->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
@@ -736,6 +727,8 @@ void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
                                      const PeerView& pv, cudaStream_t stream) {
+    if (pass >= J.resident_from)
+        return launch_jacobi_pass_resident(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream);
     const int s0 = pass * J.T;
 #define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream)
     switch (J.T) {

@@ -71,6 +71,12 @@ struct FusedJacobi {
     static constexpr int kMaxPasses = 130;
     alignas(64) unsigned char map_p[2][128];      // CUtensorMap of each pressure buffer
     alignas(64) unsigned char map_rhs[128];
+    // brick-resident passes (jacobi_resident.cu): tensor maps whose box is a brick's whole window (tile x tile x 8 + 2T
+    // planes), and the first pass of a frame that runs in that form (kMaxPasses + 1: none)
+    alignas(64) unsigned char map3_p[2][128];
+    alignas(64) unsigned char map3_rhs[128];
+    int resident_from = kMaxPasses + 1;
+    bool pdl = true;           // resident passes are launched with programmatic stream serialization
 };
 int fused_jacobi_passes(const FusedJacobi& J, int iters);  // launches per frame
 bool fused_jacobi_supported(const Domain& d);
@@ -84,5 +90,12 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
                                      const PeerView& pv, cudaStream_t stream);
+
+// jacobi_resident.cu — the same pass with the brick's window resident in shared memory (the latency shape)
+bool resident_jacobi_supported(const FusedJacobi& J);
+int resident_jacobi_window_planes(const FusedJacobi& J);
+cudaError_t launch_jacobi_pass_resident(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
+                                        int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
+                                        const PeerView& pv, cudaStream_t stream);
 
 }  // namespace fxb
