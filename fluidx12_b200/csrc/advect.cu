@@ -211,7 +211,9 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
     const Domain& d = A.d;
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int z0 = d.z_own0 + blockIdx.z * kZ;  // global plane
+    // (fused halos: the chunks next to an interior face come last, see face_last_chunk)
+    const int zc = FUSED ? face_last_chunk(pv, blockIdx.z, gridDim.z, kZ, A.reach, d.z_own1 - d.z_own0) : (int)blockIdx.z;
+    const int z0 = d.z_own0 + zc * kZ;  // global plane
     const int z1 = min(z0 + kZ, d.z_own1);
     // fused halos: the planes next to an interior face wait for the neighbour's previous frame (event m = 0)
     const bool near_lo = FUSED && pv.has_lo && z0 < d.z_own0 + A.reach;

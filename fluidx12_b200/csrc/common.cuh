@@ -80,8 +80,13 @@ __device__ __forceinline__ void peer_wait(const PeerView& pv, const unsigned lon
     const long long t0 = clock64();
     for (int side = 0; side < 2; ++side) {
         if (!(side == 0 ? (lo && pv.has_lo) : (hi && pv.has_hi))) continue;
-        volatile unsigned long long* w = pv.events + side;
-        while (*w < need) {
+        const unsigned long long* w = pv.events + side;
+        for (;;) {
+            // acquire load at system scope: what the neighbour wrote before publishing is visible to what follows
+            // (measured on B200: ~2 us per wait cheaper than a relaxed poll followed by a full system fence)
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+            if (v >= need) break;
             if (clock64() - t0 > pv.timeout_cycles) {
                 *pv.error = 1ull;
                 break;
@@ -89,7 +94,8 @@ __device__ __forceinline__ void peer_wait(const PeerView& pv, const unsigned lon
             __nanosleep(32);
         }
     }
-    __threadfence_system();  // acquire: what the neighbour wrote before publishing is visible to what follows
+    // the neighbour's stores are also read through the async proxy (TMA) by the thread that waited
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 // One thread, after everything the kernel wrote (here and into the neighbours) is complete.
@@ -97,6 +103,20 @@ __device__ __forceinline__ void peer_publish(const PeerView& pv, const unsigned 
     __threadfence_system();
     if (pv.has_lo) *reinterpret_cast<volatile unsigned long long*>(pv.ev_lo + 1) = value;
     if (pv.has_hi) *reinterpret_cast<volatile unsigned long long*>(pv.ev_hi + 0) = value;
+}
+
+// Fused halos: the z chunks of a kernel that lie next to an interior slab face wait for the neighbour rank.  CTAs are
+// scheduled in blockIdx order, so those chunks are handed out LAST: the wait then overlaps the interior chunks instead
+// of occupying every SM with spinning CTAs.  b: blockIdx.z; returns the chunk it works on (interior chunks first, then
+// the n_lo chunks at the lower face, then the n_hi at the upper face).  `chunk` planes per chunk, `reach` planes next
+// to a face that wait, n owned planes.
+__device__ __forceinline__ int face_last_chunk(const PeerView& pv, int b, int nchunks, int chunk, int reach, int n) {
+    int n_lo = pv.has_lo ? (reach + chunk - 1) / chunk : 0;
+    int n_hi = pv.has_hi ? nchunks - max(n - reach, 0) / chunk : 0;
+    n_lo = min(n_lo, nchunks);
+    n_hi = min(n_hi, nchunks - n_lo);
+    const int n_int = nchunks - n_lo - n_hi;
+    return b < n_int ? b + n_lo : (b < n_int + n_lo ? b - n_int : b);
 }
 
 // Phase marks: the device time since the previous mark is added to StepState::phase_ns[slot] (slot < 0: start of a

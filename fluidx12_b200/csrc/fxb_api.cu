@@ -133,6 +133,13 @@ __global__ void phase_mark_kernel(fxb::StepState* state, int slot, const fxb::Fr
                                   const __grid_constant__ fxb::PeerView pv, unsigned long long event_offset) {
     if (slot >= 0) fxb::phase_mark(state, slot);
     if (pv.has_lo || pv.has_hi) fxb::peer_publish(pv, frame->epoch_base + event_offset);
+#ifdef FXB_TIMING
+    if (event_offset == 2) {  // debug build: the divergence ended = the pressure solve starts (tools/mgpu_probe.py)
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        state->dbg[106] = (long long)now;
+    }
+#endif
 }
 
 // State checksum (fxb_state_checksum): per field the wrap-around sum over the rank's own voxels of a 64-bit mix of the
@@ -165,6 +172,18 @@ __global__ void __launch_bounds__(256) checksum_kernel(fxb::Domain d, const uint
         atomicAdd(&out[1], b);
         atomicAdd(&out[2], c);
     }
+}
+
+// Multi-GPU: the global number of sweeps of the frame from the summed freeze counters (jacobi_settle_kernel leaves
+// s_exec alone there: it only sees this rank's counters).
+__global__ void global_sweeps_kernel(const fxb::FrameParams* frame, fxb::StepState* state, int iters) {
+    int s = 0;
+    if (0.0f < frame->dt && iters > 0) {
+        s = 1;
+        while (s < iters && state->active_after[s - 1] != 0ull) ++s;
+    }
+    state->s_exec = s;
+    state->total_sweeps += (unsigned long long)s;
 }
 
 struct Enqueue {
@@ -252,14 +271,30 @@ void enqueue_phase(Enqueue& q, int phase) {
                     }
                     q.launched(fxb::launch_jacobi_pass_fused(s->jac, d, s->d_frame, s->d_state, k, s->cfg.jacobi_iters,
                                                              s->cfg.early_exit, s->multi(), ext_lo, ext_hi, s->pv, st),
-                               "jacobi_pass_kernel");
+                               "jacobi_pass_kernel", fxb::fused_jacobi_launches(s->jac, s->pv, k));
                 }
-                if (mg) {
-                    // freeze counters are per rank: sum them so that s_exec is the global figure; every rank runs
-                    // all passes (a pass without active cells only copies), so the buffer parity stays in step
-                    if (q.ok && !s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, st)) {
+                if (mg || q.fused()) {  // (fused halos: ONE graph serves every frame, paused ones included)
+                    // Freeze counters are per rank: their sum over the ranks (NCCL all-reduce, in place) gives the global
+                    // s_exec.  Nothing on the data path needs it — every rank runs all passes, so the buffer parity stays
+                    // in step — hence it runs on a side stream beside the settle step and the gradient, and joins the
+                    // step's stream after the gradient (the next frame resets the counters).
+                    // (With the NCCL halo backend the communicator is busy on the step's stream: no second stream then.)
+                    const bool fork = s->cfg.halo_backend != FXB_HALO_NCCL;
+                    cudaStream_t ar = fork ? s->side_stream : st;
+                    if (fork) {
+                        cudaError_t e = cudaEventRecord(s->ev[6], st);
+                        if (e == cudaSuccess) e = cudaStreamWaitEvent(ar, s->ev[6], 0);
+                        if (e != cudaSuccess) q.launched(e, "fork to the side stream", 0);
+                    }
+                    if (q.ok && !s->comm.all_reduce_sum_u64(s->d_state->active_after, 128, ar)) {
                         q.ok = false;
                         q.err = "all-reduce of the freeze counters: " + fxb::halo_last_error();
+                    }
+                    global_sweeps_kernel<<<1, 1, 0, ar>>>(s->d_frame, s->d_state, s->cfg.jacobi_iters);
+                    q.launched(cudaGetLastError(), "global_sweeps_kernel");
+                    if (fork) {
+                        q.launched(cudaEventRecord(s->ev[7], ar), "cudaEventRecord", 0);
+                        s->side_forked = true;
                     }
                 }
                 q.launched(fxb::launch_jacobi_settle(s->jac, d, s->d_frame, s->d_state, s->cfg.jacobi_iters,
@@ -286,6 +321,10 @@ void enqueue_phase(Enqueue& q, int phase) {
                 fxb::launch_gradient(d, s->d_frame, s->vel[1], s->p[0], s->p[1], s->vel[0], s->d_state, st);
             q.launched(cudaGetLastError(), "gradient_kernel");
             q.mark(3, fxb::kEventsPerFrame);
+            if (s->side_forked) {  // the side stream (global freeze counters) joins here
+                q.launched(cudaStreamWaitEvent(st, s->ev[7], 0), "join of the side stream", 0);
+                s->side_forked = false;
+            }
             break;
     }
 }
@@ -423,6 +462,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         const int fuse = cfg->fuse_t ? cfg->fuse_t : 2;
         s->h_adv = cfg->h_adv > 0 ? cfg->h_adv : 8;  // 2|u_z| voxels; |u_z| stayed below 3 in every run
         s->jacobi_group = cfg->jacobi_group > 0 ? cfg->jacobi_group : 1;
+        if (cfg->halo_backend == FXB_HALO_FUSED) s->jacobi_group = 1;  // fused halos: every pass pushes its own face planes
         s->halo = std::max(s->h_adv + 1, fuse);  // the Jacobi group uses what the advection halo provides
         int thinnest = nz;
         for (int q = 0; q < R; ++q) thinnest = std::min(thinnest, (q + 1) * nz / R - q * nz / R);
@@ -464,6 +504,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_state, sizeof(fxb::StepState));
     if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, sizeof(fxb::StepState));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && cfg->nranks > 1) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&s->ev[i]);
     if (e != cudaSuccess)
         return cleanup_fail(fail(FXB_ERR_CUDA, std::string("fxb_create: allocation failed: ") + cudaGetErrorString(e)));
@@ -530,8 +571,10 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         rc = capture_graph(s, 0, 0);
         if (rc != FXB_OK) return cleanup_fail(rc);
     } else {
-        const int jl = s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) : s->cfg.jacobi_iters;
-        s->kernels_per_step = 1 + 1 + 2 + jl + (s->fused ? 2 : 1) + 1 + ((s->cfg.phase_timing || (s->multi() && cfg->halo_backend == FXB_HALO_FUSED)) ? 2 : 0);
+        const int jl = s->fused ? fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters) - 1 + fxb::fused_jacobi_launches(s->jac, s->pv, 0)
+                                : s->cfg.jacobi_iters;
+        s->kernels_per_step = 1 + 1 + 2 + jl + (s->fused ? 2 : 1) + 1 + (s->multi() && s->fused ? 1 : 0) +
+                              ((s->cfg.phase_timing || (s->multi() && cfg->halo_backend == FXB_HALO_FUSED)) ? 2 : 0);
     }
     if (s->multi()) {
         // establish the NCCL connections now (outside any graph capture): one throw-away exchange and reduction
@@ -586,6 +629,7 @@ void fxb_destroy(fxb_sim* s) {
     for (int i = 0; i < 8; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     delete s;
 }
 

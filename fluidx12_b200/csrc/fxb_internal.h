@@ -50,6 +50,8 @@ struct fxb_sim {
 
     cudaStream_t own_stream = nullptr;
     cudaStream_t last_stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // multi-GPU: the all-reduce of the freeze counters runs beside the step's tail
+    bool side_forked = false;
     // One captured graph per (frame parity, pressure-buffer parity): both select pointers that the halo exchange
     // of the multi-GPU step needs on the host side.  Single GPU uses slot [0][0] only (its kernels select on device).
     cudaGraph_t graph[2][2] = {};

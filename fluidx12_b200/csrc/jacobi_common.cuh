@@ -89,6 +89,7 @@ struct PassParams {
     int ext_lo, ext_hi;    // multi-GPU: planes below / above the owned range to relax redundantly in this pass
     int copy_all;          // 1: every brick that froze in the first pass is copied; 0: only those next to an active brick
     int keep_lo, keep_hi;  // multi-GPU: bricks of the lowest / highest layer are always copied (a neighbour rank reads them)
+    int first_brick, first_count;  // first pass: this launch relaxes the bricks (first_brick + w) mod bricks, w < first_count
     int event;             // fused halos: this kernel's number m in the frame (common.cuh PeerView)
     int push_depth;        // fused halos: own planes next to an interior face that are also stored into the neighbour
 };
@@ -250,6 +251,8 @@ inline PassParams make_pass_params(const FusedJacobi& J, const Domain& d, int pa
     P.copy_all = J.copy_all ? 1 : 0;
     P.keep_lo = d.z_own0 > 0 ? 1 : 0;
     P.keep_hi = d.z_own1 < d.nz ? 1 : 0;
+    P.first_brick = 0;
+    P.first_count = J.ntx * J.nty * J.nzc;
     P.event = 2 + pass;
     P.push_depth = J.T;
     return P;

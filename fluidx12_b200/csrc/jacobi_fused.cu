@@ -38,9 +38,16 @@
 #include "jacobi_common.cuh"
 #include "kernels.h"
 
+// Unroll factor of the marching loop (tuning knob of the build).
+#ifndef FXB_K_UNROLL
+#define FXB_K_UNROLL 1
+#endif
+
 namespace fxb {
 
 namespace {
+
+constexpr int kUnrollK = FXB_K_UNROLL;
 
 // One fused pass (see the file header).  FUSED: the multi-GPU instantiation with fused halos (common.cuh PeerView);
 // the single-GPU one carries none of that code.
@@ -66,7 +73,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     const unsigned long long need = frame->epoch_base + (unsigned long long)P.event;
     const int p_cur = state->p_cur;
     const unsigned long long still_prev = pass > 0 ? state->active_after[s0 - 1] : 1ull;
-    const int n_relax = pass > 0 ? W.relax_count[pass] : P.ntx * P.nty * P.nzc;
+    const int n_relax = pass > 0 ? W.relax_count[pass] : P.first_count;
     const int n_copy = pass > 0 ? W.copy_count[pass] : 0;
     const int* __restrict__ list_in = W.relax[pass & 1];
     // speculative: the first two list entries of this CTA (garbage beyond n_relax, then unused)
@@ -90,6 +97,13 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
             if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
                 state->done_ctas = 0;
                 peer_publish(pv, need + 1ull);
+#ifdef FXB_TIMING
+                {  // debug build: when each pass of the frame ended on this rank (tools/mgpu_probe.py)
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    state->dbg[64 + (pass < 40 ? pass : 39)] = (long long)now;
+                }
+#endif
             }
         }
     };
@@ -146,11 +160,14 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         if (tid == 0) s_copied = 0;
         __syncthreads();
         const int nbricks = layer * P.nzc;
+            auto rot = [&](const int i) { return !FUSED ? i : (i + layer < nbricks ? i + layer : i + layer - nbricks); };
         for (int b0 = blockIdx.x; b0 < nbricks; b0 += gridDim.x * 32) {
             // 32 candidate bricks of this CTA at a time: one round trip for their flags
-            const int b = b0 + (tid & 31) * gridDim.x;
-            const int f = (tid < 32 && b < nbricks) ? W.brick_flag[b] : 0;
-            const bool edge = (P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer);
+            // (fused halos: candidates rotated by one layer, the face layers last, as in the first pass)
+            const int bi = b0 + (tid & 31) * gridDim.x;
+            const int b = rot(bi);
+            const int f = (tid < 32 && bi < nbricks) ? W.brick_flag[b] : 0;
+            const bool edge = bi < nbricks && ((P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer));
             const bool want = (f & 1) && ((f & 2) || P.copy_all || edge);
             const unsigned todo = __ballot_sync(kFull, tid < 32 && want);
             if (tid == 0) s_todo = todo;
@@ -159,7 +176,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                const int brick = b0 + j * gridDim.x;
+                const int brick = rot(b0 + j * gridDim.x);
                 bool lo, hi;
                 brick_faces(brick, lo, hi);
                 if (lo || hi) {
@@ -195,8 +212,19 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     const int nxb = P.pitch >> 3;
     const float eps = P.early_exit ? kEps : -1.0f;
 
+    // First pass: the bricks (first_brick + w) mod bricks, w < first_count — all of them on a single GPU; with fused
+    // halos the launch is split (launch_jacobi_pass_fused): the interior layers here, without any of the halo code, and
+    // the layers at the slab's faces in a second, small launch.
+    const int nbricks_all = layer * P.nzc;
     auto item_of = [&](const int w, const int listed) -> Item {
-        if (w < n_relax) return own_item<S>(P, pass > 0 ? listed : w);
+        if (w < n_relax) {
+            int brick = listed;
+            if (pass == 0) {
+                brick = w + P.first_brick;
+                if (brick >= nbricks_all) brick -= nbricks_all;
+            }
+            return own_item<S>(P, brick);
+        }
         return ext_item<S>(P, w - n_relax);
     };
 
@@ -346,7 +374,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         for (int l = 1; l <= T; ++l) ro[l] = ro[0];
         int pub_w = 0;  // half of the published planes written in this iteration (read in the next one)
 
-#pragma unroll 1
+#pragma unroll kUnrollK
         for (int k = zl0; k <= k_end; ++k) {
             float4 nw[kRows];   // the plane the level below produced in this iteration
             unsigned nfl = 0;
@@ -573,9 +601,11 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
             copy_frozen_brick<S, FUSED>(src, dst, m_dst, P, w < n_r ? lr[w] : lc[w - n_r], pv, peers, pi, mi);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // (p_cur itself is flipped by the next kernel: other CTAs still read it)
-        state->s_exec = s;
+        if (force_passes < 0) {  // (multi-GPU: the global figure comes from the summed counters, fxb_api.cu)
+            state->s_exec = s;
+            state->total_sweeps += (unsigned long long)s;
+        }
         state->passes = passes;
-        state->total_sweeps += (unsigned long long)s;
         state->total_passes += (unsigned long long)passes;
     }
 }
@@ -586,6 +616,13 @@ __global__ void jacobi_flip_kernel(const FrameParams* __restrict__ frame, StepSt
                                    const __grid_constant__ PeerView pv, int event) {
     if (0.0f < frame->dt && iters > 0 && state->passes > 0) state->p_cur ^= 1;
     phase_mark(state, 2);  // the pressure solve ends here
+#ifdef FXB_TIMING
+    {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        state->dbg[105] = (long long)now;  // the solve ended
+    }
+#endif
     if (pv.has_lo || pv.has_hi) peer_publish(pv, frame->epoch_base + (unsigned long long)event + 1ull);
 }
 
@@ -630,8 +667,8 @@ template <int T> using NarrowU = Shape<T, 16, 8, (T <= 2 ? 3 : 2), (T <= 2 ? 2 :
 
 template <class S>
 cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state, int pass,
-                         int s0, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, const PeerView& pv,
-                         cudaStream_t stream) {
+                         int s0, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi, int first_brick,
+                         int first_count, bool plain, const PeerView& pv, cudaStream_t stream) {
     // the opt-in above the 48 KB default is per device: set it whenever the device changes (cheap, idempotent)
     static int attr_device = -1;
     int dev = 0;
@@ -644,16 +681,20 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
         if (e != cudaSuccess) return e;
         attr_device = dev;
     }
-    const PassParams P = make_pass_params(J, d, pass, iters, early_exit, run_all, ext_lo, ext_hi);
+    PassParams P = make_pass_params(J, d, pass, iters, early_exit, run_all, ext_lo, ext_hi);
+    if (pass == 0 && first_count >= 0) {
+        P.first_brick = first_brick;
+        P.first_count = first_count;
+    }
     const JacobiPeers peers = make_jacobi_peers(J);
-    const int nbricks = J.ntx * J.nty * J.nzc;
+    const int nbricks = pass == 0 ? P.first_count : J.ntx * J.nty * J.nzc;
     const int slots = J.num_sms * S::kCtasPerSm;  // persistent CTAs
-    const int grid = nbricks < slots ? nbricks : slots;
+    const int grid = nbricks < slots ? (nbricks > 0 ? nbricks : 1) : slots;
     const WorkLists W = make_work_lists(J);
     const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map_p[0]);
     const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map_p[1]);
     const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map_rhs);
-    if (pv.has_lo || pv.has_hi)
+    if ((pv.has_lo || pv.has_hi) && !plain)
         jacobi_pass_kernel<S, true><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], J.p[1],
                                                                               J.mask[0], J.mask[1], W, P, pv, peers);
     else
@@ -724,13 +765,55 @@ void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]) {
     out[0] = J.tile_x - 2 * kHaloX; out[1] = J.tile_y - 2 * J.T; out[2] = J.bz;
 }
 
+// With fused halos the first pass is split when the resident kernel is available: the interior layers run in the
+// marching kernel WITHOUT the halo code (measured: the instantiation with it is ~25 % slower on every brick), the one
+// or two layers at the slab's interior faces follow in the resident kernel, which pushes their planes to the
+// neighbours and publishes the pass's event.
+static bool first_pass_split(const FusedJacobi& J, const PeerView& pv) {
+    return (pv.has_lo || pv.has_hi) && resident_jacobi_supported(J);
+}
+
+int fused_jacobi_launches(const FusedJacobi& J, const PeerView& pv, int pass) {
+    if (pass != 0 || pass >= J.resident_from || !first_pass_split(J, pv)) return 1;
+    const int layer = J.ntx * J.nty, faces = std::min(J.nzc, (pv.has_lo ? 1 : 0) + (pv.has_hi ? 1 : 0));
+    return layer * J.nzc - faces * layer > 0 ? 2 : 1;
+}
+
 cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                      int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
                                      const PeerView& pv, cudaStream_t stream) {
     if (pass >= J.resident_from)
-        return launch_jacobi_pass_resident(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream);
+        return launch_jacobi_pass_resident(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, 0, -1, pv,
+                                           stream);
     const int s0 = pass * J.T;
-#define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream)
+    int first_brick = 0, first_count = -1;
+    bool plain = false;
+    if (pass == 0 && first_pass_split(J, pv)) {
+        // bricks in rotated order: interior layers, then the top layer, then the bottom layer
+        const int layer = J.ntx * J.nty, nbricks = layer * J.nzc;
+        const int faces = std::min(J.nzc, (pv.has_lo ? 1 : 0) + (pv.has_hi ? 1 : 0));
+        const int interior = nbricks - faces * layer;
+        const int face_first = (nbricks - (pv.has_hi ? layer : 0)) % nbricks;
+        if (interior > 0) {
+            first_brick = pv.has_lo ? layer : 0;
+            first_count = interior;
+            plain = true;
+        }
+        // (launch order: the interior first — whatever the neighbours lag behind is absorbed there)
+        cudaError_t e = cudaSuccess;
+        if (interior > 0) {
+#define FXB_LAUNCH(S) e = launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, first_brick, first_count, plain, pv, stream)
+            switch (J.T) {
+                case 1: if (J.narrow) FXB_LAUNCH(NarrowU<1>); else FXB_LAUNCH(WideU<1>); break;
+                default: if (J.narrow) FXB_LAUNCH(NarrowU<2>); else FXB_LAUNCH(WideU<2>); break;
+            }
+#undef FXB_LAUNCH
+            if (e != cudaSuccess) return e;
+        }
+        return launch_jacobi_pass_resident(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, face_first,
+                                           faces * layer, pv, stream);
+    }
+#define FXB_LAUNCH(S) return launch_shape<S>(J, d, frame, state, pass, s0, iters, early_exit, run_all, ext_lo, ext_hi, first_brick, first_count, plain, pv, stream)
     switch (J.T) {
         case 1: if (J.narrow) FXB_LAUNCH(NarrowU<1>); FXB_LAUNCH(WideU<1>);
         case 2: if (J.narrow) FXB_LAUNCH(NarrowU<2>); FXB_LAUNCH(WideU<2>);

@@ -115,21 +115,31 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
         const unsigned long long need = epoch + 2ull + (unsigned long long)pass;  // this pass's event number (PassParams::event)
         // independent loads first (one round trip instead of a chain), then the decisions
         const unsigned long long still_prev = pass > 0 ? ld_l2(&state->active_after[s0 - 1]) : 1ull;
-        const int n_relax = pass > 0 ? ld_l2(&W.relax_count[pass]) : layer * P.nzc;
+        const int n_relax = pass > 0 ? ld_l2(&W.relax_count[pass]) : P.first_count;
         const int n_copy = pass > 0 ? ld_l2(&W.copy_count[pass]) : 0;
         const int* list_in = W.relax[pass & 1];
         // speculative: the first two list entries of this CTA (garbage beyond n_relax, then unused; the lists are padded)
         int listed = pass > 0 ? ld_l2(&list_in[blockIdx.x]) : (int)blockIdx.x;
         int listed_next = pass > 0 ? ld_l2(&list_in[blockIdx.x + gridDim.x]) : (int)(blockIdx.x + gridDim.x);
         // Fused halos: when the last CTA is done, this kernel's event is published to the neighbours — on every path.
+        bool pushed = false;  // this CTA stored into a neighbour rank (uniform)
         auto finish = [&]() {
             if constexpr (!FUSED) return;
             __syncthreads();
             if (tid == 0) {
-                __threadfence_system();
+                // what this CTA pushed over NVLink has arrived before its arrival is counted (the publishing CTA fences
+                // again before the event); a CTA that pushed nothing has nothing to wait for
+                if (pushed) __threadfence_system();
                 if (atomicAdd(&state->done_ctas, 1) == (int)gridDim.x - 1) {
                     state->done_ctas = 0;
                     peer_publish(pv, need + 1ull);
+#ifdef FXB_TIMING
+                    {  // debug build: when each pass of the frame ended on this rank (tools/mgpu_probe.py)
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        state->dbg[64 + (pass < 40 ? pass : 39)] = (long long)now;
+                    }
+#endif
                 }
             }
         };
@@ -160,20 +170,24 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
             waited_hi |= wh;
             return true;
         };
-        auto brick_faces = [&](const int brick, bool& lo, bool& hi) {
+        auto brick_faces = [&](const int brick, bool& lo, bool& hi) {  // called for every brick this CTA copies or relaxes
             lo = FUSED && pv.has_lo && brick < layer;
             hi = FUSED && pv.has_hi && brick >= layer * (P.nzc - 1);
+            pushed |= lo || hi;
         };
 
         // The frozen bricks of the previous pass: one copy each into the other pressure buffer (as in jacobi_fused.cu,
         // including the first pass's special case: this kernel also runs pass 1).
         if (pass == 1) {
             const int nbricks = layer * P.nzc;
+            auto rot = [&](const int i) { return !FUSED ? i : (i + layer < nbricks ? i + layer : i + layer - nbricks); };
             for (int b0 = blockIdx.x; b0 < nbricks; b0 += gridDim.x * 32) {
                 // 32 candidate bricks of this CTA at a time: one round trip for their flags
-                const int b = b0 + (tid & 31) * gridDim.x;
-                const int f = (tid < 32 && b < nbricks) ? ld_l2(&W.brick_flag[b]) : 0;
-                const bool edge = (P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer);
+                // (fused halos: candidates rotated by one layer, the face layers last, as in the first pass)
+                const int bi = b0 + (tid & 31) * gridDim.x;
+                const int b = rot(bi);
+                const int f = (tid < 32 && bi < nbricks) ? ld_l2(&W.brick_flag[b]) : 0;
+                const bool edge = bi < nbricks && ((P.keep_lo && b < layer) || (P.keep_hi && b >= nbricks - layer));
                 const bool want = (f & 1) && ((f & 2) || P.copy_all || edge);
                 const unsigned todo = __ballot_sync(kFull, tid < 32 && want);
                 if (tid == 0) s_todo = todo;
@@ -182,7 +196,7 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
                 while (m) {
                     const int j = __ffs(m) - 1;
                     m &= m - 1;
-                    const int brick = b0 + j * gridDim.x;
+                    const int brick = rot(b0 + j * gridDim.x);
                     bool lo, hi;
                     brick_faces(brick, lo, hi);
                     if (peer_sync(lo, hi)) __syncthreads();
@@ -209,7 +223,14 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
         const int n_work = n_relax + n_ext;
 
         auto item_of = [&](const int w, const int entry) -> Item {
-            if (w < n_relax) return own_item<S>(P, pass > 0 ? entry : w);
+            if (w < n_relax) {
+                int brick = entry;
+                if (pass == 0) {  // the bricks (first_brick + w) mod bricks (see PassParams)
+                    brick = w + P.first_brick;
+                    if (brick >= layer * P.nzc) brick -= layer * P.nzc;
+                }
+                return own_item<S>(P, brick);
+            }
             return ext_item<S>(P, w - n_relax);
         };
         // the window of a work item: before anything of a face brick is staged, the neighbour's data must be there
@@ -487,7 +508,7 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
 template <class S>
 cudaError_t launch_resident_shape(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                   int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
-                                  const PeerView& pv, cudaStream_t stream) {
+                                  int first_brick, int first_count, const PeerView& pv, cudaStream_t stream) {
     // the opt-in above the 48 KB default is per device: set it whenever the device changes (cheap, idempotent)
     static int attr_device = -1;
     int dev = 0;
@@ -500,11 +521,15 @@ cudaError_t launch_resident_shape(const FusedJacobi& J, const Domain& d, const F
         if (e != cudaSuccess) return e;
         attr_device = dev;
     }
-    const PassParams P = make_pass_params(J, d, pass, iters, early_exit, run_all, ext_lo, ext_hi);
+    PassParams P = make_pass_params(J, d, pass, iters, early_exit, run_all, ext_lo, ext_hi);
+    if (pass == 0 && first_count >= 0) {
+        P.first_brick = first_brick;
+        P.first_count = first_count;
+    }
     const JacobiPeers peers = make_jacobi_peers(J);
     const WorkLists W = make_work_lists(J);
-    const int nbricks = J.ntx * J.nty * J.nzc;
-    const int grid = nbricks < J.num_sms ? nbricks : J.num_sms;  // persistent, one CTA per SM
+    const int nbricks = pass == 0 ? P.first_count : J.ntx * J.nty * J.nzc;
+    const int grid = nbricks < J.num_sms ? (nbricks > 0 ? nbricks : 1) : J.num_sms;  // persistent, one CTA per SM
     const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map3_p[0]);
     const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map3_p[1]);
     const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map3_rhs);
@@ -536,8 +561,8 @@ int resident_jacobi_window_planes(const FusedJacobi& J) { return 8 + 2 * J.T; }
 
 cudaError_t launch_jacobi_pass_resident(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                         int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
-                                        const PeerView& pv, cudaStream_t stream) {
-#define FXB_LAUNCH(S) return launch_resident_shape<S>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, pv, stream)
+                                        int first_brick, int first_count, const PeerView& pv, cudaStream_t stream) {
+#define FXB_LAUNCH(S) return launch_resident_shape<S>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, first_brick, first_count, pv, stream)
     using N1 = RShape<1, 16>;
     using W1 = RShape<1, 32>;
     using N2 = RShape<2, 16>;

@@ -94,8 +94,11 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
 // jacobi_resident.cu — the same pass with the brick's window resident in shared memory (the latency shape)
 bool resident_jacobi_supported(const FusedJacobi& J);
 int resident_jacobi_window_planes(const FusedJacobi& J);
+// first_count >= 0 (first pass only): the launch relaxes the bricks (first_brick + w) mod bricks, w < first_count.
 cudaError_t launch_jacobi_pass_resident(const FusedJacobi& J, const Domain& d, const FrameParams* frame, StepState* state,
                                         int pass, int iters, int early_exit, bool run_all_passes, int ext_lo, int ext_hi,
-                                        const PeerView& pv, cudaStream_t stream);
+                                        int first_brick, int first_count, const PeerView& pv, cudaStream_t stream);
+// Kernels launch_jacobi_pass_fused enqueues for this pass (2 for the first pass with fused halos: interior + face layers).
+int fused_jacobi_launches(const FusedJacobi& J, const PeerView& pv, int pass);
 
 }  // namespace fxb

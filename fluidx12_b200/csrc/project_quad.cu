@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
     if (!(0.0f < frame->dt)) return;
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int z_begin = d.z_own0 + blockIdx.z * kDivPlanes;
+    const int zc = FUSED ? face_last_chunk(pv, blockIdx.z, gridDim.z, kDivPlanes, push_depth, d.z_own1 - d.z_own0) : (int)blockIdx.z;
+    const int z_begin = d.z_own0 + zc * kDivPlanes;
     const int z_end = min(z_begin + kDivPlanes, d.z_own1);
     // fused halos (common.cuh PeerView): the chunks at an interior face read the neighbour's first / last plane of the
     // advected velocity and store their right-hand side into the neighbour's halo as well (event m = 1)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) gradient_quad_kernel(Domain d, AxisTables
                                                             uint2* vel_out_hi, int reach, int event) {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int z = d.z_own0 + blockIdx.z;
+    const int z = d.z_own0 + (FUSED ? face_last_chunk(pv, blockIdx.z, gridDim.z, 1, reach, d.z_own1 - d.z_own0) : (int)blockIdx.z);
     // fused halos (common.cuh PeerView): the first / last plane reads the neighbour's pressure plane, and the planes the
     // neighbour's next advection can reach are stored into its halo as well
     const bool near_lo = FUSED && pv.has_lo && z < d.z_own0 + reach, near_hi = FUSED && pv.has_hi && z >= d.z_own1 - reach;

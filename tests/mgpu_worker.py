@@ -31,7 +31,7 @@ def main():
         uid = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
     dist.broadcast(uid, 0)
     f = fx.Fluid()
-    backend = fx.HALO_NCCL if os.environ.get("FXB_TEST_BACKEND", "peer") == "nccl" else fx.HALO_PEER
+    backend = {"fused": fx.HALO_FUSED, "peer": fx.HALO_PEER, "nccl": fx.HALO_NCCL}[os.environ.get("FXB_TEST_BACKEND", "fused")]
     assert f.Init(gridSize=grid, device=local, rank=rank, nranks=world, fuse_t=fuse_t, h_adv=int(os.environ.get("FXB_TEST_HADV", "8")),
                   halo_backend=backend, jacobi_group=int(os.environ.get("FXB_TEST_GROUP", "0")),
                   nccl_unique_id=uid.numpy().tobytes(), use_graph=bool(int(os.environ.get("FXB_TEST_GRAPH", "1")))), f.last_error

@@ -1,7 +1,8 @@
 """Multi-GPU (z-slab + halo exchange) parity: N ranks must reproduce the single-GPU fields bit for bit.
 
-The default halo backend stores face planes straight into the neighbours' memory (CUDA IPC over NVLink, csrc/halo.cu);
-the NCCL send/recv backend and the grouped pressure exchange are covered as well.  Needs `gpurun --gpus N`; the cases a
+The default halo backend is fused into the step's kernels: every kernel stores its face planes straight into the
+neighbours' memory (CUDA IPC over NVLink) and publishes an event counter (common.cuh PeerView).  The two exchange-kernel
+backends (peer memory, NCCL send/recv) and their grouped pressure exchange are covered as well.  Needs `gpurun --gpus N`; the cases a
 box cannot run are skipped."""
 import os
 import subprocess
@@ -32,8 +33,9 @@ def test_two_ranks_match_single_gpu(grid, t):
     _run(2, {"FXB_TEST_GRID": grid, "FXB_TEST_T": str(t)})
 
 
-def test_two_ranks_nccl_backend():
-    _run(2, {"FXB_TEST_GRID": "64,64,96", "FXB_TEST_T": "2", "FXB_TEST_BACKEND": "nccl"})
+@pytest.mark.parametrize("backend", ["peer", "nccl"])
+def test_two_ranks_exchange_backends(backend):
+    _run(2, {"FXB_TEST_GRID": "64,64,96", "FXB_TEST_T": "2", "FXB_TEST_BACKEND": backend})
 
 
 @pytest.mark.parametrize("backend", ["peer", "nccl"])
@@ -46,14 +48,14 @@ def test_four_ranks_and_eager_launch():
     _run(4, {"FXB_TEST_GRID": "64,64,128", "FXB_TEST_T": "2", "FXB_TEST_GRAPH": "0"})
 
 
-@pytest.mark.parametrize("group", [1, 4])
-def test_four_ranks(group):
-    _run(4, {"FXB_TEST_GRID": "128,128,128", "FXB_TEST_T": "2", "FXB_TEST_GROUP": str(group)})
+@pytest.mark.parametrize("backend,group", [("fused", 1), ("peer", 1), ("peer", 4)])
+def test_four_ranks(backend, group):
+    _run(4, {"FXB_TEST_GRID": "128,128,128", "FXB_TEST_T": "2", "FXB_TEST_GROUP": str(group), "FXB_TEST_BACKEND": backend})
 
 
-@pytest.mark.parametrize("group", [1, 4])
-def test_eight_ranks(group):
-    _run(8, {"FXB_TEST_GRID": "128,128,160", "FXB_TEST_T": "2", "FXB_TEST_GROUP": str(group)})
+@pytest.mark.parametrize("backend,group", [("fused", 1), ("peer", 4)])
+def test_eight_ranks(backend, group):
+    _run(8, {"FXB_TEST_GRID": "128,128,160", "FXB_TEST_T": "2", "FXB_TEST_GROUP": str(group), "FXB_TEST_BACKEND": backend})
 
 
 @pytest.mark.parametrize("nproc,grid", [(2, "64,64,96"), (4, "128,128,128")])
