@@ -38,7 +38,7 @@ METRIC = "voxel_updates_per_s"
 UNIT = "voxel-updates/s"
 # algorithmic bytes per voxel per launch
 PHASE_BYTES = {"advect": 32.0, "divergence": 12.0, "gradient": 20.0}
-PHASE_KERNEL = {"advect": "advect_kernel", "divergence": "divergence_quad_kernel", "jacobi": "jacobi_pass_kernel",
+PHASE_KERNEL = {"advect": "advect_kernel", "divergence": "divergence_quad_kernel", "jacobi": "jacobi_pass_kernel+jacobi_resident_kernel",
                 "gradient": "gradient_quad_kernel"}
 
 
@@ -203,12 +203,13 @@ def jacobi_work_bytes(st0, st1, mask_bytes, voxels_local):
     return (st1.total_passes - st0.total_passes) * (12.0 + mask_bytes) * voxels_local, 0, 0
 
 
-def ncu_traffic(grid, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
-    of this grid (profiles/traffic.json, written by tools/summarize_profiles.py), or None."""
+def ncu_traffic(grid, phase):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the phase's kernel(s), averaged over every launch of
+    whole steps, from the committed ncu pass over this grid (profiles/traffic.json, written by
+    tools/summarize_profiles.py traffic), or None."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get("%dx%dx%d" % tuple(grid), {}).get(kernel, {}).get("dram_bytes_per_launch")
+        return t.get("%dx%dx%d" % tuple(grid), {}).get(phase, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -235,7 +236,7 @@ def rooflines(grid, phases, st0, st1, steps, voxels_local, peak, peak_src):
     n_launch = launches if dom == "jacobi" else 1.0
     roof = {"bound": "hbm", "kernel": PHASE_KERNEL[dom], "phase": dom,
             "achieved": per[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per[dom]["frac"],
-            "peak_source": peak_src, "traffic": ncu_traffic(grid, PHASE_KERNEL[dom]),
+            "peak_source": peak_src, "traffic": ncu_traffic(grid, dom),
             "bytes_per_launch": round(nbytes[dom] / max(n_launch, 1e-9)),
             "avg_launch_ms": round(per[dom]["ms"] / max(n_launch, 1e-9), 5), "launches_per_step": round(n_launch, 1),
             "how": "phase marks inside the timed graph-launched steps (fxb_get_phase_times); bytes of the same steps"}

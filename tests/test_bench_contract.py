@@ -116,6 +116,6 @@ def test_ours_prints_one_line_with_every_contract_key(monkeypatch, capsys):
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
     assert line["e2e_export"]["d2h_bytes_per_step"] > 32 * 32 * 32 * 8
     assert line["gpu_launches"] == 38 * 4
-    assert line["roofline"]["kernel"] == "jacobi_pass_kernel" and line["state_checksum"].count("-") == 2
+    assert line["roofline"]["kernel"] == "jacobi_pass_kernel+jacobi_resident_kernel" and line["state_checksum"].count("-") == 2
     assert "experiments" not in line
     assert np.isclose(line["value"], 32 ** 3 * 4 / 12.5e-3)

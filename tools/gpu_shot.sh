@@ -13,12 +13,18 @@ if [ "$what" = tests ]; then
 fi
 timeout 600 python bench.py --steps 30 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
 python tools/benchsum.py $out/${tag}_bench.json 2>/dev/null | head -40
-K=38   # kernels per un-graphed step without phase marks
 for g in 256 512; do
+  K=$(python tools/profile_step.py --grid $g $g $g --steps 1 | sed -n 's/^kernels\/step \([0-9]*\).*/\1/p')
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s $((100*K)) -c $((2*K)) --csv --log-file $out/${tag}_launches_$g.csv \
       python tools/profile_step.py --grid $g $g $g --steps 102 > $out/${tag}_launches_$g.log 2>&1
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:jacobi_pass -s 3200 -c 3 -o $out/${tag}_jacobi_256 -f \
+# DRAM bytes of every launch of two steps -> profiles/traffic.json (bench.py's roofline.traffic)
+for g in 256 512; do
+  K=$(python tools/profile_step.py --grid $g $g $g --steps 1 | sed -n 's/^kernels\/step \([0-9]*\).*/\1/p')
+  timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s $((100*K)) -c $((2*K)) --csv --log-file $out/${tag}_traffic_$g.csv \
+      python tools/profile_step.py --grid $g $g $g --steps 102 > $out/${tag}_traffic_$g.log 2>&1
+done
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"jacobi_pass|jacobi_resident" -s 3200 -c 3 -o $out/${tag}_jacobi_256 -f \
     python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_j.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"advect_kernel|divergence_quad|gradient_quad" -s 300 -c 3 -o $out/${tag}_adg_256 -f \
     python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_a.log 2>&1

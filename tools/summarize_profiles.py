@@ -2,6 +2,7 @@
 
     python tools/summarize_profiles.py launches <launches.csv> <out.txt>     # per-launch device times + shares
     python tools/summarize_profiles.py full <report.ncu-rep> <out.json>      # key metrics of every kernel in a report
+    python tools/summarize_profiles.py traffic <traffic.csv> <NXxNYxNZ>      # DRAM bytes per launch -> profiles/traffic.json
 """
 import csv
 import json
@@ -77,5 +78,42 @@ def full(path, out):
     print(json.dumps(res[:2], indent=1)[:2500])
 
 
+PHASES = (("advect", "advect_kernel"), ("divergence", "divergence_quad_kernel"), ("gradient", "gradient_quad_kernel"),
+          ("jacobi", "jacobi_"))  # jacobi: the marching first pass + the resident passes + the settle copy
+
+
+def traffic(path, grid):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over the launches of whole steps: DRAM bytes per launch
+    of each phase's kernel(s), averaged over the launches captured (bench.py's roofline.traffic reads the result)."""
+    import os
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, mi, ii, ui = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Name", "ID", "Metric Unit"))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[1:]:
+        if r[mi] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e = per.setdefault(int(r[ii]), [short(r[ki]), 0.0])
+            e[1] += float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
+    out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        doc = json.load(open(out_path))
+    except Exception:
+        doc = {}
+    entry = {}
+    for phase, prefix in PHASES:
+        sel = [b for n, b in per.values() if prefix in n and "flip" not in n]
+        if sel:
+            entry[phase] = {"dram_bytes_per_launch": sum(sel) / len(sel), "launches_captured": len(sel),
+                            "dram_bytes_total": sum(sel),
+                            "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, "
+                                      "every launch of %d step(s) after 100 spin-up steps (%s)" % (
+                                          max(1, len([1 for n, _ in per.values() if "advect_kernel" in n])),
+                                          os.path.basename(path))}
+    doc[grid] = entry
+    json.dump(doc, open(out_path, "w"), indent=1)
+    print(json.dumps(entry, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
