@@ -15,7 +15,7 @@ Grid: N = 1 -> 512^3 (BASELINE config 4, its 1-GPU point: the largest single-GPU
 larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decomposed: 512x512x1024 (2), 1024x1024x512 (4),
 1024^3 (8, BASELINE config 5); `--scaling strong` keeps 512^3 at every N (config 4).  The per-phase device times and
 the roofline come from phase marks INSIDE the timed steps (fxb_get_phase_times).  At N = 1 the line also carries "c3"
-(the 256^3 roofline-characterisation config) and "c2" (128^3) and the CPU baseline; at N > 1 (weak) it carries
+(the 256^3 roofline-characterisation config), "c2" (128^3), "c150" (150^3) and the CPU baseline; at N > 1 (weak) it carries
 "c4_strong": config 4 on the same N ranks, whose state checksum must equal the N = 1 line's.  --grid overrides.
 """
 from __future__ import annotations
@@ -447,7 +447,8 @@ def run_ours(args):
     # BASELINE configs[2] (256^3: the roofline-characterisation config) and configs[1] (128^3, the reference's default
     # grid, FluidX12.cpp:44) on the same GPU, same method as the main workload
     for key, cn, label in (("c3", 256, "3D 256^3 (BASELINE config 3: roofline characterisation)"),
-                           ("c2", 128, "3D 128^3 (BASELINE config 2: the reference's default grid; fits in L2)")):
+                           ("c2", 128, "3D 128^3 (BASELINE config 2: the reference's default grid; fits in L2)"),
+                           ("c150", 150, "3D 150^3 (the reference's shipped Bin/FluidGI.bat grid: pitched pressure rows)")):
         if not (world == 1 and not args.no_c3 and grid != (cn, cn, cn)):
             continue
         g, crec = measure_config(torch, dist, fx, args, (cn, cn, cn), 0, 1, local_rank, None, stream, peak, peak_src)

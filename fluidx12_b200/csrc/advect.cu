@@ -108,10 +108,10 @@ __device__ __forceinline__ Texels advect_voxel(const AdvectArgs& A, const float 
     const bool inside = tx >= 0.0f && tx < fnx - 1.0f && ty >= 0.0f && ty < fny - 1.0f && tz >= 0.0f &&
                         tz < fnz - 1.0f && tz >= zlo && tz < zhi;
     if (inside) {  // both taps of every axis are inside the grid (and inside the valid planes of the local slab)
-        const unsigned plane = (unsigned)d.pitch * d.ny;
-        const unsigned base = ((unsigned)((int)flz - d.z_first) * d.ny + (unsigned)(int)fly) * d.pitch + (unsigned)(int)flx;
-        o[0] = base; o[1] = base + 1; o[2] = base + d.pitch; o[3] = base + d.pitch + 1;
-        o[4] = base + plane; o[5] = o[4] + 1; o[6] = o[4] + d.pitch; o[7] = o[6] + 1;
+        const unsigned plane = (unsigned)d.nx * d.ny;
+        const unsigned base = ((unsigned)((int)flz - d.z_first) * d.ny + (unsigned)(int)fly) * d.nx + (unsigned)(int)flx;
+        o[0] = base; o[1] = base + 1; o[2] = base + d.nx; o[3] = base + d.nx + 1;
+        o[4] = base + plane; o[5] = o[4] + 1; o[6] = o[4] + d.nx; o[7] = o[6] + 1;
     } else {
         const int2 xs = wrapped_pair(tx, d.nx, A.clamp_mode), ys = wrapped_pair(ty, d.ny, A.clamp_mode);
         int2 zs = wrapped_pair(tz, d.nz, A.clamp_mode);
@@ -122,8 +122,8 @@ __device__ __forceinline__ Texels advect_voxel(const AdvectArgs& A, const float 
         }
         zs.x -= d.z_first;
         zs.y -= d.z_first;
-        const unsigned r00 = ((unsigned)zs.x * d.ny + ys.x) * d.pitch, r10 = ((unsigned)zs.x * d.ny + ys.y) * d.pitch;
-        const unsigned r01 = ((unsigned)zs.y * d.ny + ys.x) * d.pitch, r11 = ((unsigned)zs.y * d.ny + ys.y) * d.pitch;
+        const unsigned r00 = ((unsigned)zs.x * d.ny + ys.x) * d.nx, r10 = ((unsigned)zs.x * d.ny + ys.y) * d.nx;
+        const unsigned r01 = ((unsigned)zs.y * d.ny + ys.x) * d.nx, r11 = ((unsigned)zs.y * d.ny + ys.y) * d.nx;
         o[0] = r00 + xs.x; o[1] = r00 + xs.y; o[2] = r10 + xs.x; o[3] = r10 + xs.y;
         o[4] = r01 + xs.x; o[5] = r01 + xs.y; o[6] = r11 + xs.x; o[7] = r11 + xs.y;
     }
@@ -230,8 +230,8 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
     uint2* __restrict__ col_out = parity ? col1 : col0;       // colour[parity]
     const float px = __ldg(A.tab.pos[0] + x), py = __ldg(A.tab.pos[1] + y);
     const float atten = fmaxf(__fmaf_rn(-dt, 0.200000003f, 1.0f), 0.0f);
-    const unsigned plane = (unsigned)d.pitch * d.ny;
-    unsigned self = ((unsigned)(z0 - d.z_first) * d.ny + y) * d.pitch + x;
+    const unsigned plane = (unsigned)d.nx * d.ny;
+    unsigned self = ((unsigned)(z0 - d.z_first) * d.ny + y) * d.nx + x;
     // the field is written by the neighbours between frames (fused halos): no non-coherent loads of halo planes
     uint2 sv = __ldg(vel_in + self), sc = __ldg(col_in + self);
     for (int z = z0; z < z1; ++z) {

@@ -16,8 +16,10 @@ namespace fxb {
 // index lz holds global plane z = z_first + lz.  Single GPU: z_first = 0, nz_alloc = nz.
 struct Domain {
     int nx, ny, nz;      // global grid
-    int pitch;           // voxels per row in memory (>= nx, a multiple of 8 on the tuned path): row y of plane lz starts
-                         // at element (lz * ny + y) * pitch of every field
+    int pitch;           // floats per row of the PRESSURE-SIDE arrays (pressure ping-pong, right-hand side; freeze masks:
+                         // pitch / 8 bytes per row): nx rounded up to a multiple of 8 on the tuned 3D path, so that rows
+                         // start 32-byte aligned for TMA and 128-bit accesses whatever the grid width (e.g. the 150^3 of
+                         // Bin/FluidGI.bat); nx otherwise.  Velocity and colour rows are nx texels apart.
     int z_first;         // global z of local plane 0 (may be negative: halo below the global face)
     int nz_alloc;        // planes allocated locally (owned + halos)
     int z_own0, z_own1;  // owned global planes [z_own0, z_own1)

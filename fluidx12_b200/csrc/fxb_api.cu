@@ -155,12 +155,13 @@ __global__ void __launch_bounds__(256) checksum_kernel(fxb::Domain d, const uint
     unsigned long long a = 0, b = 0, c = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % d.nx), y = (int)((i / d.nx) % d.ny), lz = (int)(i / ((size_t)d.nx * d.ny));
-        const size_t at = ((size_t)(d.z_own0 - d.z_first + lz) * d.ny + y) * d.pitch + x;
+        const size_t row = (size_t)(d.z_own0 - d.z_first + lz) * d.ny + y;
+        const size_t at = row * d.nx + x, at_p = row * d.pitch + x;
         const unsigned long long g = ((unsigned long long)(d.z_own0 + lz) * d.ny + y) * d.nx + x;
         const uint2 v = vel[at], k = col[at];
         a += mix64(g * 3 + 0 + (((unsigned long long)(v.y & 0xffffu) << 32 | v.x) << 20));  // velocity .w is a don't-care
         b += mix64(g * 3 + 1 + (((unsigned long long)k.y << 32 | k.x) << 20) + (unsigned long long)(k.y >> 12));
-        c += mix64(g * 3 + 2 + ((unsigned long long)__float_as_uint(p[at]) << 24));
+        c += mix64(g * 3 + 2 + ((unsigned long long)__float_as_uint(p[at_p]) << 24));
     }
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_down_sync(0xffffffffu, a, o);
@@ -453,7 +454,11 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     s->dom.nx = (int)cfg->nx; s->dom.ny = (int)cfg->ny; s->dom.nz = (int)cfg->nz;
     s->dom.z_first = 0; s->dom.nz_alloc = (int)cfg->nz;
     s->dom.z_own0 = 0; s->dom.z_own1 = (int)cfg->nz;
+    // Pitched pressure-side arrays: on the tuned 3D path their rows are padded to a multiple of 8 floats, so every grid
+    // width takes the TMA-staged fused Jacobi kernels (multi-GPU slabs require nx % 8 == 0 anyway: pitch == nx there).
     s->dom.pitch = (int)cfg->nx;
+    if (cfg->kernel_path == 0 && cfg->nz > 1 && cfg->nx >= 8 && cfg->jacobi_iters > 0 && cfg->nranks == 1)
+        s->dom.pitch = ((int)cfg->nx + 7) / 8 * 8;
     s->fuse_t = 1;
     if (cfg->nranks > 1) {
         // z-slab decomposition (fluidx12_b200/slab.py states the same rules): rank r owns planes
@@ -478,6 +483,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
 
     auto cleanup_fail = [&](int rc) { fxb_destroy(s); return rc; };
     const size_t n = s->alloc_voxels();
+    const size_t np = (size_t)s->dom.pitch * s->dom.ny * s->dom.nz_alloc;  // elements of a pressure-side array
     // Peer-memory halos (FXB_P2P=1) map these buffers into the neighbours through CUDA IPC, and an IPC handle maps a
     // whole underlying allocation: small buffers are then given at least 2 MiB so that each is an allocation of its own.
     if (cfg->halo_backend != FXB_HALO_FUSED && cfg->halo_backend != FXB_HALO_PEER && cfg->halo_backend != FXB_HALO_NCCL) {
@@ -492,11 +498,11 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
         if (e == cudaSuccess) e = cudaMemset(s->vel[i], 0, n * 8);  // zero-filled like new D3D12 resources
         if (e == cudaSuccess) e = cudaMalloc(&s->col[i], std::max(n * 8, ipc_min));
         if (e == cudaSuccess) e = cudaMemset(s->col[i], 0, n * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->p[i], std::max(n * 4, ipc_min));
-        if (e == cudaSuccess) e = cudaMemset(s->p[i], 0, n * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->p[i], std::max(np * 4, ipc_min));
+        if (e == cudaSuccess) e = cudaMemset(s->p[i], 0, np * 4);
     }
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, std::max(n * 4, ipc_min));
-    if (e == cudaSuccess) e = cudaMemset(s->rhs, 0, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->rhs, std::max(np * 4, ipc_min));
+    if (e == cudaSuccess) e = cudaMemset(s->rhs, 0, np * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->active, n);
     if (e == cudaSuccess) e = cudaMemset(s->active, 0, n);
     if (e == cudaSuccess) e = cudaMalloc((void**)&s->d_frame, sizeof(fxb::FrameParams));
@@ -520,7 +526,7 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
     if (s->cfg.kernel_path == 0 && fxb::fused_jacobi_supported(s->dom) && s->cfg.jacobi_iters > 0) {
         // Tuned path: T sweeps fused per HBM pass.  Grids whose nx is not a multiple of 8 (e.g. the 150^3 of
         // Bin/FluidGI.bat) and the 2D path use the one-sweep-per-launch kernels instead.
-        const size_t mask_bytes = n / 8;
+        const size_t mask_bytes = np / 8;
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&s->jac.mask[i], std::max(mask_bytes, ipc_min));
             if (e == cudaSuccess) e = cudaMemset(s->jac.mask[i], 0, mask_bytes);
@@ -707,6 +713,13 @@ int fxb_get_field(fxb_sim* s, int field, void* host, size_t bytes) {
     const char* src = (const char*)field_device_ptr(s, field, &eb, &err);
     if (!src) return fail(err, "fxb_get_field: bad field");
     if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_get_field: size mismatch");
+    if (field == FXB_FIELD_PRESSURE && s->dom.pitch != s->dom.nx) {  // pitched rows -> the dense host layout
+        const size_t rows = (size_t)s->dom.ny * (s->dom.z_own1 - s->dom.z_own0);
+        const size_t first = (size_t)s->dom.ny * (s->dom.z_own0 - s->dom.z_first) * s->dom.pitch;
+        FXB_CUDA(cudaMemcpy2D(host, (size_t)s->dom.nx * 4, src + first * 4, (size_t)s->dom.pitch * 4, (size_t)s->dom.nx * 4, rows,
+                              cudaMemcpyDeviceToHost));
+        return FXB_OK;
+    }
     FXB_CUDA(cudaMemcpy(host, src + s->own_offset() * eb, bytes, cudaMemcpyDeviceToHost));
     return FXB_OK;
 }
@@ -732,6 +745,14 @@ int fxb_set_field(fxb_sim* s, int field, const void* host, size_t bytes) {
     char* dst = (char*)field_device_ptr(s, field, &eb, &err);
     if (!dst) return fail(err, "fxb_set_field: bad field");
     if (bytes != s->own_voxels() * eb) return fail(FXB_ERR_SIZE, "fxb_set_field: size mismatch");
+    if (field == FXB_FIELD_PRESSURE && s->dom.pitch != s->dom.nx) {  // the dense host layout -> pitched rows
+        const size_t rows = (size_t)s->dom.ny * (s->dom.z_own1 - s->dom.z_own0);
+        const size_t first = (size_t)s->dom.ny * (s->dom.z_own0 - s->dom.z_first) * s->dom.pitch;
+        FXB_CUDA(cudaMemcpy2D(dst + first * 4, (size_t)s->dom.pitch * 4, host, (size_t)s->dom.nx * 4, (size_t)s->dom.nx * 4, rows,
+                              cudaMemcpyHostToDevice));
+        s->halo_stale = true;
+        return FXB_OK;
+    }
     FXB_CUDA(cudaMemcpy(dst + s->own_offset() * eb, host, bytes, cudaMemcpyHostToDevice));
     s->halo_stale = true;
     return FXB_OK;

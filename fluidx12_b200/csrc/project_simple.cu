@@ -20,18 +20,19 @@ struct Nbr {
     size_t c, L, R, U, D, F, B;
 };
 
-__device__ __forceinline__ Nbr neighbours(const Domain& d, int x, int y, int z) {
+// `stride`: elements per row of the array indexed — d.nx for velocity / colour, d.pitch for pressure / right-hand side.
+__device__ __forceinline__ Nbr neighbours(const Domain& d, int x, int y, int z, int stride) {
     Nbr n;
-    const size_t plane = (size_t)d.nx * d.ny;
+    const size_t plane = (size_t)stride * d.ny;
     const size_t zc = (size_t)(z - d.z_first) * plane;
-    const size_t row = zc + (size_t)y * d.nx;
+    const size_t row = zc + (size_t)y * stride;
     n.c = row + x;
     n.L = row + (max(x, 1) - 1);
     n.R = row + min(x + 1, d.nx - 1);
-    n.U = zc + (size_t)(max(y, 1) - 1) * d.nx + x;
-    n.D = zc + (size_t)min(y + 1, d.ny - 1) * d.nx + x;
-    n.F = (size_t)(max(z, 1) - 1 - d.z_first) * plane + (size_t)y * d.nx + x;
-    n.B = (size_t)(min(z + 1, d.nz - 1) - d.z_first) * plane + (size_t)y * d.nx + x;
+    n.U = zc + (size_t)(max(y, 1) - 1) * stride + x;
+    n.D = zc + (size_t)min(y + 1, d.ny - 1) * stride + x;
+    n.F = (size_t)(max(z, 1) - 1 - d.z_first) * plane + (size_t)y * stride + x;
+    n.B = (size_t)(min(z + 1, d.nz - 1) - d.z_first) * plane + (size_t)y * stride + x;
     return n;
 }
 
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) divergence_kernel(Domain d, const FramePa
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int z = d.z_own0 + blockIdx.z;
     if (x >= d.nx || y >= d.ny) return;
-    const Nbr n = neighbours(d, x, y, z);
+    const Nbr n = neighbours(d, x, y, z, d.nx);
     const float a = -comp(vel, n.L, 0) + comp(vel, n.R, 0);
     float b = -comp(vel, n.U, 1) + comp(vel, n.D, 1);
     float s;
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) divergence_kernel(Domain d, const FramePa
     } else {
         s = a + b;
     }
-    rhs[n.c] = -0.5f * s;
+    rhs[((size_t)(z - d.z_first) * d.ny + y) * d.pitch + x] = -0.5f * s;
 }
 
 __global__ void __launch_bounds__(256) jacobi_sweep_simple_kernel(Domain d, const FrameParams* __restrict__ frame,
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(256) jacobi_sweep_simple_kernel(Domain d, cons
     const int z = d.z_own0 + blockIdx.z;
     int still = 0;
     if (x < d.nx && y < d.ny) {
-        const Nbr n = neighbours(d, x, y, z);
+        const Nbr n = neighbours(d, x, y, z, d.pitch);
         const bool act = sweep == 0 ? true : active[n.c] != 0;
         const float x0 = in[n.c];
         if (!act) {
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(256) gradient_kernel(Domain d, const FramePara
     const int y = blockIdx.y * 8 + threadIdx.y;
     const int z = d.z_own0 + blockIdx.z;
     if (x >= d.nx || y >= d.ny) return;
-    const Nbr n = neighbours(d, x, y, z);
-    const float4 v = load_texel4(vel_in, n.c);
+    const Nbr nv = neighbours(d, x, y, z, d.nx), n = neighbours(d, x, y, z, d.pitch);
+    const float4 v = load_texel4(vel_in, nv.c);
     float u[3] = {v.x, v.y, v.z};
     if (0.0f < frame->dt) {
         const float* __restrict__ p = state->p_cur ? p1 : p0;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) gradient_kernel(Domain d, const FramePara
             u[k] = u[k] * m;
         }
     }
-    vel_out[n.c] = pack_texel4(u[0], u[1], u[2], 0.0f);
+    vel_out[nv.c] = pack_texel4(u[0], u[1], u[2], 0.0f);
 }
 
 inline dim3 plane_grid(const Domain& d) { return dim3((d.nx + 31) / 32, (d.ny + 7) / 8, d.z_own1 - d.z_own0); }

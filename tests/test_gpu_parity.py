@@ -161,11 +161,13 @@ def test_fused_jacobi_every_T_and_ragged_tiles(fx, oracle_mod, n, fuse_t):
 
 
 @pytest.mark.parametrize("tile", ["64", "128"])
-@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3)])
+@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3),
+                               (150, 150, 20), (61, 61, 11), (118, 118, 9), (59, 59, 24)])
 def test_default_schedule_on_both_tile_widths(fx, oracle_mod, monkeypatch, n, tile):
     """The default schedule (T = 2; bricks that froze in the first pass are copied only next to active bricks; the final
     pressure settles in the first pass's output buffer) with the tile width forced to 64 and to 128 cells (normally
-    chosen per grid)."""
+    chosen per grid).  Widths that are not a multiple of 8 (or of 4: the grid's x face then cuts through a quad) run on
+    pitched pressure rows (common.cuh Domain::pitch) — e.g. the 150-wide grid of the reference's Bin/FluidGI.bat."""
     monkeypatch.setenv("FXB_TILE", tile)
     f, o = make_pair(fx, oracle_mod, n)
     monkeypatch.delenv("FXB_TILE")
@@ -208,15 +210,21 @@ def test_fused_jacobi_partial_last_pass_and_no_early_exit(fx, oracle_mod, early,
     compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
 
 
-def test_unsupported_width_falls_back_to_per_sweep_kernels(fx, oracle_mod):
-    """nx not a multiple of 8 (e.g. the 150^3 of Bin/FluidGI.bat): still CUDA, one sweep per launch."""
-    n = (30, 30, 30)
+@pytest.mark.parametrize("n,fused", [((30, 30, 30), 1), ((6, 6, 6), 0)])
+def test_any_width_and_the_per_sweep_kernels_below_eight(fx, oracle_mod, n, fused):
+    """A width that is not a multiple of 8 (like the 150^3 of Bin/FluidGI.bat) takes the tuned pressure solve on pitched
+    rows, with the per-voxel divergence / gradient kernels around it; grids narrower than 8 cells use the per-sweep
+    kernels (still CUDA, one sweep per launch)."""
     f, o = make_pair(fx, oracle_mod, n)
-    assert f.stats().jacobi_fused == 0
+    assert f.stats().jacobi_fused == fused
     dt = fx.dt_for_grid(*n)
     for _ in range(3):
         f.step(dt); o.step(dt)
+        assert f.stats().s_exec == o.s_exec
     compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+    q = f.get_field(fx.FIELD_PRESSURE)
+    f.set_field(fx.FIELD_PRESSURE, q)  # pitched rows <-> the dense host layout, both directions
+    assert np.array_equal(f.get_field(fx.FIELD_PRESSURE), q)
 
 
 def test_graph_and_stream_launch_paths_agree(fx, oracle_mod):

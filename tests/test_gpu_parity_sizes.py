@@ -24,6 +24,7 @@ def fx():
 def test_emitter_driven_frames_at_baseline_sizes(fx, oracle_mod, n, steps):
     oracle_mod.threads(os.cpu_count() or 1)
     f, o = make_pair(fx, oracle_mod, n)
+    assert f.stats().jacobi_fused == 1  # every 3D width takes the tuned pressure solve (pitched rows)
     dt = fx.dt_for_grid(*n)
     for k in range(steps):
         f.step(dt); o.step(dt)
