@@ -73,47 +73,73 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
         if (threadIdx.x == 0 && threadIdx.y == 0) peer_wait(pv, frame->epoch_base + 1, near_lo, near_hi);
         __syncthreads();
     }
-    if (x0 >= d.nx || y >= d.ny) return;
+    // Threads beyond the grid's x edge stay (they take part in the barriers and shuffles below) on clamped coordinates
+    // and store nothing.  (ny is a multiple of 8 on this path: nx == ny, nx % 8 == 0.)
+    const bool valid = x0 < d.nx;
+    const int xq = valid ? x0 : d.nx - 4;
+    const int tx = threadIdx.x, ty = threadIdx.y;
     const unsigned plane = (unsigned)d.nx * d.ny;
-    const unsigned row_c = (unsigned)y * d.nx + x0;
-    const unsigned row_u = (unsigned)(max(y, 1) - 1) * d.nx + x0;
-    const unsigned row_d = (unsigned)min(y + 1, d.ny - 1) * d.nx + x0;
+    const unsigned row_c = (unsigned)y * d.nx + xq;
+    const unsigned row_u = (unsigned)(max(y, 1) - 1) * d.nx + xq;
+    const unsigned row_d = (unsigned)min(y + 1, d.ny - 1) * d.nx + xq;
     const unsigned row0 = (unsigned)y * d.nx;
-    const int xl = max(x0, 1) - 1, xr = min(x0 + 4, d.nx - 1);
+    const int xl = max(xq, 1) - 1, xr = min(xq + 4, d.nx - 1);
     const unsigned short* vs = reinterpret_cast<const unsigned short*>(vel);
+    // the y components of the CTA's rows (plus one row above and below) of the plane being processed, double-buffered
+    // by plane parity: [buffer][row + 1][quad] = the four y halves of a quad
+    __shared__ uint2 s_y[2][10][32];
+    auto y_of = [](const Quad8& q) {  // high halves of the texels' first words
+        return make_uint2(__byte_perm(q.a.x, q.a.z, 0x7632), __byte_perm(q.b.x, q.b.z, 0x7632));
+    };
 
     auto zoff = [&](int z) { return (unsigned)(z - d.z_first) * plane; };
-    // plane below the first one (clamped at the grid face) and the first centre plane
-    Quad8 below = load_quad8(vel, zoff(max(z_begin, 1) - 1) + row_c);
+    // plane below the first one (clamped at the grid face) and the first two planes of the chunk
+    const Quad8 below = load_quad8(vel, zoff(max(z_begin, 1) - 1) + row_c);
     float fz[4] = {h_lo(below.a.y), h_lo(below.a.w), h_lo(below.b.y), h_lo(below.b.w)};
     Quad8 c = load_quad8(vel, zoff(z_begin) + row_c);
-    // Software pipeline: everything plane z needs besides `c` (the plane above, the rows y-1 / y+1 and the two x-edge
-    // texels of plane z) is fetched one iteration ahead, so a thread always has a full plane of loads in flight.
+    Quad8 above = load_quad8(vel, zoff(min(z_begin + 1, d.nz - 1)) + row_c);
+    // Software pipeline: the plane two above (streamed from HBM), the rows just outside the CTA (one quad for the
+    // threads of the first / last row) and the x-edge texels of the warp's first / last lane are fetched one iteration
+    // ahead.  Everything else a plane needs comes from registers (z), shared memory (y) or shuffles (x): each texel is
+    // loaded from HBM once, and only the CTA's halo comes through the caches a second time.
     struct Fetch {
-        Quad8 b, u, dn;
+        Quad8 above2, edge_row;
         unsigned short el, er;
     };
-    auto fetch = [&](int z) {
+    auto fetch = [&](int z) {  // for plane z: its edge data, and the plane z + 2
         Fetch f;
         const unsigned zc = zoff(z);
-        f.b = load_quad8(vel, zoff(min(z + 1, d.nz - 1)) + row_c);  // plane above (clamped)
-        f.u = load_quad8(vel, zc + row_u);
-        f.dn = load_quad8(vel, zc + row_d);
-        f.el = __ldg(vs + 4 * (size_t)(zc + row0 + xl));
-        f.er = __ldg(vs + 4 * (size_t)(zc + row0 + xr));
+        f.above2 = load_quad8(vel, zoff(min(z + 2, d.nz - 1)) + row_c);
+        f.edge_row.a = f.edge_row.b = make_uint4(0u, 0u, 0u, 0u);
+        if (ty == 0) f.edge_row = load_quad8(vel, zc + row_u);
+        if (ty == 7) f.edge_row = load_quad8(vel, zc + row_d);
+        f.el = f.er = 0;
+        if (tx == 0) f.el = __ldg(vs + 4 * (size_t)(zc + row0 + xl));
+        if (tx == 31 || !valid || xq + 4 >= d.nx) f.er = __ldg(vs + 4 * (size_t)(zc + row0 + xr));
         return f;
     };
     Fetch cur = fetch(z_begin);
     for (int z = z_begin; z < z_end; ++z) {
         const unsigned zc = zoff(z);
+        const int buf = z & 1;
+        // publish this thread's y components (and, from the first / last row, the row outside the CTA)
+        s_y[buf][ty + 1][tx] = y_of(c);
+        if (ty == 0) s_y[buf][0][tx] = y_of(cur.edge_row);
+        if (ty == 7) s_y[buf][9][tx] = y_of(cur.edge_row);
         Fetch nxt = cur;
         if (z + 1 < z_end) nxt = fetch(z + 1);
-        const Quad8 &b = cur.b, &u = cur.u, &dn = cur.dn;
-        const float vx[6] = {half_bits_to_float(cur.el), h_lo(c.a.x), h_lo(c.a.z),
-                             h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float(cur.er)};
-        const float uy[4] = {h_hi(u.a.x), h_hi(u.a.z), h_hi(u.b.x), h_hi(u.b.z)};
-        const float dy[4] = {h_hi(dn.a.x), h_hi(dn.a.z), h_hi(dn.b.x), h_hi(dn.b.z)};
-        const float bz[4] = {h_lo(b.a.y), h_lo(b.a.w), h_lo(b.b.y), h_lo(b.b.w)};
+        __syncthreads();
+        const uint2 u = s_y[buf][ty][tx], dn = s_y[buf][ty + 2][tx];
+        // x neighbours of the quad's end cells: the neighbouring lanes' texels, or the fetched edge texel
+        const unsigned own_first = c.a.x & 0xffffu, own_last = c.b.z & 0xffffu;
+        unsigned left = __shfl_up_sync(0xffffffffu, own_last, 1), right = __shfl_down_sync(0xffffffffu, own_first, 1);
+        if (tx == 0) left = cur.el;
+        if (tx == 31 || xq + 4 >= d.nx) right = cur.er;
+        const float vx[6] = {half_bits_to_float((unsigned short)left), h_lo(c.a.x), h_lo(c.a.z),
+                             h_lo(c.b.x), h_lo(c.b.z), half_bits_to_float((unsigned short)right)};
+        const float uy[4] = {h_lo(u.x), h_hi(u.x), h_lo(u.y), h_hi(u.y)};
+        const float dy[4] = {h_lo(dn.x), h_hi(dn.x), h_lo(dn.y), h_hi(dn.y)};
+        const float bz[4] = {h_lo(above.a.y), h_lo(above.a.w), h_lo(above.b.y), h_lo(above.b.w)};
         float out[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -125,14 +151,17 @@ __global__ void __launch_bounds__(256) divergence_quad_kernel(Domain d, const __
             out[j] = -0.5f * s;
         }
         const float4 res = make_float4(out[0], out[1], out[2], out[3]);
-        *reinterpret_cast<float4*>(rhs + zc + row_c) = res;
-        if (FUSED && near_lo && z < d.z_own0 + push_depth)
-            *reinterpret_cast<float4*>(rhs_lo + (long long)zc + (long long)pv.dz_lo * plane + row_c) = res;
-        if (FUSED && near_hi && z >= d.z_own1 - push_depth)
-            *reinterpret_cast<float4*>(rhs_hi + (long long)zc + (long long)pv.dz_hi * plane + row_c) = res;
-        // march: the centre plane becomes the plane below, the plane above becomes the centre
+        if (valid) {
+            *reinterpret_cast<float4*>(rhs + zc + row_c) = res;
+            if (FUSED && near_lo && z < d.z_own0 + push_depth)
+                *reinterpret_cast<float4*>(rhs_lo + (long long)zc + (long long)pv.dz_lo * plane + row_c) = res;
+            if (FUSED && near_hi && z >= d.z_own1 - push_depth)
+                *reinterpret_cast<float4*>(rhs_hi + (long long)zc + (long long)pv.dz_hi * plane + row_c) = res;
+        }
+        // march: the centre plane becomes the plane below, the plane above the centre, the plane two above the plane above
         fz[0] = h_lo(c.a.y); fz[1] = h_lo(c.a.w); fz[2] = h_lo(c.b.y); fz[3] = h_lo(c.b.w);
-        c = cur.b;
+        c = above;
+        above = cur.above2;
         cur = nxt;
     }
 }
