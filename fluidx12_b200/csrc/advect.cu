@@ -232,15 +232,44 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
     const float atten = fmaxf(__fmaf_rn(-dt, 0.200000003f, 1.0f), 0.0f);
     const unsigned plane = (unsigned)d.nx * d.ny;
     unsigned self = ((unsigned)(z0 - d.z_first) * d.ny + y) * d.nx + x;
-    // the field is written by the neighbours between frames (fused halos): no non-coherent loads of halo planes
-    uint2 sv = __ldg(vel_in + self), sc = __ldg(col_in + self);
-    for (int z = z0; z < z1; ++z) {
-        uint2 nv = sv, nc = sc;
-        if (z + 1 < z1) {  // the next plane's own texels travel while this plane is processed
-            nv = __ldg(vel_in + self + plane);
-            nc = __ldg(col_in + self + plane);
+    // The own texels of all kZ planes are requested at once: 64 bytes in flight per thread — the kernel is a stream
+    // over most of a large grid, and a stream needs the bytes in flight more than anything else.
+    // (The field is written by the neighbours between frames with fused halos: no non-coherent loads of halo planes.)
+    uint2 sv[kZ], sc[kZ];
+#pragma unroll
+    for (int k = 0; k < kZ; ++k) {
+        sv[k] = sc[k] = make_uint2(0u, 0u);
+        if (z0 + k < z1) {
+            sv[k] = __ldg(vel_in + self + k * plane);
+            sc[k] = __ldg(col_in + self + k * plane);
         }
-        const Texels t = advect_voxel(A, dt, atten, vel_in, col_in, state, x, y, z, px, py, self, sv, sc);
+    }
+    // Rest shortcut.  A voxel whose velocity texel is all +0 back-traces onto its own texel centre wherever
+    // fma(pos, N, -0.5) reproduces the index (the `still` tables; always for power-of-two grids), so both fetches return
+    // the voxel's own texels: the new velocity is +0 * atten = +0 and the new colour its own colour * atten — exactly
+    // what advect_voxel computes for it, minus the trace.  Texels holding a -0 and voxels in the emitter's box take the
+    // general path.  This is the quiescent far field: most of a large grid.
+    const bool still_xy = dt > 0.0f && __ldg(A.tab.still[0] + x) != 0.0f && __ldg(A.tab.still[1] + y) != 0.0f;
+    const bool box_xy = x >= A.em.x0 && x < A.em.x1 && y >= A.em.y0 && y < A.em.y1;
+    const float2 at2 = make_float2(atten, atten);
+    auto neg_zero = [](unsigned w) { return (w & 0xffffu) == 0x8000u || (w >> 16) == 0x8000u; };
+#pragma unroll
+    for (int k = 0; k < kZ; ++k) {
+        const int z = z0 + k;
+        if (z >= z1) break;
+        Texels t;
+        const bool rest = still_xy && (sv[k].x | sv[k].y) == 0u && __ldg(A.tab.still[2] + z) != 0.0f && z >= A.zv0 &&
+                          z < A.zv1 - 1 && !(box_xy && z >= A.em.z0 && z < A.em.z1) && !neg_zero(sc[k].x) &&
+                          !neg_zero(sc[k].y);
+        if (rest) {
+            Pair4 c = widen(sc[k]);
+            c.lo = mul2(c.lo, at2);
+            c.hi = mul2(c.hi, at2);
+            t.vel = make_uint2(0u, 0u);
+            t.col = pack_texel4(c.lo.x, c.lo.y, c.hi.x, c.hi.y);
+        } else {
+            t = advect_voxel(A, dt, atten, vel_in, col_in, state, x, y, z, px, py, self, sv[k], sc[k]);
+        }
         vel_out[self] = t.vel;
         col_out[self] = t.col;
         if (FUSED && near_lo) {
@@ -253,8 +282,6 @@ advect_kernel(const __grid_constant__ AdvectArgs A, const __grid_constant__ Peer
             if (z == d.z_own1 - 1) A.vel_out_hi[at] = t.vel;
             if (z >= d.z_own1 - A.reach) A.col_hi[parity][at] = t.col;
         }
-        sv = nv;
-        sc = nc;
         self += plane;
     }
 }

@@ -142,10 +142,13 @@ struct Emitter {
 // Per-axis tables indexed by the global voxel coordinate, computed once on the host with the shader's own
 // arithmetic: pos = (i + 0.5) / N (a true IEEE division), bp = fma(pos, 2, -1) and
 // wall = clamp((-|bp| + 0.97) * (1/0.03), -1, 1), the soft-wall damping factor of CSProject3D.hlsl:106-108.
+// `still[a][i]` (as a float, 1 or 0): a voxel at rest back-traces exactly onto its own texel centre along axis a, i.e.
+// fma(pos[i], N, -0.5) == i, and both taps are inside the grid (i <= N - 2) — the advection's rest shortcut.
 struct AxisTables {
     const float* pos[3];
     const float* bp[3];
     const float* wall[3];
+    const float* still[3];
 };
 
 // Packed fp32 (Blackwell FADD2/FMUL2/FFMA2): two IEEE round-to-nearest operations per instruction, bit-identical

@@ -95,7 +95,7 @@ int build_axis_tables(fxb_sim* s) {
     const bool is3d = s->dom.nz > 1;
     size_t off[3], total = 0;
     for (int a = 0; a < 3; ++a) { off[a] = total; total += ((size_t)n[a] + 3) / 4 * 4; }
-    std::vector<float> host(3 * total, 0.0f);
+    std::vector<float> host(4 * total, 0.0f);
     for (int a = 0; a < 3; ++a)
         for (int i = 0; i < n[a]; ++i) {
             const float pos = ((float)i + 0.5f) / (float)n[a];
@@ -105,6 +105,8 @@ int build_axis_tables(fxb_sim* s) {
             host[off[a] + i] = pos;
             host[total + off[a] + i] = bp;
             host[2 * total + off[a] + i] = w;
+            // (a == 2 on a 2D grid: W = 1, the trace is fma(pos, 1, -0.5) = 0 and the single plane has no second tap)
+            host[3 * total + off[a] + i] = (fmaf(pos, (float)n[a], -0.5f) == (float)i && i <= n[a] - 2) ? 1.0f : 0.0f;
         }
     FXB_CUDA(cudaMalloc((void**)&s->axis_tables, host.size() * sizeof(float)));
     FXB_CUDA(cudaMemcpy(s->axis_tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -112,6 +114,7 @@ int build_axis_tables(fxb_sim* s) {
         s->tab.pos[a] = s->axis_tables + off[a];
         s->tab.bp[a] = s->axis_tables + total + off[a];
         s->tab.wall[a] = s->axis_tables + 2 * total + off[a];
+        s->tab.still[a] = s->axis_tables + 3 * total + off[a];
     }
     return FXB_OK;
 }

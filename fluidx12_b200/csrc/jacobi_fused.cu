@@ -38,16 +38,9 @@
 #include "jacobi_common.cuh"
 #include "kernels.h"
 
-// Unroll factor of the marching loop (tuning knob of the build).
-#ifndef FXB_K_UNROLL
-#define FXB_K_UNROLL 1
-#endif
-
 namespace fxb {
 
 namespace {
-
-constexpr int kUnrollK = FXB_K_UNROLL;
 
 // One fused pass (see the file header).  FUSED: the multi-GPU instantiation with fused halos (common.cuh PeerView);
 // the single-GPU one carries none of that code.
@@ -374,7 +367,7 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
         for (int l = 1; l <= T; ++l) ro[l] = ro[0];
         int pub_w = 0;  // half of the published planes written in this iteration (read in the next one)
 
-#pragma unroll kUnrollK
+#pragma unroll 1  // (unrolling by 2 or 3 was measured on B200: same time, 2-3x the code)
         for (int k = zl0; k <= k_end; ++k) {
             float4 nw[kRows];   // the plane the level below produced in this iteration
             unsigned nfl = 0;
