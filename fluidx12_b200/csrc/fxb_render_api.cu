@@ -35,10 +35,12 @@ int fxb_light_map(fxb_sim* s, const fxb_light_params* params, void* cuda_stream)
     }
     // what Fluid::Render binds: m_colors[m_frameParity] (SRV_TABLE_RAY_MARCH + !m_frameParity, Fluid.cpp:760-770, 870)
     const char* colour_own = static_cast<const char*>(s->col[s->parity]) + s->own_offset() * 8;
-    if (fxb::launch_light_map(s->dom, colour_own, s->light_density, s->light_map, params, &s->comm,
-                              (cudaStream_t)cuda_stream) != cudaSuccess)
+    // (the launcher has already consumed the sticky error: report the code it returned)
+    const cudaError_t le = fxb::launch_light_map(s->dom, colour_own, s->light_density, s->light_map, params, &s->comm,
+                                                 (cudaStream_t)cuda_stream);
+    if (le != cudaSuccess)
         return fail(s->multi() ? FXB_ERR_NCCL : FXB_ERR_CUDA, "fxb_light_map: launch failed: " +
-                    (s->multi() ? fxb::halo_last_error() : std::string(cudaGetErrorString(cudaGetLastError()))));
+                    (s->multi() ? fxb::halo_last_error() + " / " : std::string()) + cudaGetErrorString(le));
     s->last_stream = (cudaStream_t)cuda_stream;
     return FXB_OK;
 }
