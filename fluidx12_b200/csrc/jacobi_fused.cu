@@ -44,7 +44,7 @@ namespace {
 
 // One fused pass (see the file header).  FUSED: the multi-GPU instantiation with fused halos (common.cuh PeerView);
 // the single-GPU one carries none of that code.
-template <class S, bool FUSED>
+template <class S, bool FUSED, bool FIRST>
 __global__ void __launch_bounds__(S::kThreads, S::kCtasPerSm)
 jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_constant__ CUtensorMap map_p1,
                    const __grid_constant__ CUtensorMap map_rhs, const FrameParams* __restrict__ frame,
@@ -61,7 +61,10 @@ jacobi_pass_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_cons
     constexpr bool producer = false;
 
     // independent loads first (one round trip instead of a chain), then the decisions
-    const int pass = P.pass, s0 = P.s0;
+    // FIRST: the instantiation for the first pass of a frame — with the brick-resident kernel taking every later pass it
+    // is the only one the default schedule launches, and everything that depends on `pass` folds away in it (no lists,
+    // no flag bytes to fetch, nothing to copy).
+    const int pass = FIRST ? 0 : P.pass, s0 = FIRST ? 0 : P.s0;
     const float dt = frame->dt;
     const unsigned long long need = frame->epoch_base + (unsigned long long)P.event;
     const int p_cur = state->p_cur;
@@ -667,10 +670,11 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_device != dev) {
-        cudaError_t e = cudaFuncSetAttribute(jacobi_pass_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)S::kBytes);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(jacobi_pass_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
+        cudaError_t e = cudaSuccess;
+        const void* fns[4] = {(const void*)jacobi_pass_kernel<S, false, false>, (const void*)jacobi_pass_kernel<S, true, false>,
+                              (const void*)jacobi_pass_kernel<S, false, true>, (const void*)jacobi_pass_kernel<S, true, true>};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes);
         if (e != cudaSuccess) return e;
         attr_device = dev;
     }
@@ -687,12 +691,15 @@ cudaError_t launch_shape(const FusedJacobi& J, const Domain& d, const FrameParam
     const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map_p[0]);
     const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map_p[1]);
     const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map_rhs);
-    if ((pv.has_lo || pv.has_hi) && !plain)
-        jacobi_pass_kernel<S, true><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], J.p[1],
-                                                                              J.mask[0], J.mask[1], W, P, pv, peers);
-    else
-        jacobi_pass_kernel<S, false><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], J.p[1],
-                                                                               J.mask[0], J.mask[1], W, P, pv, peers);
+    const bool fused = (pv.has_lo || pv.has_hi) && !plain;
+#define FXB_GO(FU, FI) jacobi_pass_kernel<S, FU, FI><<<grid, S::kThreads, S::kBytes, stream>>>(mp0, mp1, mr, frame, state, J.p[0], \
+                                                                                        J.p[1], J.mask[0], J.mask[1], W, P, pv, peers)
+    if (pass == 0) {
+        if (fused) FXB_GO(true, true); else FXB_GO(false, true);
+    } else {
+        if (fused) FXB_GO(true, false); else FXB_GO(false, false);
+    }
+#undef FXB_GO
     return cudaGetLastError();
 }
 
