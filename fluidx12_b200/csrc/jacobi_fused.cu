@@ -726,10 +726,6 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     J->nty = tiles_for(d.ny, out_y);
     const int nz_out = d.z_own1 - d.z_own0;
     J->bz = nz_out >= 8 ? 8 : nz_out;
-    if (const char* e = getenv("FXB_BZ")) {  // tuning knob: planes per brick
-        const int v = atoi(e);
-        if (v >= 1 && v <= nz_out) J->bz = v;
-    }
     J->nzc = (nz_out + J->bz - 1) / J->bz;
     J->p[0] = p0; J->p[1] = p1; J->rhs = rhs;
     if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y)) return -1;
@@ -745,7 +741,6 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
         if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
         J->resident_from = 1;
         if (const char* e = getenv("FXB_RESIDENT_FROM")) J->resident_from = atoi(e);  // tuning knob: first resident pass
-        if (const char* e = getenv("FXB_PDL")) J->pdl = atoi(e) != 0;                 // tuning knob: dependent launch on / off
     }
     int dev = 0;
     cudaGetDevice(&dev);

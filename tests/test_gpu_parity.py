@@ -160,6 +160,23 @@ def test_fused_jacobi_every_T_and_ragged_tiles(fx, oracle_mod, n, fuse_t):
         compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
 
 
+@pytest.mark.parametrize("resident_from", ["0", "3", "999"])
+@pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (150, 150, 20)])
+def test_pass_kernels_are_interchangeable(fx, oracle_mod, monkeypatch, n, resident_from):
+    """The default schedule runs the first pass in the z-marching kernel and every later pass in the brick-resident one;
+    either kernel can run any pass (FXB_RESIDENT_FROM): all of them resident, the first three marching, all marching."""
+    monkeypatch.setenv("FXB_RESIDENT_FROM", resident_from)
+    f, o = make_pair(fx, oracle_mod, n)
+    monkeypatch.delenv("FXB_RESIDENT_FROM")
+    assert f.stats().jacobi_fused == 1
+    inject(fx, oracle_mod, f, o, n, seed=5)
+    dt = fx.dt_for_grid(*n)
+    for _ in range(4):
+        f.step(dt); o.step(dt)
+        assert f.stats().s_exec == o.s_exec
+    compare(fx, oracle_mod, f, o, TOL_1STEP, exact=True)
+
+
 @pytest.mark.parametrize("tile", ["64", "128"])
 @pytest.mark.parametrize("n", [(64, 64, 64), (136, 136, 50), (248, 248, 36), (40, 40, 7), (128, 128, 3),
                                (150, 150, 20), (61, 61, 11), (118, 118, 9), (59, 59, 24)])
