@@ -66,7 +66,7 @@ class FxbStats(C.Structure):
         ("brick_cells", C.c_uint64),
         ("bricks_per_pass", C.c_uint64),
         ("jacobi_fused", C.c_int32),
-        ("reserved", C.c_int32),
+        ("tail_from", C.c_int32),
     ]
 
 

@@ -240,7 +240,7 @@ void enqueue_phase(Enqueue& q, int phase) {
             }
             if (s->quad)
                 fxb::launch_divergence_quad(d, s->d_frame, s->vel[1], s->rhs, s->pv, (float*)s->comm.peer_of(s->rhs, 0),
-                                            (float*)s->comm.peer_of(s->rhs, 1), s->jac.T, st);
+                                            (float*)s->comm.peer_of(s->rhs, 1), s->jac.push_depth, st);
             else fxb::launch_divergence(d, s->d_frame, s->vel[1], s->rhs, st);
             q.launched(cudaGetLastError(), "divergence_kernel");
             q.mark(1, 2);
@@ -249,7 +249,7 @@ void enqueue_phase(Enqueue& q, int phase) {
             if (s->fused) {
                 const int npass = fxb::fused_jacobi_passes(s->jac, s->cfg.jacobi_iters);
                 if (cudaMemsetAsync(s->jac.work_count, 0, 3 * (fxb::FusedJacobi::kMaxPasses + 1) * sizeof(int), st) != cudaSuccess ||
-                    cudaMemsetAsync(s->jac.brick_flag, 0, fxb::fused_jacobi_bricks(s->jac) * sizeof(int), st) != cudaSuccess)
+                    cudaMemsetAsync(s->jac.brick_flag, 0, 2 * fxb::fused_jacobi_bricks(s->jac) * sizeof(int), st) != cudaSuccess)
                     q.launched(cudaGetLastError(), "cudaMemsetAsync(work lists)", 0);
                 const bool mg = s->multi() && s->dt > 0.0f;
                 // Multi-GPU: the pressure (+ freeze flag) halo is exchanged every G passes, G*T planes deep; in
@@ -534,7 +534,8 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             e = cudaMalloc((void**)&s->jac.mask[i], std::max(mask_bytes, ipc_min));
             if (e == cudaSuccess) e = cudaMemset(s->jac.mask[i], 0, mask_bytes);
         }
-        if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, cfg->fuse_t, s->p[0], s->p[1], s->rhs) != 0)
+        if (e == cudaSuccess && fxb::fused_jacobi_plan(&s->jac, s->dom, cfg->fuse_t, s->p[0], s->p[1], s->rhs,
+                                                            !s->multi() || cfg->halo_backend == FXB_HALO_FUSED) != 0)
             return cleanup_fail(fail(FXB_ERR_CUDA, "fxb_create: cuTensorMapEncodeTiled failed"));
         s->fuse_t = s->jac.T;
         const size_t nc = 3 * (fxb::FusedJacobi::kMaxPasses + 1);
@@ -543,8 +544,9 @@ int fxb_create(const fxb_config* cfg, fxb_sim** out) {
             if (e == cudaSuccess) e = cudaMemset(s->jac.work_list[i], 0, 2 * (size_t)s->jac.list_stride * sizeof(int));
         }
         const size_t nbricks = fxb::fused_jacobi_bricks(s->jac);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.brick_flag, nbricks * sizeof(int));
-        if (e == cudaSuccess) e = cudaMemset(s->jac.brick_flag, 0, nbricks * sizeof(int));
+        // (two words per brick: the first pass's flags, and where the halves of a brick meet in the tail passes)
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.brick_flag, 2 * nbricks * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemset(s->jac.brick_flag, 0, 2 * nbricks * sizeof(int));
         s->jac.copy_all = s->multi() && s->jacobi_group > 1;
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->jac.work_count, nc * sizeof(int));
         if (e == cudaSuccess) e = cudaMemset(s->jac.work_count, 0, nc * sizeof(int));
@@ -780,6 +782,7 @@ void fill_stats(const fxb_sim* s, const fxb::StepState& st, int parity, uint64_t
     out->bricks_processed = st.bricks_processed;
     out->bricks_copied = st.bricks_copied;
     out->jacobi_fused = s->fused ? 1 : 0;
+    out->tail_from = s->fused && s->jac.tail_from <= fxb::FusedJacobi::kMaxPasses ? s->jac.tail_from : 0;
     if (s->fused) {
         out->brick_cells = fxb::fused_jacobi_brick_cells(s->jac);
         out->bricks_per_pass = fxb::fused_jacobi_bricks(s->jac);

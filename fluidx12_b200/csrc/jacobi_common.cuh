@@ -100,6 +100,7 @@ struct WorkLists {
     int* relax_count;  // [pass]
     int* copy_count;   // [pass]
     int* brick_flag;   // [bricks] first pass: bit 0 = all cells froze, bit 1 = a brick next to it is still active
+    int* brick_half;   // [bricks] passes on half bricks: where the two halves of a brick meet (zero between passes)
 };
 
 // Fused halos: the neighbours' copies of the pressure and freeze-mask ping-pong buffers ([side][buffer], side 0 =
@@ -246,7 +247,7 @@ inline PassParams make_pass_params(const FusedJacobi& J, const Domain& d, int pa
     P.z_face_hi = d.nz - d.z_first;
     P.z_out0 = d.z_own0 - d.z_first; P.z_out1 = d.z_own1 - d.z_first;
     P.bz = J.bz; P.ntx = J.ntx; P.nty = J.nty; P.nzc = J.nzc;
-    P.pass = pass; P.s0 = pass * J.T; P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
+    P.pass = pass; P.s0 = fused_jacobi_s0(J, pass); P.levels_total = iters; P.early_exit = early_exit; P.run_all = run_all ? 1 : 0;
     P.ext_lo = ext_lo; P.ext_hi = ext_hi;
     P.copy_all = J.copy_all ? 1 : 0;
     P.keep_lo = d.z_own0 > 0 ? 1 : 0;
@@ -254,7 +255,7 @@ inline PassParams make_pass_params(const FusedJacobi& J, const Domain& d, int pa
     P.first_brick = 0;
     P.first_count = J.ntx * J.nty * J.nzc;
     P.event = 2 + pass;
-    P.push_depth = J.T;
+    P.push_depth = J.push_depth;
     return P;
 }
 
@@ -275,6 +276,7 @@ inline WorkLists make_work_lists(const FusedJacobi& J) {
     W.copy[0] = J.work_list[0] + J.list_stride; W.copy[1] = J.work_list[1] + J.list_stride;
     W.relax_count = J.work_count; W.copy_count = J.work_count + np;
     W.brick_flag = J.brick_flag;
+    W.brick_half = J.brick_flag + (size_t)J.ntx * J.nty * J.nzc;
     return W;
 }
 

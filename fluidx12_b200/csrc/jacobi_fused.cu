@@ -567,7 +567,7 @@ template <class S, bool FUSED>
 __global__ void __launch_bounds__(S::kThreads)
 jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restrict__ state, float* p0, float* p1,
                      unsigned char* m0, unsigned char* m1, const __grid_constant__ WorkLists W,
-                     const __grid_constant__ PassParams P, const int fuse_t, const int force_passes,
+                     const __grid_constant__ PassParams P, const int fuse_t, const int tail_from, const int force_passes,
                      const __grid_constant__ PeerView pv,
                      const __grid_constant__ JacobiPeers peers) {
     const int iters = P.levels_total;
@@ -577,7 +577,9 @@ jacobi_settle_kernel(const FrameParams* __restrict__ frame, StepState* __restric
         s = 1;
         while (s < iters && state->active_after[s - 1] != 0ull) ++s;
     }
+    // passes executed: T sweeps each up to pass tail_from, four each from there on
     int passes = (s + fuse_t - 1) / fuse_t;
+    if (passes > tail_from) passes = tail_from + (s - tail_from * fuse_t + 3) / 4;
     if (force_passes >= 0 && live) passes = force_passes;
     const int p_cur = state->p_cur;  // still the frame's input buffer X; Y is the other one
     if (passes > 0 && ((passes - 1) & 1)) {
@@ -710,7 +712,7 @@ int tiles_for(int n, int out) { return (n + out - 1) / out; }
 
 bool fused_jacobi_supported(const Domain& d) { return d.nz > 1 && d.nx >= 8 && (d.pitch % 8) == 0; }
 
-int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs) {
+int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs, bool allow_tail) {
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     J->T = fuse_t == 0 ? 2 : fuse_t;  // 0 = library default
     const int T = J->T;
@@ -734,6 +736,7 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
     // Brick-resident form for the latency-bound part of the solve.  Measured on B200 (profiles/): from the second pass
     // on the resident form is the faster one at 128^3, 256^3 and 512^3 (the first pass, every brick dense, is not).
     J->resident_from = FusedJacobi::kMaxPasses + 1;
+    J->tail_from = FusedJacobi::kMaxPasses + 1;
     if (resident_jacobi_supported(*J)) {
         const int planes = resident_jacobi_window_planes(*J);
         if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
@@ -741,16 +744,41 @@ int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, fl
         if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map3_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, J->tile_x, J->tile_y, planes)) return -1;
         J->resident_from = 1;
         if (const char* e = getenv("FXB_RESIDENT_FROM")) J->resident_from = atoi(e);  // tuning knob: first resident pass
+        // Tail schedule (T = 2, 64-wide tiles): four sweeps per pass on half bricks once the passes are latency-bound.
+        // (z-slabs: the tail passes read four halo planes, which the halos must provide and the backend must push)
+        const int halo_lo = d.z_own0 - d.z_first, halo_hi = d.z_first + d.nz_alloc - d.z_own1;
+        const bool halo_ok = (d.z_own0 == 0 || halo_lo >= 4) && (d.z_own1 == d.nz || halo_hi >= 4);
+        if (T == 2 && J->narrow && allow_tail && halo_ok) {
+            // Measured on B200 (tools/quick_time.py, FXB_TAIL_FROM sweep): a four-sweep pass on half bricks costs about as
+            // much as 1.7 two-sweep passes (halo of four: 44 plane-updates per column instead of 2 x 18, 22 rows for 14
+            // own), so it only pays where a pass is pure latency — early on small grids (128^3: 0.346 -> 0.312 ms per
+            // step from pass 5), late on large ones (256^3: 0.908 -> 0.876 ms from pass 16; 512^3: -0.6 %).
+            // (decided from the GLOBAL grid: every rank of a z-slab run must follow the same schedule)
+            J->tail_from = (long long)J->ntx * J->nty * ((d.nz + 7) / 8) < 1000 ? 5 : 16;
+            if (const char* e = getenv("FXB_TAIL_FROM")) J->tail_from = atoi(e);  // tuning knob: first four-sweep pass
+            if (J->tail_from < J->resident_from) J->tail_from = J->resident_from;
+            if (J->tail_from < 1) J->tail_from = 1;
+            if (J->tail_from > FusedJacobi::kMaxPasses) J->tail_from = FusedJacobi::kMaxPasses + 1;
+            if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map4_p[0]), p0, d.nx, d.ny, d.pitch, d.nz_alloc, 64, 22, 16)) return -1;
+            if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map4_p[1]), p1, d.nx, d.ny, d.pitch, d.nz_alloc, 64, 22, 16)) return -1;
+            if (!make_plane_map(reinterpret_cast<CUtensorMap*>(J->map4_rhs), rhs, d.nx, d.ny, d.pitch, d.nz_alloc, 64, 22, 16)) return -1;
+        }
     }
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&J->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    J->push_depth = J->tail_from <= FusedJacobi::kMaxPasses ? 4 : T;
     // the kernel prefetches list entries up to two grid strides ahead: the lists are padded accordingly
     J->list_stride = (int)fused_jacobi_bricks(*J) + 4 * J->num_sms + 8;
     return 0;
 }
 
-int fused_jacobi_passes(const FusedJacobi& J, int iters) { return iters <= 0 ? 0 : (iters + J.T - 1) / J.T; }
+int fused_jacobi_passes(const FusedJacobi& J, int iters) {
+    if (iters <= 0) return 0;
+    const int head = J.tail_from * J.T;  // sweeps of the passes before the tail schedule
+    if (iters <= head) return (iters + J.T - 1) / J.T;
+    return J.tail_from + (iters - head + 3) / 4;
+}
 
 size_t fused_jacobi_bricks(const FusedJacobi& J) { return (size_t)J.ntx * J.nty * J.nzc; }
 
@@ -780,7 +808,7 @@ cudaError_t launch_jacobi_pass_fused(const FusedJacobi& J, const Domain& d, cons
     if (pass >= J.resident_from)
         return launch_jacobi_pass_resident(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, 0, -1, pv,
                                            stream);
-    const int s0 = pass * J.T;
+    const int s0 = fused_jacobi_s0(J, pass);
     int first_brick = 0, first_count = -1;
     bool plain = false;
     if (pass == 0 && first_pass_split(J, pv)) {
@@ -828,7 +856,7 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
     P.levels_total = iters;
     const int npass = fused_jacobi_passes(J, iters);
     P.event = 2 + npass;
-    P.push_depth = J.T;
+    P.push_depth = J.push_depth;
     JacobiPeers peers;
     for (int side = 0; side < 2; ++side)
         for (int i = 0; i < 2; ++i) {
@@ -845,9 +873,9 @@ cudaError_t launch_jacobi_settle(const FusedJacobi& J, const Domain& d, const Fr
     // geometry of the own region only (shared by every shape of the schedule)
 #define FXB_SETTLE(S)                                                                                                     \
     if (pv.has_lo || pv.has_hi)                                                                                           \
-        jacobi_settle_kernel<S, true><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, force_passes, pv, peers); \
+        jacobi_settle_kernel<S, true><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.tail_from, force_passes, pv, peers); \
     else                                                                                                                  \
-        jacobi_settle_kernel<S, false><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, force_passes, pv, peers)
+        jacobi_settle_kernel<S, false><<<grid, S::kThreads, 0, stream>>>(frame, state, J.p[0], J.p[1], J.mask[0], J.mask[1], W, P, J.T, J.tail_from, force_passes, pv, peers)
     if (J.narrow) {
         switch (J.T) {
             case 1: FXB_SETTLE(NarrowU<1>); break;

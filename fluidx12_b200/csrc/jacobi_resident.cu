@@ -30,10 +30,12 @@ namespace fxb {
 namespace {
 
 // Tile of the resident kernel: the same own region as the marching shapes (so bricks, lists and masks are shared), one
-// thread per quad of a plane.
+// thread per quad of a plane.  `Geo` is the brick geometry the work lists are expressed in.
 template <int T_, int LX_>
 struct RShape {
+    using Geo = RShape;
     static constexpr int T = T_, LX = LX_;
+    static constexpr bool kHalf = false;           // a work item is a whole brick
     static constexpr int kTileX = 4 * LX_, kTileY = 2048 / kTileX;
     static constexpr int kThreads = LX_ * kTileY;  // 512
     static constexpr int kOutX = kTileX - 2 * kHaloX, kOutY = kTileY - 2 * T_;
@@ -43,6 +45,28 @@ struct RShape {
     static constexpr size_t kFloats = (size_t)2 * kPlanes * kPlane;
     static constexpr size_t kBytes = kFloats * sizeof(float) + 64;
     static_assert(kThreads == 512, "one thread per quad of a 2048-cell plane");
+    static_assert(kBytes + 1024 <= 233472, "shared memory budget");
+};
+
+// FOUR sweeps per pass on HALF bricks (the tail of the solve: half as many passes).  The bricks stay those of the T = 2
+// schedule (56 x 28 x 8 own cells: lists, masks and copies are shared); a work item is the lower or upper 14 rows of one,
+// so that the window with its halo of four — 64 x 22 x 16 cells of pressure and of right-hand side, 2 x 88 KB — fits
+// beside nothing else in shared memory.  The two halves of a brick run in different CTAs; whichever finishes second
+// decides whether the brick is relaxed again or copied.  352 threads, one quad column of 16 planes each.
+struct RShapeHalf4 {
+    struct Geo {  // the brick geometry of the T = 2 shapes with 64-wide tiles
+        static constexpr int T = 2, kOutX = 56, kOutY = 28, kThreads = 352;
+    };
+    static constexpr int T = 4, LX = 16;
+    static constexpr bool kHalf = true;
+    static constexpr int kTileX = 64, kTileY = Geo::kOutY / 2 + 2 * T;  // 22
+    static constexpr int kThreads = LX * kTileY;                         // 352
+    static constexpr int kPlane = kTileX * kTileY;
+    static constexpr int kBz = 8;
+    static constexpr int kPlanes = kBz + 2 * T;                          // 16: one flag nibble per plane in 64 bits
+    static constexpr size_t kFloats = (size_t)2 * kPlanes * kPlane;
+    static constexpr size_t kBytes = kFloats * sizeof(float) + 64;
+    static_assert(kThreads == Geo::kThreads && kThreads % 32 == 0, "whole warps");
     static_assert(kBytes + 1024 <= 233472, "shared memory budget");
 };
 
@@ -111,16 +135,18 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
         dbg_pass = pass;
 #endif
         FXB_STAMP();  // 0: pass start
-        const int s0 = pass * T;
+        const int s0 = P.s0;  // sweeps completed before this pass (the schedule may mix passes of 2 and of 4 sweeps)
         const unsigned long long need = epoch + 2ull + (unsigned long long)pass;  // this pass's event number (PassParams::event)
         // independent loads first (one round trip instead of a chain), then the decisions
         const unsigned long long still_prev = pass > 0 ? ld_l2(&state->active_after[s0 - 1]) : 1ull;
         const int n_relax = pass > 0 ? ld_l2(&W.relax_count[pass]) : P.first_count;
         const int n_copy = pass > 0 ? ld_l2(&W.copy_count[pass]) : 0;
         const int* list_in = W.relax[pass & 1];
-        // speculative: the first two list entries of this CTA (garbage beyond n_relax, then unused; the lists are padded)
-        int listed = pass > 0 ? ld_l2(&list_in[blockIdx.x]) : (int)blockIdx.x;
-        int listed_next = pass > 0 ? ld_l2(&list_in[blockIdx.x + gridDim.x]) : (int)(blockIdx.x + gridDim.x);
+        // speculative: the list entries of this CTA's first two work items (garbage beyond the list, then unused; the
+        // lists are padded)
+        constexpr int kItemShift = S::kHalf ? 1 : 0;  // two work items per listed brick when they are half bricks
+        int listed = pass > 0 ? ld_l2(&list_in[blockIdx.x >> kItemShift]) : (int)blockIdx.x;
+        int listed_next = pass > 0 ? ld_l2(&list_in[(blockIdx.x + gridDim.x) >> kItemShift]) : (int)(blockIdx.x + gridDim.x);
         // Fused halos: when the last CTA is done, this kernel's event is published to the neighbours — on every path.
         bool pushed = false;  // this CTA stored into a neighbour rank (uniform)
         auto finish = [&]() {
@@ -200,7 +226,7 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
                     bool lo, hi;
                     brick_faces(brick, lo, hi);
                     if (peer_sync(lo, hi)) __syncthreads();
-                    copy_frozen_brick<S, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
+                    copy_frozen_brick<typename S::Geo, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
                     if (tid == 0) ++s_copied;
                 }
                 __syncthreads();
@@ -213,25 +239,30 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
                 bool lo, hi;
                 brick_faces(brick, lo, hi);
                 if (peer_sync(lo, hi)) __syncthreads();
-                copy_frozen_brick<S, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
+                copy_frozen_brick<typename S::Geo, FUSED>(p_in, p_out, m_out, P, brick, pv, peers, pi, mi);
             }
             if (blockIdx.x == 0) n_copied += (unsigned)n_copy;
         }
         FXB_STAMP();  // 2: copies handed out
 
         const int n_ext = layer * ((P.ext_lo + P.bz - 1) / P.bz + (P.ext_hi + P.bz - 1) / P.bz);
-        const int n_work = n_relax + n_ext;
+        const int n_items = n_relax << kItemShift;
+        const int n_work = n_items + n_ext;
 
+        // A work item: a listed brick, or (kHalf) its lower / upper half: items 2i and 2i + 1 are the halves of entry i.
+        constexpr bool HALF = S::kHalf;
         auto item_of = [&](const int w, const int entry) -> Item {
-            if (w < n_relax) {
+            if (w < n_items) {
                 int brick = entry;
                 if (pass == 0) {  // the bricks (first_brick + w) mod bricks (see PassParams)
                     brick = w + P.first_brick;
                     if (brick >= layer * P.nzc) brick -= layer * P.nzc;
                 }
-                return own_item<S>(P, brick);
+                Item it = own_item<typename S::Geo>(P, brick);
+                if constexpr (HALF) it.gy0 += S::Geo::T - T + (w & 1) * (S::Geo::kOutY / 2);  // halo of T rows, 14 own rows
+                return it;
             }
-            return ext_item<S>(P, w - n_relax);
+            return ext_item<typename S::Geo>(P, w - n_items);
         };
         // the window of a work item: before anything of a face brick is staged, the neighbour's data must be there
         auto stage = [&](const Item& it) {
@@ -267,7 +298,7 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
             listed = listed_next;
             {
                 const int w2 = work_next + gridDim.x;
-                listed_next = (pass > 0 && w2 < n_relax) ? ld_l2(&list_in[w2]) : w2;
+                listed_next = (pass > 0 && w2 < n_items) ? ld_l2(&list_in[w2 >> kItemShift]) : w2;
             }
             const int zs = it.zs, ze = it.ze, z0 = zs - T;
             const int zl0 = max(z0, 0), zl1 = min(ze + T, P.nz_alloc);
@@ -406,6 +437,8 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
             };
             level(std::integral_constant<int, 1>{});
             if constexpr (T >= 2) level(std::integral_constant<int, 2>{});
+            if constexpr (T >= 3) level(std::integral_constant<int, 3>{});
+            if constexpr (T >= 4) level(std::integral_constant<int, 4>{});
 
             // everybody is done with the window; the next one is staged while this brick's output goes out
             const int any_alive = __syncthreads_or(alive != 0u);
@@ -461,17 +494,30 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
                     }
                 }
                 if (tid == 0 && (any_alive || pass > 0)) {
-                    if (pend_brick >= 0) pend_list[pend_slot] = pend_brick;
-                    pend_brick = cur.brick;
-                    if (any_alive) {
-                        pend_list = W.relax[(pass + 1) & 1];
-                        pend_slot = atomicAdd(&W.relax_count[pass + 1], 1);
-                    } else {
-                        pend_list = W.copy[(pass + 1) & 1];
-                        pend_slot = atomicAdd(&W.copy_count[pass + 1], 1);
+                    // Half bricks: the two halves meet in the brick's state word (zero between passes): the half that
+                    // arrives second knows whether either is still active, lists the brick and clears the word.
+                    bool mine_to_list = true, brick_alive = any_alive != 0;
+                    if constexpr (HALF) {
+                        const int old = atomicAdd(&W.brick_half[cur.brick], 1 + (any_alive ? 0x10000 : 0));
+                        mine_to_list = (old & 0xffff) == 1;
+                        brick_alive = brick_alive || (old >> 16) != 0;
+                        if (mine_to_list) W.brick_half[cur.brick] = 0;
                     }
+                    if (mine_to_list) {
+                        if (pend_brick >= 0) pend_list[pend_slot] = pend_brick;
+                        pend_brick = cur.brick;
+                        if (brick_alive) {
+                            pend_list = W.relax[(pass + 1) & 1];
+                            pend_slot = atomicAdd(&W.relax_count[pass + 1], 1);
+                        } else {
+                            pend_list = W.copy[(pass + 1) & 1];
+                            pend_slot = atomicAdd(&W.copy_count[pass + 1], 1);
+                        }
+                        ++n_done;
+                    }
+                } else if (!HALF || pass == 0) {
+                    if (tid == 0) ++n_done;
                 }
-                ++n_done;
             }
             FXB_STAMP();  // brick + 5: output stores issued, brick listed
         }
@@ -496,7 +542,7 @@ jacobi_resident_kernel(const __grid_constant__ CUtensorMap map_p0, const __grid_
         }
         FXB_STAMP();  // counters out
 
-        if (tid == 0) {
+        if (tid == 0) {  // (n_done is thread 0's count)
             if (n_done) atomicAdd(&state->bricks_processed, (unsigned long long)n_done);
             const unsigned c = n_copied + (unsigned)s_copied;
             if (c) atomicAdd(&state->bricks_copied, (unsigned long long)c);
@@ -530,9 +576,9 @@ cudaError_t launch_resident_shape(const FusedJacobi& J, const Domain& d, const F
     const WorkLists W = make_work_lists(J);
     const int nbricks = pass == 0 ? P.first_count : J.ntx * J.nty * J.nzc;
     const int grid = nbricks < J.num_sms ? (nbricks > 0 ? nbricks : 1) : J.num_sms;  // persistent, one CTA per SM
-    const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(J.map3_p[0]);
-    const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(J.map3_p[1]);
-    const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(J.map3_rhs);
+    const CUtensorMap& mp0 = *reinterpret_cast<const CUtensorMap*>(S::kHalf ? J.map4_p[0] : J.map3_p[0]);
+    const CUtensorMap& mp1 = *reinterpret_cast<const CUtensorMap*>(S::kHalf ? J.map4_p[1] : J.map3_p[1]);
+    const CUtensorMap& mr = *reinterpret_cast<const CUtensorMap*>(S::kHalf ? J.map4_rhs : J.map3_rhs);
     // programmatic dependent launch: this kernel may start while its predecessor in the stream drains (it waits,
     // griddepcontrol.wait, before it reads anything); the predecessor is the previous pass — resident kernels release
     // their dependents at once, any other kernel when it completes
@@ -563,6 +609,7 @@ cudaError_t launch_jacobi_pass_resident(const FusedJacobi& J, const Domain& d, c
                                         int pass, int iters, int early_exit, bool run_all, int ext_lo, int ext_hi,
                                         int first_brick, int first_count, const PeerView& pv, cudaStream_t stream) {
 #define FXB_LAUNCH(S) return launch_resident_shape<S>(J, d, frame, state, pass, iters, early_exit, run_all, ext_lo, ext_hi, first_brick, first_count, pv, stream)
+    if (pass >= J.tail_from) FXB_LAUNCH(RShapeHalf4);
     using N1 = RShape<1, 16>;
     using W1 = RShape<1, 32>;
     using N2 = RShape<2, 16>;

@@ -77,10 +77,23 @@ struct FusedJacobi {
     alignas(64) unsigned char map3_rhs[128];
     int resident_from = kMaxPasses + 1;
     bool pdl = true;           // resident passes are launched with programmatic stream serialization
+    // Tail schedule: from pass `tail_from` on a pass fuses FOUR sweeps and runs on half bricks (jacobi_resident.cu
+    // RShapeHalf4; tensor maps with its box); kMaxPasses + 1: none.  `push_depth`: planes next to an interior slab face
+    // every pass (and the divergence) also stores into the neighbour: the deepest halo any pass of the schedule reads.
+    alignas(64) unsigned char map4_p[2][128];
+    alignas(64) unsigned char map4_rhs[128];
+    int tail_from = kMaxPasses + 1;
+    int push_depth = 0;
 };
+// The schedule of a frame: sweeps completed before pass k, sweeps pass k fuses, passes needed for `iters` sweeps.
+inline int fused_jacobi_pass_t(const FusedJacobi& J, int pass) { return pass >= J.tail_from ? 4 : J.T; }
+inline int fused_jacobi_s0(const FusedJacobi& J, int pass) {
+    return pass <= J.tail_from ? pass * J.T : J.tail_from * J.T + (pass - J.tail_from) * 4;
+}
 int fused_jacobi_passes(const FusedJacobi& J, int iters);  // launches per frame
 bool fused_jacobi_supported(const Domain& d);
-int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs);
+// allow_tail: the four-sweep tail schedule may be used (single GPU or fused halos: nothing on the host separates passes)
+int fused_jacobi_plan(FusedJacobi* J, const Domain& d, int fuse_t, float* p0, float* p1, float* rhs, bool allow_tail);
 size_t fused_jacobi_bricks(const FusedJacobi& J);
 size_t fused_jacobi_brick_cells(const FusedJacobi& J);
 void fused_jacobi_brick_extent(const FusedJacobi& J, int out[3]);

@@ -79,7 +79,7 @@ typedef struct fxb_config {
 typedef struct fxb_stats {
     int32_t s_exec;            /* Jacobi sweeps in which >= 1 cell was still active, last step (global) */
     int32_t jacobi_passes;     /* fused HBM passes actually executed in the last step */
-    int32_t fuse_t;            /* sweeps fused per pass */
+    int32_t fuse_t;            /* sweeps fused per pass (before pass tail_from) */
     int32_t halo_overflow;     /* sticky: 1 if an advection back-trace left the z-halo */
     int32_t frame_parity;      /* m_frameParity */
     int32_t kernels_per_step;  /* CUDA kernels launched by one fxb_simulate */
@@ -92,7 +92,8 @@ typedef struct fxb_stats {
     uint64_t brick_cells;      /* output cells per brick (tile minus halo, x bz planes) */
     uint64_t bricks_per_pass;  /* bricks in the grid of one pass */
     int32_t jacobi_fused;      /* 1 when the fused Jacobi kernel is in use, 0 for one sweep per launch */
-    int32_t reserved;
+    int32_t tail_from;         /* first pass of a frame that fuses FOUR sweeps (the tail schedule of the tuned T = 2 solve:
+                                  passes 0 .. tail_from-1 fuse fuse_t sweeps each); 0 = every pass fuses fuse_t sweeps */
 } fxb_stats;
 
 /* Fills cfg with the defaults above (grid 128^3 as FluidX12.cpp:44). */

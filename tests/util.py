@@ -37,3 +37,13 @@ def rel_l2(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def expected_passes(s_exec, st):
+    """Fused passes a frame of `s_exec` sweeps takes under the schedule the stats record describes: `fuse_t` sweeps per
+    pass, four per pass from pass `tail_from` on (0: no tail schedule)."""
+    t, k0 = st.fuse_t, st.tail_from
+    n = -(-s_exec // t)
+    if k0 and n > k0:
+        n = k0 + -(-(s_exec - k0 * t) // 4)
+    return n
