@@ -24,8 +24,11 @@ for g in 256 512; do
   timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s $((100*K)) -c $((2*K)) --csv --log-file $out/${tag}_traffic_$g.csv \
       python tools/profile_step.py --grid $g $g $g --steps 102 > $out/${tag}_traffic_$g.log 2>&1
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"jacobi_pass|jacobi_resident" -s 3200 -c 3 -o $out/${tag}_jacobi_256 -f \
+# the first pass of step 101 (one jacobi_pass_kernel launch per step) and three later passes of a developed step
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:jacobi_pass_kernel -s 100 -c 1 -o $out/${tag}_jacobi_pass0_256 -f \
     python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_j.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:jacobi_resident_kernel -s 1500 -c 3 -o $out/${tag}_jacobi_256 -f \
+    python tools/profile_step.py --grid 256 256 256 --steps 101 >> $out/${tag}_ncu_j.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"advect_kernel|divergence_quad|gradient_quad" -s 300 -c 3 -o $out/${tag}_adg_256 -f \
     python tools/profile_step.py --grid 256 256 256 --steps 101 > $out/${tag}_ncu_a.log 2>&1
 ls -la $out | tail -15
