@@ -26,7 +26,8 @@ namespace fxb {
 
 namespace {
 
-constexpr int kZ = 4;  // voxels a thread marches along z
+constexpr int kZ = 4;  // voxels a thread marches along z (measured on B200: 2 is 35 % slower at 512^3, 8 is 2 % faster there
+                       // and 14 % slower at 256^3)
 
 struct Pair4 {  // one RGBA16F texel widened to fp32 as two packed pairs
     float2 lo, hi;
