@@ -843,6 +843,17 @@ int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t
     return FXB_OK;
 }
 
+int fxb_jacobi_schedule(int32_t iters, int32_t fuse_t, int32_t tail_from, int32_t* npass, int32_t* s0, int32_t n) {
+    if (!npass || iters < 0 || fuse_t < 1 || fuse_t > 4 || tail_from < 0 || n < 0 || (n > 0 && !s0))
+        return fail(FXB_ERR_INVALID, "fxb_jacobi_schedule: bad argument");
+    fxb::FusedJacobi J;
+    J.T = fuse_t;
+    J.tail_from = tail_from > 0 ? tail_from : fxb::FusedJacobi::kMaxPasses + 1;
+    *npass = fxb::fused_jacobi_passes(J, iters);
+    for (int k = 0; k < n && k < *npass; ++k) s0[k] = fxb::fused_jacobi_s0(J, k);
+    return FXB_OK;
+}
+
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {
     if (!out6 || nx == 0 || ny == 0 || nz == 0) return fail(FXB_ERR_INVALID, "fxb_emitter_box: bad argument");
     int lo[3], hi[3];

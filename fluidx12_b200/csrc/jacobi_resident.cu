@@ -16,7 +16,12 @@
 //     shared memory for the rows above and below);  T = 2: three barriers per brick instead of twelve;
 //   * a warp whose quads are all frozen in a plane skips the plane's arithmetic (one vote).
 // Shared memory: 2 x 96 KB, one CTA of 512 threads per SM.  Clamp-to-edge by index (x, y) or by the centre value (z),
-// never by TMA fill, as in the marching kernel.
+// never by TMA fill, as in the marching kernel.  Launched with programmatic dependent launch: the next pass's CTAs are
+// resident and past their prologue when this pass drains.
+// Two shapes: RShape (a work item is a brick, T <= 2 sweeps per pass) and RShapeHalf4 (a work item is half a brick, FOUR
+// sweeps per pass: the tail schedule, see the struct).  Measured on B200 (tools/timing_probe.py, 256^3, pass 16, first
+// CTA): 0.65 us pass loads, 0.6 us item + TMA issue, 2.2 us until the window has landed, 1.1 + 0.7 us the two levels,
+// 0.9 us stores and counters = 6.2 us, against ~20 us for the marching chain.
 #include <cuda.h>
 
 #include <type_traits>

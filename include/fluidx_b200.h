@@ -148,6 +148,12 @@ int fxb_wait_stats(fxb_sim* sim, int slot, fxb_stats* out);
  * array it lands in} (entries for a missing neighbour are meaningless). */
 int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t depth, int64_t* out4);
 
+/* Diagnostic, needs no GPU: the pass schedule of the fused pressure solve for `iters` sweeps when a pass fuses `fuse_t`
+ * sweeps and, from pass `tail_from` on (0 = never), four (fxb_stats.tail_from).  *npass = passes of a frame;
+ * s0[k] (k < min(n, *npass)) = sweeps completed before pass k.  Replaces nothing in the reference: its loop runs the 64
+ * sweeps one by one (CSPoisson.hlsli:8-26). */
+int fxb_jacobi_schedule(int32_t iters, int32_t fuse_t, int32_t tail_from, int32_t* npass, int32_t* s0, int32_t n);
+
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);

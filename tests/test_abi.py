@@ -212,3 +212,28 @@ def test_config_validation_needs_no_device(fx):
         assert L.fxb_create(C.byref(cfg), C.byref(h)) == -1 and text in L.fxb_last_error(), key
         setattr(cfg, key, old)
     assert L.fxb_create(None, C.byref(h)) == -1 and L.fxb_create(C.byref(cfg), None) == -1
+
+
+def test_jacobi_schedule_covers_every_sweep_once():
+    """fxb_jacobi_schedule (no GPU): passes of fuse_t sweeps, then of four from pass tail_from on — consecutive passes
+    tile the sweeps without gap or overlap, the last one may be short, and the count matches tests/util.expected_passes."""
+    import ctypes as C
+    from types import SimpleNamespace
+
+    import fluidx12_b200 as fx
+    from tests.util import expected_passes
+    L = fx.lib()
+    for iters in (0, 1, 7, 40, 63, 64, 128):
+        for t in (1, 2, 3, 4):
+            for k0 in (0, 1, 4, 5, 16, 40):
+                npass, s0 = C.c_int32(), (C.c_int32 * 160)()
+                assert L.fxb_jacobi_schedule(iters, t, k0, C.byref(npass), s0, 160) == 0
+                n = npass.value
+                assert n == expected_passes(iters, SimpleNamespace(fuse_t=t, tail_from=k0)), (iters, t, k0, n)
+                starts = list(s0[:n]) + [iters]
+                for k in range(n):
+                    width = 4 if (k0 and k >= k0) else t
+                    assert starts[k] == (0 if k == 0 else starts[k - 1] + (4 if (k0 and k - 1 >= k0) else t))
+                    assert 0 < starts[k + 1] - starts[k] <= width or k == n - 1
+                assert n == 0 or starts[n - 1] < iters
+    assert L.fxb_jacobi_schedule(64, 5, 0, C.byref(npass), s0, 160) != 0
