@@ -17,6 +17,11 @@ larger than L2).  N > 1 -> weak scaling at 134 M voxels per GPU, z-slab decompos
 the roofline come from phase marks INSIDE the timed steps (fxb_get_phase_times).  At N = 1 the line also carries "c3"
 (the 256^3 roofline-characterisation config), "c2" (128^3), "c150" (150^3) and the CPU baseline; at N > 1 (weak) it carries
 "c4_strong": config 4 on the same N ranks, whose state checksum must equal the N = 1 line's.  --grid overrides.
+
+"e2e" is the same K steps host-timed through the public calls (UpdateFrame with the 8-byte constant upload, Simulate,
+fxb_get_stats read-back every step) on the SAME frames as "value": a second simulator is spun up identically, because the
+flow keeps developing and later frames cost more (its final state checksum is compared: e2e.same_state_as_value).
+"roofline.traffic" is the ncu DRAM traffic per launch of the dominant phase's kernel(s) from profiles/traffic.json.
 """
 from __future__ import annotations
 
