@@ -17,7 +17,7 @@ FXB_OK, FXB_ERR_INVALID, FXB_ERR_CUDA, FXB_ERR_NCCL, FXB_ERR_SIZE, FXB_ERR_HALO_
 EXPORTS = (
     "fxb_config_default", "fxb_create", "fxb_destroy", "fxb_update_frame", "fxb_simulate", "fxb_sync",
     "fxb_dt_for_grid", "fxb_get_slab", "fxb_get_field", "fxb_set_field", "fxb_get_field_async", "fxb_get_stats",
-    "fxb_post_stats", "fxb_wait_stats", "fxb_p2p_plan", "fxb_jacobi_schedule", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_get_phase_times", "fxb_state_checksum", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
+    "fxb_post_stats", "fxb_wait_stats", "fxb_p2p_plan", "fxb_jacobi_schedule", "fxb_face_last_order", "fxb_emitter_box", "fxb_get_freeze_histogram", "fxb_profile_step", "fxb_get_phase_times", "fxb_state_checksum", "fxb_nccl_unique_id", "fxb_last_error", "fxb_abi_version",
     "fxb_volume_write", "fxb_volume_read_header", "fxb_volume_read", "fxb_export_field",
     "fxb_light_map", "fxb_get_light_map", "fxb_cube_visibility_mask", "fxb_estimate_cube_lod", "fxb_ray_march_v", "fxb_ray_march", "fxb_get_cube_map",
 )
@@ -148,6 +148,7 @@ def lib() -> C.CDLL:
         L.fxb_post_stats.argtypes = [vp, C.c_int]
         L.fxb_wait_stats.argtypes = [vp, C.c_int, C.POINTER(FxbStats)]
         L.fxb_p2p_plan.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int64)]
+        L.fxb_face_last_order.argtypes = [C.c_int32] * 5 + [C.POINTER(C.c_int32), C.c_int32]
         L.fxb_jacobi_schedule.argtypes = [C.c_int32] * 3 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32]
         L.fxb_emitter_box.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32)]
         L.fxb_get_freeze_histogram.argtypes = [vp, vp, C.c_int]

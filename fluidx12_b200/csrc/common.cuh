@@ -112,13 +112,17 @@ __device__ __forceinline__ void peer_publish(const PeerView& pv, const unsigned 
 // of occupying every SM with spinning CTAs.  b: blockIdx.z; returns the chunk it works on (interior chunks first, then
 // the n_lo chunks at the lower face, then the n_hi at the upper face).  `chunk` planes per chunk, `reach` planes next
 // to a face that wait, n owned planes.
-__device__ __forceinline__ int face_last_chunk(const PeerView& pv, int b, int nchunks, int chunk, int reach, int n) {
-    int n_lo = pv.has_lo ? (reach + chunk - 1) / chunk : 0;
-    int n_hi = pv.has_hi ? nchunks - max(n - reach, 0) / chunk : 0;
-    n_lo = min(n_lo, nchunks);
-    n_hi = min(n_hi, nchunks - n_lo);
+__host__ __device__ __forceinline__ int face_last_chunk_of(int has_lo, int has_hi, int b, int nchunks, int chunk,
+                                                           int reach, int n) {
+    int n_lo = has_lo ? (reach + chunk - 1) / chunk : 0;
+    int n_hi = has_hi ? nchunks - (n - reach > 0 ? n - reach : 0) / chunk : 0;
+    if (n_lo > nchunks) n_lo = nchunks;
+    if (n_hi > nchunks - n_lo) n_hi = nchunks - n_lo;
     const int n_int = nchunks - n_lo - n_hi;
     return b < n_int ? b + n_lo : (b < n_int + n_lo ? b - n_int : b);
+}
+__device__ __forceinline__ int face_last_chunk(const PeerView& pv, int b, int nchunks, int chunk, int reach, int n) {
+    return face_last_chunk_of(pv.has_lo, pv.has_hi, b, nchunks, chunk, reach, n);
 }
 
 // Phase marks: the device time since the previous mark is added to StepState::phase_ns[slot] (slot < 0: start of a

@@ -854,6 +854,13 @@ int fxb_jacobi_schedule(int32_t iters, int32_t fuse_t, int32_t tail_from, int32_
     return FXB_OK;
 }
 
+int fxb_face_last_order(int32_t n, int32_t chunk, int32_t reach, int32_t has_lo, int32_t has_hi, int32_t* out, int32_t nchunks) {
+    if (!out || n < 1 || chunk < 1 || reach < 0 || nchunks != (n + chunk - 1) / chunk)
+        return fail(FXB_ERR_INVALID, "fxb_face_last_order: bad argument");
+    for (int b = 0; b < nchunks; ++b) out[b] = fxb::face_last_chunk_of(has_lo, has_hi, b, nchunks, chunk, reach, n);
+    return FXB_OK;
+}
+
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6) {
     if (!out6 || nx == 0 || ny == 0 || nz == 0) return fail(FXB_ERR_INVALID, "fxb_emitter_box: bad argument");
     int lo[3], hi[3];

@@ -154,6 +154,11 @@ int fxb_p2p_plan(int32_t nz, int32_t nranks, int32_t rank, int32_t halo, int32_t
  * sweeps one by one (CSPoisson.hlsli:8-26). */
 int fxb_jacobi_schedule(int32_t iters, int32_t fuse_t, int32_t tail_from, int32_t* npass, int32_t* s0, int32_t n);
 
+/* Diagnostic, needs no GPU: the order in which a fused-halo kernel hands out its z chunks (`chunk` planes each over `n`
+ * owned planes; the chunks within `reach` planes of an interior face wait for the neighbour rank and come last).
+ * out[b] (b < nchunks = ceil(n / chunk)) = the chunk CTA row b works on. */
+int fxb_face_last_order(int32_t n, int32_t chunk, int32_t reach, int32_t has_lo, int32_t has_hi, int32_t* out, int32_t nchunks);
+
 /* Diagnostic, needs no GPU: the voxel box {x0,y0,z0,x1,y1,z1} (half-open) outside of which the advection kernel
  * skips the emitter (CSAdvect.hlsl:57-68) because the Gaussian basis there is below exp(-4). */
 int fxb_emitter_box(uint32_t nx, uint32_t ny, uint32_t nz, int32_t* out6);

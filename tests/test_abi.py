@@ -237,3 +237,24 @@ def test_jacobi_schedule_covers_every_sweep_once():
                     assert 0 < starts[k + 1] - starts[k] <= width or k == n - 1
                 assert n == 0 or starts[n - 1] < iters
     assert L.fxb_jacobi_schedule(64, 5, 0, C.byref(npass), s0, 160) != 0
+
+
+def test_face_chunks_come_last_and_every_chunk_exactly_once():
+    """fxb_face_last_order (no GPU; the function the fused-halo kernels call): a permutation of the chunks, interior
+    chunks first in ascending order, then the chunks within reach of the lower face, then those of the upper face."""
+    import ctypes as C
+
+    import fluidx12_b200 as fx
+    L = fx.lib()
+    for n, chunk, reach in ((128, 4, 9), (128, 8, 2), (128, 8, 4), (128, 1, 9), (20, 4, 9), (7, 8, 9), (48, 4, 9), (21, 4, 3)):
+        nchunks = -(-n // chunk)
+        for lo, hi in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            out = (C.c_int32 * nchunks)()
+            assert L.fxb_face_last_order(n, chunk, reach, lo, hi, out, nchunks) == 0
+            order = list(out)
+            assert sorted(order) == list(range(nchunks)), (n, chunk, reach, lo, hi, order)
+            near = [(lo and c * chunk < reach) or (hi and min((c + 1) * chunk, n) > n - reach) for c in order]
+            assert near == sorted(near), (n, chunk, reach, lo, hi, order)          # every waiting chunk after every free one
+            free = [c for c, w in zip(order, near) if not w]
+            assert free == sorted(free)
+    assert L.fxb_face_last_order(128, 4, 9, 1, 1, out, 3) != 0
